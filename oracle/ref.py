@@ -1,0 +1,144 @@
+"""ctypes front-end of oracle/liborb_oracle.so (built by oracle/Makefile).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("orb_ref.cpp", "match_ref.cpp", "occ_ref.cpp", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _SO
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        L.orb_ref_create.restype = C.c_void_p
+        L.orb_ref_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.orb_ref_destroy.argtypes = [C.c_void_p]
+        L.orb_ref_extract.restype = C.c_int
+        L.orb_ref_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_void_p]
+        L.orb_ref_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orb_ref_level_dims.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orb_ref_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orb_ref_resize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.orb_ref_blur.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orb_ref_fast.restype = C.c_int
+        L.orb_ref_fast.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orb_ref_fast_atan2.restype = C.c_float
+        L.orb_ref_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orb_ref_descriptor.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orb_ref_distribute.restype = C.c_int
+        L.orb_ref_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefExtractor:
+    """C++ oracle of ORB_SLAM2::ORBextractor (oracle/orb_ref.cpp)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+        self.L = lib()
+        self.nlevels = nlevels
+        self.nfeatures = nfeatures
+        self.h = C.c_void_p(self.L.orb_ref_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST))
+        sf, inv, s2, is2 = (np.zeros(nlevels, np.float32) for _ in range(4))
+        nf = np.zeros(nlevels, np.int32)
+        um = np.zeros(16, np.int32)
+        self.L.orb_ref_tables(self.h, _p(sf), _p(inv), _p(s2), _p(is2), _p(nf), _p(um))
+        self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2 = sf, inv, s2, is2
+        self.mnFeaturesPerLevel, self.umax = nf, um
+        self.candidates_per_level = np.zeros(nlevels, np.int32)
+
+    def __del__(self):
+        try:
+            self.L.orb_ref_destroy(self.h)
+        except Exception:
+            pass
+
+    def __call__(self, image: np.ndarray):
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2
+        cap = self.nfeatures + 3 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orb_ref_extract(self.h, _p(image), image.shape[0], image.shape[1], image.strides[0], _p(kps),
+                                   _p(desc), cap, _p(self.candidates_per_level))
+        if n < 0:
+            raise RuntimeError("orb_ref_extract failed: %d" % n)
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, l: int, bordered: bool = False) -> np.ndarray:
+        w, h = C.c_int(), C.c_int()
+        self.L.orb_ref_level_dims(self.h, l, C.byref(w), C.byref(h))
+        shp = (h.value + 38, w.value + 38) if bordered else (h.value, w.value)
+        out = np.zeros(shp, np.uint8)
+        self.L.orb_ref_get_level(self.h, l, int(bordered), _p(out))
+        return out
+
+
+def resize(src: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    src = np.ascontiguousarray(src)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orb_ref_resize(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def blur(src: np.ndarray) -> np.ndarray:
+    src = np.ascontiguousarray(src)
+    dst = np.zeros_like(src)
+    lib().orb_ref_blur(_p(src), src.shape[1], src.shape[0], _p(dst))
+    return dst
+
+
+def fast(roi: np.ndarray, t: int) -> np.ndarray:
+    roi = np.ascontiguousarray(roi)
+    cap = roi.size
+    out = np.zeros((cap, 3), np.int32)
+    n = lib().orb_ref_fast(_p(roi), roi.shape[1], roi.shape[0], roi.strides[0], t, _p(out), cap)
+    return out[:n]
+
+
+def fast_atan2(y: float, x: float) -> float:
+    return float(lib().orb_ref_fast_atan2(y, x))
+
+
+def descriptor(img: np.ndarray, x: float, y: float, angle: float) -> np.ndarray:
+    img = np.ascontiguousarray(img)
+    d = np.zeros(32, np.uint8)
+    lib().orb_ref_descriptor(_p(img), img.strides[0], x, y, angle, _p(d))
+    return d
+
+
+def distribute(kps: np.ndarray, minX, maxX, minY, maxY, N) -> np.ndarray:
+    kps = np.ascontiguousarray(kps)
+    out = np.zeros(max(len(kps), 1), KP_DTYPE)
+    n = lib().orb_ref_distribute(_p(kps), len(kps), minX, maxX, minY, maxY, N, _p(out), len(out))
+    if n < 0:
+        raise RuntimeError("distribute failed %d" % n)
+    return out[:n]
