@@ -1,0 +1,265 @@
+/* b200orb.h -- C-ABI of libb200orb.so: the B200 (sm_100a) implementation of the ORB-SLAM2 hot path.
+ *
+ * The reference (Ewenwan/ORB_SLAM2_SSD_Semantic) has no FFI layer; its boundary is the public surface of
+ * three C++ classes.  Every entry point below names the reference member it replaces
+ * (file:line relative to the reference root).  INTEGRATION.md shows the header-only C++ shim classes
+ * (orb_slam2_ssd_semantic_b200/csrc/shim/) that keep those class surfaces source-compatible on top of this ABI.
+ *
+ * Conventions: plain C, caller-owned buffers, int status (0 = OK, <0 = B200ORB_E*), never aborts/exits,
+ * no exceptions cross the boundary.  Opaque handles own device memory and one CUDA stream each; calls on
+ * DISTINCT handles are re-entrant (the reference runs L/R extractors on two threads, src/Frame.cc:121-124,
+ * and matchers on three).  Pointers named d_* are CUDA device pointers, everything else is host memory.
+ */
+#ifndef B200ORB_H_
+#define B200ORB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ORB_OK 0
+#define B200ORB_EINVAL (-1)     /* bad argument */
+#define B200ORB_ECAP (-2)       /* caller buffer too small */
+#define B200ORB_ECUDA (-3)      /* CUDA runtime error (see b200orb_last_error) */
+#define B200ORB_ENOGPU (-4)     /* no usable CUDA device: there is NO CPU fallback */
+#define B200ORB_EGEOM (-5)      /* image geometry the reference itself cannot process */
+
+const char* b200orb_last_error(void);   /* thread-local message of the last failing call */
+int b200orb_device_count(void);         /* number of CUDA devices visible (0 if none / no driver) */
+const char* b200orb_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB extractor  --  ORB_SLAM2::ORBextractor (include/ORBextractor.h:41-118, src/ORBextractor.cc)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbx orbx_t;
+
+typedef struct {            /* ctor arguments, src/ORBextractor.cc:399-400 */
+  int nfeatures;
+  float scale_factor;
+  int nlevels;
+  int ini_th_fast;
+  int min_th_fast;
+} OrbxParams;
+
+typedef struct {            /* cv::KeyPoint, 28 bytes, what operator() appends to _keypoints */
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} OrbxKeyPoint;
+
+/* ORBextractor::ORBextractor (src/ORBextractor.cc:399-466).  device = CUDA ordinal. */
+int orbx_create(const OrbxParams* p, int device, orbx_t** out);
+void orbx_destroy(orbx_t* h);
+
+/* Upper bound on keypoints one frame can return: nfeatures + 3*nlevels. */
+int orbx_max_keypoints(const orbx_t* h);
+
+/* ORBextractor::operator() (src/ORBextractor.cc:1052-1114) on one HOST image (CV_8UC1, row stride in bytes).
+ * kps[cap], desc[cap*32] are host buffers; *n_out keypoints are written level-major exactly as the
+ * reference orders them.  rows==0||cols==0 -> *n_out = 0, OK (reference: silent return, :1055). */
+int orbx_extract(orbx_t* h, const uint8_t* gray, int rows, int cols, size_t stride,
+                 OrbxKeyPoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* Batched many-frame mode (north_star): nframes images of identical geometry, frame f at
+ * gray + f*frame_stride.  Outputs: kps[f*cap ..], desc[(f*cap)*32 ..], n_out[f].  Host buffers. */
+int orbx_extract_batch(orbx_t* h, const uint8_t* gray, int nframes, int rows, int cols, size_t stride,
+                       size_t frame_stride, OrbxKeyPoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* Same, with the images already resident in HBM (d_gray) and results LEFT in HBM: after the call
+ * orbx_device_results() returns device pointers valid until the next extract on this handle.
+ * Asynchronous on the handle's stream; orbx_sync() waits. */
+int orbx_extract_batch_device(orbx_t* h, const uint8_t* d_gray, int nframes, int rows, int cols,
+                              size_t stride, size_t frame_stride);
+int orbx_device_results(orbx_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d_desc,
+                        const int32_t** d_counts, int* cap);
+int orbx_sync(orbx_t* h);
+void* orbx_stream(orbx_t* h);   /* cudaStream_t the handle launches on */
+
+/* Backs the public member mvImagePyramid (include/ORBextractor.h:80): level image of frame `frame` of the
+ * last extract.  bordered=0: rows x cols level (the ROI the reference stores); bordered=1: the
+ * (rows+38)x(cols+38) parent buffer with the BORDER_REFLECT_101 frame (src/ORBextractor.cc:1125-1142). */
+int orbx_level_dims(const orbx_t* h, int level, int* rows, int* cols);
+int orbx_get_level(orbx_t* h, int frame, int level, int bordered, uint8_t* dst, size_t dst_stride);
+
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (include/ORBextractor.h:63-77) + mnFeaturesPerLevel; each array has nlevels entries (NULL = skip). */
+int orbx_scale_tables(const orbx_t* h, float* sf, float* inv_sf, float* sigma2, float* inv_sigma2,
+                      int* features_per_level);
+
+/* Diagnostics for parity tests: FAST candidates per level of frame `frame` of the last extract. */
+int orbx_candidates_per_level(orbx_t* h, int frame, int* counts /*nlevels*/);
+/* Number of CUDA kernels launched by this handle since creation (bench.py's gpu_launches). */
+long long orbx_launch_count(const orbx_t* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * ORB matcher  --  ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-118, src/ORBmatcher.cc)
+ * ------------------------------------------------------------------------------------------------ */
+#define ORBM_TH_HIGH 100      /* src/ORBmatcher.cc:39 */
+#define ORBM_TH_LOW 50        /* :40 */
+#define ORBM_HISTO_LENGTH 30  /* :41 */
+#define ORBM_GRID_COLS 64     /* include/Frame.h:26 */
+#define ORBM_GRID_ROWS 48     /* include/Frame.h:25 */
+
+/* ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1968-1984): Hamming distance of two 256-bit rows. */
+int orbm_hamming(const uint8_t a[32], const uint8_t b[32]);
+
+typedef struct orbm orbm_t;   /* workspace + stream; the matcher itself is stateless like the reference's */
+int orbm_create(int device, orbm_t** out);
+void orbm_destroy(orbm_t* h);
+long long orbm_launch_count(const orbm_t* h);
+
+/* Flat view of the "current" Frame the searches read (src/Frame.cc / include/Frame.h). */
+typedef struct {
+  int n;                      /* Frame::N */
+  const float* x;             /* mvKeysUn[i].pt.x */
+  const float* y;             /* mvKeysUn[i].pt.y */
+  const int32_t* octave;      /* mvKeysUn[i].octave */
+  const float* angle;         /* mvKeysUn[i].angle */
+  const float* uright;        /* mvuRight[i] (<=0: none) */
+  const uint8_t* desc;        /* mDescriptors, n x 32 */
+  const int32_t* mp_obs;      /* per keypoint: -1 if mvpMapPoints[i]==NULL else that MapPoint's Observations();
+                                 NULL = all -1 (what Tracking does before the call, src/Tracking.cc:1337) */
+  float Tcw[16];              /* mTcw row-major 4x4 */
+  float fx, fy, cx, cy, bf, b;        /* mbf, mb */
+  float min_x, max_x, min_y, max_y;   /* mnMinX.. (static image bounds) */
+  const float* scale_factors; /* mvScaleFactors, nlevels entries */
+  int nlevels;
+} OrbmFrame;
+
+/* "Last frame" side of SearchByProjection(Frame&, const Frame&, th, bMono). */
+typedef struct {
+  int n;                      /* LastFrame.N */
+  const float* xw;            /* n x 3: pMP->GetWorldPos() of LastFrame.mvpMapPoints[i] (ignored where !valid) */
+  const uint8_t* valid;       /* 1 iff mvpMapPoints[i] != NULL && !mvbOutlier[i] */
+  const int32_t* octave;      /* LastFrame.mvKeys[i].octave */
+  const float* angle;         /* LastFrame.mvKeysUn[i].angle */
+  const uint8_t* mp_desc;     /* n x 32: pMP->GetDescriptor() */
+  const int32_t* mp_obs;      /* pMP->Observations() (decides whether a claimed keypoint blocks later queries,
+                                 src/ORBmatcher.cc:1656-1658); NULL = all 0 */
+  float Tcw[16];              /* LastFrame.mTcw */
+} OrbmLast;
+
+/* ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono)
+ * (src/ORBmatcher.cc:1578-1724).  cur2last[cur.n]: index i of the LastFrame keypoint whose MapPoint ends up
+ * in CurrentFrame.mvpMapPoints[j], or -1 (NULL) -- i.e. exactly the pointer state the reference leaves
+ * (pre-existing entries given through cur->mp_obs are reported as -2 when they survive untouched).
+ * *nmatches = the function's return value (may double-count).  Host buffers. */
+int orbm_search_by_projection_last(orbm_t* h, const OrbmFrame* cur, const OrbmLast* last, float th, int mono,
+                                   float nnratio, int check_ori, int32_t* cur2last, int* nmatches);
+
+/* Local-map search: ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*>&, th)
+ * (src/ORBmatcher.cc:63-156); the per-MapPoint fields are those Frame::isInFrustum fills (src/Frame.cc:387-451). */
+typedef struct {
+  int n;
+  const uint8_t* track_in_view;   /* mbTrackInView && !isBad() */
+  const float* proj_x;            /* mTrackProjX */
+  const float* proj_y;            /* mTrackProjY */
+  const float* proj_xr;           /* mTrackProjXR */
+  const int32_t* scale_level;     /* mnTrackScaleLevel */
+  const float* view_cos;          /* mTrackViewCos */
+  const uint8_t* mp_desc;         /* n x 32 */
+  const int32_t* mp_obs;          /* Observations(); NULL = all 1 */
+} OrbmTrackPoints;
+int orbm_search_by_projection_points(orbm_t* h, const OrbmFrame* f, const OrbmTrackPoints* pts, float th,
+                                     float nnratio, int32_t* f2pt, int* nmatches);
+
+/* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:217-363).
+ * The two DBoW2::FeatureVector maps are given flattened and sorted by node id:
+ * node_ids[k] (strictly ascending), indices of node k = idx[node_off[k] .. node_off[k+1]). */
+typedef struct {
+  int n;                       /* keypoints */
+  const uint8_t* desc;         /* n x 32 */
+  const float* angle;          /* KF: mvKeysUn[i].angle ; F: mvKeys[i].angle (src/ORBmatcher.cc:301,308) */
+  const uint8_t* valid;        /* KF side: MapPoint non-NULL && !isBad(); F side: NULL */
+  int n_nodes;
+  const uint32_t* node_ids;
+  const int32_t* node_off;     /* n_nodes+1 */
+  const uint32_t* idx;
+} OrbmBow;
+int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori,
+                       int32_t* f2kf /* f->n, -1 = none */, int* nmatches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stream pipeline (batched many-frame mode of north_star): per frame t of a batch, what
+ * Tracking::GrabImageRGBD -> Frame::Frame(RGB-D) -> TrackWithMotionModel's SearchByProjection do
+ * (src/Tracking.cc:331-375,1324-1352; src/Frame.cc:176-240): extract, ComputeStereoFromRGBD
+ * (src/Frame.cc:850-871), AssignFeaturesToGrid (:319-334), UnprojectStereo (:879-899) of frame t-1's
+ * keypoints into "map points", then SearchByProjection(frame t, frame t-1, th, mono=0).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbs orbs_t;
+typedef struct {
+  OrbxParams orb;
+  float fx, fy, cx, cy, bf;     /* Camera.* of the YAML (perfect/Examples/RGB-D/TUM3.yaml:8-25) */
+  float th;                     /* search window, 15 in src/Tracking.cc:1346 */
+  float nnratio;                /* 0.9 (src/Tracking.cc:1327) */
+  int check_ori;                /* 1 */
+  int max_frames;               /* batch capacity */
+} OrbsParams;
+int orbs_create(const OrbsParams* p, int device, orbs_t** out);
+void orbs_destroy(orbs_t* h);
+/* Host-buffer entry: gray[n][rows][cols] u8, depth[n][rows][cols] f32 metres, Tcw[n][16] f32 row-major.
+ * Outputs (host): kps[n][cap], desc[n][cap][32], nkp[n], cur2last[n][cap] (frame 0: all -1), nmatch[n]. */
+int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const float* Tcw, int nframes,
+                     int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp, int32_t* cur2last,
+                     int32_t* nmatch, int cap);
+/* Device-resident entry (inputs already in HBM, results left in HBM; asynchronous on orbs_stream). */
+int orbs_track_batch_device(orbs_t* h, const uint8_t* d_gray, const float* d_depth, const float* d_Tcw,
+                            int nframes, int rows, int cols);
+int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d_desc, const int32_t** d_nkp,
+                        const int32_t** d_cur2last, const int32_t** d_nmatch, int* cap);
+int orbs_sync(orbs_t* h);
+void* orbs_stream(orbs_t* h);
+long long orbs_launch_count(const orbs_t* h);
+orbx_t* orbs_extractor(orbs_t* h);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense mapping -- PointCloudMapping (include/pointcloudmapping.h:50-56) with the OctoMap occupancy
+ * semantics of perfect/src/MapDrawer.cc:51-56,610-675,946-1025.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ocm ocm_t;
+typedef struct {
+  double resolution;            /* octoMap.res, 0.05 (perfect/Examples/RGB-D/my_rgbd_ty_api_adj.yaml:82) */
+  double prob_hit, prob_miss;   /* 0.7 / 0.4   (perfect/src/MapDrawer.cc:55-56) */
+  double clamp_min, clamp_max;  /* 0.12 / 0.97 (perfect/src/MapDrawer.cc:53-54) */
+  float depth_min, depth_max;   /* 0.5 / 3.0   (perfect/src/MapDrawer.cc:655) */
+  float y_max;                  /* 3.0: keep |y| <= y_max (:660) */
+  float leaf;                   /* 0.01 VoxelGrid leaf (:669); <=0 disables the pre-filter */
+  int64_t map_capacity;         /* voxel hash capacity (slots); 0 = default */
+} OcmParams;
+void ocm_default_params(OcmParams* p);
+int ocm_create(const OcmParams* p, int device, ocm_t** out);
+void ocm_destroy(ocm_t* h);
+/* One keyframe: MapDrawer::GeneratePointCloud (:641-675) + InsertScan (:946-1025) with a supplied
+ * ground label per pixel (NULL = all non-ground, the reference's fallback when RANSAC finds no plane).
+ * depth f32 metres, rgb u8 BGR-interleaved as cv::Mat (kf->mImRGB), Tcw row-major (KeyFrame::GetPose()). */
+int ocm_insert_keyframe(ocm_t* h, const float* depth, const uint8_t* rgb, int rows, int cols,
+                        const float Tcw[16], float fx, float fy, float cx, float cy,
+                        const uint8_t* ground_label);
+int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
+                               const float Tcw[16], float fx, float fy, float cx, float cy,
+                               const uint8_t* d_ground_label);
+/* World-frame points of the LAST inserted keyframe after gating + leaf filter + transform (xyz f32 x n,
+ * unordered: compare as sets). */
+int ocm_last_points(ocm_t* h, float* xyz, uint8_t* rgb, int cap, int* n);
+/* Leaf export: keys (3 x u16 per leaf, octomap OcTreeKey), log-odds f32; unordered. */
+int64_t ocm_num_leaves(ocm_t* h);
+int ocm_export_leaves(ocm_t* h, uint16_t* keys, float* logodds, uint8_t* rgb, int64_t cap, int64_t* n);
+int ocm_query(ocm_t* h, const float xyz[3], float* logodds, int* found);
+/* Multi-GPU map merge: per-voxel clamp-add summaries f(x)=min(max(x+a,L),H) of everything
+ * inserted since the last reset; device buffers, n entries: key u64 (x | y<<16 | z<<32), a/L/H f32. */
+int64_t ocm_summary_count(ocm_t* h);
+int ocm_export_summaries_device(ocm_t* h, uint64_t* d_keys, float* d_a, float* d_lo, float* d_hi, int64_t cap,
+                                int64_t* n);
+/* Compose the summaries of a LATER shard onto this map (apply in keyframe order: shard 0, 1, ...). */
+int ocm_apply_summaries_device(ocm_t* h, const uint64_t* d_keys, const float* d_a, const float* d_lo,
+                               const float* d_hi, int64_t n);
+int ocm_sync(ocm_t* h);
+void* ocm_stream(ocm_t* h);
+long long ocm_launch_count(const ocm_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ORB_H_ */

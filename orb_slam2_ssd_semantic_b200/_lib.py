@@ -1,0 +1,73 @@
+"""ctypes binding of libb200orb.so (include/b200orb.h).  Fails loudly: no CPU fallback exists."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libb200orb.so")
+
+
+class B200OrbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libb200orb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class OrbxParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+
+
+_lib = None
+
+# every symbol include/b200orb.h declares that is implemented so far (tests check the .so exports them)
+EXPORTS = [
+    "b200orb_last_error", "b200orb_device_count", "b200orb_version",
+    "orbx_create", "orbx_destroy", "orbx_max_keypoints", "orbx_extract", "orbx_extract_batch",
+    "orbx_extract_batch_device", "orbx_device_results", "orbx_sync", "orbx_stream", "orbx_level_dims",
+    "orbx_get_level", "orbx_scale_tables", "orbx_candidates_per_level", "orbx_launch_count",
+]
+
+
+def library_path() -> str:
+    return _SO
+
+
+def lib() -> C.CDLL:
+    """Load libb200orb.so (built in-tree by __graft_entry__.build() / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise B200OrbError(-100, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                 "(there is no CPU fallback)" % _SO)
+    L = C.CDLL(_SO)
+    vp, i, sz = C.c_void_p, C.c_int, C.c_size_t
+    L.b200orb_last_error.restype = C.c_char_p
+    L.b200orb_version.restype = C.c_char_p
+    L.b200orb_device_count.restype = i
+    L.orbx_create.argtypes = [C.POINTER(OrbxParams), i, C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_destroy.restype = None
+    L.orbx_max_keypoints.argtypes = [vp]
+    L.orbx_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, vp]
+    L.orbx_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, vp, vp, i, vp]
+    L.orbx_extract_batch_device.argtypes = [vp, vp, i, i, i, sz, sz]
+    L.orbx_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i)]
+    L.orbx_sync.argtypes = [vp]
+    L.orbx_stream.argtypes = [vp]
+    L.orbx_stream.restype = vp
+    L.orbx_level_dims.argtypes = [vp, i, C.POINTER(i), C.POINTER(i)]
+    L.orbx_get_level.argtypes = [vp, i, i, i, vp, sz]
+    L.orbx_scale_tables.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.orbx_candidates_per_level.argtypes = [vp, i, vp]
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbx_launch_count.restype = C.c_longlong
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise B200OrbError(rc, lib().b200orb_last_error().decode("utf-8", "replace"))

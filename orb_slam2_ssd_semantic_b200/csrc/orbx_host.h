@@ -1,0 +1,51 @@
+// orbx_host.h -- definition of the extractor handle (shared by orbx.cu and the stream pipeline orbs.cu).
+#pragma once
+#include "orbx_kernels.cuh"
+
+struct orbx {
+  OrbxParams prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  // tables of the constructor (src/ORBextractor.cc:404-465)
+  float sf[b200::MAX_LEVELS], invsf[b200::MAX_LEVELS], sigma2[b200::MAX_LEVELS], invsigma2[b200::MAX_LEVELS];
+  int nfeat[b200::MAX_LEVELS];
+  b200::OrientTab otab{};
+  signed char* d_pattern = nullptr;
+  // geometry-dependent state
+  int rows = 0, cols = 0, maxF = 0, lastF = 0;
+  int lw[b200::MAX_LEVELS], lh[b200::MAX_LEVELS], lpitch[b200::MAX_LEVELS];
+  size_t loff[b200::MAX_LEVELS];
+  size_t frame_bytes = 0;
+  int xt_off[b200::MAX_LEVELS], yt_off[b200::MAX_LEVELS];
+  b200::LevelTab ltab{};
+  b200::PyrView rawv{}, blurv{};
+  int ncells = 0, slots_per_frame = 0, sel_per_frame = 0, cap = 0, qt_cap = 0;
+  size_t qt_smem = 0;
+  uint8_t *d_raw = nullptr, *d_blur = nullptr;
+  b200::CellDesc* d_cells = nullptr;
+  unsigned* d_cand = nullptr;
+  int* d_cellcnt = nullptr;
+  unsigned* d_qkp = nullptr;
+  int* d_qnode = nullptr;
+  unsigned* d_sel = nullptr;
+  int *d_selcnt = nullptr, *d_candcnt = nullptr;
+  OrbxKeyPoint* d_kps = nullptr;
+  uint8_t* d_desc = nullptr;
+  int* d_n = nullptr;
+  int2 *d_xt = nullptr, *d_yt = nullptr;
+  void* d_tmp = nullptr;
+  size_t tmp_bytes = 0;
+  void* h_stage = nullptr;
+  size_t stage_bytes = 0;
+  bool have_results = false;
+
+  orbx();
+  ~orbx();
+  int init(const OrbxParams& p, int dev);
+  void free_geometry();
+  int ensure_geometry(int r, int c, int F);
+  int run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F);
+  int ensure_stage(size_t bytes);
+  int ensure_tmp(size_t bytes);
+};

@@ -1,0 +1,652 @@
+// orbx_kernels.cuh -- sm_100a kernels of the ORB extractor (reference: src/ORBextractor.cc).
+//
+// Data layout in HBM (one batch of F frames, identical geometry):
+//   pyramid   level l : F planes of h_l rows x pitch_l bytes (pitch_l = w_l rounded up to 16), no border --
+//             the 19-px REFLECT_101 frame of ComputePyramid (:1125-1142) is never read by anything that
+//             feeds operator()'s outputs; orbx_get_level synthesises it on read-back.
+//             Level 0 aliases the caller's device buffer when the batch is already resident.
+//   blurred   same layout, GaussianBlur 7x7 sigma 2 of every level (:1094-1095)
+//   cand      per frame: one fixed segment per FAST cell (worst-case capacity ceil(iw/2)*ceil(ih/2): strict
+//             3x3 NMS forbids 8-adjacent survivors), packed u32 x:12 | y:12 | response:8, row-major in cell
+//   cellcnt   per frame, per cell survivor count
+//   sel       per (frame, level): quad-tree survivors in the reference's list order, same packing
+//   kps/desc  per frame: cap x OrbxKeyPoint (28 B) / cap x 32 B, level-major like operator() concatenates
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct PyrView {                 // one image pyramid (raw or blurred) of a batch
+  uint8_t* p[MAX_LEVELS];        // frame 0 of level l
+  size_t fstride[MAX_LEVELS];    // bytes between consecutive frames of level l
+  int pitch[MAX_LEVELS];
+  int w[MAX_LEVELS], h[MAX_LEVELS];
+};
+
+struct CellDesc {                // one FAST cell (src/ORBextractor.cc:798-838)
+  short level;
+  short x0, y0;                  // ROI origin in level coordinates (= iniX, iniY)
+  short rw, rh;                  // ROI size (maxX-iniX, maxY-iniY); detection range is the ROI minus 3 px
+  short pad;
+  int slot_off;                  // offset of this cell's segment inside a frame's cand[]
+};
+
+struct LevelTab {                // per-level constants of the extractor
+  int cell_begin[MAX_LEVELS + 1];   // cells of level l: [cell_begin[l], cell_begin[l+1])
+  int slot_begin[MAX_LEVELS + 1];   // cand slots of level l
+  int nfeat[MAX_LEVELS];            // mnFeaturesPerLevel
+  int sel_off[MAX_LEVELS + 1];      // offset of level l inside a frame's sel[] / capacity
+  int n_ini[MAX_LEVELS];            // DistributeOctTree nIni (:545)
+  int box_h[MAX_LEVELS];            // maxBorderY-minBorderY: height of the initial nodes (:558)
+  float hx[MAX_LEVELS];             // DistributeOctTree hX (:547)
+  float sf[MAX_LEVELS];             // mvScaleFactor
+  float kp_size[MAX_LEVELS];        // (float)(int)(PATCH_SIZE*mvScaleFactor[l]) (:846)
+  int nlevels;
+};
+
+__device__ __forceinline__ unsigned pack_kp(int x, int y, int resp) {
+  return (unsigned)x | ((unsigned)y << 12) | ((unsigned)resp << 24);
+}
+__device__ __forceinline__ int kp_x(unsigned v) { return v & 0xfff; }
+__device__ __forceinline__ int kp_y(unsigned v) { return (v >> 12) & 0xfff; }
+__device__ __forceinline__ int kp_r(unsigned v) { return v >> 24; }
+
+// ---------------------------------------------------------------------------------------------------
+// K1  pyramid level l from level l-1: cv::resize INTER_LINEAR 8UC1 (call site :1134).
+//     xt/yt: per destination index {source offset, a0 | a1<<16} with the 11-bit coefficients.
+//     One thread -> 4 horizontally adjacent destination pixels -> one 32-bit store.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src, int spitch, size_t sfs, int sw,
+                                                int sh, uint8_t* __restrict__ dst, int dpitch, size_t dfs,
+                                                int dw, int dh, const int2* __restrict__ xt,
+                                                const int2* __restrict__ yt) {
+  const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int dy = blockIdx.y * 8 + threadIdx.y;
+  if (dx0 >= dw || dy >= dh) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
+  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
+  const int2 ty = __ldg(&yt[dy]);
+  const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+  const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+  const uint8_t* r0 = s + (size_t)sy0 * spitch;
+  const uint8_t* r1 = s + (size_t)sy1 * spitch;
+  unsigned out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int dx = dx0 + i;
+    if (dx < dw) {
+      const int2 tx = __ldg(&xt[dx]);
+      const int x0 = tx.x, x1 = min(x0 + 1, sw - 1);
+      const int a0 = (short)(tx.y & 0xffff), a1 = (short)(tx.y >> 16);
+      const int h0 = r0[x0] * a0 + r0[x1] * a1;
+      const int h1 = r1[x0] * a0 + r1[x1] * a1;
+      const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      out |= (unsigned)(v & 0xff) << (8 * i);
+    }
+  }
+  *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2  per-cell FAST-9/16 + strict 3x3 NMS with the ini/min threshold fallback
+//     (cv::FAST TYPE_9_16 nonmax=true; call sites :818,:823; cell loop :798-838).
+//     One CTA per (cell, frame).  m(p) = max over 16 arcs of max(min d, min -d) is threshold-independent,
+//     so it is evaluated once per pixel; "corner at t" is m > t and the score is m-1.  Survivors are
+//     written row-major into the cell's fixed segment, so concatenating the segments cell-major reproduces
+//     vToDistributeKeys' order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int FAST_THREADS = 256;
+constexpr int FAST_MAX_ROI = 72;   // ROI side bound enforced at create (cell <= 60 px + 6, padded)
+
+__device__ __forceinline__ unsigned pk_d(int d) {   // lo s16 = d, hi s16 = -d
+  return ((unsigned)d & 0xffffu) | ((unsigned)(-d) << 16);
+}
+
+__device__ __forceinline__ int fast_m_exact(const uint8_t* c, int tp) {
+  const int cv = c[0];
+  unsigned v[16];
+  v[0] = pk_d(cv - c[3 * tp]);       v[1] = pk_d(cv - c[3 * tp + 1]);
+  v[2] = pk_d(cv - c[2 * tp + 2]);   v[3] = pk_d(cv - c[tp + 3]);
+  v[4] = pk_d(cv - c[3]);            v[5] = pk_d(cv - c[-tp + 3]);
+  v[6] = pk_d(cv - c[-2 * tp + 2]);  v[7] = pk_d(cv - c[-3 * tp + 1]);
+  v[8] = pk_d(cv - c[-3 * tp]);      v[9] = pk_d(cv - c[-3 * tp - 1]);
+  v[10] = pk_d(cv - c[-2 * tp - 2]); v[11] = pk_d(cv - c[-tp - 3]);
+  v[12] = pk_d(cv - c[-3]);          v[13] = pk_d(cv - c[tp - 3]);
+  v[14] = pk_d(cv - c[2 * tp - 2]);  v[15] = pk_d(cv - c[3 * tp - 1]);
+  unsigned a3[16], a9[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a3[i] = __vimin3_s16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a9[i] = __vimin3_s16x2(a3[i], a3[(i + 3) & 15], a3[(i + 6) & 15]);
+  unsigned m0 = __vimax3_s16x2(a9[0], a9[1], a9[2]);
+  unsigned m1 = __vimax3_s16x2(a9[3], a9[4], a9[5]);
+  unsigned m2 = __vimax3_s16x2(a9[6], a9[7], a9[8]);
+  unsigned m3 = __vimax3_s16x2(a9[9], a9[10], a9[11]);
+  unsigned m4 = __vimax3_s16x2(a9[12], a9[13], a9[14]);
+  m0 = __vimax3_s16x2(m0, m1, m2);
+  m3 = __vimax3_s16x2(m3, m4, a9[15]);
+  m0 = __vmaxs2(m0, m3);
+  const int lo = (short)(m0 & 0xffffu), hi = (short)(m0 >> 16);
+  return max(0, max(lo, hi));
+}
+
+__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
+                                                             int ncells, int slots_per_frame, int ini_th,
+                                                             int min_th, unsigned* __restrict__ cand,
+                                                             int* __restrict__ cellcnt) {
+  __shared__ __align__(16) uint8_t tile[FAST_MAX_ROI * FAST_MAX_ROI];
+  __shared__ uint8_t mm[FAST_MAX_ROI * FAST_MAX_ROI];
+  __shared__ int ws[33];
+  const CellDesc cd = cells[blockIdx.x];
+  const int f = blockIdx.y;
+  const int l = cd.level, rw = cd.rw, rh = cd.rh;
+  const int tp = (rw + 3) & ~3;
+  const uint8_t* img = pyr.p[l] + (size_t)f * pyr.fstride[l] + (size_t)cd.y0 * pyr.pitch[l] + cd.x0;
+  for (int i = threadIdx.x; i < rw * rh; i += FAST_THREADS) {
+    const int y = i / rw, x = i - y * rw;
+    tile[y * tp + x] = img[(size_t)y * pyr.pitch[l] + x];
+    mm[y * tp + x] = 0;
+  }
+  __syncthreads();
+  const int iw = rw - 6, ih = rh - 6, P = (iw > 0 && ih > 0) ? iw * ih : 0;
+  for (int i = threadIdx.x; i < P; i += FAST_THREADS) {
+    const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
+    const uint8_t* c = &tile[y * tp + x];
+    const int cv = c[0];
+    // necessary condition for a corner at min_th: every 9-arc contains one pixel of each opposite pair
+    const bool p0 = abs(cv - c[3 * tp]) > min_th || abs(cv - c[-3 * tp]) > min_th;
+    const bool p4 = abs(cv - c[3]) > min_th || abs(cv - c[-3]) > min_th;
+    int m = 0;
+    if (p0 && p4) m = fast_m_exact(c, tp);
+    if (m <= min_th) m = 0;   // can never be a corner nor outscore one
+    mm[y * tp + x] = (uint8_t)m;
+  }
+  __syncthreads();
+  // NMS + order-preserving compaction: thread k owns the k-th contiguous chunk of the row-major scan.
+  // :821 the min-threshold retry happens only when the ini-threshold pass returned NO keypoint AFTER
+  // non-max suppression (a plateau of equal scores suppresses itself entirely).
+  const int chunk = (P + FAST_THREADS - 1) / FAST_THREADS;
+  const int beg = min(P, (int)threadIdx.x * chunk), end = min(P, beg + chunk);
+  unsigned flags = 0;
+  int total = 0, pos = 0;
+  for (int pass = 0; pass < 2 && total == 0; ++pass) {
+    const int t = pass ? min_th : ini_th;
+    flags = 0;
+    for (int i = beg; i < end; ++i) {
+      const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
+      const uint8_t* q = &mm[y * tp + x];
+      const int m = q[0];
+      if (m > t) {
+        const int s = m - 1;
+#define SC(o) ((q[o] > t) ? (q[o] - 1) : 0)
+        if (s > SC(-1) && s > SC(1) && s > SC(-tp - 1) && s > SC(-tp) && s > SC(-tp + 1) && s > SC(tp - 1) &&
+            s > SC(tp) && s > SC(tp + 1))
+          flags |= 1u << (i - beg);
+#undef SC
+      }
+    }
+    pos = block_excl_scan(__popc(flags), ws, &total);
+  }
+  unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
+  for (int i = beg; i < end; ++i) {
+    if (flags & (1u << (i - beg))) {
+      const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
+      out[pos++] = pack_kp(cd.x0 + x, cd.y0 + y, mm[y * tp + x] - 1);
+    }
+  }
+  if (threadIdx.x == 0) cellcnt[(size_t)f * ncells + blockIdx.x] = total;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3  DistributeOctTree (src/ORBextractor.cc:540-765) + DivideNode (:478-534), one CTA per (level, frame).
+//     The std::list is held as an array in list order (front = index 0); one "round" splits a set of nodes
+//     in a given processing order and rebuilds the list exactly as the push_front/erase sequence would:
+//       [children of the LAST processed node (n4,n3,n2,n1) ... children of the FIRST processed node]
+//       ++ [untouched nodes in their old relative order].
+//     Sweep rounds (:608-667) process every node holding >1 keypoints in list order.  Largest-first rounds
+//     (:678-739) process them by (size desc, creation desc); nodes created in one round sit in the list in
+//     reverse creation order, so "later created first" == "smaller list index first" -- no addresses needed
+//     (the reference's heap-address tie-break is replaced by this documented surrogate).
+//     Keypoints keep their original (cell-major, row-major) index, so "first key with maximal response"
+//     (:752-759) is an atomicMax over (response << 24 | ~index).
+// ---------------------------------------------------------------------------------------------------
+constexpr int QT_THREADS = 512;
+
+struct QtScratchView {
+  unsigned* qkp;    // [F][slots_per_frame] gathered candidates (contiguous per level at slot_begin[l])
+  int* qnode;       // [F][slots_per_frame] list index of each candidate's node
+};
+
+struct QtSmem {   // carved from dynamic shared memory, cap entries each
+  short4* box[2];
+  int* cnt[2];
+  int* cc;        // [cap][4] child counts of nodes being split
+  int* cpos;      // [cap][4] new list index of each child
+  int* rk;        // processing rank or -1
+  int* npos;      // new list index of untouched nodes
+  int* byrank;    // node index by processing rank
+  int* pre;       // inclusive prefix of child counts by rank
+};
+
+__host__ __device__ inline size_t qt_smem_bytes(int cap) { return (size_t)cap * (2 * 8 + 2 * 4 + 16 + 16 + 4 * 4); }
+
+__device__ __forceinline__ int qt_quadrant(short4 b, unsigned kp) {
+  // DivideNode's assignment (:509-523); node boxes are relative to (minBorderX, minBorderY) = (16,16)
+  const int x = kp_x(kp) - FAST_BORDER, y = kp_y(kp) - FAST_BORDER;
+  const int mx = b.x + ((b.z - b.x + 1) >> 1);   // UL.x + ceil((UR.x-UL.x)/2)
+  const int my = b.y + ((b.w - b.y + 1) >> 1);
+  return (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
+}
+
+// in-place exclusive scan of a[0..n) (shared memory); returns the total. All threads must call.
+__device__ int qt_scan_array(int* a, int n, int* ws) {
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+  int s = 0;
+  for (int i = beg; i < end; ++i) s += a[i];
+  int total;
+  int run = block_excl_scan(s, ws, &total);
+  for (int i = beg; i < end; ++i) {
+    const int v = a[i];
+    a[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const CellDesc* __restrict__ cells,
+                                                         const unsigned* __restrict__ cand,
+                                                         const int* __restrict__ cellcnt, int ncells,
+                                                         int slots_per_frame, QtScratchView sc, int qt_cap,
+                                                         unsigned* __restrict__ sel, int* __restrict__ selcnt,
+                                                         int* __restrict__ candcnt, int sel_per_frame) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int ws[33];
+  __shared__ int s_coff[QT_THREADS];
+  __shared__ int s_expand, s_rstar;
+  const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+  const int nlev = lt.nlevels;
+  const int N = lt.nfeat[l];
+  QtSmem S;
+  {
+    unsigned char* p = smem_raw;
+    S.box[0] = (short4*)p; p += (size_t)qt_cap * 8;
+    S.box[1] = (short4*)p; p += (size_t)qt_cap * 8;
+    S.cnt[0] = (int*)p; p += (size_t)qt_cap * 4;
+    S.cnt[1] = (int*)p; p += (size_t)qt_cap * 4;
+    S.cc = (int*)p; p += (size_t)qt_cap * 16;
+    S.cpos = (int*)p; p += (size_t)qt_cap * 16;
+    S.rk = (int*)p; p += (size_t)qt_cap * 4;
+    S.npos = (int*)p; p += (size_t)qt_cap * 4;
+    S.byrank = (int*)p; p += (size_t)qt_cap * 4;
+    S.pre = (int*)p;
+  }
+  unsigned* qkp = sc.qkp + (size_t)f * slots_per_frame + lt.slot_begin[l];
+  int* qnode = sc.qnode + (size_t)f * slots_per_frame + lt.slot_begin[l];
+  const unsigned* fcand = cand + (size_t)f * slots_per_frame;
+  const int* fcnt = cellcnt + (size_t)f * ncells;
+
+  // ---- gather this level's per-cell segments into one contiguous, order-preserving list -----------
+  const int cb = lt.cell_begin[l], nc = lt.cell_begin[l + 1] - cb;
+  int K = 0;
+  for (int base = 0; base < nc; base += nthr) {
+    const int c = base + tid;
+    const int cn = (c < nc) ? fcnt[cb + c] : 0;
+    int tot;
+    const int off = block_excl_scan(cn, ws, &tot);
+    s_coff[tid] = K + off;
+    __syncthreads();
+    const int nw = nthr >> 5, w = tid >> 5, lane = tid & 31;
+    const int m = min(nthr, nc - base);
+    for (int ci = w; ci < m; ci += nw) {
+      const int n_c = fcnt[cb + base + ci];
+      const unsigned* srcp = fcand + cells[cb + base + ci].slot_off;
+      unsigned* dstp = qkp + s_coff[ci];
+      for (int i = lane; i < n_c; i += 32) dstp[i] = srcp[i];
+    }
+    K += tot;
+    __syncthreads();
+  }
+  if (tid == 0) candcnt[(size_t)f * nlev + l] = K;
+  if (K == 0) {   // DistributeOctTree on an empty input returns an empty list
+    if (tid == 0) selcnt[(size_t)f * nlev + l] = 0;
+    return;
+  }
+
+  // ---- initial nodes (:553-587) ---------------------------------------------------------------------
+  const int nIni = lt.n_ini[l];
+  const float hX = lt.hx[l];
+  const int boxH = lt.box_h[l];
+  int cur = 0;
+  int* icnt = S.cc;   // nIni counters
+  for (int i = tid; i < nIni; i += nthr) icnt[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += nthr) {
+    const float xr = (float)(kp_x(qkp[k]) - FAST_BORDER);
+    int ii = (int)__fdiv_rn(xr, hX);
+    ii = min(ii, nIni - 1);
+    qnode[k] = ii;
+    atomicAdd(&icnt[ii], 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < nIni; i += nthr) S.npos[i] = (icnt[i] > 0) ? 1 : 0;
+  __syncthreads();
+  int n = qt_scan_array(S.npos, nIni, ws);
+  for (int i = tid; i < nIni; i += nthr) {
+    if (icnt[i] > 0) {
+      const int p = S.npos[i];
+      S.box[0][p] = make_short4((short)(int)__fmul_rn(hX, (float)i), 0, (short)(int)__fmul_rn(hX, (float)(i + 1)),
+                                (short)boxH);
+      S.cnt[0][p] = icnt[i];
+    }
+  }
+  __syncthreads();
+  for (int k = tid; k < K; k += nthr) qnode[k] = S.npos[qnode[k]];
+  __syncthreads();
+
+  // ---- rounds -------------------------------------------------------------------------------------------
+  bool largest = false, finish = false;
+  while (!finish) {
+    const int prevSize = n;
+    short4* box = S.box[cur];
+    int* cnt = S.cnt[cur];
+    short4* nbox = S.box[cur ^ 1];
+    int* ncnt = S.cnt[cur ^ 1];
+    // (1) processing rank of every node holding more than one keypoint
+    int m;   // number of candidates
+    if (!largest) {
+      for (int i = tid; i < n; i += nthr) S.rk[i] = (cnt[i] > 1) ? 1 : 0;
+      __syncthreads();
+      m = qt_scan_array(S.rk, n, ws);
+      for (int i = tid; i < n; i += nthr) {
+        if (cnt[i] > 1) S.byrank[S.rk[i]] = i;
+        else S.rk[i] = -1;
+      }
+    } else {
+      for (int i = tid; i < n; i += nthr) S.npos[i] = (cnt[i] > 1) ? 1 : 0;
+      __syncthreads();
+      m = qt_scan_array(S.npos, n, ws);   // only the total is needed
+      for (int i = tid; i < n; i += nthr) {
+        const int ci = cnt[i];
+        if (ci > 1) {
+          int r = 0;
+          for (int j = 0; j < n; ++j) {
+            const int cj = cnt[j];
+            r += (cj > ci) || (cj == ci && j < i);   // (size desc, list index asc); cj>ci>1 implies candidate
+          }
+          S.rk[i] = r;
+          S.byrank[r] = i;
+        } else {
+          S.rk[i] = -1;
+        }
+      }
+    }
+    for (int i = tid; i < n * 4; i += nthr) S.cc[i] = 0;
+    __syncthreads();
+    // (2) child populations of every candidate
+    for (int k = tid; k < K; k += nthr) {
+      const int p = qnode[k];
+      if (S.rk[p] >= 0) atomicAdd(&S.cc[p * 4 + qt_quadrant(box[p], qkp[k])], 1);
+    }
+    __syncthreads();
+    // (3) inclusive prefix over processing order of the number of non-empty children
+    for (int r = tid; r < m; r += nthr) {
+      const int* c = &S.cc[S.byrank[r] * 4];
+      S.pre[r] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+    }
+    if (tid == 0) { s_rstar = m - 1; s_expand = 0; }
+    __syncthreads();
+    {
+      const int tot = qt_scan_array(S.pre, m, ws);   // exclusive in place ...
+      (void)tot;
+      for (int r = tid; r < m; r += nthr) {          // ... turn into inclusive
+        const int* c = &S.cc[S.byrank[r] * 4];
+        S.pre[r] += (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+      }
+      __syncthreads();
+    }
+    if (largest) {   // :732 stop right after the split that reaches N
+      for (int r = tid; r < m; r += nthr) {
+        const bool now = (n + S.pre[r] - (r + 1)) >= N;
+        const bool before = (r > 0) && ((n + S.pre[r - 1] - r) >= N);
+        if (now && !before) s_rstar = r;
+      }
+      __syncthreads();
+    }
+    const int rstar = s_rstar;
+    const int TC = (m > 0) ? S.pre[rstar] : 0;   // children created this round
+    // (4) new list index of untouched nodes
+    for (int i = tid; i < n; i += nthr) {
+      const int r = S.rk[i];
+      S.npos[i] = (r < 0 || r > rstar) ? 1 : 0;
+    }
+    __syncthreads();
+    const int nUn = qt_scan_array(S.npos, n, ws);
+    for (int i = tid; i < n; i += nthr) {
+      const int r = S.rk[i];
+      if (r < 0 || r > rstar) {
+        const int p = TC + S.npos[i];
+        S.npos[i] = p;
+        nbox[p] = box[i];
+        ncnt[p] = cnt[i];
+        S.rk[i] = -1;
+      }
+    }
+    // (5) children: block of rank r starts at TC - pre[r]; inside the block n4,n3,n2,n1 (non-empty only)
+    int myexp = 0;
+    for (int r = tid; r <= rstar && r < m; r += nthr) {
+      const int i = S.byrank[r];
+      const short4 b = box[i];
+      const int* c = &S.cc[i * 4];
+      const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+      int p = TC - S.pre[r];
+#pragma unroll
+      for (int q = 3; q >= 0; --q) {
+        if (c[q] > 0) {
+          S.cpos[i * 4 + q] = p;
+          short4 nb;
+          nb.x = (q & 1) ? mx : b.x;
+          nb.z = (q & 1) ? b.z : mx;
+          nb.y = (q & 2) ? my : b.y;
+          nb.w = (q & 2) ? b.w : my;
+          nbox[p] = nb;
+          ncnt[p] = c[q];
+          myexp += (c[q] > 1);
+          ++p;
+        }
+      }
+    }
+    if (myexp) atomicAdd(&s_expand, myexp);
+    __syncthreads();
+    // (6) re-home the keypoints
+    for (int k = tid; k < K; k += nthr) {
+      const int p = qnode[k];
+      qnode[k] = (S.rk[p] >= 0) ? S.cpos[p * 4 + qt_quadrant(box[p], qkp[k])] : S.npos[p];
+    }
+    n = TC + nUn;
+    const int nToExpand = s_expand;
+    cur ^= 1;
+    // (7) termination logic (:671-675, :736-737)
+    if (n >= N || n == prevSize) finish = true;
+    else if (!largest && (n + nToExpand * 3) > N) largest = true;
+    __syncthreads();
+  }
+
+  // ---- best keypoint of every node (:746-762), output in list order --------------------------------------
+  unsigned* best = (unsigned*)S.cc;
+  for (int i = tid; i < n; i += nthr) best[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += nthr)
+    atomicMax(&best[qnode[k]], ((unsigned)kp_r(qkp[k]) << 24) | (0xffffffu - (unsigned)k));
+  __syncthreads();
+  unsigned* out = sel + (size_t)f * sel_per_frame + lt.sel_off[l];
+  for (int i = tid; i < n; i += nthr) out[i] = qkp[0xffffffu - (best[i] & 0xffffffu)];
+  if (tid == 0) selcnt[(size_t)f * nlev + l] = n;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4  GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (call site :1094-1095).
+//     Integer kernel [18,34,48,56,48,34,18]/256 in both passes, (v + 32768) >> 16.
+//     Tile 64x16 outputs per CTA; (64+6)x(16+6) source halo in shared memory; horizontal pass into u16.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BL_TW = 64, BL_TH = 16;
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) k_blur7(const uint8_t* __restrict__ src, int spitch, size_t sfs,
+                                               uint8_t* __restrict__ dst, int dpitch, size_t dfs, int w, int h) {
+  __shared__ uint8_t t[(BL_TH + 6)][BL_TW + 8];
+  __shared__ unsigned short hb[(BL_TH + 6)][BL_TW];
+  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
+  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
+  const int x0 = blockIdx.x * BL_TW, y0 = blockIdx.y * BL_TH;
+  for (int i = threadIdx.x; i < (BL_TH + 6) * (BL_TW + 6); i += 256) {
+    const int ty = i / (BL_TW + 6), tx = i - ty * (BL_TW + 6);
+    const int sy = reflect101(y0 + ty - 3, h), sx = reflect101(x0 + tx - 3, w);
+    t[ty][tx] = s[(size_t)sy * spitch + sx];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (BL_TH + 6) * BL_TW; i += 256) {
+    const int ty = i / BL_TW, tx = i - ty * BL_TW;
+    const uint8_t* r = &t[ty][tx];
+    hb[ty][tx] = (unsigned short)(18 * (r[0] + r[6]) + 34 * (r[1] + r[5]) + 48 * (r[2] + r[4]) + 56 * r[3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < BL_TH * BL_TW; i += 256) {
+    const int ty = i / BL_TW, tx = i - ty * BL_TW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x < w && y < h) {
+      const unsigned v = 18u * (hb[ty][tx] + hb[ty + 6][tx]) + 34u * (hb[ty + 1][tx] + hb[ty + 5][tx]) +
+                         48u * (hb[ty + 2][tx] + hb[ty + 4][tx]) + 56u * hb[ty + 3][tx];
+      d[(size_t)y * dpitch + x] = (uint8_t)((v + 32768u) >> 16);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5  orientation (IC_Angle :59-88 on the raw level) + steered BRIEF (computeOrbDescriptor :92-131 on the
+//     blurred level) + final KeyPoint assembly (:846-856, :1104-1110).  One warp per keypoint.
+// ---------------------------------------------------------------------------------------------------
+struct OrientTab {
+  int umax[HALF_PATCH_SIZE + 1];
+};
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {   // cv::fastAtan2, SURVEY App. A.5 (no FMA)
+  const float scale = (float)(180.0 / 3.14159265358979323846);
+  const float P1 = __fmul_rn(0.9997878412794807f, scale), P3 = __fmul_rn(-0.3258083974640975f, scale),
+              P5 = __fmul_rn(0.1555786518463281f, scale), P7 = __fmul_rn(-0.04432655554792128f, scale);
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, 2.2204460492503131e-16f));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(P7, c2), P5), c2), P3), c2), P1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, 2.2204460492503131e-16f));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(P7, c2), P5), c2), P3), c2), P1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+constexpr int OD_WARPS = 8;
+
+__global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(LevelTab lt, OrientTab ot, PyrView raw, PyrView blr,
+                                                               const signed char* __restrict__ pattern,
+                                                               const unsigned* __restrict__ sel,
+                                                               const int* __restrict__ selcnt, int sel_per_frame,
+                                                               OrbxKeyPoint* __restrict__ kps,
+                                                               uint8_t* __restrict__ desc, int* __restrict__ nout,
+                                                               int cap) {
+  __shared__ int spat[256];   // 512 points x (int8 x, int8 y) = 1024 B
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) spat[i] = reinterpret_cast<const int*>(pattern)[i];
+  __syncthreads();
+  const int f = blockIdx.y, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * OD_WARPS + (threadIdx.x >> 5);
+  const int* sc = selcnt + (size_t)f * lt.nlevels;
+  int l = -1, idx = 0, acc = 0;
+  for (int q = 0; q < lt.nlevels; ++q) {
+    const int c = sc[q];
+    if (l < 0 && j < acc + c) { l = q; idx = j - acc; }
+    acc += c;
+  }
+  if (j == 0 && lane == 0) nout[f] = min(acc, cap);
+  if (l < 0 || j >= cap) return;
+  const unsigned pk = sel[(size_t)f * sel_per_frame + lt.sel_off[l] + idx];
+  const int x = kp_x(pk), y = kp_y(pk);
+  // ---- IC_Angle: lane <-> column u = lane-15 (31 columns), loop rows ----
+  const uint8_t* rc = raw.p[l] + (size_t)f * raw.fstride[l] + (size_t)y * raw.pitch[l] + x;
+  const int u = lane - HALF_PATCH_SIZE, au = abs(u);
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const int rp = raw.pitch[l];
+    m10 = u * rc[u];
+#pragma unroll
+    for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+      if (au <= ot.umax[v]) {
+        const int vp = rc[u + v * rp], vm = rc[u - v * rp];
+        m10 += u * (vp + vm);
+        m01 += v * (vp - vm);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  const float angle = fast_atan2_deg((float)m01, (float)m10);
+  // ---- steered BRIEF ----
+  const float factorPI = (float)(3.14159265358979323846 / 180.f);
+  const float ang = __fmul_rn(angle, factorPI);
+  // cosf/sinf of the reference (glibc, correctly rounded in practice): evaluate in double, round once
+  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  const uint8_t* bc = blr.p[l] + (size_t)f * blr.fstride[l] + (size_t)y * blr.pitch[l] + x;
+  const int bp = blr.pitch[l];
+  unsigned word = 0;
+  unsigned* dout = reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + j) * 32);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int pr = k * 32 + lane;                 // test index; bit pr of the descriptor
+    const int w0 = spat[pr];                       // bytes: x0,y0,x1,y1
+    const float x0 = (float)(signed char)(w0 & 0xff), y0 = (float)(signed char)((w0 >> 8) & 0xff);
+    const float x1 = (float)(signed char)((w0 >> 16) & 0xff), y1 = (float)(signed char)((w0 >> 24) & 0xff);
+    const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+    const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+    const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+    const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+    const int t0 = bc[r0 * bp + c0], t1 = bc[r1 * bp + c1];
+    const unsigned bits = __ballot_sync(0xffffffffu, t0 < t1);
+    if (lane == k) word = bits;
+  }
+  if (lane < 8) dout[lane] = word;
+  if (lane == 0) {
+    OrbxKeyPoint kp;
+    const float s = lt.sf[l];
+    kp.x = (l != 0) ? __fmul_rn((float)x, s) : (float)x;
+    kp.y = (l != 0) ? __fmul_rn((float)y, s) : (float)y;
+    kp.size = lt.kp_size[l];
+    kp.angle = angle;
+    kp.response = (float)kp_r(pk);
+    kp.octave = l;
+    kp.class_id = -1;
+    kps[(size_t)f * cap + j] = kp;
+  }
+}
+
+// bordered level read-back for orbx_get_level (copyMakeBorder BORDER_REFLECT_101, :1136-1142)
+__global__ void k_border_copy(const uint8_t* __restrict__ src, int spitch, int w, int h, uint8_t* __restrict__ dst,
+                              int dpitch, int B) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= w + 2 * B || y >= h + 2 * B) return;
+  dst[(size_t)y * dpitch + x] = src[(size_t)reflect101(y - B, h) * spitch + reflect101(x - B, w)];
+}
+
+}  // namespace b200
