@@ -92,6 +92,12 @@ int orbx_scale_tables(const orbx_t* h, float* sf, float* inv_sf, float* sigma2, 
 int orbx_candidates_per_level(orbx_t* h, int frame, int* counts /*nlevels*/);
 /* Number of CUDA kernels launched by this handle since creation (bench.py's gpu_launches). */
 long long orbx_launch_count(const orbx_t* h);
+/* Per-stage device time via CUDA events on the handle's stream (bench.py's roofline leg).  Stages:
+ * 0 pyramid resize, 1 FAST cells, 2 quad-tree, 3 blur, 4 orientation+descriptor, 5 frame glue, 6 match
+ * (5,6 only when driven through orbs_*).  read() sums ms per stage over all runs since the last read. */
+#define B200ORB_NUM_STAGES 7
+int orbx_profile_enable(orbx_t* h, int on);
+int orbx_profile_read(orbx_t* h, float* ms, long long* frames, int* runs);
 
 /* ------------------------------------------------------------------------------------------------
  * ORB matcher  --  ORB_SLAM2::ORBmatcher (include/ORBmatcher.h:37-118, src/ORBmatcher.cc)

@@ -142,3 +142,55 @@ def distribute(kps: np.ndarray, minX, maxX, minY, maxY, N) -> np.ndarray:
     if n < 0:
         raise RuntimeError("distribute failed %d" % n)
     return out[:n]
+
+
+# ------------------------------------------------------------------------------------------------
+# matcher / frame-glue oracle (oracle/match_ref.cpp); struct mirrors come from the ABI header mirror
+# ------------------------------------------------------------------------------------------------
+def _mlib():
+    L = lib()
+    if not getattr(L, "_match_ready", False):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        L.match_ref_hamming.argtypes = [C.c_void_p, C.c_void_p]
+        L.match_ref_projection_last.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmLast), C.c_float, C.c_int,
+                                                C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.match_ref_projection_points.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmTrackPoints),
+                                                  C.c_float, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+        L.match_ref_bow.argtypes = [C.POINTER(_abi.OrbmBow), C.POINTER(_abi.OrbmBow), C.c_float, C.c_int, C.c_void_p,
+                                    C.POINTER(C.c_int)]
+        L.frame_ref_stereo_unproject.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                 C.c_void_p] + [C.c_float] * 5 + [C.c_void_p] * 4
+        L.frame_ref_stereo_unproject.restype = None
+        L._match_ready = True
+    return L
+
+
+def hamming(a, b) -> int:
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return int(_mlib().match_ref_hamming(_p(a), _p(b)))
+
+
+def search_by_projection_last(cur, last, th, mono=False, nnratio=0.9, check_ori=True):
+    """cur: _abi.FrameView, last: _abi.LastView -> (nmatches, cur2last)."""
+    out = np.full(cur.n, -1, np.int32)
+    nm = C.c_int(0)
+    cs, ls = cur.struct(), last.struct()
+    _mlib().match_ref_projection_last(C.byref(cs), C.byref(ls), float(th), int(mono), float(nnratio), int(check_ori),
+                                      _p(out), C.byref(nm))
+    return nm.value, out
+
+
+def stereo_unproject(kps, depth, Tcw, fx, fy, cx, cy, bf):
+    """ComputeStereoFromRGBD + UnprojectStereo for every keypoint -> uright, depth, xw, valid."""
+    n = len(kps)
+    kf = np.ascontiguousarray(kps).view(np.float32).reshape(n, 7) if n else np.zeros((0, 7), np.float32)
+    depth = np.ascontiguousarray(depth, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    ur = np.zeros(n, np.float32)
+    dp = np.zeros(n, np.float32)
+    xw = np.zeros((n, 3), np.float32)
+    va = np.zeros(n, np.uint8)
+    _mlib().frame_ref_stereo_unproject(_p(kf), 7, n, _p(depth), depth.shape[0], depth.shape[1], _p(T), fx, fy, cx, cy,
+                                       bf, _p(ur), _p(dp), _p(xw), _p(va))
+    return ur, dp, xw, va

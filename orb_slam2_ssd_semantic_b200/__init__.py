@@ -6,5 +6,7 @@ every operator raises if the CUDA library or a GPU is missing.
 """
 from ._lib import B200OrbError, lib, library_path  # noqa: F401
 from .extractor import KP_DTYPE, ORBextractor  # noqa: F401
+from .matcher import ORBmatcher, FrameView, LastView  # noqa: F401
+from .pipeline import StreamTracker  # noqa: F401
 
 __all__ = ["ORBextractor", "KP_DTYPE", "B200OrbError", "lib", "library_path"]

@@ -1,0 +1,111 @@
+"""ctypes mirrors of the structs declared in include/b200orb.h (no library loading here)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+vp = C.c_void_p
+
+
+class OrbxParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
+                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+
+
+class OrbmFrame(C.Structure):
+    _fields_ = [("n", C.c_int), ("x", vp), ("y", vp), ("octave", vp), ("angle", vp), ("uright", vp), ("desc", vp),
+                ("mp_obs", vp), ("Tcw", C.c_float * 16),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("bf", C.c_float),
+                ("b", C.c_float),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("scale_factors", vp), ("nlevels", C.c_int)]
+
+
+class OrbmLast(C.Structure):
+    _fields_ = [("n", C.c_int), ("xw", vp), ("valid", vp), ("octave", vp), ("angle", vp), ("mp_desc", vp),
+                ("mp_obs", vp), ("Tcw", C.c_float * 16)]
+
+
+class OrbmTrackPoints(C.Structure):
+    _fields_ = [("n", C.c_int), ("track_in_view", vp), ("proj_x", vp), ("proj_y", vp), ("proj_xr", vp),
+                ("scale_level", vp), ("view_cos", vp), ("mp_desc", vp), ("mp_obs", vp)]
+
+
+class OrbmBow(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", vp), ("angle", vp), ("valid", vp), ("n_nodes", C.c_int), ("node_ids", vp),
+                ("node_off", vp), ("idx", vp)]
+
+
+class OrbsParams(C.Structure):
+    _fields_ = [("orb", OrbxParams), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("bf", C.c_float), ("th", C.c_float), ("nnratio", C.c_float), ("check_ori", C.c_int),
+                ("max_frames", C.c_int)]
+
+
+class OcmParams(C.Structure):
+    _fields_ = [("resolution", C.c_double), ("prob_hit", C.c_double), ("prob_miss", C.c_double),
+                ("clamp_min", C.c_double), ("clamp_max", C.c_double), ("depth_min", C.c_float),
+                ("depth_max", C.c_float), ("y_max", C.c_float), ("leaf", C.c_float), ("map_capacity", C.c_int64)]
+
+
+def ptr(a):
+    """numpy array (or None) -> void*; keeps no reference: callers hold the arrays alive."""
+    if a is None:
+        return None
+    return a.ctypes.data_as(vp)
+
+
+class FrameView:
+    """Flat view of a Frame for the matcher (what the C++ shim extracts from ORB_SLAM2::Frame)."""
+
+    def __init__(self, x, y, octave, angle, uright, desc, Tcw, fx, fy, cx, cy, bf, min_x, max_x, min_y, max_y,
+                 scale_factors, mp_obs=None):
+        f32, i32 = np.float32, np.int32
+        self.x = np.ascontiguousarray(x, f32)
+        self.y = np.ascontiguousarray(y, f32)
+        self.octave = np.ascontiguousarray(octave, i32)
+        self.angle = np.ascontiguousarray(angle, f32)
+        self.uright = np.ascontiguousarray(uright, f32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.mp_obs = None if mp_obs is None else np.ascontiguousarray(mp_obs, i32)
+        self.Tcw = np.ascontiguousarray(Tcw, f32).reshape(16)
+        self.scale_factors = np.ascontiguousarray(scale_factors, f32)
+        self.cam = (float(fx), float(fy), float(cx), float(cy), float(bf))
+        self.bounds = (float(min_x), float(max_x), float(min_y), float(max_y))
+        self.n = len(self.x)
+
+    def struct(self) -> OrbmFrame:
+        s = OrbmFrame()
+        s.n = self.n
+        s.x, s.y, s.octave, s.angle = ptr(self.x), ptr(self.y), ptr(self.octave), ptr(self.angle)
+        s.uright, s.desc, s.mp_obs = ptr(self.uright), ptr(self.desc), ptr(self.mp_obs)
+        s.Tcw = (C.c_float * 16)(*self.Tcw.tolist())
+        s.fx, s.fy, s.cx, s.cy, s.bf = self.cam
+        s.b = np.float32(np.float32(self.cam[4]) / np.float32(self.cam[0]))   # mb = mbf/fx (src/Frame.cc:218)
+        s.min_x, s.max_x, s.min_y, s.max_y = self.bounds
+        s.scale_factors = ptr(self.scale_factors)
+        s.nlevels = len(self.scale_factors)
+        return s
+
+
+class LastView:
+    """LastFrame side of SearchByProjection(CurrentFrame, LastFrame)."""
+
+    def __init__(self, xw, valid, octave, angle, mp_desc, Tcw, mp_obs=None):
+        self.xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+        self.valid = np.ascontiguousarray(valid, np.uint8)
+        self.octave = np.ascontiguousarray(octave, np.int32)
+        self.angle = np.ascontiguousarray(angle, np.float32)
+        self.mp_desc = np.ascontiguousarray(mp_desc, np.uint8).reshape(-1, 32)
+        self.mp_obs = None if mp_obs is None else np.ascontiguousarray(mp_obs, np.int32)
+        self.Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        self.n = len(self.valid)
+
+    def struct(self) -> OrbmLast:
+        s = OrbmLast()
+        s.n = self.n
+        s.xw, s.valid, s.octave, s.angle = ptr(self.xw), ptr(self.valid), ptr(self.octave), ptr(self.angle)
+        s.mp_desc, s.mp_obs = ptr(self.mp_desc), ptr(self.mp_obs)
+        s.Tcw = (C.c_float * 16)(*self.Tcw.tolist())
+        return s

@@ -14,9 +14,7 @@ class B200OrbError(RuntimeError):
         self.code = code
 
 
-class OrbxParams(C.Structure):
-    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int),
-                ("ini_th_fast", C.c_int), ("min_th_fast", C.c_int)]
+from ._abi import OrbmFrame, OrbmLast, OrbsParams, OrbxParams  # noqa: E402,F401
 
 
 _lib = None
@@ -27,6 +25,10 @@ EXPORTS = [
     "orbx_create", "orbx_destroy", "orbx_max_keypoints", "orbx_extract", "orbx_extract_batch",
     "orbx_extract_batch_device", "orbx_device_results", "orbx_sync", "orbx_stream", "orbx_level_dims",
     "orbx_get_level", "orbx_scale_tables", "orbx_candidates_per_level", "orbx_launch_count",
+    "orbx_profile_enable", "orbx_profile_read",
+    "orbm_hamming", "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_search_by_projection_last",
+    "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
+    "orbs_stream", "orbs_launch_count", "orbs_extractor",
 ]
 
 
@@ -64,6 +66,29 @@ def lib() -> C.CDLL:
     L.orbx_candidates_per_level.argtypes = [vp, i, vp]
     L.orbx_launch_count.argtypes = [vp]
     L.orbx_launch_count.restype = C.c_longlong
+    L.orbx_profile_enable.argtypes = [vp, i]
+    L.orbx_profile_read.argtypes = [vp, vp, C.POINTER(C.c_longlong), C.POINTER(i)]
+    L.orbm_hamming.argtypes = [vp, vp]
+    L.orbm_create.argtypes = [i, C.POINTER(vp)]
+    L.orbm_destroy.argtypes = [vp]
+    L.orbm_destroy.restype = None
+    L.orbm_launch_count.argtypes = [vp]
+    L.orbm_launch_count.restype = C.c_longlong
+    L.orbm_search_by_projection_last.argtypes = [vp, C.POINTER(OrbmFrame), C.POINTER(OrbmLast), C.c_float, i,
+                                                 C.c_float, i, vp, C.POINTER(i)]
+    L.orbs_create.argtypes = [C.POINTER(OrbsParams), i, C.POINTER(vp)]
+    L.orbs_destroy.argtypes = [vp]
+    L.orbs_destroy.restype = None
+    L.orbs_track_batch.argtypes = [vp, vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, i]
+    L.orbs_track_batch_device.argtypes = [vp, vp, vp, vp, i, i, i]
+    L.orbs_device_results.argtypes = [vp] + [C.POINTER(vp)] * 5 + [C.POINTER(i)]
+    L.orbs_sync.argtypes = [vp]
+    L.orbs_stream.argtypes = [vp]
+    L.orbs_stream.restype = vp
+    L.orbs_launch_count.argtypes = [vp]
+    L.orbs_launch_count.restype = C.c_longlong
+    L.orbs_extractor.argtypes = [vp]
+    L.orbs_extractor.restype = vp
     _lib = L
     return L
 

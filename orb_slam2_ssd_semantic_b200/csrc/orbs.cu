@@ -1,0 +1,230 @@
+// orbs.cu -- batched stream pipeline (north_star's "batched many-frame mode"): per frame t of a batch the device
+// does what Tracking::GrabImageRGBD -> Frame::Frame(RGB-D) -> TrackWithMotionModel's SearchByProjection do on the
+// CPU (src/Tracking.cc:331-375,1324-1352; src/Frame.cc:176-240), with no host round trip between the stages.
+#include <new>
+
+#include "orbm_host.h"
+#include "orbx_host.h"
+
+using namespace b200;
+
+namespace b200 {
+
+struct GlueOut {     // SoA per frame, stride cap
+  float *x, *y, *ang, *uright, *depth, *xw;
+  int* oct;
+  uint8_t* valid;
+};
+
+// Frame::ComputeStereoFromRGBD (src/Frame.cc:850-871) + Frame::UnprojectStereo (:879-899) for every keypoint,
+// and the AoS -> SoA split the matcher kernel reads.
+__global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restrict__ kps, const int* __restrict__ nkp,
+                                                    int cap, const float* __restrict__ depth, int rows, int cols,
+                                                    const float* __restrict__ Tcw, float fx, float fy, float cx,
+                                                    float cy, float bf, GlueOut o) {
+  const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkp[f]) return;
+  const size_t g = (size_t)f * cap + i;
+  const OrbxKeyPoint kp = kps[g];
+  const float* T = Tcw + (size_t)f * 16;
+  const float u = kp.x, v = kp.y;
+  const float d = depth[(size_t)f * rows * cols + (size_t)(int)v * cols + (int)u];
+  o.x[g] = u; o.y[g] = v; o.ang[g] = kp.angle; o.oct[g] = kp.octave;
+  float ur = -1.f, dd = -1.f;
+  uint8_t ok = 0;
+  if (d > 0) {
+    dd = d;
+    ur = __fsub_rn(u, __fdiv_rn(bf, d));
+    const float invfx = __fdiv_rn(1.0f, fx), invfy = __fdiv_rn(1.0f, fy);   // src/Frame.cc:215-216
+    const float x = __fmul_rn(__fmul_rn(__fsub_rn(u, cx), d), invfx);
+    const float y = __fmul_rn(__fmul_rn(__fsub_rn(v, cy), d), invfy);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float Rwc[3] = {T[0 * 4 + r], T[1 * 4 + r], T[2 * 4 + r]};   // mRwc = mRcw.t()
+      double s = 0;                                                       // mOw = -mRcw.t()*mtcw (double gemm)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)T[k * 4 + r], (double)T[k * 4 + 3]));
+      o.xw[g * 3 + r] = gemm3(Rwc, x, y, d, __double2float_rn(-s));
+    }
+    ok = 1;
+  }
+  o.uright[g] = ur; o.depth[g] = dd; o.valid[g] = ok;
+}
+
+__global__ void k_fill_i32(int* p, int v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace b200
+
+struct orbs {
+  OrbsParams prm{};
+  int device = 0;
+  orbx* ex = nullptr;
+  long long launches = 0;
+  int rows = 0, cols = 0, maxF = 0, cap = 0, lastF = 0;
+  float *d_x = nullptr, *d_y = nullptr, *d_ang = nullptr, *d_ur = nullptr, *d_dep = nullptr, *d_xw = nullptr;
+  int* d_oct = nullptr;
+  uint8_t* d_valid = nullptr;
+  int *d_c2l = nullptr, *d_nm = nullptr, *d_ncand = nullptr, *d_gidx = nullptr, *d_acc = nullptr;
+  unsigned long long* d_topk = nullptr;
+  uint8_t* d_gray = nullptr;
+  float *d_depth = nullptr, *d_T = nullptr;
+  bool have = false;
+  void free_bufs() {
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(d_x); F(d_y); F(d_ang); F(d_ur); F(d_dep); F(d_xw); F(d_oct); F(d_valid); F(d_c2l); F(d_nm); F(d_ncand);
+    F(d_gidx); F(d_acc); F(d_topk); F(d_gray); F(d_depth); F(d_T);
+    d_x = d_y = d_ang = d_ur = d_dep = d_xw = nullptr; d_oct = nullptr; d_valid = nullptr;
+    d_c2l = d_nm = d_ncand = d_gidx = d_acc = nullptr; d_topk = nullptr; d_gray = nullptr; d_depth = d_T = nullptr;
+  }
+  ~orbs() {
+    DeviceGuard g(device);
+    free_bufs();
+    delete ex;
+  }
+  int ensure(int r, int c, int F, bool host_inputs) {
+    B200_CHECK(ex->ensure_geometry(r, c, F));
+    if (!(r == rows && c == cols && F <= maxF && ex->cap == cap)) {
+      B200_CUDA(cudaStreamSynchronize(ex->stream));
+      free_bufs();
+      rows = r; cols = c; maxF = std::max(F, ex->maxF); cap = ex->cap;
+      const size_t n = (size_t)maxF * cap;
+      B200_CUDA(cudaMalloc(&d_x, n * 4)); B200_CUDA(cudaMalloc(&d_y, n * 4)); B200_CUDA(cudaMalloc(&d_ang, n * 4));
+      B200_CUDA(cudaMalloc(&d_ur, n * 4)); B200_CUDA(cudaMalloc(&d_dep, n * 4)); B200_CUDA(cudaMalloc(&d_xw, n * 12));
+      B200_CUDA(cudaMalloc(&d_oct, n * 4)); B200_CUDA(cudaMalloc(&d_valid, n));
+      B200_CUDA(cudaMalloc(&d_c2l, n * 4)); B200_CUDA(cudaMalloc(&d_nm, (size_t)maxF * 4));
+      B200_CUDA(cudaMalloc(&d_ncand, n * 4)); B200_CUDA(cudaMalloc(&d_gidx, n * 4)); B200_CUDA(cudaMalloc(&d_acc, n * 4));
+      B200_CUDA(cudaMalloc(&d_topk, n * 8 * MATCH_K));
+    }
+    if (host_inputs && !d_gray) {
+      B200_CUDA(cudaMalloc(&d_gray, (size_t)maxF * rows * cols));
+      B200_CUDA(cudaMalloc(&d_depth, (size_t)maxF * rows * cols * 4));
+      B200_CUDA(cudaMalloc(&d_T, (size_t)maxF * 64));
+    }
+    return B200ORB_OK;
+  }
+  int run(const uint8_t* dg, const float* dd, const float* dT, int F) {
+    cudaStream_t st = ex->stream;
+    B200_CHECK(ex->run(dg, cols, (size_t)rows * cols, F));
+    GlueOut go{d_x, d_y, d_ang, d_ur, d_dep, d_xw, d_oct, d_valid};
+    k_frame_glue<<<dim3((cap + 255) / 256, F), 256, 0, st>>>(ex->d_kps, ex->d_n, cap, dd, rows, cols, dT, prm.fx, prm.fy,
+                                                            prm.cx, prm.cy, prm.bf, go);
+    ++launches;
+    B200_CHECK(ex->prof_mark(ST_GLUE + 1));
+    // frame 0 of the batch has no predecessor: all -1, 0 matches
+    k_fill_i32<<<(cap + 255) / 256, 256, 0, st>>>(d_c2l, -1, (size_t)cap);
+    ++launches;
+    B200_CUDA(cudaMemsetAsync(d_nm, 0, 4, st));
+    if (F > 1) {
+      MatchCam cam;
+      memset(&cam, 0, sizeof(cam));
+      cam.fx = prm.fx; cam.fy = prm.fy; cam.cx = prm.cx; cam.cy = prm.cy; cam.bf = prm.bf;
+      cam.b = prm.bf / prm.fx;                       // mb = mbf/fx, src/Frame.cc:218
+      cam.min_x = 0.f; cam.max_x = (float)cols;      // no distortion: ComputeImageBounds, src/Frame.cc:617-623
+      cam.min_y = 0.f; cam.max_y = (float)rows;
+      for (int l = 0; l < prm.orb.nlevels; ++l) cam.sf[l] = ex->sf[l];
+      cam.th = prm.th; cam.nnratio = prm.nnratio; cam.mono = 0; cam.check_ori = prm.check_ori;
+      cam.nlevels = prm.orb.nlevels;
+      cam.last_obs_default = 1;                      // last-frame points behave like mapped points (Observations()>0)
+      MatchBatch mb{};
+      const size_t c = cap;
+      mb.cx = d_x + c; mb.cy = d_y + c; mb.cang = d_ang + c; mb.curight = d_ur + c; mb.coct = d_oct + c;
+      mb.cdesc = ex->d_desc + c * 32; mb.cobs = nullptr; mb.cn = ex->d_n + 1; mb.cTcw = dT + 16; mb.cstride = c;
+      mb.lxw = d_xw; mb.lvalid = d_valid; mb.loct = d_oct; mb.lang = d_ang; mb.ldesc = ex->d_desc; mb.lobs = nullptr;
+      mb.ln = ex->d_n; mb.lTcw = dT; mb.lstride = c;
+      mb.cur2last = d_c2l + c; mb.nmatch = d_nm + 1; mb.topk = d_topk; mb.ncand = d_ncand; mb.grididx = d_gidx;
+      mb.accepted = d_acc;
+      B200_CHECK(launch_match_last(mb, cam, F - 1, align_up(cap, 16), st));
+      ++launches;
+    }
+    B200_CHECK(ex->prof_mark(ST_MATCH + 1));
+    lastF = F;
+    have = true;
+    return B200ORB_OK;
+  }
+};
+
+extern "C" {
+
+int orbs_create(const OrbsParams* p, int device, orbs_t** out) {
+  if (!p || !out) { set_error("null argument"); return B200ORB_EINVAL; }
+  *out = nullptr;
+  orbx_t* ex = nullptr;
+  B200_CHECK(orbx_create(&p->orb, device, &ex));
+  orbs* h = new (std::nothrow) orbs();
+  if (!h) { orbx_destroy(ex); set_error("out of host memory"); return B200ORB_EINVAL; }
+  h->prm = *p;
+  h->device = device;
+  h->ex = ex;
+  *out = h;
+  return B200ORB_OK;
+}
+void orbs_destroy(orbs_t* h) { delete h; }
+
+int orbs_track_batch_device(orbs_t* h, const uint8_t* d_gray, const float* d_depth, const float* d_Tcw, int nframes,
+                            int rows, int cols) {
+  if (!h || !d_gray || !d_depth || !d_Tcw || nframes <= 0 || rows <= 0 || cols <= 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  B200_CHECK(h->ensure(rows, cols, nframes, false));
+  return h->run(d_gray, d_depth, d_Tcw, nframes);
+}
+
+int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d_desc, const int32_t** d_nkp,
+                        const int32_t** d_cur2last, const int32_t** d_nmatch, int* cap) {
+  if (!h || !h->have) { set_error("no results"); return B200ORB_EINVAL; }
+  if (d_kps) *d_kps = h->ex->d_kps;
+  if (d_desc) *d_desc = h->ex->d_desc;
+  if (d_nkp) *d_nkp = h->ex->d_n;
+  if (d_cur2last) *d_cur2last = h->d_c2l;
+  if (d_nmatch) *d_nmatch = h->d_nm;
+  if (cap) *cap = h->cap;
+  return B200ORB_OK;
+}
+
+int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const float* Tcw, int nframes, int rows,
+                     int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp, int32_t* cur2last, int32_t* nmatch,
+                     int cap) {
+  if (!h || !gray || !depth || !Tcw || !kps || !desc || !nkp || !cur2last || !nmatch || nframes <= 0 || rows <= 0 ||
+      cols <= 0) {
+    set_error("bad argument");
+    return B200ORB_EINVAL;
+  }
+  DeviceGuard g(h->device);
+  B200_CHECK(h->ensure(rows, cols, nframes, true));
+  if (cap < h->cap) { set_error("cap %d < required %d (orbx_max_keypoints)", cap, h->cap); return B200ORB_ECAP; }
+  cudaStream_t st = h->ex->stream;
+  const size_t px = (size_t)rows * cols, F = nframes;
+  B200_CUDA(cudaMemcpyAsync(h->d_gray, gray, px * F, cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(h->d_depth, depth, px * F * 4, cudaMemcpyHostToDevice, st));
+  B200_CUDA(cudaMemcpyAsync(h->d_T, Tcw, F * 64, cudaMemcpyHostToDevice, st));
+  B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes));
+  const size_t hc = h->cap;
+  if ((size_t)cap == hc) {
+    B200_CUDA(cudaMemcpyAsync(kps, h->ex->d_kps, sizeof(OrbxKeyPoint) * hc * F, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(desc, h->ex->d_desc, 32 * hc * F, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(cur2last, h->d_c2l, 4 * hc * F, cudaMemcpyDeviceToHost, st));
+  } else {
+    B200_CUDA(cudaMemcpy2DAsync(kps, sizeof(OrbxKeyPoint) * cap, h->ex->d_kps, sizeof(OrbxKeyPoint) * hc,
+                                sizeof(OrbxKeyPoint) * hc, F, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpy2DAsync(desc, (size_t)32 * cap, h->ex->d_desc, 32 * hc, 32 * hc, F, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpy2DAsync(cur2last, (size_t)4 * cap, h->d_c2l, 4 * hc, 4 * hc, F, cudaMemcpyDeviceToHost, st));
+  }
+  B200_CUDA(cudaMemcpyAsync(nkp, h->ex->d_n, 4 * F, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaMemcpyAsync(nmatch, h->d_nm, 4 * F, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return B200ORB_OK;
+}
+
+int orbs_sync(orbs_t* h) {
+  if (!h) return B200ORB_EINVAL;
+  DeviceGuard g(h->device);
+  B200_CUDA(cudaStreamSynchronize(h->ex->stream));
+  return B200ORB_OK;
+}
+void* orbs_stream(orbs_t* h) { return h ? (void*)h->ex->stream : nullptr; }
+long long orbs_launch_count(const orbs_t* h) { return h ? h->launches + h->ex->launches : 0; }
+orbx_t* orbs_extractor(orbs_t* h) { return h ? h->ex : nullptr; }
+
+}  // extern "C"

@@ -253,6 +253,7 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
   rawv.p[0] = const_cast<uint8_t*>(d_l0);
   rawv.pitch[0] = pitch0;
   rawv.fstride[0] = fstride0;
+  B200_CHECK(prof_begin(F));
   // K1 pyramid
   for (int l = 1; l < nl; ++l) {
     dim3 blk(32, 8), grd((lw[l] + 127) / 128, (lh[l] + 7) / 8, F);
@@ -261,15 +262,18 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
                                      d_yt + yt_off[l]);
     ++launches;
   }
+  B200_CHECK(prof_mark(ST_RESIZE + 1));
   // K2 FAST cells
   k_fast_cells<<<dim3(ncells, F), FAST_THREADS, 0, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
                                                             prm.min_th_fast, d_cand, d_cellcnt);
   ++launches;
+  B200_CHECK(prof_mark(ST_FAST + 1));
   // K3 quad-tree
   QtScratchView qs{d_qkp, d_qnode};
   k_quadtree<<<dim3(nl, F), QT_THREADS, qt_smem, stream>>>(ltab, d_cells, d_cand, d_cellcnt, ncells, slots_per_frame,
                                                           qs, qt_cap, d_sel, d_selcnt, d_candcnt, sel_per_frame);
   ++launches;
+  B200_CHECK(prof_mark(ST_QUADTREE + 1));
   // K4 blur
   for (int l = 0; l < nl; ++l) {
     dim3 grd((lw[l] + BL_TW - 1) / BL_TW, (lh[l] + BL_TH - 1) / BL_TH, F);
@@ -277,13 +281,33 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
                                      blurv.fstride[l], lw[l], lh[l]);
     ++launches;
   }
+  B200_CHECK(prof_mark(ST_BLUR + 1));
   // K5 orientation + descriptors
   k_orient_desc<<<dim3((cap + OD_WARPS - 1) / OD_WARPS, F), OD_WARPS * 32, 0, stream>>>(
       ltab, otab, rawv, blurv, d_pattern, d_sel, d_selcnt, sel_per_frame, d_kps, d_desc, d_n, cap);
   ++launches;
+  B200_CHECK(prof_mark(ST_ORIENT_DESC + 1));
   B200_CUDA(cudaGetLastError());
   lastF = F;
   have_results = true;
+  return B200ORB_OK;
+}
+
+int orbx::prof_begin(int frames) {
+  if (!profile) return B200ORB_OK;
+  StageEvents se;
+  memset(&se, 0, sizeof(se));
+  se.frames = frames;
+  prof_runs.push_back(se);
+  return prof_mark(0);
+}
+
+int orbx::prof_mark(int boundary) {
+  if (!profile || prof_runs.empty()) return B200ORB_OK;
+  StageEvents& se = prof_runs.back();
+  B200_CUDA(cudaEventCreate(&se.ev[boundary]));
+  B200_CUDA(cudaEventRecord(se.ev[boundary], stream));
+  se.used[boundary] = true;
   return B200ORB_OK;
 }
 
@@ -485,5 +509,36 @@ int orbx_candidates_per_level(orbx_t* h, int frame, int* counts) {
 }
 
 long long orbx_launch_count(const orbx_t* h) { return h ? h->launches : 0; }
+
+int orbx_profile_enable(orbx_t* h, int on) {
+  if (!h) return B200ORB_EINVAL;
+  h->profile = on != 0;
+  return B200ORB_OK;
+}
+
+// Sum of per-stage device time (ms) and frames over every run() since the last read; synchronises the stream.
+int orbx_profile_read(orbx_t* h, float* ms /*B200ORB_NUM_STAGES*/, long long* frames, int* runs) {
+  if (!h || !ms) return B200ORB_EINVAL;
+  DeviceGuard g(h->device);
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < ST_COUNT; ++s) ms[s] = 0.f;
+  long long fr = 0;
+  for (StageEvents& se : h->prof_runs) {
+    fr += se.frames;
+    int prev = 0;
+    for (int b = 1; b <= ST_COUNT; ++b) {
+      if (!se.used[b]) continue;
+      float t = 0.f;
+      if (se.used[prev]) cudaEventElapsedTime(&t, se.ev[prev], se.ev[b]);
+      ms[b - 1] += t;
+      prev = b;
+    }
+    for (int b = 0; b <= ST_COUNT; ++b) if (se.used[b]) cudaEventDestroy(se.ev[b]);
+  }
+  if (frames) *frames = fr;
+  if (runs) *runs = (int)h->prof_runs.size();
+  h->prof_runs.clear();
+  return B200ORB_OK;
+}
 
 }  // extern "C"

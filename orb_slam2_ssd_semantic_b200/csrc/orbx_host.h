@@ -1,6 +1,17 @@
 // orbx_host.h -- definition of the extractor handle (shared by orbx.cu and the stream pipeline orbs.cu).
 #pragma once
+#include <vector>
+
 #include "orbx_kernels.cuh"
+
+namespace b200 {
+enum { ST_RESIZE = 0, ST_FAST, ST_QUADTREE, ST_BLUR, ST_ORIENT_DESC, ST_GLUE, ST_MATCH, ST_COUNT };
+struct StageEvents {
+  cudaEvent_t ev[ST_COUNT + 1];
+  bool used[ST_COUNT + 1];
+  int frames;
+};
+}  // namespace b200
 
 struct orbx {
   OrbxParams prm{};
@@ -39,6 +50,9 @@ struct orbx {
   void* h_stage = nullptr;
   size_t stage_bytes = 0;
   bool have_results = false;
+  // optional per-stage CUDA-event timing (bench.py's roofline leg): one event set per run(), read lazily
+  bool profile = false;
+  std::vector<b200::StageEvents> prof_runs;
 
   orbx();
   ~orbx();
@@ -48,4 +62,6 @@ struct orbx {
   int run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F);
   int ensure_stage(size_t bytes);
   int ensure_tmp(size_t bytes);
+  int prof_mark(int boundary);   // record event `boundary` of the current run (no-op unless profiling)
+  int prof_begin(int frames);
 };

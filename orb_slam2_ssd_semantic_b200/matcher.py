@@ -1,0 +1,57 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher (reference include/ORBmatcher.h:37-118) over the C-ABI.
+
+The reference's methods walk Frame/KeyFrame/MapPoint objects and mutate them; here the same searches take the
+flat views the C++ shim builds (FrameView / LastView of _abi.py) and return the index vectors the shim turns
+back into pointer assignments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import FrameView, LastView, ptr  # noqa: F401
+
+
+class ORBmatcher:
+    TH_LOW = 50       # src/ORBmatcher.cc:40
+    TH_HIGH = 100     # :39
+    HISTO_LENGTH = 30  # :41
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, device: int = 0):
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        _lib.check(self._L.orbm_create(int(device), C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orbm_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    @staticmethod
+    def DescriptorDistance(a: np.ndarray, b: np.ndarray) -> int:
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        assert a.size == 32 and b.size == 32
+        return int(_lib.lib().orbm_hamming(ptr(a), ptr(b)))
+
+    def SearchByProjection(self, CurrentFrame: FrameView, LastFrame: LastView, th: float, bMono: bool = False):
+        """SearchByProjection(Frame&, const Frame&, th, bMono) (src/ORBmatcher.cc:1578-1724).
+        Returns (nmatches, cur2last) with cur2last[j] = LastFrame index now in CurrentFrame.mvpMapPoints[j]
+        (-1 NULL, -2 untouched pre-existing entry)."""
+        out = np.full(CurrentFrame.n, -1, np.int32)
+        nm = C.c_int(0)
+        cs, ls = CurrentFrame.struct(), LastFrame.struct()
+        _lib.check(self._L.orbm_search_by_projection_last(self._h, C.byref(cs), C.byref(ls), float(th), int(bMono),
+                                                          self.mfNNratio, int(self.mbCheckOrientation), ptr(out),
+                                                          C.byref(nm)))
+        return nm.value, out
+
+    def launch_count(self) -> int:
+        return int(self._L.orbm_launch_count(self._h))

@@ -1,0 +1,80 @@
+"""Batched stream pipeline (north_star's many-frame mode) over orbs_* of the C-ABI: per frame of a batch,
+extract + ComputeStereoFromRGBD + UnprojectStereo of the previous frame + SearchByProjection(cur, last)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import OrbsParams, OrbxParams, ptr
+from .extractor import KP_DTYPE
+
+
+class StreamTracker:
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, fx=535.4, fy=539.2,
+                 cx=320.1, cy=247.6, bf=40.0, th=15.0, nnratio=0.9, checkOri=True, max_frames=256, device=0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        p = OrbsParams(OrbxParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST), fx, fy, cx, cy, bf, th,
+                       nnratio, int(checkOri), max_frames)
+        _lib.check(self._L.orbs_create(C.byref(p), int(device), C.byref(self._h)))
+        self.cap = int(self._L.orbx_max_keypoints(self._L.orbs_extractor(self._h)))
+        self.nlevels = nlevels
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orbs_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def track_batch(self, gray: np.ndarray, depth: np.ndarray, Tcw: np.ndarray):
+        """Host buffers in, host buffers out (the reference-facing call; copies are inside)."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16)
+        F, rows, cols = gray.shape
+        assert depth.shape == gray.shape and Tcw.shape[0] == F
+        cap = self.cap
+        kps = np.zeros((F, cap), KP_DTYPE)
+        desc = np.zeros((F, cap, 32), np.uint8)
+        nkp = np.zeros(F, np.int32)
+        c2l = np.zeros((F, cap), np.int32)
+        nm = np.zeros(F, np.int32)
+        _lib.check(self._L.orbs_track_batch(self._h, ptr(gray), ptr(depth), ptr(Tcw), F, rows, cols, ptr(kps), ptr(desc),
+                                            ptr(nkp), ptr(c2l), ptr(nm), cap))
+        return kps, desc, nkp, c2l, nm
+
+    def track_batch_device(self, d_gray: int, d_depth: int, d_Tcw: int, nframes: int, rows: int, cols: int):
+        """Device pointers (ints) in; results stay in HBM (device_results()). Asynchronous."""
+        _lib.check(self._L.orbs_track_batch_device(self._h, C.c_void_p(d_gray), C.c_void_p(d_depth), C.c_void_p(d_Tcw),
+                                                   nframes, rows, cols))
+
+    def device_results(self):
+        ps = [C.c_void_p() for _ in range(5)]
+        cap = C.c_int()
+        _lib.check(self._L.orbs_device_results(self._h, *[C.byref(p) for p in ps], C.byref(cap)))
+        return [p.value for p in ps], cap.value
+
+    STAGES = ("resize", "fast", "quadtree", "blur", "orient_desc", "glue", "match")
+
+    def profile_enable(self, on: bool = True):
+        _lib.check(self._L.orbx_profile_enable(self._L.orbs_extractor(self._h), int(on)))
+
+    def profile_read(self):
+        """-> ({stage: total ms}, frames, runs) since the last read (synchronises)."""
+        ms = np.zeros(7, np.float32)
+        fr, runs = C.c_longlong(0), C.c_int(0)
+        _lib.check(self._L.orbx_profile_read(self._L.orbs_extractor(self._h), ptr(ms), C.byref(fr), C.byref(runs)))
+        return dict(zip(self.STAGES, ms.tolist())), fr.value, runs.value
+
+    def sync(self):
+        _lib.check(self._L.orbs_sync(self._h))
+
+    def stream(self) -> int:
+        return int(self._L.orbs_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self._L.orbs_launch_count(self._h))

@@ -1,0 +1,98 @@
+"""GPU parity of ORBmatcher::SearchByProjection(Cur, Last) through the C-ABI vs the CPU oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+from orb_slam2_ssd_semantic_b200 import synth
+from tests.helpers import frame_views
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def stream_feats(oracle):
+    ws = synth.WallStream(seed=1234, n=8)
+    R = oracle.RefExtractor(1000, 1.2, 8, 20, 7)
+    out = []
+    for t in (0, 1, 2, 5):
+        gray, depth, rgb, T = ws.frame(t)
+        K, D = R(gray)
+        out.append((K, D, depth, T))
+    return out, R.mvScaleFactor.copy()
+
+
+@pytest.mark.parametrize("obs", [0, 1])
+@pytest.mark.parametrize("th", [15.0, 7.0, 30.0])
+def test_projection_last_stream(oracle, stream_feats, obs, th):
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    feats, sf = stream_feats
+    m = ORBmatcher(0.9, True)
+    for a in range(1, len(feats)):
+        Kc, Dc, dc, Tc = feats[a]
+        Kl, Dl, dl, Tl = feats[a - 1]
+        cur, last = frame_views(oracle, Kc, Dc, dc, Tc, Kl, Dl, dl, Tl, sf, obs=obs)
+        n_ref, ref = oracle.search_by_projection_last(cur, last, th, False, 0.9, True)
+        n_gpu, gpu = m.SearchByProjection(cur, last, th, False)
+        assert n_ref > 50, "test is vacuous: %d matches" % n_ref
+        assert n_gpu == n_ref
+        assert (gpu == ref).all(), np.nonzero(gpu != ref)[0][:10]
+
+
+def test_projection_last_noisy_pose_and_flags(oracle, stream_feats):
+    """Pose noise, forward/backward motion branches, no orientation check, mono, pre-existing MapPoints."""
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    feats, sf = stream_feats
+    rng = np.random.default_rng(7)
+    Kc, Dc, dc, Tc = feats[1]
+    Kl, Dl, dl, Tl = feats[0]
+    for case in range(8):
+        T = Tc.copy()
+        T[:3, 3] += rng.normal(0, 0.01, 3).astype(np.float32)
+        if case == 1:
+            T[2, 3] += 0.5     # |tlc.z| > mb: one of the forward/backward octave windows
+        if case == 2:
+            T[2, 3] -= 0.5
+        cur, last = frame_views(oracle, Kc, Dc, dc, T, Kl, Dl, dl, Tl, sf, obs=1)
+        if case == 3:
+            cur.mp_obs = rng.integers(-1, 3, size=cur.n).astype(np.int32)
+        if case == 4:
+            last.valid[::3] = 0
+        check_ori = case != 5
+        mono = case == 6
+        m = ORBmatcher(0.9, check_ori)
+        n_ref, ref = oracle.search_by_projection_last(cur, last, 15.0, mono, 0.9, check_ori)
+        n_gpu, gpu = m.SearchByProjection(cur, last, 15.0, mono)
+        assert n_gpu == n_ref and (gpu == ref).all(), "case %d" % case
+
+
+def test_projection_last_crowded(oracle):
+    """Many more than K candidates per window and heavy claiming: exercises the re-walk path."""
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    from orb_slam2_ssd_semantic_b200._abi import FrameView, LastView
+    rng = np.random.default_rng(3)
+    n = 600
+    x = rng.uniform(300, 340, n).astype(np.float32)
+    y = rng.uniform(220, 260, n).astype(np.float32)
+    base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+    desc = np.repeat(base, n, 0)
+    flip = rng.integers(0, 256, size=(n, 2), dtype=np.uint8)
+    desc[:, :2] ^= flip            # all descriptors within a few bits of each other
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    T = np.eye(4, dtype=np.float32)
+    cur = FrameView(x, y, np.zeros(n, np.int32), rng.uniform(0, 360, n).astype(np.float32), np.full(n, -1, np.float32),
+                    desc, T, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, 0, 640, 0, 480, sf)
+    z = 2.0
+    xw = np.stack([(x - synth.CX) * z / synth.FX, (y - synth.CY) * z / synth.FY, np.full(n, z)], 1).astype(np.float32)
+    last = LastView(xw, np.ones(n, np.uint8), np.zeros(n, np.int32), rng.uniform(0, 360, n).astype(np.float32), desc,
+                    T, mp_obs=np.ones(n, np.int32))
+    m = ORBmatcher(0.9, True)
+    n_ref, ref = oracle.search_by_projection_last(cur, last, 15.0, False, 0.9, True)
+    n_gpu, gpu = m.SearchByProjection(cur, last, 15.0, False)
+    assert n_gpu == n_ref and (gpu == ref).all()
+
+
+def test_hamming_matches_oracle(oracle):
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        a, b = rng.integers(0, 256, size=(2, 32), dtype=np.uint8)
+        assert ORBmatcher.DescriptorDistance(a, b) == oracle.hamming(a, b) == int(np.unpackbits(a ^ b).sum())

@@ -1,0 +1,38 @@
+"""GPU parity of the batched stream pipeline (extract -> stereo/unproject glue -> SearchByProjection) vs the
+oracle run stage by stage on the CPU."""
+import numpy as np
+import pytest
+
+from orb_slam2_ssd_semantic_b200 import synth
+from tests.helpers import frame_views
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stream_batch_matches_oracle(oracle):
+    from orb_slam2_ssd_semantic_b200 import StreamTracker
+    F = 5
+    ws = synth.WallStream(seed=1234, n=F)
+    frames = [ws.frame(t) for t in range(F)]
+    gray = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames])
+    T = np.stack([f[3] for f in frames])
+    st = StreamTracker(1000, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, th=15.0, nnratio=0.9)
+    kps, desc, nkp, c2l, nm = st.track_batch(gray, depth, T)
+    R = oracle.RefExtractor(1000, 1.2, 8, 20, 7)
+    prev = None
+    for t in range(F):
+        K, D = R(gray[t])
+        assert nkp[t] == len(K)
+        assert kps[t, :nkp[t]].tobytes() == K.tobytes()
+        assert (desc[t, :nkp[t]] == D).all()
+        if prev is None:
+            assert nm[t] == 0 and (c2l[t, :nkp[t]] == -1).all()
+        else:
+            cur, last = frame_views(oracle, K, D, depth[t], T[t], prev[0], prev[1], depth[t - 1], T[t - 1],
+                                    R.mvScaleFactor, obs=1)
+            n_ref, ref = oracle.search_by_projection_last(cur, last, 15.0, False, 0.9, True)
+            assert n_ref > 100
+            assert nm[t] == n_ref
+            assert (c2l[t, :nkp[t]] == ref).all()
+        prev = (K, D)
