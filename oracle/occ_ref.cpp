@@ -1,0 +1,270 @@
+// oracle/occ_ref.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.
+//
+// CPU restatement of the keyframe -> point cloud -> OctoMap occupancy path:
+//   MapDrawer::GeneratePointCloud   perfect/src/MapDrawer.cc:641-675 (back-projection, gates, VoxelGrid 1 cm, transform)
+//   MapDrawer::InsertScan           perfect/src/MapDrawer.cc:946-1025
+//   MapDrawer ctor octree params    perfect/src/MapDrawer.cc:51-56
+//   PointCloudMapping::generatePointCloud (T variant, all pixels, no gate)  src/pointcloudmapping.cc:131-194
+// Third-party semantics restated from their published behaviour (NOT vendored; parity unpinned):
+//   PCL 1.7 VoxelGrid, pcl::transformPointCloud<PointT,double>, octomap 1.9 OcTreeKey /
+//   coordToKeyChecked / computeRayKeys / updateNode log-odds.  The shipped artefact octomap.ot pins
+//   the log-odds constants and clamps (tests/test_golden_cpu.py).
+// Where PCL leaves an order unspecified (std::sort of equal voxel indices) the oracle sums a voxel's points in
+// pixel row-major order; the RANSAC ground split is replaced by a supplied per-pixel label (voxel label = label of
+// its first pixel).
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <tuple>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../include/b200orb.h"
+
+namespace {
+
+struct OccMap {
+  OcmParams p;
+  double res, res_factor;
+  float hit_log, miss_log, cmin, cmax;
+  std::unordered_map<uint64_t, float> leaves;
+  std::unordered_map<uint64_t, uint32_t> colors;
+  // last scan
+  std::vector<float> pts;
+  std::vector<uint8_t> pts_rgb, pts_label;
+
+  explicit OccMap(const OcmParams& q) : p(q) {
+    res = q.resolution;
+    res_factor = 1.0 / res;
+    auto logodds = [](double pr) { return (float)std::log(pr / (1 - pr)); };   // octomap::logodds
+    hit_log = logodds(q.prob_hit);
+    miss_log = logodds(q.prob_miss);
+    cmin = logodds(q.clamp_min);
+    cmax = logodds(q.clamp_max);
+  }
+  static uint64_t pack(const uint16_t k[3]) { return (uint64_t)k[0] | ((uint64_t)k[1] << 16) | ((uint64_t)k[2] << 32); }
+  bool coord_to_key(double c, uint16_t& k) const {   // coordToKeyChecked, tree_max_val = 32768
+    const int s = ((int)std::floor(res_factor * c)) + 32768;
+    if (s >= 0 && (unsigned)s < 65536u) { k = (uint16_t)s; return true; }
+    return false;
+  }
+  bool point_to_key(const float* pt, uint16_t k[3]) const {
+    return coord_to_key((double)pt[0], k[0]) && coord_to_key((double)pt[1], k[1]) && coord_to_key((double)pt[2], k[2]);
+  }
+  double key_to_coord(uint16_t k) const { return (double((int)k - 32768) + 0.5) * res; }
+
+  // OcTreeBaseImpl::computeRayKeys (end cell excluded)
+  bool ray_keys(const float* o, const float* e, std::vector<uint64_t>& ray) const {
+    ray.clear();
+    uint16_t ko[3], ke[3];
+    if (!point_to_key(o, ko) || !point_to_key(e, ke)) return false;
+    if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return true;
+    ray.push_back(pack(ko));
+    float dir[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
+    double n2 = 0;
+    for (int i = 0; i < 3; ++i) n2 += dir[i] * dir[i];   // float product added into a double
+    const float length = (float)std::sqrt(n2);
+    for (int i = 0; i < 3; ++i) dir[i] /= length;
+    int step[3];
+    double tMax[3], tDelta[3];
+    uint16_t cur[3] = {ko[0], ko[1], ko[2]};
+    for (int i = 0; i < 3; ++i) {
+      if (dir[i] > 0.0) step[i] = 1;
+      else if (dir[i] < 0.0) step[i] = -1;
+      else step[i] = 0;
+      if (step[i] != 0) {
+        double voxelBorder = key_to_coord(cur[i]);
+        voxelBorder += (float)(step[i] * res * 0.5);
+        tMax[i] = (voxelBorder - o[i]) / dir[i];
+        tDelta[i] = res / std::fabs(dir[i]);
+      } else {
+        tMax[i] = 1.7976931348623157e308;
+        tDelta[i] = 1.7976931348623157e308;
+      }
+    }
+    for (;;) {
+      unsigned dim;
+      if (tMax[0] < tMax[1]) dim = (tMax[0] < tMax[2]) ? 0 : 2;
+      else dim = (tMax[1] < tMax[2]) ? 1 : 2;
+      cur[dim] = (uint16_t)(cur[dim] + step[dim]);
+      tMax[dim] += tDelta[dim];
+      if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
+      const double dist = std::min(std::min(tMax[0], tMax[1]), tMax[2]);
+      if (dist > length) break;
+      ray.push_back(pack(cur));
+    }
+    return true;
+  }
+
+  void update(uint64_t key, bool occupied) {   // OccupancyOcTreeBase::updateNode -> updateNodeLogOdds
+    const float d = occupied ? hit_log : miss_log;
+    auto it = leaves.find(key);
+    if (it == leaves.end()) it = leaves.emplace(key, 0.0f).first;
+    float v = it->second + d;
+    if (v < cmin) v = cmin;
+    if (v > cmax) v = cmax;
+    it->second = v;
+  }
+
+  // MapDrawer::GeneratePointCloud: gates + VoxelGrid + transform; fills pts/pts_rgb/pts_label
+  void generate(const float* depth, const uint8_t* rgb, int rows, int cols, const float* Tcw, float fx, float fy,
+                float cx, float cy, const uint8_t* label) {
+    struct Acc { float sx = 0, sy = 0, sz = 0, sr = 0, sg = 0, sb = 0; int n = 0; uint8_t label = 0; };
+    std::map<std::tuple<int, int, int>, Acc> vox;   // ordered by (iz, iy, ix): PCL's ascending linear index
+    std::vector<float> raw;
+    std::vector<uint8_t> raw_rgb, raw_label;
+    const bool filter = p.leaf > 0;
+    const float inv_leaf = filter ? 1.0f / p.leaf : 0.f;
+    for (int m = 0; m < rows; ++m)
+      for (int n = 0; n < cols; ++n) {
+        const float d = depth[(size_t)m * cols + n];
+        if (d < p.depth_min || d > p.depth_max) continue;            // :655
+        const float z = d;
+        const float x = (n - cx) * z / fx;                          // :658-659
+        const float y = (m - cy) * z / fy;
+        if (y < -p.y_max || y > p.y_max) continue;                  // :660
+        const uint8_t* c = rgb + ((size_t)m * cols + n) * 3;        // b,g,r
+        const uint8_t lab = label ? label[(size_t)m * cols + n] : 0;
+        if (!filter) {
+          raw.push_back(x); raw.push_back(y); raw.push_back(z);
+          raw_rgb.push_back(c[2]); raw_rgb.push_back(c[1]); raw_rgb.push_back(c[0]);
+          raw_label.push_back(lab);
+          continue;
+        }
+        const int ix = (int)std::floor(x * inv_leaf), iy = (int)std::floor(y * inv_leaf), iz = (int)std::floor(z * inv_leaf);
+        Acc& a = vox[std::make_tuple(iz, iy, ix)];
+        if (a.n == 0) a.label = lab;
+        a.sx += x; a.sy += y; a.sz += z;
+        a.sr += (float)c[2]; a.sg += (float)c[1]; a.sb += (float)c[0];
+        a.n++;
+      }
+    if (filter) {
+      for (auto& kv : vox) {
+        const Acc& a = kv.second;
+        const float fn = (float)a.n;
+        raw.push_back(a.sx / fn); raw.push_back(a.sy / fn); raw.push_back(a.sz / fn);
+        raw_rgb.push_back((uint8_t)(a.sr / fn)); raw_rgb.push_back((uint8_t)(a.sg / fn)); raw_rgb.push_back((uint8_t)(a.sb / fn));
+        raw_label.push_back(a.label);
+      }
+    }
+    // pcl::transformPointCloud(cloud, temp, T.inverse().matrix()) with T = toSE3Quat(Tcw) (double)
+    double R[9], t[3], Rt[9], ti[3];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)Tcw[i * 4 + j]; t[i] = (double)Tcw[i * 4 + 3]; }
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = R[j * 3 + i];
+      ti[i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+    }
+    const size_t np = raw.size() / 3;
+    pts.resize(np * 3);
+    for (size_t k = 0; k < np; ++k) {
+      const double px = raw[3 * k], py = raw[3 * k + 1], pz = raw[3 * k + 2];
+      for (int i = 0; i < 3; ++i)
+        pts[3 * k + i] = (float)(Rt[i * 3 + 0] * px + Rt[i * 3 + 1] * py + Rt[i * 3 + 2] * pz + ti[i]);
+    }
+    pts_rgb = raw_rgb;
+    pts_label = raw_label;
+  }
+
+  // MapDrawer::InsertScan :946-1025 (+ UpdateOctomap's sensorOrigin quirk :619,631-632: translation of Tcw)
+  void insert_scan(const float* Tcw) {
+    const float origin[3] = {Tcw[3], Tcw[7], Tcw[11]};
+    std::unordered_set<uint64_t> free_cells, occupied;
+    std::vector<uint64_t> ray;
+    const size_t np = pts.size() / 3;
+    for (size_t k = 0; k < np; ++k) {
+      const float* pt = &pts[3 * k];
+      if (pts_label[k]) {            // ground: only clears space along the ray
+        if (ray_keys(origin, pt, ray)) free_cells.insert(ray.begin(), ray.end());
+      } else {                       // non-ground: endpoint occupied (its ray is computed but unused, :988-991)
+        uint16_t key[3];
+        if (point_to_key(pt, key)) {
+          occupied.insert(pack(key));
+          colors[pack(key)] = (uint32_t)pts_rgb[3 * k] | ((uint32_t)pts_rgb[3 * k + 1] << 8) | ((uint32_t)pts_rgb[3 * k + 2] << 16);
+        }
+      }
+    }
+    for (uint64_t k : free_cells)
+      if (occupied.find(k) == occupied.end()) update(k, false);
+    for (uint64_t k : occupied) update(k, true);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void occ_ref_default_params(OcmParams* p) {
+  p->resolution = 0.05; p->prob_hit = 0.7; p->prob_miss = 0.4; p->clamp_min = 0.12; p->clamp_max = 0.97;
+  p->depth_min = 0.5f; p->depth_max = 3.0f; p->y_max = 3.0f; p->leaf = 0.01f; p->map_capacity = 0;
+}
+void* occ_ref_create(const OcmParams* p) { return new OccMap(*p); }
+void occ_ref_destroy(void* h) { delete (OccMap*)h; }
+void occ_ref_constants(void* h, float* out4) {
+  OccMap* m = (OccMap*)h;
+  out4[0] = m->hit_log; out4[1] = m->miss_log; out4[2] = m->cmin; out4[3] = m->cmax;
+}
+int occ_ref_insert_keyframe(void* h, const float* depth, const uint8_t* rgb, int rows, int cols, const float* Tcw,
+                            float fx, float fy, float cx, float cy, const uint8_t* label) {
+  OccMap* m = (OccMap*)h;
+  m->generate(depth, rgb, rows, cols, Tcw, fx, fy, cx, cy, label);
+  m->insert_scan(Tcw);
+  return (int)(m->pts.size() / 3);
+}
+int occ_ref_last_points(void* h, float* xyz, uint8_t* rgb, uint8_t* label, int cap) {
+  OccMap* m = (OccMap*)h;
+  const int n = (int)(m->pts.size() / 3);
+  if (n > cap) return -n;
+  memcpy(xyz, m->pts.data(), sizeof(float) * 3 * n);
+  if (rgb) memcpy(rgb, m->pts_rgb.data(), 3 * (size_t)n);
+  if (label) memcpy(label, m->pts_label.data(), (size_t)n);
+  return n;
+}
+long long occ_ref_num_leaves(void* h) { return (long long)((OccMap*)h)->leaves.size(); }
+long long occ_ref_export_leaves(void* h, uint16_t* keys, float* logodds, long long cap) {
+  OccMap* m = (OccMap*)h;
+  long long n = 0;
+  for (auto& kv : m->leaves) {
+    if (n >= cap) break;
+    keys[3 * n] = (uint16_t)(kv.first & 0xffff);
+    keys[3 * n + 1] = (uint16_t)((kv.first >> 16) & 0xffff);
+    keys[3 * n + 2] = (uint16_t)((kv.first >> 32) & 0xffff);
+    logodds[n] = kv.second;
+    ++n;
+  }
+  return n;
+}
+// ray keys of a single (origin, end) pair for direct DDA tests; returns count or -1 (out of range)
+int occ_ref_ray(void* h, const float* origin, const float* end, uint16_t* keys, int cap) {
+  OccMap* m = (OccMap*)h;
+  std::vector<uint64_t> ray;
+  if (!m->ray_keys(origin, end, ray)) return -1;
+  int n = 0;
+  for (uint64_t k : ray) {
+    if (n < cap) { keys[3 * n] = (uint16_t)(k & 0xffff); keys[3 * n + 1] = (uint16_t)((k >> 16) & 0xffff); keys[3 * n + 2] = (uint16_t)((k >> 32) & 0xffff); }
+    ++n;
+  }
+  return n;
+}
+// T variant (src/pointcloudmapping.cc:131-194): every pixel, no gate, d=0 -> camera centre.  out: rows*cols*3 floats
+void occ_ref_backproject_all(const float* depth, int rows, int cols, const float* Tcw, float fx, float fy, float cx,
+                             float cy, float* out) {
+  double R[9], t[3], Rt[9], ti[3];
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)Tcw[i * 4 + j]; t[i] = (double)Tcw[i * 4 + 3]; }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) Rt[i * 3 + j] = R[j * 3 + i];
+    ti[i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+  }
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const size_t i = (size_t)r * cols + c;
+      const float d = depth[i];
+      const float xf = (c - cx) * d / fx, yf = (r - cy) * d / fy;   // float, like the reference (:174-176)
+      const double px = xf, py = yf, pz = d;
+      for (int k = 0; k < 3; ++k) out[3 * i + k] = (float)(Rt[k * 3 + 0] * px + Rt[k * 3 + 1] * py + Rt[k * 3 + 2] * pz + ti[k]);
+    }
+}
+
+}  // extern "C"

@@ -102,17 +102,23 @@ void gaussian7_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, i
   std::vector<uint16_t> hb((size_t)w * h);
   for (int y = 0; y < h; ++y) {
     const uint8_t* s = src + (size_t)y * sstride;
+    uint16_t* o = &hb[(size_t)y * w];
     for (int x = 0; x < w; ++x) {
-      int acc = 0;
-      for (int k = 0; k < 7; ++k) acc += q[k] * s[reflect101(x + k - 3, w)];
-      hb[(size_t)y * w + x] = (uint16_t)acc;
+      if (x >= 3 && x < w - 3) {
+        o[x] = (uint16_t)(18 * (s[x - 3] + s[x + 3]) + 34 * (s[x - 2] + s[x + 2]) + 48 * (s[x - 1] + s[x + 1]) + 56 * s[x]);
+      } else {
+        int acc = 0;
+        for (int k = 0; k < 7; ++k) acc += q[k] * s[reflect101(x + k - 3, w)];
+        o[x] = (uint16_t)acc;
+      }
     }
   }
   for (int y = 0; y < h; ++y) {
     uint8_t* o = dst + (size_t)y * dstride;
+    const uint16_t* r[7];
+    for (int k = 0; k < 7; ++k) r[k] = &hb[(size_t)reflect101(y + k - 3, h) * w];
     for (int x = 0; x < w; ++x) {
-      uint32_t acc = 0;
-      for (int k = 0; k < 7; ++k) acc += (uint32_t)q[k] * hb[(size_t)reflect101(y + k - 3, h) * w + x];
+      const uint32_t acc = 18u * (r[0][x] + r[6][x]) + 34u * (r[1][x] + r[5][x]) + 48u * (r[2][x] + r[4][x]) + 56u * r[3][x];
       o[x] = (uint8_t)((acc + 32768u) >> 16);
     }
   }
@@ -144,16 +150,46 @@ inline int fast_m(const uint8_t* p, int stride) {
 
 struct FastKp { int x, y, score; };
 
+// corner test at threshold t without the score: 16-bit masks of ring pixels brighter than c+t / darker than
+// c-t and a 9-contiguous-bits test on the doubled mask (equivalent to m > t; the exact m is only evaluated for
+// corners, like OpenCV evaluates cornerScore only for detected corners).
+inline bool fast_is_corner(const uint8_t* p, int stride, int t) {
+  const int c = p[0], hi = c + t, lo = c - t;
+  const int r0 = p[3 * stride], r8 = p[-3 * stride];
+  if (!((r0 > hi) | (r8 > hi) | (r0 < lo) | (r8 < lo))) return false;   // any 9-arc holds pixel 0 or pixel 8
+  const int r4 = p[3], r12 = p[-3];
+  if (!((r4 > hi) | (r12 > hi) | (r4 < lo) | (r12 < lo))) return false;
+  uint32_t mb = 0, md = 0;
+  for (int k = 0; k < 16; ++k) {
+    const int v = p[kRingDy[k] * stride + kRingDx[k]];
+    mb |= (uint32_t)(v > hi) << k;
+    md |= (uint32_t)(v < lo) << k;
+  }
+  auto run9 = [](uint32_t m) {
+    m |= m << 16;
+    m &= m >> 1;   // runs >= 2
+    m &= m >> 2;   // runs >= 4
+    m &= m >> 4;   // runs >= 8
+    m &= m >> 1;   // runs >= 9
+    return m != 0;
+  };
+  return run9(mb) || run9(md);
+}
+
 void fast9_roi(const uint8_t* roi, int rw, int rh, int stride, int t, std::vector<FastKp>& out,
                std::vector<int>& sc /*scratch rw*rh*/) {
   out.clear();
   if (rw < 7 || rh < 7) return;
   sc.assign((size_t)rw * rh, 0);   // the 3-px ROI margin never scores (stays 0)
+  bool any = false;
   for (int y = 3; y < rh - 3; ++y)
     for (int x = 3; x < rw - 3; ++x) {
-      int m = fast_m(roi + (size_t)y * stride + x, stride);
-      sc[(size_t)y * rw + x] = (m > t) ? (m - 1) : 0;
+      const uint8_t* p = roi + (size_t)y * stride + x;
+      if (!fast_is_corner(p, stride, t)) continue;
+      sc[(size_t)y * rw + x] = fast_m(p, stride) - 1;   // m > t >= 0
+      any = true;
     }
+  if (!any) return;
   for (int y = 3; y < rh - 3; ++y)
     for (int x = 3; x < rw - 3; ++x) {
       const int* r = &sc[(size_t)y * rw + x];

@@ -16,7 +16,8 @@ assert KP_DTYPE.itemsize == 28
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("orb_ref.cpp", "match_ref.cpp", "occ_ref.cpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("orb_ref.cpp", "match_ref.cpp", "occ_ref.cpp", "pipeline_ref.cpp",
+                                             "Makefile")]
     if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return _SO
@@ -194,3 +195,102 @@ def stereo_unproject(kps, depth, Tcw, fx, fy, cx, cy, bf):
     _mlib().frame_ref_stereo_unproject(_p(kf), 7, n, _p(depth), depth.shape[0], depth.shape[1], _p(T), fx, fy, cx, cy,
                                        bf, _p(ur), _p(dp), _p(xw), _p(va))
     return ur, dp, xw, va
+
+
+def pipeline_run(gray, depth, Tcw, nthreads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, fx=535.4,
+                 fy=539.2, cx=320.1, cy=247.6, bf=40.0, th=15.0, nnratio=0.9, check_ori=True, last_obs=1):
+    """Multi-threaded CPU baseline (oracle/pipeline_ref.cpp) -> (seconds, nkp, nmatch)."""
+    L = lib()
+    L.pipeline_ref_run.restype = C.c_double
+    L.pipeline_ref_run.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + \
+        [C.c_float] * 7 + [C.c_int] * 3 + [C.c_void_p] * 2
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16)
+    n, rows, cols = gray.shape
+    nkp = np.zeros(n, np.int32)
+    nm = np.zeros(n, np.int32)
+    sec = L.pipeline_ref_run(_p(gray), _p(depth), _p(T), n, rows, cols, nfeatures, scale, nlevels, ini_th, min_th, fx, fy,
+                             cx, cy, bf, th, nnratio, int(check_ori), last_obs, nthreads, _p(nkp), _p(nm))
+    return sec, nkp, nm
+
+
+# ------------------------------------------------------------------------------------------------
+# occupancy oracle (oracle/occ_ref.cpp)
+# ------------------------------------------------------------------------------------------------
+class RefOccupancy:
+    def __init__(self, **kw):
+        from orb_slam2_ssd_semantic_b200._abi import OcmParams
+        L = lib()
+        L.occ_ref_create.restype = C.c_void_p
+        L.occ_ref_create.argtypes = [C.POINTER(OcmParams)]
+        L.occ_ref_destroy.argtypes = [C.c_void_p]
+        L.occ_ref_default_params.argtypes = [C.POINTER(OcmParams)]
+        L.occ_ref_constants.argtypes = [C.c_void_p, C.c_void_p]
+        L.occ_ref_insert_keyframe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p] + \
+            [C.c_float] * 4 + [C.c_void_p]
+        L.occ_ref_last_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.occ_ref_num_leaves.restype = C.c_longlong
+        L.occ_ref_num_leaves.argtypes = [C.c_void_p]
+        L.occ_ref_export_leaves.restype = C.c_longlong
+        L.occ_ref_export_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+        L.occ_ref_ray.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        self.L = L
+        p = OcmParams()
+        L.occ_ref_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self.params = p
+        self.h = C.c_void_p(L.occ_ref_create(C.byref(p)))
+
+    def __del__(self):
+        try:
+            self.L.occ_ref_destroy(self.h)
+        except Exception:
+            pass
+
+    def constants(self):
+        out = np.zeros(4, np.float32)
+        self.L.occ_ref_constants(self.h, _p(out))
+        return out   # hit, miss, clamp_min, clamp_max (log-odds)
+
+    def insert_keyframe(self, Tcw, depth, rgb, fx, fy, cx, cy, ground_label=None):
+        depth = np.ascontiguousarray(depth, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        lab = None if ground_label is None else np.ascontiguousarray(ground_label, np.uint8)
+        return self.L.occ_ref_insert_keyframe(self.h, _p(depth), _p(rgb), depth.shape[0], depth.shape[1], _p(T), fx, fy,
+                                              cx, cy, None if lab is None else _p(lab))
+
+    def last_points(self):
+        cap = 1 << 20
+        xyz = np.zeros((cap, 3), np.float32)
+        rgb = np.zeros((cap, 3), np.uint8)
+        lab = np.zeros(cap, np.uint8)
+        n = self.L.occ_ref_last_points(self.h, _p(xyz), _p(rgb), _p(lab), cap)
+        return xyz[:n].copy(), rgb[:n].copy(), lab[:n].copy()
+
+    def export_leaves(self):
+        n = self.L.occ_ref_num_leaves(self.h)
+        keys = np.zeros((max(n, 1), 3), np.uint16)
+        lo = np.zeros(max(n, 1), np.float32)
+        m = self.L.occ_ref_export_leaves(self.h, _p(keys), _p(lo), n)
+        return keys[:m], lo[:m]
+
+    def ray(self, origin, end):
+        o = np.ascontiguousarray(origin, np.float32)
+        e = np.ascontiguousarray(end, np.float32)
+        keys = np.zeros((4096, 3), np.uint16)
+        n = self.L.occ_ref_ray(self.h, _p(o), _p(e), _p(keys), 4096)
+        return None if n < 0 else keys[:n].copy()
+
+
+def backproject_all(depth, Tcw, fx, fy, cx, cy):
+    """T variant (src/pointcloudmapping.cc:131-194): every pixel, no gate -> rows*cols x 3 world points."""
+    L = lib()
+    L.occ_ref_backproject_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p] + [C.c_float] * 4 + [C.c_void_p]
+    depth = np.ascontiguousarray(depth, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    out = np.zeros((depth.size, 3), np.float32)
+    L.occ_ref_backproject_all(_p(depth), depth.shape[0], depth.shape[1], _p(T), fx, fy, cx, cy, _p(out))
+    return out

@@ -14,7 +14,7 @@ class B200OrbError(RuntimeError):
         self.code = code
 
 
-from ._abi import OrbmFrame, OrbmLast, OrbsParams, OrbxParams  # noqa: E402,F401
+from ._abi import OcmParams, OrbmFrame, OrbmLast, OrbsParams, OrbxParams  # noqa: E402,F401
 
 
 _lib = None
@@ -29,6 +29,9 @@ EXPORTS = [
     "orbm_hamming", "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_search_by_projection_last",
     "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
     "orbs_stream", "orbs_launch_count", "orbs_extractor",
+    "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device",
+    "ocm_last_points", "ocm_num_leaves", "ocm_export_leaves", "ocm_query", "ocm_summary_count",
+    "ocm_export_summaries_device", "ocm_apply_summaries_device", "ocm_sync", "ocm_stream", "ocm_launch_count",
 ]
 
 
@@ -89,6 +92,26 @@ def lib() -> C.CDLL:
     L.orbs_launch_count.restype = C.c_longlong
     L.orbs_extractor.argtypes = [vp]
     L.orbs_extractor.restype = vp
+    f = C.c_float
+    L.ocm_create.argtypes = [C.POINTER(OcmParams), i, C.POINTER(vp)]
+    L.ocm_destroy.argtypes = [vp]
+    L.ocm_destroy.restype = None
+    L.ocm_insert_keyframe.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f, vp]
+    L.ocm_insert_keyframe_device.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f, vp]
+    L.ocm_last_points.argtypes = [vp, vp, vp, i, C.POINTER(i)]
+    L.ocm_num_leaves.argtypes = [vp]
+    L.ocm_num_leaves.restype = C.c_int64
+    L.ocm_export_leaves.argtypes = [vp, vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.ocm_query.argtypes = [vp, vp, C.POINTER(f), C.POINTER(i)]
+    L.ocm_summary_count.argtypes = [vp]
+    L.ocm_summary_count.restype = C.c_int64
+    L.ocm_export_summaries_device.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    L.ocm_apply_summaries_device.argtypes = [vp, vp, vp, vp, vp, C.c_int64]
+    L.ocm_sync.argtypes = [vp]
+    L.ocm_stream.argtypes = [vp]
+    L.ocm_stream.restype = vp
+    L.ocm_launch_count.argtypes = [vp]
+    L.ocm_launch_count.restype = C.c_longlong
     _lib = L
     return L
 

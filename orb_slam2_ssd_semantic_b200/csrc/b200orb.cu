@@ -2,3 +2,4 @@
 #include "orbx.cu"
 #include "orbm.cu"
 #include "orbs.cu"
+#include "ocm.cu"

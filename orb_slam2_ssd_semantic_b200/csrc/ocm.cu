@@ -1,0 +1,724 @@
+// ocm.cu -- keyframe RGB-D -> point cloud -> occupancy (OctoMap log-odds) on sm_100a.
+// Reference: MapDrawer::GeneratePointCloud / InsertScan / ctor params (perfect/src/MapDrawer.cc:641-675, 946-1025,
+// 51-56), UpdateOctomap's sensor-origin quirk (:619,631-632), PointCloudMapping::insertKeyFrame (class surface,
+// include/pointcloudmapping.h:50-56).  Third-party semantics (PCL VoxelGrid, pcl::transformPointCloud, octomap
+// keys / computeRayKeys / updateNode) follow oracle/occ_ref.cpp, which states them.
+//
+// HBM layout:
+//   leaf table   open-addressing hash of the 1-cm VoxelGrid cells of ONE keyframe (key = 3 x 21-bit cell index):
+//                count, first pixel, bucket offset, cursor.  Pixels of a cell are bucketed, sorted ascending and
+//                summed sequentially in float so the centroid equals the oracle's pixel-order sum bit for bit.
+//   points       world-frame centroids of the last keyframe (xyz f32, rgb, ground label), unordered
+//   scan sets    two open-addressing key sets per scan: occupied endpoints and free ray cells
+//   map          persistent open-addressing hash: key (3 x u16 OcTreeKey packed in u64) -> float log-odds, colour and
+//                the clamp-add summary (a, lo, hi) used by the multi-GPU merge
+#include <new>
+
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+
+__device__ __forceinline__ unsigned long long hash64(unsigned long long k) {   // splitmix64 finaliser
+  k ^= k >> 30; k *= 0xbf58476d1ce4e5b9ull;
+  k ^= k >> 27; k *= 0x94d049bb133111ebull;
+  k ^= k >> 31;
+  return k;
+}
+
+// find-or-insert; returns slot or -1 when the table is full
+__device__ __forceinline__ long long table_insert(unsigned long long* keys, long long cap_mask, unsigned long long key) {
+  long long s = (long long)(hash64(key) & (unsigned long long)cap_mask);
+  for (long long probe = 0; probe <= cap_mask; ++probe) {
+    const unsigned long long cur = keys[s];
+    if (cur == key) return s;
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&keys[s], EMPTY_KEY, key);
+      if (old == EMPTY_KEY || old == key) return s;
+    }
+    s = (s + 1) & cap_mask;
+  }
+  return -1;
+}
+
+__device__ __forceinline__ long long table_find(const unsigned long long* keys, long long cap_mask, unsigned long long key) {
+  long long s = (long long)(hash64(key) & (unsigned long long)cap_mask);
+  for (long long probe = 0; probe <= cap_mask; ++probe) {
+    const unsigned long long cur = keys[s];
+    if (cur == key) return s;
+    if (cur == EMPTY_KEY) return -1;
+    s = (s + 1) & cap_mask;
+  }
+  return -1;
+}
+
+struct OcmConst {
+  float fx, fy, cx, cy;
+  float depth_min, depth_max, y_max, leaf, inv_leaf;
+  double res, res_factor;
+  float hit_log, miss_log, cmin, cmax;
+  double Rt[9], ti[3];     // Twc = inverse of Tcw, double (pcl::transformPointCloud<.., double>)
+  float origin[3];         // translation of Tcw (UpdateOctomap quirk)
+  int rows, cols;
+};
+
+struct LeafTable {
+  unsigned long long* keys;
+  int* count;
+  int* first;     // smallest pixel index
+  int* offset;
+  int* cursor;
+  long long mask;
+};
+
+__device__ __forceinline__ bool backproject(const OcmConst& c, const float* __restrict__ depth, int pix, float& x,
+                                            float& y, float& z) {
+  const int m = pix / c.cols, n = pix - m * c.cols;
+  const float d = depth[pix];
+  if (d < c.depth_min || d > c.depth_max) return false;       // MapDrawer.cc:655 (NaN fails neither test: kept like the reference)
+  z = d;
+  x = ((float)n - c.cx) * z / c.fx;                           // :658-659 (float, true division; --fmad=false)
+  y = ((float)m - c.cy) * z / c.fy;
+  if (y < -c.y_max || y > c.y_max) return false;             // :660
+  return true;
+}
+
+__device__ __forceinline__ unsigned long long leaf_key(const OcmConst& c, float x, float y, float z) {
+  const long long ix = (long long)floorf(x * c.inv_leaf) + (1 << 20);
+  const long long iy = (long long)floorf(y * c.inv_leaf) + (1 << 20);
+  const long long iz = (long long)floorf(z * c.inv_leaf) + (1 << 20);
+  return (unsigned long long)(ix & 0x1fffff) | ((unsigned long long)(iy & 0x1fffff) << 21) |
+         ((unsigned long long)(iz & 0x1fffff) << 42);
+}
+
+// K11a: gate + VoxelGrid cell of every pixel
+__global__ void k_ocm_bin(OcmConst c, const float* __restrict__ depth, LeafTable lt, int* __restrict__ pix_slot,
+                          int* __restrict__ err) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= c.rows * c.cols) return;
+  float x, y, z;
+  int slot = -1;
+  if (backproject(c, depth, pix, x, y, z)) {
+    const long long s = table_insert(lt.keys, lt.mask, leaf_key(c, x, y, z));
+    if (s < 0) { atomicExch(err, 1); }
+    else {
+      slot = (int)s;
+      atomicAdd(&lt.count[s], 1);
+      atomicMin(&lt.first[s], pix);
+    }
+  }
+  pix_slot[pix] = slot;
+}
+
+// K11b: bucket ranges for the used cells (arbitrary order: the cloud is a set)
+__global__ void k_ocm_ranges(LeafTable lt, long long nslots, int* __restrict__ counters /*[0]=pixels,[1]=voxels*/,
+                             int* __restrict__ voxlist) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const int cn = lt.count[s];
+  if (cn > 0) {
+    lt.offset[s] = atomicAdd(&counters[0], cn);
+    voxlist[atomicAdd(&counters[1], 1)] = (int)s;
+  }
+}
+
+// K11c: scatter the pixel indices into their cell's bucket
+__global__ void k_ocm_scatter(int npix, const int* __restrict__ pix_slot, LeafTable lt, int* __restrict__ bucket) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= npix) return;
+  const int s = pix_slot[pix];
+  if (s >= 0) bucket[lt.offset[s] + atomicAdd(&lt.cursor[s], 1)] = pix;
+}
+
+// K11d: per cell: restore pixel order, sequential float centroid (PCL VoxelGrid), transform to the world frame in
+// double (pcl::transformPointCloud), emit the point; also resets the cell's table entry for the next keyframe.
+__global__ void k_ocm_centroids(OcmConst c, const float* __restrict__ depth, const uint8_t* __restrict__ rgb,
+                                const uint8_t* __restrict__ label, LeafTable lt, const int* __restrict__ counters,
+                                const int* __restrict__ voxlist, int* __restrict__ bucket, float* __restrict__ pts,
+                                uint8_t* __restrict__ pts_rgb, uint8_t* __restrict__ pts_label) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= counters[1]) return;
+  const int s = voxlist[v];
+  const int n = lt.count[s];
+  int* b = bucket + lt.offset[s];
+  for (int i = 1; i < n; ++i) {   // insertion sort: ascending pixel index = row-major order
+    const int val = b[i];
+    int j = i - 1;
+    while (j >= 0 && b[j] > val) { b[j + 1] = b[j]; --j; }
+    b[j + 1] = val;
+  }
+  float sx = 0.f, sy = 0.f, sz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float x, y, z;
+    backproject(c, depth, b[i], x, y, z);
+    sx += x; sy += y; sz += z;
+    const uint8_t* col = rgb + (size_t)b[i] * 3;   // b,g,r (cv::Mat BGR)
+    sr += (float)col[2]; sg += (float)col[1]; sb += (float)col[0];
+  }
+  const float fn = (float)n;
+  const double px = (double)(sx / fn), py = (double)(sy / fn), pz = (double)(sz / fn);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    pts[(size_t)v * 3 + i] = (float)(c.Rt[i * 3 + 0] * px + c.Rt[i * 3 + 1] * py + c.Rt[i * 3 + 2] * pz + c.ti[i]);
+  pts_rgb[(size_t)v * 3 + 0] = (uint8_t)(sr / fn);
+  pts_rgb[(size_t)v * 3 + 1] = (uint8_t)(sg / fn);
+  pts_rgb[(size_t)v * 3 + 2] = (uint8_t)(sb / fn);
+  pts_label[v] = label ? label[lt.first[s]] : 0;
+  lt.keys[s] = EMPTY_KEY; lt.count[s] = 0; lt.first[s] = 0x7fffffff; lt.cursor[s] = 0;
+}
+
+// leaf <= 0: no VoxelGrid; every gated pixel is a point (used for the T-variant style clouds)
+__global__ void k_ocm_points_nofilter(OcmConst c, const float* __restrict__ depth, const uint8_t* __restrict__ rgb,
+                                      const uint8_t* __restrict__ label, int* __restrict__ counters,
+                                      float* __restrict__ pts, uint8_t* __restrict__ pts_rgb,
+                                      uint8_t* __restrict__ pts_label) {
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= c.rows * c.cols) return;
+  float x, y, z;
+  if (!backproject(c, depth, pix, x, y, z)) return;
+  const int v = atomicAdd(&counters[1], 1);
+  const double px = x, py = y, pz = z;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    pts[(size_t)v * 3 + i] = (float)(c.Rt[i * 3 + 0] * px + c.Rt[i * 3 + 1] * py + c.Rt[i * 3 + 2] * pz + c.ti[i]);
+  const uint8_t* col = rgb + (size_t)pix * 3;
+  pts_rgb[(size_t)v * 3 + 0] = col[2]; pts_rgb[(size_t)v * 3 + 1] = col[1]; pts_rgb[(size_t)v * 3 + 2] = col[0];
+  pts_label[v] = label ? label[pix] : 0;
+}
+
+__device__ __forceinline__ bool coord_to_key(const OcmConst& c, float coord, int& k) {   // coordToKeyChecked
+  const int s = (int)floor(c.res_factor * (double)coord) + 32768;
+  k = s;
+  return s >= 0 && s < 65536;
+}
+__device__ __forceinline__ unsigned long long pack_key(int kx, int ky, int kz) {
+  return (unsigned long long)kx | ((unsigned long long)ky << 16) | ((unsigned long long)kz << 32);
+}
+
+struct KeySet {
+  unsigned long long* keys;
+  long long mask;
+};
+
+// K12/K13: per point -> occupied endpoint key, or (ground) the free cells along the ray (computeRayKeys)
+__global__ void k_ocm_scan_keys(OcmConst c, const int* __restrict__ counters, const float* __restrict__ pts,
+                                const uint8_t* __restrict__ pts_label, const uint8_t* __restrict__ pts_rgb,
+                                KeySet occ, unsigned* __restrict__ occ_rgb, KeySet fre, int* __restrict__ err) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= counters[1]) return;
+  const float e[3] = {pts[(size_t)v * 3], pts[(size_t)v * 3 + 1], pts[(size_t)v * 3 + 2]};
+  int ke[3];
+  const bool end_ok = coord_to_key(c, e[0], ke[0]) && coord_to_key(c, e[1], ke[1]) && coord_to_key(c, e[2], ke[2]);
+  if (!pts_label[v]) {
+    if (end_ok) {
+      const long long s = table_insert(occ.keys, occ.mask, pack_key(ke[0], ke[1], ke[2]));
+      if (s < 0) atomicExch(err, 2);
+      else occ_rgb[s] = (unsigned)pts_rgb[(size_t)v * 3] | ((unsigned)pts_rgb[(size_t)v * 3 + 1] << 8) |
+                        ((unsigned)pts_rgb[(size_t)v * 3 + 2] << 16);
+    }
+    return;
+  }
+  int ko[3];
+  if (!end_ok || !coord_to_key(c, c.origin[0], ko[0]) || !coord_to_key(c, c.origin[1], ko[1]) ||
+      !coord_to_key(c, c.origin[2], ko[2]))
+    return;
+  if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return;
+  if (table_insert(fre.keys, fre.mask, pack_key(ko[0], ko[1], ko[2])) < 0) atomicExch(err, 3);
+  float dir[3] = {e[0] - c.origin[0], e[1] - c.origin[1], e[2] - c.origin[2]};
+  double n2 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) n2 += (double)(dir[i] * dir[i]);
+  const float length = (float)sqrt(n2);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) dir[i] = dir[i] / length;
+  int step[3], cur[3] = {ko[0], ko[1], ko[2]};
+  double tMax[3], tDelta[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    step[i] = (dir[i] > 0.f) ? 1 : ((dir[i] < 0.f) ? -1 : 0);
+    if (step[i] != 0) {
+      double border = ((double)(cur[i] - 32768) + 0.5) * c.res;
+      border += (double)(float)((double)step[i] * c.res * 0.5);
+      tMax[i] = (border - (double)c.origin[i]) / (double)dir[i];
+      tDelta[i] = c.res / fabs((double)dir[i]);
+    } else {
+      tMax[i] = 1.7976931348623157e308;
+      tDelta[i] = 1.7976931348623157e308;
+    }
+  }
+  for (int guard = 0; guard < 3 * 65536; ++guard) {
+    int dim;
+    if (tMax[0] < tMax[1]) dim = (tMax[0] < tMax[2]) ? 0 : 2;
+    else dim = (tMax[1] < tMax[2]) ? 1 : 2;
+    // (no dynamic register indexing: unrolled select)
+    if (dim == 0) { cur[0] = (cur[0] + step[0]) & 0xffff; tMax[0] += tDelta[0]; }
+    else if (dim == 1) { cur[1] = (cur[1] + step[1]) & 0xffff; tMax[1] += tDelta[1]; }
+    else { cur[2] = (cur[2] + step[2]) & 0xffff; tMax[2] += tDelta[2]; }
+    if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
+    const double dist = fmin(fmin(tMax[0], tMax[1]), tMax[2]);
+    if (dist > (double)length) break;
+    if (table_insert(fre.keys, fre.mask, pack_key(cur[0], cur[1], cur[2])) < 0) { atomicExch(err, 3); break; }
+  }
+}
+
+struct MapView {
+  unsigned long long* keys;
+  float* val;
+  float *a, *lo, *hi;   // clamp-add summary since the last reset: f(x) = min(max(x + a, lo), hi)
+  unsigned* rgb;
+  int* nleaves;
+  long long mask;
+};
+
+__device__ __forceinline__ void map_update(const MapView& m, const OcmConst& c, unsigned long long key, bool occupied,
+                                           unsigned rgb, int* err) {
+  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  bool found = false;
+  for (long long probe = 0; probe <= m.mask; ++probe) {
+    const unsigned long long cur = m.keys[s];
+    if (cur == key) { found = true; break; }
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&m.keys[s], EMPTY_KEY, key);
+      if (old == EMPTY_KEY) { atomicAdd(m.nleaves, 1); found = true; break; }
+      if (old == key) { found = true; break; }
+    }
+    s = (s + 1) & m.mask;
+  }
+  if (!found) { atomicExch(err, 4); return; }
+  // one update per key per scan: plain read-modify-write (updateNodeLogOdds)
+  const float d = occupied ? c.hit_log : c.miss_log;
+  float v = m.val[s] + d;
+  v = fminf(fmaxf(v, c.cmin), c.cmax);
+  m.val[s] = v;
+  m.a[s] = m.a[s] + d;
+  m.lo[s] = fminf(fmaxf(m.lo[s] + d, c.cmin), c.cmax);
+  m.hi[s] = fminf(fmaxf(m.hi[s] + d, c.cmin), c.cmax);
+  if (occupied) m.rgb[s] = rgb;
+}
+
+// K14: free \ occupied get a miss, occupied get a hit (MapDrawer.cc:1007-1022); clears the scan sets on the way
+__global__ void k_ocm_apply(OcmConst c, KeySet occ, const unsigned* __restrict__ occ_rgb, KeySet fre, MapView m,
+                            int* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= fre.mask) {
+    const unsigned long long k = fre.keys[i];
+    if (k != EMPTY_KEY && table_find(occ.keys, occ.mask, k) < 0) map_update(m, c, k, false, 0u, err);
+  }
+}
+__global__ void k_ocm_apply_occ(OcmConst c, KeySet occ, const unsigned* __restrict__ occ_rgb, MapView m,
+                                int* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= occ.mask) {
+    const unsigned long long k = occ.keys[i];
+    if (k != EMPTY_KEY) map_update(m, c, k, true, occ_rgb[i], err);
+  }
+}
+__global__ void k_ocm_clear_sets(KeySet occ, KeySet fre) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= occ.mask) occ.keys[i] = EMPTY_KEY;
+  if (i <= fre.mask) fre.keys[i] = EMPTY_KEY;
+}
+
+__global__ void k_ocm_fill_u64(unsigned long long* p, unsigned long long v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_ocm_fill_i32(int* p, int v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void k_ocm_fill_f32(float* p, float v, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// export: compact the map (or its summaries) into dense arrays
+__global__ void k_ocm_export(MapView m, long long* __restrict__ counter, long long cap, unsigned short* __restrict__ keys3,
+                             unsigned long long* __restrict__ keys64, float* __restrict__ val, unsigned char* __restrict__ rgb,
+                             float* __restrict__ a, float* __restrict__ lo, float* __restrict__ hi, int only_touched) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > m.mask) return;
+  const unsigned long long k = m.keys[i];
+  if (k == EMPTY_KEY) return;
+  if (only_touched && m.a[i] == 0.f && m.lo[i] == -INFINITY) return;
+  const long long o = (long long)atomicAdd((unsigned long long*)counter, 1ull);
+  if (o >= cap) return;
+  if (keys3) { keys3[o * 3] = (unsigned short)(k & 0xffff); keys3[o * 3 + 1] = (unsigned short)((k >> 16) & 0xffff); keys3[o * 3 + 2] = (unsigned short)((k >> 32) & 0xffff); }
+  if (keys64) keys64[o] = k;
+  if (val) val[o] = m.val[i];
+  if (rgb) { const unsigned c = m.rgb[i]; rgb[o * 3] = c & 0xff; rgb[o * 3 + 1] = (c >> 8) & 0xff; rgb[o * 3 + 2] = (c >> 16) & 0xff; }
+  if (a) { a[o] = m.a[i]; lo[o] = m.lo[i]; hi[o] = m.hi[i]; }
+}
+
+// merge: apply a later shard's per-voxel clamp-add summaries onto this map
+__global__ void k_ocm_apply_summaries(OcmConst c, MapView m, const unsigned long long* __restrict__ keys,
+                                      const float* __restrict__ a, const float* __restrict__ lo,
+                                      const float* __restrict__ hi, long long n, int* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  bool found = false;
+  for (long long probe = 0; probe <= m.mask; ++probe) {
+    const unsigned long long cur = m.keys[s];
+    if (cur == key) { found = true; break; }
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&m.keys[s], EMPTY_KEY, key);
+      if (old == EMPTY_KEY) { atomicAdd(m.nleaves, 1); found = true; break; }
+      if (old == key) { found = true; break; }
+    }
+    s = (s + 1) & m.mask;
+  }
+  if (!found) { atomicExch(err, 4); return; }
+  // value: v <- g(v); summary: f <- g o f  with g = (a, lo, hi)
+  const float ga = a[i], gl = lo[i], gh = hi[i];
+  m.val[s] = fminf(fmaxf(m.val[s] + ga, gl), gh);
+  m.a[s] = m.a[s] + ga;
+  m.lo[s] = fminf(fmaxf(m.lo[s] + ga, gl), gh);
+  m.hi[s] = fminf(fmaxf(m.hi[s] + ga, gl), gh);
+}
+
+__global__ void k_ocm_query(MapView m, unsigned long long key, float* out, int* found) {
+  const long long s = table_find(m.keys, m.mask, key);
+  *found = s >= 0;
+  *out = s >= 0 ? m.val[s] : 0.f;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct ocm {
+  OcmParams prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  float hit_log, miss_log, cmin, cmax;
+  // map
+  MapView map{};
+  long long map_cap = 0;
+  // per-keyframe scratch
+  int rows = 0, cols = 0;
+  LeafTable leaf{};
+  long long leaf_cap = 0;
+  int *d_pix_slot = nullptr, *d_bucket = nullptr, *d_voxlist = nullptr, *d_counters = nullptr, *d_err = nullptr;
+  float* d_pts = nullptr;
+  uint8_t *d_pts_rgb = nullptr, *d_pts_label = nullptr;
+  KeySet occ{}, fre{};
+  unsigned* d_occ_rgb = nullptr;
+  float* d_depth = nullptr;
+  uint8_t *d_rgb = nullptr, *d_label = nullptr;
+  int last_points = 0;
+  long long* d_export_counter = nullptr;
+
+  ~ocm() {
+    DeviceGuard g(device);
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves);
+    free_scratch();
+    F(d_counters); F(d_err); F(d_export_counter);
+    if (stream) cudaStreamDestroy(stream);
+  }
+  void free_scratch() {
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(leaf.keys); F(leaf.count); F(leaf.first); F(leaf.offset); F(leaf.cursor); F(d_pix_slot); F(d_bucket); F(d_voxlist);
+    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label);
+    leaf = LeafTable{}; d_pix_slot = d_bucket = d_voxlist = nullptr; d_pts = nullptr; d_pts_rgb = d_pts_label = nullptr;
+    occ = KeySet{}; fre = KeySet{}; d_occ_rgb = nullptr; d_depth = nullptr; d_rgb = d_label = nullptr;
+  }
+  template <class T>
+  int fill(T* p, T v, long long n);
+  int ensure_scratch(int r, int c);
+  int insert(const float* dd, const uint8_t* drgb, const uint8_t* dlabel, int r, int c, const float* Tcw, float fx,
+             float fy, float cx, float cy);
+  int check_err();
+};
+
+template <>
+int ocm::fill<unsigned long long>(unsigned long long* p, unsigned long long v, long long n) {
+  k_ocm_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, v, n);
+  ++launches;
+  return B200ORB_OK;
+}
+template <>
+int ocm::fill<int>(int* p, int v, long long n) {
+  k_ocm_fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, v, n);
+  ++launches;
+  return B200ORB_OK;
+}
+template <>
+int ocm::fill<float>(float* p, float v, long long n) {
+  k_ocm_fill_f32<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, v, n);
+  ++launches;
+  return B200ORB_OK;
+}
+
+static long long pow2_at_least(long long v) {
+  long long p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+int ocm::ensure_scratch(int r, int c) {
+  if (r == rows && c == cols) return B200ORB_OK;
+  B200_CUDA(cudaStreamSynchronize(stream));
+  free_scratch();
+  rows = r; cols = c;
+  const long long npix = (long long)r * c;
+  leaf_cap = pow2_at_least(2 * npix);
+  leaf.mask = leaf_cap - 1;
+  B200_CUDA(cudaMalloc(&leaf.keys, 8 * leaf_cap)); B200_CUDA(cudaMalloc(&leaf.count, 4 * leaf_cap));
+  B200_CUDA(cudaMalloc(&leaf.first, 4 * leaf_cap)); B200_CUDA(cudaMalloc(&leaf.offset, 4 * leaf_cap));
+  B200_CUDA(cudaMalloc(&leaf.cursor, 4 * leaf_cap));
+  B200_CUDA(cudaMalloc(&d_pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&d_bucket, 4 * npix));
+  B200_CUDA(cudaMalloc(&d_voxlist, 4 * npix));
+  B200_CUDA(cudaMalloc(&d_pts, 12 * npix)); B200_CUDA(cudaMalloc(&d_pts_rgb, 3 * npix)); B200_CUDA(cudaMalloc(&d_pts_label, npix));
+  const long long occ_cap = pow2_at_least(2 * npix), fre_cap = pow2_at_least(8 * npix);
+  occ.mask = occ_cap - 1; fre.mask = fre_cap - 1;
+  B200_CUDA(cudaMalloc(&occ.keys, 8 * occ_cap)); B200_CUDA(cudaMalloc(&fre.keys, 8 * fre_cap));
+  B200_CUDA(cudaMalloc(&d_occ_rgb, 4 * occ_cap));
+  fill(leaf.keys, EMPTY_KEY, leaf_cap); fill(leaf.count, 0, leaf_cap); fill(leaf.first, 0x7fffffff, leaf_cap);
+  fill(leaf.cursor, 0, leaf_cap); fill(occ.keys, EMPTY_KEY, occ_cap); fill(fre.keys, EMPTY_KEY, fre_cap);
+  B200_CUDA(cudaGetLastError());
+  return B200ORB_OK;
+}
+
+int ocm::check_err() {
+  int e = 0;
+  B200_CUDA(cudaMemcpyAsync(&e, d_err, 4, cudaMemcpyDeviceToHost, stream));
+  B200_CUDA(cudaStreamSynchronize(stream));
+  if (e) {
+    B200_CUDA(cudaMemsetAsync(d_err, 0, 4, stream));
+    static const char* what[] = {"", "VoxelGrid table full", "occupied set full", "free set full", "map full (raise OcmParams.map_capacity)"};
+    set_error("occupancy insert: %s", what[e < 5 ? e : 0]);
+    return B200ORB_ECAP;
+  }
+  return B200ORB_OK;
+}
+
+int ocm::insert(const float* dd, const uint8_t* drgb, const uint8_t* dlabel, int r, int c, const float* Tcw, float fx,
+                float fy, float cx, float cy) {
+  B200_CHECK(ensure_scratch(r, c));
+  OcmConst k;
+  memset(&k, 0, sizeof(k));
+  k.fx = fx; k.fy = fy; k.cx = cx; k.cy = cy;
+  k.depth_min = prm.depth_min; k.depth_max = prm.depth_max; k.y_max = prm.y_max; k.leaf = prm.leaf;
+  k.inv_leaf = prm.leaf > 0 ? 1.0f / prm.leaf : 0.f;
+  k.res = prm.resolution; k.res_factor = 1.0 / prm.resolution;
+  k.hit_log = hit_log; k.miss_log = miss_log; k.cmin = cmin; k.cmax = cmax;
+  double R[9], t[3];
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)Tcw[i * 4 + j]; t[i] = (double)Tcw[i * 4 + 3]; }
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) k.Rt[i * 3 + j] = R[j * 3 + i];
+    k.ti[i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+  }
+  k.origin[0] = Tcw[3]; k.origin[1] = Tcw[7]; k.origin[2] = Tcw[11];
+  k.rows = r; k.cols = c;
+  const int npix = r * c;
+  B200_CUDA(cudaMemsetAsync(d_counters, 0, 8, stream));
+  if (prm.leaf > 0) {
+    k_ocm_bin<<<(npix + 255) / 256, 256, 0, stream>>>(k, dd, leaf, d_pix_slot, d_err);
+    k_ocm_ranges<<<(unsigned)((leaf_cap + 255) / 256), 256, 0, stream>>>(leaf, leaf_cap, d_counters, d_voxlist);
+    k_ocm_scatter<<<(npix + 255) / 256, 256, 0, stream>>>(npix, d_pix_slot, leaf, d_bucket);
+    k_ocm_centroids<<<(npix + 127) / 128, 128, 0, stream>>>(k, dd, drgb, dlabel, leaf, d_counters, d_voxlist, d_bucket,
+                                                          d_pts, d_pts_rgb, d_pts_label);
+    launches += 4;
+  } else {
+    k_ocm_points_nofilter<<<(npix + 255) / 256, 256, 0, stream>>>(k, dd, drgb, dlabel, d_counters, d_pts, d_pts_rgb, d_pts_label);
+    launches += 1;
+  }
+  k_ocm_scan_keys<<<(npix + 127) / 128, 128, 0, stream>>>(k, d_counters, d_pts, d_pts_label, d_pts_rgb, occ, d_occ_rgb, fre, d_err);
+  const long long big = std::max(occ.mask, fre.mask) + 1;
+  k_ocm_apply<<<(unsigned)((fre.mask + 256) / 256), 256, 0, stream>>>(k, occ, d_occ_rgb, fre, map, d_err);
+  k_ocm_apply_occ<<<(unsigned)((occ.mask + 256) / 256), 256, 0, stream>>>(k, occ, d_occ_rgb, map, d_err);
+  k_ocm_clear_sets<<<(unsigned)((big + 255) / 256), 256, 0, stream>>>(occ, fre);
+  launches += 4;
+  B200_CUDA(cudaGetLastError());
+  return B200ORB_OK;
+}
+
+extern "C" {
+
+void ocm_default_params(OcmParams* p) {
+  if (!p) return;
+  p->resolution = 0.05; p->prob_hit = 0.7; p->prob_miss = 0.4; p->clamp_min = 0.12; p->clamp_max = 0.97;
+  p->depth_min = 0.5f; p->depth_max = 3.0f; p->y_max = 3.0f; p->leaf = 0.01f; p->map_capacity = 0;
+}
+
+int ocm_create(const OcmParams* p, int device, ocm_t** out) {
+  if (!p || !out) { set_error("null argument"); return B200ORB_EINVAL; }
+  *out = nullptr;
+  if (!(p->resolution > 0) || !(p->prob_hit > 0 && p->prob_hit < 1) || !(p->prob_miss > 0 && p->prob_miss < 1) ||
+      !(p->clamp_min > 0 && p->clamp_min < p->clamp_max && p->clamp_max < 1)) {
+    set_error("bad OcmParams");
+    return B200ORB_EINVAL;
+  }
+  B200_CHECK(check_device(device));
+  DeviceGuard g(device);
+  ocm* h = new (std::nothrow) ocm();
+  if (!h) { set_error("out of host memory"); return B200ORB_EINVAL; }
+  h->prm = *p;
+  h->device = device;
+  auto logodds = [](double pr) { return (float)log(pr / (1 - pr)); };   // octomap::logodds (float)
+  h->hit_log = logodds(p->prob_hit); h->miss_log = logodds(p->prob_miss);
+  h->cmin = logodds(p->clamp_min); h->cmax = logodds(p->clamp_max);
+  h->map_cap = pow2_at_least(p->map_capacity > 0 ? p->map_capacity : (1ll << 23));
+  auto fail = [&](cudaError_t e) { set_error("ocm_create: %s", cudaGetErrorString(e)); delete h; return B200ORB_ECUDA; };
+  cudaError_t e;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+  const long long C = h->map_cap;
+  h->map.mask = C - 1;
+  if ((e = cudaMalloc(&h->map.keys, 8 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.val, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.a, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.lo, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.hi, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.rgb, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.nleaves, 4)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->d_counters, 8)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->d_export_counter, 8)) != cudaSuccess) return fail(e);
+  h->fill(h->map.keys, EMPTY_KEY, C); h->fill(h->map.val, 0.f, C); h->fill(h->map.a, 0.f, C);
+  h->fill(h->map.lo, -INFINITY, C); h->fill(h->map.hi, INFINITY, C);
+  cudaMemsetAsync(h->map.rgb, 0xff, 4 * C, h->stream);
+  cudaMemsetAsync(h->map.nleaves, 0, 4, h->stream);
+  cudaMemsetAsync(h->d_err, 0, 4, h->stream);
+  if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e);
+  *out = h;
+  return B200ORB_OK;
+}
+void ocm_destroy(ocm_t* h) { delete h; }
+
+int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
+                               const float Tcw[16], float fx, float fy, float cx, float cy, const uint8_t* d_label) {
+  if (!h || !d_depth || !d_rgb || !Tcw || rows <= 0 || cols <= 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  return h->insert(d_depth, d_rgb, d_label, rows, cols, Tcw, fx, fy, cx, cy);
+}
+
+int ocm_insert_keyframe(ocm_t* h, const float* depth, const uint8_t* rgb, int rows, int cols, const float Tcw[16],
+                        float fx, float fy, float cx, float cy, const uint8_t* ground_label) {
+  if (!h || !depth || !rgb || !Tcw || rows <= 0 || cols <= 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  B200_CHECK(h->ensure_scratch(rows, cols));
+  const size_t npix = (size_t)rows * cols;
+  if (!h->d_depth) {
+    B200_CUDA(cudaMalloc(&h->d_depth, npix * 4)); B200_CUDA(cudaMalloc(&h->d_rgb, npix * 3)); B200_CUDA(cudaMalloc(&h->d_label, npix));
+  }
+  B200_CUDA(cudaMemcpyAsync(h->d_depth, depth, npix * 4, cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA(cudaMemcpyAsync(h->d_rgb, rgb, npix * 3, cudaMemcpyHostToDevice, h->stream));
+  if (ground_label) B200_CUDA(cudaMemcpyAsync(h->d_label, ground_label, npix, cudaMemcpyHostToDevice, h->stream));
+  B200_CHECK(h->insert(h->d_depth, h->d_rgb, ground_label ? h->d_label : nullptr, rows, cols, Tcw, fx, fy, cx, cy));
+  return h->check_err();
+}
+
+int ocm_last_points(ocm_t* h, float* xyz, uint8_t* rgb, int cap, int* n) {
+  if (!h || !n) { set_error("null argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  int cnt[2] = {0, 0};
+  B200_CUDA(cudaMemcpyAsync(cnt, h->d_counters, 8, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  *n = cnt[1];
+  if (!xyz) return B200ORB_OK;
+  if (cnt[1] > cap) { set_error("cap %d < %d points", cap, cnt[1]); return B200ORB_ECAP; }
+  B200_CUDA(cudaMemcpyAsync(xyz, h->d_pts, (size_t)12 * cnt[1], cudaMemcpyDeviceToHost, h->stream));
+  if (rgb) B200_CUDA(cudaMemcpyAsync(rgb, h->d_pts_rgb, (size_t)3 * cnt[1], cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int64_t ocm_num_leaves(ocm_t* h) {
+  if (!h) return -1;
+  DeviceGuard g(h->device);
+  int n = 0;
+  if (cudaMemcpyAsync(&n, h->map.nleaves, 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+  cudaStreamSynchronize(h->stream);
+  return n;
+}
+
+static int export_common(ocm* h, int64_t cap, int64_t* n, unsigned short* d_k3, unsigned long long* d_k64, float* d_val,
+                         unsigned char* d_rgb, float* d_a, float* d_lo, float* d_hi, int only_touched) {
+  B200_CUDA(cudaMemsetAsync(h->d_export_counter, 0, 8, h->stream));
+  k_ocm_export<<<(unsigned)((h->map_cap + 255) / 256), 256, 0, h->stream>>>(h->map, h->d_export_counter, cap, d_k3, d_k64,
+                                                                          d_val, d_rgb, d_a, d_lo, d_hi, only_touched);
+  ++h->launches;
+  long long cnt = 0;
+  B200_CUDA(cudaMemcpyAsync(&cnt, h->d_export_counter, 8, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  if (n) *n = cnt;
+  if (cnt > cap) { set_error("export cap %lld < %lld entries", (long long)cap, cnt); return B200ORB_ECAP; }
+  return B200ORB_OK;
+}
+
+int ocm_export_leaves(ocm_t* h, uint16_t* keys, float* logodds, uint8_t* rgb, int64_t cap, int64_t* n) {
+  if (!h || !keys || !logodds || cap < 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  unsigned short* dk = nullptr; float* dv = nullptr; unsigned char* dc = nullptr;
+  const int64_t c = cap > 0 ? cap : 1;
+  B200_CUDA(cudaMalloc(&dk, 6 * c)); B200_CUDA(cudaMalloc(&dv, 4 * c)); B200_CUDA(cudaMalloc(&dc, 3 * c));
+  int64_t cnt = 0;
+  int rc = export_common(h, cap, &cnt, dk, nullptr, dv, dc, nullptr, nullptr, nullptr, 0);
+  if (rc == B200ORB_OK) {
+    cudaMemcpy(keys, dk, 6 * cnt, cudaMemcpyDeviceToHost);
+    cudaMemcpy(logodds, dv, 4 * cnt, cudaMemcpyDeviceToHost);
+    if (rgb) cudaMemcpy(rgb, dc, 3 * cnt, cudaMemcpyDeviceToHost);
+  }
+  if (n) *n = cnt;
+  cudaFree(dk); cudaFree(dv); cudaFree(dc);
+  return rc;
+}
+
+int ocm_query(ocm_t* h, const float xyz[3], float* logodds, int* found) {
+  if (!h || !xyz || !logodds || !found) { set_error("null argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  int k[3];
+  const double rf = 1.0 / h->prm.resolution;
+  for (int i = 0; i < 3; ++i) {
+    k[i] = (int)floor(rf * (double)xyz[i]) + 32768;
+    if (k[i] < 0 || k[i] >= 65536) { *found = 0; *logodds = 0; return B200ORB_OK; }
+  }
+  const unsigned long long key = (unsigned long long)k[0] | ((unsigned long long)k[1] << 16) | ((unsigned long long)k[2] << 32);
+  float* dv; int* df;
+  B200_CUDA(cudaMalloc(&dv, 4)); B200_CUDA(cudaMalloc(&df, 4));
+  k_ocm_query<<<1, 1, 0, h->stream>>>(h->map, key, dv, df);
+  ++h->launches;
+  cudaMemcpyAsync(logodds, dv, 4, cudaMemcpyDeviceToHost, h->stream);
+  cudaMemcpyAsync(found, df, 4, cudaMemcpyDeviceToHost, h->stream);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(dv); cudaFree(df);
+  return B200ORB_OK;
+}
+
+int64_t ocm_summary_count(ocm_t* h) { return ocm_num_leaves(h); }
+
+int ocm_export_summaries_device(ocm_t* h, uint64_t* d_keys, float* d_a, float* d_lo, float* d_hi, int64_t cap, int64_t* n) {
+  if (!h || !d_keys || !d_a || !d_lo || !d_hi) { set_error("null argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  return export_common(h, cap, n, nullptr, (unsigned long long*)d_keys, nullptr, nullptr, d_a, d_lo, d_hi, 1);
+}
+
+int ocm_apply_summaries_device(ocm_t* h, const uint64_t* d_keys, const float* d_a, const float* d_lo, const float* d_hi,
+                               int64_t n) {
+  if (!h || (n > 0 && (!d_keys || !d_a || !d_lo || !d_hi))) { set_error("null argument"); return B200ORB_EINVAL; }
+  if (n <= 0) return B200ORB_OK;
+  DeviceGuard g(h->device);
+  OcmConst k;
+  memset(&k, 0, sizeof(k));
+  k_ocm_apply_summaries<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(k, h->map, (const unsigned long long*)d_keys, d_a,
+                                                                          d_lo, d_hi, n, h->d_err);
+  ++h->launches;
+  B200_CUDA(cudaGetLastError());
+  return h->check_err();
+}
+
+int ocm_sync(ocm_t* h) {
+  if (!h) return B200ORB_EINVAL;
+  DeviceGuard g(h->device);
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return h->check_err();
+}
+void* ocm_stream(ocm_t* h) { return h ? (void*)h->stream : nullptr; }
+long long ocm_launch_count(const ocm_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

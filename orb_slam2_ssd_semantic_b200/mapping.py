@@ -1,0 +1,91 @@
+"""Host-side mirror of PointCloudMapping (reference include/pointcloudmapping.h:50-56) in its occupancy mode:
+insertKeyFrame() pushes one RGB-D keyframe through MapDrawer::GeneratePointCloud + InsertScan semantics
+(perfect/src/MapDrawer.cc:641-675, 946-1025) on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._abi import OcmParams, ptr
+
+
+class PointCloudMapping:
+    def __init__(self, resolution: float = 0.05, prob_hit=0.7, prob_miss=0.4, clamp_min=0.12, clamp_max=0.97,
+                 depth_min=0.5, depth_max=3.0, y_max=3.0, leaf=0.01, map_capacity=0, device: int = 0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.params = OcmParams(resolution, prob_hit, prob_miss, clamp_min, clamp_max, depth_min, depth_max, y_max, leaf,
+                                map_capacity)
+        _lib.check(self._L.ocm_create(C.byref(self.params), int(device), C.byref(self._h)))
+        self.resolution = float(resolution)
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.ocm_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    def shutdown(self):   # PointCloudMapping::shutdown (src/pointcloudmapping.cc:104-113): nothing to join here
+        _lib.check(self._L.ocm_sync(self._h))
+
+    def insertKeyFrame(self, Tcw, depth, rgb, fx, fy, cx, cy, ground_label=None):
+        """insertKeyFrame(kf, color, depth[, imgRGB]) (src/pointcloudmapping.cc:116-128): kf supplies GetPose() and the
+        intrinsics; depth f32 metres; rgb u8 BGR like cv::Mat."""
+        depth = np.ascontiguousarray(depth, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        lab = None if ground_label is None else np.ascontiguousarray(ground_label, np.uint8)
+        rows, cols = depth.shape
+        assert rgb.shape == (rows, cols, 3)
+        _lib.check(self._L.ocm_insert_keyframe(self._h, ptr(depth), ptr(rgb), rows, cols, ptr(T), float(fx), float(fy),
+                                               float(cx), float(cy), ptr(lab)))
+
+    def insert_keyframe_device(self, d_depth: int, d_rgb: int, rows: int, cols: int, Tcw, fx, fy, cx, cy, d_label: int = 0):
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        _lib.check(self._L.ocm_insert_keyframe_device(self._h, C.c_void_p(d_depth), C.c_void_p(d_rgb), rows, cols, ptr(T),
+                                                      float(fx), float(fy), float(cx), float(cy),
+                                                      C.c_void_p(d_label) if d_label else None))
+
+    def last_points(self):
+        n = C.c_int(0)
+        _lib.check(self._L.ocm_last_points(self._h, None, None, 0, C.byref(n)))
+        xyz = np.zeros((n.value, 3), np.float32)
+        rgb = np.zeros((n.value, 3), np.uint8)
+        if n.value:
+            _lib.check(self._L.ocm_last_points(self._h, ptr(xyz), ptr(rgb), n.value, C.byref(n)))
+        return xyz, rgb
+
+    def num_leaves(self) -> int:
+        return int(self._L.ocm_num_leaves(self._h))
+
+    def export_leaves(self):
+        n = self.num_leaves()
+        keys = np.zeros((max(n, 1), 3), np.uint16)
+        lo = np.zeros(max(n, 1), np.float32)
+        rgb = np.zeros((max(n, 1), 3), np.uint8)
+        cnt = C.c_int64(0)
+        _lib.check(self._L.ocm_export_leaves(self._h, ptr(keys), ptr(lo), ptr(rgb), n, C.byref(cnt)))
+        return keys[:cnt.value], lo[:cnt.value], rgb[:cnt.value]
+
+    def query(self, xyz):
+        p = np.ascontiguousarray(xyz, np.float32)
+        v, f = C.c_float(0), C.c_int(0)
+        _lib.check(self._L.ocm_query(self._h, ptr(p), C.byref(v), C.byref(f)))
+        return (v.value if f.value else None)
+
+    def sync(self):
+        _lib.check(self._L.ocm_sync(self._h))
+
+    def stream(self) -> int:
+        return int(self._L.ocm_stream(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self._L.ocm_launch_count(self._h))
+
+    @property
+    def handle(self):
+        return self._h

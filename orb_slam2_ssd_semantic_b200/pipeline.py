@@ -30,7 +30,25 @@ class StreamTracker:
         except Exception:
             pass
 
-    def track_batch(self, gray: np.ndarray, depth: np.ndarray, Tcw: np.ndarray):
+    def alloc_outputs(self, nframes: int, pinned: bool = False):
+        """Output buffers for track_batch (kps, desc, nkp, cur2last, nmatch); pinned=True uses page-locked host
+        memory (through torch) so the device->host copies are plain DMA."""
+        cap = self.cap
+        shapes = [((nframes, cap), KP_DTYPE), ((nframes, cap, 32), np.uint8), ((nframes,), np.int32),
+                  ((nframes, cap), np.int32), ((nframes,), np.int32)]
+        if not pinned:
+            return tuple(np.zeros(s, d) for s, d in shapes)
+        import torch
+        outs = []
+        self._pinned_keep = []
+        for s, d in shapes:
+            nbytes = int(np.prod(s)) * np.dtype(d).itemsize
+            t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            self._pinned_keep.append(t)
+            outs.append(t.numpy().view(d).reshape(s))
+        return tuple(outs)
+
+    def track_batch(self, gray: np.ndarray, depth: np.ndarray, Tcw: np.ndarray, out=None):
         """Host buffers in, host buffers out (the reference-facing call; copies are inside)."""
         gray = np.ascontiguousarray(gray, np.uint8)
         depth = np.ascontiguousarray(depth, np.float32)
@@ -38,11 +56,7 @@ class StreamTracker:
         F, rows, cols = gray.shape
         assert depth.shape == gray.shape and Tcw.shape[0] == F
         cap = self.cap
-        kps = np.zeros((F, cap), KP_DTYPE)
-        desc = np.zeros((F, cap, 32), np.uint8)
-        nkp = np.zeros(F, np.int32)
-        c2l = np.zeros((F, cap), np.int32)
-        nm = np.zeros(F, np.int32)
+        kps, desc, nkp, c2l, nm = out if out is not None else self.alloc_outputs(F)
         _lib.check(self._L.orbs_track_batch(self._h, ptr(gray), ptr(depth), ptr(Tcw), F, rows, cols, ptr(kps), ptr(desc),
                                             ptr(nkp), ptr(c2l), ptr(nm), cap))
         return kps, desc, nkp, c2l, nm

@@ -1,0 +1,99 @@
+"""GPU parity of the keyframe -> point cloud -> occupancy path vs the CPU oracle: points within 1e-5 (they are
+bit-equal by construction), leaf sets identical, log-odds within 1e-5."""
+import numpy as np
+import pytest
+
+from orb_slam2_ssd_semantic_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sorted_pts(xyz):
+    o = np.lexsort((xyz[:, 2], xyz[:, 1], xyz[:, 0]))
+    return xyz[o]
+
+
+def _leaf_dict(keys, lo):
+    k = keys.astype(np.uint64)
+    packed = k[:, 0] | (k[:, 1] << np.uint64(16)) | (k[:, 2] << np.uint64(32))
+    o = np.argsort(packed)
+    return packed[o], lo[o]
+
+
+def _scene(n):
+    ws = synth.WallStream(seed=99, n=n, depth0=2.0)
+    out = []
+    for t in range(n):
+        gray, depth, rgb, T = ws.frame(t * 7)
+        # add relief so rays / voxels vary: a tilted depth ramp + a box in front
+        yy, xx = np.mgrid[0:480, 0:640]
+        depth = (depth + 0.3 * np.sin(xx / 90.0) * np.cos(yy / 70.0)).astype(np.float32)
+        depth[100:200, 150:300] = 1.1
+        depth[::50, ::60] = 0.0      # invalid pixels
+        depth[300:320, 400:460] = 3.7   # beyond depth_max
+        out.append((depth, rgb, T))
+    return out
+
+
+@pytest.mark.parametrize("mode", ["nonground", "floor_ground"])
+def test_insert_keyframes_match_oracle(oracle, mode):
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    scene = _scene(5)
+    gpu = PointCloudMapping(0.05)
+    ref = oracle.RefOccupancy()
+    for depth, rgb, T in scene:
+        label = None
+        if mode == "floor_ground":
+            label = np.zeros(depth.shape, np.uint8)
+            label[300:, :] = 1          # lower image part is "ground": exercises the ray casting
+        gpu.insertKeyFrame(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY, label)
+        ref.insert_keyframe(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY, label)
+        pg, _ = gpu.last_points()
+        pr, _, _ = ref.last_points()
+        assert len(pg) == len(pr) and len(pr) > 1000
+        assert np.abs(_sorted_pts(pg) - _sorted_pts(pr)).max() <= 1e-5
+    kg, lg, _ = gpu.export_leaves()
+    kr, lr = ref.export_leaves()
+    pk_g, lo_g = _leaf_dict(kg, lg)
+    pk_r, lo_r = _leaf_dict(kr, lr)
+    assert len(pk_r) > 500
+    assert len(pk_g) == len(pk_r) and (pk_g == pk_r).all()
+    assert np.abs(lo_g - lo_r).max() <= 1e-5
+    assert gpu.num_leaves() == len(pk_r)
+    if mode == "floor_ground":
+        assert (lo_r < 0).sum() > 100     # free cells were carved
+
+
+def test_clamping_and_query(oracle):
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    depth, rgb, T = _scene(1)[0]
+    gpu = PointCloudMapping(0.05)
+    ref = oracle.RefOccupancy()
+    for _ in range(8):   # same keyframe over and over: values must saturate at the clamp
+        gpu.insertKeyFrame(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY)
+        ref.insert_keyframe(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY)
+    kg, lg, _ = gpu.export_leaves()
+    kr, lr = ref.export_leaves()
+    a, b = _leaf_dict(kg, lg), _leaf_dict(kr, lr)
+    assert (a[0] == b[0]).all() and np.abs(a[1] - b[1]).max() <= 1e-5
+    hit, miss, cmin, cmax = ref.constants()
+    assert np.isclose(lg.max(), cmax) and lg.max() <= cmax + 1e-6
+    pts, _ = gpu.last_points()
+    v = gpu.query(pts[0])
+    assert v is not None and v > 0
+    assert gpu.query(np.array([50.0, 50.0, 50.0], np.float32)) is None
+
+
+def test_no_leaf_filter_and_other_resolution(oracle):
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    depth, rgb, T = _scene(2)[1]
+    gpu = PointCloudMapping(0.1, leaf=0.0, depth_max=4.0)
+    ref = oracle.RefOccupancy(resolution=0.1, leaf=0.0, depth_max=4.0)
+    gpu.insertKeyFrame(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY)
+    ref.insert_keyframe(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY)
+    pg, _ = gpu.last_points()
+    pr, _, _ = ref.last_points()
+    assert len(pg) == len(pr)
+    assert np.abs(_sorted_pts(pg) - _sorted_pts(pr)).max() <= 1e-5
+    a, b = _leaf_dict(*gpu.export_leaves()[:2]), _leaf_dict(*ref.export_leaves())
+    assert (a[0] == b[0]).all() and np.abs(a[1] - b[1]).max() <= 1e-5
