@@ -1,0 +1,175 @@
+"""oracle/match_py.py -- TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Second, independent restatement (pure Python + numpy float32 scalars; small cases only) of
+ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (reference src/ORBmatcher.cc:1578-1724) and the
+Frame grid helpers (src/Frame.cc:319-334,465-531).  It pins oracle/match_ref.cpp and generates the golden match
+vectors under tests/golden/ (tools/make_golden.py).  Reads the same FrameView / LastView objects.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+f32 = np.float32
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+GRID_COLS, GRID_ROWS = 64, 48
+
+
+def c_round(v: float) -> int:
+    """C round(): half away from zero."""
+    return int(math.floor(v + 0.5)) if v >= 0 else -int(math.floor(-v + 0.5))
+
+
+def hamming(a, b) -> int:
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def gemm3(a, b, c):
+    """OpenCV small-matrix gemm row: float accumulation left to right, '+C' in double."""
+    t = f32(f32(f32(a[0] * b[0]) + f32(a[1] * b[1])) + f32(a[2] * b[2]))
+    return f32(float(t) + float(c))
+
+
+class Grid:
+    def __init__(self, F):
+        self.F = F
+        self.minx, self.maxx, self.miny, self.maxy = (f32(v) for v in F.bounds)
+        self.invw = f32(f32(GRID_COLS) / f32(self.maxx - self.minx))
+        self.invh = f32(f32(GRID_ROWS) / f32(self.maxy - self.miny))
+        self.cells = [[[] for _ in range(GRID_ROWS)] for _ in range(GRID_COLS)]
+        for i in range(F.n):
+            px = c_round(float(f32(f32(F.x[i] - self.minx) * self.invw)))
+            py = c_round(float(f32(f32(F.y[i] - self.miny) * self.invh)))
+            if px < 0 or px >= GRID_COLS or py < 0 or py >= GRID_ROWS:
+                continue
+            self.cells[px][py].append(i)
+
+    def query(self, x, y, r, minLevel, maxLevel):
+        F = self.F
+        out = []
+        nMinCellX = max(0, int(math.floor(float(f32(f32(f32(x - self.minx) - r) * self.invw)))))
+        if nMinCellX >= GRID_COLS:
+            return out
+        nMaxCellX = min(GRID_COLS - 1, int(math.ceil(float(f32(f32(f32(x - self.minx) + r) * self.invw)))))
+        if nMaxCellX < 0:
+            return out
+        nMinCellY = max(0, int(math.floor(float(f32(f32(f32(y - self.miny) - r) * self.invh)))))
+        if nMinCellY >= GRID_ROWS:
+            return out
+        nMaxCellY = min(GRID_ROWS - 1, int(math.ceil(float(f32(f32(f32(y - self.miny) + r) * self.invh)))))
+        if nMaxCellY < 0:
+            return out
+        check = (minLevel > 0) or (maxLevel >= 0)
+        for ix in range(nMinCellX, nMaxCellX + 1):
+            for iy in range(nMinCellY, nMaxCellY + 1):
+                for idx in self.cells[ix][iy]:
+                    if check:
+                        if F.octave[idx] < minLevel:
+                            continue
+                        if maxLevel >= 0 and F.octave[idx] > maxLevel:
+                            continue
+                    if abs(f32(F.x[idx] - x)) < r and abs(f32(F.y[idx] - y)) < r:
+                        out.append(idx)
+        return out
+
+
+def three_maxima(histo):
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, h in enumerate(histo):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if f32(max2) < f32(f32(0.1) * f32(max1)):
+        ind2 = ind3 = -1
+    elif f32(max3) < f32(f32(0.1) * f32(max1)):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def search_by_projection_last(cur, last, th, mono=False, check_ori=True):
+    th = f32(th)
+    fx, fy, cx, cy, bf = (f32(v) for v in cur.cam)
+    mb = f32(bf / fx)
+    T = cur.Tcw.reshape(4, 4)
+    Rcw, tcw = T[:3, :3], T[:3, 3]
+    twc = [f32(-sum(float(Rcw[k, i]) * float(tcw[k]) for k in range(3))) for i in range(3)]
+    Tl = last.Tcw.reshape(4, 4)
+    tlc2 = gemm3(Tl[2, :3], twc, Tl[2, 3])
+    bForward = (tlc2 > mb) and not mono
+    bBackward = (-tlc2 > mb) and not mono
+    grid = Grid(cur)
+    state = [-1] * cur.n
+    obs = [0] * cur.n
+    if cur.mp_obs is not None:
+        for j in range(cur.n):
+            if cur.mp_obs[j] >= 0:
+                state[j], obs[j] = -2, int(cur.mp_obs[j])
+    rot = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    for i in range(last.n):
+        if not last.valid[i]:
+            continue
+        X = last.xw[i]
+        xc = gemm3(Rcw[0], X, tcw[0])
+        yc = gemm3(Rcw[1], X, tcw[1])
+        zc = gemm3(Rcw[2], X, tcw[2])
+        with np.errstate(divide="ignore"):
+            invzc = f32(np.float64(1.0) / np.float64(zc))
+        if invzc < 0:
+            continue
+        u = f32(f32(f32(fx * xc) * invzc) + cx)
+        v = f32(f32(f32(fy * yc) * invzc) + cy)
+        if np.isnan(u) or np.isnan(v):
+            continue
+        if u < grid.minx or u > grid.maxx or v < grid.miny or v > grid.maxy:
+            continue
+        octv = int(last.octave[i])
+        radius = f32(th * cur.scale_factors[octv])
+        if bForward:
+            cand = grid.query(u, v, radius, octv, -1)
+        elif bBackward:
+            cand = grid.query(u, v, radius, 0, octv)
+        else:
+            cand = grid.query(u, v, radius, octv - 1, octv + 1)
+        if not cand:
+            continue
+        best, bidx = 256, -1
+        for i2 in cand:
+            if state[i2] != -1 and obs[i2] > 0:
+                continue
+            if cur.uright[i2] > 0:
+                ur = f32(u - f32(bf * invzc))
+                if abs(f32(ur - cur.uright[i2])) > radius:
+                    continue
+            d = hamming(last.mp_desc[i], cur.desc[i2])
+            if d < best:
+                best, bidx = d, i2
+        if best <= TH_HIGH:
+            state[bidx] = i
+            obs[bidx] = int(last.mp_obs[i]) if last.mp_obs is not None else 0
+            nmatches += 1
+            if check_ori:
+                r = f32(last.angle[i] - cur.angle[bidx])
+                if r < 0:
+                    r = f32(r + f32(360.0))
+                b = c_round(float(f32(r * factor)))
+                if b == HISTO_LENGTH:
+                    b = 0
+                rot[b].append(bidx)
+    if check_ori:
+        i1, i2_, i3 = three_maxima(rot)
+        for b in range(HISTO_LENGTH):
+            if b not in (i1, i2_, i3):
+                for idx in rot[b]:
+                    state[idx] = -1
+                    nmatches -= 1
+    return nmatches, np.array(state, np.int32)

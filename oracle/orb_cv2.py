@@ -16,6 +16,14 @@ import os
 
 import numpy as np
 
+import ctypes as _C
+
+_LIBM = _C.CDLL("libm.so.6")
+_LIBM.cosf.restype = _C.c_float
+_LIBM.cosf.argtypes = [_C.c_float]
+_LIBM.sinf.restype = _C.c_float
+_LIBM.sinf.argtypes = [_C.c_float]
+
 PATCH_SIZE = 31
 HALF_PATCH_SIZE = 15
 EDGE_THRESHOLD = 19
@@ -305,10 +313,9 @@ class ORBextractorCV2:
     def computeOrbDescriptor(self, kp, img):
         factorPI = f32(math.pi / float(f32(180.0)))
         angle = f32(kp[3] * factorPI)
-        # cosf/sinf: evaluate in double and round once (glibc's float versions are correctly rounded for
-        # all but astronomically rare arguments; tests/test_oracle_cv2.py checks the C oracle agrees)
-        a = f32(math.cos(float(angle)))
-        b = f32(math.sin(float(angle)))
+        # cos()/sin() on a float bind to libm's cosf/sinf (not correctly rounded): call the host libm itself
+        a = f32(_LIBM.cosf(float(angle)))
+        b = f32(_LIBM.sinf(float(angle)))
         cy = cv_round(kp[1])
         cx = cv_round(kp[0])
         px = self.pattern[:, 0].astype(np.float32)

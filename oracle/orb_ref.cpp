@@ -20,6 +20,8 @@
 #include <list>
 #include <vector>
 
+#include "../include/glibc_sincosf.h"
+
 namespace {
 
 static const signed char kPattern[1024] = {
@@ -610,6 +612,19 @@ int orb_ref_fast(const uint8_t* roi, int rw, int rh, int stride, int t, int* out
   return n;
 }
 float orb_ref_fast_atan2(float y, float x) { return fast_atan2_deg(y, x); }
+// count of floats in [lo_bits, hi_bits] (stepping by `step`) where the restated glibc sinf/cosf (include/glibc_sincosf.h,
+// the algorithm the CUDA kernel runs) differs from the host libm the oracle calls
+long orb_ref_sincosf_mismatches(uint32_t lo_bits, uint32_t hi_bits, uint32_t step) {
+  long bad = 0;
+  for (uint64_t u = lo_bits; u <= hi_bits; u += step) {
+    float x;
+    uint32_t uu = (uint32_t)u;
+    memcpy(&x, &uu, 4);
+    if (b200_cosf(x) != cosf(x)) ++bad;
+    if (b200_sinf(x) != sinf(x)) ++bad;
+  }
+  return bad;
+}
 void orb_ref_descriptor(const uint8_t* img, int step, float x, float y, float angle, uint8_t* desc) {
   KeyPoint kp{x, y, 31.f, angle, 0.f, 0, -1};
   Extractor::descriptor(kp, img, step, desc);

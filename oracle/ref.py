@@ -182,6 +182,22 @@ def search_by_projection_last(cur, last, th, mono=False, nnratio=0.9, check_ori=
     return nm.value, out
 
 
+def search_by_projection_points(F, pts, th, nnratio=0.8):
+    out = np.full(F.n, -1, np.int32)
+    nm = C.c_int(0)
+    fs, ps = F.struct(), pts.struct()
+    _mlib().match_ref_projection_points(C.byref(fs), C.byref(ps), float(th), float(nnratio), _p(out), C.byref(nm))
+    return nm.value, out
+
+
+def search_by_bow(kf, f, nnratio=0.7, check_ori=True):
+    out = np.full(f.n, -1, np.int32)
+    nm = C.c_int(0)
+    ks, fs = kf.struct(), f.struct()
+    _mlib().match_ref_bow(C.byref(ks), C.byref(fs), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+    return nm.value, out
+
+
 def stereo_unproject(kps, depth, Tcw, fx, fy, cx, cy, bf):
     """ComputeStereoFromRGBD + UnprojectStereo for every keypoint -> uright, depth, xw, valid."""
     n = len(kps)

@@ -109,3 +109,52 @@ class LastView:
         s.mp_desc, s.mp_obs = ptr(self.mp_desc), ptr(self.mp_obs)
         s.Tcw = (C.c_float * 16)(*self.Tcw.tolist())
         return s
+
+
+class TrackPointsView:
+    """Local-map MapPoints as Frame::isInFrustum leaves them (src/Frame.cc:387-451)."""
+
+    def __init__(self, track_in_view, proj_x, proj_y, proj_xr, scale_level, view_cos, mp_desc, mp_obs=None):
+        self.track_in_view = np.ascontiguousarray(track_in_view, np.uint8)
+        self.proj_x = np.ascontiguousarray(proj_x, np.float32)
+        self.proj_y = np.ascontiguousarray(proj_y, np.float32)
+        self.proj_xr = np.ascontiguousarray(proj_xr, np.float32)
+        self.scale_level = np.ascontiguousarray(scale_level, np.int32)
+        self.view_cos = np.ascontiguousarray(view_cos, np.float32)
+        self.mp_desc = np.ascontiguousarray(mp_desc, np.uint8).reshape(-1, 32)
+        self.mp_obs = None if mp_obs is None else np.ascontiguousarray(mp_obs, np.int32)
+        self.n = len(self.track_in_view)
+
+    def struct(self) -> OrbmTrackPoints:
+        s = OrbmTrackPoints()
+        s.n = self.n
+        s.track_in_view, s.proj_x, s.proj_y, s.proj_xr = ptr(self.track_in_view), ptr(self.proj_x), ptr(self.proj_y), ptr(self.proj_xr)
+        s.scale_level, s.view_cos, s.mp_desc, s.mp_obs = ptr(self.scale_level), ptr(self.view_cos), ptr(self.mp_desc), ptr(self.mp_obs)
+        return s
+
+
+class BowView:
+    """One side of SearchByBoW: descriptors + angles + the DBoW2::FeatureVector flattened (node ids ascending)."""
+
+    def __init__(self, desc, angle, feat_vec: dict, valid=None):
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.angle = np.ascontiguousarray(angle, np.float32)
+        self.valid = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+        ids = sorted(feat_vec.keys())
+        self.node_ids = np.array(ids, np.uint32)
+        off = [0]
+        idx = []
+        for k in ids:
+            idx.extend(int(v) for v in feat_vec[k])
+            off.append(len(idx))
+        self.node_off = np.array(off, np.int32)
+        self.idx = np.array(idx if idx else [0], np.uint32)
+        self.n = len(self.desc)
+
+    def struct(self) -> OrbmBow:
+        s = OrbmBow()
+        s.n = self.n
+        s.desc, s.angle, s.valid = ptr(self.desc), ptr(self.angle), ptr(self.valid)
+        s.n_nodes = len(self.node_ids)
+        s.node_ids, s.node_off, s.idx = ptr(self.node_ids), ptr(self.node_off), ptr(self.idx)
+        return s

@@ -1,4 +1,5 @@
 // orbm.cu -- host side + C-ABI of the B200 ORB matcher (reference: src/ORBmatcher.cc, include/ORBmatcher.h).
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -29,21 +30,33 @@ struct Carver {   // sequential sub-allocation out of the arena, 256-byte aligne
   template <class T>
   T* take(size_t n) {
     T* p = (T*)(base + off);
-    off = align_up_sz(off + n * sizeof(T), 256);
+    off = align_up_sz(off + std::max<size_t>(n, 1) * sizeof(T), 256);
     return p;
   }
 };
+
+int resolve_smem(int cmax, size_t* smem, const void* func) {
+  *smem = (size_t)cmax * 5 + 16;
+  if (*smem > 200 * 1024) { set_error("too many keypoints per frame for the matcher's shared memory"); return B200ORB_EINVAL; }
+  if (*smem > 48 * 1024) B200_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+  return B200ORB_OK;
+}
 }  // namespace
 
-int launch_match_last(const MatchBatch& mb, const MatchCam& cam, int npairs, int cmax, cudaStream_t stream) {
-  const size_t smem = (size_t)cmax * 5 + 16;
-  if (smem > 160 * 1024) { set_error("too many keypoints per frame for the matcher's shared memory"); return B200ORB_EINVAL; }
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    B200_CUDA(cudaFuncSetAttribute(k_match_last, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  k_match_last<<<npairs, MATCH_THREADS, smem, stream>>>(mb, cam, cmax);
+// Enqueue grid build + candidates + resolve of `npairs` (cur, last) instances.  nframes_cur grids are built from cv.
+int launch_match_last(const CurView& cv_in, const LastView& lv, const MatchCam& cam, int npairs, int* d_goff, int* d_gidx,
+                      unsigned* d_list, int* d_count, int* d_accepted, int* d_cur2last, int* d_nmatch, int cmax,
+                      int lmax, cudaStream_t stream, long long* launches) {
+  CurView cv = cv_in;
+  k_grid_build<<<npairs, 256, 0, stream>>>(cv.x, cv.y, cv.n, cv.stride, cam.min_x, cam.max_x, cam.min_y, cam.max_y, d_goff,
+                                          d_gidx);
+  cv.goff = d_goff; cv.gidx = d_gidx;
+  ListView lsv{d_list, d_count};
+  k_cand_last<<<dim3((lmax + CAND_WARPS - 1) / CAND_WARPS, npairs), CAND_WARPS * 32, 0, stream>>>(cv, lv, cam, lsv);
+  size_t smem;
+  B200_CHECK(resolve_smem(cmax, &smem, (const void*)k_resolve_last));
+  k_resolve_last<<<npairs, 32, smem, stream>>>(cv, lv, cam, lsv, d_accepted, d_cur2last, d_nmatch, cmax);
+  if (launches) *launches += 3;
   B200_CUDA(cudaGetLastError());
   return B200ORB_OK;
 }
@@ -91,10 +104,39 @@ static int fill_cam(const OrbmFrame* f, float th, int mono, float nnratio, int c
 #define UP(dst, src, count, T)                                                                              \
   B200_CUDA(cudaMemcpyAsync((dst), (src), sizeof(T) * (size_t)(count), cudaMemcpyHostToDevice, h->stream))
 
+// uploads the current-frame arrays; fills cv (single instance)
+static int upload_cur(orbm* h, Carver& cv_mem, const OrbmFrame* cur, CurView* cv, int** d_goff, int** d_gidx) {
+  const size_t nc = cur->n;
+  float* d_cx = cv_mem.take<float>(nc); float* d_cy = cv_mem.take<float>(nc); float* d_cang = cv_mem.take<float>(nc);
+  float* d_cur = cv_mem.take<float>(nc); int* d_coct = cv_mem.take<int>(nc); uint8_t* d_cdesc = cv_mem.take<uint8_t>(nc * 32);
+  int* d_cobs = cur->mp_obs ? cv_mem.take<int>(nc) : nullptr;
+  int* d_cn = cv_mem.take<int>(1); float* d_cT = cv_mem.take<float>(16);
+  *d_goff = cv_mem.take<int>(GRID_CELLS + 1); *d_gidx = cv_mem.take<int>(nc);
+  UP(d_cx, cur->x, nc, float); UP(d_cy, cur->y, nc, float); UP(d_cang, cur->angle, nc, float);
+  UP(d_cur, cur->uright, nc, float); UP(d_coct, cur->octave, nc, int); UP(d_cdesc, cur->desc, nc * 32, uint8_t);
+  if (d_cobs) UP(d_cobs, cur->mp_obs, nc, int);
+  const int cn = cur->n;
+  UP(d_cn, &cn, 1, int); UP(d_cT, cur->Tcw, 16, float);
+  memset(cv, 0, sizeof(*cv));
+  cv->x = d_cx; cv->y = d_cy; cv->ang = d_cang; cv->uright = d_cur; cv->oct = d_coct; cv->desc = d_cdesc; cv->obs = d_cobs;
+  cv->n = d_cn; cv->Tcw = d_cT; cv->stride = nc; cv->goff = *d_goff; cv->gidx = *d_gidx;
+  return B200ORB_OK;
+}
+
+static int check_cur(const OrbmFrame* cur) {
+  if (cur->n < 0 || cur->n >= (1 << 20)) { set_error("bad keypoint count"); return B200ORB_EINVAL; }
+  if (cur->n > 0 && (!cur->x || !cur->y || !cur->octave || !cur->angle || !cur->uright || !cur->desc)) {
+    set_error("null keypoint array");
+    return B200ORB_EINVAL;
+  }
+  return B200ORB_OK;
+}
+
 int orbm_search_by_projection_last(orbm_t* h, const OrbmFrame* cur, const OrbmLast* last, float th, int mono,
                                    float nnratio, int check_ori, int32_t* cur2last, int* nmatches) {
   if (!h || !cur || !last || !cur2last || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
-  if (cur->n < 0 || last->n < 0 || cur->n >= (1 << 20)) { set_error("bad keypoint count"); return B200ORB_EINVAL; }
+  B200_CHECK(check_cur(cur));
+  if (last->n < 0) { set_error("bad keypoint count"); return B200ORB_EINVAL; }
   *nmatches = 0;
   if (cur->n == 0) return B200ORB_OK;
   if (last->n == 0) {
@@ -108,38 +150,140 @@ int orbm_search_by_projection_last(orbm_t* h, const OrbmFrame* cur, const OrbmLa
   cam.last_obs_default = 0;
   DeviceGuard g(h->device);
   const size_t nc = cur->n, nl = last->n;
-  const size_t need = (nc * (4 * 4 + 4 + 32 + 4 + 4 + 4) + nl * (12 + 1 + 4 + 4 + 32 + 4 + 8 * MATCH_K + 4 + 4) + 4096) + 64 * 256;
+  const size_t need = nc * (4 * 4 + 4 + 32 + 4 + 4 + 4) + nl * (12 + 1 + 4 + 4 + 32 + 4 + 4 * LCAP + 4 + 4) + 4 * (GRID_CELLS + 1) +
+                      64 * 256 + 4096;
   B200_CHECK(h->reserve(need));
-  Carver cv(h->d_arena);
-  MatchBatch mb{};
-  float* d_cx = cv.take<float>(nc); float* d_cy = cv.take<float>(nc); float* d_cang = cv.take<float>(nc);
-  float* d_cur = cv.take<float>(nc); int* d_coct = cv.take<int>(nc); uint8_t* d_cdesc = cv.take<uint8_t>(nc * 32);
-  int* d_cobs = cur->mp_obs ? cv.take<int>(nc) : nullptr;
-  int* d_cn = cv.take<int>(1); float* d_cT = cv.take<float>(16);
-  float* d_lxw = cv.take<float>(nl * 3); uint8_t* d_lvalid = cv.take<uint8_t>(nl); int* d_loct = cv.take<int>(nl);
-  float* d_lang = cv.take<float>(nl); uint8_t* d_ldesc = cv.take<uint8_t>(nl * 32);
-  int* d_lobs = last->mp_obs ? cv.take<int>(nl) : nullptr;
-  int* d_ln = cv.take<int>(1); float* d_lT = cv.take<float>(16);
-  int* d_out = cv.take<int>(nc); int* d_nm = cv.take<int>(1);
-  unsigned long long* d_topk = cv.take<unsigned long long>(nl * MATCH_K);
-  int* d_ncand = cv.take<int>(nl); int* d_gidx = cv.take<int>(nc); int* d_acc = cv.take<int>(nl);
-  UP(d_cx, cur->x, nc, float); UP(d_cy, cur->y, nc, float); UP(d_cang, cur->angle, nc, float);
-  UP(d_cur, cur->uright, nc, float); UP(d_coct, cur->octave, nc, int); UP(d_cdesc, cur->desc, nc * 32, uint8_t);
-  if (d_cobs) UP(d_cobs, cur->mp_obs, nc, int);
-  const int cn = cur->n, ln = last->n;
-  UP(d_cn, &cn, 1, int); UP(d_cT, cur->Tcw, 16, float);
+  Carver cm(h->d_arena);
+  CurView cv;
+  int *d_goff, *d_gidx;
+  B200_CHECK(upload_cur(h, cm, cur, &cv, &d_goff, &d_gidx));
+  float* d_lxw = cm.take<float>(nl * 3); uint8_t* d_lvalid = cm.take<uint8_t>(nl); int* d_loct = cm.take<int>(nl);
+  float* d_lang = cm.take<float>(nl); uint8_t* d_ldesc = cm.take<uint8_t>(nl * 32);
+  int* d_lobs = last->mp_obs ? cm.take<int>(nl) : nullptr;
+  int* d_ln = cm.take<int>(1); float* d_lT = cm.take<float>(16);
+  int* d_out = cm.take<int>(nc); int* d_nm = cm.take<int>(1);
+  unsigned* d_list = cm.take<unsigned>(nl * LCAP); int* d_count = cm.take<int>(nl); int* d_acc = cm.take<int>(nl);
   UP(d_lxw, last->xw, nl * 3, float); UP(d_lvalid, last->valid, nl, uint8_t); UP(d_loct, last->octave, nl, int);
   UP(d_lang, last->angle, nl, float); UP(d_ldesc, last->mp_desc, nl * 32, uint8_t);
   if (d_lobs) UP(d_lobs, last->mp_obs, nl, int);
+  const int ln = last->n;
   UP(d_ln, &ln, 1, int); UP(d_lT, last->Tcw, 16, float);
-  mb.cx = d_cx; mb.cy = d_cy; mb.cang = d_cang; mb.curight = d_cur; mb.coct = d_coct; mb.cdesc = d_cdesc;
-  mb.cobs = d_cobs; mb.cn = d_cn; mb.cTcw = d_cT; mb.cstride = nc;
-  mb.lxw = d_lxw; mb.lvalid = d_lvalid; mb.loct = d_loct; mb.lang = d_lang; mb.ldesc = d_ldesc; mb.lobs = d_lobs;
-  mb.ln = d_ln; mb.lTcw = d_lT; mb.lstride = nl;
-  mb.cur2last = d_out; mb.nmatch = d_nm; mb.topk = d_topk; mb.ncand = d_ncand; mb.grididx = d_gidx; mb.accepted = d_acc;
-  B200_CHECK(launch_match_last(mb, cam, 1, align_up((int)nc, 16), h->stream));
-  ++h->launches;
+  LastView lv{d_lxw, d_lvalid, d_loct, d_lang, d_ldesc, d_lobs, d_ln, d_lT, nl};
+  B200_CHECK(launch_match_last(cv, lv, cam, 1, d_goff, d_gidx, d_list, d_count, d_acc, d_out, d_nm, align_up((int)nc, 16),
+                               (int)nl, h->stream, &h->launches));
   B200_CUDA(cudaMemcpyAsync(cur2last, d_out, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int orbm_search_by_projection_points(orbm_t* h, const OrbmFrame* f, const OrbmTrackPoints* pts, float th, float nnratio,
+                                     int32_t* f2pt, int* nmatches) {
+  if (!h || !f || !pts || !f2pt || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
+  B200_CHECK(check_cur(f));
+  if (pts->n < 0) { set_error("bad point count"); return B200ORB_EINVAL; }
+  *nmatches = 0;
+  if (f->n == 0) return B200ORB_OK;
+  if (pts->n == 0) {
+    for (int j = 0; j < f->n; ++j) f2pt[j] = (f->mp_obs && f->mp_obs[j] >= 0) ? -2 : -1;
+    return B200ORB_OK;
+  }
+  for (int i = 0; i < pts->n; ++i)
+    if (pts->track_in_view[i] && (pts->scale_level[i] < 0 || pts->scale_level[i] >= f->nlevels)) {
+      set_error("scale level out of range");
+      return B200ORB_EINVAL;
+    }
+  MatchCam cam;
+  B200_CHECK(fill_cam(f, th, 0, nnratio, 0, &cam));
+  cam.last_obs_default = 1;
+  DeviceGuard g(h->device);
+  const size_t nc = f->n, np = pts->n;
+  const size_t need = nc * (4 * 4 + 4 + 32 + 4 + 4 + 4) + np * (1 + 16 + 4 + 32 + 4 + 4 * LCAP + 4) + 4 * (GRID_CELLS + 1) + 64 * 256 + 4096;
+  B200_CHECK(h->reserve(need));
+  Carver cm(h->d_arena);
+  CurView cv;
+  int *d_goff, *d_gidx;
+  B200_CHECK(upload_cur(h, cm, f, &cv, &d_goff, &d_gidx));
+  uint8_t* d_inv = cm.take<uint8_t>(np); float* d_px = cm.take<float>(np); float* d_py = cm.take<float>(np);
+  float* d_pxr = cm.take<float>(np); float* d_vc = cm.take<float>(np); int* d_lvl = cm.take<int>(np);
+  uint8_t* d_desc = cm.take<uint8_t>(np * 32); int* d_obs = pts->mp_obs ? cm.take<int>(np) : nullptr;
+  unsigned* d_list = cm.take<unsigned>(np * LCAP); int* d_count = cm.take<int>(np);
+  int* d_out = cm.take<int>(nc); int* d_nm = cm.take<int>(1);
+  UP(d_inv, pts->track_in_view, np, uint8_t); UP(d_px, pts->proj_x, np, float); UP(d_py, pts->proj_y, np, float);
+  UP(d_pxr, pts->proj_xr, np, float); UP(d_vc, pts->view_cos, np, float); UP(d_lvl, pts->scale_level, np, int);
+  UP(d_desc, pts->mp_desc, np * 32, uint8_t);
+  if (d_obs) UP(d_obs, pts->mp_obs, np, int);
+  PointsView pv{d_inv, d_px, d_py, d_pxr, d_vc, d_lvl, d_desc, d_obs, (int)np};
+  ListView lsv{d_list, d_count};
+  k_grid_build<<<1, 256, 0, h->stream>>>(cv.x, cv.y, cv.n, cv.stride, cam.min_x, cam.max_x, cam.min_y, cam.max_y, d_goff, d_gidx);
+  k_cand_points<<<((int)np + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, h->stream>>>(cv, pv, cam, lsv);
+  size_t smem;
+  const int cmax = align_up((int)nc, 16);
+  B200_CHECK(resolve_smem(cmax, &smem, (const void*)k_resolve_points));
+  k_resolve_points<<<1, 32, smem, h->stream>>>(cv, pv, cam, lsv, d_out, d_nm, cmax);
+  h->launches += 3;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(f2pt, d_out, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
+                       int* nmatches) {
+  if (!h || !kf || !f || !f2kf || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
+  if (kf->n < 0 || f->n < 0 || kf->n_nodes < 0 || f->n_nodes < 0 || f->n >= (1 << 20)) { set_error("bad counts"); return B200ORB_EINVAL; }
+  *nmatches = 0;
+  for (int j = 0; j < f->n; ++j) f2kf[j] = -1;
+  if (kf->n == 0 || f->n == 0 || kf->n_nodes == 0 || f->n_nodes == 0) return B200ORB_OK;
+  // merge-join of the two FeatureVectors (:242-335): equal node ids pair up; queries in the reference's visiting order
+  std::vector<int> q_kf, q_beg, q_end;
+  {
+    int a = 0, b = 0;
+    while (a < kf->n_nodes && b < f->n_nodes) {
+      const uint32_t ka = kf->node_ids[a], kb = f->node_ids[b];
+      if (ka == kb) {
+        for (int i = kf->node_off[a]; i < kf->node_off[a + 1]; ++i) {
+          const uint32_t r = kf->idx[i];
+          if (r >= (uint32_t)kf->n) { set_error("KF index out of range"); return B200ORB_EINVAL; }
+          if (kf->valid && !kf->valid[r]) continue;
+          q_kf.push_back((int)r); q_beg.push_back(f->node_off[b]); q_end.push_back(f->node_off[b + 1]);
+        }
+        ++a; ++b;
+      } else if (ka < kb) {
+        a = (int)(std::lower_bound(kf->node_ids, kf->node_ids + kf->n_nodes, kb) - kf->node_ids);
+      } else {
+        b = (int)(std::lower_bound(f->node_ids, f->node_ids + f->n_nodes, ka) - f->node_ids);
+      }
+    }
+  }
+  const size_t nq = q_kf.size(), nfi = (size_t)f->node_off[f->n_nodes];
+  if (nq == 0) return B200ORB_OK;
+  for (size_t i = 0; i < nfi; ++i)
+    if (f->idx[i] >= (uint32_t)f->n) { set_error("F index out of range"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  const size_t need = nq * (12 + 4 * LCAP + 8) + nfi * 4 + (size_t)kf->n * 36 + (size_t)f->n * (36 + 4) + 64 * 256 + 4096;
+  B200_CHECK(h->reserve(need));
+  Carver cm(h->d_arena);
+  int* d_qkf = cm.take<int>(nq); int* d_qb = cm.take<int>(nq); int* d_qe = cm.take<int>(nq);
+  unsigned* d_fidx = cm.take<unsigned>(nfi);
+  uint8_t* d_kd = cm.take<uint8_t>((size_t)kf->n * 32); uint8_t* d_fd = cm.take<uint8_t>((size_t)f->n * 32);
+  float* d_ka = cm.take<float>(kf->n); float* d_fa = cm.take<float>(f->n);
+  unsigned* d_list = cm.take<unsigned>(nq * LCAP); int* d_count = cm.take<int>(nq); int* d_acc = cm.take<int>(nq);
+  int* d_out = cm.take<int>(f->n); int* d_nm = cm.take<int>(1);
+  UP(d_qkf, q_kf.data(), nq, int); UP(d_qb, q_beg.data(), nq, int); UP(d_qe, q_end.data(), nq, int);
+  UP(d_fidx, f->idx, nfi, unsigned); UP(d_kd, kf->desc, (size_t)kf->n * 32, uint8_t); UP(d_fd, f->desc, (size_t)f->n * 32, uint8_t);
+  UP(d_ka, kf->angle, kf->n, float); UP(d_fa, f->angle, f->n, float);
+  BowQueries bq{d_qkf, d_qb, d_qe, d_fidx, d_kd, d_fd, d_ka, d_fa, (int)nq, f->n};
+  ListView lsv{d_list, d_count};
+  k_cand_bow<<<((int)nq + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, h->stream>>>(bq, lsv);
+  size_t smem;
+  const int cmax = align_up(f->n, 16);
+  B200_CHECK(resolve_smem(cmax, &smem, (const void*)k_resolve_bow));
+  k_resolve_bow<<<1, 32, smem, h->stream>>>(bq, nnratio, check_ori, lsv, d_acc, d_out, d_nm, cmax);
+  h->launches += 2;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(f2kf, d_out, sizeof(int) * (size_t)f->n, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return B200ORB_OK;

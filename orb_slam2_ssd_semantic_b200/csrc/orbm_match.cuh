@@ -1,18 +1,73 @@
-// orbm_match.cuh -- the SearchByProjection(CurrentFrame, LastFrame) kernel (src/ORBmatcher.cc:1578-1724).
+// orbm_match.cuh -- candidate (K8) and order-exact resolve (K9/K10) kernels of the three searches:
+//   LAST    SearchByProjection(Frame&, const Frame&, th, bMono)          src/ORBmatcher.cc:1578-1724
+//   POINTS  SearchByProjection(Frame&, const vector<MapPoint*>&, th)      src/ORBmatcher.cc:63-156
+//   BOW     SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)            src/ORBmatcher.cc:217-363
 #pragma once
 #include "orbm_kernels.cuh"
 
 namespace b200 {
 
-struct LastQuery {   // per-query projection state shared by phase B and the re-walk of phase C
-  QueryGeom g;
-  uint4 d0, d1;
+constexpr int CAND_WARPS = 8;
+
+struct LastView {            // LastFrame side; instance p reads at p*stride
+  const float* xw;
+  const uint8_t* valid;
+  const int* oct;
+  const float* ang;
+  const uint8_t* desc;
+  const int* obs;            // nullable
+  const int* n;
+  const float* Tcw;
+  size_t stride;
 };
 
+struct PointsView {          // local-map points (fields Frame::isInFrustum fills)
+  const uint8_t* in_view;
+  const float *px, *py, *pxr, *view_cos;
+  const int* level;
+  const uint8_t* desc;
+  const int* obs;            // nullable
+  int n;
+};
+
+struct ListView {            // per query: LCAP entries + count (negative = overflowed, true count = -n)
+  unsigned* list;
+  int* count;
+};
+
+__device__ __forceinline__ WalkCtx make_ctx(const CurView& cv, const MatchCam& cam, int p) {
+  WalkCtx g;
+  const size_t co = (size_t)p * cv.stride;
+  g.off = cv.goff + (size_t)p * (GRID_CELLS + 1);
+  g.idx = cv.gidx + co;
+  g.x = cv.x + co; g.y = cv.y + co; g.uright = cv.uright + co; g.oct = cv.oct + co;
+  g.obs = cv.obs ? cv.obs + co : nullptr;
+  g.desc = cv.desc + co * 32;
+  g.min_x = cam.min_x; g.min_y = cam.min_y;
+  g.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(cam.max_x, cam.min_x));
+  g.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(cam.max_y, cam.min_y));
+  return g;
+}
+
+// forward / backward decision of the LAST search (:1590-1602); warp-uniform
+__device__ __forceinline__ void motion_flags(const MatchCam& cam, const float* Tc, const float* Tl, bool& fwd, bool& bwd) {
+  float twc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {   // -Rcw.t()*tcw through the generic (double-accumulating) gemm
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)Tc[k * 4 + i], (double)Tc[k * 4 + 3]));
+    twc[i] = __double2float_rn(-s);
+  }
+  const float Rl2[3] = {Tl[8], Tl[9], Tl[10]};
+  const float tlc2 = gemm3(Rl2, twc[0], twc[1], twc[2], Tl[11]);
+  fwd = (tlc2 > cam.b) && !cam.mono;
+  bwd = (-tlc2 > cam.b) && !cam.mono;
+}
+
 // Projection + window set-up of one last-frame MapPoint (:1616-1644).
-__device__ __forceinline__ bool setup_last_query(const MatchCam& cam, const float* Rt /*cur Tcw row-major 16*/,
-                                                 bool bForward, bool bBackward, const float* __restrict__ xw,
-                                                 int octave, const uint8_t* __restrict__ desc, LastQuery& q) {
+__device__ __forceinline__ bool setup_last_query(const MatchCam& cam, const float* Rt, bool bForward, bool bBackward,
+                                                 const float* __restrict__ xw, int octave, QueryGeom& q) {
   const float R0[3] = {Rt[0], Rt[1], Rt[2]}, R1[3] = {Rt[4], Rt[5], Rt[6]}, R2[3] = {Rt[8], Rt[9], Rt[10]};
   const float xc = gemm3(R0, xw[0], xw[1], xw[2], Rt[3]);
   const float yc = gemm3(R1, xw[0], xw[1], xw[2], Rt[7]);
@@ -24,214 +79,352 @@ __device__ __forceinline__ bool setup_last_query(const MatchCam& cam, const floa
   if (isnan(u) || isnan(v)) return false;   // reference: UB; documented deviation (oracle does the same)
   if (u < cam.min_x || u > cam.max_x) return false;
   if (v < cam.min_y || v > cam.max_y) return false;
-  q.g.u = u; q.g.v = v;
-  q.g.r = __fmul_rn(cam.th, cam.sf[octave]);
-  q.g.ur = __fsub_rn(u, __fmul_rn(cam.bf, invzc));
-  if (bForward) { q.g.min_level = octave; q.g.max_level = -1; }
-  else if (bBackward) { q.g.min_level = 0; q.g.max_level = octave; }
-  else { q.g.min_level = octave - 1; q.g.max_level = octave + 1; }
-  q.d0 = __ldg(reinterpret_cast<const uint4*>(desc));
-  q.d1 = __ldg(reinterpret_cast<const uint4*>(desc) + 1);
+  q.u = u; q.v = v;
+  q.r = __fmul_rn(cam.th, cam.sf[octave]);
+  q.rr = q.r;
+  q.ur = __fsub_rn(u, __fmul_rn(cam.bf, invzc));
+  if (bForward) { q.min_level = octave; q.max_level = -1; }
+  else if (bBackward) { q.min_level = 0; q.max_level = octave; }
+  else { q.min_level = octave - 1; q.max_level = octave + 1; }
   return true;
 }
 
-// dynamic shared memory: state[cmax] ints + taken[cmax] bytes (cmax = cur stride rounded up)
-__global__ void __launch_bounds__(MATCH_THREADS) k_match_last(MatchBatch mb, MatchCam cam, int cmax) {
-  extern __shared__ __align__(16) unsigned char msm[];
-  __shared__ int s_off[GRID_CELLS + 1];
-  __shared__ int s_cur[GRID_CELLS];
-  __shared__ int ws[33];
-  __shared__ int s_hist[ORBM_HISTO_LENGTH];
-  __shared__ int s_keep[3];
-  __shared__ int s_acc, s_pruned;
-  int* state = reinterpret_cast<int*>(msm);
-  uint8_t* taken = msm + (size_t)cmax * 4;
-  const int p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
-  const int nc = mb.cn[p], nl = mb.ln[p];
-  const size_t co = (size_t)p * mb.cstride, lo = (size_t)p * mb.lstride;
-  const float *cx = mb.cx + co, *cy = mb.cy + co, *cang = mb.cang + co, *cur = mb.curight + co;
-  const int* coct = mb.coct + co;
-  const uint8_t* cdesc = mb.cdesc + co * 32;
-  const int* cobs = mb.cobs ? mb.cobs + co : nullptr;
-  const float* lxw = mb.lxw + lo * 3;
-  const uint8_t* lvalid = mb.lvalid + lo;
-  const int* loct = mb.loct + lo;
-  const float* lang = mb.lang + lo;
-  const uint8_t* ldesc = mb.ldesc + lo * 32;
-  const int* lobs = mb.lobs ? mb.lobs + lo : nullptr;
-  int* grididx = mb.grididx + co;
-  unsigned long long* topk = mb.topk + lo * MATCH_K;
-  int* ncand = mb.ncand + lo;
-  int* accepted = mb.accepted + lo;
-  int* out = mb.cur2last + co;
-  const float* Tc = mb.cTcw + (size_t)p * 16;
-  const float* Tl = mb.lTcw + (size_t)p * 16;
+// window set-up of one local-map point (:79-91)
+__device__ __forceinline__ bool setup_point_query(const MatchCam& cam, const PointsView& pv, int i, QueryGeom& q) {
+  if (!pv.in_view[i]) return false;
+  const int lvl = pv.level[i];
+  float r = ((double)pv.view_cos[i] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos :159-165
+  if (cam.th != 1.0f) r = __fmul_rn(r, cam.th);
+  q.u = pv.px[i]; q.v = pv.py[i];
+  q.r = __fmul_rn(r, cam.sf[lvl]);
+  q.rr = q.r;
+  q.ur = pv.pxr[i];
+  q.min_level = lvl - 1; q.max_level = lvl;
+  return true;
+}
 
-  // ---- A: grid ------------------------------------------------------------------------------------------
-  GridView gv;
-  gv.min_x = cam.min_x; gv.min_y = cam.min_y;
-  gv.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(cam.max_x, cam.min_x));   // src/Frame.cc:221-222
-  gv.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(cam.max_y, cam.min_y));
-  build_grid(nc, cx, cy, gv.min_x, gv.min_y, gv.inv_w, gv.inv_h, s_off, s_cur, grididx, ws);
-  gv.off = s_off; gv.idx = grididx;
-  for (int j = tid; j < nc; j += nthr) {
-    const bool pre = cobs && cobs[j] >= 0;
-    state[j] = pre ? -2 : -1;
-    taken[j] = 0;   // pre-existing entries with observations are filtered statically in walk_window
-  }
-  if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
-  if (tid == 0) { s_acc = 0; s_pruned = 0; }
-  // forward / backward decision (:1590-1602)
-  float twc[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {   // -Rcw.t()*tcw through the generic (double-accumulating) gemm
-    double s = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)Tc[k * 4 + i], (double)Tc[k * 4 + 3]));
-    twc[i] = __double2float_rn(-s);
-  }
-  const float Rl2[3] = {Tl[8], Tl[9], Tl[10]};
-  const float tlc2 = gemm3(Rl2, twc[0], twc[1], twc[2], Tl[11]);
-  const bool bForward = (tlc2 > cam.b) && !cam.mono;
-  const bool bBackward = (-tlc2 > cam.b) && !cam.mono;
-  __syncthreads();
-
-  // ---- B: independent part of every query -----------------------------------------------------------------
-  for (int i = tid; i < nl; i += nthr) {
-    unsigned long long k0 = ~0ull, k1 = ~0ull, k2 = ~0ull, k3 = ~0ull;
-    int n_c = 0;
-    if (lvalid[i]) {
-      LastQuery q;
-      if (setup_last_query(cam, Tc, bForward, bBackward, lxw + 3 * (size_t)i, loct[i], ldesc + 32 * (size_t)i, q)) {
-        n_c = walk_window(gv, q.g, cx, cy, coct, cur, cobs, cdesc, q.d0, q.d1, true,
-                          [&](int idx, int ord, int dist) {
-                            const unsigned long long k = mk_key(dist, ord, idx);
-                            if (k < k3) {
-                              if (k < k2) {
-                                k3 = k2;
-                                if (k < k1) {
-                                  k2 = k1;
-                                  if (k < k0) { k1 = k0; k0 = k; } else k1 = k;
-                                } else k2 = k;
-                              } else k3 = k;
-                            }
-                          });
-      }
-    }
-    topk[(size_t)i * MATCH_K + 0] = k0;
-    topk[(size_t)i * MATCH_K + 1] = k1;
-    topk[(size_t)i * MATCH_K + 2] = k2;
-    topk[(size_t)i * MATCH_K + 3] = k3;
-    ncand[i] = n_c;
-    accepted[i] = -1;
-  }
-  __syncthreads();
-
-  // ---- C: order-exact resolve (one warp, all lanes redundant) ---------------------------------------------
-  if (tid < 32) {
-    const int lane = tid;
-    for (int base = 0; base < nl; base += 32) {
-      const int i = base + lane;
-      unsigned long long k[MATCH_K];
-      int n_c = 0, obs = 0;
-#pragma unroll
-      for (int j = 0; j < MATCH_K; ++j) k[j] = (i < nl) ? topk[(size_t)i * MATCH_K + j] : ~0ull;
-      if (i < nl) {
-        n_c = ncand[i];
-        obs = lobs ? lobs[i] : cam.last_obs_default;
-      }
-      const int lim = min(32, nl - base);
-      for (int t = 0; t < lim; ++t) {
-        const int qn = __shfl_sync(0xffffffffu, n_c, t);
-        if (qn == 0) continue;
-        const int qobs = __shfl_sync(0xffffffffu, obs, t);
-        int best_idx = -1, best_dist = 256;
-        bool exhausted = true;
-#pragma unroll
-        for (int j = 0; j < MATCH_K; ++j) {
-          const unsigned long long kj = __shfl_sync(0xffffffffu, k[j], t);
-          if (best_idx < 0 && kj != ~0ull) {
-            const int idx = (int)(kj & 0xfffffull);
-            if (!taken[idx]) { best_idx = idx; best_dist = (int)(kj >> 40); exhausted = false; }
-          }
-        }
-        if (best_idx < 0 && qn <= MATCH_K) exhausted = false;   // every candidate is claimed: no match
-        if (exhausted && best_idx < 0) {
-          // more than K candidates and the K best are all claimed: re-walk the window with the claimed filter
-          const int qi = base + t;
-          LastQuery q;
-          if (setup_last_query(cam, Tc, bForward, bBackward, lxw + 3 * (size_t)qi, loct[qi], ldesc + 32 * (size_t)qi, q)) {
-            walk_window(gv, q.g, cx, cy, coct, cur, cobs, cdesc, q.d0, q.d1, true,
-                        [&](int idx, int /*ord*/, int dist) {
-                          if (!taken[idx] && dist < best_dist) { best_dist = dist; best_idx = idx; }
-                        });
-          }
-        }
-        if (best_idx >= 0 && best_dist <= ORBM_TH_HIGH) {
-          if (lane == 0) {
-            state[best_idx] = base + t;
-            if (qobs > 0) taken[best_idx] = 1;
-            accepted[base + t] = best_idx;
-          }
-        }
-        __syncwarp();
-      }
+// K8 (LAST): grid = (ceil(lstride / CAND_WARPS), npairs); one warp per last-frame keypoint
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_last(CurView cv, LastView lv, MatchCam cam, ListView out) {
+  const int p = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+  if (i >= lv.n[p]) return;
+  const size_t lo = (size_t)p * lv.stride;
+  unsigned* list = out.list + (lo + i) * LCAP;
+  int cnt = 0;
+  if (lv.valid[lo + i]) {
+    bool fwd, bwd;
+    motion_flags(cam, cv.Tcw + (size_t)p * 16, lv.Tcw + (size_t)p * 16, fwd, bwd);
+    QueryGeom q;
+    if (setup_last_query(cam, cv.Tcw + (size_t)p * 16, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], q)) {
+      const uint8_t* d = lv.desc + (lo + i) * 32;
+      const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+      const WalkCtx g = make_ctx(cv, cam, p);
+      cnt = warp_walk(g, q, d0, d1, [&](int ord, int idx, int dist) {
+        if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
+      });
     }
   }
-  __syncthreads();
+  if (lane == 0) out.count[lo + i] = (cnt > LCAP) ? -cnt : cnt;
+}
 
-  // ---- D: rotation consistency (:1683-1721) -----------------------------------------------------------------
-  int my_bins[4];   // up to 4 queries per thread at nl <= 4*nthr; generic loop recomputes otherwise
-  (void)my_bins;
-  int acc = 0;
-  for (int i = tid; i < nl; i += nthr) {
+// K8 (POINTS): grid = ceil(n / CAND_WARPS); a single current frame (instance 0)
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_points(CurView cv, PointsView pv, MatchCam cam, ListView out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+  if (i >= pv.n) return;
+  unsigned* list = out.list + (size_t)i * LCAP;
+  int cnt = 0;
+  QueryGeom q;
+  if (setup_point_query(cam, pv, i, q)) {
+    const uint8_t* d = pv.desc + (size_t)i * 32;
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+    const WalkCtx g = make_ctx(cv, cam, 0);
+    cnt = warp_walk(g, q, d0, d1, [&](int ord, int idx, int dist) {
+      if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
+    });
+  }
+  if (lane == 0) out.count[i] = (cnt > LCAP) ? -cnt : cnt;
+}
+
+// K8 (BOW): queries are (KF keypoint, F node range) pairs prepared by the host merge-join of the two FeatureVectors
+struct BowQueries {
+  const int* kf_idx;       // realIdxKF of query q
+  const int* f_beg;        // range of the matching F node inside f_idx
+  const int* f_end;
+  const unsigned* f_idx;   // concatenated F node lists (realIdxF)
+  const uint8_t* kf_desc;
+  const uint8_t* f_desc;
+  const float *kf_ang, *f_ang;
+  int nq, nf;
+};
+
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_bow(BowQueries bq, ListView out) {
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+  if (q >= bq.nq) return;
+  const uint8_t* d = bq.kf_desc + (size_t)bq.kf_idx[q] * 32;
+  const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+  const int b = bq.f_beg[q], n = bq.f_end[q] - b;
+  unsigned* list = out.list + (size_t)q * LCAP;
+  for (int e = lane; e < n && e < LCAP; e += 32) {
+    const unsigned idx = bq.f_idx[b + e];
+    list[e] = ((unsigned)hamming256(d0, d1, bq.f_desc + (size_t)idx * 32) << 20) | idx;
+  }
+  if (lane == 0) out.count[q] = (n > LCAP) ? -n : n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K9 helpers: warp-wide "first minimum among unclaimed entries" over one candidate list
+// ---------------------------------------------------------------------------------------------------------------------
+struct Pick { int idx, dist, ord; };
+
+// entries e = lane and lane+32 held in registers (v0, v1); `skip` = ord to ignore (second-best pass) or -1
+__device__ __forceinline__ Pick pick_min(unsigned v0, unsigned v1, int n, const uint8_t* taken, int skip, int lane) {
+  unsigned k0 = KEY_INF, k1 = KEY_INF;
+  if (lane < n && lane != skip && !taken[v0 & 0xfffffu]) k0 = ((v0 >> 20) << 6) | (unsigned)lane;
+  if (lane + 32 < n && lane + 32 != skip && !taken[v1 & 0xfffffu]) k1 = ((v1 >> 20) << 6) | (unsigned)(lane + 32);
+  const unsigned m = __reduce_min_sync(0xffffffffu, min(k0, k1));
+  Pick pk{-1, 256, -1};
+  if (m != KEY_INF) {
+    pk.ord = (int)(m & 63u);
+    pk.dist = (int)(m >> 6);
+    const unsigned src = (pk.ord < 32) ? v0 : v1;
+    pk.idx = (int)(__shfl_sync(0xffffffffu, src, pk.ord & 31) & 0xfffffu);
+  }
+  return pk;
+}
+
+// 64-bit (dist, ord, idx) warp min used by the overflow re-walks
+__device__ __forceinline__ unsigned long long warp_min64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = (t < v) ? t : v;
+  }
+  return v;
+}
+__device__ __forceinline__ unsigned long long key64(int dist, int ord, int idx) {
+  return ((unsigned long long)dist << 44) | ((unsigned long long)ord << 22) | (unsigned long long)idx;
+}
+
+// rotation histogram + prune shared by LAST and BOW (:1700-1721 / :338-360).  accepted[q] = claimed cur index or -1;
+// state[] is the pointer state of the current frame; returns the number of pruned entries (warp-uniform).
+__device__ __forceinline__ int prune_rotation(int nq, const int* accepted, const float* qang, const int* qmap,
+                                              const float* cang, int* state, int* s_hist, int* s_keep, int lane) {
+  for (int b = lane; b < ORBM_HISTO_LENGTH; b += 32) s_hist[b] = 0;
+  __syncwarp();
+  for (int i = lane; i < nq; i += 32) {
+    const int idx = accepted[i];
+    if (idx >= 0) atomicAdd(&s_hist[rot_bin(qang[qmap ? qmap[i] : i], cang[idx])], 1);
+  }
+  __syncwarp();
+  if (lane == 0) three_maxima(s_hist, s_keep);
+  __syncwarp();
+  int pr = 0;
+  for (int i = lane; i < nq; i += 32) {
     const int idx = accepted[i];
     if (idx >= 0) {
-      ++acc;
-      if (cam.check_ori) {
-        float rot = __fsub_rn(lang[i], cang[idx]);
-        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-        int bin = (int)roundf(__fmul_rn(rot, 1.0f / ORBM_HISTO_LENGTH));
-        if (bin == ORBM_HISTO_LENGTH) bin = 0;
-        atomicAdd(&s_hist[bin], 1);
+      const int bin = rot_bin(qang[qmap ? qmap[i] : i], cang[idx]);
+      if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) {
+        state[idx] = -1;   // every writer stores NULL: order-free
+        ++pr;
       }
     }
   }
-  if (acc) atomicAdd(&s_acc, acc);
-  __syncthreads();
-  if (cam.check_ori) {
-    if (tid == 0) {   // ComputeThreeMaxima (:1912-1957)
-      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
-      for (int i = 0; i < ORBM_HISTO_LENGTH; ++i) {
-        const int s = s_hist[i];
-        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
-        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
-        else if (s > max3) { max3 = s; ind3 = i; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+  return pr;
+}
+
+// K9/K10 (LAST): one warp per pair.  dynamic smem: state[cmax] ints + taken[cmax] bytes
+__global__ void __launch_bounds__(32) k_resolve_last(CurView cv, LastView lv, MatchCam cam, ListView in, int* accepted,
+                                                     int* cur2last, int* nmatch, int cmax) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  __shared__ int s_hist[ORBM_HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  int* state = reinterpret_cast<int*>(rsm);
+  uint8_t* taken = rsm + (size_t)cmax * 4;
+  const int p = blockIdx.x, lane = threadIdx.x;
+  const int nc = cv.n[p], nl = lv.n[p];
+  const size_t co = (size_t)p * cv.stride, lo = (size_t)p * lv.stride;
+  const int* cobs = cv.obs ? cv.obs + co : nullptr;
+  const int* lobs = lv.obs ? lv.obs + lo : nullptr;
+  int* acc = accepted + lo;
+  for (int j = lane; j < nc; j += 32) {
+    state[j] = (cobs && cobs[j] >= 0) ? -2 : -1;
+    taken[j] = 0;
+  }
+  __syncwarp();
+  bool fwd = false, bwd = false;
+  motion_flags(cam, cv.Tcw + (size_t)p * 16, lv.Tcw + (size_t)p * 16, fwd, bwd);
+  const WalkCtx g = make_ctx(cv, cam, p);
+  int n_acc = 0;
+  // software pipeline: entries of query i+1 are loaded while query i is resolved
+  const unsigned* L = in.list + lo * LCAP;
+  const int* C = in.count + lo;
+  unsigned v0 = 0, v1 = 0;
+  int cn = 0;
+  if (nl > 0) { cn = C[0]; v0 = L[lane]; v1 = L[lane + 32]; }
+  for (int i = 0; i < nl; ++i) {
+    unsigned nv0 = 0, nv1 = 0;
+    int ncn = 0;
+    if (i + 1 < nl) { ncn = C[i + 1]; nv0 = L[(size_t)(i + 1) * LCAP + lane]; nv1 = L[(size_t)(i + 1) * LCAP + lane + 32]; }
+    int best_idx = -1, best_dist = 256;
+    if (cn > 0) {
+      const Pick pk = pick_min(v0, v1, cn, taken, -1, lane);
+      best_idx = pk.idx; best_dist = pk.dist;
+    } else if (cn < 0) {   // overflowed list: exact re-walk with the claimed filter
+      QueryGeom q;
+      if (setup_last_query(cam, cv.Tcw + (size_t)p * 16, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], q)) {
+        const uint8_t* d = lv.desc + (lo + i) * 32;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+        unsigned long long bk = ~0ull;
+        warp_walk(g, q, d0, d1, [&](int ord, int idx, int dist) {
+          if (!taken[idx]) { const unsigned long long k = key64(dist, ord, idx); bk = (k < bk) ? k : bk; }
+        });
+        bk = warp_min64(bk);
+        if (bk != ~0ull) { best_idx = (int)(bk & 0x3fffffull); best_dist = (int)(bk >> 44); }
       }
-      if ((float)max2 < __fmul_rn(0.1f, (float)max1)) { ind2 = -1; ind3 = -1; }
-      else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) { ind3 = -1; }
-      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
     }
-    __syncthreads();
-    int pr = 0;
-    for (int i = tid; i < nl; i += nthr) {
-      const int idx = accepted[i];
-      if (idx >= 0) {
-        float rot = __fsub_rn(lang[i], cang[idx]);
-        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
-        int bin = (int)roundf(__fmul_rn(rot, 1.0f / ORBM_HISTO_LENGTH));
-        if (bin == ORBM_HISTO_LENGTH) bin = 0;
-        if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) {
-          state[idx] = -1;   // every writer stores NULL: order-free
-          ++pr;
+    int a = -1;
+    if (best_idx >= 0 && best_dist <= ORBM_TH_HIGH) {
+      a = best_idx;
+      ++n_acc;
+      if (lane == 0) {
+        state[best_idx] = i;
+        if ((lobs ? lobs[i] : cam.last_obs_default) > 0) taken[best_idx] = 1;
+      }
+    }
+    if (lane == 0) acc[i] = a;
+    __syncwarp();
+    v0 = nv0; v1 = nv1; cn = ncn;
+  }
+  int pruned = 0;
+  if (cam.check_ori) pruned = prune_rotation(nl, acc, lv.ang + lo, nullptr, cv.ang + co, state, s_hist, s_keep, lane);
+  __syncwarp();
+  int* out = cur2last + co;
+  for (int j = lane; j < nc; j += 32) out[j] = state[j];
+  if (lane == 0) nmatch[p] = n_acc - pruned;
+}
+
+// K9 (POINTS): best and second best among unclaimed candidates, level-aware ratio test (:98-152)
+__global__ void __launch_bounds__(32) k_resolve_points(CurView cv, PointsView pv, MatchCam cam, ListView in, int* f2pt,
+                                                       int* nmatch, int cmax) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  int* state = reinterpret_cast<int*>(rsm);
+  uint8_t* taken = rsm + (size_t)cmax * 4;
+  const int lane = threadIdx.x;
+  const int nc = cv.n[0];
+  for (int j = lane; j < nc; j += 32) {
+    state[j] = (cv.obs && cv.obs[j] >= 0) ? -2 : -1;
+    taken[j] = 0;
+  }
+  __syncwarp();
+  const WalkCtx g = make_ctx(cv, cam, 0);
+  int n_acc = 0;
+  for (int i = 0; i < pv.n; ++i) {
+    const int cn = in.count[i];
+    if (cn == 0) continue;
+    int bestIdx = -1, bestDist = 256, bestDist2 = 256, bestLevel = -1, bestLevel2 = -1;
+    if (cn > 0) {
+      const unsigned v0 = in.list[(size_t)i * LCAP + lane], v1 = in.list[(size_t)i * LCAP + lane + 32];
+      const Pick p1 = pick_min(v0, v1, cn, taken, -1, lane);
+      if (p1.idx >= 0) {
+        bestIdx = p1.idx; bestDist = p1.dist; bestLevel = cv.oct[p1.idx];
+        const Pick p2 = pick_min(v0, v1, cn, taken, p1.ord, lane);
+        if (p2.idx >= 0) { bestDist2 = p2.dist; bestLevel2 = cv.oct[p2.idx]; }
+      }
+    } else {
+      QueryGeom q;
+      if (setup_point_query(cam, pv, i, q)) {
+        const uint8_t* d = pv.desc + (size_t)i * 32;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+        unsigned long long b1 = ~0ull, b2 = ~0ull;   // two smallest keys per lane
+        warp_walk(g, q, d0, d1, [&](int ord, int idx, int dist) {
+          if (!taken[idx]) {
+            const unsigned long long k = key64(dist, ord, idx);
+            if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
+          }
+        });
+        const unsigned long long m1 = warp_min64(b1);
+        if (m1 != ~0ull) {
+          bestIdx = (int)(m1 & 0x3fffffull); bestDist = (int)(m1 >> 44); bestLevel = cv.oct[bestIdx];
+          const unsigned long long m2 = warp_min64((b1 == m1) ? b2 : b1);
+          if (m2 != ~0ull) { bestDist2 = (int)(m2 >> 44); bestLevel2 = cv.oct[(int)(m2 & 0x3fffffull)]; }
         }
       }
     }
-    if (pr) atomicAdd(&s_pruned, pr);
-    __syncthreads();
+    if (bestIdx >= 0 && bestDist <= ORBM_TH_HIGH) {
+      if (bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(cam.nnratio, (float)bestDist2)) continue;
+      ++n_acc;
+      if (lane == 0) {
+        state[bestIdx] = i;
+        if ((pv.obs ? pv.obs[i] : cam.last_obs_default) > 0) taken[bestIdx] = 1;
+      }
+      __syncwarp();
+    }
   }
-  for (int j = tid; j < nc; j += nthr) out[j] = state[j];
-  if (tid == 0) mb.nmatch[p] = s_acc - s_pruned;
+  __syncwarp();
+  for (int j = lane; j < nc; j += 32) f2pt[j] = state[j];
+  if (lane == 0) *nmatch = n_acc;
+}
+
+// K9/K10 (BOW): claimed = any assignment (:273-274); TH_LOW and ratio on the two best (:292-299)
+__global__ void __launch_bounds__(32) k_resolve_bow(BowQueries bq, float nnratio, int check_ori, ListView in, int* accepted,
+                                                    int* f2kf, int* nmatch, int cmax) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  __shared__ int s_hist[ORBM_HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  int* state = reinterpret_cast<int*>(rsm);
+  uint8_t* taken = rsm + (size_t)cmax * 4;
+  const int lane = threadIdx.x;
+  for (int j = lane; j < bq.nf; j += 32) { state[j] = -1; taken[j] = 0; }
+  __syncwarp();
+  int n_acc = 0;
+  for (int q = 0; q < bq.nq; ++q) {
+    const int cn = in.count[q];
+    int a = -1;
+    int best1 = 256, best2 = 256, bestIdx = -1;
+    if (cn > 0) {
+      const unsigned v0 = in.list[(size_t)q * LCAP + lane], v1 = in.list[(size_t)q * LCAP + lane + 32];
+      const Pick p1 = pick_min(v0, v1, cn, taken, -1, lane);
+      if (p1.idx >= 0) {
+        bestIdx = p1.idx; best1 = p1.dist;
+        const Pick p2 = pick_min(v0, v1, cn, taken, p1.ord, lane);
+        if (p2.idx >= 0) best2 = p2.dist;
+      }
+    } else if (cn < 0) {   // long node list: recompute over the whole range
+      const uint8_t* d = bq.kf_desc + (size_t)bq.kf_idx[q] * 32;
+      const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+      unsigned long long b1 = ~0ull, b2 = ~0ull;
+      const int b = bq.f_beg[q], n = -cn;
+      for (int e = lane; e < n; e += 32) {
+        const int idx = (int)bq.f_idx[b + e];
+        if (!taken[idx]) {
+          const unsigned long long k = key64(hamming256(d0, d1, bq.f_desc + (size_t)idx * 32), e, idx);
+          if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
+        }
+      }
+      const unsigned long long m1 = warp_min64(b1);
+      if (m1 != ~0ull) {
+        bestIdx = (int)(m1 & 0x3fffffull); best1 = (int)(m1 >> 44);
+        const unsigned long long m2 = warp_min64((b1 == m1) ? b2 : b1);
+        if (m2 != ~0ull) best2 = (int)(m2 >> 44);
+      }
+    }
+    if (bestIdx >= 0 && best1 <= ORBM_TH_LOW && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
+      a = bestIdx;
+      ++n_acc;
+      if (lane == 0) { state[bestIdx] = bq.kf_idx[q]; taken[bestIdx] = 1; }
+    }
+    if (lane == 0) accepted[q] = a;
+    __syncwarp();
+  }
+  int pruned = 0;
+  if (check_ori) pruned = prune_rotation(bq.nq, accepted, bq.kf_ang, bq.kf_idx, bq.f_ang, state, s_hist, s_keep, lane);
+  __syncwarp();
+  for (int j = lane; j < bq.nf; j += 32) f2kf[j] = state[j];
+  if (lane == 0) *nmatch = n_acc - pruned;
 }
 
 }  // namespace b200

@@ -13,6 +13,8 @@
 //   kps/desc  per frame: cap x OrbxKeyPoint (28 B) / cap x 32 B, level-major like operator() concatenates
 #pragma once
 #include "common.cuh"
+#define B200_HD __host__ __device__ __forceinline__
+#include "../../include/glibc_sincosf.h"
 
 namespace b200 {
 
@@ -606,8 +608,8 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(LevelTab lt, Orie
   // ---- steered BRIEF ----
   const float factorPI = (float)(3.14159265358979323846 / 180.f);
   const float ang = __fmul_rn(angle, factorPI);
-  // cosf/sinf of the reference (glibc, correctly rounded in practice): evaluate in double, round once
-  const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+  // cos()/sin() of the reference bind to glibc's cosf/sinf, which are NOT correctly rounded: run the same algorithm
+  const float a = b200_cosf(ang), b = b200_sinf(ang);
   const uint8_t* bc = blr.p[l] + (size_t)f * blr.fstride[l] + (size_t)y * blr.pitch[l] + x;
   const int bp = blr.pitch[l];
   unsigned word = 0;

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import FrameView, LastView, ptr  # noqa: F401
+from ._abi import BowView, FrameView, LastView, TrackPointsView, ptr  # noqa: F401
 
 
 class ORBmatcher:
@@ -41,16 +41,34 @@ class ORBmatcher:
         assert a.size == 32 and b.size == 32
         return int(_lib.lib().orbm_hamming(ptr(a), ptr(b)))
 
-    def SearchByProjection(self, CurrentFrame: FrameView, LastFrame: LastView, th: float, bMono: bool = False):
-        """SearchByProjection(Frame&, const Frame&, th, bMono) (src/ORBmatcher.cc:1578-1724).
-        Returns (nmatches, cur2last) with cur2last[j] = LastFrame index now in CurrentFrame.mvpMapPoints[j]
-        (-1 NULL, -2 untouched pre-existing entry)."""
-        out = np.full(CurrentFrame.n, -1, np.int32)
+    def SearchByProjection(self, F: FrameView, other, th: float, bMono: bool = False):
+        """Overloads of the reference:
+          (Frame&, const Frame& LastFrame, th, bMono)      src/ORBmatcher.cc:1578-1724  -> other is a LastView
+          (Frame&, const vector<MapPoint*>&, th)            src/ORBmatcher.cc:63-156     -> other is a TrackPointsView
+        Returns (nmatches, index vector): entry j = index of the LastFrame keypoint / MapPoint now held by
+        F.mvpMapPoints[j] (-1 NULL, -2 untouched pre-existing entry)."""
+        out = np.full(F.n, -1, np.int32)
         nm = C.c_int(0)
-        cs, ls = CurrentFrame.struct(), LastFrame.struct()
-        _lib.check(self._L.orbm_search_by_projection_last(self._h, C.byref(cs), C.byref(ls), float(th), int(bMono),
-                                                          self.mfNNratio, int(self.mbCheckOrientation), ptr(out),
-                                                          C.byref(nm)))
+        fs, os_ = F.struct(), other.struct()
+        if isinstance(other, LastView):
+            _lib.check(self._L.orbm_search_by_projection_last(self._h, C.byref(fs), C.byref(os_), float(th), int(bMono),
+                                                              self.mfNNratio, int(self.mbCheckOrientation), ptr(out),
+                                                              C.byref(nm)))
+        elif isinstance(other, TrackPointsView):
+            _lib.check(self._L.orbm_search_by_projection_points(self._h, C.byref(fs), C.byref(os_), float(th),
+                                                                self.mfNNratio, ptr(out), C.byref(nm)))
+        else:
+            raise TypeError("SearchByProjection: second argument must be a LastView or a TrackPointsView")
+        return nm.value, out
+
+    def SearchByBoW(self, pKF: BowView, F: BowView):
+        """SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:217-363) -> (nmatches, f2kf) with
+        f2kf[j] = keyframe keypoint whose MapPoint lands in vpMapPointMatches[j], or -1."""
+        out = np.full(F.n, -1, np.int32)
+        nm = C.c_int(0)
+        ks, fs = pKF.struct(), F.struct()
+        _lib.check(self._L.orbm_search_by_bow(self._h, C.byref(ks), C.byref(fs), self.mfNNratio,
+                                              int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
 
     def launch_count(self) -> int:

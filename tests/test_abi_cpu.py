@@ -1,0 +1,58 @@
+"""CPU suite: the C-ABI library loads, exports every symbol include/b200orb.h declares, and refuses to run without a
+GPU (no silent CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "b200orb.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:orbx|orbm|orbs|ocm|b200orb)_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    import orb_slam2_ssd_semantic_b200 as pkg
+    L = pkg.lib()
+    names = _declared()
+    assert len(names) > 40
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, "declared in include/b200orb.h but not exported: %s" % missing
+
+
+def test_python_binding_lists_match_header():
+    from orb_slam2_ssd_semantic_b200._lib import EXPORTS
+    assert set(EXPORTS) <= set(_declared())
+
+
+def test_struct_layouts_match_header():
+    from orb_slam2_ssd_semantic_b200 import _abi
+    from orb_slam2_ssd_semantic_b200.extractor import KP_DTYPE
+    assert KP_DTYPE.itemsize == 28 and C.sizeof(_abi.OrbxParams) == 20
+    assert C.sizeof(_abi.OrbmFrame) == 8 + 7 * 8 + 64 + 10 * 4 + 8 + 8     # n(+pad), 7 ptrs, Tcw, 10 floats, ptr, nlevels(+pad)
+    assert C.sizeof(_abi.OrbmLast) == 8 + 6 * 8 + 64
+    assert C.sizeof(_abi.OcmParams) == 5 * 8 + 4 * 4 + 8
+
+
+def test_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import orb_slam2_ssd_semantic_b200 as pkg
+    for ctor in (pkg.ORBextractor, pkg.ORBmatcher, pkg.StreamTracker, pkg.PointCloudMapping):
+        with pytest.raises(pkg.B200OrbError) as e:
+            ctor()
+        assert e.value.code == -4 and "no CPU fallback" in str(e.value)
+
+
+def test_hamming_host_inline():
+    import numpy as np
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    a = np.arange(32, dtype=np.uint8)
+    b = np.zeros(32, np.uint8)
+    assert ORBmatcher.DescriptorDistance(a, b) == int(np.unpackbits(a).sum())
+    assert ORBmatcher.TH_HIGH == 100 and ORBmatcher.TH_LOW == 50 and ORBmatcher.HISTO_LENGTH == 30

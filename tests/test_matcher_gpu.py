@@ -96,3 +96,69 @@ def test_hamming_matches_oracle(oracle):
     for _ in range(50):
         a, b = rng.integers(0, 256, size=(2, 32), dtype=np.uint8)
         assert ORBmatcher.DescriptorDistance(a, b) == oracle.hamming(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+def _points_view(oracle, K, D, depth, T_pts, T_cur, sf, rng, noise=0.0):
+    """MapPoints = unprojected keypoints of another frame; the isInFrustum fields are computed here in float like
+    src/Frame.cc:387-451 does (the C-ABI takes them as inputs)."""
+    from orb_slam2_ssd_semantic_b200._abi import TrackPointsView
+    _, _, xw, valid = oracle.stereo_unproject(K, depth, T_pts, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+    R, t = T_cur[:3, :3].astype(np.float32), T_cur[:3, 3].astype(np.float32)
+    Pc = (xw @ R.T + t).astype(np.float32)
+    invz = (np.float32(1.0) / Pc[:, 2]).astype(np.float32)
+    u = (np.float32(synth.FX) * Pc[:, 0] * invz + np.float32(synth.CX)).astype(np.float32) + rng.normal(0, noise, len(K)).astype(np.float32)
+    v = (np.float32(synth.FY) * Pc[:, 1] * invz + np.float32(synth.CY)).astype(np.float32) + rng.normal(0, noise, len(K)).astype(np.float32)
+    inview = (valid > 0) & (Pc[:, 2] > 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480)
+    xr = (u - np.float32(synth.BF) * invz).astype(np.float32)
+    level = np.clip(K["octave"] + rng.integers(-1, 2, len(K)), 0, 7).astype(np.int32)
+    vcos = np.where(rng.random(len(K)) < 0.5, 0.9995, 0.9).astype(np.float32)
+    return TrackPointsView(inview.astype(np.uint8), u, v, xr, level, vcos, D, mp_obs=rng.integers(0, 3, len(K)).astype(np.int32))
+
+
+@pytest.mark.parametrize("th", [1.0, 3.0, 5.0])
+def test_projection_points_local_map(oracle, stream_feats, th):
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    from orb_slam2_ssd_semantic_b200._abi import FrameView
+    feats, sf = stream_feats
+    rng = np.random.default_rng(11)
+    Kc, Dc, dc, Tc = feats[2]
+    ur, _, _, _ = oracle.stereo_unproject(Kc, dc, Tc, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+    for src in (0, 1, 3):
+        Kl, Dl, dl, Tl = feats[src]
+        F = FrameView(Kc["x"], Kc["y"], Kc["octave"], Kc["angle"], ur, Dc, Tc, synth.FX, synth.FY, synth.CX, synth.CY,
+                      synth.BF, 0.0, 640.0, 0.0, 480.0, sf)
+        if src == 3:
+            F.mp_obs = rng.integers(-1, 2, F.n).astype(np.int32)
+        pts = _points_view(oracle, Kl, Dl, dl, Tl, Tc, sf, rng, noise=0.5)
+        for ratio in (0.8, 0.6):
+            n_ref, ref = oracle.search_by_projection_points(F, pts, th, ratio)
+            n_gpu, gpu = ORBmatcher(ratio, True).SearchByProjection(F, pts, th)
+            assert n_ref > 20
+            assert n_gpu == n_ref and (gpu == ref).all(), (src, th, ratio)
+
+
+def _bow_view(D, ang, rng, nwords, valid=None):
+    """Synthetic FeatureVector: node = a few descriptor bits (stands in for the absent DBoW2 vocabulary)."""
+    from orb_slam2_ssd_semantic_b200._abi import BowView
+    node = (D[:, 0].astype(np.int64) * 7 + D[:, 5].astype(np.int64)) % nwords
+    fv = {}
+    for i, w in enumerate(node):
+        fv.setdefault(int(w), []).append(i)
+    return BowView(D, ang, fv, valid)
+
+
+@pytest.mark.parametrize("nwords", [3, 40, 400])
+def test_search_by_bow(oracle, stream_feats, nwords):
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    feats, sf = stream_feats
+    rng = np.random.default_rng(13)
+    Kk, Dk, _, _ = feats[0]
+    Kf, Df, _, _ = feats[1]
+    valid = (rng.random(len(Kk)) < 0.8).astype(np.uint8)
+    kf = _bow_view(Dk, Kk["angle"], rng, nwords, valid)
+    f = _bow_view(Df, Kf["angle"], rng, nwords)
+    for ratio, ori in ((0.7, True), (0.9, True), (0.75, False)):
+        n_ref, ref = oracle.search_by_bow(kf, f, ratio, ori)
+        n_gpu, gpu = ORBmatcher(ratio, ori).SearchByBoW(kf, f)
+        assert n_gpu == n_ref and (gpu == ref).all(), (nwords, ratio, ori)
+    assert n_ref > 5

@@ -1,0 +1,181 @@
+"""CPU suite: pins the C++ oracle (test infrastructure) against (a) the committed golden vectors generated with the
+real OpenCV primitives / the pure-Python restatements, (b) cv2 itself when it is importable, (c) artefacts of the
+reference (map.bin keyframes, octomap.ot log-odds lattice)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from orb_slam2_ssd_semantic_b200 import synth
+from orb_slam2_ssd_semantic_b200._abi import FrameView, LastView
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _views(z):
+    fx, fy, cx, cy, bf = [float(v) for v in z["cam"]]
+    cur = FrameView(z["cur_x"], z["cur_y"], z["cur_oct"], z["cur_angle"], z["cur_uright"], z["cur_desc"], z["cur_Tcw"], fx,
+                    fy, cx, cy, bf, 0.0, 640.0, 0.0, 480.0, z["sf"])
+    last = LastView(z["last_xw"], z["last_valid"], z["last_oct"], z["last_angle"], z["last_desc"], z["last_Tcw"],
+                    mp_obs=np.ones(len(z["last_valid"]), np.int32))
+    return cur, last
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(G, "extract_*.npz"))))
+def test_extractor_oracle_reproduces_cv2_golden(oracle, path):
+    z = np.load(path)
+    prm = z["params"]
+    R = oracle.RefExtractor(int(prm[0]), float(prm[1]), int(prm[2]), int(prm[3]), int(prm[4]))
+    K, D = R(z["image"])
+    assert (R.candidates_per_level == z["candidates"]).all()
+    assert K.tobytes() == z["kps"].tobytes()
+    assert (D == z["desc"]).all()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(G, "match_mapbin_*.npz"))))
+def test_matcher_oracle_reproduces_mapbin_golden(oracle, path):
+    z = np.load(path)
+    cur, last = _views(z)
+    n, m = oracle.search_by_projection_last(cur, last, float(z["th"]), False, 0.9, True)
+    assert n == int(z["nmatches"]) and n > 100
+    assert (m == z["cur2last"]).all()
+
+
+def test_matcher_oracle_vs_python_restatement_random(oracle):
+    """Small random frames: C++ oracle == pure-Python restatement, incl. pre-existing points, obs=0 double claims,
+    no-orientation and mono variants."""
+    from oracle import match_py
+    rng = np.random.default_rng(5)
+    sf = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2), np.float32)])).astype(np.float32)
+    for case in range(12):
+        n = int(rng.integers(40, 160))
+        x = rng.uniform(5, 635, n).astype(np.float32)
+        y = rng.uniform(5, 475, n).astype(np.float32)
+        octv = rng.integers(0, 8, n).astype(np.int32)
+        desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        T = np.eye(4, dtype=np.float32)
+        T[:3, 3] = rng.normal(0, 0.02, 3)
+        if case % 4 == 1:
+            T[2, 3] = 0.3
+        if case % 4 == 2:
+            T[2, 3] = -0.3
+        z = rng.uniform(0.5, 4.0, n).astype(np.float32)
+        ur = np.where(rng.random(n) < 0.7, x - synth.BF / z, -1).astype(np.float32)
+        cur = FrameView(x, y, octv, rng.uniform(0, 360, n).astype(np.float32), ur, desc, T, synth.FX, synth.FY, synth.CX,
+                        synth.CY, synth.BF, 0, 640, 0, 480, sf)
+        if case % 3 == 0:
+            cur.mp_obs = rng.integers(-1, 2, n).astype(np.int32)
+        m = int(rng.integers(40, 160))
+        sel = rng.integers(0, n, m)
+        zz = z[sel] * rng.uniform(0.98, 1.02, m).astype(np.float32)
+        xw = np.stack([(x[sel] + rng.normal(0, 3, m) - synth.CX) * zz / synth.FX,
+                       (y[sel] + rng.normal(0, 3, m) - synth.CY) * zz / synth.FY, zz], 1).astype(np.float32)
+        d2 = desc[sel].copy()
+        d2[:, :4] ^= rng.integers(0, 256, size=(m, 4), dtype=np.uint8)
+        last = LastView(xw, (rng.random(m) < 0.9).astype(np.uint8), np.clip(octv[sel] + rng.integers(-1, 2, m), 0, 7),
+                        rng.uniform(0, 360, m).astype(np.float32), d2, np.eye(4, dtype=np.float32),
+                        mp_obs=rng.integers(0, 2, m).astype(np.int32))
+        chk = case % 5 != 4
+        mono = case == 7
+        n1, m1 = oracle.search_by_projection_last(cur, last, 15.0, mono, 0.9, chk)
+        n2, m2 = match_py.search_by_projection_last(cur, last, 15.0, mono, chk)
+        assert n1 == n2 and (m1 == m2).all(), "case %d" % case
+
+
+def test_primitives_against_cv2(oracle):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (h, w) in [(480, 640), (97, 131), (33, 47)]:
+        img = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+        dw, dh = int(round(w / 1.2)), int(round(h / 1.2))
+        assert (cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR) == oracle.resize(img, dw, dh)).all()
+        blur = cv2.GaussianBlur(img, (7, 7), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+        assert (blur == oracle.blur(img)).all()
+    img = synth.synth_frame(3, 1)
+    for t in (20, 7):
+        det = cv2.FastFeatureDetector_create(threshold=t, nonmaxSuppression=True)
+        for (y0, x0, hh, ww) in [(16, 16, 38, 37), (100, 200, 37, 36), (0, 0, 60, 60), (400, 500, 9, 9)]:
+            roi = img[y0:y0 + hh, x0:x0 + ww]
+            k = det.detect(roi)
+            f = oracle.fast(roi, t)
+            assert len(k) == len(f)
+            assert all((int(a.pt[0]), int(a.pt[1]), int(a.response)) == tuple(b) for a, b in zip(k, f))
+    for _ in range(2000):
+        yv, xv = [float(v) for v in rng.integers(-200000, 200000, 2)]
+        assert oracle.fast_atan2(yv, xv) == np.float32(cv2.fastAtan2(yv, xv))
+
+
+def test_full_extractor_against_cv2_restatement(oracle):
+    pytest.importorskip("cv2")
+    from oracle.orb_cv2 import ORBextractorCV2
+    img = synth.synth_frame(21, 4, h=240, w=320)
+    K, D = oracle.RefExtractor(400, 1.2, 6, 20, 7)(img)
+    K2, D2 = ORBextractorCV2(400, 1.2, 6, 20, 7)(img)
+    assert K.tobytes() == K2.tobytes() and (D == D2).all()
+
+
+def test_scale_tables(oracle):
+    R = oracle.RefExtractor(1000, 1.2, 8, 20, 7)
+    assert R.mnFeaturesPerLevel.tolist() == [217, 181, 151, 126, 105, 87, 73, 60]
+    assert oracle.RefExtractor(2000, 1.2, 8, 20, 7).mnFeaturesPerLevel.tolist() == [434, 362, 302, 251, 209, 175, 145, 122]
+    assert R.umax.tolist() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    R(synth.synth_frame(1, 0))
+    assert [R.level(l).shape for l in range(8)] == [(480, 640), (400, 533), (333, 444), (278, 370), (231, 309),
+                                                    (193, 257), (161, 214), (134, 179)]
+
+
+def test_octomap_artifact_pins_logodds_lattice(oracle):
+    """Every node value stored in the reference's octomap.ot is reachable by the oracle's clamp-add update rule with
+    its (hit, miss, clamp) constants -> pins setProbHit/Miss/ClampingThres and float32 storage."""
+    z = np.load(os.path.join(G, "octomap_logodds.npz"))
+    hit, miss, cmin, cmax = oracle.RefOccupancy().constants()
+    assert abs(hit - 0.8473) < 1e-4 and abs(miss + 0.405465) < 1e-6
+    assert abs(cmin + 1.99243) < 1e-5 and abs(cmax - 3.4761) < 1e-4
+    reach = {np.float32(0.0)}
+    frontier = [np.float32(0.0)]
+    while frontier and len(reach) < 20000:
+        nxt = []
+        for v in frontier:
+            for d in (hit, miss):
+                w = np.float32(min(max(np.float32(v + d), cmin), cmax))
+                if w not in reach:
+                    reach.add(w)
+                    nxt.append(w)
+        frontier = nxt
+    r = np.array(sorted(reach), np.float32)
+    vals = z["values"]
+    assert vals.min() >= cmin - 1e-6 and vals.max() <= cmax + 1e-6
+    d = np.abs(vals[:, None] - r[None, :]).min(axis=1)
+    assert d.max() < 2e-6, "octomap.ot holds values off the oracle's log-odds lattice: %s" % vals[d.argmax()]
+
+
+def test_occupancy_oracle_properties(oracle):
+    ws = synth.WallStream(seed=5, n=2)
+    gray, depth, rgb, T = ws.frame(0)
+    R = oracle.RefOccupancy()
+    n = R.insert_keyframe(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY)
+    pts, col, lab = R.last_points()
+    assert n == len(pts) > 1000
+    # the wall is the plane z_w = 2: every centroid lies on it; leaf filter keeps < 1 point per cm^3 cell
+    assert np.abs(pts[:, 2] - 2.0).max() < 2e-3
+    keys, lo = R.export_leaves()
+    assert len(np.unique(keys, axis=0)) == len(keys) and np.allclose(lo, R.constants()[0])
+    # ray: end cell excluded, first cell is the origin's, consecutive cells are face neighbours
+    ray = R.ray([0.01, 0.02, 0.03], [1.234, -0.5, 2.2]).astype(np.int64)
+    assert (ray[0] == 32768).all()
+    assert (np.abs(np.diff(ray, axis=0)).sum(axis=1) == 1).all()
+    end = (np.floor(np.array([1.234, -0.5, 2.2]) / 0.05) + 32768).astype(np.int64)
+    assert not (ray == end).all(axis=1).any() and np.abs(ray[-1] - end).sum() == 1
+
+
+def test_restated_glibc_sincosf_equals_host_libm(oracle):
+    """The CUDA kernel runs include/glibc_sincosf.h; the oracle calls the host libm like the reference does
+    (src/ORBextractor.cc:97).  They must agree on every float angle the descriptor path can see ([0, 2 pi])."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orb_ref_sincosf_mismatches.restype = C.c_long
+    L.orb_ref_sincosf_mismatches.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    two_pi_bits = int(np.float32(6.2831855).view(np.uint32))
+    assert L.orb_ref_sincosf_mismatches(0, two_pi_bits + 64, 53) == 0        # ~20 M angles, every binade
+    assert L.orb_ref_sincosf_mismatches(int(np.float32(3.0).view(np.uint32)), two_pi_bits, 1) == 0   # dense top binade
