@@ -43,10 +43,30 @@ int resolve_smem(int cmax, size_t* smem, const void* func) {
 }
 }  // namespace
 
-// Enqueue grid build + candidates + resolve of `npairs` (cur, last) instances.  nframes_cur grids are built from cv.
+int launch_match_last_unfused(const CurView& cv_in, const LastView& lv, const MatchCam& cam, int npairs, int* d_goff,
+                              int* d_gidx, unsigned* d_list, int* d_count, int* d_accepted, int* d_cur2last,
+                              int* d_nmatch, int cmax, int lmax, cudaStream_t stream, long long* launches);
+
+// Enqueue the LAST search of `npairs` (cur, last) instances.
 int launch_match_last(const CurView& cv_in, const LastView& lv, const MatchCam& cam, int npairs, int* d_goff, int* d_gidx,
                       unsigned* d_list, int* d_count, int* d_accepted, int* d_cur2last, int* d_nmatch, int cmax,
                       int lmax, cudaStream_t stream, long long* launches) {
+  const size_t smem = mf_smem_bytes(cmax);
+  if (smem > 200 * 1024)   // frame too large to stage in shared memory: separate grid / candidate / resolve kernels
+    return launch_match_last_unfused(cv_in, lv, cam, npairs, d_goff, d_gidx, d_list, d_count, d_accepted, d_cur2last,
+                                     d_nmatch, cmax, lmax, stream, launches);
+  B200_CUDA(cudaFuncSetAttribute(k_match_last_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ListView lsv{d_list, d_count};
+  k_match_last_fused<<<npairs, MF_THREADS, smem, stream>>>(cv_in, lv, cam, lsv, d_accepted, d_cur2last, d_nmatch, cmax);
+  if (launches) *launches += 1;
+  B200_CUDA(cudaGetLastError());
+  return B200ORB_OK;
+}
+
+// The unfused three-kernel path (grid / candidates / resolve as separate launches); kept for A/B timing.
+int launch_match_last_unfused(const CurView& cv_in, const LastView& lv, const MatchCam& cam, int npairs, int* d_goff,
+                              int* d_gidx, unsigned* d_list, int* d_count, int* d_accepted, int* d_cur2last,
+                              int* d_nmatch, int cmax, int lmax, cudaStream_t stream, long long* launches) {
   CurView cv = cv_in;
   k_grid_build<<<npairs, 256, 0, stream>>>(cv.x, cv.y, cv.n, cv.stride, cam.min_x, cam.max_x, cam.min_y, cam.max_y, d_goff,
                                           d_gidx);

@@ -44,8 +44,9 @@ struct CurView {             // SoA view of the "current" frames; instance p rea
   size_t stride;
 };
 
-__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t* __restrict__ b) {
-  const uint4 b0 = __ldg(reinterpret_cast<const uint4*>(b)), b1 = __ldg(reinterpret_cast<const uint4*>(b) + 1);
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint8_t* b) {
+  // generic loads: the candidate descriptors live in shared memory in the fused kernel, in global memory otherwise
+  const uint4 b0 = *reinterpret_cast<const uint4*>(b), b1 = *(reinterpret_cast<const uint4*>(b) + 1);
   return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }

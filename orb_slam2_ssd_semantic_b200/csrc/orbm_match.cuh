@@ -307,6 +307,206 @@ __global__ void __launch_bounds__(32) k_resolve_last(CurView cv, LastView lv, Ma
   if (lane == 0) nmatch[p] = n_acc - pruned;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused LAST search: one CTA per frame pair does K7 + K8 + K9 + K10 with the current frame's keypoints, descriptors
+// and 64x48 grid staged in shared memory (every dependent load of the window walk becomes a shared-memory load), the
+// candidate lists written to L2 once, and the ordered resolve fed through a double-buffered shared-memory ring that the
+// other warps refill while warp 0 resolves.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MF_THREADS = 512;
+constexpr int MF_QC = 16;   // queries per resolve chunk
+
+__host__ __device__ inline size_t mf_smem_bytes(int cmax) {
+  return (size_t)(GRID_CELLS + 1) * 4 + (size_t)GRID_CELLS * 4 + (size_t)cmax * (4 + 4 + 4 + 4 + 4 + 32 + 4 + 1) + 64;
+}
+
+__global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, LastView lv, MatchCam cam, ListView lists,
+                                                                 int* accepted, int* cur2last, int* nmatch, int cmax) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  __shared__ int ws[33];
+  __shared__ int s_hist[ORBM_HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  __shared__ int s_nacc, s_pruned;
+  const int p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  const int nc = cv.n[p], nl = lv.n[p];
+  const size_t co = (size_t)p * cv.stride, lo = (size_t)p * lv.stride;
+  // carve shared memory
+  unsigned char* q = fsm;
+  uint4* s_desc = reinterpret_cast<uint4*>(q); q += (size_t)cmax * 32;
+  int* s_off = reinterpret_cast<int*>(q); q += (size_t)(GRID_CELLS + 1) * 4;
+  int* s_cur = reinterpret_cast<int*>(q); q += (size_t)GRID_CELLS * 4;   // grid-build scratch, later the list ring
+  int* s_idx = reinterpret_cast<int*>(q); q += (size_t)cmax * 4;
+  float* s_x = reinterpret_cast<float*>(q); q += (size_t)cmax * 4;
+  float* s_y = reinterpret_cast<float*>(q); q += (size_t)cmax * 4;
+  float* s_ur = reinterpret_cast<float*>(q); q += (size_t)cmax * 4;
+  int* s_oct = reinterpret_cast<int*>(q); q += (size_t)cmax * 4;
+  int* state = reinterpret_cast<int*>(q); q += (size_t)cmax * 4;
+  uint8_t* taken = q;
+  const int* cobs = cv.obs ? cv.obs + co : nullptr;
+
+  // ---- stage the current frame -------------------------------------------------------------------------------------
+  for (int j = tid; j < nc; j += nthr) {
+    s_x[j] = cv.x[co + j]; s_y[j] = cv.y[co + j]; s_ur[j] = cv.uright[co + j]; s_oct[j] = cv.oct[co + j];
+    state[j] = (cobs && cobs[j] >= 0) ? -2 : -1;
+    taken[j] = 0;
+  }
+  {
+    const uint4* gd = reinterpret_cast<const uint4*>(cv.desc + co * 32);
+    for (int j = tid; j < nc * 2; j += nthr) s_desc[j] = __ldg(gd + j);
+  }
+  for (int c = tid; c < GRID_CELLS; c += nthr) s_cur[c] = 0;
+  if (tid < ORBM_HISTO_LENGTH) s_hist[tid] = 0;
+  if (tid == 0) { s_nacc = 0; s_pruned = 0; }
+  __syncthreads();
+  // ---- K7 grid in shared memory ---------------------------------------------------------------------------------------
+  const float inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(cam.max_x, cam.min_x));
+  const float inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(cam.max_y, cam.min_y));
+  for (int i = tid; i < nc; i += nthr) {
+    const int c = grid_cell(s_x[i], s_y[i], cam.min_x, cam.min_y, inv_w, inv_h);
+    if (c >= 0) atomicAdd(&s_cur[c], 1);
+  }
+  __syncthreads();
+  {
+    const int per = (GRID_CELLS + nthr - 1) / nthr;
+    const int beg = min(GRID_CELLS, tid * per), end = min(GRID_CELLS, beg + per);
+    int s = 0;
+    for (int c = beg; c < end; ++c) s += s_cur[c];
+    int total;
+    int run = block_excl_scan(s, ws, &total);
+    for (int c = beg; c < end; ++c) {
+      s_off[c] = run;
+      run += s_cur[c];
+      s_cur[c] = 0;
+    }
+    if (tid == 0) s_off[GRID_CELLS] = total;
+    __syncthreads();
+  }
+  for (int i = tid; i < nc; i += nthr) {
+    const int c = grid_cell(s_x[i], s_y[i], cam.min_x, cam.min_y, inv_w, inv_h);
+    if (c >= 0) s_idx[s_off[c] + atomicAdd(&s_cur[c], 1)] = i;
+  }
+  __syncthreads();
+  for (int c = tid; c < GRID_CELLS; c += nthr) {
+    const int b = s_off[c], e = s_off[c + 1];
+    for (int i = b + 1; i < e; ++i) {
+      const int v = s_idx[i];
+      int j = i - 1;
+      while (j >= b && s_idx[j] > v) { s_idx[j + 1] = s_idx[j]; --j; }
+      s_idx[j + 1] = v;
+    }
+  }
+  __syncthreads();
+  WalkCtx g;
+  g.off = s_off; g.idx = s_idx; g.x = s_x; g.y = s_y; g.uright = s_ur; g.oct = s_oct; g.obs = cobs;
+  g.desc = reinterpret_cast<const uint8_t*>(s_desc);
+  g.min_x = cam.min_x; g.min_y = cam.min_y; g.inv_w = inv_w; g.inv_h = inv_h;
+  bool fwd, bwd;
+  motion_flags(cam, cv.Tcw + (size_t)p * 16, lv.Tcw + (size_t)p * 16, fwd, bwd);
+  const float* Tc = cv.Tcw + (size_t)p * 16;
+  unsigned* L = lists.list + lo * LCAP;
+  int* C = lists.count + lo;
+  // ---- K8 candidates: warps stride over the queries -------------------------------------------------------------------
+  for (int i = warp; i < nl; i += nwarp) {
+    int cnt = 0;
+    if (lv.valid[lo + i]) {
+      QueryGeom qg;
+      if (setup_last_query(cam, Tc, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], qg)) {
+        const uint8_t* d = lv.desc + (lo + i) * 32;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+        unsigned* list = L + (size_t)i * LCAP;
+        cnt = warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
+          if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
+        });
+      }
+    }
+    if (lane == 0) C[i] = (cnt > LCAP) ? -cnt : cnt;
+  }
+  __syncthreads();   // lists are read back by this CTA only: block-level visibility is enough
+  // ---- K9 ordered resolve through a double-buffered ring --------------------------------------------------------------
+  unsigned* ring = reinterpret_cast<unsigned*>(s_cur);            // 2 x MF_QC x LCAP words = 8 KB
+  int* rcnt = reinterpret_cast<int*>(ring + 2 * MF_QC * LCAP);     // 2 x MF_QC
+  const int nchunk = (nl + MF_QC - 1) / MF_QC;
+  auto load_chunk = [&](int k, int t0, int tn) {
+    const int q0 = k * MF_QC, nq = min(MF_QC, nl - q0);
+    unsigned* dst = ring + (k & 1) * MF_QC * LCAP;
+    for (int w_ = t0; w_ < nq * LCAP; w_ += tn) dst[w_] = L[(size_t)q0 * LCAP + w_];
+    for (int w_ = t0; w_ < nq; w_ += tn) rcnt[(k & 1) * MF_QC + w_] = C[q0 + w_];
+  };
+  if (nchunk > 0) load_chunk(0, tid, nthr);
+  __syncthreads();
+  const int* lobs = lv.obs ? lv.obs + lo : nullptr;
+  int* acc = accepted + lo;
+  int n_acc = 0;
+  for (int k = 0; k < nchunk; ++k) {
+    if (warp == 0) {
+      const int q0 = k * MF_QC, nq = min(MF_QC, nl - q0);
+      const unsigned* buf = ring + (k & 1) * MF_QC * LCAP;
+      for (int t = 0; t < nq; ++t) {
+        const int i = q0 + t;
+        const int cn = rcnt[(k & 1) * MF_QC + t];
+        int best_idx = -1, best_dist = 256;
+        if (cn > 0) {
+          const Pick pk = pick_min(buf[t * LCAP + lane], buf[t * LCAP + lane + 32], cn, taken, -1, lane);
+          best_idx = pk.idx; best_dist = pk.dist;
+        } else if (cn < 0) {   // overflowed list: exact re-walk with the claimed filter
+          QueryGeom qg;
+          if (setup_last_query(cam, Tc, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], qg)) {
+            const uint8_t* d = lv.desc + (lo + i) * 32;
+            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+            unsigned long long bk = ~0ull;
+            warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
+              if (!taken[idx]) { const unsigned long long kk = key64(dist, ord, idx); bk = (kk < bk) ? kk : bk; }
+            });
+            bk = warp_min64(bk);
+            if (bk != ~0ull) { best_idx = (int)(bk & 0x3fffffull); best_dist = (int)(bk >> 44); }
+          }
+        }
+        int a = -1;
+        if (best_idx >= 0 && best_dist <= ORBM_TH_HIGH) {
+          a = best_idx;
+          ++n_acc;
+          if (lane == 0) {
+            state[best_idx] = i;
+            if ((lobs ? lobs[i] : cam.last_obs_default) > 0) taken[best_idx] = 1;
+          }
+        }
+        if (lane == 0) acc[i] = a;
+        __syncwarp();
+      }
+    } else if (k + 1 < nchunk) {
+      load_chunk(k + 1, tid - 32, nthr - 32);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) s_nacc = n_acc;
+  __syncthreads();
+  // ---- K10 rotation consistency -------------------------------------------------------------------------------------
+  const float* lang = lv.ang + lo;
+  const float* cang = cv.ang + co;
+  if (cam.check_ori) {
+    for (int i = tid; i < nl; i += nthr) {
+      const int idx = acc[i];
+      if (idx >= 0) atomicAdd(&s_hist[rot_bin(lang[i], cang[idx])], 1);
+    }
+    __syncthreads();
+    if (tid == 0) three_maxima(s_hist, s_keep);
+    __syncthreads();
+    int pr = 0;
+    for (int i = tid; i < nl; i += nthr) {
+      const int idx = acc[i];
+      if (idx >= 0) {
+        const int bin = rot_bin(lang[i], cang[idx]);
+        if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { state[idx] = -1; ++pr; }
+      }
+    }
+    if (pr) atomicAdd(&s_pruned, pr);
+    __syncthreads();
+  }
+  int* out = cur2last + co;
+  for (int j = tid; j < nc; j += nthr) out[j] = state[j];
+  if (tid == 0) nmatch[p] = s_nacc - s_pruned;
+}
+
 // K9 (POINTS): best and second best among unclaimed candidates, level-aware ratio test (:98-152)
 __global__ void __launch_bounds__(32) k_resolve_points(CurView cv, PointsView pv, MatchCam cam, ListView in, int* f2pt,
                                                        int* nmatch, int cmax) {

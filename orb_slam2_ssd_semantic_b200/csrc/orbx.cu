@@ -184,7 +184,7 @@ int orbx::ensure_geometry(int r, int c, int F) {
         cd.rw = (short)((int)maxX - (int)iniX); cd.rh = (short)((int)maxY - (int)iniY);
         cd.pad = 0;
         cd.slot_off = slots;
-        if (cd.rw > FAST_MAX_ROI || cd.rh > FAST_MAX_ROI) { set_error("FAST cell larger than %d px", FAST_MAX_ROI); return B200ORB_EGEOM; }
+        if (cd.rw > FAST_MAX_ROI - 2 || cd.rh > FAST_MAX_ROI) { set_error("FAST cell larger than %d px", FAST_MAX_ROI); return B200ORB_EGEOM; }
         const int iw = cd.rw - 6, ih = cd.rh - 6;
         if (iw > 0 && ih > 0) slots += ((iw + 1) / 2) * ((ih + 1) / 2);
         cells.push_back(cd);
@@ -276,9 +276,16 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
   B200_CHECK(prof_mark(ST_QUADTREE + 1));
   // K4 blur
   for (int l = 0; l < nl; ++l) {
-    dim3 grd((lw[l] + BL_TW - 1) / BL_TW, (lh[l] + BL_TH - 1) / BL_TH, F);
-    k_blur7<<<grd, 256, 0, stream>>>(rawv.p[l], rawv.pitch[l], rawv.fstride[l], blurv.p[l], blurv.pitch[l],
-                                     blurv.fstride[l], lw[l], lh[l]);
+    const bool aligned = (((uintptr_t)rawv.p[l]) & 3) == 0 && (rawv.pitch[l] & 3) == 0 && (rawv.fstride[l] & 3) == 0;
+    if (aligned) {
+      dim3 grd((lw[l] + 511) / 512, (lh[l] + BLS_ROWS - 1) / BLS_ROWS, F);
+      k_blur7_strip<<<grd, 128, 0, stream>>>(rawv.p[l], rawv.pitch[l], rawv.fstride[l], blurv.p[l], blurv.pitch[l],
+                                            blurv.fstride[l], lw[l], lh[l]);
+    } else {
+      dim3 grd((lw[l] + BL_TW - 1) / BL_TW, (lh[l] + BL_TH - 1) / BL_TH, F);
+      k_blur7<<<grd, 256, 0, stream>>>(rawv.p[l], rawv.pitch[l], rawv.fstride[l], blurv.p[l], blurv.pitch[l],
+                                       blurv.fstride[l], lw[l], lh[l]);
+    }
     ++launches;
   }
   B200_CHECK(prof_mark(ST_BLUR + 1));

@@ -97,24 +97,26 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 //     written row-major into the cell's fixed segment, so concatenating the segments cell-major reproduces
 //     vToDistributeKeys' order.
 // ---------------------------------------------------------------------------------------------------
-constexpr int FAST_THREADS = 256;
+constexpr int FAST_WARPS = 8;
+constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_MAX_ROI = 72;   // ROI side bound enforced at create (cell <= 60 px + 6, padded)
+constexpr int FAST_TP = FAST_MAX_ROI;   // compile-time tile pitch: every ring offset becomes an immediate
 
-__device__ __forceinline__ unsigned pk_d(int d) {   // lo s16 = d, hi s16 = -d
-  return ((unsigned)d & 0xffffu) | ((unsigned)(-d) << 16);
-}
-
-__device__ __forceinline__ int fast_m_exact(const uint8_t* c, int tp) {
-  const int cv = c[0];
+// m(p) of one pixel.  Packing: one IMAD per ring pixel gives lo16 = 256 + (c - r), hi16 = 256 + (r - c) (biased,
+// both in [1, 511], so no borrow crosses the halves); min3/max3 on s16x2 then evaluate the bright and the dark
+// arcs at once: a3[i] = min(v[i..i+2]), a9[i] = min(a3[i], a3[i+3], a3[i+6]) = min over the 9-arc starting at i.
+__device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
+  constexpr int tp = FAST_TP;
+  const int bias = 256 * 65537 - (int)c[0] * 65535;
   unsigned v[16];
-  v[0] = pk_d(cv - c[3 * tp]);       v[1] = pk_d(cv - c[3 * tp + 1]);
-  v[2] = pk_d(cv - c[2 * tp + 2]);   v[3] = pk_d(cv - c[tp + 3]);
-  v[4] = pk_d(cv - c[3]);            v[5] = pk_d(cv - c[-tp + 3]);
-  v[6] = pk_d(cv - c[-2 * tp + 2]);  v[7] = pk_d(cv - c[-3 * tp + 1]);
-  v[8] = pk_d(cv - c[-3 * tp]);      v[9] = pk_d(cv - c[-3 * tp - 1]);
-  v[10] = pk_d(cv - c[-2 * tp - 2]); v[11] = pk_d(cv - c[-tp - 3]);
-  v[12] = pk_d(cv - c[-3]);          v[13] = pk_d(cv - c[tp - 3]);
-  v[14] = pk_d(cv - c[2 * tp - 2]);  v[15] = pk_d(cv - c[3 * tp - 1]);
+  v[0] = (unsigned)((int)c[3 * tp] * 65535 + bias);       v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
+  v[2] = (unsigned)((int)c[2 * tp + 2] * 65535 + bias);   v[3] = (unsigned)((int)c[tp + 3] * 65535 + bias);
+  v[4] = (unsigned)((int)c[3] * 65535 + bias);            v[5] = (unsigned)((int)c[-tp + 3] * 65535 + bias);
+  v[6] = (unsigned)((int)c[-2 * tp + 2] * 65535 + bias);  v[7] = (unsigned)((int)c[-3 * tp + 1] * 65535 + bias);
+  v[8] = (unsigned)((int)c[-3 * tp] * 65535 + bias);      v[9] = (unsigned)((int)c[-3 * tp - 1] * 65535 + bias);
+  v[10] = (unsigned)((int)c[-2 * tp - 2] * 65535 + bias); v[11] = (unsigned)((int)c[-tp - 3] * 65535 + bias);
+  v[12] = (unsigned)((int)c[-3] * 65535 + bias);          v[13] = (unsigned)((int)c[tp - 3] * 65535 + bias);
+  v[14] = (unsigned)((int)c[2 * tp - 2] * 65535 + bias);  v[15] = (unsigned)((int)c[3 * tp - 1] * 65535 + bias);
   unsigned a3[16], a9[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a3[i] = __vimin3_s16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
@@ -128,72 +130,98 @@ __device__ __forceinline__ int fast_m_exact(const uint8_t* c, int tp) {
   m0 = __vimax3_s16x2(m0, m1, m2);
   m3 = __vimax3_s16x2(m3, m4, a9[15]);
   m0 = __vmaxs2(m0, m3);
-  const int lo = (short)(m0 & 0xffffu), hi = (short)(m0 >> 16);
-  return max(0, max(lo, hi));
+  // halves hold 256 + min(d) over the best bright arc / 256 + min(-d) over the best dark arc
+  return max(0, max((int)(m0 & 0xffffu), (int)(m0 >> 16)) - 256);
 }
 
+// One CTA per (cell, frame); warp w owns rows w, w+8, ...; lane = column (second sweep for cells wider than 32).
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
                                                              int ncells, int slots_per_frame, int ini_th,
                                                              int min_th, unsigned* __restrict__ cand,
                                                              int* __restrict__ cellcnt) {
-  __shared__ __align__(16) uint8_t tile[FAST_MAX_ROI * FAST_MAX_ROI];
-  __shared__ uint8_t mm[FAST_MAX_ROI * FAST_MAX_ROI];
-  __shared__ int ws[33];
+  __shared__ __align__(16) uint8_t tile[FAST_MAX_ROI * FAST_TP];
+  __shared__ __align__(16) uint8_t mm[FAST_MAX_ROI * FAST_TP];
+  __shared__ unsigned rowmask[FAST_MAX_ROI][2];
+  __shared__ int rowoff[FAST_MAX_ROI + 1];
+  constexpr int tp = FAST_TP;
   const CellDesc cd = cells[blockIdx.x];
-  const int f = blockIdx.y;
+  const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int l = cd.level, rw = cd.rw, rh = cd.rh;
-  const int tp = (rw + 3) & ~3;
   const uint8_t* img = pyr.p[l] + (size_t)f * pyr.fstride[l] + (size_t)cd.y0 * pyr.pitch[l] + cd.x0;
-  for (int i = threadIdx.x; i < rw * rh; i += FAST_THREADS) {
-    const int y = i / rw, x = i - y * rw;
-    tile[y * tp + x] = img[(size_t)y * pyr.pitch[l] + x];
-    mm[y * tp + x] = 0;
+  const int pitch = pyr.pitch[l];
+  for (int y = w; y < rh; y += FAST_WARPS) {
+    const uint8_t* src = img + (size_t)y * pitch;
+    for (int x = lane; x < rw; x += 32) {
+      tile[y * tp + x] = __ldg(src + x);
+      mm[y * tp + x] = 0;
+    }
   }
   __syncthreads();
-  const int iw = rw - 6, ih = rh - 6, P = (iw > 0 && ih > 0) ? iw * ih : 0;
-  for (int i = threadIdx.x; i < P; i += FAST_THREADS) {
-    const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
-    const uint8_t* c = &tile[y * tp + x];
-    const int cv = c[0];
-    // necessary condition for a corner at min_th: every 9-arc contains one pixel of each opposite pair
-    const bool p0 = abs(cv - c[3 * tp]) > min_th || abs(cv - c[-3 * tp]) > min_th;
-    const bool p4 = abs(cv - c[3]) > min_th || abs(cv - c[-3]) > min_th;
-    int m = 0;
-    if (p0 && p4) m = fast_m_exact(c, tp);
-    if (m <= min_th) m = 0;   // can never be a corner nor outscore one
-    mm[y * tp + x] = (uint8_t)m;
+  const int iw = rw - 6, ih = rh - 6;
+  for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
+    for (int x = 3 + lane; x < rw - 3; x += 32) {
+      const uint8_t* c = &tile[y * tp + x];
+      const int cv = c[0];
+      // necessary condition for a corner at min_th: every 9-arc contains one pixel of each opposite pair
+      const bool p0 = abs(cv - (int)c[3 * tp]) > min_th || abs(cv - (int)c[-3 * tp]) > min_th;
+      const bool p4 = abs(cv - (int)c[3]) > min_th || abs(cv - (int)c[-3]) > min_th;
+      int m = 0;
+      if (p0 && p4) m = fast_m_exact(c);
+      if (m > min_th) mm[y * tp + x] = (uint8_t)m;   // others stay 0: can never be a corner nor outscore one
+    }
   }
   __syncthreads();
-  // NMS + order-preserving compaction: thread k owns the k-th contiguous chunk of the row-major scan.
-  // :821 the min-threshold retry happens only when the ini-threshold pass returned NO keypoint AFTER
-  // non-max suppression (a plateau of equal scores suppresses itself entirely).
-  const int chunk = (P + FAST_THREADS - 1) / FAST_THREADS;
-  const int beg = min(P, (int)threadIdx.x * chunk), end = min(P, beg + chunk);
-  unsigned flags = 0;
-  int total = 0, pos = 0;
+  // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving
+  // compaction: ballots per row, one scan over the rows.  :821 the min-threshold retry happens only when the
+  // ini-threshold pass returned NO keypoint AFTER non-max suppression.
+  int total = 0;
   for (int pass = 0; pass < 2 && total == 0; ++pass) {
     const int t = pass ? min_th : ini_th;
-    flags = 0;
-    for (int i = beg; i < end; ++i) {
-      const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
-      const uint8_t* q = &mm[y * tp + x];
-      const int m = q[0];
-      if (m > t) {
-        const int s = m - 1;
-#define SC(o) ((q[o] > t) ? (q[o] - 1) : 0)
-        if (s > SC(-1) && s > SC(1) && s > SC(-tp - 1) && s > SC(-tp) && s > SC(-tp + 1) && s > SC(tp - 1) &&
-            s > SC(tp) && s > SC(tp + 1))
-          flags |= 1u << (i - beg);
-#undef SC
+    for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = 3 + lane + 32 * h;
+        bool keep = false;
+        if (x < rw - 3) {
+          const uint8_t* q = &mm[y * tp + x];
+          const int m = q[0];
+          if (m > t) {
+            const int n0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
+            const int n1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
+            const int n2 = max((int)q[tp], (int)q[tp + 1]);
+            const int nmax = max(max(n0, n1), n2);
+            keep = m > ((nmax > t) ? nmax : 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t else 0)
+          }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) rowmask[y][h] = bal;
       }
     }
-    pos = block_excl_scan(__popc(flags), ws, &total);
+    __syncthreads();
+    if (w == 0) {   // exclusive scan of the per-row counts (ih <= 66 rows)
+      int run = 0;
+      for (int base = 0; base < ih; base += 32) {
+        const int y = 3 + base + lane;
+        const int c = (base + lane < ih) ? (__popc(rowmask[y][0]) + __popc(rowmask[y][1])) : 0;
+        const int inc = warp_incl_scan(c, lane);
+        if (base + lane < ih) rowoff[y] = run + inc - c;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) rowoff[0] = run;
+    }
+    __syncthreads();
+    total = rowoff[0];
+    if (total == 0 && pass == 0 && ini_th != min_th) __syncthreads();   // keep rowoff[0] stable until everyone read it
   }
+  (void)iw;
   unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
-  for (int i = beg; i < end; ++i) {
-    if (flags & (1u << (i - beg))) {
-      const int y = i / iw + 3, x = i - (y - 3) * iw + 3;
-      out[pos++] = pack_kp(cd.x0 + x, cd.y0 + y, mm[y * tp + x] - 1);
+  if (total > 0) {
+    for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
+      const unsigned b0 = rowmask[y][0], b1 = rowmask[y][1];
+      const int base = rowoff[y];
+      if ((b0 >> lane) & 1u) out[base + __popc(b0 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 3 + lane, cd.y0 + y, mm[y * tp + 3 + lane] - 1);
+      if ((b1 >> lane) & 1u)
+        out[base + __popc(b0) + __popc(b1 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 35 + lane, cd.y0 + y, mm[y * tp + 35 + lane] - 1);
     }
   }
   if (threadIdx.x == 0) cellcnt[(size_t)f * ncells + blockIdx.x] = total;
@@ -640,6 +668,57 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(LevelTab lt, Orie
     kp.octave = l;
     kp.class_id = -1;
     kps[(size_t)f * cap + j] = kp;
+  }
+}
+
+// K4 (fast path): same arithmetic, register sliding window.  One thread owns 4 adjacent columns and walks down
+// BLS_ROWS rows of a strip; per row it reads the 10 source bytes as three aligned 32-bit words, forms the four
+// horizontal sums and keeps the last 7 rows of them in registers for the vertical pass -- no shared memory, no
+// intermediate plane.  Requires 4-byte aligned rows (always true for the internal planes; level 0 falls back to
+// k_blur7 when the caller's buffer is not aligned).
+constexpr int BLS_ROWS = 32;
+
+__device__ __forceinline__ void blur_hsum4(const uint8_t* __restrict__ row, int x0, int w, unsigned (&h)[4]) {
+  int b[10];
+  if (x0 >= 4 && x0 + 8 <= w) {   // interior: words k-1, k, k+1 cover bytes x0-4 .. x0+7
+    const unsigned* p = reinterpret_cast<const unsigned*>(row + x0 - 4);
+    const unsigned w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
+    b[0] = (w0 >> 8) & 0xff; b[1] = (w0 >> 16) & 0xff; b[2] = w0 >> 24;
+    b[3] = w1 & 0xff; b[4] = (w1 >> 8) & 0xff; b[5] = (w1 >> 16) & 0xff; b[6] = w1 >> 24;
+    b[7] = w2 & 0xff; b[8] = (w2 >> 8) & 0xff; b[9] = (w2 >> 16) & 0xff;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) b[i] = __ldg(row + reflect101(x0 - 3 + i, w));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    h[i] = 18u * (b[i] + b[i + 6]) + 34u * (b[i + 1] + b[i + 5]) + 48u * (b[i + 2] + b[i + 4]) + 56u * b[i + 3];
+}
+
+__global__ void __launch_bounds__(128) k_blur7_strip(const uint8_t* __restrict__ src, int spitch, size_t sfs,
+                                                     uint8_t* __restrict__ dst, int dpitch, size_t dfs, int w, int h) {
+  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (x0 >= w) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
+  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
+  const int y0 = blockIdx.y * BLS_ROWS, y1 = min(h, y0 + BLS_ROWS);
+  unsigned win[7][4];   // horizontal sums of rows y-3 .. y+3
+#pragma unroll
+  for (int j = 0; j < 6; ++j) blur_hsum4(s + (size_t)reflect101(y0 - 3 + j, h) * spitch, x0, w, win[j]);
+  for (int y = y0; y < y1; ++y) {
+    blur_hsum4(s + (size_t)reflect101(y + 3, h) * spitch, x0, w, win[6]);
+    unsigned out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned v = 18u * (win[0][i] + win[6][i]) + 34u * (win[1][i] + win[5][i]) + 48u * (win[2][i] + win[4][i]) +
+                         56u * win[3][i];
+      out |= ((v + 32768u) >> 16) << (8 * i);
+    }
+    *reinterpret_cast<unsigned*>(d + (size_t)y * dpitch + x0) = out;   // dst pitch is a multiple of 16
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) win[j][i] = win[j + 1][i];
   }
 }
 

@@ -56,3 +56,19 @@ def test_hamming_host_inline():
     b = np.zeros(32, np.uint8)
     assert ORBmatcher.DescriptorDistance(a, b) == int(np.unpackbits(a).sum())
     assert ORBmatcher.TH_HIGH == 100 and ORBmatcher.TH_LOW == 50 and ORBmatcher.HISTO_LENGTH == 30
+
+
+def test_cpp_shims_compile_link_and_fail_loudly(tmp_path):
+    """The header-only C++ shims (class surface of the reference) compile against the stand-in cv:: types, link the
+    C-ABI library, and -- on this GPU-less box -- refuse to construct."""
+    import subprocess
+    import torch
+    shim = os.path.join(ROOT, "orb_slam2_ssd_semantic_b200", "csrc", "shim")
+    libdir = os.path.join(ROOT, "orb_slam2_ssd_semantic_b200")
+    exe = str(tmp_path / "shim_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(shim, "shim_check.cpp"),
+                           "-L" + libdir, "-lb200orb", "-Wl,-rpath," + libdir])
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: exercised by tests/test_shim_gpu.py")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "loud failure" in out.stdout and "no CPU fallback" in out.stdout

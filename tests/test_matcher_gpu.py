@@ -162,3 +162,30 @@ def test_search_by_bow(oracle, stream_feats, nwords):
         n_gpu, gpu = ORBmatcher(ratio, ori).SearchByBoW(kf, f)
         assert n_gpu == n_ref and (gpu == ref).all(), (nwords, ratio, ori)
     assert n_ref > 5
+
+
+def test_projection_last_huge_frame_uses_unfused_path(oracle):
+    """More keypoints than fit the fused kernel's shared memory -> separate grid/candidate/resolve kernels."""
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    from orb_slam2_ssd_semantic_b200._abi import FrameView, LastView
+    rng = np.random.default_rng(21)
+    n = 5000
+    x = rng.uniform(5, 635, n).astype(np.float32)
+    y = rng.uniform(5, 475, n).astype(np.float32)
+    desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    sf = (1.2 ** np.arange(8)).astype(np.float32)
+    T = np.eye(4, dtype=np.float32)
+    cur = FrameView(x, y, rng.integers(0, 8, n), rng.uniform(0, 360, n).astype(np.float32), np.full(n, -1, np.float32), desc,
+                    T, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, 0, 640, 0, 480, sf)
+    z = 2.0
+    m = 3000
+    sel = rng.integers(0, n, m)
+    xw = np.stack([(x[sel] + rng.normal(0, 2, m) - synth.CX) * z / synth.FX, (y[sel] + rng.normal(0, 2, m) - synth.CY) * z / synth.FY,
+                   np.full(m, z)], 1).astype(np.float32)
+    d2 = desc[sel].copy()
+    d2[:, :3] ^= rng.integers(0, 256, size=(m, 3), dtype=np.uint8)
+    last = LastView(xw, np.ones(m, np.uint8), cur.octave[sel], rng.uniform(0, 360, m).astype(np.float32), d2, T,
+                    mp_obs=rng.integers(0, 2, m).astype(np.int32))
+    n_ref, ref = oracle.search_by_projection_last(cur, last, 15.0, False, 0.9, True)
+    n_gpu, gpu = ORBmatcher(0.9, True).SearchByProjection(cur, last, 15.0, False)
+    assert n_ref > 500 and n_gpu == n_ref and (gpu == ref).all()
