@@ -41,6 +41,7 @@ KF_EVERY = 12   # tool/KeyFrameTrajectory_f3_walk_src.txt holds 69 keyframes for
 S_IN = ROWS * COLS
 LEVEL_PX = [640 * 480, 533 * 400, 444 * 333, 370 * 278, 309 * 231, 257 * 193, 214 * 161, 179 * 134]
 S_PYR = sum(LEVEL_PX)
+METRIC = "RGB-D frames/sec (extract+match+octomap) @640x480"
 
 
 def algorithmic_bytes(n_kp: float, n_cand: float) -> dict:
@@ -123,13 +124,14 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of src/ORBextractor.cc + src/Frame.cc glue + src/ORBmatcher.cc) on the host cores
 # --------------------------------------------------------------------------------------------------------------
-def cpu_pipeline(gray, depth, T, nthreads: int):
+def cpu_pipeline(gray, depth, rgb, T, nthreads: int):
     """extract -> stereo/unproject -> SearchByProjection(cur,last) over the frames on `nthreads` host threads
     (oracle/pipeline_ref.cpp: frame-parallel, one extractor instance per thread as src/Frame.cc:121-124 does for
-    stereo; timed inside with steady_clock).  Returns seconds."""
+    stereo) with every KF_EVERY-th frame also pushed through the occupancy oracle on its own mapping thread (the
+    reference maps on a separate std::thread, src/pointcloudmapping.cc:43); timed inside with steady_clock."""
     from oracle import ref
     sec, _, _ = ref.pipeline_run(gray, depth, T, nthreads, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY,
-                                 synth.CX, synth.CY, synth.BF, TH, NNRATIO, True, 1)
+                                 synth.CX, synth.CY, synth.BF, TH, NNRATIO, True, 1, rgb=rgb, kf_every=KF_EVERY)
     return sec
 
 
@@ -143,12 +145,12 @@ def run_reference(args):
     sample = min(args.frames, max(2 * nthreads, 32))
     gray, depth, rgb, T = make_batch(sample)
     for _ in range(min(args.warmup, 1)):
-        cpu_pipeline(gray[:max(2, nthreads)], depth, T, nthreads)
-    times = [cpu_pipeline(gray, depth, T, nthreads) for _ in range(args.steps)]
+        cpu_pipeline(gray[:max(2, nthreads)], depth, rgb, T, nthreads)
+    times = [cpu_pipeline(gray, depth, rgb, T, nthreads) for _ in range(args.steps)]
     tot = float(np.sum(times))
     value = sample * args.steps / tot
     line = {
-        "impl": "reference", "metric": "RGB-D frames/sec (extract+match) @640x480", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, sample),
@@ -163,7 +165,9 @@ def run_reference(args):
 
 def workload_config(args, frames):
     return {"workload": "TUM fr3_walking-shaped synthetic RGB-D stream 640x480, ORBextractor(1000,1.2,8,20,7) + "
-                        "SearchByProjection(cur,last,th=15) per frame (BASELINE.json configs[1])",
+                        "SearchByProjection(cur,last,th=15) per frame, every %dth frame a keyframe inserted into the "
+                        "0.05 m occupancy map (BASELINE.json configs[1] + keyframe path of configs[3])" % KF_EVERY,
+            "keyframes_per_step_per_gpu": len(range(0, frames, KF_EVERY)),
             "frames_per_step_per_gpu": frames, "nfeatures": NFEAT, "parallelism": "frame-sharded x%d" % args.gpus,
             "l2": "inputs (%.0f MB gray+depth per step) exceed the 126 MB L2" % (frames * S_IN * 5 / 1e6)}
 
@@ -171,7 +175,7 @@ def workload_config(args, frames):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from orb_slam2_ssd_semantic_b200 import StreamTracker
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping, StreamTracker
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -186,10 +190,25 @@ def run_b200(args):
     d_gray = torch.from_numpy(gray).to(dev)
     d_depth = torch.from_numpy(depth).to(dev)
     d_T = torch.from_numpy(T).to(dev)
+    d_rgb = torch.from_numpy(rgb).to(dev)
+    pcm = PointCloudMapping(0.05, device=local)
+    kfs = list(range(0, F, KF_EVERY))
     ext = torch.cuda.ExternalStream(st.stream(), device=dev)
+    ext_map = torch.cuda.ExternalStream(pcm.stream(), device=dev)
+    npx = ROWS * COLS
 
     def step_device():
+        # tracking (extract + glue + match) on the pipeline stream, dense mapping on its own stream beside it -- the
+        # reference also maps on a separate thread (src/pointcloudmapping.cc:43)
         st.track_batch_device(d_gray.data_ptr(), d_depth.data_ptr(), d_T.data_ptr(), F, ROWS, COLS)
+        for t in kfs:
+            pcm.insert_keyframe_device(d_depth.data_ptr() + 4 * npx * t, d_rgb.data_ptr() + 3 * npx * t, ROWS, COLS, T[t],
+                                       synth.FX, synth.FY, synth.CX, synth.CY)
+
+    def join_streams():
+        ev = torch.cuda.Event()
+        ev.record(ext_map)
+        ext.wait_event(ev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -200,7 +219,8 @@ def run_b200(args):
     for _ in range(args.warmup):
         step_device()
     st.sync()
-    launches0 = st.launch_count()
+    pcm.sync()
+    launches0 = st.launch_count() + pcm.launch_count()
     st.profile_enable(True)
     st.profile_read()
     sampler = ClockSampler(local)
@@ -208,16 +228,22 @@ def run_b200(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
+    em0, em1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    em0.record(ext_map)
     for _ in range(args.steps):
         step_device()
+    em1.record(ext_map)
+    join_streams()
     e1.record(ext)
     st.sync()
+    pcm.sync()
     barrier()
+    map_ms = em0.elapsed_time(em1)
     clocks = sampler.result()
     ms_total = e0.elapsed_time(e1)
     stage_ms, prof_frames, prof_runs = st.profile_read()
     st.profile_enable(False)
-    launches = st.launch_count() - launches0
+    launches = st.launch_count() + pcm.launch_count() - launches0
     tms = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
@@ -229,14 +255,24 @@ def run_b200(args):
     p_depth = torch.from_numpy(depth).pin_memory()
     p_T = torch.from_numpy(T).pin_memory()
     st_gray, st_depth, st_T = p_gray.numpy(), p_depth.numpy(), p_T.numpy()
+    p_rgb = torch.from_numpy(rgb).pin_memory()
+    st_rgb = p_rgb.numpy()
     outs = st.alloc_outputs(F, pinned=True)
+
+    def step_host():
+        o = st.track_batch(st_gray, st_depth, st_T, out=outs)
+        for t in kfs:
+            pcm.insertKeyFrame(st_T[t], st_depth[t], st_rgb[t], synth.FX, synth.FY, synth.CX, synth.CY)
+        return o
+
     for _ in range(2):
-        out = st.track_batch(st_gray, st_depth, st_T, out=outs)
+        out = step_host()
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(3, args.steps // 2)
     for _ in range(e2e_steps):
-        out = st.track_batch(st_gray, st_depth, st_T, out=outs)
+        out = step_host()
+    pcm.sync()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
@@ -244,7 +280,7 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F * e2e_steps / float(te.item())
     kps, desc, nkp, c2l, nm = out
-    h2d = gray.nbytes + depth.nbytes + T.nbytes
+    h2d = gray.nbytes + depth.nbytes + T.nbytes + len(kfs) * (npx * 7)   # + depth & rgb of the keyframes
     d2h = kps.nbytes + desc.nbytes + nkp.nbytes + c2l.nbytes + nm.nbytes
     n_kp = float(nkp.mean())
     n_match = float(nm[1:].mean())
@@ -266,7 +302,7 @@ def run_b200(args):
         dom = max(stage_ms, key=lambda k: stage_ms[k])
         pipe_gbs = pipeline_bytes(n_kp) * F * args.steps / (ms_total * 1e-3) / 1e9
         line = {
-            "metric": "RGB-D frames/sec (extract+match) @640x480", "value": value, "unit": "frames/s",
+            "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, F),
@@ -278,13 +314,15 @@ def run_b200(args):
                          "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
                                       "algorithmic_bytes_per_frame": pipeline_bytes(n_kp)},
                          "stages": stages},
-            "stats": {"keypoints_per_frame": n_kp, "fast_candidates_frame0": n_cand, "matches_per_frame": n_match},
+            "stats": {"keypoints_per_frame": n_kp, "fast_candidates_frame0": n_cand, "matches_per_frame": n_match,
+                      "map_leaves": pcm.num_leaves(), "mapping_stream_ms_per_step": map_ms / args.steps,
+                      "keyframes_per_step": len(kfs)},
         }
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             nthreads = min(cores, 64)
             sample = min(F, max(2 * nthreads, 32))
-            t_cpu = cpu_pipeline(gray[:sample], depth[:sample], T[:sample], nthreads)
+            t_cpu = cpu_pipeline(gray[:sample], depth[:sample], rgb[:sample], T[:sample], nthreads)
             line["cpu_baseline"] = {"value": sample / t_cpu, "unit": "frames/s", "cores": nthreads, "kind": "port",
                                     "sample": "%d frames, frame-parallel on %d host threads (oracle/ C++ port)" % (sample, nthreads)}
         print(json.dumps(line))

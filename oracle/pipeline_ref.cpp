@@ -21,12 +21,18 @@ void orb_ref_tables(void*, float*, float*, float*, float*, int*, int*);
 int match_ref_projection_last(const OrbmFrame*, const OrbmLast*, float, int, float, int, int32_t*, int*);
 void frame_ref_stereo_unproject(const float*, int, int, const float*, int, int, const float*, float, float, float,
                                 float, float, float*, float*, float*, uint8_t*);
+void occ_ref_default_params(OcmParams*);
+void* occ_ref_create(const OcmParams*);
+void occ_ref_destroy(void*);
+int occ_ref_insert_keyframe(void*, const float*, const uint8_t*, int, int, const float*, float, float, float, float,
+                            const uint8_t*);
+long long occ_ref_num_leaves(void*);
 
 // Returns elapsed seconds; nkp[n], nmatch[n] receive per-frame counts (nmatch[0] = 0).
 double pipeline_ref_run(const uint8_t* gray, const float* depth, const float* Tcw, int n, int rows, int cols,
                         int nfeatures, float scale, int nlevels, int ini_th, int min_th, float fx, float fy, float cx,
                         float cy, float bf, float th, float nnratio, int check_ori, int last_obs, int nthreads,
-                        int* nkp, int* nmatch) {
+                        int* nkp, int* nmatch, const uint8_t* rgb, int kf_every, long long* leaves_out) {
   const int cap = nfeatures + 3 * nlevels + 64;
   std::vector<OrbxKeyPoint> kps((size_t)n * cap);
   std::vector<uint8_t> desc((size_t)n * cap * 32);
@@ -39,6 +45,19 @@ double pipeline_ref_run(const uint8_t* gray, const float* depth, const float* Tc
   }
   const size_t px = (size_t)rows * cols;
   auto t0 = std::chrono::steady_clock::now();
+  // the dense-mapping thread of the reference (src/pointcloudmapping.cc:43: its own std::thread) runs beside tracking
+  std::thread mapper;
+  if (rgb && kf_every > 0) {
+    mapper = std::thread([&]() {
+      OcmParams op;
+      occ_ref_default_params(&op);
+      void* m = occ_ref_create(&op);
+      for (int i = 0; i < n; i += kf_every)
+        occ_ref_insert_keyframe(m, depth + px * i, rgb + px * 3 * i, rows, cols, Tcw + 16 * i, fx, fy, cx, cy, nullptr);
+      if (leaves_out) *leaves_out = occ_ref_num_leaves(m);
+      occ_ref_destroy(m);
+    });
+  }
   {
     std::atomic<int> next(0);
     std::vector<std::thread> th_;
@@ -90,6 +109,7 @@ double pipeline_ref_run(const uint8_t* gray, const float* depth, const float* Tc
       });
     for (auto& t : th_) t.join();
   }
+  if (mapper.joinable()) mapper.join();
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 }

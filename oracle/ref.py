@@ -214,20 +214,25 @@ def stereo_unproject(kps, depth, Tcw, fx, fy, cx, cy, bf):
 
 
 def pipeline_run(gray, depth, Tcw, nthreads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, fx=535.4,
-                 fy=539.2, cx=320.1, cy=247.6, bf=40.0, th=15.0, nnratio=0.9, check_ori=True, last_obs=1):
-    """Multi-threaded CPU baseline (oracle/pipeline_ref.cpp) -> (seconds, nkp, nmatch)."""
+                 fy=539.2, cx=320.1, cy=247.6, bf=40.0, th=15.0, nnratio=0.9, check_ori=True, last_obs=1, rgb=None,
+                 kf_every=0):
+    """Multi-threaded CPU baseline (oracle/pipeline_ref.cpp) -> (seconds, nkp, nmatch[, leaves]).  With rgb and
+    kf_every > 0 every kf_every-th frame is also pushed through the occupancy oracle on its own mapping thread."""
     L = lib()
     L.pipeline_ref_run.restype = C.c_double
     L.pipeline_ref_run.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + \
-        [C.c_float] * 7 + [C.c_int] * 3 + [C.c_void_p] * 2
+        [C.c_float] * 7 + [C.c_int] * 3 + [C.c_void_p] * 2 + [C.c_void_p, C.c_int, C.c_void_p]
     gray = np.ascontiguousarray(gray, np.uint8)
     depth = np.ascontiguousarray(depth, np.float32)
     T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16)
     n, rows, cols = gray.shape
     nkp = np.zeros(n, np.int32)
     nm = np.zeros(n, np.int32)
+    leaves = C.c_longlong(0)
+    rgbp = None if rgb is None else np.ascontiguousarray(rgb, np.uint8)
     sec = L.pipeline_ref_run(_p(gray), _p(depth), _p(T), n, rows, cols, nfeatures, scale, nlevels, ini_th, min_th, fx, fy,
-                             cx, cy, bf, th, nnratio, int(check_ori), last_obs, nthreads, _p(nkp), _p(nm))
+                             cx, cy, bf, th, nnratio, int(check_ori), last_obs, nthreads, _p(nkp), _p(nm),
+                             None if rgbp is None else _p(rgbp), int(kf_every), C.byref(leaves))
     return sec, nkp, nm
 
 

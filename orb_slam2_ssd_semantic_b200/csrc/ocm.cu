@@ -27,15 +27,18 @@ __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {   /
   return k;
 }
 
-// find-or-insert; returns slot or -1 when the table is full
-__device__ __forceinline__ long long table_insert(unsigned long long* keys, long long cap_mask, unsigned long long key) {
+// find-or-insert; returns slot or -1 when the table is full; *fresh = this call created the entry
+__device__ __forceinline__ long long table_insert(unsigned long long* keys, long long cap_mask, unsigned long long key,
+                                                  bool* fresh) {
   long long s = (long long)(hash64(key) & (unsigned long long)cap_mask);
+  *fresh = false;
   for (long long probe = 0; probe <= cap_mask; ++probe) {
     const unsigned long long cur = keys[s];
     if (cur == key) return s;
     if (cur == EMPTY_KEY) {
       const unsigned long long old = atomicCAS(&keys[s], EMPTY_KEY, key);
-      if (old == EMPTY_KEY || old == key) return s;
+      if (old == EMPTY_KEY) { *fresh = true; return s; }
+      if (old == key) return s;
     }
     s = (s + 1) & cap_mask;
   }
@@ -94,16 +97,18 @@ __device__ __forceinline__ unsigned long long leaf_key(const OcmConst& c, float 
 
 // K11a: gate + VoxelGrid cell of every pixel
 __global__ void k_ocm_bin(OcmConst c, const float* __restrict__ depth, LeafTable lt, int* __restrict__ pix_slot,
-                          int* __restrict__ err) {
+                          int* __restrict__ counters, int* __restrict__ voxlist, int* __restrict__ err) {
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= c.rows * c.cols) return;
   float x, y, z;
   int slot = -1;
   if (backproject(c, depth, pix, x, y, z)) {
-    const long long s = table_insert(lt.keys, lt.mask, leaf_key(c, x, y, z));
+    bool fresh;
+    const long long s = table_insert(lt.keys, lt.mask, leaf_key(c, x, y, z), &fresh);
     if (s < 0) { atomicExch(err, 1); }
     else {
       slot = (int)s;
+      if (fresh) voxlist[atomicAdd(&counters[1], 1)] = slot;   // list of occupied cells: no table sweep later
       atomicAdd(&lt.count[s], 1);
       atomicMin(&lt.first[s], pix);
     }
@@ -111,16 +116,13 @@ __global__ void k_ocm_bin(OcmConst c, const float* __restrict__ depth, LeafTable
   pix_slot[pix] = slot;
 }
 
-// K11b: bucket ranges for the used cells (arbitrary order: the cloud is a set)
-__global__ void k_ocm_ranges(LeafTable lt, long long nslots, int* __restrict__ counters /*[0]=pixels,[1]=voxels*/,
-                             int* __restrict__ voxlist) {
-  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= nslots) return;
-  const int cn = lt.count[s];
-  if (cn > 0) {
-    lt.offset[s] = atomicAdd(&counters[0], cn);
-    voxlist[atomicAdd(&counters[1], 1)] = (int)s;
-  }
+// K11b: bucket ranges for the occupied cells (arbitrary order: the cloud is a set)
+__global__ void k_ocm_ranges(LeafTable lt, int* __restrict__ counters /*[0]=pixels,[1]=voxels*/,
+                             const int* __restrict__ voxlist) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= counters[1]) return;
+  const int s = voxlist[v];
+  lt.offset[s] = atomicAdd(&counters[0], lt.count[s]);
 }
 
 // K11c: scatter the pixel indices into their cell's bucket
@@ -199,7 +201,16 @@ __device__ __forceinline__ unsigned long long pack_key(int kx, int ky, int kz) {
 struct KeySet {
   unsigned long long* keys;
   long long mask;
+  int* list;      // slots filled during this scan
+  int* count;
 };
+
+__device__ __forceinline__ long long set_insert(const KeySet& st, unsigned long long key) {
+  bool fresh;
+  const long long s = table_insert(st.keys, st.mask, key, &fresh);
+  if (s >= 0 && fresh) st.list[atomicAdd(st.count, 1)] = (int)s;
+  return s;
+}
 
 // K12/K13: per point -> occupied endpoint key, or (ground) the free cells along the ray (computeRayKeys)
 __global__ void k_ocm_scan_keys(OcmConst c, const int* __restrict__ counters, const float* __restrict__ pts,
@@ -212,7 +223,7 @@ __global__ void k_ocm_scan_keys(OcmConst c, const int* __restrict__ counters, co
   const bool end_ok = coord_to_key(c, e[0], ke[0]) && coord_to_key(c, e[1], ke[1]) && coord_to_key(c, e[2], ke[2]);
   if (!pts_label[v]) {
     if (end_ok) {
-      const long long s = table_insert(occ.keys, occ.mask, pack_key(ke[0], ke[1], ke[2]));
+      const long long s = set_insert(occ, pack_key(ke[0], ke[1], ke[2]));
       if (s < 0) atomicExch(err, 2);
       else occ_rgb[s] = (unsigned)pts_rgb[(size_t)v * 3] | ((unsigned)pts_rgb[(size_t)v * 3 + 1] << 8) |
                         ((unsigned)pts_rgb[(size_t)v * 3 + 2] << 16);
@@ -224,7 +235,7 @@ __global__ void k_ocm_scan_keys(OcmConst c, const int* __restrict__ counters, co
       !coord_to_key(c, c.origin[2], ko[2]))
     return;
   if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return;
-  if (table_insert(fre.keys, fre.mask, pack_key(ko[0], ko[1], ko[2])) < 0) atomicExch(err, 3);
+  if (set_insert(fre, pack_key(ko[0], ko[1], ko[2])) < 0) atomicExch(err, 3);
   float dir[3] = {e[0] - c.origin[0], e[1] - c.origin[1], e[2] - c.origin[2]};
   double n2 = 0;
 #pragma unroll
@@ -258,7 +269,7 @@ __global__ void k_ocm_scan_keys(OcmConst c, const int* __restrict__ counters, co
     if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
     const double dist = fmin(fmin(tMax[0], tMax[1]), tMax[2]);
     if (dist > (double)length) break;
-    if (table_insert(fre.keys, fre.mask, pack_key(cur[0], cur[1], cur[2])) < 0) { atomicExch(err, 3); break; }
+    if (set_insert(fre, pack_key(cur[0], cur[1], cur[2])) < 0) { atomicExch(err, 3); break; }
   }
 }
 
@@ -297,27 +308,26 @@ __device__ __forceinline__ void map_update(const MapView& m, const OcmConst& c, 
   if (occupied) m.rgb[s] = rgb;
 }
 
-// K14: free \ occupied get a miss, occupied get a hit (MapDrawer.cc:1007-1022); clears the scan sets on the way
-__global__ void k_ocm_apply(OcmConst c, KeySet occ, const unsigned* __restrict__ occ_rgb, KeySet fre, MapView m,
-                            int* __restrict__ err) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= fre.mask) {
-    const unsigned long long k = fre.keys[i];
-    if (k != EMPTY_KEY && table_find(occ.keys, occ.mask, k) < 0) map_update(m, c, k, false, 0u, err);
+// K14: free \ occupied get a miss, occupied get a hit (MapDrawer.cc:1007-1022).  Both walk the scan's slot lists
+// (no table sweep) and clear the entries they consume; the free pass must run before the occupied pass.
+__global__ void k_ocm_apply_free(OcmConst c, KeySet occ, KeySet fre, MapView m, int* __restrict__ err) {
+  const int n = *fre.count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = fre.list[i];
+    const unsigned long long k = fre.keys[s];
+    fre.keys[s] = EMPTY_KEY;
+    if (table_find(occ.keys, occ.mask, k) < 0) map_update(m, c, k, false, 0u, err);
   }
 }
 __global__ void k_ocm_apply_occ(OcmConst c, KeySet occ, const unsigned* __restrict__ occ_rgb, MapView m,
                                 int* __restrict__ err) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= occ.mask) {
-    const unsigned long long k = occ.keys[i];
-    if (k != EMPTY_KEY) map_update(m, c, k, true, occ_rgb[i], err);
+  const int n = *occ.count;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = occ.list[i];
+    const unsigned long long k = occ.keys[s];
+    occ.keys[s] = EMPTY_KEY;
+    map_update(m, c, k, true, occ_rgb[s], err);
   }
-}
-__global__ void k_ocm_clear_sets(KeySet occ, KeySet fre) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= occ.mask) occ.keys[i] = EMPTY_KEY;
-  if (i <= fre.mask) fre.keys[i] = EMPTY_KEY;
 }
 
 __global__ void k_ocm_fill_u64(unsigned long long* p, unsigned long long v, long long n) {
@@ -423,7 +433,7 @@ struct ocm {
   void free_scratch() {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(leaf.keys); F(leaf.count); F(leaf.first); F(leaf.offset); F(leaf.cursor); F(d_pix_slot); F(d_bucket); F(d_voxlist);
-    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label);
+    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(occ.list); F(fre.list); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label);
     leaf = LeafTable{}; d_pix_slot = d_bucket = d_voxlist = nullptr; d_pts = nullptr; d_pts_rgb = d_pts_label = nullptr;
     occ = KeySet{}; fre = KeySet{}; d_occ_rgb = nullptr; d_depth = nullptr; d_rgb = d_label = nullptr;
   }
@@ -477,6 +487,8 @@ int ocm::ensure_scratch(int r, int c) {
   const long long occ_cap = pow2_at_least(2 * npix), fre_cap = pow2_at_least(8 * npix);
   occ.mask = occ_cap - 1; fre.mask = fre_cap - 1;
   B200_CUDA(cudaMalloc(&occ.keys, 8 * occ_cap)); B200_CUDA(cudaMalloc(&fre.keys, 8 * fre_cap));
+  B200_CUDA(cudaMalloc(&occ.list, 4 * occ_cap)); B200_CUDA(cudaMalloc(&fre.list, 4 * fre_cap));
+  occ.count = d_counters + 2; fre.count = d_counters + 3;
   B200_CUDA(cudaMalloc(&d_occ_rgb, 4 * occ_cap));
   fill(leaf.keys, EMPTY_KEY, leaf_cap); fill(leaf.count, 0, leaf_cap); fill(leaf.first, 0x7fffffff, leaf_cap);
   fill(leaf.cursor, 0, leaf_cap); fill(occ.keys, EMPTY_KEY, occ_cap); fill(fre.keys, EMPTY_KEY, fre_cap);
@@ -516,10 +528,10 @@ int ocm::insert(const float* dd, const uint8_t* drgb, const uint8_t* dlabel, int
   k.origin[0] = Tcw[3]; k.origin[1] = Tcw[7]; k.origin[2] = Tcw[11];
   k.rows = r; k.cols = c;
   const int npix = r * c;
-  B200_CUDA(cudaMemsetAsync(d_counters, 0, 8, stream));
+  B200_CUDA(cudaMemsetAsync(d_counters, 0, 16, stream));
   if (prm.leaf > 0) {
-    k_ocm_bin<<<(npix + 255) / 256, 256, 0, stream>>>(k, dd, leaf, d_pix_slot, d_err);
-    k_ocm_ranges<<<(unsigned)((leaf_cap + 255) / 256), 256, 0, stream>>>(leaf, leaf_cap, d_counters, d_voxlist);
+    k_ocm_bin<<<(npix + 255) / 256, 256, 0, stream>>>(k, dd, leaf, d_pix_slot, d_counters, d_voxlist, d_err);
+    k_ocm_ranges<<<(npix + 255) / 256, 256, 0, stream>>>(leaf, d_counters, d_voxlist);
     k_ocm_scatter<<<(npix + 255) / 256, 256, 0, stream>>>(npix, d_pix_slot, leaf, d_bucket);
     k_ocm_centroids<<<(npix + 127) / 128, 128, 0, stream>>>(k, dd, drgb, dlabel, leaf, d_counters, d_voxlist, d_bucket,
                                                           d_pts, d_pts_rgb, d_pts_label);
@@ -529,11 +541,10 @@ int ocm::insert(const float* dd, const uint8_t* drgb, const uint8_t* dlabel, int
     launches += 1;
   }
   k_ocm_scan_keys<<<(npix + 127) / 128, 128, 0, stream>>>(k, d_counters, d_pts, d_pts_label, d_pts_rgb, occ, d_occ_rgb, fre, d_err);
-  const long long big = std::max(occ.mask, fre.mask) + 1;
-  k_ocm_apply<<<(unsigned)((fre.mask + 256) / 256), 256, 0, stream>>>(k, occ, d_occ_rgb, fre, map, d_err);
-  k_ocm_apply_occ<<<(unsigned)((occ.mask + 256) / 256), 256, 0, stream>>>(k, occ, d_occ_rgb, map, d_err);
-  k_ocm_clear_sets<<<(unsigned)((big + 255) / 256), 256, 0, stream>>>(occ, fre);
-  launches += 4;
+  // list lengths live on the device: grid-stride kernels on a fixed grid (2 CTAs per SM)
+  k_ocm_apply_free<<<296, 256, 0, stream>>>(k, occ, fre, map, d_err);
+  k_ocm_apply_occ<<<296, 256, 0, stream>>>(k, occ, d_occ_rgb, map, d_err);
+  launches += 3;
   B200_CUDA(cudaGetLastError());
   return B200ORB_OK;
 }
@@ -576,7 +587,7 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   if ((e = cudaMalloc(&h->map.hi, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.rgb, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.nleaves, 4)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&h->d_counters, 8)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->d_counters, 16)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_export_counter, 8)) != cudaSuccess) return fail(e);
   h->fill(h->map.keys, EMPTY_KEY, C); h->fill(h->map.val, 0.f, C); h->fill(h->map.a, 0.f, C);

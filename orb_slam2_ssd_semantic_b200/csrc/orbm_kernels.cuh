@@ -168,6 +168,40 @@ __device__ __forceinline__ int warp_walk(const WalkCtx& g, const QueryGeom& q, c
     }
     return true;
   };
+  const int nx = x1 - x0 + 1;
+  if (nx <= 32) {
+    // Cells are stored column-major (cell = ix*GRID_ROWS + iy), so one grid column of the window is ONE contiguous
+    // CSR range [off[ix*48+y0], off[ix*48+y1+1]) already in the reference's visiting order.  Lane j owns column j's
+    // range; a warp scan flattens the (few dozen) entries of all columns, and the lanes then test / score 32 entries
+    // per step instead of walking cells.
+    int rs = 0, len = 0;
+    if (lane < nx) {
+      const int cbase = (x0 + lane) * GRID_ROWS;
+      rs = g.off[cbase + y0];
+      len = g.off[cbase + y1 + 1] - rs;
+    }
+    const int cum = warp_incl_scan(len, lane);
+    const int T = __shfl_sync(0xffffffffu, cum, 31);
+    int total = 0;
+    for (int base = 0; base < T; base += 32) {
+      const int t = base + lane;
+      int j = 0;
+      for (int k = 0; k < nx; ++k) j += (__shfl_sync(0xffffffffu, cum, k) <= t) ? 1 : 0;   // column holding entry t
+      const int jj = min(j, nx - 1);
+      const int cj = __shfl_sync(0xffffffffu, cum, jj), lj = __shfl_sync(0xffffffffu, len, jj),
+                rj = __shfl_sync(0xffffffffu, rs, jj);
+      bool ok = false;
+      int idx = 0;
+      if (t < T) {
+        idx = g.idx[rj + (t - (cj - lj))];
+        ok = pass(idx);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ok);
+      if (ok) emit(total + __popc(bal & ((1u << lane) - 1u)), idx, hamming256(d0, d1, g.desc + (size_t)idx * 32));
+      total += __popc(bal);
+    }
+    return total;
+  }
   int total = 0;
   for (int base = 0; base < ncell; base += 32) {
     const int c = base + lane;

@@ -92,7 +92,8 @@ int orbx::init(const OrbxParams& p, int dev) {
 void orbx::free_geometry() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_raw); F(d_blur); F(d_cells); F(d_cand); F(d_cellcnt); F(d_qkp); F(d_qnode); F(d_sel); F(d_selcnt);
-  F(d_candcnt); F(d_kps); F(d_desc); F(d_n); F(d_xt); F(d_yt); F(d_tmp);
+  F(d_candcnt); F(d_kps); F(d_desc); F(d_n); F(d_xt); F(d_yt); F(d_tmp); F(d_blur_tiles);
+  d_blur_tiles = nullptr;
   d_raw = d_blur = nullptr; d_cells = nullptr; d_cand = nullptr; d_cellcnt = nullptr; d_qkp = nullptr;
   d_qnode = nullptr; d_sel = nullptr; d_selcnt = nullptr; d_candcnt = nullptr; d_kps = nullptr; d_desc = nullptr;
   d_n = nullptr; d_xt = d_yt = nullptr; d_tmp = nullptr; tmp_bytes = 0;
@@ -212,8 +213,30 @@ int orbx::ensure_geometry(int r, int c, int F) {
   cap = selcap;
   qt_cap = align_up(qcap, 8);
   qt_smem = qt_smem_bytes(qt_cap);
-  if (qt_smem > 200 * 1024) { set_error("nfeatures too large for the quad-tree kernel's shared memory"); return B200ORB_EINVAL; }
-  B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qt_smem));
+  if (qt_smem > 100 * 1024) { set_error("nfeatures too large for the quad-tree kernel's shared memory"); return B200ORB_EINVAL; }
+  {
+    // Levels are launched in three groups with decreasing shared-memory budgets (level 0-1: 200 KB, 2-4: 112 KB,
+    // 5+: 56 KB) so that small levels keep several CTAs per SM; a (frame, level) whose candidates exceed its group's
+    // budget uses the global scratch instead (same code path, generic pointers).
+    // Measured on B200 (profiles/r01_notes.md): staging the candidates in shared memory cuts a CTA's latency but
+    // costs more in lost CTA-level concurrency (1 CTA/SM for the big levels, split launches for the small ones) than
+    // it gains: 0.51 ms -> 0.74-0.83 ms per 256 frames.  All levels therefore run in ONE launch on the L2-resident
+    // scratch (budget 0); the staging path stays available behind the budgets.
+    const int bounds[4] = {0, nl, nl, nl};
+    const size_t budget[3] = {0, 0, 0};
+    size_t mx = 0;
+    for (int g = 0; g < 3; ++g) {
+      qt_group_lb[g] = bounds[g]; qt_group_le[g] = bounds[g + 1];
+      int worst = 0;
+      for (int l = bounds[g]; l < bounds[g + 1]; ++l) worst = std::max(worst, ltab.slot_begin[l + 1] - ltab.slot_begin[l]);
+      size_t room = budget[g] > qt_smem ? budget[g] - qt_smem : 0;
+      int kcap = (int)std::min<size_t>((size_t)worst, room / 8) & ~3;
+      qt_group_kcap[g] = std::max(kcap, 0);
+      qt_group_smem[g] = qt_smem + (size_t)qt_group_kcap[g] * 8;
+      mx = std::max(mx, qt_group_smem[g]);
+    }
+    B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+  }
 
   rows = r; cols = c; maxF = keepF;
   const size_t Fz = (size_t)maxF;
@@ -232,6 +255,16 @@ int orbx::ensure_geometry(int r, int c, int F) {
   B200_CUDA(cudaMalloc(&d_n, sizeof(int) * Fz));
   B200_CUDA(cudaMalloc(&d_xt, sizeof(int2) * std::max<size_t>(xt.size(), 1)));
   B200_CUDA(cudaMalloc(&d_yt, sizeof(int2) * std::max<size_t>(yt.size(), 1)));
+  {
+    std::vector<BlurTile> bt;
+    for (int l = 0; l < nl; ++l)
+      for (int y = 0; y < lh[l]; y += BLS_ROWS)
+        for (int x = 0; x < lw[l]; x += 128) bt.push_back(BlurTile{(short)l, (short)x, (short)y, 0});
+    n_blur_tiles = (int)bt.size();
+    B200_CUDA(cudaMalloc(&d_blur_tiles, sizeof(BlurTile) * bt.size()));
+    B200_CUDA(cudaMemcpyAsync(d_blur_tiles, bt.data(), sizeof(BlurTile) * bt.size(), cudaMemcpyHostToDevice, stream));
+    B200_CUDA(cudaStreamSynchronize(stream));   // bt is a local
+  }
   B200_CUDA(cudaMemcpyAsync(d_cells, cells.data(), sizeof(CellDesc) * ncells, cudaMemcpyHostToDevice, stream));
   if (!xt.empty()) B200_CUDA(cudaMemcpyAsync(d_xt, xt.data(), sizeof(int2) * xt.size(), cudaMemcpyHostToDevice, stream));
   if (!yt.empty()) B200_CUDA(cudaMemcpyAsync(d_yt, yt.data(), sizeof(int2) * yt.size(), cudaMemcpyHostToDevice, stream));
@@ -264,29 +297,40 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
   }
   B200_CHECK(prof_mark(ST_RESIZE + 1));
   // K2 FAST cells
+  int fast_aligned = 1;   // every level's rows 4-byte aligned? (internal planes always are; level 0 may alias a caller buffer)
+  for (int l = 0; l < nl; ++l)
+    if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) fast_aligned = 0;
   k_fast_cells<<<dim3(ncells, F), FAST_THREADS, 0, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
-                                                            prm.min_th_fast, d_cand, d_cellcnt);
+                                                            prm.min_th_fast, d_cand, d_cellcnt, fast_aligned);
   ++launches;
   B200_CHECK(prof_mark(ST_FAST + 1));
-  // K3 quad-tree
+  // K3 quad-tree: levels are launched in two groups so that each group's per-candidate arrays fit shared memory
   QtScratchView qs{d_qkp, d_qnode};
-  k_quadtree<<<dim3(nl, F), QT_THREADS, qt_smem, stream>>>(ltab, d_cells, d_cand, d_cellcnt, ncells, slots_per_frame,
-                                                          qs, qt_cap, d_sel, d_selcnt, d_candcnt, sel_per_frame);
-  ++launches;
-  B200_CHECK(prof_mark(ST_QUADTREE + 1));
-  // K4 blur
-  for (int l = 0; l < nl; ++l) {
-    const bool aligned = (((uintptr_t)rawv.p[l]) & 3) == 0 && (rawv.pitch[l] & 3) == 0 && (rawv.fstride[l] & 3) == 0;
-    if (aligned) {
-      dim3 grd((lw[l] + 511) / 512, (lh[l] + BLS_ROWS - 1) / BLS_ROWS, F);
-      k_blur7_strip<<<grd, 128, 0, stream>>>(rawv.p[l], rawv.pitch[l], rawv.fstride[l], blurv.p[l], blurv.pitch[l],
-                                            blurv.fstride[l], lw[l], lh[l]);
-    } else {
-      dim3 grd((lw[l] + BL_TW - 1) / BL_TW, (lh[l] + BL_TH - 1) / BL_TH, F);
-      k_blur7<<<grd, 256, 0, stream>>>(rawv.p[l], rawv.pitch[l], rawv.fstride[l], blurv.p[l], blurv.pitch[l],
-                                       blurv.fstride[l], lw[l], lh[l]);
-    }
+  for (int g = 0; g < 3; ++g) {
+    const int lb = qt_group_lb[g], le = qt_group_le[g];
+    if (le <= lb) continue;
+    k_quadtree<<<dim3(le - lb, F), QT_THREADS, qt_group_smem[g], stream>>>(ltab, d_cells, d_cand, d_cellcnt, ncells,
+                                                                           slots_per_frame, qs, qt_cap, d_sel, d_selcnt,
+                                                                           d_candcnt, sel_per_frame, lb, qt_group_kcap[g]);
     ++launches;
+  }
+  B200_CHECK(prof_mark(ST_QUADTREE + 1));
+  // K4 blur: one launch over every (level, 128x35 tile, frame) when all planes are 4-byte aligned
+  {
+    bool aligned = true;
+    for (int l = 0; l < nl; ++l)
+      if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) aligned = false;
+    if (aligned) {
+      k_blur7_strip<<<dim3(n_blur_tiles, F), 32, 0, stream>>>(rawv, blurv, d_blur_tiles);
+      ++launches;
+    } else {
+      for (int l = 0; l < nl; ++l) {
+        dim3 grd((lw[l] + BL_TW - 1) / BL_TW, (lh[l] + BL_TH - 1) / BL_TH, F);
+        k_blur7<<<grd, 256, 0, stream>>>(rawv.p[l], rawv.pitch[l], rawv.fstride[l], blurv.p[l], blurv.pitch[l],
+                                         blurv.fstride[l], lw[l], lh[l]);
+        ++launches;
+      }
+    }
   }
   B200_CHECK(prof_mark(ST_BLUR + 1));
   // K5 orientation + descriptors

@@ -100,22 +100,23 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 constexpr int FAST_WARPS = 8;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_MAX_ROI = 72;   // ROI side bound enforced at create (cell <= 60 px + 6, padded)
-constexpr int FAST_TP = FAST_MAX_ROI;   // compile-time tile pitch: every ring offset becomes an immediate
+constexpr int FAST_TP = 80;        // compile-time tile pitch (>= 3 + 72, multiple of 4): ring offsets are immediates
 
 // m(p) of one pixel.  Packing: one IMAD per ring pixel gives lo16 = 256 + (c - r), hi16 = 256 + (r - c) (biased,
 // both in [1, 511], so no borrow crosses the halves); min3/max3 on s16x2 then evaluate the bright and the dark
 // arcs at once: a3[i] = min(v[i..i+2]), a9[i] = min(a3[i], a3[i+3], a3[i+6]) = min over the 9-arc starting at i.
-__device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
+// r0/r4/r8/r12 are the four compass pixels the caller already loaded for the quick rejection test.
+__device__ __forceinline__ int fast_m_exact(const uint8_t* c, int cv, int r0, int r4, int r8, int r12) {
   constexpr int tp = FAST_TP;
-  const int bias = 256 * 65537 - (int)c[0] * 65535;
+  const int bias = 256 * 65537 - cv * 65535;
   unsigned v[16];
-  v[0] = (unsigned)((int)c[3 * tp] * 65535 + bias);       v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
+  v[0] = (unsigned)(r0 * 65535 + bias);                   v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
   v[2] = (unsigned)((int)c[2 * tp + 2] * 65535 + bias);   v[3] = (unsigned)((int)c[tp + 3] * 65535 + bias);
-  v[4] = (unsigned)((int)c[3] * 65535 + bias);            v[5] = (unsigned)((int)c[-tp + 3] * 65535 + bias);
+  v[4] = (unsigned)(r4 * 65535 + bias);                   v[5] = (unsigned)((int)c[-tp + 3] * 65535 + bias);
   v[6] = (unsigned)((int)c[-2 * tp + 2] * 65535 + bias);  v[7] = (unsigned)((int)c[-3 * tp + 1] * 65535 + bias);
-  v[8] = (unsigned)((int)c[-3 * tp] * 65535 + bias);      v[9] = (unsigned)((int)c[-3 * tp - 1] * 65535 + bias);
+  v[8] = (unsigned)(r8 * 65535 + bias);                   v[9] = (unsigned)((int)c[-3 * tp - 1] * 65535 + bias);
   v[10] = (unsigned)((int)c[-2 * tp - 2] * 65535 + bias); v[11] = (unsigned)((int)c[-tp - 3] * 65535 + bias);
-  v[12] = (unsigned)((int)c[-3] * 65535 + bias);          v[13] = (unsigned)((int)c[tp - 3] * 65535 + bias);
+  v[12] = (unsigned)(r12 * 65535 + bias);                 v[13] = (unsigned)((int)c[tp - 3] * 65535 + bias);
   v[14] = (unsigned)((int)c[2 * tp - 2] * 65535 + bias);  v[15] = (unsigned)((int)c[3 * tp - 1] * 65535 + bias);
   unsigned a3[16], a9[16];
 #pragma unroll
@@ -135,10 +136,12 @@ __device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
 }
 
 // One CTA per (cell, frame); warp w owns rows w, w+8, ...; lane = column (second sweep for cells wider than 32).
+// `aligned` (host-checked): level rows are 4-byte aligned, so the ROI is fetched as aligned 32-bit words and kept
+// in shared memory at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
                                                              int ncells, int slots_per_frame, int ini_th,
                                                              int min_th, unsigned* __restrict__ cand,
-                                                             int* __restrict__ cellcnt) {
+                                                             int* __restrict__ cellcnt, int aligned) {
   __shared__ __align__(16) uint8_t tile[FAST_MAX_ROI * FAST_TP];
   __shared__ __align__(16) uint8_t mm[FAST_MAX_ROI * FAST_TP];
   __shared__ unsigned rowmask[FAST_MAX_ROI][2];
@@ -147,50 +150,64 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
   const CellDesc cd = cells[blockIdx.x];
   const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int l = cd.level, rw = cd.rw, rh = cd.rh;
-  const uint8_t* img = pyr.p[l] + (size_t)f * pyr.fstride[l] + (size_t)cd.y0 * pyr.pitch[l] + cd.x0;
   const int pitch = pyr.pitch[l];
-  for (int y = w; y < rh; y += FAST_WARPS) {
-    const uint8_t* src = img + (size_t)y * pitch;
-    for (int x = lane; x < rw; x += 32) {
-      tile[y * tp + x] = __ldg(src + x);
-      mm[y * tp + x] = 0;
+  const int sh = aligned ? (cd.x0 & 3) : 0;   // byte phase of the ROI inside its first word
+  {
+    const uint8_t* img = pyr.p[l] + (size_t)f * pyr.fstride[l] + (size_t)cd.y0 * pitch + (cd.x0 - sh);
+    if (aligned) {
+      const int nw = (sh + rw + 3) >> 2;
+      for (int y = w; y < rh; y += FAST_WARPS)
+        if (lane < nw) reinterpret_cast<unsigned*>(tile + y * tp)[lane] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + lane);
+    } else {
+      for (int y = w; y < rh; y += FAST_WARPS)
+        for (int x = lane; x < rw; x += 32) tile[y * tp + x] = __ldg(img + (size_t)y * pitch + x);
     }
+    // only the one-pixel frame around the detection range is read without being written: clear it
+    for (int i = threadIdx.x; i < rw; i += FAST_THREADS) { mm[2 * tp + sh + i] = 0; mm[(rh - 3) * tp + sh + i] = 0; }
+    for (int i = threadIdx.x; i < rh; i += FAST_THREADS) { mm[i * tp + sh + 2] = 0; mm[i * tp + sh + rw - 3] = 0; }
   }
   __syncthreads();
-  const int iw = rw - 6, ih = rh - 6;
-  for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
-    for (int x = 3 + lane; x < rw - 3; x += 32) {
-      const uint8_t* c = &tile[y * tp + x];
-      const int cv = c[0];
-      // necessary condition for a corner at min_th: every 9-arc contains one pixel of each opposite pair
-      const bool p0 = abs(cv - (int)c[3 * tp]) > min_th || abs(cv - (int)c[-3 * tp]) > min_th;
-      const bool p4 = abs(cv - (int)c[3]) > min_th || abs(cv - (int)c[-3]) > min_th;
-      int m = 0;
-      if (p0 && p4) m = fast_m_exact(c);
-      if (m > min_th) mm[y * tp + x] = (uint8_t)m;   // others stay 0: can never be a corner nor outscore one
-    }
-  }
-  __syncthreads();
-  // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving
-  // compaction: ballots per row, one scan over the rows.  :821 the min-threshold retry happens only when the
-  // ini-threshold pass returned NO keypoint AFTER non-max suppression.
+  unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
+  const int ih = rh - 6;
   int total = 0;
+  // pass 0: everything at ini_th (pixels with m <= ini_th can neither be corners nor outscore one at that threshold);
+  // pass 1 (:821, only when the cell is EMPTY AFTER non-max suppression): the same at min_th.
   for (int pass = 0; pass < 2 && total == 0; ++pass) {
     const int t = pass ? min_th : ini_th;
+    if (pass == 1 && ini_th == min_th) break;
+    for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int x = 3 + lane + 32 * h;
+        if (x < rw - 3) {
+          const uint8_t* c = &tile[y * tp + sh + x];
+          const int cv = c[0], r0 = c[3 * tp], r8 = c[-3 * tp], r4 = c[3], r12 = c[-3];
+          // necessary condition for a corner at t: every 9-arc contains one pixel of each opposite pair
+          const bool p0 = abs(cv - r0) > t || abs(cv - r8) > t;
+          const bool p4 = abs(cv - r4) > t || abs(cv - r12) > t;
+          int m = 0;
+          if (p0 && p4) m = fast_m_exact(c, cv, r0, r4, r8, r12);
+          mm[y * tp + sh + x] = (uint8_t)((m > t) ? m : 0);
+        }
+      }
+    }
+    __syncthreads();
+    // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving
+    // compaction: ballots per row, one scan over the rows.
     for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int x = 3 + lane + 32 * h;
         bool keep = false;
         if (x < rw - 3) {
-          const uint8_t* q = &mm[y * tp + x];
+          const uint8_t* q = &mm[y * tp + sh + x];
           const int m = q[0];
-          if (m > t) {
+          if (m > 0) {   // m > t
             const int n0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
             const int n1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
             const int n2 = max((int)q[tp], (int)q[tp + 1]);
             const int nmax = max(max(n0, n1), n2);
-            keep = m > ((nmax > t) ? nmax : 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t else 0)
+            keep = m > max(nmax, 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t else 0)
           }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
@@ -211,17 +228,16 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
     }
     __syncthreads();
     total = rowoff[0];
-    if (total == 0 && pass == 0 && ini_th != min_th) __syncthreads();   // keep rowoff[0] stable until everyone read it
+    __syncthreads();   // rowoff[0] is rewritten by the next pass
   }
-  (void)iw;
-  unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
   if (total > 0) {
     for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
       const unsigned b0 = rowmask[y][0], b1 = rowmask[y][1];
       const int base = rowoff[y];
-      if ((b0 >> lane) & 1u) out[base + __popc(b0 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 3 + lane, cd.y0 + y, mm[y * tp + 3 + lane] - 1);
+      if ((b0 >> lane) & 1u)
+        out[base + __popc(b0 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 3 + lane, cd.y0 + y, mm[y * tp + sh + 3 + lane] - 1);
       if ((b1 >> lane) & 1u)
-        out[base + __popc(b0) + __popc(b1 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 35 + lane, cd.y0 + y, mm[y * tp + 35 + lane] - 1);
+        out[base + __popc(b0) + __popc(b1 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 35 + lane, cd.y0 + y, mm[y * tp + sh + 35 + lane] - 1);
     }
   }
   if (threadIdx.x == 0) cellcnt[(size_t)f * ncells + blockIdx.x] = total;
@@ -290,12 +306,13 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
                                                          const int* __restrict__ cellcnt, int ncells,
                                                          int slots_per_frame, QtScratchView sc, int qt_cap,
                                                          unsigned* __restrict__ sel, int* __restrict__ selcnt,
-                                                         int* __restrict__ candcnt, int sel_per_frame) {
+                                                         int* __restrict__ candcnt, int sel_per_frame,
+                                                         int level_begin, int kp_smem_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int ws[33];
   __shared__ int s_coff[QT_THREADS];
   __shared__ int s_expand, s_rstar;
-  const int l = blockIdx.x, f = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+  const int l = blockIdx.x + level_begin, f = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
   const int nlev = lt.nlevels;
   const int N = lt.nfeat[l];
   QtSmem S;
@@ -312,10 +329,22 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
     S.byrank = (int*)p; p += (size_t)qt_cap * 4;
     S.pre = (int*)p;
   }
-  unsigned* qkp = sc.qkp + (size_t)f * slots_per_frame + lt.slot_begin[l];
-  int* qnode = sc.qnode + (size_t)f * slots_per_frame + lt.slot_begin[l];
   const unsigned* fcand = cand + (size_t)f * slots_per_frame;
   const int* fcnt = cellcnt + (size_t)f * ncells;
+  // The per-candidate arrays (packed keypoint + node id) live in shared memory when this level's candidates fit
+  // (every round then walks shared memory instead of L2); otherwise in the global scratch.
+  unsigned* qkp = sc.qkp + (size_t)f * slots_per_frame + lt.slot_begin[l];
+  int* qnode = sc.qnode + (size_t)f * slots_per_frame + lt.slot_begin[l];
+  {
+    int part = 0;
+    for (int c = tid; c < lt.cell_begin[l + 1] - lt.cell_begin[l]; c += nthr) part += fcnt[lt.cell_begin[l] + c];
+    int ktot;
+    block_excl_scan(part, ws, &ktot);
+    if (ktot <= kp_smem_cap) {
+      qkp = reinterpret_cast<unsigned*>(smem_raw + qt_smem_bytes(qt_cap));
+      qnode = reinterpret_cast<int*>(qkp + kp_smem_cap);
+    }
+  }
 
   // ---- gather this level's per-cell segments into one contiguous, order-preserving list -----------
   const int cb = lt.cell_begin[l], nc = lt.cell_begin[l + 1] - cb;
@@ -672,53 +701,83 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(LevelTab lt, Orie
 }
 
 // K4 (fast path): same arithmetic, register sliding window.  One thread owns 4 adjacent columns and walks down
-// BLS_ROWS rows of a strip; per row it reads the 10 source bytes as three aligned 32-bit words, forms the four
-// horizontal sums and keeps the last 7 rows of them in registers for the vertical pass -- no shared memory, no
-// intermediate plane.  Requires 4-byte aligned rows (always true for the internal planes; level 0 falls back to
-// k_blur7 when the caller's buffer is not aligned).
-constexpr int BLS_ROWS = 32;
+// BLS_ROWS rows of a strip.  Per row it reads the 10 source bytes as three aligned 32-bit words, builds the byte pairs
+// P_k = b[k] | b[k+2] << 16 with one funnel shift + mask each, and evaluates the horizontal pass on two pixels per
+// register (every partial sum stays below 2^16, so the halves never carry into each other).  The last 7 rows of
+// horizontal sums live in a statically rotated register ring for the vertical pass -- no shared memory, no
+// intermediate plane.  Requires 4-byte aligned rows (true for the internal planes; level 0 falls back to k_blur7 when
+// the caller's buffer is not aligned).
+constexpr int BLS_ROWS = 35;   // multiple of 7: the ring rotation is unrolled by 7
 
-__device__ __forceinline__ void blur_hsum4(const uint8_t* __restrict__ row, int x0, int w, unsigned (&h)[4]) {
-  int b[10];
-  if (x0 >= 4 && x0 + 8 <= w) {   // interior: words k-1, k, k+1 cover bytes x0-4 .. x0+7
+struct HRow { unsigned h02, h13; };   // horizontal sums of pixels (0,2) and (1,3) of the thread's 4 columns
+
+__device__ __forceinline__ HRow blur_hrow(const uint8_t* __restrict__ row, int x0, int w) {
+  unsigned w0, w1, w2;   // bytes x0-4 .. x0+7
+  if (x0 >= 4 && x0 + 8 <= w) {
     const unsigned* p = reinterpret_cast<const unsigned*>(row + x0 - 4);
-    const unsigned w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2);
-    b[0] = (w0 >> 8) & 0xff; b[1] = (w0 >> 16) & 0xff; b[2] = w0 >> 24;
-    b[3] = w1 & 0xff; b[4] = (w1 >> 8) & 0xff; b[5] = (w1 >> 16) & 0xff; b[6] = w1 >> 24;
-    b[7] = w2 & 0xff; b[8] = (w2 >> 8) & 0xff; b[9] = (w2 >> 16) & 0xff;
-  } else {
+    w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2);
+  } else {   // image border: assemble the same three words through BORDER_REFLECT_101
+    unsigned b[12];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) b[i] = __ldg(row + reflect101(x0 - 3 + i, w));
+    for (int i = 0; i < 12; ++i) b[i] = __ldg(row + reflect101(x0 - 4 + i, w));
+    w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+    w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
+    w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    h[i] = 18u * (b[i] + b[i + 6]) + 34u * (b[i + 1] + b[i + 5]) + 48u * (b[i + 2] + b[i + 4]) + 56u * b[i + 3];
+  // P[k] = byte(k+1) | byte(k+3) << 16 of the 12-byte window, i.e. source pixels x0-3+k and x0-1+k
+  unsigned P[8];
+  P[0] = __funnelshift_r(w0, w1, 8) & 0x00ff00ffu;    // bytes 1,3
+  P[1] = __funnelshift_r(w0, w1, 16) & 0x00ff00ffu;   // bytes 2,4
+  P[2] = __funnelshift_r(w0, w1, 24) & 0x00ff00ffu;   // bytes 3,5
+  P[3] = w1 & 0x00ff00ffu;                            // bytes 4,6
+  P[4] = __funnelshift_r(w1, w2, 8) & 0x00ff00ffu;    // bytes 5,7
+  P[5] = __funnelshift_r(w1, w2, 16) & 0x00ff00ffu;   // bytes 6,8
+  P[6] = __funnelshift_r(w1, w2, 24) & 0x00ff00ffu;   // bytes 7,9
+  P[7] = w2 & 0x00ff00ffu;                            // bytes 8,10
+  HRow r;   // output pixel i uses source bytes i+1 .. i+7; pair (0,2) = P[0..6], pair (1,3) = P[1..7]
+  r.h02 = 18u * (P[0] + P[6]) + 34u * (P[1] + P[5]) + 48u * (P[2] + P[4]) + 56u * P[3];
+  r.h13 = 18u * (P[1] + P[7]) + 34u * (P[2] + P[6]) + 48u * (P[3] + P[5]) + 56u * P[4];
+  return r;
 }
 
-__global__ void __launch_bounds__(128) k_blur7_strip(const uint8_t* __restrict__ src, int spitch, size_t sfs,
-                                                     uint8_t* __restrict__ dst, int dpitch, size_t dfs, int w, int h) {
-  const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+struct BlurTile { short level, x0, y0, pad; };   // one warp-tile: 128 columns x BLS_ROWS rows of one level
+
+// All levels in ONE launch (a thread walks 35+6 rows sequentially, so a per-level launch is bounded below by that
+// latency chain; one launch lets the small levels hide inside the big ones).  One warp per tile, blockIdx.y = frame.
+__global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, const BlurTile* __restrict__ tiles) {
+  const BlurTile t = tiles[blockIdx.x];
+  const int l = t.level, w = src.w[l], h = src.h[l];
+  const int x0 = t.x0 + threadIdx.x * 4;
   if (x0 >= w) return;
-  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
-  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
-  const int y0 = blockIdx.y * BLS_ROWS, y1 = min(h, y0 + BLS_ROWS);
-  unsigned win[7][4];   // horizontal sums of rows y-3 .. y+3
+  const int spitch = src.pitch[l], dpitch = dstv.pitch[l];
+  const uint8_t* s = src.p[l] + (size_t)blockIdx.y * src.fstride[l];
+  uint8_t* d = dstv.p[l] + (size_t)blockIdx.y * dstv.fstride[l];
+  const int y0 = t.y0, y1 = min(h, y0 + BLS_ROWS);
+  unsigned ring[7][4];   // unpacked horizontal sums (pixels 0..3) of 7 consecutive rows, slot = row phase
 #pragma unroll
-  for (int j = 0; j < 6; ++j) blur_hsum4(s + (size_t)reflect101(y0 - 3 + j, h) * spitch, x0, w, win[j]);
-  for (int y = y0; y < y1; ++y) {
-    blur_hsum4(s + (size_t)reflect101(y + 3, h) * spitch, x0, w, win[6]);
-    unsigned out = 0;
+  for (int j = 0; j < 6; ++j) {
+    const HRow r = blur_hrow(s + (size_t)reflect101(y0 - 3 + j, h) * spitch, x0, w);
+    ring[j][0] = r.h02 & 0xffffu; ring[j][2] = r.h02 >> 16; ring[j][1] = r.h13 & 0xffffu; ring[j][3] = r.h13 >> 16;
+  }
+  for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const unsigned v = 18u * (win[0][i] + win[6][i]) + 34u * (win[1][i] + win[5][i]) + 48u * (win[2][i] + win[4][i]) +
-                         56u * win[3][i];
-      out |= ((v + 32768u) >> 16) << (8 * i);
+    for (int k = 0; k < 7; ++k) {
+      const int y = yb + k;
+      if (y < y1) {
+        // rows y-3 .. y+2 sit in slots (k+0)%7 .. (k+5)%7; the new row y+3 goes to slot (k+6)%7
+        const HRow r = blur_hrow(s + (size_t)reflect101(y + 3, h) * spitch, x0, w);
+        ring[(k + 6) % 7][0] = r.h02 & 0xffffu; ring[(k + 6) % 7][2] = r.h02 >> 16;
+        ring[(k + 6) % 7][1] = r.h13 & 0xffffu; ring[(k + 6) % 7][3] = r.h13 >> 16;
+        unsigned out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned v = 18u * (ring[k % 7][i] + ring[(k + 6) % 7][i]) + 34u * (ring[(k + 1) % 7][i] + ring[(k + 5) % 7][i]) +
+                             48u * (ring[(k + 2) % 7][i] + ring[(k + 4) % 7][i]) + 56u * ring[(k + 3) % 7][i];
+          out |= ((v + 32768u) >> 16) << (8 * i);
+        }
+        *reinterpret_cast<unsigned*>(d + (size_t)y * dpitch + x0) = out;   // dst pitch is a multiple of 16
+      }
     }
-    *reinterpret_cast<unsigned*>(d + (size_t)y * dpitch + x0) = out;   // dst pitch is a multiple of 16
-#pragma unroll
-    for (int j = 0; j < 6; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) win[j][i] = win[j + 1][i];
   }
 }
 
