@@ -171,6 +171,30 @@ typedef struct {
 int orbm_search_by_projection_points(orbm_t* h, const OrbmFrame* f, const OrbmTrackPoints* pts, float th,
                                      float nnratio, int32_t* f2pt, int* nmatches);
 
+/* Generic guided search for the remaining projection overloads: the caller (shim) has already projected its MapPoints
+ * and chosen window + octave range per query -- SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist)
+ * (src/ORBmatcher.cc:1757-1899, relocalisation) and the Sim3 / loop-closing variants do that part in a dozen
+ * scalar lines each (PredictScale, distance gates) -- and the GPU does what they share: GetFeaturesInArea, the Hamming
+ * loop, the ordered "already matched" rule, the rotation histogram.
+ *   claim_rule 0: a keypoint blocks later queries iff the MapPoint holding it has Observations()>0 (:1656-1658)
+ *   claim_rule 1: any MapPoint already on the keypoint blocks it (:1830-1831 `if(CurrentFrame.mvpMapPoints[i2]) continue`)
+ * cur2q[j] = query index now on keypoint j (-1 NULL, -2 untouched pre-existing). */
+typedef struct {
+  int n;
+  const uint8_t* valid;        /* query takes part (MapPoint non-NULL, !isBad(), in image, distance gates passed) */
+  const float* u;              /* projected pixel */
+  const float* v;
+  const float* radius;         /* th * mvScaleFactors[nPredictedLevel] */
+  const int32_t* min_level;    /* GetFeaturesInArea(minLevel, maxLevel) semantics (src/Frame.cc:486-506) */
+  const int32_t* max_level;
+  const float* uright;         /* predicted right coordinate for the stereo gate; NULL = no gate */
+  const uint8_t* desc;         /* n x 32: pMP->GetDescriptor() */
+  const float* angle;          /* angle used for the rotation histogram (e.g. pKF->mvKeysUn[i].angle) */
+  const int32_t* obs;          /* Observations() per query (claim_rule 0); NULL = all 1 */
+} OrbmQueries;
+int orbm_search_projected(orbm_t* h, const OrbmFrame* cur, const OrbmQueries* q, int max_dist, int claim_rule,
+                          int check_ori, int32_t* cur2q, int* nmatches);
+
 /* ORBmatcher::SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:217-363).
  * The two DBoW2::FeatureVector maps are given flattened and sorted by node id:
  * node_ids[k] (strictly ascending), indices of node k = idx[node_off[k] .. node_off[k+1]). */

@@ -236,6 +236,57 @@ int match_ref_projection_points(const OrbmFrame* F, const OrbmTrackPoints* pts, 
   return 0;
 }
 
+// Generic guided search behind orbm_search_projected: the shared tail of the projection overloads whose query geometry
+// the caller computes -- candidate loop + "already matched" rule + rotation histogram, e.g. src/ORBmatcher.cc:1804-1897
+// (relocalisation: claim_rule 1, bestDist <= ORBdist) or :1645-1721 (claim_rule 0).
+int match_ref_projected(const OrbmFrame* cur, const OrbmQueries* q, int max_dist, int claim_rule, int check_ori,
+                        int32_t* cur2q, int* nmatches_out) {
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  Grid* grid = new Grid();
+  grid->build(cur);
+  std::vector<int> state(cur->n, -1), state_obs(cur->n, 0);
+  for (int j = 0; j < cur->n; ++j)
+    if (cur->mp_obs && cur->mp_obs[j] >= 0) { state[j] = -2; state_obs[j] = cur->mp_obs[j]; }
+  std::vector<int> cand;
+  for (int i = 0; i < q->n; ++i) {
+    if (!q->valid[i]) continue;
+    const float u = q->u[i], v = q->v[i], radius = q->radius[i];
+    if (std::isnan(u) || std::isnan(v)) continue;
+    grid->query(u, v, radius, q->min_level[i], q->max_level[i], cand);
+    if (cand.empty()) continue;
+    const uint8_t* dMP = q->desc + 32 * (size_t)i;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : cand) {
+      if (claim_rule) { if (state[i2] != -1) continue; }
+      else if (state[i2] != -1 && state_obs[i2] > 0) continue;
+      if (q->uright && cur->uright[i2] > 0) {
+        const float er = std::fabs(q->uright[i] - cur->uright[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = desc_dist(dMP, cur->desc + 32 * (size_t)i2);
+      if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+    }
+    if (bestDist <= max_dist) {
+      state[bestIdx2] = i;
+      state_obs[bestIdx2] = q->obs ? q->obs[i] : 1;
+      nmatches++;
+      if (check_ori) rotHist[rot_bin(q->angle[i], cur->angle[bestIdx2])].push_back(bestIdx2);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i)
+      if (i != ind1 && i != ind2 && i != ind3)
+        for (int idx : rotHist[i]) { state[idx] = -1; nmatches--; }
+  }
+  for (int j = 0; j < cur->n; ++j) cur2q[j] = state[j];
+  *nmatches_out = nmatches;
+  delete grid;
+  return 0;
+}
+
 // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:217-363
 int match_ref_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
                   int* nmatches_out) {

@@ -190,6 +190,18 @@ def search_by_projection_points(F, pts, th, nnratio=0.8):
     return nm.value, out
 
 
+def search_projected(F, queries, max_dist, claim_rule=1, check_ori=True):
+    from orb_slam2_ssd_semantic_b200 import _abi
+    L = _mlib()
+    L.match_ref_projected.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmQueries), C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.POINTER(C.c_int)]
+    out = np.full(F.n, -1, np.int32)
+    nm = C.c_int(0)
+    fs, qs = F.struct(), queries.struct()
+    L.match_ref_projected(C.byref(fs), C.byref(qs), int(max_dist), int(claim_rule), int(check_ori), _p(out), C.byref(nm))
+    return nm.value, out
+
+
 def search_by_bow(kf, f, nnratio=0.7, check_ori=True):
     out = np.full(f.n, -1, np.int32)
     nm = C.c_int(0)

@@ -6,7 +6,7 @@ every operator raises if the CUDA library or a GPU is missing.
 """
 from ._lib import B200OrbError, lib, library_path  # noqa: F401
 from .extractor import KP_DTYPE, ORBextractor  # noqa: F401
-from .matcher import ORBmatcher, FrameView, LastView, TrackPointsView, BowView  # noqa: F401
+from .matcher import ORBmatcher, FrameView, LastView, TrackPointsView, BowView, QueriesView  # noqa: F401
 from .pipeline import StreamTracker  # noqa: F401
 from .mapping import PointCloudMapping  # noqa: F401
 

@@ -32,6 +32,11 @@ class OrbmTrackPoints(C.Structure):
                 ("scale_level", vp), ("view_cos", vp), ("mp_desc", vp), ("mp_obs", vp)]
 
 
+class OrbmQueries(C.Structure):
+    _fields_ = [("n", C.c_int), ("valid", vp), ("u", vp), ("v", vp), ("radius", vp), ("min_level", vp), ("max_level", vp),
+                ("uright", vp), ("desc", vp), ("angle", vp), ("obs", vp)]
+
+
 class OrbmBow(C.Structure):
     _fields_ = [("n", C.c_int), ("desc", vp), ("angle", vp), ("valid", vp), ("n_nodes", C.c_int), ("node_ids", vp),
                 ("node_off", vp), ("idx", vp)]
@@ -157,4 +162,29 @@ class BowView:
         s.desc, s.angle, s.valid = ptr(self.desc), ptr(self.angle), ptr(self.valid)
         s.n_nodes = len(self.node_ids)
         s.node_ids, s.node_off, s.idx = ptr(self.node_ids), ptr(self.node_off), ptr(self.idx)
+        return s
+
+
+class QueriesView:
+    """Pre-projected MapPoints for the generic guided search (orbm_search_projected)."""
+
+    def __init__(self, valid, u, v, radius, min_level, max_level, desc, angle, uright=None, obs=None):
+        self.valid = np.ascontiguousarray(valid, np.uint8)
+        self.u = np.ascontiguousarray(u, np.float32)
+        self.v = np.ascontiguousarray(v, np.float32)
+        self.radius = np.ascontiguousarray(radius, np.float32)
+        self.min_level = np.ascontiguousarray(min_level, np.int32)
+        self.max_level = np.ascontiguousarray(max_level, np.int32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.angle = np.ascontiguousarray(angle, np.float32)
+        self.uright = None if uright is None else np.ascontiguousarray(uright, np.float32)
+        self.obs = None if obs is None else np.ascontiguousarray(obs, np.int32)
+        self.n = len(self.valid)
+
+    def struct(self) -> OrbmQueries:
+        s = OrbmQueries()
+        s.n = self.n
+        s.valid, s.u, s.v, s.radius = ptr(self.valid), ptr(self.u), ptr(self.v), ptr(self.radius)
+        s.min_level, s.max_level, s.uright = ptr(self.min_level), ptr(self.max_level), ptr(self.uright)
+        s.desc, s.angle, s.obs = ptr(self.desc), ptr(self.angle), ptr(self.obs)
         return s

@@ -249,6 +249,58 @@ int orbm_search_by_projection_points(orbm_t* h, const OrbmFrame* f, const OrbmTr
   return B200ORB_OK;
 }
 
+int orbm_search_projected(orbm_t* h, const OrbmFrame* cur, const OrbmQueries* q, int max_dist, int claim_rule,
+                          int check_ori, int32_t* cur2q, int* nmatches) {
+  if (!h || !cur || !q || !cur2q || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
+  B200_CHECK(check_cur(cur));
+  if (q->n < 0) { set_error("bad query count"); return B200ORB_EINVAL; }
+  *nmatches = 0;
+  if (cur->n == 0) return B200ORB_OK;
+  if (q->n == 0) {
+    for (int j = 0; j < cur->n; ++j) cur2q[j] = (cur->mp_obs && cur->mp_obs[j] >= 0) ? -2 : -1;
+    return B200ORB_OK;
+  }
+  if (!q->valid || !q->u || !q->v || !q->radius || !q->min_level || !q->max_level || !q->desc || (check_ori && !q->angle)) {
+    set_error("null query array");
+    return B200ORB_EINVAL;
+  }
+  MatchCam cam;
+  B200_CHECK(fill_cam(cur, 0.f, 0, 0.f, check_ori, &cam));
+  DeviceGuard g(h->device);
+  const size_t nc = cur->n, nq = q->n;
+  const size_t need = nc * (4 * 4 + 4 + 32 + 4 + 4 + 4) + nq * (1 + 4 * 5 + 8 + 32 + 4 + 4 * LCAP + 8) + 4 * (GRID_CELLS + 1) + 64 * 256 + 4096;
+  B200_CHECK(h->reserve(need));
+  Carver cm(h->d_arena);
+  CurView cv;
+  int *d_goff, *d_gidx;
+  B200_CHECK(upload_cur(h, cm, cur, &cv, &d_goff, &d_gidx));
+  uint8_t* d_valid = cm.take<uint8_t>(nq); float* d_u = cm.take<float>(nq); float* d_v = cm.take<float>(nq);
+  float* d_r = cm.take<float>(nq); int* d_mn = cm.take<int>(nq); int* d_mx = cm.take<int>(nq);
+  float* d_ur = q->uright ? cm.take<float>(nq) : nullptr; float* d_ang = cm.take<float>(nq);
+  int* d_obs = q->obs ? cm.take<int>(nq) : nullptr; uint8_t* d_desc = cm.take<uint8_t>(nq * 32);
+  unsigned* d_list = cm.take<unsigned>(nq * LCAP); int* d_count = cm.take<int>(nq); int* d_acc = cm.take<int>(nq);
+  int* d_out = cm.take<int>(nc); int* d_nm = cm.take<int>(1);
+  UP(d_valid, q->valid, nq, uint8_t); UP(d_u, q->u, nq, float); UP(d_v, q->v, nq, float); UP(d_r, q->radius, nq, float);
+  UP(d_mn, q->min_level, nq, int); UP(d_mx, q->max_level, nq, int); UP(d_desc, q->desc, nq * 32, uint8_t);
+  if (d_ur) UP(d_ur, q->uright, nq, float);
+  if (q->angle) UP(d_ang, q->angle, nq, float);
+  if (d_obs) UP(d_obs, q->obs, nq, int);
+  QueriesView qv{d_valid, d_u, d_v, d_r, d_ur, d_ang, d_mn, d_mx, d_obs, d_desc, (int)nq};
+  ListView lsv{d_list, d_count};
+  k_grid_build<<<1, 256, 0, h->stream>>>(cv.x, cv.y, cv.n, cv.stride, cam.min_x, cam.max_x, cam.min_y, cam.max_y, d_goff, d_gidx);
+  k_cand_generic<<<((int)nq + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, h->stream>>>(cv, qv, cam, claim_rule, lsv);
+  size_t smem;
+  const int cmax = align_up((int)nc, 16);
+  B200_CHECK(resolve_smem(cmax, &smem, (const void*)k_resolve_generic));
+  k_resolve_generic<<<1, 32, smem, h->stream>>>(cv, qv, cam, max_dist, claim_rule, lsv, d_acc, d_out, d_nm, cmax);
+  h->launches += 3;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(cur2q, d_out, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
 int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
                        int* nmatches) {
   if (!h || !kf || !f || !f2kf || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }

@@ -131,6 +131,7 @@ struct WalkCtx {     // per-instance pointers of the current frame
   const int *oct, *obs;
   const uint8_t* desc;
   float min_x, min_y, inv_w, inv_h;
+  int obs_block_min;   // a pre-existing MapPoint blocks its keypoint iff obs >= this (1: claim rule 0, 0: claim rule 1)
 };
 
 // GetFeaturesInArea (src/Frame.cc:465-518) fused with the static part of the candidate loops of the projection
@@ -160,11 +161,13 @@ __device__ __forceinline__ int warp_walk(const WalkCtx& g, const QueryGeom& q, c
     }
     const float dx = __fsub_rn(g.x[idx], q.u), dy = __fsub_rn(g.y[idx], q.v);
     if (!(fabsf(dx) < q.r && fabsf(dy) < q.r)) return false;
-    if (g.obs && g.obs[idx] > 0) return false;   // pre-existing MapPoint with observations: never a candidate
-    const float ur = g.uright[idx];
-    if (ur > 0) {
-      const float er = fabsf(__fsub_rn(q.ur, ur));
-      if (er > q.rr) return false;
+    if (g.obs && g.obs[idx] >= g.obs_block_min) return false;   // pre-existing MapPoint that blocks: never a candidate
+    if (g.uright) {   // stereo / RGB-D gate (null for the overloads without it)
+      const float ur = g.uright[idx];
+      if (ur > 0) {
+        const float er = fabsf(__fsub_rn(q.ur, ur));
+        if (er > q.rr) return false;
+      }
     }
     return true;
   };

@@ -46,6 +46,7 @@ __device__ __forceinline__ WalkCtx make_ctx(const CurView& cv, const MatchCam& c
   g.min_x = cam.min_x; g.min_y = cam.min_y;
   g.inv_w = __fdiv_rn((float)GRID_COLS, __fsub_rn(cam.max_x, cam.min_x));
   g.inv_h = __fdiv_rn((float)GRID_ROWS, __fsub_rn(cam.max_y, cam.min_y));
+  g.obs_block_min = 1;
   return g;
 }
 
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   WalkCtx g;
   g.off = s_off; g.idx = s_idx; g.x = s_x; g.y = s_y; g.uright = s_ur; g.oct = s_oct; g.obs = cobs;
   g.desc = reinterpret_cast<const uint8_t*>(s_desc);
-  g.min_x = cam.min_x; g.min_y = cam.min_y; g.inv_w = inv_w; g.inv_h = inv_h;
+  g.min_x = cam.min_x; g.min_y = cam.min_y; g.inv_w = inv_w; g.inv_h = inv_h; g.obs_block_min = 1;
   bool fwd, bwd;
   motion_flags(cam, cv.Tcw + (size_t)p * 16, lv.Tcw + (size_t)p * 16, fwd, bwd);
   const float* Tc = cv.Tcw + (size_t)p * 16;
@@ -505,6 +506,103 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   int* out = cur2last + co;
   for (int j = tid; j < nc; j += nthr) out[j] = state[j];
   if (tid == 0) nmatch[p] = s_nacc - s_pruned;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Generic guided search (orbm_search_projected): query geometry supplied by the caller
+// ---------------------------------------------------------------------------------------------------------------------
+struct QueriesView {
+  const uint8_t* valid;
+  const float *u, *v, *radius, *uright, *ang;
+  const int *min_level, *max_level, *obs;
+  const uint8_t* desc;
+  int n;
+};
+
+__device__ __forceinline__ bool setup_generic_query(const QueriesView& qv, int i, QueryGeom& q) {
+  if (!qv.valid[i]) return false;
+  q.u = qv.u[i]; q.v = qv.v[i]; q.r = qv.radius[i]; q.rr = q.r;
+  q.ur = qv.uright ? qv.uright[i] : 0.f;
+  q.min_level = qv.min_level[i]; q.max_level = qv.max_level[i];
+  return !(isnan(q.u) || isnan(q.v));
+}
+
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_generic(CurView cv, QueriesView qv, MatchCam cam, int claim_rule,
+                                                                  ListView out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * CAND_WARPS + (threadIdx.x >> 5);
+  if (i >= qv.n) return;
+  unsigned* list = out.list + (size_t)i * LCAP;
+  int cnt = 0;
+  QueryGeom q;
+  if (setup_generic_query(qv, i, q)) {
+    const uint8_t* d = qv.desc + (size_t)i * 32;
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+    WalkCtx g = make_ctx(cv, cam, 0);
+    g.obs_block_min = claim_rule ? 0 : 1;
+    if (!qv.uright) g.uright = nullptr;
+    cnt = warp_walk(g, q, d0, d1, [&](int ord, int idx, int dist) {
+      if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
+    });
+  }
+  if (lane == 0) out.count[i] = (cnt > LCAP) ? -cnt : cnt;
+}
+
+__global__ void __launch_bounds__(32) k_resolve_generic(CurView cv, QueriesView qv, MatchCam cam, int max_dist,
+                                                        int claim_rule, ListView in, int* accepted, int* cur2q,
+                                                        int* nmatch, int cmax) {
+  extern __shared__ __align__(16) unsigned char rsm[];
+  __shared__ int s_hist[ORBM_HISTO_LENGTH];
+  __shared__ int s_keep[3];
+  int* state = reinterpret_cast<int*>(rsm);
+  uint8_t* taken = rsm + (size_t)cmax * 4;
+  const int lane = threadIdx.x;
+  const int nc = cv.n[0];
+  for (int j = lane; j < nc; j += 32) {
+    state[j] = (cv.obs && cv.obs[j] >= 0) ? -2 : -1;
+    taken[j] = 0;
+  }
+  __syncwarp();
+  WalkCtx g = make_ctx(cv, cam, 0);
+  g.obs_block_min = claim_rule ? 0 : 1;
+  if (!qv.uright) g.uright = nullptr;
+  int n_acc = 0;
+  for (int i = 0; i < qv.n; ++i) {
+    const int cn = in.count[i];
+    int best_idx = -1, best_dist = 256;
+    if (cn > 0) {
+      const Pick pk = pick_min(in.list[(size_t)i * LCAP + lane], in.list[(size_t)i * LCAP + lane + 32], cn, taken, -1, lane);
+      best_idx = pk.idx; best_dist = pk.dist;
+    } else if (cn < 0) {
+      QueryGeom q;
+      if (setup_generic_query(qv, i, q)) {
+        const uint8_t* d = qv.desc + (size_t)i * 32;
+        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+        unsigned long long bk = ~0ull;
+        warp_walk(g, q, d0, d1, [&](int ord, int idx, int dist) {
+          if (!taken[idx]) { const unsigned long long kk = key64(dist, ord, idx); bk = (kk < bk) ? kk : bk; }
+        });
+        bk = warp_min64(bk);
+        if (bk != ~0ull) { best_idx = (int)(bk & 0x3fffffull); best_dist = (int)(bk >> 44); }
+      }
+    }
+    int a = -1;
+    if (best_idx >= 0 && best_dist <= max_dist) {
+      a = best_idx;
+      ++n_acc;
+      if (lane == 0) {
+        state[best_idx] = i;
+        if (claim_rule || (qv.obs ? qv.obs[i] : 1) > 0) taken[best_idx] = 1;
+      }
+    }
+    if (lane == 0) accepted[i] = a;
+    __syncwarp();
+  }
+  int pruned = 0;
+  if (cam.check_ori) pruned = prune_rotation(qv.n, accepted, qv.ang, nullptr, cv.ang, state, s_hist, s_keep, lane);
+  __syncwarp();
+  for (int j = lane; j < nc; j += 32) cur2q[j] = state[j];
+  if (lane == 0) *nmatch = n_acc - pruned;
 }
 
 // K9 (POINTS): best and second best among unclaimed candidates, level-aware ratio test (:98-152)

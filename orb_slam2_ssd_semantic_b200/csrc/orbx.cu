@@ -92,8 +92,8 @@ int orbx::init(const OrbxParams& p, int dev) {
 void orbx::free_geometry() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_raw); F(d_blur); F(d_cells); F(d_cand); F(d_cellcnt); F(d_qkp); F(d_qnode); F(d_sel); F(d_selcnt);
-  F(d_candcnt); F(d_kps); F(d_desc); F(d_n); F(d_xt); F(d_yt); F(d_tmp); F(d_blur_tiles);
-  d_blur_tiles = nullptr;
+  F(d_candcnt); F(d_kps); F(d_desc); F(d_n); F(d_xt); F(d_yt); F(d_tmp); F(d_blur_tiles); F(d_blur_edges);
+  d_blur_tiles = nullptr; d_blur_edges = nullptr;
   d_raw = d_blur = nullptr; d_cells = nullptr; d_cand = nullptr; d_cellcnt = nullptr; d_qkp = nullptr;
   d_qnode = nullptr; d_sel = nullptr; d_selcnt = nullptr; d_candcnt = nullptr; d_kps = nullptr; d_desc = nullptr;
   d_n = nullptr; d_xt = d_yt = nullptr; d_tmp = nullptr; tmp_bytes = 0;
@@ -208,6 +208,17 @@ int orbx::ensure_geometry(int r, int c, int F) {
   ltab.slot_begin[nl] = slots;
   ltab.sel_off[nl] = selcap;
   ncells = (int)cells.size();
+  {
+    int rwm = 0, rhm = 0;
+    for (const CellDesc& cd : cells) { rwm = std::max(rwm, (int)cd.rw); rhm = std::max(rhm, (int)cd.rh); }
+    fast_tp = (rwm + 3 <= FAST_TP_SMALL) ? FAST_TP_SMALL : FAST_TP_BIG;
+    fast_rows_max = rhm;
+    fast_smem = (size_t)FAST_WARPS * 2 * rhm * fast_tp;
+    if (fast_smem > 48 * 1024) {
+      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+    }
+  }
   slots_per_frame = align_up(slots, 4);
   sel_per_frame = selcap;
   cap = selcap;
@@ -261,6 +272,15 @@ int orbx::ensure_geometry(int r, int c, int F) {
       for (int y = 0; y < lh[l]; y += BLS_ROWS)
         for (int x = 0; x < lw[l]; x += 128) bt.push_back(BlurTile{(short)l, (short)x, (short)y, 0});
     n_blur_tiles = (int)bt.size();
+    std::vector<BlurEdge> be;
+    int rowsum = 0;
+    for (int l = 0; l < nl; ++l)
+      for (int x = 0; x < lw[l]; x += 4)
+        if (x < 4 || x + 8 > lw[l]) { be.push_back(BlurEdge{(short)l, (short)x, rowsum}); rowsum += lh[l]; }
+    n_blur_edges = (int)be.size();
+    blur_edge_rows = rowsum;
+    B200_CUDA(cudaMalloc(&d_blur_edges, sizeof(BlurEdge) * be.size()));
+    B200_CUDA(cudaMemcpyAsync(d_blur_edges, be.data(), sizeof(BlurEdge) * be.size(), cudaMemcpyHostToDevice, stream));
     B200_CUDA(cudaMalloc(&d_blur_tiles, sizeof(BlurTile) * bt.size()));
     B200_CUDA(cudaMemcpyAsync(d_blur_tiles, bt.data(), sizeof(BlurTile) * bt.size(), cudaMemcpyHostToDevice, stream));
     B200_CUDA(cudaStreamSynchronize(stream));   // bt is a local
@@ -300,8 +320,15 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
   int fast_aligned = 1;   // every level's rows 4-byte aligned? (internal planes always are; level 0 may alias a caller buffer)
   for (int l = 0; l < nl; ++l)
     if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) fast_aligned = 0;
-  k_fast_cells<<<dim3(ncells, F), FAST_THREADS, 0, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
-                                                            prm.min_th_fast, d_cand, d_cellcnt, fast_aligned);
+  {
+    const dim3 grd((ncells + FAST_WARPS - 1) / FAST_WARPS, F);
+    if (fast_tp == FAST_TP_SMALL)
+      k_fast_cells<FAST_TP_SMALL><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
+                                                                           prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max);
+    else
+      k_fast_cells<FAST_TP_BIG><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
+                                                                         prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max);
+  }
   ++launches;
   B200_CHECK(prof_mark(ST_FAST + 1));
   // K3 quad-tree: levels are launched in two groups so that each group's per-candidate arrays fit shared memory
@@ -322,7 +349,8 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
       if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) aligned = false;
     if (aligned) {
       k_blur7_strip<<<dim3(n_blur_tiles, F), 32, 0, stream>>>(rawv, blurv, d_blur_tiles);
-      ++launches;
+      k_blur7_edges<<<dim3((blur_edge_rows + 127) / 128, F), 128, 0, stream>>>(rawv, blurv, d_blur_edges, n_blur_edges, blur_edge_rows);
+      launches += 2;
     } else {
       for (int l = 0; l < nl; ++l) {
         dim3 grd((lw[l] + BL_TW - 1) / BL_TW, (lh[l] + BL_TH - 1) / BL_TH, F);

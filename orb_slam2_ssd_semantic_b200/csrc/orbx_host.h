@@ -33,6 +33,8 @@ struct orbx {
   b200::PyrView rawv{}, blurv{};
   int ncells = 0, slots_per_frame = 0, sel_per_frame = 0, cap = 0, qt_cap = 0;
   size_t qt_smem = 0;
+  int fast_tp = 0, fast_rows_max = 0;
+  size_t fast_smem = 0;
   int qt_group_lb[3] = {0, 0, 0}, qt_group_le[3] = {0, 0, 0}, qt_group_kcap[3] = {0, 0, 0};
   size_t qt_group_smem[3] = {0, 0, 0};
   uint8_t *d_raw = nullptr, *d_blur = nullptr;
@@ -48,7 +50,8 @@ struct orbx {
   int* d_n = nullptr;
   int2 *d_xt = nullptr, *d_yt = nullptr;
   b200::BlurTile* d_blur_tiles = nullptr;
-  int n_blur_tiles = 0;
+  b200::BlurEdge* d_blur_edges = nullptr;
+  int n_blur_tiles = 0, n_blur_edges = 0, blur_edge_rows = 0;
   void* d_tmp = nullptr;
   size_t tmp_bytes = 0;
   void* h_stage = nullptr;

@@ -100,14 +100,16 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
 constexpr int FAST_WARPS = 8;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_MAX_ROI = 72;   // ROI side bound enforced at create (cell <= 60 px + 6, padded)
-constexpr int FAST_TP = 80;        // compile-time tile pitch (>= 3 + 72, multiple of 4): ring offsets are immediates
+constexpr int FAST_TP_SMALL = 48;  // compile-time tile pitches (>= 3 + ROI width, multiple of 4): ring offsets are
+constexpr int FAST_TP_BIG = 80;    // immediates; SMALL serves ROIs up to 45 px (640x480: 43), BIG the general case
 
 // m(p) of one pixel.  Packing: one IMAD per ring pixel gives lo16 = 256 + (c - r), hi16 = 256 + (r - c) (biased,
 // both in [1, 511], so no borrow crosses the halves); min3/max3 on s16x2 then evaluate the bright and the dark
 // arcs at once: a3[i] = min(v[i..i+2]), a9[i] = min(a3[i], a3[i+3], a3[i+6]) = min over the 9-arc starting at i.
 // r0/r4/r8/r12 are the four compass pixels the caller already loaded for the quick rejection test.
+template <int TP>
 __device__ __forceinline__ int fast_m_exact(const uint8_t* c, int cv, int r0, int r4, int r8, int r12) {
-  constexpr int tp = FAST_TP;
+  constexpr int tp = TP;
   const int bias = 256 * 65537 - cv * 65535;
   unsigned v[16];
   v[0] = (unsigned)(r0 * 65535 + bias);                   v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
@@ -135,112 +137,108 @@ __device__ __forceinline__ int fast_m_exact(const uint8_t* c, int cv, int r0, in
   return max(0, max((int)(m0 & 0xffffu), (int)(m0 >> 16)) - 256);
 }
 
-// One CTA per (cell, frame); warp w owns rows w, w+8, ...; lane = column (second sweep for cells wider than 32).
+// One WARP per (cell, frame), 8 cells per CTA, no block-level synchronisation: the warp loads its ROI, walks the
+// rows (lane = column; a second sweep covers cells wider than 32), and compacts the survivors with a ballot per row
+// and a running offset -- row-major order for free.  Per-warp shared memory: ROI tile + score map, pitch TP.
 // `aligned` (host-checked): level rows are 4-byte aligned, so the ROI is fetched as aligned 32-bit words and kept
-// in shared memory at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).
+// at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).
+template <int TP>
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
                                                              int ncells, int slots_per_frame, int ini_th,
                                                              int min_th, unsigned* __restrict__ cand,
-                                                             int* __restrict__ cellcnt, int aligned) {
-  __shared__ __align__(16) uint8_t tile[FAST_MAX_ROI * FAST_TP];
-  __shared__ __align__(16) uint8_t mm[FAST_MAX_ROI * FAST_TP];
-  __shared__ unsigned rowmask[FAST_MAX_ROI][2];
-  __shared__ int rowoff[FAST_MAX_ROI + 1];
-  constexpr int tp = FAST_TP;
-  const CellDesc cd = cells[blockIdx.x];
-  const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+                                                             int* __restrict__ cellcnt, int aligned, int rows_max) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  constexpr int tp = TP;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int cell = blockIdx.x * FAST_WARPS + w, f = blockIdx.y;
+  if (cell >= ncells) return;
+  uint8_t* tile = fsm + (size_t)w * 2 * rows_max * tp;
+  uint8_t* mm = tile + (size_t)rows_max * tp;
+  const CellDesc cd = cells[cell];
   const int l = cd.level, rw = cd.rw, rh = cd.rh;
   const int pitch = pyr.pitch[l];
   const int sh = aligned ? (cd.x0 & 3) : 0;   // byte phase of the ROI inside its first word
   {
     const uint8_t* img = pyr.p[l] + (size_t)f * pyr.fstride[l] + (size_t)cd.y0 * pitch + (cd.x0 - sh);
     if (aligned) {
-      const int nw = (sh + rw + 3) >> 2;
-      for (int y = w; y < rh; y += FAST_WARPS)
-        if (lane < nw) reinterpret_cast<unsigned*>(tile + y * tp)[lane] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + lane);
+      const int nw = (sh + rw + 3) >> 2;   // words per ROI row
+      if (nw <= 16) {                      // two rows per step: lanes 0-15 / 16-31
+        const int k = lane & 15, half = lane >> 4;
+        for (int y = half; y < rh; y += 2)
+          if (k < nw) reinterpret_cast<unsigned*>(tile + y * tp)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
+      } else {
+        for (int y = 0; y < rh; ++y)
+          for (int k = lane; k < nw; k += 32)
+            reinterpret_cast<unsigned*>(tile + y * tp)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
+      }
     } else {
-      for (int y = w; y < rh; y += FAST_WARPS)
+      for (int y = 0; y < rh; ++y)
         for (int x = lane; x < rw; x += 32) tile[y * tp + x] = __ldg(img + (size_t)y * pitch + x);
     }
     // only the one-pixel frame around the detection range is read without being written: clear it
-    for (int i = threadIdx.x; i < rw; i += FAST_THREADS) { mm[2 * tp + sh + i] = 0; mm[(rh - 3) * tp + sh + i] = 0; }
-    for (int i = threadIdx.x; i < rh; i += FAST_THREADS) { mm[i * tp + sh + 2] = 0; mm[i * tp + sh + rw - 3] = 0; }
+    for (int i = lane; i < rw; i += 32) { mm[2 * tp + sh + i] = 0; mm[(rh - 3) * tp + sh + i] = 0; }
+    for (int i = lane; i < rh; i += 32) { mm[i * tp + sh + 2] = 0; mm[i * tp + sh + rw - 3] = 0; }
   }
-  __syncthreads();
+  __syncwarp();
   unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
-  const int ih = rh - 6;
+  const bool wide = rw - 6 > 32;
   int total = 0;
   // pass 0: everything at ini_th (pixels with m <= ini_th can neither be corners nor outscore one at that threshold);
   // pass 1 (:821, only when the cell is EMPTY AFTER non-max suppression): the same at min_th.
   for (int pass = 0; pass < 2 && total == 0; ++pass) {
     const int t = pass ? min_th : ini_th;
     if (pass == 1 && ini_th == min_th) break;
-    for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
+    {
+      const uint8_t* c = tile + 3 * tp + sh + 3 + lane;
+      uint8_t* q = mm + 3 * tp + sh + 3 + lane;
+      for (int y = 3; y < rh - 3; ++y, c += tp, q += tp) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int x = 3 + lane + 32 * h;
-        if (x < rw - 3) {
-          const uint8_t* c = &tile[y * tp + sh + x];
-          const int cv = c[0], r0 = c[3 * tp], r8 = c[-3 * tp], r4 = c[3], r12 = c[-3];
-          // necessary condition for a corner at t: every 9-arc contains one pixel of each opposite pair
-          const bool p0 = abs(cv - r0) > t || abs(cv - r8) > t;
-          const bool p4 = abs(cv - r4) > t || abs(cv - r12) > t;
-          int m = 0;
-          if (p0 && p4) m = fast_m_exact(c, cv, r0, r4, r8, r12);
-          mm[y * tp + sh + x] = (uint8_t)((m > t) ? m : 0);
-        }
-      }
-    }
-    __syncthreads();
-    // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving
-    // compaction: ballots per row, one scan over the rows.
-    for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int x = 3 + lane + 32 * h;
-        bool keep = false;
-        if (x < rw - 3) {
-          const uint8_t* q = &mm[y * tp + sh + x];
-          const int m = q[0];
-          if (m > 0) {   // m > t
-            const int n0 = max(max((int)q[-tp - 1], (int)q[-tp]), (int)q[-tp + 1]);
-            const int n1 = max(max((int)q[-1], (int)q[1]), (int)q[tp - 1]);
-            const int n2 = max((int)q[tp], (int)q[tp + 1]);
-            const int nmax = max(max(n0, n1), n2);
-            keep = m > max(nmax, 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t else 0)
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !wide) break;
+          if (3 + lane + 32 * h < rw - 3) {
+            const uint8_t* cc = c + 32 * h;
+            const int cv = cc[0], r0 = cc[3 * tp], r8 = cc[-3 * tp], r4 = cc[3], r12 = cc[-3];
+            // necessary condition for a corner at t: every 9-arc contains one pixel of each opposite pair
+            const bool p0 = abs(cv - r0) > t || abs(cv - r8) > t;
+            const bool p4 = abs(cv - r4) > t || abs(cv - r12) > t;
+            int m = 0;
+            if (p0 && p4) m = fast_m_exact<TP>(cc, cv, r0, r4, r8, r12);
+            q[32 * h] = (uint8_t)((m > t) ? m : 0);
           }
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, keep);
-        if (lane == 0) rowmask[y][h] = bal;
       }
     }
-    __syncthreads();
-    if (w == 0) {   // exclusive scan of the per-row counts (ih <= 66 rows)
-      int run = 0;
-      for (int base = 0; base < ih; base += 32) {
-        const int y = 3 + base + lane;
-        const int c = (base + lane < ih) ? (__popc(rowmask[y][0]) + __popc(rowmask[y][1])) : 0;
-        const int inc = warp_incl_scan(c, lane);
-        if (base + lane < ih) rowoff[y] = run + inc - c;
-        run += __shfl_sync(0xffffffffu, inc, 31);
+    __syncwarp();
+    // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving
+    // compaction: one ballot per row sweep, running offset.
+    {
+      const uint8_t* q = mm + 3 * tp + sh + 3 + lane;
+      for (int y = 3; y < rh - 3; ++y, q += tp) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h == 1 && !wide) break;
+          bool keep = false;
+          int m = 0;
+          if (3 + lane + 32 * h < rw - 3) {
+            const uint8_t* qq = q + 32 * h;
+            m = qq[0];
+            if (m > 0) {   // m > t
+              const int n0 = max(max((int)qq[-tp - 1], (int)qq[-tp]), (int)qq[-tp + 1]);
+              const int n1 = max(max((int)qq[-1], (int)qq[1]), (int)qq[tp - 1]);
+              const int n2 = max((int)qq[tp], (int)qq[tp + 1]);
+              const int nmax = max(max(n0, n1), n2);
+              keep = m > max(nmax, 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t else 0)
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, keep);
+          if (keep) out[total + __popc(bal & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 3 + lane + 32 * h, cd.y0 + y, m - 1);
+          total += __popc(bal);
+        }
       }
-      if (lane == 0) rowoff[0] = run;
     }
-    __syncthreads();
-    total = rowoff[0];
-    __syncthreads();   // rowoff[0] is rewritten by the next pass
+    __syncwarp();
   }
-  if (total > 0) {
-    for (int y = 3 + w; y < rh - 3; y += FAST_WARPS) {
-      const unsigned b0 = rowmask[y][0], b1 = rowmask[y][1];
-      const int base = rowoff[y];
-      if ((b0 >> lane) & 1u)
-        out[base + __popc(b0 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 3 + lane, cd.y0 + y, mm[y * tp + sh + 3 + lane] - 1);
-      if ((b1 >> lane) & 1u)
-        out[base + __popc(b0) + __popc(b1 & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 35 + lane, cd.y0 + y, mm[y * tp + sh + 35 + lane] - 1);
-    }
-  }
-  if (threadIdx.x == 0) cellcnt[(size_t)f * ncells + blockIdx.x] = total;
+  if (lane == 0) cellcnt[(size_t)f * ncells + cell] = total;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -331,21 +329,11 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
   }
   const unsigned* fcand = cand + (size_t)f * slots_per_frame;
   const int* fcnt = cellcnt + (size_t)f * ncells;
-  // The per-candidate arrays (packed keypoint + node id) live in shared memory when this level's candidates fit
-  // (every round then walks shared memory instead of L2); otherwise in the global scratch.
-  unsigned* qkp = sc.qkp + (size_t)f * slots_per_frame + lt.slot_begin[l];
-  int* qnode = sc.qnode + (size_t)f * slots_per_frame + lt.slot_begin[l];
-  {
-    int part = 0;
-    for (int c = tid; c < lt.cell_begin[l + 1] - lt.cell_begin[l]; c += nthr) part += fcnt[lt.cell_begin[l] + c];
-    int ktot;
-    block_excl_scan(part, ws, &ktot);
-    if (ktot <= kp_smem_cap) {
-      qkp = reinterpret_cast<unsigned*>(smem_raw + qt_smem_bytes(qt_cap));
-      qnode = reinterpret_cast<int*>(qkp + kp_smem_cap);
-    }
-  }
-
+  // Per-candidate arrays (packed keypoint + node id) stay in the L2-resident global scratch: staging them in shared
+  // memory was measured slower on B200 (profiles/r01_notes.md) -- it costs CTA-level concurrency and generic addressing.
+  unsigned* __restrict__ qkp = sc.qkp + (size_t)f * slots_per_frame + lt.slot_begin[l];
+  int* __restrict__ qnode = sc.qnode + (size_t)f * slots_per_frame + lt.slot_begin[l];
+  (void)kp_smem_cap;
   // ---- gather this level's per-cell segments into one contiguous, order-preserving list -----------
   const int cb = lt.cell_begin[l], nc = lt.cell_begin[l + 1] - cb;
   int K = 0;
@@ -711,20 +699,8 @@ constexpr int BLS_ROWS = 35;   // multiple of 7: the ring rotation is unrolled b
 
 struct HRow { unsigned h02, h13; };   // horizontal sums of pixels (0,2) and (1,3) of the thread's 4 columns
 
-__device__ __forceinline__ HRow blur_hrow(const uint8_t* __restrict__ row, int x0, int w) {
-  unsigned w0, w1, w2;   // bytes x0-4 .. x0+7
-  if (x0 >= 4 && x0 + 8 <= w) {
-    const unsigned* p = reinterpret_cast<const unsigned*>(row + x0 - 4);
-    w0 = __ldg(p); w1 = __ldg(p + 1); w2 = __ldg(p + 2);
-  } else {   // image border: assemble the same three words through BORDER_REFLECT_101
-    unsigned b[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) b[i] = __ldg(row + reflect101(x0 - 4 + i, w));
-    w0 = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
-    w1 = b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24);
-    w2 = b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24);
-  }
-  // P[k] = byte(k+1) | byte(k+3) << 16 of the 12-byte window, i.e. source pixels x0-3+k and x0-1+k
+__device__ __forceinline__ HRow blur_hrow_words(unsigned w0, unsigned w1, unsigned w2) {
+  // w0..w2 = bytes x0-4 .. x0+7.  P[k] = byte(k+1) | byte(k+3) << 16, i.e. source pixels x0-3+k and x0-1+k
   unsigned P[8];
   P[0] = __funnelshift_r(w0, w1, 8) & 0x00ff00ffu;    // bytes 1,3
   P[1] = __funnelshift_r(w0, w1, 16) & 0x00ff00ffu;   // bytes 2,4
@@ -740,6 +716,21 @@ __device__ __forceinline__ HRow blur_hrow(const uint8_t* __restrict__ row, int x
   return r;
 }
 
+// interior column groups only (x0 >= 4 and x0 + 8 <= w): three aligned word loads, no border logic
+__device__ __forceinline__ HRow blur_hrow(const uint8_t* __restrict__ row, int x0) {
+  const unsigned* p = reinterpret_cast<const unsigned*>(row + x0 - 4);
+  return blur_hrow_words(__ldg(p), __ldg(p + 1), __ldg(p + 2));
+}
+
+// border column groups: the same three words assembled through BORDER_REFLECT_101
+__device__ __forceinline__ HRow blur_hrow_border(const uint8_t* __restrict__ row, int x0, int w) {
+  unsigned b[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) b[i] = __ldg(row + reflect101(x0 - 4 + i, w));
+  return blur_hrow_words(b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24), b[4] | (b[5] << 8) | (b[6] << 16) | (b[7] << 24),
+                         b[8] | (b[9] << 8) | (b[10] << 16) | (b[11] << 24));
+}
+
 struct BlurTile { short level, x0, y0, pad; };   // one warp-tile: 128 columns x BLS_ROWS rows of one level
 
 // All levels in ONE launch (a thread walks 35+6 rows sequentially, so a per-level launch is bounded below by that
@@ -748,7 +739,7 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
   const BlurTile t = tiles[blockIdx.x];
   const int l = t.level, w = src.w[l], h = src.h[l];
   const int x0 = t.x0 + threadIdx.x * 4;
-  if (x0 >= w) return;
+  if (x0 < 4 || x0 + 8 > w) return;   // border column groups (<= 3 per row) are done by k_blur7_edges
   const int spitch = src.pitch[l], dpitch = dstv.pitch[l];
   const uint8_t* s = src.p[l] + (size_t)blockIdx.y * src.fstride[l];
   uint8_t* d = dstv.p[l] + (size_t)blockIdx.y * dstv.fstride[l];
@@ -756,7 +747,7 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
   unsigned ring[7][4];   // unpacked horizontal sums (pixels 0..3) of 7 consecutive rows, slot = row phase
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
-    const HRow r = blur_hrow(s + (size_t)reflect101(y0 - 3 + j, h) * spitch, x0, w);
+    const HRow r = blur_hrow(s + (size_t)reflect101(y0 - 3 + j, h) * spitch, x0);
     ring[j][0] = r.h02 & 0xffffu; ring[j][2] = r.h02 >> 16; ring[j][1] = r.h13 & 0xffffu; ring[j][3] = r.h13 >> 16;
   }
   for (int yb = y0; yb < y1; yb += 7) {
@@ -765,7 +756,7 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
       const int y = yb + k;
       if (y < y1) {
         // rows y-3 .. y+2 sit in slots (k+0)%7 .. (k+5)%7; the new row y+3 goes to slot (k+6)%7
-        const HRow r = blur_hrow(s + (size_t)reflect101(y + 3, h) * spitch, x0, w);
+        const HRow r = blur_hrow(s + (size_t)reflect101(y + 3, h) * spitch, x0);
         ring[(k + 6) % 7][0] = r.h02 & 0xffffu; ring[(k + 6) % 7][2] = r.h02 >> 16;
         ring[(k + 6) % 7][1] = r.h13 & 0xffffu; ring[(k + 6) % 7][3] = r.h13 >> 16;
         unsigned out = 0;
@@ -779,6 +770,34 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
       }
     }
   }
+}
+
+// Border column groups of every row of every level (the group at x0 = 0 and the last one or two groups): one thread
+// per (row, group), full 7x7 through BORDER_REFLECT_101.  ~3 % of the pixels.
+struct BlurEdge { short level, x0; int row_begin; };   // rows of this (level, group) start at linear index row_begin
+
+__global__ void __launch_bounds__(128) k_blur7_edges(PyrView src, PyrView dstv, const BlurEdge* __restrict__ edges,
+                                                     int nedges, int total_rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_rows) return;
+  int e = 0;
+  while (e + 1 < nedges && edges[e + 1].row_begin <= i) ++e;   // nedges <= 3 * nlevels
+  const int l = edges[e].level, x0 = edges[e].x0, y = i - edges[e].row_begin;
+  const int w = src.w[l], h = src.h[l], spitch = src.pitch[l];
+  const uint8_t* s = src.p[l] + (size_t)blockIdx.y * src.fstride[l];
+  uint8_t* d = dstv.p[l] + (size_t)blockIdx.y * dstv.fstride[l];
+  unsigned acc[4] = {0, 0, 0, 0};
+  const unsigned q[7] = {18, 34, 48, 56, 48, 34, 18};
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const HRow r = blur_hrow_border(s + (size_t)reflect101(y - 3 + j, h) * spitch, x0, w);
+    acc[0] += q[j] * (r.h02 & 0xffffu); acc[2] += q[j] * (r.h02 >> 16);
+    acc[1] += q[j] * (r.h13 & 0xffffu); acc[3] += q[j] * (r.h13 >> 16);
+  }
+  unsigned out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) out |= ((acc[k] + 32768u) >> 16) << (8 * k);
+  *reinterpret_cast<unsigned*>(d + (size_t)y * dstv.pitch[l] + x0) = out;
 }
 
 // bordered level read-back for orbx_get_level (copyMakeBorder BORDER_REFLECT_101, :1136-1142)

@@ -77,6 +77,12 @@ class PointCloudMapping:
         _lib.check(self._L.ocm_query(self._h, ptr(p), C.byref(v), C.byref(f)))
         return (v.value if f.value else None)
 
+    def SaveOctoMap(self, name: str):
+        """MapDrawer::SaveOctoMap (perfect/src/MapDrawer.cc:1103-1111): writes a pruned ColorOcTree `.ot` file
+        (octovis-readable) from the GPU leaf map.  Returns (leaves, nodes)."""
+        from . import octree_io
+        return octree_io.save_octomap(self, name)
+
     def sync(self):
         _lib.check(self._L.ocm_sync(self._h))
 

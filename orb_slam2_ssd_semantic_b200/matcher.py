@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import BowView, FrameView, LastView, TrackPointsView, ptr  # noqa: F401
+from ._abi import BowView, FrameView, LastView, QueriesView, TrackPointsView, ptr  # noqa: F401
 
 
 class ORBmatcher:
@@ -59,6 +59,16 @@ class ORBmatcher:
                                                                 self.mfNNratio, ptr(out), C.byref(nm)))
         else:
             raise TypeError("SearchByProjection: second argument must be a LastView or a TrackPointsView")
+        return nm.value, out
+
+    def SearchProjected(self, F: FrameView, queries: QueriesView, max_dist: int, claim_rule: int = 1):
+        """Shared tail of the projection overloads whose geometry the caller computes (relocalisation
+        src/ORBmatcher.cc:1757-1899 -> claim_rule 1, max_dist = ORBdist; see include/b200orb.h)."""
+        out = np.full(F.n, -1, np.int32)
+        nm = C.c_int(0)
+        fs, qs = F.struct(), queries.struct()
+        _lib.check(self._L.orbm_search_projected(self._h, C.byref(fs), C.byref(qs), int(max_dist), int(claim_rule),
+                                                 int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
 
     def SearchByBoW(self, pKF: BowView, F: BowView):

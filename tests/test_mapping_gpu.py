@@ -97,3 +97,21 @@ def test_no_leaf_filter_and_other_resolution(oracle):
     assert np.abs(_sorted_pts(pg) - _sorted_pts(pr)).max() <= 1e-5
     a, b = _leaf_dict(*gpu.export_leaves()[:2]), _leaf_dict(*ref.export_leaves())
     assert (a[0] == b[0]).all() and np.abs(a[1] - b[1]).max() <= 1e-5
+
+
+def test_save_octomap_round_trip(oracle, tmp_path):
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    from orb_slam2_ssd_semantic_b200 import octree_io as O
+    gpu = PointCloudMapping(0.05)
+    for depth, rgb, T in _scene(3):
+        gpu.insertKeyFrame(T, depth, rgb, synth.FX, synth.FY, synth.CX, synth.CY)
+    path = str(tmp_path / "map.ot")
+    nleaves, nnodes = gpu.SaveOctoMap(path)
+    res, nodes, hdr = O.read_ot(path)
+    assert hdr.startswith("# Octomap OcTree file") and "id ColorOcTree" in hdr and res == 0.05
+    keys, depths, vals, cols, consistent, used = O.leaves_from_nodes(nodes)
+    assert consistent and used == len(nodes) == nnodes
+    k16, v16, _ = O.expand_to_max_depth(keys, depths, vals, cols)
+    kg, lg, _ = gpu.export_leaves()
+    a, b = _leaf_dict(k16, v16), _leaf_dict(kg, lg)
+    assert len(a[0]) == nleaves and (a[0] == b[0]).all() and (a[1] == b[1]).all()

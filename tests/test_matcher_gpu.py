@@ -189,3 +189,44 @@ def test_projection_last_huge_frame_uses_unfused_path(oracle):
     n_ref, ref = oracle.search_by_projection_last(cur, last, 15.0, False, 0.9, True)
     n_gpu, gpu = ORBmatcher(0.9, True).SearchByProjection(cur, last, 15.0, False)
     assert n_ref > 500 and n_gpu == n_ref and (gpu == ref).all()
+
+
+def test_search_projected_relocalisation_variant(oracle, stream_feats):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1757-1899) through the
+    generic API: the shim side (projection, distance gates, MapPoint::PredictScale src/MapPoint.cc:448-480) is done
+    here in float like the reference; the candidate loop / claim rule / rotation prune run on the GPU."""
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    from orb_slam2_ssd_semantic_b200._abi import FrameView, QueriesView
+    feats, sf = stream_feats
+    rng = np.random.default_rng(17)
+    Kc, Dc, dc, Tc = feats[3]
+    Kk, Dk, dk, Tk = feats[0]
+    ur, _, _, _ = oracle.stereo_unproject(Kc, dc, Tc, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+    _, _, xw, valid = oracle.stereo_unproject(Kk, dk, Tk, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+    R, t = Tc[:3, :3].astype(np.float32), Tc[:3, 3].astype(np.float32)
+    Pc = (xw @ R.T + t).astype(np.float32)
+    invz = (np.float32(1.0) / Pc[:, 2]).astype(np.float32)
+    u = (np.float32(synth.FX) * Pc[:, 0] * invz + np.float32(synth.CX)).astype(np.float32)
+    v = (np.float32(synth.FY) * Pc[:, 1] * invz + np.float32(synth.CY)).astype(np.float32)
+    Ow = (-R.T @ t).astype(np.float32)
+    dist3d = np.linalg.norm(xw - Ow, axis=1).astype(np.float32)
+    maxd = dist3d * sf[Kk["octave"]] * np.float32(1.2)          # mfMaxDistance ~ dist * levelScaleFactor (MapPoint.cc:404-417)
+    ratio = maxd / dist3d
+    lvl = np.clip(np.ceil(np.log(ratio) / np.log(np.float32(1.2))).astype(np.int32), 0, 7)   # PredictScale
+    ok = (valid > 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480) & (rng.random(len(Kk)) < 0.9)
+    for th, orbdist, ori in ((10.0, 100, True), (3.0, 64, True), (10.0, 100, False)):
+        q = QueriesView(ok.astype(np.uint8), u, v, (np.float32(th) * sf[lvl]).astype(np.float32), lvl - 1, lvl + 1, Dk,
+                        Kk["angle"])
+        F = FrameView(Kc["x"], Kc["y"], Kc["octave"], Kc["angle"], ur, Dc, Tc, synth.FX, synth.FY, synth.CX, synth.CY,
+                      synth.BF, 0.0, 640.0, 0.0, 480.0, sf, mp_obs=np.where(rng.random(len(Kc)) < 0.1, 0, -1).astype(np.int32))
+        n_ref, ref = oracle.search_projected(F, q, orbdist, 1, ori)
+        n_gpu, gpu = ORBmatcher(0.9, ori).SearchProjected(F, q, orbdist, 1)
+        assert n_ref > 30 and n_gpu == n_ref and (gpu == ref).all(), (th, orbdist, ori)
+    # claim rule 0 with a stereo gate == the LAST semantics on supplied geometry
+    q = QueriesView(ok.astype(np.uint8), u, v, (np.float32(15.0) * sf[Kk["octave"]]).astype(np.float32), Kk["octave"] - 1,
+                    Kk["octave"] + 1, Dk, Kk["angle"], uright=(u - np.float32(synth.BF) * invz).astype(np.float32),
+                    obs=rng.integers(0, 2, len(Kk)).astype(np.int32))
+    F.mp_obs = None
+    n_ref, ref = oracle.search_projected(F, q, 100, 0, True)
+    n_gpu, gpu = ORBmatcher(0.9, True).SearchProjected(F, q, 100, 0)
+    assert n_ref > 100 and n_gpu == n_ref and (gpu == ref).all()

@@ -179,3 +179,23 @@ def test_restated_glibc_sincosf_equals_host_libm(oracle):
     two_pi_bits = int(np.float32(6.2831855).view(np.uint32))
     assert L.orb_ref_sincosf_mismatches(0, two_pi_bits + 64, 53) == 0        # ~20 M angles, every binade
     assert L.orb_ref_sincosf_mismatches(int(np.float32(3.0).view(np.uint32)), two_pi_bits, 1) == 0   # dense top binade
+
+
+def test_ot_export_round_trips_reference_octomap():
+    """octree_io.build_ot(leaves of the reference's octomap.ot) reproduces that file: same node count and pre-order,
+    every log-odds value, every child mask, every leaf colour (inner colours are history dependent in octomap and
+    are written white -- see octree_io.py)."""
+    from orb_slam2_ssd_semantic_b200 import octree_io as O
+    z = np.load(os.path.join(G, "octomap_nodes.npz"))
+    nodes = np.zeros(len(z["v"]), O.NODE_DT)
+    nodes["v"], nodes["rgb"], nodes["child"] = z["v"], z["rgb"], z["child"]
+    keys, depths, vals, cols, consistent, used = O.leaves_from_nodes(nodes)
+    assert consistent and used == len(nodes)               # inner value == max over children everywhere
+    assert np.bincount(depths, minlength=17)[13:].tolist() == [4, 187, 8376, 310363]   # pruned leaves exist
+    k16, v16, c16 = O.expand_to_max_depth(keys, depths, vals, cols)
+    out = O.build_ot(k16, v16, c16, 0.05, "0.05")
+    res, n2, hdr = O.read_ot(out)
+    assert hdr == str(z["header"]) and len(n2) == len(nodes) == 390133
+    assert (n2["v"] == nodes["v"]).all() and (n2["child"] == nodes["child"]).all()
+    leaf = nodes["child"] == 0
+    assert (n2["rgb"][leaf] == nodes["rgb"][leaf]).all()

@@ -113,6 +113,9 @@ def octomap_fixture():
     print("octomap nodes", size, "res", res, "distinct values", len(vals), "leaf distinct", len(leaf_vals))
     np.savez_compressed(os.path.join(G, "octomap_logodds.npz"), values=vals, leaf_values=leaf_vals, size=np.int64(size),
                         res=np.float64(res))
+    # the whole node array (pre-order) for the .ot exporter round trip (orb_slam2_ssd_semantic_b200/octree_io.py)
+    np.savez_compressed(os.path.join(G, "octomap_nodes.npz"), v=body["v"], rgb=body["rgb"], child=body["child"],
+                        header=np.array(header))
 
 
 if __name__ == "__main__":
