@@ -201,9 +201,8 @@ def run_b200(args):
         # tracking (extract + glue + match) on the pipeline stream, dense mapping on its own stream beside it -- the
         # reference also maps on a separate thread (src/pointcloudmapping.cc:43)
         st.track_batch_device(d_gray.data_ptr(), d_depth.data_ptr(), d_T.data_ptr(), F, ROWS, COLS)
-        for t in kfs:
-            pcm.insert_keyframe_device(d_depth.data_ptr() + 4 * npx * t, d_rgb.data_ptr() + 3 * npx * t, ROWS, COLS, T[t],
-                                       synth.FX, synth.FY, synth.CX, synth.CY)
+        pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), ROWS, COLS, kfs, T[kfs], synth.FX, synth.FY,
+                                    synth.CX, synth.CY)
 
     def join_streams():
         ev = torch.cuda.Event()

@@ -270,6 +270,13 @@ int ocm_insert_keyframe(ocm_t* h, const float* depth, const uint8_t* rgb, int ro
 int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
                                const float Tcw[16], float fx, float fy, float cx, float cy,
                                const uint8_t* d_ground_label);
+/* Batched variant for a resident RGB-D stream: inserts keyframes frame_idx[0..n) (in that order) of a batch laid out
+ * as depth[F][rows][cols] f32, rgb[F][rows][cols][3] u8 in HBM, Tcw[n][16] on the host (one pose per inserted
+ * keyframe).  One call enqueues everything on the handle's stream (what UpdateOctomap's loop does,
+ * perfect/src/MapDrawer.cc:610-638). */
+int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
+                                const int32_t* frame_idx, int n, const float* Tcw, float fx, float fy, float cx,
+                                float cy);
 /* World-frame points of the LAST inserted keyframe after gating + leaf filter + transform (xyz f32 x n,
  * unordered: compare as sets). */
 int ocm_last_points(ocm_t* h, float* xyz, uint8_t* rgb, int cap, int* n);

@@ -608,6 +608,20 @@ int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_
   return h->insert(d_depth, d_rgb, d_label, rows, cols, Tcw, fx, fy, cx, cy);
 }
 
+int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
+                                const int32_t* frame_idx, int n, const float* Tcw, float fx, float fy, float cx,
+                                float cy) {
+  if (!h || !d_depth || !d_rgb || !frame_idx || !Tcw || rows <= 0 || cols <= 0 || n < 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  const size_t npix = (size_t)rows * cols;
+  for (int i = 0; i < n; ++i) {
+    if (frame_idx[i] < 0) { set_error("negative frame index"); return B200ORB_EINVAL; }
+    B200_CHECK(h->insert(d_depth + npix * frame_idx[i], d_rgb + npix * 3 * frame_idx[i], nullptr, rows, cols, Tcw + 16 * i, fx,
+                         fy, cx, cy));
+  }
+  return B200ORB_OK;
+}
+
 int ocm_insert_keyframe(ocm_t* h, const float* depth, const uint8_t* rgb, int rows, int cols, const float Tcw[16],
                         float fx, float fy, float cx, float cy, const uint8_t* ground_label) {
   if (!h || !depth || !rgb || !Tcw || rows <= 0 || cols <= 0) { set_error("bad argument"); return B200ORB_EINVAL; }

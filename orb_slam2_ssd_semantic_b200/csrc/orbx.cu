@@ -273,12 +273,11 @@ int orbx::ensure_geometry(int r, int c, int F) {
         for (int x = 0; x < lw[l]; x += 128) bt.push_back(BlurTile{(short)l, (short)x, (short)y, 0});
     n_blur_tiles = (int)bt.size();
     std::vector<BlurEdge> be;
-    int rowsum = 0;
     for (int l = 0; l < nl; ++l)
       for (int x = 0; x < lw[l]; x += 4)
-        if (x < 4 || x + 8 > lw[l]) { be.push_back(BlurEdge{(short)l, (short)x, rowsum}); rowsum += lh[l]; }
+        if (x < 4 || x + 8 > lw[l])
+          for (int y = 0; y < lh[l]; y += BLS_ROWS) be.push_back(BlurEdge{(short)l, (short)x, (short)y, 0});
     n_blur_edges = (int)be.size();
-    blur_edge_rows = rowsum;
     B200_CUDA(cudaMalloc(&d_blur_edges, sizeof(BlurEdge) * be.size()));
     B200_CUDA(cudaMemcpyAsync(d_blur_edges, be.data(), sizeof(BlurEdge) * be.size(), cudaMemcpyHostToDevice, stream));
     B200_CUDA(cudaMalloc(&d_blur_tiles, sizeof(BlurTile) * bt.size()));
@@ -310,9 +309,16 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
   // K1 pyramid
   for (int l = 1; l < nl; ++l) {
     dim3 blk(32, 8), grd((lw[l] + 127) / 128, (lh[l] + 7) / 8, F);
-    k_resize<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lw[l - 1], lh[l - 1],
-                                     rawv.p[l], rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xt + xt_off[l],
-                                     d_yt + yt_off[l]);
+    // k_resize_w needs aligned source rows and 4 outputs within a 12-byte source window (scale factor <= 2)
+    const bool src_aligned = prm.scale_factor <= 2.0f && (((uintptr_t)rawv.p[l - 1]) & 3) == 0 && (rawv.pitch[l - 1] & 3) == 0 && (rawv.fstride[l - 1] & 3) == 0;
+    if (src_aligned)
+      k_resize_w<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lw[l - 1], lh[l - 1],
+                                         rawv.p[l], rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xt + xt_off[l],
+                                         d_yt + yt_off[l]);
+    else
+      k_resize<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lw[l - 1], lh[l - 1],
+                                       rawv.p[l], rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xt + xt_off[l],
+                                       d_yt + yt_off[l]);
     ++launches;
   }
   B200_CHECK(prof_mark(ST_RESIZE + 1));
@@ -349,7 +355,7 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
       if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) aligned = false;
     if (aligned) {
       k_blur7_strip<<<dim3(n_blur_tiles, F), 32, 0, stream>>>(rawv, blurv, d_blur_tiles);
-      k_blur7_edges<<<dim3((blur_edge_rows + 127) / 128, F), 128, 0, stream>>>(rawv, blurv, d_blur_edges, n_blur_edges, blur_edge_rows);
+      k_blur7_edges<<<dim3((n_blur_edges + 63) / 64, F), 64, 0, stream>>>(rawv, blurv, d_blur_edges, n_blur_edges);
       launches += 2;
     } else {
       for (int l = 0; l < nl; ++l) {

@@ -89,6 +89,49 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
   *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
 }
 
+// K1 (fast path, 4-byte aligned source rows): each thread still produces 4 adjacent destination pixels, but fetches
+// the two source rows as aligned 32-bit words (the 4 outputs need at most 8 consecutive source bytes = 3 words), picks
+// every (s[x], s[x+1]) byte pair with ONE dynamic PRMT and does the horizontal pass with ONE two-way dot product
+// (IDP.2A: a0*s[x] + a1*s[x+1], 16-bit coefficients x 8-bit pixels) per row.  Same integer arithmetic as k_resize.
+__global__ void __launch_bounds__(256) k_resize_w(const uint8_t* __restrict__ src, int spitch, size_t sfs, int sw,
+                                                  int sh, uint8_t* __restrict__ dst, int dpitch, size_t dfs,
+                                                  int dw, int dh, const int2* __restrict__ xt,
+                                                  const int2* __restrict__ yt) {
+  const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int dy = blockIdx.y * 8 + threadIdx.y;
+  if (dx0 >= dw || dy >= dh) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
+  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
+  const int2 ty = __ldg(&yt[dy]);
+  const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+  const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+  int2 tx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tx[i] = __ldg(&xt[min(dx0 + i, dw - 1)]);
+  const int xb = tx[0].x & ~3;                 // first source word; the 4 outputs read bytes xb .. xb+11 at most
+  const int wlast = (spitch >> 2) - 1;         // never read past the row's last word (pitch is a multiple of 4)
+  const int wi = xb >> 2;
+  const unsigned* r0 = reinterpret_cast<const unsigned*>(s + (size_t)sy0 * spitch);
+  const unsigned* r1 = reinterpret_cast<const unsigned*>(s + (size_t)sy1 * spitch);
+  const unsigned a0 = __ldg(r0 + wi), a1 = __ldg(r0 + min(wi + 1, wlast)), a2 = __ldg(r0 + min(wi + 2, wlast));
+  const unsigned c0 = __ldg(r1 + wi), c1 = __ldg(r1 + min(wi + 1, wlast)), c2 = __ldg(r1 + min(wi + 2, wlast));
+  unsigned out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int off = tx[i].x - xb;                        // 0 .. 10: byte offset of s[x] inside the 12-byte window
+    // window bytes off, off+1 (off+1 may be one past the row end when x == sw-1; its coefficient is 0 then)
+    const unsigned lo = (off < 4) ? a0 : ((off < 8) ? a1 : a2), hi = (off < 4) ? a1 : ((off < 8) ? a2 : a2);
+    const unsigned lo1 = (off < 4) ? c0 : ((off < 8) ? c1 : c2), hi1 = (off < 4) ? c1 : ((off < 8) ? c2 : c2);
+    const unsigned sel = (unsigned)(off & 3) | ((unsigned)((off & 3) + 1) << 4);
+    const unsigned p0 = __byte_perm(lo, hi, sel), p1 = __byte_perm(lo1, hi1, sel);   // bytes 0,1 = s[x], s[x+1]
+    const int h0 = (int)__dp2a_lo((unsigned)tx[i].y, p0, 0u);   // a0*s[x] + a1*s[x+1]
+    const int h1 = (int)__dp2a_lo((unsigned)tx[i].y, p1, 0u);
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    out |= (unsigned)(v & 0xff) << (8 * i);
+  }
+  *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2  per-cell FAST-9/16 + strict 3x3 NMS with the ini/min threshold fallback
 //     (cv::FAST TYPE_9_16 nonmax=true; call sites :818,:823; cell loop :798-838).
@@ -772,32 +815,44 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
   }
 }
 
-// Border column groups of every row of every level (the group at x0 = 0 and the last one or two groups): one thread
-// per (row, group), full 7x7 through BORDER_REFLECT_101.  ~3 % of the pixels.
-struct BlurEdge { short level, x0; int row_begin; };   // rows of this (level, group) start at linear index row_begin
+// Border column groups of every level (the group at x0 = 0 and the last one or two groups): same register-ring walk
+// as k_blur7_strip with the horizontal pass fetched through BORDER_REFLECT_101; one thread per (group, 35-row strip).
+// ~3 % of the pixels.
+struct BlurEdge { short level, x0, y0, pad; };
 
-__global__ void __launch_bounds__(128) k_blur7_edges(PyrView src, PyrView dstv, const BlurEdge* __restrict__ edges,
-                                                     int nedges, int total_rows) {
+__global__ void __launch_bounds__(64) k_blur7_edges(PyrView src, PyrView dstv, const BlurEdge* __restrict__ edges, int nedges) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total_rows) return;
-  int e = 0;
-  while (e + 1 < nedges && edges[e + 1].row_begin <= i) ++e;   // nedges <= 3 * nlevels
-  const int l = edges[e].level, x0 = edges[e].x0, y = i - edges[e].row_begin;
-  const int w = src.w[l], h = src.h[l], spitch = src.pitch[l];
+  if (i >= nedges) return;
+  const BlurEdge e = edges[i];
+  const int l = e.level, x0 = e.x0, w = src.w[l], h = src.h[l], spitch = src.pitch[l], dpitch = dstv.pitch[l];
   const uint8_t* s = src.p[l] + (size_t)blockIdx.y * src.fstride[l];
   uint8_t* d = dstv.p[l] + (size_t)blockIdx.y * dstv.fstride[l];
-  unsigned acc[4] = {0, 0, 0, 0};
-  const unsigned q[7] = {18, 34, 48, 56, 48, 34, 18};
+  const int y0 = e.y0, y1 = min(h, y0 + BLS_ROWS);
+  unsigned ring[7][4];
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const HRow r = blur_hrow_border(s + (size_t)reflect101(y - 3 + j, h) * spitch, x0, w);
-    acc[0] += q[j] * (r.h02 & 0xffffu); acc[2] += q[j] * (r.h02 >> 16);
-    acc[1] += q[j] * (r.h13 & 0xffffu); acc[3] += q[j] * (r.h13 >> 16);
+  for (int j = 0; j < 6; ++j) {
+    const HRow r = blur_hrow_border(s + (size_t)reflect101(y0 - 3 + j, h) * spitch, x0, w);
+    ring[j][0] = r.h02 & 0xffffu; ring[j][2] = r.h02 >> 16; ring[j][1] = r.h13 & 0xffffu; ring[j][3] = r.h13 >> 16;
   }
-  unsigned out = 0;
+  for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
-  for (int k = 0; k < 4; ++k) out |= ((acc[k] + 32768u) >> 16) << (8 * k);
-  *reinterpret_cast<unsigned*>(d + (size_t)y * dstv.pitch[l] + x0) = out;
+    for (int k = 0; k < 7; ++k) {
+      const int y = yb + k;
+      if (y < y1) {
+        const HRow r = blur_hrow_border(s + (size_t)reflect101(y + 3, h) * spitch, x0, w);
+        ring[(k + 6) % 7][0] = r.h02 & 0xffffu; ring[(k + 6) % 7][2] = r.h02 >> 16;
+        ring[(k + 6) % 7][1] = r.h13 & 0xffffu; ring[(k + 6) % 7][3] = r.h13 >> 16;
+        unsigned out = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned v = 18u * (ring[k % 7][q] + ring[(k + 6) % 7][q]) + 34u * (ring[(k + 1) % 7][q] + ring[(k + 5) % 7][q]) +
+                             48u * (ring[(k + 2) % 7][q] + ring[(k + 4) % 7][q]) + 56u * ring[(k + 3) % 7][q];
+          out |= ((v + 32768u) >> 16) << (8 * q);
+        }
+        *reinterpret_cast<unsigned*>(d + (size_t)y * dpitch + x0) = out;
+      }
+    }
+  }
 }
 
 // bordered level read-back for orbx_get_level (copyMakeBorder BORDER_REFLECT_101, :1136-1142)

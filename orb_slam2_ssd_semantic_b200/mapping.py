@@ -50,6 +50,13 @@ class PointCloudMapping:
                                                       float(fx), float(fy), float(cx), float(cy),
                                                       C.c_void_p(d_label) if d_label else None))
 
+    def insert_keyframes_device(self, d_depth: int, d_rgb: int, rows: int, cols: int, frame_idx, Tcw, fx, fy, cx, cy):
+        """Keyframes frame_idx (order = insertion order) of an RGB-D batch resident in HBM; one enqueue."""
+        idx = np.ascontiguousarray(frame_idx, np.int32)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(len(idx), 16)
+        _lib.check(self._L.ocm_insert_keyframes_device(self._h, C.c_void_p(d_depth), C.c_void_p(d_rgb), rows, cols, ptr(idx),
+                                                       len(idx), ptr(T), float(fx), float(fy), float(cx), float(cy)))
+
     def last_points(self):
         n = C.c_int(0)
         _lib.check(self._L.ocm_last_points(self._h, None, None, 0, C.byref(n)))
