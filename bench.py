@@ -249,19 +249,30 @@ def run_b200(args):
     ms_total = float(tms.item())
     value = world * F * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers (pinned) through the reference-facing call ----
+    # ---- e2e: host buffers (pinned) through the reference-facing calls ----
+    # What the host hands over per step is what the reference's callers hold: gray u8 + the sensor's CV_16U depth +
+    # poses for every frame (Tracking::GrabImageRGBD converts the depth itself, src/Tracking.cc:366-367) and the
+    # colour image of every keyframe (Tracking::CreateNewKeyFrame -> insertKeyFrame, src/Tracking.cc:1889).  The
+    # keyframe depth is NOT uploaded twice: the mapper reads the tracker's converted device copy.
+    depth_u16 = np.rint(depth.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)
+    assert (depth_u16.astype(np.float32) * np.float32(1.0 / synth.DEPTH_FACTOR) == depth).all()
     p_gray = torch.from_numpy(gray).pin_memory()
-    p_depth = torch.from_numpy(depth).pin_memory()
+    p_d16 = torch.from_numpy(depth_u16).pin_memory()
     p_T = torch.from_numpy(T).pin_memory()
-    st_gray, st_depth, st_T = p_gray.numpy(), p_depth.numpy(), p_T.numpy()
-    p_rgb = torch.from_numpy(rgb).pin_memory()
-    st_rgb = p_rgb.numpy()
+    p_rgbk = torch.from_numpy(np.ascontiguousarray(rgb[kfs])).pin_memory()
+    d_rgbk = torch.empty_like(p_rgbk, device=dev)
+    st_gray, st_d16, st_T = p_gray.numpy(), p_d16.numpy(), p_T.numpy()
     outs = st.alloc_outputs(F, pinned=True)
+    factor = np.float32(1.0 / synth.DEPTH_FACTOR)
 
     def step_host():
-        o = st.track_batch(st_gray, st_depth, st_T, out=outs)
-        for t in kfs:
-            pcm.insertKeyFrame(st_T[t], st_depth[t], st_rgb[t], synth.FX, synth.FY, synth.CX, synth.CY)
+        o = st.track_batch_u16(st_gray, st_d16, factor, st_T, out=outs)          # H2D gray + u16 depth, D2H results
+        with torch.cuda.stream(ext_map):
+            d_rgbk.copy_(p_rgbk, non_blocking=True)                               # H2D keyframe colour images
+        _, d_dep = st.device_inputs()
+        pcm.insert_keyframes_device(d_dep, d_rgbk.data_ptr(), ROWS, COLS, kfs, T[kfs], synth.FX, synth.FY, synth.CX,
+                                    synth.CY, rgb_idx=list(range(len(kfs))))
+        pcm.sync()
         return o
 
     for _ in range(2):
@@ -271,7 +282,6 @@ def run_b200(args):
     e2e_steps = max(3, args.steps // 2)
     for _ in range(e2e_steps):
         out = step_host()
-    pcm.sync()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
@@ -279,7 +289,7 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F * e2e_steps / float(te.item())
     kps, desc, nkp, c2l, nm = out
-    h2d = gray.nbytes + depth.nbytes + T.nbytes + len(kfs) * (npx * 7)   # + depth & rgb of the keyframes
+    h2d = gray.nbytes + depth_u16.nbytes + T.nbytes + p_rgbk.numel()   # gray + u16 depth + poses + keyframe colour
     d2h = kps.nbytes + desc.nbytes + nkp.nbytes + c2l.nbytes + nm.nbytes
     n_kp = float(nkp.mean())
     n_match = float(nm[1:].mean())

@@ -234,6 +234,15 @@ void orbs_destroy(orbs_t* h);
 int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const float* Tcw, int nframes,
                      int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp, int32_t* cur2last,
                      int32_t* nmatch, int cap);
+/* Same with the depth image as the sensor delivers it (CV_16U, e.g. TUM PNGs): the conversion
+ * imDepth.convertTo(CV_32F, mDepthMapFactor) of Tracking::GrabImageRGBD (src/Tracking.cc:366-367; float multiply by
+ * depth_factor = 1.0f / DepthMapFactor) runs on the device, halving the host->device traffic of the depth stream. */
+int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u16, float depth_factor, const float* Tcw,
+                         int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp,
+                         int32_t* cur2last, int32_t* nmatch, int cap);
+/* Device copies of the inputs of the last host-buffer call (gray u8, depth f32 metres), e.g. to hand keyframes to
+ * ocm_insert_keyframes_device without a second upload. */
+int orbs_device_inputs(orbs_t* h, const uint8_t** d_gray, const float** d_depth);
 /* Device-resident entry (inputs already in HBM, results left in HBM; asynchronous on orbs_stream). */
 int orbs_track_batch_device(orbs_t* h, const uint8_t* d_gray, const float* d_depth, const float* d_Tcw,
                             int nframes, int rows, int cols);
@@ -272,11 +281,12 @@ int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_
                                const uint8_t* d_ground_label);
 /* Batched variant for a resident RGB-D stream: inserts keyframes frame_idx[0..n) (in that order) of a batch laid out
  * as depth[F][rows][cols] f32, rgb[F][rows][cols][3] u8 in HBM, Tcw[n][16] on the host (one pose per inserted
- * keyframe).  One call enqueues everything on the handle's stream (what UpdateOctomap's loop does,
+ * keyframe); keyframe i reads depth image depth_idx[i] and colour image rgb_idx[i] of the two batches.  One call
+ * enqueues everything on the handle's stream (what UpdateOctomap's loop does,
  * perfect/src/MapDrawer.cc:610-638). */
 int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
-                                const int32_t* frame_idx, int n, const float* Tcw, float fx, float fy, float cx,
-                                float cy);
+                                const int32_t* depth_idx, const int32_t* rgb_idx /* NULL = depth_idx */, int n,
+                                const float* Tcw, float fx, float fy, float cx, float cy);
 /* World-frame points of the LAST inserted keyframe after gating + leaf filter + transform (xyz f32 x n,
  * unordered: compare as sets). */
 int ocm_last_points(ocm_t* h, float* xyz, uint8_t* rgb, int cap, int* n);

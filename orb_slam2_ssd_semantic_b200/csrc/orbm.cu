@@ -51,13 +51,14 @@ int launch_match_last_unfused(const CurView& cv_in, const LastView& lv, const Ma
 int launch_match_last(const CurView& cv_in, const LastView& lv, const MatchCam& cam, int npairs, int* d_goff, int* d_gidx,
                       unsigned* d_list, int* d_count, int* d_accepted, int* d_cur2last, int* d_nmatch, int cmax,
                       int lmax, cudaStream_t stream, long long* launches) {
-  const size_t smem = mf_smem_bytes(cmax);
+  const int lmax16 = align_up(lmax, 16);
+  const size_t smem = mf_smem_bytes(cmax, lmax16);
   if (smem > 200 * 1024)   // frame too large to stage in shared memory: separate grid / candidate / resolve kernels
     return launch_match_last_unfused(cv_in, lv, cam, npairs, d_goff, d_gidx, d_list, d_count, d_accepted, d_cur2last,
                                      d_nmatch, cmax, lmax, stream, launches);
   B200_CUDA(cudaFuncSetAttribute(k_match_last_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ListView lsv{d_list, d_count};
-  k_match_last_fused<<<npairs, MF_THREADS, smem, stream>>>(cv_in, lv, cam, lsv, d_accepted, d_cur2last, d_nmatch, cmax);
+  k_match_last_fused<<<npairs, MF_THREADS, smem, stream>>>(cv_in, lv, cam, lsv, d_accepted, d_cur2last, d_nmatch, cmax, lmax16);
   if (launches) *launches += 1;
   B200_CUDA(cudaGetLastError());
   return B200ORB_OK;

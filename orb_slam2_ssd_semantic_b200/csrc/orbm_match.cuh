@@ -317,12 +317,14 @@ __global__ void __launch_bounds__(32) k_resolve_last(CurView cv, LastView lv, Ma
 constexpr int MF_THREADS = 512;
 constexpr int MF_QC = 16;   // queries per resolve chunk
 
-__host__ __device__ inline size_t mf_smem_bytes(int cmax) {
-  return (size_t)(GRID_CELLS + 1) * 4 + (size_t)GRID_CELLS * 4 + (size_t)cmax * (4 + 4 + 4 + 4 + 4 + 32 + 4 + 1) + 64;
+__host__ __device__ inline size_t mf_smem_bytes(int cmax, int lmax) {
+  return (size_t)(GRID_CELLS + 1) * 4 + (size_t)GRID_CELLS * 4 + (size_t)cmax * (4 + 4 + 4 + 4 + 4 + 32 + 4 + 1) +
+         (size_t)lmax * 20 + 64;
 }
 
 __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, LastView lv, MatchCam cam, ListView lists,
-                                                                 int* accepted, int* cur2last, int* nmatch, int cmax) {
+                                                                 int* accepted, int* cur2last, int* nmatch, int cmax,
+                                                                 int lmax) {
   extern __shared__ __align__(16) unsigned char fsm[];
   __shared__ int ws[33];
   __shared__ int s_hist[ORBM_HISTO_LENGTH];
@@ -342,6 +344,11 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   float* s_ur = reinterpret_cast<float*>(q); q += (size_t)cmax * 4;
   int* s_oct = reinterpret_cast<int*>(q); q += (size_t)cmax * 4;
   int* state = reinterpret_cast<int*>(q); q += (size_t)cmax * 4;
+  float* q_u = reinterpret_cast<float*>(q); q += (size_t)lmax * 4;      // per-query window geometry (phase B1)
+  float* q_v = reinterpret_cast<float*>(q); q += (size_t)lmax * 4;
+  float* q_r = reinterpret_cast<float*>(q); q += (size_t)lmax * 4;
+  float* q_ur = reinterpret_cast<float*>(q); q += (size_t)lmax * 4;
+  int* q_lv = reinterpret_cast<int*>(q); q += (size_t)lmax * 4;         // (min_level + 1) | (max_level + 1) << 8 | ok << 16
   uint8_t* taken = q;
   const int* cobs = cv.obs ? cv.obs + co : nullptr;
 
@@ -406,21 +413,41 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   const float* Tc = cv.Tcw + (size_t)p * 16;
   unsigned* L = lists.list + lo * LCAP;
   int* C = lists.count + lo;
-  // ---- K8 candidates: warps stride over the queries -------------------------------------------------------------------
-  for (int i = warp; i < nl; i += nwarp) {
-    int cnt = 0;
+  // ---- K8a: projection + window of every query, one THREAD per query (scalar double-precision chain off the
+  //      warp-serial path) -----------------------------------------------------------------------------------------
+  for (int i = tid; i < nl; i += nthr) {
+    int packed = 0;
     if (lv.valid[lo + i]) {
       QueryGeom qg;
       if (setup_last_query(cam, Tc, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], qg)) {
-        const uint8_t* d = lv.desc + (lo + i) * 32;
-        const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+        q_u[i] = qg.u; q_v[i] = qg.v; q_r[i] = qg.r; q_ur[i] = qg.ur;
+        packed = ((qg.min_level + 1) & 0xff) | (((qg.max_level + 1) & 0xff) << 8) | (1 << 16);
+      }
+    }
+    q_lv[i] = packed;
+  }
+  __syncthreads();
+  // ---- K8b candidates: warps stride over the queries; the next query's descriptor is fetched one iteration ahead --
+  {
+    const uint4* dbase = reinterpret_cast<const uint4*>(lv.desc + lo * 32);
+    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
+    if (warp < nl) { n0 = __ldg(dbase + 2 * (size_t)warp); n1 = __ldg(dbase + 2 * (size_t)warp + 1); }
+    for (int i = warp; i < nl; i += nwarp) {
+      const uint4 d0 = n0, d1 = n1;
+      if (i + nwarp < nl) { n0 = __ldg(dbase + 2 * (size_t)(i + nwarp)); n1 = __ldg(dbase + 2 * (size_t)(i + nwarp) + 1); }
+      int cnt = 0;
+      const int packed = q_lv[i];
+      if (packed >> 16) {
+        QueryGeom qg;
+        qg.u = q_u[i]; qg.v = q_v[i]; qg.r = q_r[i]; qg.rr = qg.r; qg.ur = q_ur[i];
+        qg.min_level = (packed & 0xff) - 1; qg.max_level = ((packed >> 8) & 0xff) - 1;
         unsigned* list = L + (size_t)i * LCAP;
         cnt = warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
           if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
         });
       }
+      if (lane == 0) C[i] = (cnt > LCAP) ? -cnt : cnt;
     }
-    if (lane == 0) C[i] = (cnt > LCAP) ? -cnt : cnt;
   }
   __syncthreads();   // lists are read back by this CTA only: block-level visibility is enough
   // ---- K9 ordered resolve through a double-buffered ring --------------------------------------------------------------

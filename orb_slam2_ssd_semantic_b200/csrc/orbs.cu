@@ -51,6 +51,15 @@ __global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restri
   o.uright[g] = ur; o.depth[g] = dd; o.valid[g] = ok;
 }
 
+// imDepth.convertTo(CV_32F, mDepthMapFactor) (src/Tracking.cc:366-367): float(u16) * factor, 4 pixels per thread
+__global__ void k_depth_u16_to_f32(const ushort4* __restrict__ src, float4* __restrict__ dst, float factor, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const ushort4 v = src[i];
+  dst[i] = make_float4(__fmul_rn((float)v.x, factor), __fmul_rn((float)v.y, factor), __fmul_rn((float)v.z, factor),
+                       __fmul_rn((float)v.w, factor));
+}
+
 __global__ void k_fill_i32(int* p, int v, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -71,11 +80,13 @@ struct orbs {
   unsigned* d_list = nullptr;
   uint8_t* d_gray = nullptr;
   float *d_depth = nullptr, *d_T = nullptr;
+  uint16_t* d_depth16 = nullptr;
   bool have = false;
   void free_bufs() {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(d_x); F(d_y); F(d_ang); F(d_ur); F(d_dep); F(d_xw); F(d_oct); F(d_valid); F(d_c2l); F(d_nm); F(d_count);
-    F(d_gidx); F(d_goff); F(d_acc); F(d_list); F(d_gray); F(d_depth); F(d_T);
+    F(d_gidx); F(d_goff); F(d_acc); F(d_list); F(d_gray); F(d_depth); F(d_T); F(d_depth16);
+    d_depth16 = nullptr;
     d_x = d_y = d_ang = d_ur = d_dep = d_xw = nullptr; d_oct = nullptr; d_valid = nullptr;
     d_c2l = d_nm = d_count = d_gidx = d_goff = d_acc = nullptr; d_list = nullptr; d_gray = nullptr; d_depth = d_T = nullptr;
   }
@@ -103,6 +114,7 @@ struct orbs {
       B200_CUDA(cudaMalloc(&d_gray, (size_t)maxF * rows * cols));
       B200_CUDA(cudaMalloc(&d_depth, (size_t)maxF * rows * cols * 4));
       B200_CUDA(cudaMalloc(&d_T, (size_t)maxF * 64));
+      B200_CUDA(cudaMalloc(&d_depth16, (size_t)maxF * rows * cols * 2));
     }
     return B200ORB_OK;
   }
@@ -182,11 +194,11 @@ int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d
   return B200ORB_OK;
 }
 
-int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const float* Tcw, int nframes, int rows,
-                     int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp, int32_t* cur2last, int32_t* nmatch,
-                     int cap) {
-  if (!h || !gray || !depth || !Tcw || !kps || !desc || !nkp || !cur2last || !nmatch || nframes <= 0 || rows <= 0 ||
-      cols <= 0) {
+static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, const uint16_t* depth16, float factor,
+                            const float* Tcw, int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc,
+                            int32_t* nkp, int32_t* cur2last, int32_t* nmatch, int cap) {
+  if (!h || !gray || (!depth && !depth16) || !Tcw || !kps || !desc || !nkp || !cur2last || !nmatch || nframes <= 0 ||
+      rows <= 0 || cols <= 0) {
     set_error("bad argument");
     return B200ORB_EINVAL;
   }
@@ -196,7 +208,16 @@ int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const f
   cudaStream_t st = h->ex->stream;
   const size_t px = (size_t)rows * cols, F = nframes;
   B200_CUDA(cudaMemcpyAsync(h->d_gray, gray, px * F, cudaMemcpyHostToDevice, st));
-  B200_CUDA(cudaMemcpyAsync(h->d_depth, depth, px * F * 4, cudaMemcpyHostToDevice, st));
+  if (depth16) {
+    if ((px * F) % 4) { set_error("u16 depth path needs rows*cols*nframes to be a multiple of 4"); return B200ORB_EINVAL; }
+    B200_CUDA(cudaMemcpyAsync(h->d_depth16, depth16, px * F * 2, cudaMemcpyHostToDevice, st));
+    const size_t n4 = px * F / 4;
+    k_depth_u16_to_f32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ushort4*>(h->d_depth16),
+                                                                     reinterpret_cast<float4*>(h->d_depth), factor, n4);
+    ++h->launches;
+  } else {
+    B200_CUDA(cudaMemcpyAsync(h->d_depth, depth, px * F * 4, cudaMemcpyHostToDevice, st));
+  }
   B200_CUDA(cudaMemcpyAsync(h->d_T, Tcw, F * 64, cudaMemcpyHostToDevice, st));
   B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes));
   const size_t hc = h->cap;
@@ -213,6 +234,26 @@ int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const f
   B200_CUDA(cudaMemcpyAsync(nkp, h->ex->d_n, 4 * F, cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaMemcpyAsync(nmatch, h->d_nm, 4 * F, cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  return B200ORB_OK;
+}
+
+int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const float* Tcw, int nframes, int rows,
+                     int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp, int32_t* cur2last, int32_t* nmatch,
+                     int cap) {
+  return track_batch_host(h, gray, depth, nullptr, 0.f, Tcw, nframes, rows, cols, kps, desc, nkp, cur2last, nmatch, cap);
+}
+
+int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u16, float depth_factor, const float* Tcw,
+                         int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp,
+                         int32_t* cur2last, int32_t* nmatch, int cap) {
+  return track_batch_host(h, gray, nullptr, depth_u16, depth_factor, Tcw, nframes, rows, cols, kps, desc, nkp, cur2last,
+                          nmatch, cap);
+}
+
+int orbs_device_inputs(orbs_t* h, const uint8_t** d_gray, const float** d_depth) {
+  if (!h || !h->d_gray) { set_error("no host-buffer call yet"); return B200ORB_EINVAL; }
+  if (d_gray) *d_gray = h->d_gray;
+  if (d_depth) *d_depth = h->d_depth;
   return B200ORB_OK;
 }
 

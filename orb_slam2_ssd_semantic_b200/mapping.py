@@ -50,12 +50,16 @@ class PointCloudMapping:
                                                       float(fx), float(fy), float(cx), float(cy),
                                                       C.c_void_p(d_label) if d_label else None))
 
-    def insert_keyframes_device(self, d_depth: int, d_rgb: int, rows: int, cols: int, frame_idx, Tcw, fx, fy, cx, cy):
-        """Keyframes frame_idx (order = insertion order) of an RGB-D batch resident in HBM; one enqueue."""
+    def insert_keyframes_device(self, d_depth: int, d_rgb: int, rows: int, cols: int, frame_idx, Tcw, fx, fy, cx, cy,
+                                rgb_idx=None):
+        """Keyframes (order = insertion order) of an RGB-D batch resident in HBM; one enqueue.  Keyframe i reads depth
+        image frame_idx[i] and colour image rgb_idx[i] (default: the same index)."""
         idx = np.ascontiguousarray(frame_idx, np.int32)
+        ridx = None if rgb_idx is None else np.ascontiguousarray(rgb_idx, np.int32)
         T = np.ascontiguousarray(Tcw, np.float32).reshape(len(idx), 16)
         _lib.check(self._L.ocm_insert_keyframes_device(self._h, C.c_void_p(d_depth), C.c_void_p(d_rgb), rows, cols, ptr(idx),
-                                                       len(idx), ptr(T), float(fx), float(fy), float(cx), float(cy)))
+                                                       ptr(ridx), len(idx), ptr(T), float(fx), float(fy), float(cx),
+                                                       float(cy)))
 
     def last_points(self):
         n = C.c_int(0)

@@ -61,6 +61,24 @@ class StreamTracker:
                                             ptr(nkp), ptr(c2l), ptr(nm), cap))
         return kps, desc, nkp, c2l, nm
 
+    def track_batch_u16(self, gray: np.ndarray, depth_u16: np.ndarray, depth_factor: float, Tcw: np.ndarray, out=None):
+        """Like track_batch with the sensor's CV_16U depth; convertTo(CV_32F, depth_factor) runs on the device."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth_u16 = np.ascontiguousarray(depth_u16, np.uint16)
+        Tcw = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16)
+        F, rows, cols = gray.shape
+        assert depth_u16.shape == gray.shape and Tcw.shape[0] == F
+        kps, desc, nkp, c2l, nm = out if out is not None else self.alloc_outputs(F)
+        _lib.check(self._L.orbs_track_batch_u16(self._h, ptr(gray), ptr(depth_u16), float(np.float32(depth_factor)), ptr(Tcw),
+                                                F, rows, cols, ptr(kps), ptr(desc), ptr(nkp), ptr(c2l), ptr(nm), self.cap))
+        return kps, desc, nkp, c2l, nm
+
+    def device_inputs(self):
+        """(d_gray, d_depth) device pointers of the last host-buffer batch (depth as f32 metres)."""
+        g, d = C.c_void_p(), C.c_void_p()
+        _lib.check(self._L.orbs_device_inputs(self._h, C.byref(g), C.byref(d)))
+        return g.value, d.value
+
     def track_batch_device(self, d_gray: int, d_depth: int, d_Tcw: int, nframes: int, rows: int, cols: int):
         """Device pointers (ints) in; results stay in HBM (device_results()). Asynchronous."""
         _lib.check(self._L.orbs_track_batch_device(self._h, C.c_void_p(d_gray), C.c_void_p(d_depth), C.c_void_p(d_Tcw),

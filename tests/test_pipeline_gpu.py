@@ -36,3 +36,24 @@ def test_stream_batch_matches_oracle(oracle):
             assert nm[t] == n_ref
             assert (c2l[t, :nkp[t]] == ref).all()
         prev = (K, D)
+
+
+def test_u16_depth_path_equals_float_path():
+    """orbs_track_batch_u16 (device-side convertTo(CV_32F, 1/5000)) == orbs_track_batch on the float depth the
+    reference would have computed (src/Tracking.cc:366-367)."""
+    from orb_slam2_ssd_semantic_b200 import StreamTracker
+    F = 4
+    ws = synth.WallStream(seed=77, n=F)
+    frames = [ws.frame(t) for t in range(F)]
+    gray = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames])
+    T = np.stack([f[3] for f in frames])
+    d16 = np.rint(depth.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)
+    factor = np.float32(1.0 / synth.DEPTH_FACTOR)
+    assert (d16.astype(np.float32) * factor == depth).all()
+    st = StreamTracker(1000, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+    a = st.track_batch(gray, depth, T)
+    b = st.track_batch_u16(gray, d16, factor, T)
+    for x, y in zip(a, b):
+        assert x.tobytes() == y.tobytes()
+    assert b[4][1:].min() > 100
