@@ -260,18 +260,31 @@ def run_b200(args):
     p_d16 = torch.from_numpy(depth_u16).pin_memory()
     p_T = torch.from_numpy(T).pin_memory()
     p_rgbk = torch.from_numpy(np.ascontiguousarray(rgb[kfs])).pin_memory()
+    p_d16k = torch.from_numpy(np.ascontiguousarray(depth_u16[kfs])).pin_memory()
     d_rgbk = torch.empty_like(p_rgbk, device=dev)
+    d_d16k = torch.empty_like(p_d16k, device=dev)
+    d_depk = torch.empty(p_d16k.shape, dtype=torch.float32, device=dev)
     st_gray, st_d16, st_T = p_gray.numpy(), p_d16.numpy(), p_T.numpy()
     outs = st.alloc_outputs(F, pinned=True)
     factor = np.float32(1.0 / synth.DEPTH_FACTOR)
+    import ctypes as C
+    from orb_slam2_ssd_semantic_b200 import _lib
+    L = _lib.lib()
+    nkfpx = int(p_d16k.numel())
 
     def step_host():
-        o = st.track_batch_u16(st_gray, st_d16, factor, st_T, out=outs)          # H2D gray + u16 depth, D2H results
+        # mapper first, asynchronously on its own stream: H2D depth (CV_16U) + colour of the keyframes only, converted
+        # on the device, then the keyframe inserts -- all of it overlaps the tracker call below
         with torch.cuda.stream(ext_map):
-            d_rgbk.copy_(p_rgbk, non_blocking=True)                               # H2D keyframe colour images
-        _, d_dep = st.device_inputs()
-        pcm.insert_keyframes_device(d_dep, d_rgbk.data_ptr(), ROWS, COLS, kfs, T[kfs], synth.FX, synth.FY, synth.CX,
-                                    synth.CY, rgb_idx=list(range(len(kfs))))
+            d_d16k.copy_(p_d16k, non_blocking=True)
+            d_rgbk.copy_(p_rgbk, non_blocking=True)
+        _lib.check(L.b200orb_depth_u16_to_f32_device(C.c_void_p(d_d16k.data_ptr()), C.c_void_p(d_depk.data_ptr()), nkfpx,
+                                                     float(factor), C.c_void_p(pcm.stream())))
+        pcm.insert_keyframes_device(d_depk.data_ptr(), d_rgbk.data_ptr(), ROWS, COLS, list(range(len(kfs))), T[kfs], synth.FX,
+                                    synth.FY, synth.CX, synth.CY)
+        # tracker (synchronous call): H2D gray in chunks overlapped with extraction; the page-locked CV_16U depth is
+        # read under the keypoints in place (zero-copy gather); D2H keypoints, descriptors, matches
+        o = st.track_batch_u16(st_gray, st_d16, factor, st_T, out=outs)
         pcm.sync()
         return o
 
@@ -289,7 +302,8 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * F * e2e_steps / float(te.item())
     kps, desc, nkp, c2l, nm = out
-    h2d = gray.nbytes + depth_u16.nbytes + T.nbytes + p_rgbk.numel()   # gray + u16 depth + poses + keyframe colour
+    # gray + poses + one 32-byte PCIe sector per keypoint of the in-place depth gather + keyframe depth (u16) and colour
+    h2d = gray.nbytes + T.nbytes + int(nkp.sum()) * 32 + p_d16k.numel() * 2 + p_rgbk.numel()
     d2h = kps.nbytes + desc.nbytes + nkp.nbytes + c2l.nbytes + nm.nbytes
     n_kp = float(nkp.mean())
     n_match = float(nm[1:].mean())

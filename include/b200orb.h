@@ -240,6 +240,13 @@ int orbs_track_batch(orbs_t* h, const uint8_t* gray, const float* depth, const f
 int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u16, float depth_factor, const float* Tcw,
                          int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp,
                          int32_t* cur2last, int32_t* nmatch, int cap);
+/* When depth_u16 is page-locked host memory (cudaHostAlloc / cudaHostRegister) orbs_track_batch_u16 does not upload
+ * the depth images at all: the tracking path reads depth only under the keypoints (Frame::ComputeStereoFromRGBD,
+ * src/Frame.cc:850-871), so the device gathers those pixels in place over PCIe.  orbs_set_full_depth_upload(h, 1)
+ * forces the full upload (then orbs_device_inputs returns the converted f32 batch). */
+int orbs_set_full_depth_upload(orbs_t* h, int on);
+/* convertTo(CV_32F, factor) of n CV_16U pixels resident in HBM (n multiple of 4) on the given cudaStream_t. */
+int b200orb_depth_u16_to_f32_device(const uint16_t* d_src, float* d_dst, size_t n, float factor, void* stream);
 /* Device copies of the inputs of the last host-buffer call (gray u8, depth f32 metres), e.g. to hand keyframes to
  * ocm_insert_keyframes_device without a second upload. */
 int orbs_device_inputs(orbs_t* h, const uint8_t** d_gray, const float** d_depth);

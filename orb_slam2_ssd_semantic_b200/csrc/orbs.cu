@@ -19,16 +19,21 @@ struct GlueOut {     // SoA per frame, stride cap
 // Frame::ComputeStereoFromRGBD (src/Frame.cc:850-871) + Frame::UnprojectStereo (:879-899) for every keypoint,
 // and the AoS -> SoA split the matcher kernel reads.
 __global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restrict__ kps, const int* __restrict__ nkp,
-                                                    int cap, const float* __restrict__ depth, int rows, int cols,
-                                                    const float* __restrict__ Tcw, float fx, float fy, float cx,
-                                                    float cy, float bf, GlueOut o) {
+                                                    int cap, const float* __restrict__ depth,
+                                                    const uint16_t* __restrict__ depth16, float depth_factor, int rows,
+                                                    int cols, const float* __restrict__ Tcw, float fx, float fy,
+                                                    float cx, float cy, float bf, GlueOut o) {
   const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nkp[f]) return;
   const size_t g = (size_t)f * cap + i;
   const OrbxKeyPoint kp = kps[g];
   const float* T = Tcw + (size_t)f * 16;
   const float u = kp.x, v = kp.y;
-  const float d = depth[(size_t)f * rows * cols + (size_t)(int)v * cols + (int)u];
+  // imDepth.at<float>(v,u) (src/Frame.cc:863).  With depth16 the CV_16U sensor image is read in place -- possibly
+  // straight out of pinned host memory over PCIe, one 2-byte read per keypoint instead of uploading 0.6 MB per frame
+  // -- and converted like convertTo(CV_32F, mDepthMapFactor) does (src/Tracking.cc:366-367).
+  const size_t di = (size_t)f * rows * cols + (size_t)(int)v * cols + (int)u;
+  const float d = depth16 ? __fmul_rn((float)depth16[di], depth_factor) : depth[di];
   o.x[g] = u; o.y[g] = v; o.ang[g] = kp.angle; o.oct[g] = kp.octave;
   float ur = -1.f, dd = -1.f;
   uint8_t ok = 0;
@@ -81,6 +86,9 @@ struct orbs {
   uint8_t* d_gray = nullptr;
   float *d_depth = nullptr, *d_T = nullptr;
   uint16_t* d_depth16 = nullptr;
+  bool full_depth_valid = false, force_full_depth_upload = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have = false;
   void free_bufs() {
     auto F = [](void* p) { if (p) cudaFree(p); };
@@ -93,6 +101,8 @@ struct orbs {
   ~orbs() {
     DeviceGuard g(device);
     free_bufs();
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    for (cudaEvent_t e : chunk_ev) if (e) cudaEventDestroy(e);
     delete ex;
   }
   int ensure(int r, int c, int F, bool host_inputs) {
@@ -118,11 +128,12 @@ struct orbs {
     }
     return B200ORB_OK;
   }
-  int run(const uint8_t* dg, const float* dd, const float* dT, int F) {
+  int run(const uint8_t* dg, const float* dd, const float* dT, int F, const uint16_t* dd16 = nullptr, float factor = 0.f,
+          bool extracted = false) {
     cudaStream_t st = ex->stream;
-    B200_CHECK(ex->run(dg, cols, (size_t)rows * cols, F));
+    if (!extracted) B200_CHECK(ex->run(dg, cols, (size_t)rows * cols, F));
     GlueOut go{d_x, d_y, d_ang, d_ur, d_dep, d_xw, d_oct, d_valid};
-    k_frame_glue<<<dim3((cap + 255) / 256, F), 256, 0, st>>>(ex->d_kps, ex->d_n, cap, dd, rows, cols, dT, prm.fx, prm.fy,
+    k_frame_glue<<<dim3((cap + 255) / 256, F), 256, 0, st>>>(ex->d_kps, ex->d_n, cap, dd, dd16, factor, rows, cols, dT, prm.fx, prm.fy,
                                                             prm.cx, prm.cy, prm.bf, go);
     ++launches;
     B200_CHECK(ex->prof_mark(ST_GLUE + 1));
@@ -207,19 +218,51 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
   if (cap < h->cap) { set_error("cap %d < required %d (orbx_max_keypoints)", cap, h->cap); return B200ORB_ECAP; }
   cudaStream_t st = h->ex->stream;
   const size_t px = (size_t)rows * cols, F = nframes;
-  B200_CUDA(cudaMemcpyAsync(h->d_gray, gray, px * F, cudaMemcpyHostToDevice, st));
+  // gray images go up in chunks on a copy stream while the extractor already works on the chunks that have arrived
+  // (PCIe and SMs overlap); everything after extraction runs on the whole batch.
+  if (!h->copy_stream) {
+    B200_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : h->chunk_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int nchunk = (int)std::min<size_t>(7, (F + 63) / 64);   // 64-frame chunks keep each extractor launch wide enough
+  {
+    // the copy stream may only overwrite d_gray once the previous call's kernels are done with it
+    B200_CUDA(cudaEventRecord(h->chunk_ev[7], st));
+    B200_CUDA(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[7], 0));
+    for (int c = 0; c < nchunk; ++c) {
+      const size_t f0 = F * c / nchunk, f1 = F * (c + 1) / nchunk;
+      B200_CUDA(cudaMemcpyAsync(h->d_gray + px * f0, gray + px * f0, px * (f1 - f0), cudaMemcpyHostToDevice, h->copy_stream));
+      B200_CUDA(cudaEventRecord(h->chunk_ev[c], h->copy_stream));
+      B200_CUDA(cudaStreamWaitEvent(st, h->chunk_ev[c], 0));
+      B200_CHECK(h->ex->run(h->d_gray + px * f0, cols, px, (int)(f1 - f0), (int)f0));
+    }
+  }
+  const uint16_t* d16_sparse = nullptr;   // non-null: depth is read per keypoint from this (device-visible) u16 image
+  h->full_depth_valid = true;
   if (depth16) {
-    if ((px * F) % 4) { set_error("u16 depth path needs rows*cols*nframes to be a multiple of 4"); return B200ORB_EINVAL; }
-    B200_CUDA(cudaMemcpyAsync(h->d_depth16, depth16, px * F * 2, cudaMemcpyHostToDevice, st));
-    const size_t n4 = px * F / 4;
-    k_depth_u16_to_f32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ushort4*>(h->d_depth16),
-                                                                     reinterpret_cast<float4*>(h->d_depth), factor, n4);
-    ++h->launches;
+    // Page-locked host depth (cudaHostAlloc / cudaHostRegister, e.g. torch.pin_memory): the only depth pixels the
+    // tracking path ever reads are the ones under the keypoints (Frame::ComputeStereoFromRGBD), so they are gathered
+    // straight from host memory by the glue kernel and the 0.6 MB/frame image is never uploaded.
+    cudaPointerAttributes at;
+    void* dev_alias = nullptr;
+    if (!h->force_full_depth_upload && cudaPointerGetAttributes(&at, depth16) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        cudaHostGetDevicePointer(&dev_alias, const_cast<uint16_t*>(depth16), 0) == cudaSuccess && dev_alias) {
+      d16_sparse = reinterpret_cast<const uint16_t*>(dev_alias);
+      h->full_depth_valid = false;
+    } else {
+      cudaGetLastError();
+      if ((px * F) % 4) { set_error("u16 depth path needs rows*cols*nframes to be a multiple of 4"); return B200ORB_EINVAL; }
+      B200_CUDA(cudaMemcpyAsync(h->d_depth16, depth16, px * F * 2, cudaMemcpyHostToDevice, st));
+      const size_t n4 = px * F / 4;
+      k_depth_u16_to_f32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ushort4*>(h->d_depth16),
+                                                                       reinterpret_cast<float4*>(h->d_depth), factor, n4);
+      ++h->launches;
+    }
   } else {
     B200_CUDA(cudaMemcpyAsync(h->d_depth, depth, px * F * 4, cudaMemcpyHostToDevice, st));
   }
   B200_CUDA(cudaMemcpyAsync(h->d_T, Tcw, F * 64, cudaMemcpyHostToDevice, st));
-  B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes));
+  B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes, d16_sparse, factor, /*extracted=*/true));
   const size_t hc = h->cap;
   if ((size_t)cap == hc) {
     B200_CUDA(cudaMemcpyAsync(kps, h->ex->d_kps, sizeof(OrbxKeyPoint) * hc * F, cudaMemcpyDeviceToHost, st));
@@ -253,7 +296,24 @@ int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u
 int orbs_device_inputs(orbs_t* h, const uint8_t** d_gray, const float** d_depth) {
   if (!h || !h->d_gray) { set_error("no host-buffer call yet"); return B200ORB_EINVAL; }
   if (d_gray) *d_gray = h->d_gray;
-  if (d_depth) *d_depth = h->d_depth;
+  if (d_depth) *d_depth = h->full_depth_valid ? h->d_depth : nullptr;   // NULL after a sparse (zero-copy) depth call
+  return B200ORB_OK;
+}
+
+// 1: always upload the whole CV_16U depth batch (device copy available through orbs_device_inputs); 0 (default): read
+// the depth under the keypoints in place when the host buffer is page-locked.
+int orbs_set_full_depth_upload(orbs_t* h, int on) {
+  if (!h) return B200ORB_EINVAL;
+  h->force_full_depth_upload = on != 0;
+  return B200ORB_OK;
+}
+
+// convertTo(CV_32F, factor) of n CV_16U pixels already in HBM (n multiple of 4), on `stream` (cudaStream_t)
+int b200orb_depth_u16_to_f32_device(const uint16_t* d_src, float* d_dst, size_t n, float factor, void* stream) {
+  if (!d_src || !d_dst || (n % 4)) { set_error("bad argument (n must be a multiple of 4)"); return B200ORB_EINVAL; }
+  k_depth_u16_to_f32<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const ushort4*>(d_src), reinterpret_cast<float4*>(d_dst), factor, n / 4);
+  B200_CUDA(cudaGetLastError());
   return B200ORB_OK;
 }
 

@@ -300,11 +300,30 @@ int orbx::ensure_geometry(int r, int c, int F) {
 }
 
 // Enqueue the whole extractor for F frames whose level 0 is (d_l0, pitch0, fstride0) on `stream`.
-int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
+// Enqueue the whole extractor for frames [f0, f0+F) of the batch; d_l0 = level 0 of frame f0.  Ranges of one batch may be
+// enqueued one after another (the host path uploads and extracts in chunks so that PCIe and the SMs overlap).
+int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
   const int nl = prm.nlevels;
+  // frame-range views: every per-frame array is addressed as base + frame * stride inside the kernels
+  PyrView rawv = this->rawv, blurv = this->blurv;
+  for (int l = 1; l < nl; ++l) rawv.p[l] += (size_t)f0 * rawv.fstride[l];
+  for (int l = 0; l < nl; ++l) blurv.p[l] += (size_t)f0 * blurv.fstride[l];
   rawv.p[0] = const_cast<uint8_t*>(d_l0);
   rawv.pitch[0] = pitch0;
   rawv.fstride[0] = fstride0;
+  if (f0 == 0) {   // what orbx_get_level reads back
+    this->rawv.p[0] = const_cast<uint8_t*>(d_l0); this->rawv.pitch[0] = pitch0; this->rawv.fstride[0] = fstride0;
+  }
+  unsigned* d_cand = this->d_cand + (size_t)f0 * slots_per_frame;
+  int* d_cellcnt = this->d_cellcnt + (size_t)f0 * ncells;
+  unsigned* d_qkp = this->d_qkp + (size_t)f0 * slots_per_frame;
+  int* d_qnode = this->d_qnode + (size_t)f0 * slots_per_frame;
+  unsigned* d_sel = this->d_sel + (size_t)f0 * sel_per_frame;
+  int* d_selcnt = this->d_selcnt + (size_t)f0 * nl;
+  int* d_candcnt = this->d_candcnt + (size_t)f0 * nl;
+  OrbxKeyPoint* d_kps = this->d_kps + (size_t)f0 * cap;
+  uint8_t* d_desc = this->d_desc + (size_t)f0 * cap * 32;
+  int* d_n = this->d_n + f0;
   B200_CHECK(prof_begin(F));
   // K1 pyramid
   for (int l = 1; l < nl; ++l) {
@@ -373,7 +392,7 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F) {
   ++launches;
   B200_CHECK(prof_mark(ST_ORIENT_DESC + 1));
   B200_CUDA(cudaGetLastError());
-  lastF = F;
+  lastF = f0 + F;
   have_results = true;
   return B200ORB_OK;
 }

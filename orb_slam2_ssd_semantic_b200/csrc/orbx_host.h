@@ -66,7 +66,7 @@ struct orbx {
   int init(const OrbxParams& p, int dev);
   void free_geometry();
   int ensure_geometry(int r, int c, int F);
-  int run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F);
+  int run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0 = 0);
   int ensure_stage(size_t bytes);
   int ensure_tmp(size_t bytes);
   int prof_mark(int boundary);   // record event `boundary` of the current run (no-op unless profiling)

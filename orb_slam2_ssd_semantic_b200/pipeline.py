@@ -73,6 +73,10 @@ class StreamTracker:
                                                 F, rows, cols, ptr(kps), ptr(desc), ptr(nkp), ptr(c2l), ptr(nm), self.cap))
         return kps, desc, nkp, c2l, nm
 
+    def set_full_depth_upload(self, on: bool):
+        """False (default): page-locked CV_16U depth is read under the keypoints in place; True: always upload it."""
+        _lib.check(self._L.orbs_set_full_depth_upload(self._h, int(on)))
+
     def device_inputs(self):
         """(d_gray, d_depth) device pointers of the last host-buffer batch (depth as f32 metres)."""
         g, d = C.c_void_p(), C.c_void_p()
