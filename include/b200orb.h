@@ -210,6 +210,11 @@ typedef struct {
 } OrbmBow;
 int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori,
                        int32_t* f2kf /* f->n, -1 = none */, int* nmatches);
+/* ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12) (src/ORBmatcher.cc:665-812,
+ * loop closing): both sides carry `valid` (MapPoint non-NULL && !isBad()); matches12[kf1->n] = index of the pKF2
+ * keypoint whose MapPoint lands in vpMatches12[i], or -1. */
+int orbm_search_by_bow_kf(orbm_t* h, const OrbmBow* kf1, const OrbmBow* kf2, float nnratio, int check_ori,
+                          int32_t* matches12, int* nmatches);
 
 /* ------------------------------------------------------------------------------------------------
  * Stream pipeline (batched many-frame mode of north_star): per frame t of a batch, what

@@ -336,6 +336,57 @@ int match_ref_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_
   return 0;
 }
 
+// SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, vector<MapPoint*>& vpMatches12), src/ORBmatcher.cc:665-812
+int match_ref_bow_kf(const OrbmBow* k1, const OrbmBow* k2, float nnratio, int check_ori, int32_t* matches12,
+                     int* nmatches_out) {
+  std::vector<int> m12(k1->n, -1);
+  std::vector<char> matched2(k2->n, 0);
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int a = 0, b = 0;
+  while (a < k1->n_nodes && b < k2->n_nodes) {
+    if (k1->node_ids[a] == k2->node_ids[b]) {
+      for (int i1 = k1->node_off[a]; i1 < k1->node_off[a + 1]; ++i1) {
+        const unsigned idx1 = k1->idx[i1];
+        if (k1->valid && !k1->valid[idx1]) continue;
+        const uint8_t* d1 = k1->desc + 32 * (size_t)idx1;
+        int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+        for (int i2 = k2->node_off[b]; i2 < k2->node_off[b + 1]; ++i2) {
+          const unsigned idx2 = k2->idx[i2];
+          if (matched2[idx2] || (k2->valid && !k2->valid[idx2])) continue;
+          const int dist = desc_dist(d1, k2->desc + 32 * (size_t)idx2);
+          if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = (int)idx2; }
+          else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestDist1 < TH_LOW) {
+          if (static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+            m12[idx1] = bestIdx2;
+            matched2[bestIdx2] = 1;
+            if (check_ori) rotHist[rot_bin(k1->angle[idx1], k2->angle[bestIdx2])].push_back((int)idx1);
+            nmatches++;
+          }
+        }
+      }
+      ++a; ++b;
+    } else if (k1->node_ids[a] < k2->node_ids[b]) {
+      a = (int)(std::lower_bound(k1->node_ids, k1->node_ids + k1->n_nodes, k2->node_ids[b]) - k1->node_ids);
+    } else {
+      b = (int)(std::lower_bound(k2->node_ids, k2->node_ids + k2->n_nodes, k1->node_ids[a]) - k2->node_ids);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rotHist[i]) { m12[idx] = -1; nmatches--; }
+    }
+  }
+  for (int j = 0; j < k1->n; ++j) matches12[j] = m12[j];
+  *nmatches_out = nmatches;
+  return 0;
+}
+
 // Frame::ComputeStereoFromRGBD (src/Frame.cc:850-871) + Frame::UnprojectStereo (:879-899) for every keypoint.
 // kps: n x (x,y) pairs with stride `kp_stride` floats (OrbxKeyPoint = 7). depth: rows x cols f32.
 // Outputs: uright[n], depth_out[n] (-1 where d<=0), xw[n*3] (untouched where d<=0), valid[n].

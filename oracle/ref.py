@@ -210,6 +210,18 @@ def search_by_bow(kf, f, nnratio=0.7, check_ori=True):
     return nm.value, out
 
 
+def search_by_bow_kf(kf1, kf2, nnratio=0.75, check_ori=True):
+    from orb_slam2_ssd_semantic_b200 import _abi
+    L = _mlib()
+    L.match_ref_bow_kf.argtypes = [C.POINTER(_abi.OrbmBow), C.POINTER(_abi.OrbmBow), C.c_float, C.c_int, C.c_void_p,
+                                   C.POINTER(C.c_int)]
+    out = np.full(kf1.n, -1, np.int32)
+    nm = C.c_int(0)
+    a, b = kf1.struct(), kf2.struct()
+    L.match_ref_bow_kf(C.byref(a), C.byref(b), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+    return nm.value, out
+
+
 def stereo_unproject(kps, depth, Tcw, fx, fy, cx, cy, bf):
     """ComputeStereoFromRGBD + UnprojectStereo for every keypoint -> uright, depth, xw, valid."""
     n = len(kps)

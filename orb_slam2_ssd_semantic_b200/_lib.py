@@ -27,7 +27,7 @@ EXPORTS = [
     "orbx_get_level", "orbx_scale_tables", "orbx_candidates_per_level", "orbx_launch_count",
     "orbx_profile_enable", "orbx_profile_read",
     "orbm_hamming", "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_search_by_projection_last",
-    "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_projected",
+    "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_by_bow_kf", "orbm_search_projected",
     "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_u16", "orbs_device_inputs", "orbs_set_full_depth_upload", "b200orb_depth_u16_to_f32_device", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
     "orbs_stream", "orbs_launch_count", "orbs_extractor",
     "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device", "ocm_insert_keyframes_device",
@@ -84,6 +84,7 @@ def lib() -> C.CDLL:
                                                    C.c_float, vp, C.POINTER(i)]
     L.orbm_search_projected.argtypes = [vp, C.POINTER(OrbmFrame), C.POINTER(OrbmQueries), i, i, i, vp, C.POINTER(i)]
     L.orbm_search_by_bow.argtypes = [vp, C.POINTER(OrbmBow), C.POINTER(OrbmBow), C.c_float, i, vp, C.POINTER(i)]
+    L.orbm_search_by_bow_kf.argtypes = [vp, C.POINTER(OrbmBow), C.POINTER(OrbmBow), C.c_float, i, vp, C.POINTER(i)]
     L.orbs_create.argtypes = [C.POINTER(OrbsParams), i, C.POINTER(vp)]
     L.orbs_destroy.argtypes = [vp]
     L.orbs_destroy.restype = None

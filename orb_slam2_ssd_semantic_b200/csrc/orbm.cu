@@ -302,12 +302,13 @@ int orbm_search_projected(orbm_t* h, const OrbmFrame* cur, const OrbmQueries* q,
   return B200ORB_OK;
 }
 
-int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
-                       int* nmatches) {
+static int bow_impl(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int kfkf, int32_t* f2kf,
+                    int* nmatches) {
   if (!h || !kf || !f || !f2kf || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
   if (kf->n < 0 || f->n < 0 || kf->n_nodes < 0 || f->n_nodes < 0 || f->n >= (1 << 20)) { set_error("bad counts"); return B200ORB_EINVAL; }
   *nmatches = 0;
-  for (int j = 0; j < f->n; ++j) f2kf[j] = -1;
+  const int nout = kfkf ? kf->n : f->n;
+  for (int j = 0; j < nout; ++j) f2kf[j] = -1;
   if (kf->n == 0 || f->n == 0 || kf->n_nodes == 0 || f->n_nodes == 0) return B200ORB_OK;
   // merge-join of the two FeatureVectors (:242-335): equal node ids pair up; queries in the reference's visiting order
   std::vector<int> q_kf, q_beg, q_end;
@@ -335,7 +336,7 @@ int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnr
   for (size_t i = 0; i < nfi; ++i)
     if (f->idx[i] >= (uint32_t)f->n) { set_error("F index out of range"); return B200ORB_EINVAL; }
   DeviceGuard g(h->device);
-  const size_t need = nq * (12 + 4 * LCAP + 8) + nfi * 4 + (size_t)kf->n * 36 + (size_t)f->n * (36 + 4) + 64 * 256 + 4096;
+  const size_t need = nq * (12 + 4 * LCAP + 8) + nfi * 4 + (size_t)kf->n * (36 + 4) + (size_t)f->n * (36 + 4 + 1) + 64 * 256 + 4096;
   B200_CHECK(h->reserve(need));
   Carver cm(h->d_arena);
   int* d_qkf = cm.take<int>(nq); int* d_qb = cm.take<int>(nq); int* d_qe = cm.take<int>(nq);
@@ -343,23 +344,35 @@ int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnr
   uint8_t* d_kd = cm.take<uint8_t>((size_t)kf->n * 32); uint8_t* d_fd = cm.take<uint8_t>((size_t)f->n * 32);
   float* d_ka = cm.take<float>(kf->n); float* d_fa = cm.take<float>(f->n);
   unsigned* d_list = cm.take<unsigned>(nq * LCAP); int* d_count = cm.take<int>(nq); int* d_acc = cm.take<int>(nq);
-  int* d_out = cm.take<int>(f->n); int* d_nm = cm.take<int>(1);
+  int* d_out = cm.take<int>(nout); int* d_nm = cm.take<int>(1);
+  uint8_t* d_fvalid = (kfkf && f->valid) ? cm.take<uint8_t>(f->n) : nullptr;
+  if (d_fvalid) UP(d_fvalid, f->valid, f->n, uint8_t);
   UP(d_qkf, q_kf.data(), nq, int); UP(d_qb, q_beg.data(), nq, int); UP(d_qe, q_end.data(), nq, int);
   UP(d_fidx, f->idx, nfi, unsigned); UP(d_kd, kf->desc, (size_t)kf->n * 32, uint8_t); UP(d_fd, f->desc, (size_t)f->n * 32, uint8_t);
   UP(d_ka, kf->angle, kf->n, float); UP(d_fa, f->angle, f->n, float);
-  BowQueries bq{d_qkf, d_qb, d_qe, d_fidx, d_kd, d_fd, d_ka, d_fa, (int)nq, f->n};
+  BowQueries bq{d_qkf, d_qb, d_qe, d_fidx, d_kd, d_fd, d_ka, d_fa, d_fvalid, (int)nq, f->n, kf->n};
   ListView lsv{d_list, d_count};
   k_cand_bow<<<((int)nq + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, h->stream>>>(bq, lsv);
   size_t smem;
-  const int cmax = align_up(f->n, 16);
+  const int cmax = align_up(std::max(f->n, kf->n), 16);
   B200_CHECK(resolve_smem(cmax, &smem, (const void*)k_resolve_bow));
-  k_resolve_bow<<<1, 32, smem, h->stream>>>(bq, nnratio, check_ori, lsv, d_acc, d_out, d_nm, cmax);
+  k_resolve_bow<<<1, 32, smem, h->stream>>>(bq, nnratio, check_ori, kfkf, lsv, d_acc, d_out, d_nm, cmax);
   h->launches += 2;
   B200_CUDA(cudaGetLastError());
-  B200_CUDA(cudaMemcpyAsync(f2kf, d_out, sizeof(int) * (size_t)f->n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(f2kf, d_out, sizeof(int) * (size_t)nout, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return B200ORB_OK;
+}
+
+int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
+                       int* nmatches) {
+  return bow_impl(h, kf, f, nnratio, check_ori, 0, f2kf, nmatches);
+}
+
+int orbm_search_by_bow_kf(orbm_t* h, const OrbmBow* kf1, const OrbmBow* kf2, float nnratio, int check_ori,
+                          int32_t* matches12, int* nmatches) {
+  return bow_impl(h, kf1, kf2, nnratio, check_ori, 1, matches12, nmatches);
 }
 
 }  // extern "C"

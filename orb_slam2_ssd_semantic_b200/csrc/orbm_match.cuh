@@ -156,7 +156,8 @@ struct BowQueries {
   const uint8_t* kf_desc;
   const uint8_t* f_desc;
   const float *kf_ang, *f_ang;
-  int nq, nf;
+  const uint8_t* f_valid;  // nullable: side-2 entries that may be matched at all (KF-KF overload: MapPoint non-NULL && !isBad())
+  int nq, nf, nkf;
 };
 
 __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_bow(BowQueries bq, ListView out) {
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_bow(BowQueries bq, Lis
   unsigned* list = out.list + (size_t)q * LCAP;
   for (int e = lane; e < n && e < LCAP; e += 32) {
     const unsigned idx = bq.f_idx[b + e];
-    list[e] = ((unsigned)hamming256(d0, d1, bq.f_desc + (size_t)idx * 32) << 20) | idx;
+    list[e] = (bq.f_valid && !bq.f_valid[idx]) ? KEY_INF
+                                                : (((unsigned)hamming256(d0, d1, bq.f_desc + (size_t)idx * 32) << 20) | idx);
   }
   if (lane == 0) out.count[q] = (n > LCAP) ? -n : n;
 }
@@ -182,8 +184,8 @@ struct Pick { int idx, dist, ord; };
 // entries e = lane and lane+32 held in registers (v0, v1); `skip` = ord to ignore (second-best pass) or -1
 __device__ __forceinline__ Pick pick_min(unsigned v0, unsigned v1, int n, const uint8_t* taken, int skip, int lane) {
   unsigned k0 = KEY_INF, k1 = KEY_INF;
-  if (lane < n && lane != skip && !taken[v0 & 0xfffffu]) k0 = ((v0 >> 20) << 6) | (unsigned)lane;
-  if (lane + 32 < n && lane + 32 != skip && !taken[v1 & 0xfffffu]) k1 = ((v1 >> 20) << 6) | (unsigned)(lane + 32);
+  if (lane < n && lane != skip && v0 != KEY_INF && !taken[v0 & 0xfffffu]) k0 = ((v0 >> 20) << 6) | (unsigned)lane;
+  if (lane + 32 < n && lane + 32 != skip && v1 != KEY_INF && !taken[v1 & 0xfffffu]) k1 = ((v1 >> 20) << 6) | (unsigned)(lane + 32);
   const unsigned m = __reduce_min_sync(0xffffffffu, min(k0, k1));
   Pick pk{-1, 256, -1};
   if (m != KEY_INF) {
@@ -211,7 +213,8 @@ __device__ __forceinline__ unsigned long long key64(int dist, int ord, int idx) 
 // rotation histogram + prune shared by LAST and BOW (:1700-1721 / :338-360).  accepted[q] = claimed cur index or -1;
 // state[] is the pointer state of the current frame; returns the number of pruned entries (warp-uniform).
 __device__ __forceinline__ int prune_rotation(int nq, const int* accepted, const float* qang, const int* qmap,
-                                              const float* cang, int* state, int* s_hist, int* s_keep, int lane) {
+                                              const float* cang, int* state, int* s_hist, int* s_keep, int lane,
+                                              bool state_by_query = false) {
   for (int b = lane; b < ORBM_HISTO_LENGTH; b += 32) s_hist[b] = 0;
   __syncwarp();
   for (int i = lane; i < nq; i += 32) {
@@ -227,7 +230,7 @@ __device__ __forceinline__ int prune_rotation(int nq, const int* accepted, const
     if (idx >= 0) {
       const int bin = rot_bin(qang[qmap ? qmap[i] : i], cang[idx]);
       if (bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) {
-        state[idx] = -1;   // every writer stores NULL: order-free
+        state[state_by_query ? qmap[i] : idx] = -1;   // every writer stores NULL: order-free
         ++pr;
       }
     }
@@ -695,15 +698,19 @@ __global__ void __launch_bounds__(32) k_resolve_points(CurView cv, PointsView pv
 }
 
 // K9/K10 (BOW): claimed = any assignment (:273-274); TH_LOW and ratio on the two best (:292-299)
-__global__ void __launch_bounds__(32) k_resolve_bow(BowQueries bq, float nnratio, int check_ori, ListView in, int* accepted,
-                                                    int* f2kf, int* nmatch, int cmax) {
+// kfkf = 1: SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (:665-812): output indexed by the FIRST keyframe's keypoints,
+// strict bestDist1 < TH_LOW, side-2 validity filter; kfkf = 0: the (KeyFrame*, Frame&) overload (:217-363).
+__global__ void __launch_bounds__(32) k_resolve_bow(BowQueries bq, float nnratio, int check_ori, int kfkf, ListView in,
+                                                    int* accepted, int* f2kf, int* nmatch, int cmax) {
   extern __shared__ __align__(16) unsigned char rsm[];
   __shared__ int s_hist[ORBM_HISTO_LENGTH];
   __shared__ int s_keep[3];
   int* state = reinterpret_cast<int*>(rsm);
   uint8_t* taken = rsm + (size_t)cmax * 4;
   const int lane = threadIdx.x;
-  for (int j = lane; j < bq.nf; j += 32) { state[j] = -1; taken[j] = 0; }
+  const int nstate = kfkf ? bq.nkf : bq.nf;
+  for (int j = lane; j < nstate; j += 32) state[j] = -1;
+  for (int j = lane; j < bq.nf; j += 32) taken[j] = 0;
   __syncwarp();
   int n_acc = 0;
   for (int q = 0; q < bq.nq; ++q) {
@@ -725,7 +732,7 @@ __global__ void __launch_bounds__(32) k_resolve_bow(BowQueries bq, float nnratio
       const int b = bq.f_beg[q], n = -cn;
       for (int e = lane; e < n; e += 32) {
         const int idx = (int)bq.f_idx[b + e];
-        if (!taken[idx]) {
+        if (!taken[idx] && !(bq.f_valid && !bq.f_valid[idx])) {
           const unsigned long long k = key64(hamming256(d0, d1, bq.f_desc + (size_t)idx * 32), e, idx);
           if (k < b1) { b2 = b1; b1 = k; } else if (k < b2) b2 = k;
         }
@@ -737,18 +744,22 @@ __global__ void __launch_bounds__(32) k_resolve_bow(BowQueries bq, float nnratio
         if (m2 != ~0ull) best2 = (int)(m2 >> 44);
       }
     }
-    if (bestIdx >= 0 && best1 <= ORBM_TH_LOW && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
+    const bool under = kfkf ? (best1 < ORBM_TH_LOW) : (best1 <= ORBM_TH_LOW);   // :751 '<' vs :292 '<='
+    if (bestIdx >= 0 && under && (float)best1 < __fmul_rn(nnratio, (float)best2)) {
       a = bestIdx;
       ++n_acc;
-      if (lane == 0) { state[bestIdx] = bq.kf_idx[q]; taken[bestIdx] = 1; }
+      if (lane == 0) {
+        if (kfkf) state[bq.kf_idx[q]] = bestIdx; else state[bestIdx] = bq.kf_idx[q];
+        taken[bestIdx] = 1;
+      }
     }
     if (lane == 0) accepted[q] = a;
     __syncwarp();
   }
   int pruned = 0;
-  if (check_ori) pruned = prune_rotation(bq.nq, accepted, bq.kf_ang, bq.kf_idx, bq.f_ang, state, s_hist, s_keep, lane);
+  if (check_ori) pruned = prune_rotation(bq.nq, accepted, bq.kf_ang, bq.kf_idx, bq.f_ang, state, s_hist, s_keep, lane, kfkf != 0);
   __syncwarp();
-  for (int j = lane; j < bq.nf; j += 32) f2kf[j] = state[j];
+  for (int j = lane; j < nstate; j += 32) f2kf[j] = state[j];
   if (lane == 0) *nmatch = n_acc - pruned;
 }
 

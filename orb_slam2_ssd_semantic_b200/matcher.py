@@ -81,5 +81,15 @@ class ORBmatcher:
                                               int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
 
+    def SearchByBoWKF(self, pKF1: BowView, pKF2: BowView):
+        """SearchByBoW(KeyFrame*, KeyFrame*, vpMatches12) (src/ORBmatcher.cc:665-812) -> (nmatches, matches12) with
+        matches12[i] = pKF2 keypoint matched to pKF1 keypoint i, or -1."""
+        out = np.full(pKF1.n, -1, np.int32)
+        nm = C.c_int(0)
+        a, b = pKF1.struct(), pKF2.struct()
+        _lib.check(self._L.orbm_search_by_bow_kf(self._h, C.byref(a), C.byref(b), self.mfNNratio,
+                                                 int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        return nm.value, out
+
     def launch_count(self) -> int:
         return int(self._L.orbm_launch_count(self._h))

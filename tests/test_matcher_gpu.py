@@ -230,3 +230,19 @@ def test_search_projected_relocalisation_variant(oracle, stream_feats):
     n_ref, ref = oracle.search_projected(F, q, 100, 0, True)
     n_gpu, gpu = ORBmatcher(0.9, True).SearchProjected(F, q, 100, 0)
     assert n_ref > 100 and n_gpu == n_ref and (gpu == ref).all()
+
+
+@pytest.mark.parametrize("nwords", [5, 60])
+def test_search_by_bow_keyframe_keyframe(oracle, stream_feats, nwords):
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    feats, sf = stream_feats
+    rng = np.random.default_rng(23)
+    K1, D1, _, _ = feats[0]
+    K2, D2, _, _ = feats[2]
+    k1 = _bow_view(D1, K1["angle"], rng, nwords, (rng.random(len(K1)) < 0.85).astype(np.uint8))
+    k2 = _bow_view(D2, K2["angle"], rng, nwords, (rng.random(len(K2)) < 0.85).astype(np.uint8))
+    for ratio, ori in ((0.75, True), (0.95, True), (0.8, False)):
+        n_ref, ref = oracle.search_by_bow_kf(k1, k2, ratio, ori)
+        n_gpu, gpu = ORBmatcher(ratio, ori).SearchByBoWKF(k1, k2)
+        assert n_gpu == n_ref and (gpu == ref).all(), (nwords, ratio, ori)
+    assert n_ref > 5
