@@ -250,6 +250,14 @@ int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u
  * src/Frame.cc:850-871), so the device gathers those pixels in place over PCIe.  orbs_set_full_depth_upload(h, 1)
  * forces the full upload (then orbs_device_inputs returns the converted f32 batch). */
 int orbs_set_full_depth_upload(orbs_t* h, int on);
+/* Streaming form of orbs_track_batch_u16: enqueues uploads, kernels and result downloads on the handle's streams and
+ * returns; the outputs are valid after orbs_sync(h).  All host buffers must be page-locked and stay untouched until
+ * then.  Two handles used alternately keep two batches in flight, so the upload of batch k+1 and the download of
+ * batch k-1 overlap the kernels of batch k (what the reference's grab thread / tracking thread split does for one
+ * frame, Examples/RGB-D/rgbd_tum.cc:88-109, done here for whole batches). */
+int orbs_submit_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u16, float depth_factor, const float* Tcw,
+                          int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp,
+                          int32_t* cur2last, int32_t* nmatch, int cap);
 /* convertTo(CV_32F, factor) of n CV_16U pixels resident in HBM (n multiple of 4) on the given cudaStream_t. */
 int b200orb_depth_u16_to_f32_device(const uint16_t* d_src, float* d_dst, size_t n, float factor, void* stream);
 /* Device copies of the inputs of the last host-buffer call (gray u8, depth f32 metres), e.g. to hand keyframes to

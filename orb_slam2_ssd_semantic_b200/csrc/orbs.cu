@@ -207,7 +207,7 @@ int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d
 
 static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, const uint16_t* depth16, float factor,
                             const float* Tcw, int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc,
-                            int32_t* nkp, int32_t* cur2last, int32_t* nmatch, int cap) {
+                            int32_t* nkp, int32_t* cur2last, int32_t* nmatch, int cap, bool wait = true) {
   if (!h || !gray || (!depth && !depth16) || !Tcw || !kps || !desc || !nkp || !cur2last || !nmatch || nframes <= 0 ||
       rows <= 0 || cols <= 0) {
     set_error("bad argument");
@@ -276,7 +276,7 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
   }
   B200_CUDA(cudaMemcpyAsync(nkp, h->ex->d_n, 4 * F, cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaMemcpyAsync(nmatch, h->d_nm, 4 * F, cudaMemcpyDeviceToHost, st));
-  B200_CUDA(cudaStreamSynchronize(st));
+  if (wait) B200_CUDA(cudaStreamSynchronize(st));
   return B200ORB_OK;
 }
 
@@ -291,6 +291,13 @@ int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u
                          int32_t* cur2last, int32_t* nmatch, int cap) {
   return track_batch_host(h, gray, nullptr, depth_u16, depth_factor, Tcw, nframes, rows, cols, kps, desc, nkp, cur2last,
                           nmatch, cap);
+}
+
+int orbs_submit_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u16, float depth_factor, const float* Tcw,
+                          int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc, int32_t* nkp,
+                          int32_t* cur2last, int32_t* nmatch, int cap) {
+  return track_batch_host(h, gray, nullptr, depth_u16, depth_factor, Tcw, nframes, rows, cols, kps, desc, nkp, cur2last,
+                          nmatch, cap, /*wait=*/false);
 }
 
 int orbs_device_inputs(orbs_t* h, const uint8_t** d_gray, const float** d_depth) {

@@ -73,6 +73,19 @@ class StreamTracker:
                                                 F, rows, cols, ptr(kps), ptr(desc), ptr(nkp), ptr(c2l), ptr(nm), self.cap))
         return kps, desc, nkp, c2l, nm
 
+    def submit_batch_u16(self, gray: np.ndarray, depth_u16: np.ndarray, depth_factor: float, Tcw: np.ndarray, out):
+        """Asynchronous track_batch_u16: returns after enqueueing; `out` (alloc_outputs(pinned=True)) is valid after
+        sync().  The input arrays must be page-locked, C-contiguous and stay untouched until then."""
+        for a, dt in ((gray, np.uint8), (depth_u16, np.uint16), (Tcw, np.float32)):
+            if a.dtype != dt or not a.flags.c_contiguous:
+                raise ValueError("submit_batch_u16 takes C-contiguous %s arrays (no hidden copies)" % np.dtype(dt).name)
+        F, rows, cols = gray.shape
+        assert depth_u16.shape == gray.shape and Tcw.size == F * 16
+        kps, desc, nkp, c2l, nm = out
+        _lib.check(self._L.orbs_submit_batch_u16(self._h, ptr(gray), ptr(depth_u16), float(np.float32(depth_factor)), ptr(Tcw),
+                                                 F, rows, cols, ptr(kps), ptr(desc), ptr(nkp), ptr(c2l), ptr(nm), self.cap))
+        return out
+
     def set_full_depth_upload(self, on: bool):
         """False (default): page-locked CV_16U depth is read under the keypoints in place; True: always upload it."""
         _lib.check(self._L.orbs_set_full_depth_upload(self._h, int(on)))

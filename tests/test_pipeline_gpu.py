@@ -83,3 +83,43 @@ def test_u16_depth_zero_copy_gather_from_pinned_memory():
     assert st.device_inputs()[1] is not None
     for x, y, z in zip(a, b, c):
         assert x.tobytes() == y.tobytes() == z.tobytes()
+
+
+@pytest.mark.gpu
+def test_two_batches_in_flight_equal_synchronous_calls():
+    """orbs_submit_batch_u16 on two alternating handles == orbs_track_batch_u16, batch by batch."""
+    import torch
+    from orb_slam2_ssd_semantic_b200 import StreamTracker
+    ws = synth.WallStream(seed=9)
+    batches = []
+    for b in range(3):
+        frames = [ws.frame(b * 5 + i) for i in range(5)]
+        gray = torch.from_numpy(np.stack([f[0] for f in frames])).pin_memory()
+        depth = np.stack([f[1] for f in frames])
+        d16 = torch.from_numpy(np.rint(depth.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)).pin_memory()
+        T = torch.from_numpy(np.ascontiguousarray(np.stack([f[3] for f in frames]), np.float32)).pin_memory()
+        batches.append((gray, d16, T))
+    factor = np.float32(1.0 / synth.DEPTH_FACTOR)
+    mk = lambda: StreamTracker(1000, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, max_frames=5)
+    ref = mk()
+    want = [[x.copy() for x in ref.track_batch_u16(g.numpy(), d.numpy(), factor, T.numpy())] for g, d, T in batches]
+    trk = [mk(), mk()]
+    outs = [t.alloc_outputs(5, pinned=True) for t in trk]
+    got = []
+    for k, (g, d, T) in enumerate(batches):
+        if k >= 2:
+            trk[k & 1].sync()
+            got.append([x.copy() for x in outs[k & 1]])
+        trk[k & 1].submit_batch_u16(g.numpy(), d.numpy(), factor, T.numpy(), outs[k & 1])
+    for k in range(max(0, len(batches) - 2), len(batches)):
+        trk[k & 1].sync()
+        got.append([x.copy() for x in outs[k & 1]])
+    for w, g in zip(want, got):
+        n = w[2]
+        assert (g[2] == n).all() and (g[4] == w[4]).all()
+        for f in range(5):
+            assert g[0][f, :n[f]].tobytes() == w[0][f, :n[f]].tobytes()
+            assert g[1][f, :n[f]].tobytes() == w[1][f, :n[f]].tobytes()
+            assert (g[3][f, :n[f]] == w[3][f, :n[f]]).all()
+    with pytest.raises(ValueError):
+        trk[0].submit_batch_u16(batches[0][0].numpy()[:, ::2], batches[0][1].numpy(), factor, batches[0][2].numpy(), outs[0])
