@@ -253,7 +253,8 @@ def run_b200(args):
     # What the host hands over per step is what the reference's callers hold: gray u8 + the sensor's CV_16U depth +
     # poses for every frame (Tracking::GrabImageRGBD converts the depth itself, src/Tracking.cc:366-367) and the
     # colour image of every keyframe (Tracking::CreateNewKeyFrame -> insertKeyFrame, src/Tracking.cc:1889).  The
-    # keyframe depth is NOT uploaded twice: the mapper reads the tracker's converted device copy.
+    # tracker never uploads depth images (it reads the pixels under the keypoints in place); the mapper uploads the
+    # depth + colour of the keyframes only.
     depth_u16 = np.rint(depth.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)
     assert (depth_u16.astype(np.float32) * np.float32(1.0 / synth.DEPTH_FACTOR) == depth).all()
     p_gray = torch.from_numpy(gray).pin_memory()
@@ -261,17 +262,10 @@ def run_b200(args):
     p_T = torch.from_numpy(T).pin_memory()
     p_rgbk = torch.from_numpy(np.ascontiguousarray(rgb[kfs])).pin_memory()
     p_d16k = torch.from_numpy(np.ascontiguousarray(depth_u16[kfs])).pin_memory()
-    d_rgbk = torch.empty_like(p_rgbk, device=dev)
-    d_d16k = torch.empty_like(p_d16k, device=dev)
-    d_depk = torch.empty(p_d16k.shape, dtype=torch.float32, device=dev)
+    kf_d16, kf_rgb = p_d16k.numpy(), p_rgbk.numpy()
     st_gray, st_d16, st_T = p_gray.numpy(), p_d16.numpy(), p_T.numpy()
     outs = st.alloc_outputs(F, pinned=True)
     factor = np.float32(1.0 / synth.DEPTH_FACTOR)
-    import ctypes as C
-    from orb_slam2_ssd_semantic_b200 import _lib
-    L = _lib.lib()
-    nkfpx = int(p_d16k.numel())
-
     # Two tracker handles used alternately keep two batches in flight: the upload of batch k+1 and the download of
     # batch k-1 overlap the kernels of batch k.  Every batch still crosses PCIe in both directions inside the timed
     # region, and its results are on the host (sync of its handle) before the batch after the next is submitted.
@@ -281,15 +275,9 @@ def run_b200(args):
     outs2 = [outs, st2.alloc_outputs(F, pinned=True)]
 
     def submit(k):
-        # mapper first, asynchronously on its own stream: H2D depth (CV_16U) + colour of the keyframes only, converted
-        # on the device, then the keyframe inserts
-        with torch.cuda.stream(ext_map):
-            d_d16k.copy_(p_d16k, non_blocking=True)
-            d_rgbk.copy_(p_rgbk, non_blocking=True)
-        _lib.check(L.b200orb_depth_u16_to_f32_device(C.c_void_p(d_d16k.data_ptr()), C.c_void_p(d_depk.data_ptr()), nkfpx,
-                                                     float(factor), C.c_void_p(pcm.stream())))
-        pcm.insert_keyframes_device(d_depk.data_ptr(), d_rgbk.data_ptr(), ROWS, COLS, list(range(len(kfs))), T[kfs], synth.FX,
-                                    synth.FY, synth.CX, synth.CY)
+        # mapper first, asynchronously on its own stream (ocm_insert_keyframes_u16): H2D depth (CV_16U) + colour of the
+        # keyframes only, converted on the device, then the keyframe inserts
+        pcm.insert_keyframes_u16(kf_d16, kf_rgb, factor, T[kfs], synth.FX, synth.FY, synth.CX, synth.CY)
         # tracker: H2D gray in chunks overlapped with extraction; the page-locked CV_16U depth is read under the
         # keypoints in place (zero-copy gather); D2H keypoints, descriptors, matches
         trk[k & 1].submit_batch_u16(st_gray, st_d16, factor, st_T, outs2[k & 1])

@@ -307,6 +307,13 @@ int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_
 int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
                                 const int32_t* depth_idx, const int32_t* rgb_idx /* NULL = depth_idx */, int n,
                                 const float* Tcw, float fx, float fy, float cx, float cy);
+/* Host-buffer form for a batch of keyframes as the reference's callers hold them: the sensor's CV_16U depth images
+ * (imDepth before convertTo, src/Tracking.cc:353-367; depth_factor = 1.0f / DepthMapFactor) and the colour images
+ * handed to insertKeyFrame (src/Tracking.cc:1889), depth_u16[n][rows][cols], rgb[n][rows][cols][3], Tcw[n][16].
+ * Uploads, the conversion and the n inserts are enqueued on the map's stream and the call returns; the host buffers
+ * (page-locked for a truly asynchronous upload) must stay untouched until ocm_sync(h). */
+int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t* rgb, int rows, int cols, int n,
+                             float depth_factor, const float* Tcw, float fx, float fy, float cx, float cy);
 /* World-frame points of the LAST inserted keyframe after gating + leaf filter + transform (xyz f32 x n,
  * unordered: compare as sets). */
 int ocm_last_points(ocm_t* h, float* xyz, uint8_t* rgb, int cap, int* n);

@@ -30,7 +30,7 @@ EXPORTS = [
     "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_by_bow_kf", "orbm_search_projected",
     "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_u16", "orbs_submit_batch_u16", "orbs_device_inputs", "orbs_set_full_depth_upload", "b200orb_depth_u16_to_f32_device", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
     "orbs_stream", "orbs_launch_count", "orbs_extractor",
-    "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device", "ocm_insert_keyframes_device",
+    "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device", "ocm_insert_keyframes_device", "ocm_insert_keyframes_u16",
     "ocm_last_points", "ocm_num_leaves", "ocm_export_leaves", "ocm_query", "ocm_summary_count",
     "ocm_export_summaries_device", "ocm_apply_summaries_device", "ocm_sync", "ocm_stream", "ocm_launch_count",
 ]
@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.ocm_insert_keyframe.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f, vp]
     L.ocm_insert_keyframe_device.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f, vp]
     L.ocm_insert_keyframes_device.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp, f, f, f, f]
+    L.ocm_insert_keyframes_u16.argtypes = [vp, vp, vp, i, i, i, f, vp, f, f, f, f]
     L.ocm_last_points.argtypes = [vp, vp, vp, i, C.POINTER(i)]
     L.ocm_num_leaves.argtypes = [vp]
     L.ocm_num_leaves.restype = C.c_int64

@@ -419,6 +419,10 @@ struct ocm {
   unsigned* d_occ_rgb = nullptr;
   float* d_depth = nullptr;
   uint8_t *d_rgb = nullptr, *d_label = nullptr;
+  uint16_t* d_kf_d16 = nullptr;   // staging of ocm_insert_keyframes_u16
+  float* d_kf_depth = nullptr;
+  uint8_t* d_kf_rgb = nullptr;
+  size_t kf_cap = 0;
   int last_points = 0;
   long long* d_export_counter = nullptr;
 
@@ -433,9 +437,10 @@ struct ocm {
   void free_scratch() {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(leaf.keys); F(leaf.count); F(leaf.first); F(leaf.offset); F(leaf.cursor); F(d_pix_slot); F(d_bucket); F(d_voxlist);
-    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(occ.list); F(fre.list); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label);
+    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(occ.list); F(fre.list); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb);
     leaf = LeafTable{}; d_pix_slot = d_bucket = d_voxlist = nullptr; d_pts = nullptr; d_pts_rgb = d_pts_label = nullptr;
     occ = KeySet{}; fre = KeySet{}; d_occ_rgb = nullptr; d_depth = nullptr; d_rgb = d_label = nullptr;
+    d_kf_d16 = nullptr; d_kf_depth = nullptr; d_kf_rgb = nullptr; kf_cap = 0;
   }
   template <class T>
   int fill(T* p, T v, long long n);
@@ -626,6 +631,30 @@ int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d
     if (di < 0 || ri < 0) { set_error("negative frame index"); return B200ORB_EINVAL; }
     B200_CHECK(h->insert(d_depth + npix * di, d_rgb + npix * 3 * ri, nullptr, rows, cols, Tcw + 16 * i, fx, fy, cx, cy));
   }
+  return B200ORB_OK;
+}
+
+int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t* rgb, int rows, int cols, int n,
+                             float depth_factor, const float* Tcw, float fx, float fy, float cx, float cy) {
+  if (!h || !depth_u16 || !rgb || !Tcw || rows <= 0 || cols <= 0 || n < 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  if (n == 0) return B200ORB_OK;
+  DeviceGuard g(h->device);
+  const size_t npix = (size_t)rows * cols, tot = npix * n;
+  if ((npix % 4) != 0) { set_error("rows*cols must be a multiple of 4"); return B200ORB_EINVAL; }
+  if (tot > h->kf_cap) {   // staging for n keyframes (grown on demand; reused by every later call)
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_kf_d16); cudaFree(h->d_kf_depth); cudaFree(h->d_kf_rgb);
+    h->d_kf_d16 = nullptr; h->d_kf_depth = nullptr; h->d_kf_rgb = nullptr; h->kf_cap = 0;
+    B200_CUDA(cudaMalloc(&h->d_kf_d16, tot * 2)); B200_CUDA(cudaMalloc(&h->d_kf_depth, tot * 4)); B200_CUDA(cudaMalloc(&h->d_kf_rgb, tot * 3));
+    h->kf_cap = tot;
+  }
+  B200_CUDA(cudaMemcpyAsync(h->d_kf_d16, depth_u16, tot * 2, cudaMemcpyHostToDevice, h->stream));
+  B200_CUDA(cudaMemcpyAsync(h->d_kf_rgb, rgb, tot * 3, cudaMemcpyHostToDevice, h->stream));
+  k_depth_u16_to_f32<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, h->stream>>>(
+      reinterpret_cast<const ushort4*>(h->d_kf_d16), reinterpret_cast<float4*>(h->d_kf_depth), depth_factor, tot / 4);
+  ++h->launches;
+  for (int i = 0; i < n; ++i)
+    B200_CHECK(h->insert(h->d_kf_depth + npix * i, h->d_kf_rgb + npix * 3 * i, nullptr, rows, cols, Tcw + 16 * i, fx, fy, cx, cy));
   return B200ORB_OK;
 }
 

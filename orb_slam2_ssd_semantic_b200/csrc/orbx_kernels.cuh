@@ -144,24 +144,24 @@ constexpr int FAST_WARPS = 8;
 constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_MAX_ROI = 72;   // ROI side bound enforced at create (cell <= 60 px + 6, padded)
 constexpr int FAST_TP_SMALL = 48;  // compile-time tile pitches (>= 3 + ROI width, multiple of 4): ring offsets are
-constexpr int FAST_TP_BIG = 80;    // immediates; SMALL serves ROIs up to 45 px (640x480: 43), BIG the general case
+constexpr int FAST_TP_BIG = 80;
+constexpr int FAST_QLEN = 64;      // per-warp ring of pixels that passed the compass test (<= 31 pending + 32 new)    // immediates; SMALL serves ROIs up to 45 px (640x480: 43), BIG the general case
 
 // m(p) of one pixel.  Packing: one IMAD per ring pixel gives lo16 = 256 + (c - r), hi16 = 256 + (r - c) (biased,
 // both in [1, 511], so no borrow crosses the halves); min3/max3 on s16x2 then evaluate the bright and the dark
 // arcs at once: a3[i] = min(v[i..i+2]), a9[i] = min(a3[i], a3[i+3], a3[i+6]) = min over the 9-arc starting at i.
-// r0/r4/r8/r12 are the four compass pixels the caller already loaded for the quick rejection test.
 template <int TP>
-__device__ __forceinline__ int fast_m_exact(const uint8_t* c, int cv, int r0, int r4, int r8, int r12) {
+__device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
   constexpr int tp = TP;
-  const int bias = 256 * 65537 - cv * 65535;
+  const int bias = 256 * 65537 - (int)c[0] * 65535;
   unsigned v[16];
-  v[0] = (unsigned)(r0 * 65535 + bias);                   v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
+  v[0] = (unsigned)((int)c[3 * tp] * 65535 + bias);       v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
   v[2] = (unsigned)((int)c[2 * tp + 2] * 65535 + bias);   v[3] = (unsigned)((int)c[tp + 3] * 65535 + bias);
-  v[4] = (unsigned)(r4 * 65535 + bias);                   v[5] = (unsigned)((int)c[-tp + 3] * 65535 + bias);
+  v[4] = (unsigned)((int)c[3] * 65535 + bias);            v[5] = (unsigned)((int)c[-tp + 3] * 65535 + bias);
   v[6] = (unsigned)((int)c[-2 * tp + 2] * 65535 + bias);  v[7] = (unsigned)((int)c[-3 * tp + 1] * 65535 + bias);
-  v[8] = (unsigned)(r8 * 65535 + bias);                   v[9] = (unsigned)((int)c[-3 * tp - 1] * 65535 + bias);
+  v[8] = (unsigned)((int)c[-3 * tp] * 65535 + bias);      v[9] = (unsigned)((int)c[-3 * tp - 1] * 65535 + bias);
   v[10] = (unsigned)((int)c[-2 * tp - 2] * 65535 + bias); v[11] = (unsigned)((int)c[-tp - 3] * 65535 + bias);
-  v[12] = (unsigned)(r12 * 65535 + bias);                 v[13] = (unsigned)((int)c[tp - 3] * 65535 + bias);
+  v[12] = (unsigned)((int)c[-3] * 65535 + bias);          v[13] = (unsigned)((int)c[tp - 3] * 65535 + bias);
   v[14] = (unsigned)((int)c[2 * tp - 2] * 65535 + bias);  v[15] = (unsigned)((int)c[3 * tp - 1] * 65535 + bias);
   unsigned a3[16], a9[16];
 #pragma unroll
@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int cell = blockIdx.x * FAST_WARPS + w, f = blockIdx.y;
   if (cell >= ncells) return;
+  __shared__ unsigned short s_queue[FAST_WARPS][FAST_QLEN];
+  unsigned short* queue = s_queue[w];
   uint8_t* tile = fsm + (size_t)w * 2 * rows_max * tp;
   uint8_t* mm = tile + (size_t)rows_max * tp;
   const CellDesc cd = cells[cell];
@@ -226,30 +228,56 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
   unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
   const bool wide = rw - 6 > 32;
   int total = 0;
+  int qh = 0, qn = 0;   // candidate ring (warp-uniform head / fill)
   // pass 0: everything at ini_th (pixels with m <= ini_th can neither be corners nor outscore one at that threshold);
   // pass 1 (:821, only when the cell is EMPTY AFTER non-max suppression): the same at min_th.
   for (int pass = 0; pass < 2 && total == 0; ++pass) {
     const int t = pass ? min_th : ini_th;
     if (pass == 1 && ini_th == min_th) break;
     {
-      const uint8_t* c = tile + 3 * tp + sh + 3 + lane;
-      uint8_t* q = mm + 3 * tp + sh + 3 + lane;
-      for (int y = 3; y < rh - 3; ++y, c += tp, q += tp) {
+      // Sweep 1 (lane = column): the compass test in packed form -- a 9-arc always holds one pixel of each opposite
+      // compass pair, and all its pixels lie on the same side of the centre, so
+      //   min(max(v0, v8), max(v4, v12)) > 256 + t  in either half
+      // is necessary for a corner at t.  Pixels that fail get score 0 right away; the others are queued (tile offset)
+      // and their exact m is evaluated 32 at a time by full warps, whatever rows/columns they came from.
+      const unsigned kq = (unsigned)(0x7fff - 256 - t) * 0x10001u;
+      const int off0 = 3 * tp + sh + 3 + lane;
+      for (int y = 3; y < rh - 3; ++y) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 1 && !wide) break;
+          const int off = off0 + (y - 3) * tp + 32 * h;
+          bool hit = false;
           if (3 + lane + 32 * h < rw - 3) {
-            const uint8_t* cc = c + 32 * h;
-            const int cv = cc[0], r0 = cc[3 * tp], r8 = cc[-3 * tp], r4 = cc[3], r12 = cc[-3];
-            // necessary condition for a corner at t: every 9-arc contains one pixel of each opposite pair
-            const bool p0 = abs(cv - r0) > t || abs(cv - r8) > t;
-            const bool p4 = abs(cv - r4) > t || abs(cv - r12) > t;
-            int m = 0;
-            if (p0 && p4) m = fast_m_exact<TP>(cc, cv, r0, r4, r8, r12);
-            q[32 * h] = (uint8_t)((m > t) ? m : 0);
+            const uint8_t* cc = tile + off;
+            const int bias = 256 * 65537 - (int)cc[0] * 65535;
+            const unsigned v0 = (unsigned)((int)cc[3 * tp] * 65535 + bias), v8 = (unsigned)((int)cc[-3 * tp] * 65535 + bias);
+            const unsigned v4 = (unsigned)((int)cc[3] * 65535 + bias), v12 = (unsigned)((int)cc[-3] * 65535 + bias);
+            const unsigned qv = __vmins2(__vmaxs2(v0, v8), __vmaxs2(v4, v12));
+            hit = ((qv + kq) & 0x80008000u) != 0u;    // halves are in [1,511]: no carry between them
+            if (!hit) mm[off] = 0;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          if (hit) queue[(qh + qn + __popc(bal & ((1u << lane) - 1u))) & (FAST_QLEN - 1)] = (unsigned short)off;
+          qn += __popc(bal);
+          if (qn >= 32) {
+            __syncwarp();
+            const int o = queue[(qh + lane) & (FAST_QLEN - 1)];
+            const int m = fast_m_exact<TP>(tile + o);
+            mm[o] = (uint8_t)((m > t) ? m : 0);
+            qh += 32;
+            qn -= 32;
           }
         }
       }
+      __syncwarp();
+      if (lane < qn) {
+        const int o = queue[(qh + lane) & (FAST_QLEN - 1)];
+        const int m = fast_m_exact<TP>(tile + o);
+        mm[o] = (uint8_t)((m > t) ? m : 0);
+      }
+      qh = 0;
+      qn = 0;
     }
     __syncwarp();
     // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving

@@ -61,6 +61,19 @@ class PointCloudMapping:
                                                        ptr(ridx), len(idx), ptr(T), float(fx), float(fy), float(cx),
                                                        float(cy)))
 
+    def insert_keyframes_u16(self, depth_u16: np.ndarray, rgb: np.ndarray, depth_factor: float, Tcw, fx, fy, cx, cy):
+        """Keyframes from HOST buffers as the reference's callers hold them: CV_16U depth [n,rows,cols] (converted with
+        depth_factor = 1/DepthMapFactor on the device) and colour [n,rows,cols,3].  Asynchronous: the arrays (page-locked
+        for a truly asynchronous upload) must stay untouched until sync()."""
+        if depth_u16.dtype != np.uint16 or rgb.dtype != np.uint8 or not depth_u16.flags.c_contiguous or not rgb.flags.c_contiguous:
+            raise ValueError("insert_keyframes_u16 takes C-contiguous uint16 depth and uint8 colour arrays (no hidden copies)")
+        n, rows, cols = depth_u16.shape
+        assert rgb.shape == (n, rows, cols, 3)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(n, 16)
+        _lib.check(self._L.ocm_insert_keyframes_u16(self._h, ptr(depth_u16), ptr(rgb), rows, cols, n,
+                                                    float(np.float32(depth_factor)), ptr(T), float(fx), float(fy), float(cx),
+                                                    float(cy)))
+
     def last_points(self):
         n = C.c_int(0)
         _lib.check(self._L.ocm_last_points(self._h, None, None, 0, C.byref(n)))

@@ -115,3 +115,36 @@ def test_save_octomap_round_trip(oracle, tmp_path):
     kg, lg, _ = gpu.export_leaves()
     a, b = _leaf_dict(k16, v16), _leaf_dict(kg, lg)
     assert len(a[0]) == nleaves and (a[0] == b[0]).all() and (a[1] == b[1]).all()
+
+
+def test_host_u16_keyframe_batch_equals_per_keyframe_inserts(oracle):
+    """ocm_insert_keyframes_u16 (CV_16U depth + colour from host buffers, one asynchronous call) builds the same map as
+    the per-keyframe float-depth inserts and as the oracle."""
+    import torch
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    scene = _scene(4)
+    d16 = np.stack([np.rint(d.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16) for d, _, _ in scene])
+    factor = np.float32(1.0 / synth.DEPTH_FACTOR)
+    depth = d16.astype(np.float32) * factor
+    rgb = np.ascontiguousarray(np.stack([c for _, c, _ in scene]))
+    T = np.stack([t for _, _, t in scene]).astype(np.float32)
+    a = PointCloudMapping(0.05)
+    p16, prgb = torch.from_numpy(d16).pin_memory(), torch.from_numpy(rgb).pin_memory()
+    a.insert_keyframes_u16(p16.numpy(), prgb.numpy(), factor, T, synth.FX, synth.FY, synth.CX, synth.CY)
+    a.insert_keyframes_u16(p16.numpy()[:0], prgb.numpy()[:0], factor, T[:0], synth.FX, synth.FY, synth.CX, synth.CY)   # n = 0
+    a.sync()
+    b = PointCloudMapping(0.05)
+    ref = oracle.RefOccupancy()
+    for i in range(len(scene)):
+        b.insertKeyFrame(T[i], depth[i], rgb[i], synth.FX, synth.FY, synth.CX, synth.CY)
+        ref.insert_keyframe(T[i], depth[i], rgb[i], synth.FX, synth.FY, synth.CX, synth.CY, None)
+    ka, la, _ = a.export_leaves()
+    kb, lb, _ = b.export_leaves()
+    kr, lr = ref.export_leaves()
+    pa, va = _leaf_dict(ka, la)
+    pb, vb = _leaf_dict(kb, lb)
+    pr, vr = _leaf_dict(kr, lr)
+    assert len(pr) > 500 and (pa == pb).all() and (va == vb).all()
+    assert len(pa) == len(pr) and (pa == pr).all() and np.abs(va - vr).max() <= 1e-5
+    with pytest.raises(ValueError):
+        a.insert_keyframes_u16(d16.astype(np.int32), rgb, factor, T, synth.FX, synth.FY, synth.CX, synth.CY)
