@@ -431,16 +431,15 @@ struct ocm {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves);
     free_scratch();
-    F(d_counters); F(d_err); F(d_export_counter);
+    F(d_counters); F(d_err); F(d_export_counter); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb);
     if (stream) cudaStreamDestroy(stream);
   }
   void free_scratch() {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(leaf.keys); F(leaf.count); F(leaf.first); F(leaf.offset); F(leaf.cursor); F(d_pix_slot); F(d_bucket); F(d_voxlist);
-    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(occ.list); F(fre.list); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb);
+    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(occ.list); F(fre.list); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label);
     leaf = LeafTable{}; d_pix_slot = d_bucket = d_voxlist = nullptr; d_pts = nullptr; d_pts_rgb = d_pts_label = nullptr;
     occ = KeySet{}; fre = KeySet{}; d_occ_rgb = nullptr; d_depth = nullptr; d_rgb = d_label = nullptr;
-    d_kf_d16 = nullptr; d_kf_depth = nullptr; d_kf_rgb = nullptr; kf_cap = 0;
   }
   template <class T>
   int fill(T* p, T v, long long n);
@@ -641,6 +640,7 @@ int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t*
   DeviceGuard g(h->device);
   const size_t npix = (size_t)rows * cols, tot = npix * n;
   if ((npix % 4) != 0) { set_error("rows*cols must be a multiple of 4"); return B200ORB_EINVAL; }
+  B200_CHECK(h->ensure_scratch(rows, cols));
   if (tot > h->kf_cap) {   // staging for n keyframes (grown on demand; reused by every later call)
     B200_CUDA(cudaStreamSynchronize(h->stream));
     cudaFree(h->d_kf_d16); cudaFree(h->d_kf_depth); cudaFree(h->d_kf_rgb);

@@ -53,7 +53,8 @@ int launch_match_last(const CurView& cv_in, const LastView& lv, const MatchCam& 
                       int lmax, cudaStream_t stream, long long* launches) {
   const int lmax16 = align_up(lmax, 16);
   const size_t smem = mf_smem_bytes(cmax, lmax16);
-  if (smem > 200 * 1024)   // frame too large to stage in shared memory: separate grid / candidate / resolve kernels
+  if (smem > 200 * 1024 || cmax > 4096)   // frame too large to stage in shared memory (or for the packed resolve key):
+                                          // separate grid / candidate / resolve kernels
     return launch_match_last_unfused(cv_in, lv, cam, npairs, d_goff, d_gidx, d_list, d_count, d_accepted, d_cur2last,
                                      d_nmatch, cmax, lmax, stream, launches);
   B200_CUDA(cudaFuncSetAttribute(k_match_last_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

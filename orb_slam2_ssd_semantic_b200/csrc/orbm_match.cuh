@@ -318,10 +318,15 @@ __global__ void __launch_bounds__(32) k_resolve_last(CurView cv, LastView lv, Ma
 // other warps refill while warp 0 resolves.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int MF_THREADS = 512;
-constexpr int MF_QC = 16;   // queries per resolve chunk
+constexpr int MF_QC = 30;   // queries per chunk: two per producer warp (15 producers + the resolving warp)
 
+// grid-build scratch (one counter per cell), reused as the candidate ring: 2 x MF_QC lists + lengths + claim flags
+__host__ __device__ inline size_t mf_ring_bytes() {
+  const size_t ring = (size_t)2 * MF_QC * LCAP * 4 + (size_t)4 * MF_QC * 4, grid = (size_t)GRID_CELLS * 4;
+  return ((ring > grid ? ring : grid) + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t mf_smem_bytes(int cmax, int lmax) {
-  return (size_t)(GRID_CELLS + 1) * 4 + (size_t)GRID_CELLS * 4 + (size_t)cmax * (4 + 4 + 4 + 4 + 4 + 32 + 4 + 1) +
+  return (size_t)(GRID_CELLS + 1) * 4 + mf_ring_bytes() + (size_t)cmax * (4 + 4 + 4 + 4 + 4 + 32 + 4 + 1) +
          (size_t)lmax * 20 + 64;
 }
 
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   unsigned char* q = fsm;
   uint4* s_desc = reinterpret_cast<uint4*>(q); q += (size_t)cmax * 32;
   int* s_off = reinterpret_cast<int*>(q); q += (size_t)(GRID_CELLS + 1) * 4;
-  int* s_cur = reinterpret_cast<int*>(q); q += (size_t)GRID_CELLS * 4;   // grid-build scratch, later the list ring
+  int* s_cur = reinterpret_cast<int*>(q); q += mf_ring_bytes();           // grid-build scratch, later the list ring
   int* s_idx = reinterpret_cast<int*>(q); q += (size_t)cmax * 4;
   float* s_x = reinterpret_cast<float*>(q); q += (size_t)cmax * 4;
   float* s_y = reinterpret_cast<float*>(q); q += (size_t)cmax * 4;
@@ -414,8 +419,7 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   bool fwd, bwd;
   motion_flags(cam, cv.Tcw + (size_t)p * 16, lv.Tcw + (size_t)p * 16, fwd, bwd);
   const float* Tc = cv.Tcw + (size_t)p * 16;
-  unsigned* L = lists.list + lo * LCAP;
-  int* C = lists.count + lo;
+  (void)lists;   // the candidate lists of the fused path never leave shared memory
   // ---- K8a: projection + window of every query, one THREAD per query (scalar double-precision chain off the
   //      warp-serial path) -----------------------------------------------------------------------------------------
   for (int i = tid; i < nl; i += nthr) {
@@ -430,55 +434,74 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
     q_lv[i] = packed;
   }
   __syncthreads();
-  // ---- K8b candidates: warps stride over the queries; the next query's descriptor is fetched one iteration ahead --
-  {
-    const uint4* dbase = reinterpret_cast<const uint4*>(lv.desc + lo * 32);
-    uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;
-    if (warp < nl) { n0 = __ldg(dbase + 2 * (size_t)warp); n1 = __ldg(dbase + 2 * (size_t)warp + 1); }
-    for (int i = warp; i < nl; i += nwarp) {
-      const uint4 d0 = n0, d1 = n1;
-      if (i + nwarp < nl) { n0 = __ldg(dbase + 2 * (size_t)(i + nwarp)); n1 = __ldg(dbase + 2 * (size_t)(i + nwarp) + 1); }
-      int cnt = 0;
-      const int packed = q_lv[i];
-      if (packed >> 16) {
-        QueryGeom qg;
-        qg.u = q_u[i]; qg.v = q_v[i]; qg.r = q_r[i]; qg.rr = qg.r; qg.ur = q_ur[i];
-        qg.min_level = (packed & 0xff) - 1; qg.max_level = ((packed >> 8) & 0xff) - 1;
-        unsigned* list = L + (size_t)i * LCAP;
-        cnt = warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
-          if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
-        });
-      }
-      if (lane == 0) C[i] = (cnt > LCAP) ? -cnt : cnt;
-    }
-  }
-  __syncthreads();   // lists are read back by this CTA only: block-level visibility is enough
-  // ---- K9 ordered resolve through a double-buffered ring --------------------------------------------------------------
-  unsigned* ring = reinterpret_cast<unsigned*>(s_cur);            // 2 x MF_QC x LCAP words = 8 KB
-  int* rcnt = reinterpret_cast<int*>(ring + 2 * MF_QC * LCAP);     // 2 x MF_QC
+  // ---- K8b + K9, pipelined through a double-buffered shared-memory ring ------------------------------------------------
+  // Chunk c = queries [c*MF_QC, (c+1)*MF_QC).  In step c the producer warps (1..15) build the candidate lists of chunk c
+  // straight into ring[c & 1] (two queries per warp) while warp 0 resolves chunk c-1 from ring[(c-1) & 1] in query
+  // order -- the only loop-carried state (claimed current keypoints) lives in that one warp.  One barrier per step.
+  unsigned* ring = reinterpret_cast<unsigned*>(s_cur);            // 2 x MF_QC x LCAP words (grid scratch + pad)
+  int* rcnt = reinterpret_cast<int*>(ring + 2 * MF_QC * LCAP);     // 2 x MF_QC list lengths (negative: overflowed)
+  int* robs = rcnt + 2 * MF_QC;                                     // 2 x MF_QC "query claims its match" flags
   const int nchunk = (nl + MF_QC - 1) / MF_QC;
-  auto load_chunk = [&](int k, int t0, int tn) {
-    const int q0 = k * MF_QC, nq = min(MF_QC, nl - q0);
-    unsigned* dst = ring + (k & 1) * MF_QC * LCAP;
-    for (int w_ = t0; w_ < nq * LCAP; w_ += tn) dst[w_] = L[(size_t)q0 * LCAP + w_];
-    for (int w_ = t0; w_ < nq; w_ += tn) rcnt[(k & 1) * MF_QC + w_] = C[q0 + w_];
-  };
-  if (nchunk > 0) load_chunk(0, tid, nthr);
-  __syncthreads();
   const int* lobs = lv.obs ? lv.obs + lo : nullptr;
   int* acc = accepted + lo;
   int n_acc = 0;
-  for (int k = 0; k < nchunk; ++k) {
-    if (warp == 0) {
+  const uint4* dbase = reinterpret_cast<const uint4*>(lv.desc + lo * 32);
+  const int nprod = nwarp - 1;
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;   // producer: descriptor of its next query, fetched one query ahead
+  if (warp > 0 && warp - 1 < nl) { n0 = __ldg(dbase + 2 * (size_t)(warp - 1)); n1 = __ldg(dbase + 2 * (size_t)(warp - 1) + 1); }
+  for (int c = 0; c <= nchunk; ++c) {
+    if (warp > 0) {
+      if (c < nchunk) {
+        const int q0 = c * MF_QC;
+        unsigned* rb = ring + (c & 1) * MF_QC * LCAP;
+        for (int t = warp - 1; t < MF_QC; t += nprod) {
+          const int i = q0 + t;
+          if (i >= nl) break;
+          const uint4 d0 = n0, d1 = n1;
+          {   // next query of this warp: t + nprod in this chunk, else (warp - 1) in the next chunk
+            const int tn = t + nprod;
+            const int in = (tn < MF_QC) ? q0 + tn : q0 + MF_QC + (warp - 1);
+            if (in < nl) { n0 = __ldg(dbase + 2 * (size_t)in); n1 = __ldg(dbase + 2 * (size_t)in + 1); }
+          }
+          int cnt = 0;
+          const int packed = q_lv[i];
+          if (packed >> 16) {
+            QueryGeom qg;
+            qg.u = q_u[i]; qg.v = q_v[i]; qg.r = q_r[i]; qg.rr = qg.r; qg.ur = q_ur[i];
+            qg.min_level = (packed & 0xff) - 1; qg.max_level = ((packed >> 8) & 0xff) - 1;
+            unsigned* list = rb + t * LCAP;
+            cnt = warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
+              if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
+            });
+          }
+          if (lane == 0) {
+            rcnt[(c & 1) * MF_QC + t] = (cnt > LCAP) ? -cnt : cnt;
+            robs[(c & 1) * MF_QC + t] = (lobs ? lobs[i] : cam.last_obs_default) > 0;
+          }
+        }
+      }
+    } else if (c > 0) {
+      const int k = c - 1;
       const int q0 = k * MF_QC, nq = min(MF_QC, nl - q0);
       const unsigned* buf = ring + (k & 1) * MF_QC * LCAP;
+      const int* bcnt = rcnt + (k & 1) * MF_QC;
+      const int* bobs = robs + (k & 1) * MF_QC;
+      // entries of the NEXT query are fetched before the current one is resolved (they do not depend on the claims)
+      int cn_n = bcnt[0];
+      unsigned v0_n = buf[lane], v1_n = buf[lane + 32];
       for (int t = 0; t < nq; ++t) {
         const int i = q0 + t;
-        const int cn = rcnt[(k & 1) * MF_QC + t];
+        const int cn = cn_n;
+        const unsigned v0 = v0_n, v1 = v1_n;
+        if (t + 1 < nq) { cn_n = bcnt[t + 1]; v0_n = buf[(t + 1) * LCAP + lane]; v1_n = buf[(t + 1) * LCAP + lane + 32]; }
         int best_idx = -1, best_dist = 256;
         if (cn > 0) {
-          const Pick pk = pick_min(buf[t * LCAP + lane], buf[t * LCAP + lane + 32], cn, taken, -1, lane);
-          best_idx = pk.idx; best_dist = pk.dist;
+          // key = dist << 18 | position << 12 | index (index < 4096, host-checked): one redux yields the first minimum
+          unsigned k0 = KEY_INF, k1 = KEY_INF;
+          if (lane < cn && !taken[v0 & 0xfffu]) k0 = ((v0 >> 20) << 18) | ((unsigned)lane << 12) | (v0 & 0xfffu);
+          if (lane + 32 < cn && !taken[v1 & 0xfffu]) k1 = ((v1 >> 20) << 18) | ((unsigned)(lane + 32) << 12) | (v1 & 0xfffu);
+          const unsigned m = __reduce_min_sync(0xffffffffu, min(k0, k1));
+          if (m != KEY_INF) { best_idx = (int)(m & 0xfffu); best_dist = (int)(m >> 18); }
         } else if (cn < 0) {   // overflowed list: exact re-walk with the claimed filter
           QueryGeom qg;
           if (setup_last_query(cam, Tc, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], qg)) {
@@ -498,14 +521,12 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
           ++n_acc;
           if (lane == 0) {
             state[best_idx] = i;
-            if ((lobs ? lobs[i] : cam.last_obs_default) > 0) taken[best_idx] = 1;
+            if (bobs[t]) taken[best_idx] = 1;
           }
         }
         if (lane == 0) acc[i] = a;
         __syncwarp();
       }
-    } else if (k + 1 < nchunk) {
-      load_chunk(k + 1, tid - 32, nthr - 32);
     }
     __syncthreads();
   }

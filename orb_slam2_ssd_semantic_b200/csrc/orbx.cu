@@ -209,11 +209,15 @@ int orbx::ensure_geometry(int r, int c, int F) {
   ltab.sel_off[nl] = selcap;
   ncells = (int)cells.size();
   {
-    int rwm = 0, rhm = 0;
-    for (const CellDesc& cd : cells) { rwm = std::max(rwm, (int)cd.rw); rhm = std::max(rhm, (int)cd.rh); }
+    int rwm = 0, rhm = 0, det = 0;
+    for (const CellDesc& cd : cells) {
+      rwm = std::max(rwm, (int)cd.rw); rhm = std::max(rhm, (int)cd.rh);
+      det = std::max(det, ((int)cd.rw - 6) * ((int)cd.rh - 6));
+    }
+    fast_clist_cap = align_up(std::max(det, 8), 8);   // every detection pixel of a cell may be a corner
     fast_tp = (rwm + 3 <= FAST_TP_SMALL) ? FAST_TP_SMALL : FAST_TP_BIG;
     fast_rows_max = rhm;
-    fast_smem = (size_t)FAST_WARPS * 2 * rhm * fast_tp;
+    fast_smem = (size_t)FAST_WARPS * (2 * rhm * fast_tp + 2 * fast_clist_cap);
     if (fast_smem > 48 * 1024) {
       B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
       B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
@@ -349,10 +353,10 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
     const dim3 grd((ncells + FAST_WARPS - 1) / FAST_WARPS, F);
     if (fast_tp == FAST_TP_SMALL)
       k_fast_cells<FAST_TP_SMALL><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
-                                                                           prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max);
+                                                                           prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max, fast_clist_cap);
     else
       k_fast_cells<FAST_TP_BIG><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
-                                                                         prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max);
+                                                                         prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max, fast_clist_cap);
   }
   ++launches;
   B200_CHECK(prof_mark(ST_FAST + 1));

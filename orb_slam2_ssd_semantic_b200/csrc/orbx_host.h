@@ -33,7 +33,7 @@ struct orbx {
   b200::PyrView rawv{}, blurv{};
   int ncells = 0, slots_per_frame = 0, sel_per_frame = 0, cap = 0, qt_cap = 0;
   size_t qt_smem = 0;
-  int fast_tp = 0, fast_rows_max = 0;
+  int fast_tp = 0, fast_rows_max = 0, fast_clist_cap = 0;
   size_t fast_smem = 0;
   int qt_group_lb[3] = {0, 0, 0}, qt_group_le[3] = {0, 0, 0}, qt_group_kcap[3] = {0, 0, 0};
   size_t qt_group_smem[3] = {0, 0, 0};

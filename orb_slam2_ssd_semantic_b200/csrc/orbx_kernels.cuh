@@ -189,7 +189,8 @@ template <int TP>
 __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
                                                              int ncells, int slots_per_frame, int ini_th,
                                                              int min_th, unsigned* __restrict__ cand,
-                                                             int* __restrict__ cellcnt, int aligned, int rows_max) {
+                                                             int* __restrict__ cellcnt, int aligned, int rows_max,
+                                                             int clist_cap) {
   extern __shared__ __align__(16) uint8_t fsm[];
   constexpr int tp = TP;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -197,8 +198,9 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
   if (cell >= ncells) return;
   __shared__ unsigned short s_queue[FAST_WARPS][FAST_QLEN];
   unsigned short* queue = s_queue[w];
-  uint8_t* tile = fsm + (size_t)w * 2 * rows_max * tp;
+  uint8_t* tile = fsm + (size_t)w * (2 * rows_max * tp + 2 * clist_cap);
   uint8_t* mm = tile + (size_t)rows_max * tp;
+  unsigned short* clist = reinterpret_cast<unsigned short*>(mm + (size_t)rows_max * tp);   // corners at t, row-major
   const CellDesc cd = cells[cell];
   const int l = cd.level, rw = cd.rw, rh = cd.rh;
   const int pitch = pyr.pitch[l];
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
   const bool wide = rw - 6 > 32;
   int total = 0;
   int qh = 0, qn = 0;   // candidate ring (warp-uniform head / fill)
+  int cn = 0;           // corners at t found so far (warp-uniform)
   // pass 0: everything at ini_th (pixels with m <= ini_th can neither be corners nor outscore one at that threshold);
   // pass 1 (:821, only when the cell is EMPTY AFTER non-max suppression): the same at min_th.
   for (int pass = 0; pass < 2 && total == 0; ++pass) {
@@ -264,49 +267,56 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
             __syncwarp();
             const int o = queue[(qh + lane) & (FAST_QLEN - 1)];
             const int m = fast_m_exact<TP>(tile + o);
-            mm[o] = (uint8_t)((m > t) ? m : 0);
+            const bool cr = m > t;
+            mm[o] = (uint8_t)(cr ? m : 0);
+            const unsigned cb = __ballot_sync(0xffffffffu, cr);   // the queue is FIFO over a row-major sweep, so the
+            if (cr) clist[cn + __popc(cb & ((1u << lane) - 1u))] = (unsigned short)o;   // corner list is row-major too
+            cn += __popc(cb);
             qh += 32;
             qn -= 32;
           }
         }
       }
       __syncwarp();
-      if (lane < qn) {
-        const int o = queue[(qh + lane) & (FAST_QLEN - 1)];
-        const int m = fast_m_exact<TP>(tile + o);
-        mm[o] = (uint8_t)((m > t) ? m : 0);
+      {
+        bool cr = false;
+        int o = 0;
+        if (lane < qn) {
+          o = queue[(qh + lane) & (FAST_QLEN - 1)];
+          const int m = fast_m_exact<TP>(tile + o);
+          cr = m > t;
+          mm[o] = (uint8_t)(cr ? m : 0);
+        }
+        const unsigned cb = __ballot_sync(0xffffffffu, cr);
+        if (cr) clist[cn + __popc(cb & ((1u << lane) - 1u))] = (unsigned short)o;
+        cn += __popc(cb);
       }
       qh = 0;
       qn = 0;
     }
     __syncwarp();
-    // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) + order-preserving
-    // compaction: one ballot per row sweep, running offset.
-    {
-      const uint8_t* q = mm + 3 * tp + sh + 3 + lane;
-      for (int y = 3; y < rh - 3; ++y, q += tp) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (h == 1 && !wide) break;
-          bool keep = false;
-          int m = 0;
-          if (3 + lane + 32 * h < rw - 3) {
-            const uint8_t* qq = q + 32 * h;
-            m = qq[0];
-            if (m > 0) {   // m > t
-              const int n0 = max(max((int)qq[-tp - 1], (int)qq[-tp]), (int)qq[-tp + 1]);
-              const int n1 = max(max((int)qq[-1], (int)qq[1]), (int)qq[tp - 1]);
-              const int n2 = max((int)qq[tp], (int)qq[tp + 1]);
-              const int nmax = max(max(n0, n1), n2);
-              keep = m > max(nmax, 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t else 0)
-            }
-          }
-          const unsigned bal = __ballot_sync(0xffffffffu, keep);
-          if (keep) out[total + __popc(bal & ((1u << lane) - 1u))] = pack_kp(cd.x0 + 3 + lane + 32 * h, cd.y0 + y, m - 1);
-          total += __popc(bal);
-        }
+    // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) over the corner list, 32
+    // corners at a time, + order-preserving compaction (one ballot per batch, running offset).
+    for (int base = 0; base < cn; base += 32) {
+      bool keep = false;
+      int m = 0, o = 0;
+      if (base + lane < cn) {
+        o = clist[base + lane];
+        const uint8_t* qq = mm + o;
+        m = qq[0];
+        const int n0 = max(max((int)qq[-tp - 1], (int)qq[-tp]), (int)qq[-tp + 1]);
+        const int n1 = max(max((int)qq[-1], (int)qq[1]), (int)qq[tp - 1]);
+        const int n2 = max((int)qq[tp], (int)qq[tp + 1]);
+        keep = m > max(max(max(n0, n1), n2), 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t, else 0)
       }
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int y = o / tp, x = o - y * tp - sh;
+        out[total + __popc(bal & ((1u << lane) - 1u))] = pack_kp(cd.x0 + x, cd.y0 + y, m - 1);
+      }
+      total += __popc(bal);
     }
+    cn = 0;
     __syncwarp();
   }
   if (lane == 0) cellcnt[(size_t)f * ncells + cell] = total;
