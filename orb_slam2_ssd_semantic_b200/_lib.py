@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libb200orb.so")
+# B200ORB_LIB: development override (e.g. the clock-instrumented build `make timing` produces)
+_SO = os.environ.get("B200ORB_LIB") or os.path.join(_HERE, "libb200orb.so")
 
 
 class B200OrbError(RuntimeError):

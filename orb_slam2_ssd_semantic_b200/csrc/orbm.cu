@@ -85,6 +85,16 @@ int launch_match_last_unfused(const CurView& cv_in, const LastView& lv, const Ma
 
 extern "C" {
 
+#ifdef B200ORB_TIMING
+int orbm_debug_read(unsigned long long* out16) {   // profiling builds only: phase cycle counters of k_match_last_fused
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_mf_dbg, sizeof(unsigned long long) * 16) != cudaSuccess) return B200ORB_ECUDA;
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(g_mf_dbg, z, sizeof(z));
+  return B200ORB_OK;
+}
+#endif
+
 int orbm_hamming(const uint8_t a[32], const uint8_t b[32]) {   // DescriptorDistance, src/ORBmatcher.cc:1968-1984
   int d = 0;
   for (int i = 0; i < 32; i += 4) {

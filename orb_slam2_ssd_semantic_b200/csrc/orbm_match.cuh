@@ -318,17 +318,27 @@ __global__ void __launch_bounds__(32) k_resolve_last(CurView cv, LastView lv, Ma
 // other warps refill while warp 0 resolves.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int MF_THREADS = 512;
-constexpr int MF_QC = 30;   // queries per chunk: two per producer warp (15 producers + the resolving warp)
+constexpr int MF_RING = 64;   // candidate lists in flight between the producer warps and the resolving warp
+constexpr int MF_LSTR = LCAP + 1;   // slot stride in words: odd, so 32 lanes walking 32 lists hit 32 banks
 
-// grid-build scratch (one counter per cell), reused as the candidate ring: 2 x MF_QC lists + lengths + claim flags
+// grid-build scratch (one counter per cell), reused as the candidate ring: MF_RING lists + lengths, claim flags, ready flags
 __host__ __device__ inline size_t mf_ring_bytes() {
-  const size_t ring = (size_t)2 * MF_QC * LCAP * 4 + (size_t)4 * MF_QC * 4, grid = (size_t)GRID_CELLS * 4;
+  const size_t ring = (size_t)MF_RING * MF_LSTR * 4 + (size_t)3 * MF_RING * 4, grid = (size_t)GRID_CELLS * 4;
   return ((ring > grid ? ring : grid) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t mf_smem_bytes(int cmax, int lmax) {
   return (size_t)(GRID_CELLS + 1) * 4 + mf_ring_bytes() + (size_t)cmax * (4 + 4 + 4 + 4 + 4 + 32 + 4 + 1) +
          (size_t)lmax * 20 + 64;
 }
+
+#ifdef B200ORB_TIMING
+__device__ unsigned long long g_mf_dbg[16];
+#define MF_T(var) const long long var = clock64()
+#define MF_ADD(slot, v) atomicAdd(&g_mf_dbg[slot], (unsigned long long)(v))
+#else
+#define MF_T(var)
+#define MF_ADD(slot, v)
+#endif
 
 __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, LastView lv, MatchCam cam, ListView lists,
                                                                  int* accepted, int* cur2last, int* nmatch, int cmax,
@@ -337,8 +347,8 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   __shared__ int ws[33];
   __shared__ int s_hist[ORBM_HISTO_LENGTH];
   __shared__ int s_keep[3];
-  __shared__ int s_nacc, s_pruned;
-  const int p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+  __shared__ int s_nacc, s_pruned, s_next, s_consumed;
+  const int p = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int nc = cv.n[p], nl = lv.n[p];
   const size_t co = (size_t)p * cv.stride, lo = (size_t)p * lv.stride;
   // carve shared memory
@@ -360,6 +370,7 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
   uint8_t* taken = q;
   const int* cobs = cv.obs ? cv.obs + co : nullptr;
 
+  MF_T(T0);
   // ---- stage the current frame -------------------------------------------------------------------------------------
   for (int j = tid; j < nc; j += nthr) {
     s_x[j] = cv.x[co + j]; s_y[j] = cv.y[co + j]; s_ur[j] = cv.uright[co + j]; s_oct[j] = cv.oct[co + j];
@@ -412,6 +423,7 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
     }
   }
   __syncthreads();
+  MF_T(T1);
   WalkCtx g;
   g.off = s_off; g.idx = s_idx; g.x = s_x; g.y = s_y; g.uright = s_ur; g.oct = s_oct; g.obs = cobs;
   g.desc = reinterpret_cast<const uint8_t*>(s_desc);
@@ -434,102 +446,175 @@ __global__ void __launch_bounds__(MF_THREADS) k_match_last_fused(CurView cv, Las
     q_lv[i] = packed;
   }
   __syncthreads();
-  // ---- K8b + K9, pipelined through a double-buffered shared-memory ring ------------------------------------------------
-  // Chunk c = queries [c*MF_QC, (c+1)*MF_QC).  In step c the producer warps (1..15) build the candidate lists of chunk c
-  // straight into ring[c & 1] (two queries per warp) while warp 0 resolves chunk c-1 from ring[(c-1) & 1] in query
-  // order -- the only loop-carried state (claimed current keypoints) lives in that one warp.  One barrier per step.
-  unsigned* ring = reinterpret_cast<unsigned*>(s_cur);            // 2 x MF_QC x LCAP words (grid scratch + pad)
-  int* rcnt = reinterpret_cast<int*>(ring + 2 * MF_QC * LCAP);     // 2 x MF_QC list lengths (negative: overflowed)
-  int* robs = rcnt + 2 * MF_QC;                                     // 2 x MF_QC "query claims its match" flags
-  const int nchunk = (nl + MF_QC - 1) / MF_QC;
+  // ---- K8b + K9, decoupled through a shared-memory ring of MF_RING candidate lists ------------------------------------
+  // Producer warps (1..15) take queries in order from a counter, build the candidate list of query i in slot i % MF_RING
+  // and publish it (ready[slot] = i + 1); warp 0 resolves the queries in order -- the only loop-carried state (claimed
+  // current keypoints) lives in that one warp -- and frees the slots (s_consumed).  No block barrier inside: an
+  // expensive window only delays its own warp.
+  unsigned* ring = reinterpret_cast<unsigned*>(s_cur);   // MF_RING x MF_LSTR words (grid scratch region)
+  int* rcnt = reinterpret_cast<int*>(ring + MF_RING * MF_LSTR);   // list lengths (negative: overflowed)
+  int* robs = rcnt + MF_RING;                                   // "query claims its match" flags
+  volatile int* ready = robs + MF_RING;                         // i + 1 once slot i % MF_RING holds query i
   const int* lobs = lv.obs ? lv.obs + lo : nullptr;
   int* acc = accepted + lo;
   int n_acc = 0;
-  const uint4* dbase = reinterpret_cast<const uint4*>(lv.desc + lo * 32);
-  const int nprod = nwarp - 1;
-  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;   // producer: descriptor of its next query, fetched one query ahead
-  if (warp > 0 && warp - 1 < nl) { n0 = __ldg(dbase + 2 * (size_t)(warp - 1)); n1 = __ldg(dbase + 2 * (size_t)(warp - 1) + 1); }
-  for (int c = 0; c <= nchunk; ++c) {
-    if (warp > 0) {
-      if (c < nchunk) {
-        const int q0 = c * MF_QC;
-        unsigned* rb = ring + (c & 1) * MF_QC * LCAP;
-        for (int t = warp - 1; t < MF_QC; t += nprod) {
-          const int i = q0 + t;
-          if (i >= nl) break;
-          const uint4 d0 = n0, d1 = n1;
-          {   // next query of this warp: t + nprod in this chunk, else (warp - 1) in the next chunk
-            const int tn = t + nprod;
-            const int in = (tn < MF_QC) ? q0 + tn : q0 + MF_QC + (warp - 1);
-            if (in < nl) { n0 = __ldg(dbase + 2 * (size_t)in); n1 = __ldg(dbase + 2 * (size_t)in + 1); }
-          }
-          int cnt = 0;
-          const int packed = q_lv[i];
-          if (packed >> 16) {
-            QueryGeom qg;
-            qg.u = q_u[i]; qg.v = q_v[i]; qg.r = q_r[i]; qg.rr = qg.r; qg.ur = q_ur[i];
-            qg.min_level = (packed & 0xff) - 1; qg.max_level = ((packed >> 8) & 0xff) - 1;
-            unsigned* list = rb + t * LCAP;
-            cnt = warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
-              if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
-            });
-          }
-          if (lane == 0) {
-            rcnt[(c & 1) * MF_QC + t] = (cnt > LCAP) ? -cnt : cnt;
-            robs[(c & 1) * MF_QC + t] = (lobs ? lobs[i] : cam.last_obs_default) > 0;
-          }
-        }
+  for (int j = tid; j < MF_RING; j += nthr) ready[j] = 0;
+  if (tid == 0) { s_next = 0; s_consumed = 0; }
+  __syncthreads();
+  MF_T(T2);
+#ifdef B200ORB_TIMING
+  long long tw_wait = 0, tw_walk = 0, tw_n = 0;
+#endif
+  if (warp > 0) {
+    const uint4* dbase = reinterpret_cast<const uint4*>(lv.desc + lo * 32);
+    for (;;) {
+      int i = 0;
+      if (lane == 0) i = atomicAdd(&s_next, 1);
+      i = __shfl_sync(0xffffffffu, i, 0);
+      if (i >= nl) break;
+      const int slot = i % MF_RING;
+      int cnt = 0;
+      const int packed = q_lv[i];
+      uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+      if (packed >> 16) { d0 = __ldg(dbase + 2 * (size_t)i); d1 = __ldg(dbase + 2 * (size_t)i + 1); }
+      int qobs = cam.last_obs_default;   // requested now, needed when the list is published
+      if (lobs && lane == 0) qobs = __ldg(lobs + i);
+      // slot still holds query i - MF_RING?  Every lane polls (one broadcast load per iteration, warp-uniform exit): a
+      // lane-0-only spin leaves the warp split in two for the whole walk below.
+      MF_T(Ta);
+      while (i - *(volatile int*)&s_consumed >= MF_RING) __nanosleep(32);
+      __syncwarp();
+      MF_T(Tb);
+      if (packed >> 16) {
+        QueryGeom qg;
+        qg.u = q_u[i]; qg.v = q_v[i]; qg.r = q_r[i]; qg.rr = qg.r; qg.ur = q_ur[i];
+        qg.min_level = (packed & 0xff) - 1; qg.max_level = ((packed >> 8) & 0xff) - 1;
+        unsigned* list = ring + slot * MF_LSTR;
+        cnt = warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
+          if (ord < LCAP) list[ord] = ((unsigned)dist << 20) | (unsigned)idx;
+        });
       }
-    } else if (c > 0) {
-      const int k = c - 1;
-      const int q0 = k * MF_QC, nq = min(MF_QC, nl - q0);
-      const unsigned* buf = ring + (k & 1) * MF_QC * LCAP;
-      const int* bcnt = rcnt + (k & 1) * MF_QC;
-      const int* bobs = robs + (k & 1) * MF_QC;
-      // entries of the NEXT query are fetched before the current one is resolved (they do not depend on the claims)
-      int cn_n = bcnt[0];
-      unsigned v0_n = buf[lane], v1_n = buf[lane + 32];
-      for (int t = 0; t < nq; ++t) {
-        const int i = q0 + t;
-        const int cn = cn_n;
-        const unsigned v0 = v0_n, v1 = v1_n;
-        if (t + 1 < nq) { cn_n = bcnt[t + 1]; v0_n = buf[(t + 1) * LCAP + lane]; v1_n = buf[(t + 1) * LCAP + lane + 32]; }
-        int best_idx = -1, best_dist = 256;
-        if (cn > 0) {
-          // key = dist << 18 | position << 12 | index (index < 4096, host-checked): one redux yields the first minimum
-          unsigned k0 = KEY_INF, k1 = KEY_INF;
-          if (lane < cn && !taken[v0 & 0xfffu]) k0 = ((v0 >> 20) << 18) | ((unsigned)lane << 12) | (v0 & 0xfffu);
-          if (lane + 32 < cn && !taken[v1 & 0xfffu]) k1 = ((v1 >> 20) << 18) | ((unsigned)(lane + 32) << 12) | (v1 & 0xfffu);
-          const unsigned m = __reduce_min_sync(0xffffffffu, min(k0, k1));
-          if (m != KEY_INF) { best_idx = (int)(m & 0xfffu); best_dist = (int)(m >> 18); }
-        } else if (cn < 0) {   // overflowed list: exact re-walk with the claimed filter
-          QueryGeom qg;
-          if (setup_last_query(cam, Tc, fwd, bwd, lv.xw + (lo + i) * 3, lv.oct[lo + i], qg)) {
-            const uint8_t* d = lv.desc + (lo + i) * 32;
-            const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
-            unsigned long long bk = ~0ull;
-            warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
-              if (!taken[idx]) { const unsigned long long kk = key64(dist, ord, idx); bk = (kk < bk) ? kk : bk; }
-            });
-            bk = warp_min64(bk);
-            if (bk != ~0ull) { best_idx = (int)(bk & 0x3fffffull); best_dist = (int)(bk >> 44); }
-          }
-        }
-        int a = -1;
-        if (best_idx >= 0 && best_dist <= ORBM_TH_HIGH) {
-          a = best_idx;
-          ++n_acc;
-          if (lane == 0) {
-            state[best_idx] = i;
-            if (bobs[t]) taken[best_idx] = 1;
-          }
-        }
-        if (lane == 0) acc[i] = a;
-        __syncwarp();
+      __syncwarp();
+      if (lane == 0) {
+        rcnt[slot] = (cnt > LCAP) ? -cnt : cnt;
+        robs[slot] = qobs > 0;
+        __threadfence_block();
+        ready[slot] = i + 1;
       }
+#ifdef B200ORB_TIMING
+      tw_wait += Tb - Ta; tw_walk += clock64() - Tb; ++tw_n;
+#endif
     }
-    __syncthreads();
+#ifdef B200ORB_TIMING
+    if (warp == 1 && lane == 0 && blockIdx.x == 0) { MF_ADD(4, tw_wait); MF_ADD(5, tw_walk); MF_ADD(6, tw_n); MF_ADD(7, clock64() - T2); }
+#endif
+  } else {
+    // Resolving warp: 32 consecutive queries per step, lane = query.  Every lane picks the first minimum of its own
+    // list among the keypoints not claimed so far (speculatively ignoring the other lanes of the step).  A pick is
+    // final when no earlier lane of the step claims the same keypoint; all lanes before the first conflicting one are
+    // therefore final, the rest pick again in the next round (at least the first open lane finishes per round, and a
+    // conflict needs two map points choosing the same keypoint, so one or two rounds are the rule).  The sequential
+    // semantics of the reference loop (src/ORBmatcher.cc:1612-1698) are preserved exactly: a claimed keypoint is
+    // invisible to later queries, an unclaimed assignment is overwritten by the later query (atomicMax on the query
+    // index).  Nothing on this path touches global memory.
+    for (int base = 0; base < nl; base += 32) {
+      const int i = base + lane;
+      const bool active = i < nl;
+      const int slot = i % MF_RING;
+      {
+        MF_T(Tc0);
+        while (!__all_sync(0xffffffffu, !active || ready[slot] == i + 1)) __nanosleep(20);
+#ifdef B200ORB_TIMING
+        tw_wait += clock64() - Tc0;
+#endif
+      }
+      __syncwarp();
+      const int cn = active ? rcnt[slot] : 0;
+      const int claims = active ? robs[slot] : 0;
+      const unsigned* list = ring + slot * MF_LSTR;
+      int a = -1;
+      if (__any_sync(0xffffffffu, cn < 0)) {
+        // a list of this step overflowed LCAP (rare): resolve the 32 queries one after the other, exact re-walk for
+        // the overflowed ones
+        for (int t = 0; t < 32 && base + t < nl; ++t) {
+          const int it = base + t, st_ = it % MF_RING;
+          const int cnt_t = __shfl_sync(0xffffffffu, cn, t);
+          int best_idx = -1, best_dist = 256;
+          if (cnt_t > 0) {
+            const unsigned v0 = ring[st_ * MF_LSTR + lane], v1 = ring[st_ * MF_LSTR + lane + 32];
+            unsigned k0 = KEY_INF, k1 = KEY_INF;
+            if (lane < cnt_t && !taken[v0 & 0xfffu]) k0 = ((v0 >> 20) << 18) | ((unsigned)lane << 12) | (v0 & 0xfffu);
+            if (lane + 32 < cnt_t && !taken[v1 & 0xfffu]) k1 = ((v1 >> 20) << 18) | ((unsigned)(lane + 32) << 12) | (v1 & 0xfffu);
+            const unsigned m = __reduce_min_sync(0xffffffffu, min(k0, k1));
+            if (m != KEY_INF) { best_idx = (int)(m & 0xfffu); best_dist = (int)(m >> 18); }
+          } else if (cnt_t < 0) {
+            QueryGeom qg;
+            if (setup_last_query(cam, Tc, fwd, bwd, lv.xw + (lo + it) * 3, lv.oct[lo + it], qg)) {
+              const uint8_t* d = lv.desc + (lo + it) * 32;
+              const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(d)), d1 = __ldg(reinterpret_cast<const uint4*>(d) + 1);
+              unsigned long long bk = ~0ull;
+              warp_walk(g, qg, d0, d1, [&](int ord, int idx, int dist) {
+                if (!taken[idx]) { const unsigned long long kk = key64(dist, ord, idx); bk = (kk < bk) ? kk : bk; }
+              });
+              bk = warp_min64(bk);
+              if (bk != ~0ull) { best_idx = (int)(bk & 0x3fffffull); best_dist = (int)(bk >> 44); }
+            }
+          }
+          const bool acc_t = best_idx >= 0 && best_dist <= ORBM_TH_HIGH;
+          if (acc_t) {
+            ++n_acc;
+            if (lane == t) {
+              a = best_idx;
+              state[best_idx] = it;
+              if (claims) taken[best_idx] = 1;
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        unsigned open = __ballot_sync(0xffffffffu, active && cn > 0);
+        while (open) {
+          int pick = -1;
+          if ((open >> lane) & 1u) {
+            unsigned best = KEY_INF;   // dist << 18 | position << 12 | index: the first minimum in list order
+            for (int e = 0; e < cn; ++e) {
+              const unsigned v = list[e];
+              if (!taken[v & 0xfffu]) best = min(best, ((v >> 20) << 18) | ((unsigned)e << 12) | (v & 0xfffu));
+            }
+            if (best != KEY_INF && (int)(best >> 18) <= ORBM_TH_HIGH) pick = (int)(best & 0xfffu);
+          }
+          // equal picks among the open lanes; a lane conflicts when an EARLIER open lane that claims picked the same
+          const unsigned same = __match_any_sync(0xffffffffu, (pick >= 0) ? pick : -1 - lane);
+          const unsigned claimers = __ballot_sync(0xffffffffu, pick >= 0 && claims);
+          const bool conflict = pick >= 0 && (same & claimers & ((1u << lane) - 1u)) != 0u;
+          const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+          const unsigned fin = open & (cm ? ((1u << (__ffs(cm) - 1)) - 1u) : 0xffffffffu);
+          if ((fin >> lane) & 1u) {
+            a = pick;
+            if (pick >= 0) {
+              atomicMax(&state[pick], i);   // the later query of a step overwrites an unclaimed assignment
+              if (claims) taken[pick] = 1;
+            }
+          }
+          n_acc += __popc(__ballot_sync(0xffffffffu, ((fin >> lane) & 1u) && pick >= 0));
+          open &= ~fin;
+          __syncwarp();
+        }
+      }
+      if (active) q_lv[i] = a;   // accepted index, staged in shared memory (q_lv[i] was consumed by query i's producer)
+      __syncwarp();
+      if (lane == 0) *(volatile int*)&s_consumed = min(base + 32, nl);
+    }
   }
+#ifdef B200ORB_TIMING
+  if (tid == 0 && blockIdx.x == 0) { MF_ADD(8, tw_wait); MF_ADD(9, clock64() - T2); }
+#endif
+  __syncthreads();
+  for (int i = tid; i < nl; i += nthr) acc[i] = q_lv[i];
+  MF_T(T3);
+#ifdef B200ORB_TIMING
+  if (tid == 0 && blockIdx.x == 0) { MF_ADD(0, T1 - T0); MF_ADD(1, T2 - T1); MF_ADD(2, T3 - T2); MF_ADD(10, 1); }
+#endif
   if (tid == 0) s_nacc = n_acc;
   __syncthreads();
   // ---- K10 rotation consistency -------------------------------------------------------------------------------------

@@ -832,6 +832,31 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
     ring[j][0] = r.h02 & 0xffffu; ring[j][2] = r.h02 >> 16; ring[j][1] = r.h13 & 0xffffu; ring[j][3] = r.h13 >> 16;
   }
   for (int yb = y0; yb < y1; yb += 7) {
+    if (yb + 7 <= y1) {
+      // full block: all 21 source words of the 7 new rows are requested before the first one is used, so a warp keeps
+      // 7 rows (2.7 KB) in flight instead of one -- the walk is latency-bound otherwise
+      unsigned W[7][3];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const unsigned* p = reinterpret_cast<const unsigned*>(s + (size_t)reflect101(yb + k + 3, h) * spitch + x0 - 4);
+        W[k][0] = __ldg(p); W[k][1] = __ldg(p + 1); W[k][2] = __ldg(p + 2);
+      }
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        const HRow r = blur_hrow_words(W[k][0], W[k][1], W[k][2]);
+        ring[(k + 6) % 7][0] = r.h02 & 0xffffu; ring[(k + 6) % 7][2] = r.h02 >> 16;
+        ring[(k + 6) % 7][1] = r.h13 & 0xffffu; ring[(k + 6) % 7][3] = r.h13 >> 16;
+        unsigned out = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned v = 18u * (ring[k % 7][i] + ring[(k + 6) % 7][i]) + 34u * (ring[(k + 1) % 7][i] + ring[(k + 5) % 7][i]) +
+                             48u * (ring[(k + 2) % 7][i] + ring[(k + 4) % 7][i]) + 56u * ring[(k + 3) % 7][i];
+          out |= ((v + 32768u) >> 16) << (8 * i);
+        }
+        *reinterpret_cast<unsigned*>(d + (size_t)(yb + k) * dpitch + x0) = out;   // dst pitch is a multiple of 16
+      }
+      continue;
+    }
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
       const int y = yb + k;
