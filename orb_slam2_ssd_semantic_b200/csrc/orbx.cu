@@ -217,7 +217,7 @@ int orbx::ensure_geometry(int r, int c, int F) {
     fast_clist_cap = align_up(std::max(det, 8), 8);   // every detection pixel of a cell may be a corner
     fast_tp = (rwm + 3 <= FAST_TP_SMALL) ? FAST_TP_SMALL : FAST_TP_BIG;
     fast_rows_max = rhm;
-    fast_smem = (size_t)FAST_WARPS * (2 * rhm * fast_tp + 2 * fast_clist_cap);
+    fast_smem = (size_t)FAST_WARPS * (2 * rhm * fast_tp + 2 * FAST_QLEN + 2 * fast_clist_cap);
     if (fast_smem > 48 * 1024) {
       B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
       B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));

@@ -150,19 +150,19 @@ constexpr int FAST_QLEN = 64;      // per-warp ring of pixels that passed the co
 // m(p) of one pixel.  Packing: one IMAD per ring pixel gives lo16 = 256 + (c - r), hi16 = 256 + (r - c) (biased,
 // both in [1, 511], so no borrow crosses the halves); min3/max3 on s16x2 then evaluate the bright and the dark
 // arcs at once: a3[i] = min(v[i..i+2]), a9[i] = min(a3[i], a3[i+3], a3[i+6]) = min over the 9-arc starting at i.
-template <int TP>
+// P = row pitch of the tile in bytes.
+template <int P>
 __device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
-  constexpr int tp = TP;
   const int bias = 256 * 65537 - (int)c[0] * 65535;
   unsigned v[16];
-  v[0] = (unsigned)((int)c[3 * tp] * 65535 + bias);       v[1] = (unsigned)((int)c[3 * tp + 1] * 65535 + bias);
-  v[2] = (unsigned)((int)c[2 * tp + 2] * 65535 + bias);   v[3] = (unsigned)((int)c[tp + 3] * 65535 + bias);
-  v[4] = (unsigned)((int)c[3] * 65535 + bias);            v[5] = (unsigned)((int)c[-tp + 3] * 65535 + bias);
-  v[6] = (unsigned)((int)c[-2 * tp + 2] * 65535 + bias);  v[7] = (unsigned)((int)c[-3 * tp + 1] * 65535 + bias);
-  v[8] = (unsigned)((int)c[-3 * tp] * 65535 + bias);      v[9] = (unsigned)((int)c[-3 * tp - 1] * 65535 + bias);
-  v[10] = (unsigned)((int)c[-2 * tp - 2] * 65535 + bias); v[11] = (unsigned)((int)c[-tp - 3] * 65535 + bias);
-  v[12] = (unsigned)((int)c[-3] * 65535 + bias);          v[13] = (unsigned)((int)c[tp - 3] * 65535 + bias);
-  v[14] = (unsigned)((int)c[2 * tp - 2] * 65535 + bias);  v[15] = (unsigned)((int)c[3 * tp - 1] * 65535 + bias);
+  v[0] = (unsigned)((int)c[3 * P] * 65535 + bias);       v[1] = (unsigned)((int)c[3 * P + 1] * 65535 + bias);
+  v[2] = (unsigned)((int)c[2 * P + 2] * 65535 + bias);   v[3] = (unsigned)((int)c[P + 3] * 65535 + bias);
+  v[4] = (unsigned)((int)c[3] * 65535 + bias);           v[5] = (unsigned)((int)c[-P + 3] * 65535 + bias);
+  v[6] = (unsigned)((int)c[-2 * P + 2] * 65535 + bias);  v[7] = (unsigned)((int)c[-3 * P + 1] * 65535 + bias);
+  v[8] = (unsigned)((int)c[-3 * P] * 65535 + bias);      v[9] = (unsigned)((int)c[-3 * P - 1] * 65535 + bias);
+  v[10] = (unsigned)((int)c[-2 * P - 2] * 65535 + bias); v[11] = (unsigned)((int)c[-P - 3] * 65535 + bias);
+  v[12] = (unsigned)((int)c[-3] * 65535 + bias);         v[13] = (unsigned)((int)c[P - 3] * 65535 + bias);
+  v[14] = (unsigned)((int)c[2 * P - 2] * 65535 + bias);  v[15] = (unsigned)((int)c[3 * P - 1] * 65535 + bias);
   unsigned a3[16], a9[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) a3[i] = __vimin3_s16x2(v[i], v[(i + 1) & 15], v[(i + 2) & 15]);
@@ -180,27 +180,30 @@ __device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
   return max(0, max((int)(m0 & 0xffffu), (int)(m0 >> 16)) - 256);
 }
 
-// One WARP per (cell, frame), 8 cells per CTA, no block-level synchronisation: the warp loads its ROI, walks the
-// rows (lane = column; a second sweep covers cells wider than 32), and compacts the survivors with a ballot per row
-// and a running offset -- row-major order for free.  Per-warp shared memory: ROI tile + score map, pitch TP.
+// One WARP per (cell, frame), 8 cells per CTA, no block-level synchronisation.  Per-warp shared memory: the ROI and
+// its score map interleaved row by row (pixel row y at y*2*TP, its score row at y*2*TP + TP, so one base register and
+// compile-time offsets address both), a 64-entry ring of pixels that passed the compass test, and the list of corners.
+//   sweep   lane = column, row by row (a second sweep covers cells wider than 32): compass test; failing pixels get
+//           score 0, passing ones are queued;
+//   dense   whenever 32 pixels are queued, a full warp evaluates their exact m(p); corners (m > t) go to the corner
+//           list -- the queue is FIFO over a row-major sweep, so the list is row-major as well;
+//   NMS     32 corners at a time: strict 3x3 maximum, order-preserving compaction into the cell's output segment.
 // `aligned` (host-checked): level rows are 4-byte aligned, so the ROI is fetched as aligned 32-bit words and kept
 // at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).
 template <int TP>
-__global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
-                                                             int ncells, int slots_per_frame, int ini_th,
-                                                             int min_th, unsigned* __restrict__ cand,
-                                                             int* __restrict__ cellcnt, int aligned, int rows_max,
-                                                             int clist_cap) {
+__global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
+                                                                int ncells, int slots_per_frame, int ini_th,
+                                                                int min_th, unsigned* __restrict__ cand,
+                                                                int* __restrict__ cellcnt, int aligned, int rows_max,
+                                                                int clist_cap) {
   extern __shared__ __align__(16) uint8_t fsm[];
-  constexpr int tp = TP;
+  constexpr int P = 2 * TP;   // row pitch of the interleaved tile
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int cell = blockIdx.x * FAST_WARPS + w, f = blockIdx.y;
   if (cell >= ncells) return;
-  __shared__ unsigned short s_queue[FAST_WARPS][FAST_QLEN];
-  unsigned short* queue = s_queue[w];
-  uint8_t* tile = fsm + (size_t)w * (2 * rows_max * tp + 2 * clist_cap);
-  uint8_t* mm = tile + (size_t)rows_max * tp;
-  unsigned short* clist = reinterpret_cast<unsigned short*>(mm + (size_t)rows_max * tp);   // corners at t, row-major
+  uint8_t* tile = fsm + (size_t)w * (rows_max * P + 2 * FAST_QLEN + 2 * clist_cap);
+  unsigned short* queue = reinterpret_cast<unsigned short*>(tile + (size_t)rows_max * P);
+  unsigned short* clist = queue + FAST_QLEN;   // corners at t, row-major
   const CellDesc cd = cells[cell];
   const int l = cd.level, rw = cd.rw, rh = cd.rh;
   const int pitch = pyr.pitch[l];
@@ -212,87 +215,78 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
       if (nw <= 16) {                      // two rows per step: lanes 0-15 / 16-31
         const int k = lane & 15, half = lane >> 4;
         for (int y = half; y < rh; y += 2)
-          if (k < nw) reinterpret_cast<unsigned*>(tile + y * tp)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
+          if (k < nw) reinterpret_cast<unsigned*>(tile + y * P)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
       } else {
         for (int y = 0; y < rh; ++y)
           for (int k = lane; k < nw; k += 32)
-            reinterpret_cast<unsigned*>(tile + y * tp)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
+            reinterpret_cast<unsigned*>(tile + y * P)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
       }
     } else {
       for (int y = 0; y < rh; ++y)
-        for (int x = lane; x < rw; x += 32) tile[y * tp + x] = __ldg(img + (size_t)y * pitch + x);
+        for (int x = lane; x < rw; x += 32) tile[y * P + x] = __ldg(img + (size_t)y * pitch + x);
     }
     // only the one-pixel frame around the detection range is read without being written: clear it
-    for (int i = lane; i < rw; i += 32) { mm[2 * tp + sh + i] = 0; mm[(rh - 3) * tp + sh + i] = 0; }
-    for (int i = lane; i < rh; i += 32) { mm[i * tp + sh + 2] = 0; mm[i * tp + sh + rw - 3] = 0; }
+    for (int i = lane; i < rw; i += 32) { tile[2 * P + TP + sh + i] = 0; tile[(rh - 3) * P + TP + sh + i] = 0; }
+    for (int i = lane; i < rh; i += 32) { tile[i * P + TP + sh + 2] = 0; tile[i * P + TP + sh + rw - 3] = 0; }
   }
   __syncwarp();
   unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
   const bool wide = rw - 6 > 32;
+  const unsigned lt_mask = (1u << lane) - 1u;
   int total = 0;
-  int qh = 0, qn = 0;   // candidate ring (warp-uniform head / fill)
-  int cn = 0;           // corners at t found so far (warp-uniform)
   // pass 0: everything at ini_th (pixels with m <= ini_th can neither be corners nor outscore one at that threshold);
   // pass 1 (:821, only when the cell is EMPTY AFTER non-max suppression): the same at min_th.
   for (int pass = 0; pass < 2 && total == 0; ++pass) {
     const int t = pass ? min_th : ini_th;
     if (pass == 1 && ini_th == min_th) break;
+    int qh = 0, qn = 0;   // candidate ring (warp-uniform head / fill)
+    int cn = 0;           // corners at t found so far (warp-uniform)
+    // exact m of the queued pixel `o` (tile offset) of the lanes with `on`, score map + corner list update
+    auto dense = [&](int o, bool on) {
+      bool cr = false;
+      if (on) {
+        const int m = fast_m_exact<P>(tile + o);
+        cr = m > t;
+        tile[o + TP] = (uint8_t)(cr ? m : 0);
+      }
+      const unsigned cb = __ballot_sync(0xffffffffu, cr);
+      if (cr) clist[cn + __popc(cb & lt_mask)] = (unsigned short)o;
+      cn += __popc(cb);
+    };
     {
-      // Sweep 1 (lane = column): the compass test in packed form -- a 9-arc always holds one pixel of each opposite
-      // compass pair, and all its pixels lie on the same side of the centre, so
-      //   min(max(v0, v8), max(v4, v12)) > 256 + t  in either half
-      // is necessary for a corner at t.  Pixels that fail get score 0 right away; the others are queued (tile offset)
-      // and their exact m is evaluated 32 at a time by full warps, whatever rows/columns they came from.
+      // The compass test in packed form: a 9-arc always holds one pixel of each opposite compass pair, and all its
+      // pixels lie on the same side of the centre, so min(max(v0, v8), max(v4, v12)) > 256 + t in either half is
+      // necessary for a corner at t.
       const unsigned kq = (unsigned)(0x7fff - 256 - t) * 0x10001u;
-      const int off0 = 3 * tp + sh + 3 + lane;
-      for (int y = 3; y < rh - 3; ++y) {
+      uint8_t* rowp = tile + 3 * P + sh + 3 + lane;
+      const int colmax = rw - 6;   // detection columns
+      for (int y = 3; y < rh - 3; ++y, rowp += P) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (h == 1 && !wide) break;
-          const int off = off0 + (y - 3) * tp + 32 * h;
+          uint8_t* cc = rowp + 32 * h;
           bool hit = false;
-          if (3 + lane + 32 * h < rw - 3) {
-            const uint8_t* cc = tile + off;
+          if (lane + 32 * h < colmax) {
             const int bias = 256 * 65537 - (int)cc[0] * 65535;
-            const unsigned v0 = (unsigned)((int)cc[3 * tp] * 65535 + bias), v8 = (unsigned)((int)cc[-3 * tp] * 65535 + bias);
+            const unsigned v0 = (unsigned)((int)cc[3 * P] * 65535 + bias), v8 = (unsigned)((int)cc[-3 * P] * 65535 + bias);
             const unsigned v4 = (unsigned)((int)cc[3] * 65535 + bias), v12 = (unsigned)((int)cc[-3] * 65535 + bias);
             const unsigned qv = __vmins2(__vmaxs2(v0, v8), __vmaxs2(v4, v12));
-            hit = ((qv + kq) & 0x80008000u) != 0u;    // halves are in [1,511]: no carry between them
-            if (!hit) mm[off] = 0;
+            hit = ((qv + kq) & 0x80008000u) != 0u;   // halves are in [1,511]: no carry between them
+            if (!hit) cc[TP] = 0;
           }
           const unsigned bal = __ballot_sync(0xffffffffu, hit);
-          if (hit) queue[(qh + qn + __popc(bal & ((1u << lane) - 1u))) & (FAST_QLEN - 1)] = (unsigned short)off;
+          if (hit) queue[(qh + qn + __popc(bal & lt_mask)) & (FAST_QLEN - 1)] = (unsigned short)(cc - tile);
           qn += __popc(bal);
           if (qn >= 32) {
             __syncwarp();
-            const int o = queue[(qh + lane) & (FAST_QLEN - 1)];
-            const int m = fast_m_exact<TP>(tile + o);
-            const bool cr = m > t;
-            mm[o] = (uint8_t)(cr ? m : 0);
-            const unsigned cb = __ballot_sync(0xffffffffu, cr);   // the queue is FIFO over a row-major sweep, so the
-            if (cr) clist[cn + __popc(cb & ((1u << lane) - 1u))] = (unsigned short)o;   // corner list is row-major too
-            cn += __popc(cb);
+            dense(queue[(qh + lane) & (FAST_QLEN - 1)], true);
             qh += 32;
             qn -= 32;
           }
         }
       }
       __syncwarp();
-      {
-        bool cr = false;
-        int o = 0;
-        if (lane < qn) {
-          o = queue[(qh + lane) & (FAST_QLEN - 1)];
-          const int m = fast_m_exact<TP>(tile + o);
-          cr = m > t;
-          mm[o] = (uint8_t)(cr ? m : 0);
-        }
-        const unsigned cb = __ballot_sync(0xffffffffu, cr);
-        if (cr) clist[cn + __popc(cb & ((1u << lane) - 1u))] = (unsigned short)o;
-        cn += __popc(cb);
-      }
-      qh = 0;
-      qn = 0;
+      dense((lane < qn) ? queue[(qh + lane) & (FAST_QLEN - 1)] : 0, lane < qn);
     }
     __syncwarp();
     // NMS (strict 3x3 maximum of the scores; a neighbour that is no corner at t scores 0) over the corner list, 32
@@ -302,21 +296,20 @@ __global__ void __launch_bounds__(FAST_THREADS) k_fast_cells(PyrView pyr, const 
       int m = 0, o = 0;
       if (base + lane < cn) {
         o = clist[base + lane];
-        const uint8_t* qq = mm + o;
+        const uint8_t* qq = tile + o + TP;
         m = qq[0];
-        const int n0 = max(max((int)qq[-tp - 1], (int)qq[-tp]), (int)qq[-tp + 1]);
-        const int n1 = max(max((int)qq[-1], (int)qq[1]), (int)qq[tp - 1]);
-        const int n2 = max((int)qq[tp], (int)qq[tp + 1]);
+        const int n0 = max(max((int)qq[-P - 1], (int)qq[-P]), (int)qq[-P + 1]);
+        const int n1 = max(max((int)qq[-1], (int)qq[1]), (int)qq[P - 1]);
+        const int n2 = max((int)qq[P], (int)qq[P + 1]);
         keep = m > max(max(max(n0, n1), n2), 1);   // score m-1 vs neighbour scores (m_q-1 if m_q > t, else 0)
       }
       const unsigned bal = __ballot_sync(0xffffffffu, keep);
       if (keep) {
-        const int y = o / tp, x = o - y * tp - sh;
-        out[total + __popc(bal & ((1u << lane) - 1u))] = pack_kp(cd.x0 + x, cd.y0 + y, m - 1);
+        const int y = o / P, x = o - y * P - sh;
+        out[total + __popc(bal & lt_mask)] = pack_kp(cd.x0 + x, cd.y0 + y, m - 1);
       }
       total += __popc(bal);
     }
-    cn = 0;
     __syncwarp();
   }
   if (lane == 0) cellcnt[(size_t)f * ncells + cell] = total;
