@@ -338,7 +338,8 @@ struct QtScratchView {
 struct QtSmem {   // carved from dynamic shared memory, cap entries each
   short4* box[2];
   int* cnt[2];
-  int* cc;        // [cap][4] child counts of nodes being split
+  int* cc;        // [cap][4] child counts (per quadrant) of every node of the current list
+  int* cc2;       // [cap][4] the same for the list being built (filled while the keypoints are re-homed)
   int* cpos;      // [cap][4] new list index of each child
   int* rk;        // processing rank or -1
   int* npos;      // new list index of untouched nodes
@@ -346,7 +347,7 @@ struct QtSmem {   // carved from dynamic shared memory, cap entries each
   int* pre;       // inclusive prefix of child counts by rank
 };
 
-__host__ __device__ inline size_t qt_smem_bytes(int cap) { return (size_t)cap * (2 * 8 + 2 * 4 + 16 + 16 + 4 * 4); }
+__host__ __device__ inline size_t qt_smem_bytes(int cap) { return (size_t)cap * (2 * 8 + 2 * 4 + 16 + 16 + 16 + 4 * 4); }
 
 __device__ __forceinline__ int qt_quadrant(short4 b, unsigned kp) {
   // DivideNode's assignment (:509-523); node boxes are relative to (minBorderX, minBorderY) = (16,16)
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
     S.cnt[0] = (int*)p; p += (size_t)qt_cap * 4;
     S.cnt[1] = (int*)p; p += (size_t)qt_cap * 4;
     S.cc = (int*)p; p += (size_t)qt_cap * 16;
+    S.cc2 = (int*)p; p += (size_t)qt_cap * 16;
     S.cpos = (int*)p; p += (size_t)qt_cap * 16;
     S.rk = (int*)p; p += (size_t)qt_cap * 4;
     S.npos = (int*)p; p += (size_t)qt_cap * 4;
@@ -462,9 +464,16 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
       S.cnt[0][p] = icnt[i];
     }
   }
+  for (int i = tid; i < nIni * 4; i += nthr) S.cc2[i] = 0;
   __syncthreads();
-  for (int k = tid; k < K; k += nthr) qnode[k] = S.npos[qnode[k]];
+  // compact the node ids and count, per node, the keypoints of each quadrant (the child populations of round 0)
+  for (int k = tid; k < K; k += nthr) {
+    const int p = S.npos[qnode[k]];
+    qnode[k] = p;
+    atomicAdd(&S.cc2[p * 4 + qt_quadrant(S.box[0][p], qkp[k])], 1);
+  }
   __syncthreads();
+  { int* t = S.cc; S.cc = S.cc2; S.cc2 = t; }   // S.cc aliased icnt until here
 
   // ---- rounds -------------------------------------------------------------------------------------------
   bool largest = false, finish = false;
@@ -503,14 +512,8 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
         }
       }
     }
-    for (int i = tid; i < n * 4; i += nthr) S.cc[i] = 0;
     __syncthreads();
-    // (2) child populations of every candidate
-    for (int k = tid; k < K; k += nthr) {
-      const int p = qnode[k];
-      if (S.rk[p] >= 0) atomicAdd(&S.cc[p * 4 + qt_quadrant(box[p], qkp[k])], 1);
-    }
-    __syncthreads();
+    // (2) the child populations S.cc[node][quadrant] were counted while the keypoints were re-homed last round
     // (3) inclusive prefix over processing order of the number of non-empty children
     for (int r = tid; r < m; r += nthr) {
       const int* c = &S.cc[S.byrank[r] * 4];
@@ -579,12 +582,18 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
       }
     }
     if (myexp) atomicAdd(&s_expand, myexp);
+    for (int i = tid; i < (TC + nUn) * 4; i += nthr) S.cc2[i] = 0;
     __syncthreads();
-    // (6) re-home the keypoints
+    // (6) re-home the keypoints; the same pass counts the quadrant populations inside the NEW nodes, i.e. the child
+    //     populations the next round needs (one pass over the keypoints per round instead of two)
     for (int k = tid; k < K; k += nthr) {
       const int p = qnode[k];
-      qnode[k] = (S.rk[p] >= 0) ? S.cpos[p * 4 + qt_quadrant(box[p], qkp[k])] : S.npos[p];
+      const unsigned kp = qkp[k];
+      const int np = (S.rk[p] >= 0) ? S.cpos[p * 4 + qt_quadrant(box[p], kp)] : S.npos[p];
+      qnode[k] = np;
+      atomicAdd(&S.cc2[np * 4 + qt_quadrant(nbox[np], kp)], 1);
     }
+    { int* t = S.cc; S.cc = S.cc2; S.cc2 = t; }
     n = TC + nUn;
     const int nToExpand = s_expand;
     cur ^= 1;
