@@ -250,6 +250,9 @@ int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u
  * src/Frame.cc:850-871), so the device gathers those pixels in place over PCIe.  orbs_set_full_depth_upload(h, 1)
  * forces the full upload (then orbs_device_inputs returns the converted f32 batch). */
 int orbs_set_full_depth_upload(orbs_t* h, int on);
+/* Frames per upload chunk of the host-buffer entries (default 128, at most 7 chunks per call): the extraction of a chunk
+ * starts as soon as it has arrived while the next one is still crossing PCIe. */
+int orbs_set_chunk_frames(orbs_t* h, int frames);
 /* Streaming form of orbs_track_batch_u16: enqueues uploads, kernels and result downloads on the handle's streams and
  * returns; the outputs are valid after orbs_sync(h).  All host buffers must be page-locked and stay untouched until
  * then.  Two handles used alternately keep two batches in flight, so the upload of batch k+1 and the download of

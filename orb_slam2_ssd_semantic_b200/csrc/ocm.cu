@@ -12,7 +12,9 @@
 //   scan sets    two open-addressing key sets per scan: occupied endpoints and free ray cells
 //   map          persistent open-addressing hash: key (3 x u16 OcTreeKey packed in u64) -> float log-odds, colour and
 //                the clamp-add summary (a, lo, hi) used by the multi-GPU merge
+#include <algorithm>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -75,6 +77,39 @@ struct LeafTable {
   long long mask;
 };
 
+struct KeySet {
+  unsigned long long* keys;
+  long long mask;
+  int* list;      // slots filled during this scan
+  int* count;
+};
+
+__device__ __forceinline__ long long set_insert(const KeySet& st, unsigned long long key) {
+  bool fresh;
+  const long long s = table_insert(st.keys, st.mask, key, &fresh);
+  if (s >= 0 && fresh) st.list[atomicAdd(st.count, 1)] = (int)s;
+  return s;
+}
+
+// Everything one keyframe needs between back-projection and the map update.  A batch of keyframes runs every stage
+// up to the key sets as ONE launch (blockIdx.y = job); only the map update itself is ordered keyframe by keyframe.
+struct KfScratch {
+  LeafTable leaf;
+  int *pix_slot, *bucket, *voxlist;
+  int* counters;   // [0] pixels, [1] voxels (= points), [2] occupied keys, [3] free keys
+  float* pts;
+  uint8_t *pts_rgb, *pts_label;
+  KeySet occ, fre;
+  unsigned* occ_rgb;
+};
+struct KfJob {
+  OcmConst c;
+  const float* depth;
+  const uint8_t* rgb;
+  const uint8_t* label;
+  KfScratch s;
+};
+
 __device__ __forceinline__ bool backproject(const OcmConst& c, const float* __restrict__ depth, int pix, float& x,
                                             float& y, float& z) {
   const int m = pix / c.cols, n = pix - m * c.cols;
@@ -96,8 +131,14 @@ __device__ __forceinline__ unsigned long long leaf_key(const OcmConst& c, float 
 }
 
 // K11a: gate + VoxelGrid cell of every pixel
-__global__ void k_ocm_bin(OcmConst c, const float* __restrict__ depth, LeafTable lt, int* __restrict__ pix_slot,
-                          int* __restrict__ counters, int* __restrict__ voxlist, int* __restrict__ err) {
+__global__ void k_ocm_bin(const KfJob* __restrict__ jobs, int* __restrict__ err) {
+  const KfJob& J = jobs[blockIdx.y];
+  const OcmConst& c = J.c;
+  const float* __restrict__ depth = J.depth;
+  const LeafTable lt = J.s.leaf;
+  int* __restrict__ pix_slot = J.s.pix_slot;
+  int* __restrict__ counters = J.s.counters;
+  int* __restrict__ voxlist = J.s.voxlist;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= c.rows * c.cols) return;
   float x, y, z;
@@ -117,8 +158,11 @@ __global__ void k_ocm_bin(OcmConst c, const float* __restrict__ depth, LeafTable
 }
 
 // K11b: bucket ranges for the occupied cells (arbitrary order: the cloud is a set)
-__global__ void k_ocm_ranges(LeafTable lt, int* __restrict__ counters /*[0]=pixels,[1]=voxels*/,
-                             const int* __restrict__ voxlist) {
+__global__ void k_ocm_ranges(const KfJob* __restrict__ jobs) {
+  const KfJob& J = jobs[blockIdx.y];
+  const LeafTable lt = J.s.leaf;
+  int* __restrict__ counters = J.s.counters;   // [0]=pixels, [1]=voxels
+  const int* __restrict__ voxlist = J.s.voxlist;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
   const int s = voxlist[v];
@@ -126,7 +170,12 @@ __global__ void k_ocm_ranges(LeafTable lt, int* __restrict__ counters /*[0]=pixe
 }
 
 // K11c: scatter the pixel indices into their cell's bucket
-__global__ void k_ocm_scatter(int npix, const int* __restrict__ pix_slot, LeafTable lt, int* __restrict__ bucket) {
+__global__ void k_ocm_scatter(const KfJob* __restrict__ jobs) {
+  const KfJob& J = jobs[blockIdx.y];
+  const int npix = J.c.rows * J.c.cols;
+  const int* __restrict__ pix_slot = J.s.pix_slot;
+  const LeafTable lt = J.s.leaf;
+  int* __restrict__ bucket = J.s.bucket;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   const int s = pix_slot[pix];
@@ -135,10 +184,19 @@ __global__ void k_ocm_scatter(int npix, const int* __restrict__ pix_slot, LeafTa
 
 // K11d: per cell: restore pixel order, sequential float centroid (PCL VoxelGrid), transform to the world frame in
 // double (pcl::transformPointCloud), emit the point; also resets the cell's table entry for the next keyframe.
-__global__ void k_ocm_centroids(OcmConst c, const float* __restrict__ depth, const uint8_t* __restrict__ rgb,
-                                const uint8_t* __restrict__ label, LeafTable lt, const int* __restrict__ counters,
-                                const int* __restrict__ voxlist, int* __restrict__ bucket, float* __restrict__ pts,
-                                uint8_t* __restrict__ pts_rgb, uint8_t* __restrict__ pts_label) {
+__global__ void k_ocm_centroids(const KfJob* __restrict__ jobs) {
+  const KfJob& J = jobs[blockIdx.y];
+  const OcmConst& c = J.c;
+  const float* __restrict__ depth = J.depth;
+  const uint8_t* __restrict__ rgb = J.rgb;
+  const uint8_t* __restrict__ label = J.label;
+  const LeafTable lt = J.s.leaf;
+  const int* __restrict__ counters = J.s.counters;
+  const int* __restrict__ voxlist = J.s.voxlist;
+  int* __restrict__ bucket = J.s.bucket;
+  float* __restrict__ pts = J.s.pts;
+  uint8_t* __restrict__ pts_rgb = J.s.pts_rgb;
+  uint8_t* __restrict__ pts_label = J.s.pts_label;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
   const int s = voxlist[v];
@@ -171,10 +229,16 @@ __global__ void k_ocm_centroids(OcmConst c, const float* __restrict__ depth, con
 }
 
 // leaf <= 0: no VoxelGrid; every gated pixel is a point (used for the T-variant style clouds)
-__global__ void k_ocm_points_nofilter(OcmConst c, const float* __restrict__ depth, const uint8_t* __restrict__ rgb,
-                                      const uint8_t* __restrict__ label, int* __restrict__ counters,
-                                      float* __restrict__ pts, uint8_t* __restrict__ pts_rgb,
-                                      uint8_t* __restrict__ pts_label) {
+__global__ void k_ocm_points_nofilter(const KfJob* __restrict__ jobs) {
+  const KfJob& J = jobs[blockIdx.y];
+  const OcmConst& c = J.c;
+  const float* __restrict__ depth = J.depth;
+  const uint8_t* __restrict__ rgb = J.rgb;
+  const uint8_t* __restrict__ label = J.label;
+  int* __restrict__ counters = J.s.counters;
+  float* __restrict__ pts = J.s.pts;
+  uint8_t* __restrict__ pts_rgb = J.s.pts_rgb;
+  uint8_t* __restrict__ pts_label = J.s.pts_label;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= c.rows * c.cols) return;
   float x, y, z;
@@ -198,24 +262,16 @@ __device__ __forceinline__ unsigned long long pack_key(int kx, int ky, int kz) {
   return (unsigned long long)kx | ((unsigned long long)ky << 16) | ((unsigned long long)kz << 32);
 }
 
-struct KeySet {
-  unsigned long long* keys;
-  long long mask;
-  int* list;      // slots filled during this scan
-  int* count;
-};
-
-__device__ __forceinline__ long long set_insert(const KeySet& st, unsigned long long key) {
-  bool fresh;
-  const long long s = table_insert(st.keys, st.mask, key, &fresh);
-  if (s >= 0 && fresh) st.list[atomicAdd(st.count, 1)] = (int)s;
-  return s;
-}
-
 // K12/K13: per point -> occupied endpoint key, or (ground) the free cells along the ray (computeRayKeys)
-__global__ void k_ocm_scan_keys(OcmConst c, const int* __restrict__ counters, const float* __restrict__ pts,
-                                const uint8_t* __restrict__ pts_label, const uint8_t* __restrict__ pts_rgb,
-                                KeySet occ, unsigned* __restrict__ occ_rgb, KeySet fre, int* __restrict__ err) {
+__global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, int* __restrict__ err) {
+  const KfJob& J = jobs[blockIdx.y];
+  const OcmConst& c = J.c;
+  const int* __restrict__ counters = J.s.counters;
+  const float* __restrict__ pts = J.s.pts;
+  const uint8_t* __restrict__ pts_label = J.s.pts_label;
+  const uint8_t* __restrict__ pts_rgb = J.s.pts_rgb;
+  const KeySet occ = J.s.occ, fre = J.s.fre;
+  unsigned* __restrict__ occ_rgb = J.s.occ_rgb;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
   const float e[3] = {pts[(size_t)v * 3], pts[(size_t)v * 3 + 1], pts[(size_t)v * 3 + 2]};
@@ -310,7 +366,9 @@ __device__ __forceinline__ void map_update(const MapView& m, const OcmConst& c, 
 
 // K14: free \ occupied get a miss, occupied get a hit (MapDrawer.cc:1007-1022).  Both walk the scan's slot lists
 // (no table sweep) and clear the entries they consume; the free pass must run before the occupied pass.
-__global__ void k_ocm_apply_free(OcmConst c, KeySet occ, KeySet fre, MapView m, int* __restrict__ err) {
+__global__ void k_ocm_apply_free(const KfJob* __restrict__ job, MapView m, int* __restrict__ err) {
+  const OcmConst& c = job->c;
+  const KeySet occ = job->s.occ, fre = job->s.fre;
   const int n = *fre.count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int s = fre.list[i];
@@ -319,8 +377,10 @@ __global__ void k_ocm_apply_free(OcmConst c, KeySet occ, KeySet fre, MapView m, 
     if (table_find(occ.keys, occ.mask, k) < 0) map_update(m, c, k, false, 0u, err);
   }
 }
-__global__ void k_ocm_apply_occ(OcmConst c, KeySet occ, const unsigned* __restrict__ occ_rgb, MapView m,
-                                int* __restrict__ err) {
+__global__ void k_ocm_apply_occ(const KfJob* __restrict__ job, MapView m, int* __restrict__ err) {
+  const OcmConst& c = job->c;
+  const KeySet occ = job->s.occ;
+  const unsigned* __restrict__ occ_rgb = job->s.occ_rgb;
   const int n = *occ.count;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int s = occ.list[i];
@@ -408,22 +468,24 @@ struct ocm {
   // map
   MapView map{};
   long long map_cap = 0;
-  // per-keyframe scratch
+  // per-keyframe scratch: one slot per keyframe of a batch (grown on demand, self-cleaning between uses)
   int rows = 0, cols = 0;
-  LeafTable leaf{};
-  long long leaf_cap = 0;
-  int *d_pix_slot = nullptr, *d_bucket = nullptr, *d_voxlist = nullptr, *d_counters = nullptr, *d_err = nullptr;
-  float* d_pts = nullptr;
-  uint8_t *d_pts_rgb = nullptr, *d_pts_label = nullptr;
-  KeySet occ{}, fre{};
-  unsigned* d_occ_rgb = nullptr;
+  static constexpr int MAX_SLOTS = 32;
+  std::vector<KfScratch> slots;
+  int* d_counters = nullptr;          // 4 ints per slot
+  int* d_err = nullptr;
+  KfJob* d_jobs = nullptr;            // device copy of the running batch, JOB_RING batches deep
+  KfJob* h_jobs = nullptr;            // page-locked staging of the same
+  static constexpr int JOB_RING = 8;
+  cudaEvent_t job_ev[JOB_RING] = {};
+  int job_head = 0;
+  int last_slot = 0;
   float* d_depth = nullptr;
   uint8_t *d_rgb = nullptr, *d_label = nullptr;
   uint16_t* d_kf_d16 = nullptr;   // staging of ocm_insert_keyframes_u16
   float* d_kf_depth = nullptr;
   uint8_t* d_kf_rgb = nullptr;
   size_t kf_cap = 0;
-  int last_points = 0;
   long long* d_export_counter = nullptr;
 
   ~ocm() {
@@ -431,21 +493,33 @@ struct ocm {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves);
     free_scratch();
-    F(d_counters); F(d_err); F(d_export_counter); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb);
+    F(d_counters); F(d_err); F(d_export_counter); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb); F(d_jobs);
+    if (h_jobs) cudaFreeHost(h_jobs);
+    for (cudaEvent_t e : job_ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
+  }
+  static void free_slot(KfScratch& k) {
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    F(k.leaf.keys); F(k.leaf.count); F(k.leaf.first); F(k.leaf.offset); F(k.leaf.cursor); F(k.pix_slot); F(k.bucket); F(k.voxlist);
+    F(k.pts); F(k.pts_rgb); F(k.pts_label); F(k.occ.keys); F(k.fre.keys); F(k.occ.list); F(k.fre.list); F(k.occ_rgb);
+    k = KfScratch{};
   }
   void free_scratch() {
     auto F = [](void* p) { if (p) cudaFree(p); };
-    F(leaf.keys); F(leaf.count); F(leaf.first); F(leaf.offset); F(leaf.cursor); F(d_pix_slot); F(d_bucket); F(d_voxlist);
-    F(d_pts); F(d_pts_rgb); F(d_pts_label); F(occ.keys); F(fre.keys); F(occ.list); F(fre.list); F(d_occ_rgb); F(d_depth); F(d_rgb); F(d_label);
-    leaf = LeafTable{}; d_pix_slot = d_bucket = d_voxlist = nullptr; d_pts = nullptr; d_pts_rgb = d_pts_label = nullptr;
-    occ = KeySet{}; fre = KeySet{}; d_occ_rgb = nullptr; d_depth = nullptr; d_rgb = d_label = nullptr;
+    for (KfScratch& k : slots) free_slot(k);
+    slots.clear();
+    F(d_depth); F(d_rgb); F(d_label);
+    d_depth = nullptr; d_rgb = d_label = nullptr;
   }
   template <class T>
   int fill(T* p, T v, long long n);
-  int ensure_scratch(int r, int c);
+  int ensure_scratch(int r, int c, int nslots = 1);
+  int insert_batch(int n, const float* const* dd, const uint8_t* const* drgb, const uint8_t* const* dlabel, int r, int c,
+                   const float* Tcw, float fx, float fy, float cx, float cy);
   int insert(const float* dd, const uint8_t* drgb, const uint8_t* dlabel, int r, int c, const float* Tcw, float fx,
-             float fy, float cx, float cy);
+             float fy, float cx, float cy) {
+    return insert_batch(1, &dd, &drgb, &dlabel, r, c, Tcw, fx, fy, cx, cy);
+  }
   int check_err();
 };
 
@@ -474,29 +548,41 @@ static long long pow2_at_least(long long v) {
   return p;
 }
 
-int ocm::ensure_scratch(int r, int c) {
-  if (r == rows && c == cols) return B200ORB_OK;
-  B200_CUDA(cudaStreamSynchronize(stream));
-  free_scratch();
-  rows = r; cols = c;
+int ocm::ensure_scratch(int r, int c, int nslots) {
+  if (r != rows || c != cols) {
+    B200_CUDA(cudaStreamSynchronize(stream));
+    free_scratch();
+    rows = r; cols = c;
+  }
+  nslots = std::min(std::max(nslots, 1), (int)MAX_SLOTS);
+  if (!d_jobs) {
+    B200_CUDA(cudaMalloc(&d_jobs, sizeof(KfJob) * MAX_SLOTS * JOB_RING));
+    B200_CUDA(cudaHostAlloc(&h_jobs, sizeof(KfJob) * MAX_SLOTS * JOB_RING, cudaHostAllocDefault));
+    for (cudaEvent_t& e : job_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   const long long npix = (long long)r * c;
-  leaf_cap = pow2_at_least(2 * npix);
-  leaf.mask = leaf_cap - 1;
-  B200_CUDA(cudaMalloc(&leaf.keys, 8 * leaf_cap)); B200_CUDA(cudaMalloc(&leaf.count, 4 * leaf_cap));
-  B200_CUDA(cudaMalloc(&leaf.first, 4 * leaf_cap)); B200_CUDA(cudaMalloc(&leaf.offset, 4 * leaf_cap));
-  B200_CUDA(cudaMalloc(&leaf.cursor, 4 * leaf_cap));
-  B200_CUDA(cudaMalloc(&d_pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&d_bucket, 4 * npix));
-  B200_CUDA(cudaMalloc(&d_voxlist, 4 * npix));
-  B200_CUDA(cudaMalloc(&d_pts, 12 * npix)); B200_CUDA(cudaMalloc(&d_pts_rgb, 3 * npix)); B200_CUDA(cudaMalloc(&d_pts_label, npix));
-  const long long occ_cap = pow2_at_least(2 * npix), fre_cap = pow2_at_least(8 * npix);
-  occ.mask = occ_cap - 1; fre.mask = fre_cap - 1;
-  B200_CUDA(cudaMalloc(&occ.keys, 8 * occ_cap)); B200_CUDA(cudaMalloc(&fre.keys, 8 * fre_cap));
-  B200_CUDA(cudaMalloc(&occ.list, 4 * occ_cap)); B200_CUDA(cudaMalloc(&fre.list, 4 * fre_cap));
-  occ.count = d_counters + 2; fre.count = d_counters + 3;
-  B200_CUDA(cudaMalloc(&d_occ_rgb, 4 * occ_cap));
-  fill(leaf.keys, EMPTY_KEY, leaf_cap); fill(leaf.count, 0, leaf_cap); fill(leaf.first, 0x7fffffff, leaf_cap);
-  fill(leaf.cursor, 0, leaf_cap); fill(occ.keys, EMPTY_KEY, occ_cap); fill(fre.keys, EMPTY_KEY, fre_cap);
-  B200_CUDA(cudaGetLastError());
+  const long long leaf_cap = pow2_at_least(2 * npix), occ_cap = pow2_at_least(2 * npix), fre_cap = pow2_at_least(8 * npix);
+  while ((int)slots.size() < nslots) {
+    KfScratch k{};
+    const int id = (int)slots.size();
+    k.leaf.mask = leaf_cap - 1;
+    B200_CUDA(cudaMalloc(&k.leaf.keys, 8 * leaf_cap)); B200_CUDA(cudaMalloc(&k.leaf.count, 4 * leaf_cap));
+    B200_CUDA(cudaMalloc(&k.leaf.first, 4 * leaf_cap)); B200_CUDA(cudaMalloc(&k.leaf.offset, 4 * leaf_cap));
+    B200_CUDA(cudaMalloc(&k.leaf.cursor, 4 * leaf_cap));
+    B200_CUDA(cudaMalloc(&k.pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&k.bucket, 4 * npix));
+    B200_CUDA(cudaMalloc(&k.voxlist, 4 * npix));
+    B200_CUDA(cudaMalloc(&k.pts, 12 * npix)); B200_CUDA(cudaMalloc(&k.pts_rgb, 3 * npix)); B200_CUDA(cudaMalloc(&k.pts_label, npix));
+    k.occ.mask = occ_cap - 1; k.fre.mask = fre_cap - 1;
+    B200_CUDA(cudaMalloc(&k.occ.keys, 8 * occ_cap)); B200_CUDA(cudaMalloc(&k.fre.keys, 8 * fre_cap));
+    B200_CUDA(cudaMalloc(&k.occ.list, 4 * occ_cap)); B200_CUDA(cudaMalloc(&k.fre.list, 4 * fre_cap));
+    k.counters = d_counters + 4 * id;
+    k.occ.count = k.counters + 2; k.fre.count = k.counters + 3;
+    B200_CUDA(cudaMalloc(&k.occ_rgb, 4 * occ_cap));
+    fill(k.leaf.keys, EMPTY_KEY, leaf_cap); fill(k.leaf.count, 0, leaf_cap); fill(k.leaf.first, 0x7fffffff, leaf_cap);
+    fill(k.leaf.cursor, 0, leaf_cap); fill(k.occ.keys, EMPTY_KEY, occ_cap); fill(k.fre.keys, EMPTY_KEY, fre_cap);
+    B200_CUDA(cudaGetLastError());
+    slots.push_back(k);
+  }
   return B200ORB_OK;
 }
 
@@ -513,43 +599,65 @@ int ocm::check_err() {
   return B200ORB_OK;
 }
 
-int ocm::insert(const float* dd, const uint8_t* drgb, const uint8_t* dlabel, int r, int c, const float* Tcw, float fx,
-                float fy, float cx, float cy) {
-  B200_CHECK(ensure_scratch(r, c));
-  OcmConst k;
-  memset(&k, 0, sizeof(k));
-  k.fx = fx; k.fy = fy; k.cx = cx; k.cy = cy;
-  k.depth_min = prm.depth_min; k.depth_max = prm.depth_max; k.y_max = prm.y_max; k.leaf = prm.leaf;
-  k.inv_leaf = prm.leaf > 0 ? 1.0f / prm.leaf : 0.f;
-  k.res = prm.resolution; k.res_factor = 1.0 / prm.resolution;
-  k.hit_log = hit_log; k.miss_log = miss_log; k.cmin = cmin; k.cmax = cmax;
-  double R[9], t[3];
-  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[i * 3 + j] = (double)Tcw[i * 4 + j]; t[i] = (double)Tcw[i * 4 + 3]; }
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) k.Rt[i * 3 + j] = R[j * 3 + i];
-    k.ti[i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
-  }
-  k.origin[0] = Tcw[3]; k.origin[1] = Tcw[7]; k.origin[2] = Tcw[11];
-  k.rows = r; k.cols = c;
+// n keyframes (insertion order = array order).  Stages up to the key sets: one launch per stage for up to MAX_SLOTS
+// keyframes; map update: two small launches per keyframe, in order (clamped log-odds updates do not commute).
+int ocm::insert_batch(int n, const float* const* dd, const uint8_t* const* drgb, const uint8_t* const* dlabel, int r, int c,
+                      const float* Tcw_all, float fx, float fy, float cx, float cy) {
+  B200_CHECK(ensure_scratch(r, c, n));
   const int npix = r * c;
-  B200_CUDA(cudaMemsetAsync(d_counters, 0, 16, stream));
-  if (prm.leaf > 0) {
-    k_ocm_bin<<<(npix + 255) / 256, 256, 0, stream>>>(k, dd, leaf, d_pix_slot, d_counters, d_voxlist, d_err);
-    k_ocm_ranges<<<(npix + 255) / 256, 256, 0, stream>>>(leaf, d_counters, d_voxlist);
-    k_ocm_scatter<<<(npix + 255) / 256, 256, 0, stream>>>(npix, d_pix_slot, leaf, d_bucket);
-    k_ocm_centroids<<<(npix + 127) / 128, 128, 0, stream>>>(k, dd, drgb, dlabel, leaf, d_counters, d_voxlist, d_bucket,
-                                                          d_pts, d_pts_rgb, d_pts_label);
-    launches += 4;
-  } else {
-    k_ocm_points_nofilter<<<(npix + 255) / 256, 256, 0, stream>>>(k, dd, drgb, dlabel, d_counters, d_pts, d_pts_rgb, d_pts_label);
+  for (int b0 = 0; b0 < n; b0 += (int)slots.size()) {
+    const int B = std::min((int)slots.size(), n - b0);
+    const int ring = job_head;
+    job_head = (job_head + 1) % JOB_RING;
+    B200_CUDA(cudaEventSynchronize(job_ev[ring]));   // the batch that used this staging entry has been uploaded
+    KfJob* hj = h_jobs + (size_t)ring * MAX_SLOTS;
+    KfJob* dj = d_jobs + (size_t)ring * MAX_SLOTS;
+    for (int j = 0; j < B; ++j) {
+      const float* Tcw = Tcw_all + 16 * (b0 + j);
+      KfJob& J = hj[j];
+      OcmConst& k = J.c;
+      memset(&k, 0, sizeof(k));
+      k.fx = fx; k.fy = fy; k.cx = cx; k.cy = cy;
+      k.depth_min = prm.depth_min; k.depth_max = prm.depth_max; k.y_max = prm.y_max; k.leaf = prm.leaf;
+      k.inv_leaf = prm.leaf > 0 ? 1.0f / prm.leaf : 0.f;
+      k.res = prm.resolution; k.res_factor = 1.0 / prm.resolution;
+      k.hit_log = hit_log; k.miss_log = miss_log; k.cmin = cmin; k.cmax = cmax;
+      double R[9], t[3];
+      for (int i = 0; i < 3; ++i) { for (int q = 0; q < 3; ++q) R[i * 3 + q] = (double)Tcw[i * 4 + q]; t[i] = (double)Tcw[i * 4 + 3]; }
+      for (int i = 0; i < 3; ++i) {
+        for (int q = 0; q < 3; ++q) k.Rt[i * 3 + q] = R[q * 3 + i];
+        k.ti[i] = -(R[0 * 3 + i] * t[0] + R[1 * 3 + i] * t[1] + R[2 * 3 + i] * t[2]);
+      }
+      k.origin[0] = Tcw[3]; k.origin[1] = Tcw[7]; k.origin[2] = Tcw[11];
+      k.rows = r; k.cols = c;
+      J.depth = dd[b0 + j]; J.rgb = drgb[b0 + j]; J.label = dlabel ? dlabel[b0 + j] : nullptr;
+      J.s = slots[j];
+    }
+    B200_CUDA(cudaMemcpyAsync(dj, hj, sizeof(KfJob) * B, cudaMemcpyHostToDevice, stream));
+    B200_CUDA(cudaEventRecord(job_ev[ring], stream));
+    B200_CUDA(cudaMemsetAsync(d_counters, 0, 16 * B, stream));
+    const dim3 g256((npix + 255) / 256, B), g128((npix + 127) / 128, B);
+    if (prm.leaf > 0) {
+      k_ocm_bin<<<g256, 256, 0, stream>>>(dj, d_err);
+      k_ocm_ranges<<<g256, 256, 0, stream>>>(dj);
+      k_ocm_scatter<<<g256, 256, 0, stream>>>(dj);
+      k_ocm_centroids<<<g128, 128, 0, stream>>>(dj);
+      launches += 4;
+    } else {
+      k_ocm_points_nofilter<<<g256, 256, 0, stream>>>(dj);
+      launches += 1;
+    }
+    k_ocm_scan_keys<<<g128, 128, 0, stream>>>(dj, d_err);
     launches += 1;
+    for (int j = 0; j < B; ++j) {
+      // list lengths live on the device: grid-stride kernels on a fixed grid (2 CTAs per SM)
+      k_ocm_apply_free<<<296, 256, 0, stream>>>(dj + j, map, d_err);
+      k_ocm_apply_occ<<<296, 256, 0, stream>>>(dj + j, map, d_err);
+      launches += 2;
+    }
+    last_slot = B - 1;
+    B200_CUDA(cudaGetLastError());
   }
-  k_ocm_scan_keys<<<(npix + 127) / 128, 128, 0, stream>>>(k, d_counters, d_pts, d_pts_label, d_pts_rgb, occ, d_occ_rgb, fre, d_err);
-  // list lengths live on the device: grid-stride kernels on a fixed grid (2 CTAs per SM)
-  k_ocm_apply_free<<<296, 256, 0, stream>>>(k, occ, fre, map, d_err);
-  k_ocm_apply_occ<<<296, 256, 0, stream>>>(k, occ, d_occ_rgb, map, d_err);
-  launches += 3;
-  B200_CUDA(cudaGetLastError());
   return B200ORB_OK;
 }
 
@@ -598,7 +706,7 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   if ((e = cudaMalloc(&h->map.hi, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.rgb, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.nleaves, 4)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&h->d_counters, 16)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->d_counters, 16 * ocm::MAX_SLOTS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_export_counter, 8)) != cudaSuccess) return fail(e);
   h->fill(h->map.keys, EMPTY_KEY, C); h->fill(h->map.val, 0.f, C); h->fill(h->map.a, 0.f, C);
@@ -625,12 +733,16 @@ int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d
   if (!h || !d_depth || !d_rgb || !depth_idx || !Tcw || rows <= 0 || cols <= 0 || n < 0) { set_error("bad argument"); return B200ORB_EINVAL; }
   DeviceGuard g(h->device);
   const size_t npix = (size_t)rows * cols;
+  std::vector<const float*> dd(n);
+  std::vector<const uint8_t*> dc(n);
   for (int i = 0; i < n; ++i) {
     const int di = depth_idx[i], ri = rgb_idx ? rgb_idx[i] : depth_idx[i];
     if (di < 0 || ri < 0) { set_error("negative frame index"); return B200ORB_EINVAL; }
-    B200_CHECK(h->insert(d_depth + npix * di, d_rgb + npix * 3 * ri, nullptr, rows, cols, Tcw + 16 * i, fx, fy, cx, cy));
+    dd[i] = d_depth + npix * di;
+    dc[i] = d_rgb + npix * 3 * ri;
   }
-  return B200ORB_OK;
+  if (n == 0) return B200ORB_OK;
+  return h->insert_batch(n, dd.data(), dc.data(), nullptr, rows, cols, Tcw, fx, fy, cx, cy);
 }
 
 int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t* rgb, int rows, int cols, int n,
@@ -653,9 +765,10 @@ int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t*
   k_depth_u16_to_f32<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, h->stream>>>(
       reinterpret_cast<const ushort4*>(h->d_kf_d16), reinterpret_cast<float4*>(h->d_kf_depth), depth_factor, tot / 4);
   ++h->launches;
-  for (int i = 0; i < n; ++i)
-    B200_CHECK(h->insert(h->d_kf_depth + npix * i, h->d_kf_rgb + npix * 3 * i, nullptr, rows, cols, Tcw + 16 * i, fx, fy, cx, cy));
-  return B200ORB_OK;
+  std::vector<const float*> dd(n);
+  std::vector<const uint8_t*> dc(n);
+  for (int i = 0; i < n; ++i) { dd[i] = h->d_kf_depth + npix * i; dc[i] = h->d_kf_rgb + npix * 3 * i; }
+  return h->insert_batch(n, dd.data(), dc.data(), nullptr, rows, cols, Tcw, fx, fy, cx, cy);
 }
 
 int ocm_insert_keyframe(ocm_t* h, const float* depth, const uint8_t* rgb, int rows, int cols, const float Tcw[16],
@@ -678,13 +791,15 @@ int ocm_last_points(ocm_t* h, float* xyz, uint8_t* rgb, int cap, int* n) {
   if (!h || !n) { set_error("null argument"); return B200ORB_EINVAL; }
   DeviceGuard g(h->device);
   int cnt[2] = {0, 0};
-  B200_CUDA(cudaMemcpyAsync(cnt, h->d_counters, 8, cudaMemcpyDeviceToHost, h->stream));
+  if (h->slots.empty()) { *n = 0; return B200ORB_OK; }
+  const KfScratch& ls = h->slots[h->last_slot];
+  B200_CUDA(cudaMemcpyAsync(cnt, ls.counters, 8, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   *n = cnt[1];
   if (!xyz) return B200ORB_OK;
   if (cnt[1] > cap) { set_error("cap %d < %d points", cap, cnt[1]); return B200ORB_ECAP; }
-  B200_CUDA(cudaMemcpyAsync(xyz, h->d_pts, (size_t)12 * cnt[1], cudaMemcpyDeviceToHost, h->stream));
-  if (rgb) B200_CUDA(cudaMemcpyAsync(rgb, h->d_pts_rgb, (size_t)3 * cnt[1], cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(xyz, ls.pts, (size_t)12 * cnt[1], cudaMemcpyDeviceToHost, h->stream));
+  if (rgb) B200_CUDA(cudaMemcpyAsync(rgb, ls.pts_rgb, (size_t)3 * cnt[1], cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return B200ORB_OK;
 }

@@ -87,6 +87,7 @@ struct orbs {
   float *d_depth = nullptr, *d_T = nullptr;
   uint16_t* d_depth16 = nullptr;
   bool full_depth_valid = false, force_full_depth_upload = false;
+  int chunk_frames = 128;   // frames per upload chunk of the host-buffer entries
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have = false;
@@ -224,7 +225,7 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
     B200_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : h->chunk_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  const int nchunk = (int)std::min<size_t>(7, (F + 63) / 64);   // 64-frame chunks keep each extractor launch wide enough
+  const int nchunk = (int)std::min<size_t>(7, (F + h->chunk_frames - 1) / h->chunk_frames);   // >= 64-frame chunks keep each launch wide enough
   {
     // the copy stream may only overwrite d_gray once the previous call's kernels are done with it
     B200_CUDA(cudaEventRecord(h->chunk_ev[7], st));
@@ -321,6 +322,14 @@ int b200orb_depth_u16_to_f32_device(const uint16_t* d_src, float* d_dst, size_t 
   k_depth_u16_to_f32<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const ushort4*>(d_src), reinterpret_cast<float4*>(d_dst), factor, n / 4);
   B200_CUDA(cudaGetLastError());
+  return B200ORB_OK;
+}
+
+// frames per upload chunk of the host-buffer entries (default 128; at most 7 chunks per call): smaller chunks start the
+// extraction earlier, larger ones keep the launches wider
+int orbs_set_chunk_frames(orbs_t* h, int frames) {
+  if (!h || frames <= 0) { set_error("bad argument"); return B200ORB_EINVAL; }
+  h->chunk_frames = frames;
   return B200ORB_OK;
 }
 

@@ -90,6 +90,10 @@ class StreamTracker:
         """False (default): page-locked CV_16U depth is read under the keypoints in place; True: always upload it."""
         _lib.check(self._L.orbs_set_full_depth_upload(self._h, int(on)))
 
+    def set_chunk_frames(self, frames: int):
+        """Frames per upload chunk of the host-buffer calls (default 128)."""
+        _lib.check(self._L.orbs_set_chunk_frames(self._h, int(frames)))
+
     def device_inputs(self):
         """(d_gray, d_depth) device pointers of the last host-buffer batch (depth as f32 metres)."""
         g, d = C.c_void_p(), C.c_void_p()
