@@ -9,9 +9,11 @@
 //                count, first pixel, bucket offset, cursor.  Pixels of a cell are bucketed, sorted ascending and
 //                summed sequentially in float so the centroid equals the oracle's pixel-order sum bit for bit.
 //   points       world-frame centroids of the last keyframe (xyz f32, rgb, ground label), unordered
-//   scan sets    two open-addressing key sets per scan: occupied endpoints and free ray cells
-//   map          persistent open-addressing hash: key (3 x u16 OcTreeKey packed in u64) -> float log-odds, colour and
-//                the clamp-add summary (a, lo, hi) used by the multi-GPU merge
+//   map          persistent open-addressing hash: key (3 x u16 OcTreeKey packed in u64) -> float log-odds, colour, the
+//                clamp-add summary (a, lo, hi) used by the multi-GPU merge, and the batch masks: bit j of the hit / miss
+//                word = keyframe j of the running batch observed the voxel occupied / free.  The scan of ALL keyframes
+//                of a batch only ORs bits (order-free, one launch); one more launch replays each touched voxel's bits in
+//                keyframe order, which reproduces the sequential clamped updates exactly.
 #include <algorithm>
 #include <new>
 #include <vector>
@@ -77,30 +79,52 @@ struct LeafTable {
   long long mask;
 };
 
-struct KeySet {
+struct MapView {
   unsigned long long* keys;
+  float* val;
+  float *a, *lo, *hi;   // clamp-add summary since the last reset: f(x) = min(max(x + a, lo), hi)
+  unsigned* rgb;
+  int* nleaves;
   long long mask;
-  int* list;      // slots filled during this scan
-  int* count;
+  // batch accumulation: which keyframes of the running batch hit (high word) / missed (low word) the voxel, the colour
+  // of its latest hit (keyframe << 24 | rgb), and the list of voxels touched by the batch
+  unsigned long long* bm;
+  unsigned* bm_rgb;
+  int* touched;
+  int* ntouched;
 };
 
-__device__ __forceinline__ long long set_insert(const KeySet& st, unsigned long long key) {
-  bool fresh;
-  const long long s = table_insert(st.keys, st.mask, key, &fresh);
-  if (s >= 0 && fresh) st.list[atomicAdd(st.count, 1)] = (int)s;
-  return s;
+// Record "keyframe j of the batch observed voxel `key` as occupied / free".  Order-free (atomicOr), so every keyframe
+// of a batch can be scanned in one launch; k_ocm_apply replays the bits of each voxel in keyframe order.
+__device__ __forceinline__ bool map_touch(const MapView& m, unsigned long long key, int j, bool occupied, unsigned rgb) {
+  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  bool found = false;
+  for (long long probe = 0; probe <= m.mask; ++probe) {
+    const unsigned long long cur = m.keys[s];
+    if (cur == key) { found = true; break; }
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&m.keys[s], EMPTY_KEY, key);
+      if (old == EMPTY_KEY) { atomicAdd(m.nleaves, 1); found = true; break; }
+      if (old == key) { found = true; break; }
+    }
+    s = (s + 1) & m.mask;
+  }
+  if (!found) return false;
+  const unsigned long long bit = occupied ? (1ull << (32 + j)) : (1ull << j);
+  const unsigned long long old = atomicOr(&m.bm[s], bit);
+  if (old == 0ull) m.touched[atomicAdd(m.ntouched, 1)] = (int)s;
+  if (occupied) atomicMax(&m.bm_rgb[s], ((unsigned)j << 24) | (rgb & 0xffffffu));
+  return true;
 }
 
 // Everything one keyframe needs between back-projection and the map update.  A batch of keyframes runs every stage
-// up to the key sets as ONE launch (blockIdx.y = job); only the map update itself is ordered keyframe by keyframe.
+// as ONE launch (blockIdx.y = job = bit index of the keyframe in the batch masks of the map).
 struct KfScratch {
   LeafTable leaf;
   int *pix_slot, *bucket, *voxlist;
-  int* counters;   // [0] pixels, [1] voxels (= points), [2] occupied keys, [3] free keys
+  int* counters;   // [0] pixels, [1] voxels (= points)
   float* pts;
   uint8_t *pts_rgb, *pts_label;
-  KeySet occ, fre;
-  unsigned* occ_rgb;
 };
 struct KfJob {
   OcmConst c;
@@ -262,16 +286,16 @@ __device__ __forceinline__ unsigned long long pack_key(int kx, int ky, int kz) {
   return (unsigned long long)kx | ((unsigned long long)ky << 16) | ((unsigned long long)kz << 32);
 }
 
-// K12/K13: per point -> occupied endpoint key, or (ground) the free cells along the ray (computeRayKeys)
-__global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, int* __restrict__ err) {
-  const KfJob& J = jobs[blockIdx.y];
+// K12/K13: per point -> occupied endpoint key, or (ground) the free cells along the ray (computeRayKeys); the
+// observations go straight into the map's batch masks (bit = keyframe).
+__global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* __restrict__ err) {
+  const int j = blockIdx.y;
+  const KfJob& J = jobs[j];
   const OcmConst& c = J.c;
   const int* __restrict__ counters = J.s.counters;
   const float* __restrict__ pts = J.s.pts;
   const uint8_t* __restrict__ pts_label = J.s.pts_label;
   const uint8_t* __restrict__ pts_rgb = J.s.pts_rgb;
-  const KeySet occ = J.s.occ, fre = J.s.fre;
-  unsigned* __restrict__ occ_rgb = J.s.occ_rgb;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
   const float e[3] = {pts[(size_t)v * 3], pts[(size_t)v * 3 + 1], pts[(size_t)v * 3 + 2]};
@@ -279,10 +303,9 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, int* __restrict_
   const bool end_ok = coord_to_key(c, e[0], ke[0]) && coord_to_key(c, e[1], ke[1]) && coord_to_key(c, e[2], ke[2]);
   if (!pts_label[v]) {
     if (end_ok) {
-      const long long s = set_insert(occ, pack_key(ke[0], ke[1], ke[2]));
-      if (s < 0) atomicExch(err, 2);
-      else occ_rgb[s] = (unsigned)pts_rgb[(size_t)v * 3] | ((unsigned)pts_rgb[(size_t)v * 3 + 1] << 8) |
-                        ((unsigned)pts_rgb[(size_t)v * 3 + 2] << 16);
+      const unsigned rgb = (unsigned)pts_rgb[(size_t)v * 3] | ((unsigned)pts_rgb[(size_t)v * 3 + 1] << 8) |
+                           ((unsigned)pts_rgb[(size_t)v * 3 + 2] << 16);
+      if (!map_touch(m, pack_key(ke[0], ke[1], ke[2]), j, true, rgb)) atomicExch(err, 4);
     }
     return;
   }
@@ -291,7 +314,7 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, int* __restrict_
       !coord_to_key(c, c.origin[2], ko[2]))
     return;
   if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return;
-  if (set_insert(fre, pack_key(ko[0], ko[1], ko[2])) < 0) atomicExch(err, 3);
+  if (!map_touch(m, pack_key(ko[0], ko[1], ko[2]), j, false, 0u)) atomicExch(err, 4);
   float dir[3] = {e[0] - c.origin[0], e[1] - c.origin[1], e[2] - c.origin[2]};
   double n2 = 0;
 #pragma unroll
@@ -325,68 +348,33 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, int* __restrict_
     if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
     const double dist = fmin(fmin(tMax[0], tMax[1]), tMax[2]);
     if (dist > (double)length) break;
-    if (set_insert(fre, pack_key(cur[0], cur[1], cur[2])) < 0) { atomicExch(err, 3); break; }
+    if (!map_touch(m, pack_key(cur[0], cur[1], cur[2]), j, false, 0u)) { atomicExch(err, 4); break; }
   }
 }
 
-struct MapView {
-  unsigned long long* keys;
-  float* val;
-  float *a, *lo, *hi;   // clamp-add summary since the last reset: f(x) = min(max(x + a, lo), hi)
-  unsigned* rgb;
-  int* nleaves;
-  long long mask;
-};
-
-__device__ __forceinline__ void map_update(const MapView& m, const OcmConst& c, unsigned long long key, bool occupied,
-                                           unsigned rgb, int* err) {
-  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
-  bool found = false;
-  for (long long probe = 0; probe <= m.mask; ++probe) {
-    const unsigned long long cur = m.keys[s];
-    if (cur == key) { found = true; break; }
-    if (cur == EMPTY_KEY) {
-      const unsigned long long old = atomicCAS(&m.keys[s], EMPTY_KEY, key);
-      if (old == EMPTY_KEY) { atomicAdd(m.nleaves, 1); found = true; break; }
-      if (old == key) { found = true; break; }
+// K14: replay, voxel by voxel, the observations of the batch in keyframe order (MapDrawer.cc:1007-1022 per keyframe:
+// free \ occupied get a miss, occupied get a hit; updateNodeLogOdds clamps after every add, so the order matters and
+// is kept).  One thread per touched voxel; the batch masks are cleared for the next batch.
+__global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cmax, MapView m) {
+  const int n = *m.ntouched;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int s = m.touched[i];
+    const unsigned long long w = m.bm[s];
+    m.bm[s] = 0ull;
+    const unsigned hit = (unsigned)(w >> 32), miss = (unsigned)w & ~hit;
+    float v = m.val[s], a = m.a[s], lo = m.lo[s], hi = m.hi[s];
+    unsigned all = hit | miss;
+    while (all) {
+      const int j = __ffs(all) - 1;
+      all &= all - 1u;
+      const float d = ((hit >> j) & 1u) ? hit_log : miss_log;
+      v = fminf(fmaxf(v + d, cmin), cmax);
+      a = a + d;
+      lo = fminf(fmaxf(lo + d, cmin), cmax);
+      hi = fminf(fmaxf(hi + d, cmin), cmax);
     }
-    s = (s + 1) & m.mask;
-  }
-  if (!found) { atomicExch(err, 4); return; }
-  // one update per key per scan: plain read-modify-write (updateNodeLogOdds)
-  const float d = occupied ? c.hit_log : c.miss_log;
-  float v = m.val[s] + d;
-  v = fminf(fmaxf(v, c.cmin), c.cmax);
-  m.val[s] = v;
-  m.a[s] = m.a[s] + d;
-  m.lo[s] = fminf(fmaxf(m.lo[s] + d, c.cmin), c.cmax);
-  m.hi[s] = fminf(fmaxf(m.hi[s] + d, c.cmin), c.cmax);
-  if (occupied) m.rgb[s] = rgb;
-}
-
-// K14: free \ occupied get a miss, occupied get a hit (MapDrawer.cc:1007-1022).  Both walk the scan's slot lists
-// (no table sweep) and clear the entries they consume; the free pass must run before the occupied pass.
-__global__ void k_ocm_apply_free(const KfJob* __restrict__ job, MapView m, int* __restrict__ err) {
-  const OcmConst& c = job->c;
-  const KeySet occ = job->s.occ, fre = job->s.fre;
-  const int n = *fre.count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int s = fre.list[i];
-    const unsigned long long k = fre.keys[s];
-    fre.keys[s] = EMPTY_KEY;
-    if (table_find(occ.keys, occ.mask, k) < 0) map_update(m, c, k, false, 0u, err);
-  }
-}
-__global__ void k_ocm_apply_occ(const KfJob* __restrict__ job, MapView m, int* __restrict__ err) {
-  const OcmConst& c = job->c;
-  const KeySet occ = job->s.occ;
-  const unsigned* __restrict__ occ_rgb = job->s.occ_rgb;
-  const int n = *occ.count;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int s = occ.list[i];
-    const unsigned long long k = occ.keys[s];
-    occ.keys[s] = EMPTY_KEY;
-    map_update(m, c, k, true, occ_rgb[s], err);
+    m.val[s] = v; m.a[s] = a; m.lo[s] = lo; m.hi[s] = hi;
+    if (hit) { m.rgb[s] = m.bm_rgb[s] & 0xffffffu; m.bm_rgb[s] = 0u; }
   }
 }
 
@@ -491,7 +479,8 @@ struct ocm {
   ~ocm() {
     DeviceGuard g(device);
     auto F = [](void* p) { if (p) cudaFree(p); };
-    F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves);
+    F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves); F(map.bm); F(map.bm_rgb);
+    F(map.touched); F(map.ntouched);
     free_scratch();
     F(d_counters); F(d_err); F(d_export_counter); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb); F(d_jobs);
     if (h_jobs) cudaFreeHost(h_jobs);
@@ -501,7 +490,7 @@ struct ocm {
   static void free_slot(KfScratch& k) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(k.leaf.keys); F(k.leaf.count); F(k.leaf.first); F(k.leaf.offset); F(k.leaf.cursor); F(k.pix_slot); F(k.bucket); F(k.voxlist);
-    F(k.pts); F(k.pts_rgb); F(k.pts_label); F(k.occ.keys); F(k.fre.keys); F(k.occ.list); F(k.fre.list); F(k.occ_rgb);
+    F(k.pts); F(k.pts_rgb); F(k.pts_label);
     k = KfScratch{};
   }
   void free_scratch() {
@@ -561,7 +550,7 @@ int ocm::ensure_scratch(int r, int c, int nslots) {
     for (cudaEvent_t& e : job_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   const long long npix = (long long)r * c;
-  const long long leaf_cap = pow2_at_least(2 * npix), occ_cap = pow2_at_least(2 * npix), fre_cap = pow2_at_least(8 * npix);
+  const long long leaf_cap = pow2_at_least(2 * npix);
   while ((int)slots.size() < nslots) {
     KfScratch k{};
     const int id = (int)slots.size();
@@ -572,14 +561,9 @@ int ocm::ensure_scratch(int r, int c, int nslots) {
     B200_CUDA(cudaMalloc(&k.pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&k.bucket, 4 * npix));
     B200_CUDA(cudaMalloc(&k.voxlist, 4 * npix));
     B200_CUDA(cudaMalloc(&k.pts, 12 * npix)); B200_CUDA(cudaMalloc(&k.pts_rgb, 3 * npix)); B200_CUDA(cudaMalloc(&k.pts_label, npix));
-    k.occ.mask = occ_cap - 1; k.fre.mask = fre_cap - 1;
-    B200_CUDA(cudaMalloc(&k.occ.keys, 8 * occ_cap)); B200_CUDA(cudaMalloc(&k.fre.keys, 8 * fre_cap));
-    B200_CUDA(cudaMalloc(&k.occ.list, 4 * occ_cap)); B200_CUDA(cudaMalloc(&k.fre.list, 4 * fre_cap));
     k.counters = d_counters + 4 * id;
-    k.occ.count = k.counters + 2; k.fre.count = k.counters + 3;
-    B200_CUDA(cudaMalloc(&k.occ_rgb, 4 * occ_cap));
     fill(k.leaf.keys, EMPTY_KEY, leaf_cap); fill(k.leaf.count, 0, leaf_cap); fill(k.leaf.first, 0x7fffffff, leaf_cap);
-    fill(k.leaf.cursor, 0, leaf_cap); fill(k.occ.keys, EMPTY_KEY, occ_cap); fill(k.fre.keys, EMPTY_KEY, fre_cap);
+    fill(k.leaf.cursor, 0, leaf_cap);
     B200_CUDA(cudaGetLastError());
     slots.push_back(k);
   }
@@ -592,15 +576,15 @@ int ocm::check_err() {
   B200_CUDA(cudaStreamSynchronize(stream));
   if (e) {
     B200_CUDA(cudaMemsetAsync(d_err, 0, 4, stream));
-    static const char* what[] = {"", "VoxelGrid table full", "occupied set full", "free set full", "map full (raise OcmParams.map_capacity)"};
+    static const char* what[] = {"", "VoxelGrid table full", "", "", "map full (raise OcmParams.map_capacity)"};
     set_error("occupancy insert: %s", what[e < 5 ? e : 0]);
     return B200ORB_ECAP;
   }
   return B200ORB_OK;
 }
 
-// n keyframes (insertion order = array order).  Stages up to the key sets: one launch per stage for up to MAX_SLOTS
-// keyframes; map update: two small launches per keyframe, in order (clamped log-odds updates do not commute).
+// n keyframes (insertion order = array order), up to MAX_SLOTS per round of launches: every stage is one launch for
+// the whole round, including the map update (per-voxel replay of the round's observations in keyframe order).
 int ocm::insert_batch(int n, const float* const* dd, const uint8_t* const* drgb, const uint8_t* const* dlabel, int r, int c,
                       const float* Tcw_all, float fx, float fy, float cx, float cy) {
   B200_CHECK(ensure_scratch(r, c, n));
@@ -647,14 +631,11 @@ int ocm::insert_batch(int n, const float* const* dd, const uint8_t* const* drgb,
       k_ocm_points_nofilter<<<g256, 256, 0, stream>>>(dj);
       launches += 1;
     }
-    k_ocm_scan_keys<<<g128, 128, 0, stream>>>(dj, d_err);
-    launches += 1;
-    for (int j = 0; j < B; ++j) {
-      // list lengths live on the device: grid-stride kernels on a fixed grid (2 CTAs per SM)
-      k_ocm_apply_free<<<296, 256, 0, stream>>>(dj + j, map, d_err);
-      k_ocm_apply_occ<<<296, 256, 0, stream>>>(dj + j, map, d_err);
-      launches += 2;
-    }
+    B200_CUDA(cudaMemsetAsync(map.ntouched, 0, 4, stream));
+    k_ocm_scan_keys<<<g128, 128, 0, stream>>>(dj, map, d_err);
+    // the touched-list length lives on the device: grid-stride kernel on a fixed grid (2 CTAs per SM)
+    k_ocm_apply<<<296, 256, 0, stream>>>(hit_log, miss_log, cmin, cmax, map);
+    launches += 2;
     last_slot = B - 1;
     B200_CUDA(cudaGetLastError());
   }
@@ -706,6 +687,10 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   if ((e = cudaMalloc(&h->map.hi, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.rgb, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.nleaves, 4)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.bm, 8 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.bm_rgb, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.touched, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.ntouched, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_counters, 16 * ocm::MAX_SLOTS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_export_counter, 8)) != cudaSuccess) return fail(e);
@@ -713,6 +698,9 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   h->fill(h->map.lo, -INFINITY, C); h->fill(h->map.hi, INFINITY, C);
   cudaMemsetAsync(h->map.rgb, 0xff, 4 * C, h->stream);
   cudaMemsetAsync(h->map.nleaves, 0, 4, h->stream);
+  cudaMemsetAsync(h->map.bm, 0, 8 * C, h->stream);
+  cudaMemsetAsync(h->map.bm_rgb, 0, 4 * C, h->stream);
+  cudaMemsetAsync(h->map.ntouched, 0, 4, h->stream);
   cudaMemsetAsync(h->d_err, 0, 4, h->stream);
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e);
   *out = h;
