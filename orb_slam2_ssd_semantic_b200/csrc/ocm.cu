@@ -5,8 +5,8 @@
 // keys / computeRayKeys / updateNode) follow oracle/occ_ref.cpp, which states them.
 //
 // HBM layout:
-//   leaf table   open-addressing hash of the 1-cm VoxelGrid cells of ONE keyframe (key = 3 x 21-bit cell index):
-//                count, first pixel, bucket offset, cursor.  Pixels of a cell are bucketed, sorted ascending and
+//   leaf table   open-addressing hash of the 1-cm VoxelGrid cells of ONE keyframe (key = 3 x 21-bit cell index), one
+//                32-byte record per cell: key, count, first pixel, bucket offset, cursor.  Pixels of a cell are bucketed, sorted ascending and
 //                summed sequentially in float so the centroid equals the oracle's pixel-order sum bit for bit.
 //   points       world-frame centroids of the last keyframe (xyz f32, rgb, ground label), unordered
 //   map          persistent open-addressing hash: key (3 x u16 OcTreeKey packed in u64) -> float log-odds, colour, the
@@ -70,14 +70,37 @@ struct OcmConst {
   int rows, cols;
 };
 
+// One 32-byte record (= one L2 sector) per VoxelGrid cell: an insert, the bucket bookkeeping and the reset all touch
+// the same sector instead of five arrays.
+struct __align__(32) LeafRec {
+  unsigned long long key;
+  int count;
+  int first;     // smallest pixel index
+  int offset;
+  int cursor;
+  int pad[2];
+};
 struct LeafTable {
-  unsigned long long* keys;
-  int* count;
-  int* first;     // smallest pixel index
-  int* offset;
-  int* cursor;
+  LeafRec* rec;
   long long mask;
 };
+
+// find-or-insert on the record table; returns slot or -1 when the table is full
+__device__ __forceinline__ long long leaf_insert(const LeafTable& lt, unsigned long long key, bool* fresh) {
+  long long s = (long long)(hash64(key) & (unsigned long long)lt.mask);
+  *fresh = false;
+  for (long long probe = 0; probe <= lt.mask; ++probe) {
+    const unsigned long long cur = lt.rec[s].key;
+    if (cur == key) return s;
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&lt.rec[s].key, EMPTY_KEY, key);
+      if (old == EMPTY_KEY) { *fresh = true; return s; }
+      if (old == key) return s;
+    }
+    s = (s + 1) & lt.mask;
+  }
+  return -1;
+}
 
 struct MapView {
   unsigned long long* keys;
@@ -154,6 +177,22 @@ __device__ __forceinline__ unsigned long long leaf_key(const OcmConst& c, float 
          ((unsigned long long)(iz & 0x1fffff) << 42);
 }
 
+// Pixel of this thread for the warp-tiled kernels: a warp covers an 8 x 4 pixel tile (lane = ty * 8 + tx, so lanes are
+// in row-major order inside the tile).  Neighbouring pixels mostly fall into the same 1-cm cell, so the cell-level
+// atomics are issued once per (warp, cell) by the lowest lane of each __match_any group.
+__device__ __forceinline__ int tile_pixel(int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int tiles_x = (cols + 7) >> 3;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int y = ty * 4 + (lane >> 3), x = tx * 8 + (lane & 7);
+  return (y < rows && x < cols) ? y * cols + x : -1;
+}
+__host__ __device__ inline int tile_blocks(int rows, int cols, int warps_per_block) {
+  const int tiles = ((cols + 7) >> 3) * ((rows + 3) >> 2);
+  return (tiles + warps_per_block - 1) / warps_per_block;
+}
+
 // K11a: gate + VoxelGrid cell of every pixel
 __global__ void k_ocm_bin(const KfJob* __restrict__ jobs, int* __restrict__ err) {
   const KfJob& J = jobs[blockIdx.y];
@@ -163,22 +202,27 @@ __global__ void k_ocm_bin(const KfJob* __restrict__ jobs, int* __restrict__ err)
   int* __restrict__ pix_slot = J.s.pix_slot;
   int* __restrict__ counters = J.s.counters;
   int* __restrict__ voxlist = J.s.voxlist;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= c.rows * c.cols) return;
+  const int lane = threadIdx.x & 31;
+  const int pix = tile_pixel(c.rows, c.cols);
   float x, y, z;
+  const bool ok = pix >= 0 && backproject(c, depth, pix, x, y, z);
+  const unsigned long long key = ok ? leaf_key(c, x, y, z) : (EMPTY_KEY - 1ull - (unsigned long long)lane);
+  const unsigned grp = __match_any_sync(0xffffffffu, key);
+  const int leader = __ffs(grp) - 1;
   int slot = -1;
-  if (backproject(c, depth, pix, x, y, z)) {
+  if (ok && lane == leader) {   // lowest lane of the group = smallest pixel index of the group
     bool fresh;
-    const long long s = table_insert(lt.keys, lt.mask, leaf_key(c, x, y, z), &fresh);
+    const long long s = leaf_insert(lt, key, &fresh);
     if (s < 0) { atomicExch(err, 1); }
     else {
       slot = (int)s;
       if (fresh) voxlist[atomicAdd(&counters[1], 1)] = slot;   // list of occupied cells: no table sweep later
-      atomicAdd(&lt.count[s], 1);
-      atomicMin(&lt.first[s], pix);
+      atomicAdd(&lt.rec[s].count, __popc(grp));
+      atomicMin(&lt.rec[s].first, pix);
     }
   }
-  pix_slot[pix] = slot;
+  slot = __shfl_sync(0xffffffffu, slot, leader);
+  if (pix >= 0) pix_slot[pix] = ok ? slot : -1;
 }
 
 // K11b: bucket ranges for the occupied cells (arbitrary order: the cloud is a set)
@@ -190,20 +234,24 @@ __global__ void k_ocm_ranges(const KfJob* __restrict__ jobs) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
   const int s = voxlist[v];
-  lt.offset[s] = atomicAdd(&counters[0], lt.count[s]);
+  lt.rec[s].offset = atomicAdd(&counters[0], lt.rec[s].count);
 }
 
 // K11c: scatter the pixel indices into their cell's bucket
 __global__ void k_ocm_scatter(const KfJob* __restrict__ jobs) {
   const KfJob& J = jobs[blockIdx.y];
-  const int npix = J.c.rows * J.c.cols;
   const int* __restrict__ pix_slot = J.s.pix_slot;
   const LeafTable lt = J.s.leaf;
   int* __restrict__ bucket = J.s.bucket;
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= npix) return;
-  const int s = pix_slot[pix];
-  if (s >= 0) bucket[lt.offset[s] + atomicAdd(&lt.cursor[s], 1)] = pix;
+  const int lane = threadIdx.x & 31;
+  const int pix = tile_pixel(J.c.rows, J.c.cols);
+  const int s = (pix >= 0) ? pix_slot[pix] : -1;
+  const unsigned grp = __match_any_sync(0xffffffffu, (s >= 0) ? s : -1 - lane);
+  const int leader = __ffs(grp) - 1;
+  int base = 0;
+  if (s >= 0 && lane == leader) base = lt.rec[s].offset + atomicAdd(&lt.rec[s].cursor, __popc(grp));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (s >= 0) bucket[base + __popc(grp & ((1u << lane) - 1u))] = pix;
 }
 
 // K11d: per cell: restore pixel order, sequential float centroid (PCL VoxelGrid), transform to the world frame in
@@ -224,8 +272,8 @@ __global__ void k_ocm_centroids(const KfJob* __restrict__ jobs) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
   const int s = voxlist[v];
-  const int n = lt.count[s];
-  int* b = bucket + lt.offset[s];
+  const int n = lt.rec[s].count;
+  int* b = bucket + lt.rec[s].offset;
   for (int i = 1; i < n; ++i) {   // insertion sort: ascending pixel index = row-major order
     const int val = b[i];
     int j = i - 1;
@@ -248,8 +296,11 @@ __global__ void k_ocm_centroids(const KfJob* __restrict__ jobs) {
   pts_rgb[(size_t)v * 3 + 0] = (uint8_t)(sr / fn);
   pts_rgb[(size_t)v * 3 + 1] = (uint8_t)(sg / fn);
   pts_rgb[(size_t)v * 3 + 2] = (uint8_t)(sb / fn);
-  pts_label[v] = label ? label[lt.first[s]] : 0;
-  lt.keys[s] = EMPTY_KEY; lt.count[s] = 0; lt.first[s] = 0x7fffffff; lt.cursor[s] = 0;
+  pts_label[v] = label ? label[lt.rec[s].first] : 0;
+  LeafRec fresh_rec;
+  fresh_rec.key = EMPTY_KEY; fresh_rec.count = 0; fresh_rec.first = 0x7fffffff; fresh_rec.offset = 0; fresh_rec.cursor = 0;
+  fresh_rec.pad[0] = fresh_rec.pad[1] = 0;
+  lt.rec[s] = fresh_rec;
 }
 
 // leaf <= 0: no VoxelGrid; every gated pixel is a point (used for the T-variant style clouds)
@@ -378,6 +429,13 @@ __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cma
   }
 }
 
+__global__ void k_ocm_fill_leaf(LeafRec* p, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  LeafRec r;
+  r.key = EMPTY_KEY; r.count = 0; r.first = 0x7fffffff; r.offset = 0; r.cursor = 0; r.pad[0] = r.pad[1] = 0;
+  p[i] = r;
+}
 __global__ void k_ocm_fill_u64(unsigned long long* p, unsigned long long v, long long n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -489,7 +547,7 @@ struct ocm {
   }
   static void free_slot(KfScratch& k) {
     auto F = [](void* p) { if (p) cudaFree(p); };
-    F(k.leaf.keys); F(k.leaf.count); F(k.leaf.first); F(k.leaf.offset); F(k.leaf.cursor); F(k.pix_slot); F(k.bucket); F(k.voxlist);
+    F(k.leaf.rec); F(k.pix_slot); F(k.bucket); F(k.voxlist);
     F(k.pts); F(k.pts_rgb); F(k.pts_label);
     k = KfScratch{};
   }
@@ -555,15 +613,13 @@ int ocm::ensure_scratch(int r, int c, int nslots) {
     KfScratch k{};
     const int id = (int)slots.size();
     k.leaf.mask = leaf_cap - 1;
-    B200_CUDA(cudaMalloc(&k.leaf.keys, 8 * leaf_cap)); B200_CUDA(cudaMalloc(&k.leaf.count, 4 * leaf_cap));
-    B200_CUDA(cudaMalloc(&k.leaf.first, 4 * leaf_cap)); B200_CUDA(cudaMalloc(&k.leaf.offset, 4 * leaf_cap));
-    B200_CUDA(cudaMalloc(&k.leaf.cursor, 4 * leaf_cap));
+    B200_CUDA(cudaMalloc(&k.leaf.rec, sizeof(LeafRec) * leaf_cap));
     B200_CUDA(cudaMalloc(&k.pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&k.bucket, 4 * npix));
     B200_CUDA(cudaMalloc(&k.voxlist, 4 * npix));
     B200_CUDA(cudaMalloc(&k.pts, 12 * npix)); B200_CUDA(cudaMalloc(&k.pts_rgb, 3 * npix)); B200_CUDA(cudaMalloc(&k.pts_label, npix));
     k.counters = d_counters + 4 * id;
-    fill(k.leaf.keys, EMPTY_KEY, leaf_cap); fill(k.leaf.count, 0, leaf_cap); fill(k.leaf.first, 0x7fffffff, leaf_cap);
-    fill(k.leaf.cursor, 0, leaf_cap);
+    k_ocm_fill_leaf<<<(unsigned)((leaf_cap + 255) / 256), 256, 0, stream>>>(k.leaf.rec, leaf_cap);
+    ++launches;
     B200_CUDA(cudaGetLastError());
     slots.push_back(k);
   }
@@ -622,9 +678,10 @@ int ocm::insert_batch(int n, const float* const* dd, const uint8_t* const* drgb,
     B200_CUDA(cudaMemsetAsync(d_counters, 0, 16 * B, stream));
     const dim3 g256((npix + 255) / 256, B), g128((npix + 127) / 128, B);
     if (prm.leaf > 0) {
-      k_ocm_bin<<<g256, 256, 0, stream>>>(dj, d_err);
+      const dim3 gt(tile_blocks(r, c, 8), B);   // 8 x 4 pixel tile per warp
+      k_ocm_bin<<<gt, 256, 0, stream>>>(dj, d_err);
       k_ocm_ranges<<<g256, 256, 0, stream>>>(dj);
-      k_ocm_scatter<<<g256, 256, 0, stream>>>(dj);
+      k_ocm_scatter<<<gt, 256, 0, stream>>>(dj);
       k_ocm_centroids<<<g128, 128, 0, stream>>>(dj);
       launches += 4;
     } else {
