@@ -20,7 +20,8 @@ struct GlueOut {     // SoA per frame, stride cap
 // and the AoS -> SoA split the matcher kernel reads.
 __global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restrict__ kps, const int* __restrict__ nkp,
                                                     int cap, const float* __restrict__ depth,
-                                                    const uint16_t* __restrict__ depth16, float depth_factor, int rows,
+                                                    const uint16_t* __restrict__ depth16,
+                                                    const uint16_t* __restrict__ kpd16, float depth_factor, int rows,
                                                     int cols, const float* __restrict__ Tcw, float fx, float fy,
                                                     float cx, float cy, float bf, GlueOut o) {
   const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,7 +34,9 @@ __global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restri
   // straight out of pinned host memory over PCIe, one 2-byte read per keypoint instead of uploading 0.6 MB per frame
   // -- and converted like convertTo(CV_32F, mDepthMapFactor) does (src/Tracking.cc:366-367).
   const size_t di = (size_t)f * rows * cols + (size_t)(int)v * cols + (int)u;
-  const float d = depth16 ? __fmul_rn((float)depth16[di], depth_factor) : depth[di];
+  // kpd16: the same CV_16U pixel, already fetched per keypoint by k_depth_prefetch
+  const float d = kpd16 ? __fmul_rn((float)kpd16[g], depth_factor)
+                        : (depth16 ? __fmul_rn((float)depth16[di], depth_factor) : depth[di]);
   o.x[g] = u; o.y[g] = v; o.ang[g] = kp.angle; o.oct[g] = kp.octave;
   float ur = -1.f, dd = -1.f;
   uint8_t ok = 0;
@@ -54,6 +57,30 @@ __global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restri
     ok = 1;
   }
   o.uright[g] = ur; o.depth[g] = dd; o.valid[g] = ok;
+}
+
+// Depth under the selected keypoints, fetched as soon as the selection exists (the final KeyPoint coordinates are the
+// level coordinates times the level's scale factor, src/ORBextractor.cc:1104-1110, exactly as k_orient_desc forms them)
+// -- on a side stream, so the PCIe round trips of the in-place host reads overlap blur and descriptors.
+__global__ void __launch_bounds__(256) k_depth_prefetch(LevelTab lt, const unsigned* __restrict__ sel,
+                                                        const int* __restrict__ selcnt, int sel_per_frame, int cap,
+                                                        const uint16_t* __restrict__ depth16, int rows, int cols, int f0,
+                                                        uint16_t* __restrict__ kpd16) {
+  const int f = f0 + blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cap) return;
+  const int* sc = selcnt + (size_t)f * lt.nlevels;
+  int l = -1, idx = 0, acc = 0;
+  for (int q = 0; q < lt.nlevels; ++q) {
+    const int c = sc[q];
+    if (l < 0 && j < acc + c) { l = q; idx = j - acc; }
+    acc += c;
+  }
+  if (l < 0) return;
+  const unsigned pk = sel[(size_t)f * sel_per_frame + lt.sel_off[l] + idx];
+  const float s = lt.sf[l];
+  const float u = (l != 0) ? __fmul_rn((float)kp_x(pk), s) : (float)kp_x(pk);
+  const float v = (l != 0) ? __fmul_rn((float)kp_y(pk), s) : (float)kp_y(pk);
+  kpd16[(size_t)f * cap + j] = depth16[(size_t)f * rows * cols + (size_t)(int)v * cols + (int)u];
 }
 
 // imDepth.convertTo(CV_32F, mDepthMapFactor) (src/Tracking.cc:366-367): float(u16) * factor, 4 pixels per thread
@@ -89,13 +116,17 @@ struct orbs {
   bool full_depth_valid = false, force_full_depth_upload = false;
   int chunk_frames = 128;   // frames per upload chunk of the host-buffer entries
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t gather_stream = nullptr;   // in-place depth reads under the keypoints (sparse mode)
+  cudaEvent_t sel_ev = nullptr, gather_ev = nullptr;
+  uint16_t* d_kpd16 = nullptr;            // [maxF][cap] depth under the keypoints
+  const uint16_t* sparse_d16 = nullptr;   // device alias of the caller's page-locked depth during a sparse call
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool have = false;
   void free_bufs() {
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(d_x); F(d_y); F(d_ang); F(d_ur); F(d_dep); F(d_xw); F(d_oct); F(d_valid); F(d_c2l); F(d_nm); F(d_count);
-    F(d_gidx); F(d_goff); F(d_acc); F(d_list); F(d_gray); F(d_depth); F(d_T); F(d_depth16);
-    d_depth16 = nullptr;
+    F(d_gidx); F(d_goff); F(d_acc); F(d_list); F(d_gray); F(d_depth); F(d_T); F(d_depth16); F(d_kpd16);
+    d_depth16 = nullptr; d_kpd16 = nullptr;
     d_x = d_y = d_ang = d_ur = d_dep = d_xw = nullptr; d_oct = nullptr; d_valid = nullptr;
     d_c2l = d_nm = d_count = d_gidx = d_goff = d_acc = nullptr; d_list = nullptr; d_gray = nullptr; d_depth = d_T = nullptr;
   }
@@ -103,6 +134,9 @@ struct orbs {
     DeviceGuard g(device);
     free_bufs();
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (gather_stream) cudaStreamDestroy(gather_stream);
+    if (sel_ev) cudaEventDestroy(sel_ev);
+    if (gather_ev) cudaEventDestroy(gather_ev);
     for (cudaEvent_t e : chunk_ev) if (e) cudaEventDestroy(e);
     delete ex;
   }
@@ -126,15 +160,16 @@ struct orbs {
       B200_CUDA(cudaMalloc(&d_depth, (size_t)maxF * rows * cols * 4));
       B200_CUDA(cudaMalloc(&d_T, (size_t)maxF * 64));
       B200_CUDA(cudaMalloc(&d_depth16, (size_t)maxF * rows * cols * 2));
+      B200_CUDA(cudaMalloc(&d_kpd16, (size_t)maxF * cap * 2));
     }
     return B200ORB_OK;
   }
   int run(const uint8_t* dg, const float* dd, const float* dT, int F, const uint16_t* dd16 = nullptr, float factor = 0.f,
-          bool extracted = false) {
+          bool extracted = false, const uint16_t* kpd16 = nullptr) {
     cudaStream_t st = ex->stream;
     if (!extracted) B200_CHECK(ex->run(dg, cols, (size_t)rows * cols, F));
     GlueOut go{d_x, d_y, d_ang, d_ur, d_dep, d_xw, d_oct, d_valid};
-    k_frame_glue<<<dim3((cap + 255) / 256, F), 256, 0, st>>>(ex->d_kps, ex->d_n, cap, dd, dd16, factor, rows, cols, dT, prm.fx, prm.fy,
+    k_frame_glue<<<dim3((cap + 255) / 256, F), 256, 0, st>>>(ex->d_kps, ex->d_n, cap, dd, dd16, kpd16, factor, rows, cols, dT, prm.fx, prm.fy,
                                                             prm.cx, prm.cy, prm.bf, go);
     ++launches;
     B200_CHECK(ex->prof_mark(ST_GLUE + 1));
@@ -206,6 +241,20 @@ int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d
   return B200ORB_OK;
 }
 
+// orbx::after_select hook of the sparse-depth mode: the keypoints of frames [f0, f0 + F) are selected -> fetch the depth
+// under them on the side stream (the stream of the extractor goes on with blur and descriptors meanwhile)
+static int orbs_after_select(void* ctx, int f0, int F) {
+  orbs* h = static_cast<orbs*>(ctx);
+  orbx* ex = h->ex;
+  B200_CUDA(cudaEventRecord(h->sel_ev, ex->stream));
+  B200_CUDA(cudaStreamWaitEvent(h->gather_stream, h->sel_ev, 0));
+  k_depth_prefetch<<<dim3((h->cap + 255) / 256, F), 256, 0, h->gather_stream>>>(ex->ltab, ex->d_sel, ex->d_selcnt, ex->sel_per_frame,
+                                                                               h->cap, h->sparse_d16, h->rows, h->cols, f0, h->d_kpd16);
+  ++h->launches;
+  B200_CUDA(cudaEventRecord(h->gather_ev, h->gather_stream));
+  return B200ORB_OK;
+}
+
 static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, const uint16_t* depth16, float factor,
                             const float* Tcw, int nframes, int rows, int cols, OrbxKeyPoint* kps, uint8_t* desc,
                             int32_t* nkp, int32_t* cur2last, int32_t* nmatch, int cap, bool wait = true) {
@@ -226,6 +275,27 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
     for (cudaEvent_t& e : h->chunk_ev) B200_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   const int nchunk = (int)std::min<size_t>(7, (F + h->chunk_frames - 1) / h->chunk_frames);   // >= 64-frame chunks keep each launch wide enough
+  // Page-locked CV_16U depth (cudaHostAlloc / cudaHostRegister, e.g. torch.pin_memory): the only depth pixels the
+  // tracking path ever reads are the ones under the keypoints (Frame::ComputeStereoFromRGBD), so the 0.6 MB/frame
+  // images are never uploaded; the pixels are read in place over PCIe as soon as a chunk's keypoints are selected.
+  const uint16_t* d16_sparse = nullptr;
+  if (depth16 && !h->force_full_depth_upload) {
+    cudaPointerAttributes at;
+    void* dev_alias = nullptr;
+    if (cudaPointerGetAttributes(&at, depth16) == cudaSuccess && at.type == cudaMemoryTypeHost &&
+        cudaHostGetDevicePointer(&dev_alias, const_cast<uint16_t*>(depth16), 0) == cudaSuccess && dev_alias)
+      d16_sparse = reinterpret_cast<const uint16_t*>(dev_alias);
+    else
+      cudaGetLastError();
+  }
+  if (d16_sparse && !h->gather_stream) {
+    B200_CUDA(cudaStreamCreateWithFlags(&h->gather_stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreateWithFlags(&h->sel_ev, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&h->gather_ev, cudaEventDisableTiming));
+  }
+  h->sparse_d16 = d16_sparse;
+  h->ex->after_select = d16_sparse ? &orbs_after_select : nullptr;
+  h->ex->after_select_ctx = h;
   {
     // the copy stream may only overwrite d_gray once the previous call's kernels are done with it
     B200_CUDA(cudaEventRecord(h->chunk_ev[7], st));
@@ -238,32 +308,23 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
       B200_CHECK(h->ex->run(h->d_gray + px * f0, cols, px, (int)(f1 - f0), (int)f0));
     }
   }
-  const uint16_t* d16_sparse = nullptr;   // non-null: depth is read per keypoint from this (device-visible) u16 image
+  h->ex->after_select = nullptr;
   h->full_depth_valid = true;
-  if (depth16) {
-    // Page-locked host depth (cudaHostAlloc / cudaHostRegister, e.g. torch.pin_memory): the only depth pixels the
-    // tracking path ever reads are the ones under the keypoints (Frame::ComputeStereoFromRGBD), so they are gathered
-    // straight from host memory by the glue kernel and the 0.6 MB/frame image is never uploaded.
-    cudaPointerAttributes at;
-    void* dev_alias = nullptr;
-    if (!h->force_full_depth_upload && cudaPointerGetAttributes(&at, depth16) == cudaSuccess && at.type == cudaMemoryTypeHost &&
-        cudaHostGetDevicePointer(&dev_alias, const_cast<uint16_t*>(depth16), 0) == cudaSuccess && dev_alias) {
-      d16_sparse = reinterpret_cast<const uint16_t*>(dev_alias);
-      h->full_depth_valid = false;
-    } else {
-      cudaGetLastError();
-      if ((px * F) % 4) { set_error("u16 depth path needs rows*cols*nframes to be a multiple of 4"); return B200ORB_EINVAL; }
-      B200_CUDA(cudaMemcpyAsync(h->d_depth16, depth16, px * F * 2, cudaMemcpyHostToDevice, st));
-      const size_t n4 = px * F / 4;
-      k_depth_u16_to_f32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ushort4*>(h->d_depth16),
-                                                                       reinterpret_cast<float4*>(h->d_depth), factor, n4);
-      ++h->launches;
-    }
+  if (d16_sparse) {
+    h->full_depth_valid = false;
+    B200_CUDA(cudaStreamWaitEvent(st, h->gather_ev, 0));   // the last chunk's prefetch (the side stream is in order)
+  } else if (depth16) {
+    if ((px * F) % 4) { set_error("u16 depth path needs rows*cols*nframes to be a multiple of 4"); return B200ORB_EINVAL; }
+    B200_CUDA(cudaMemcpyAsync(h->d_depth16, depth16, px * F * 2, cudaMemcpyHostToDevice, st));
+    const size_t n4 = px * F / 4;
+    k_depth_u16_to_f32<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const ushort4*>(h->d_depth16),
+                                                                     reinterpret_cast<float4*>(h->d_depth), factor, n4);
+    ++h->launches;
   } else {
     B200_CUDA(cudaMemcpyAsync(h->d_depth, depth, px * F * 4, cudaMemcpyHostToDevice, st));
   }
   B200_CUDA(cudaMemcpyAsync(h->d_T, Tcw, F * 64, cudaMemcpyHostToDevice, st));
-  B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes, d16_sparse, factor, /*extracted=*/true));
+  B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes, d16_sparse, factor, /*extracted=*/true, d16_sparse ? h->d_kpd16 : nullptr));
   const size_t hc = h->cap;
   if ((size_t)cap == hc) {
     B200_CUDA(cudaMemcpyAsync(kps, h->ex->d_kps, sizeof(OrbxKeyPoint) * hc * F, cudaMemcpyDeviceToHost, st));

@@ -371,6 +371,7 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
     ++launches;
   }
   B200_CHECK(prof_mark(ST_QUADTREE + 1));
+  if (after_select) B200_CHECK(after_select(after_select_ctx, f0, F));
   // K4 blur: one launch over every (level, 128x35 tile, frame) when all planes are 4-byte aligned
   {
     bool aligned = true;

@@ -18,6 +18,10 @@ struct orbx {
   int device = 0;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  // optional hook, called by run() right after the keypoint selection of frames [f0, f0 + F) has been enqueued
+  // (the batch tracker uses it to start fetching the depth under the selected keypoints while blur / descriptors run)
+  int (*after_select)(void* ctx, int f0, int F) = nullptr;
+  void* after_select_ctx = nullptr;
   // tables of the constructor (src/ORBextractor.cc:404-465)
   float sf[b200::MAX_LEVELS], invsf[b200::MAX_LEVELS], sigma2[b200::MAX_LEVELS], invsigma2[b200::MAX_LEVELS];
   int nfeat[b200::MAX_LEVELS];

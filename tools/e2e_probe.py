@@ -19,7 +19,7 @@ kf_d16 = torch.from_numpy(np.ascontiguousarray(d16.numpy()[kfs])).pin_memory()
 kf_rgb = torch.from_numpy(np.ascontiguousarray(rgb[kfs])).pin_memory()
 factor = np.float32(1.0 / synth.DEPTH_FACTOR)
 mk = lambda: StreamTracker(1000, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, max_frames=F)
-trk = [mk(), mk()]
+trk = [mk(), mk(), mk()]
 outs = [t.alloc_outputs(F, pinned=True) for t in trk]
 pcm = PointCloudMapping(0.05)
 Tk = T.numpy()[kfs]
@@ -52,9 +52,13 @@ def run(n, inflight, mapper, chunk, full_depth):
     return F * n / dt, dt / n * 1e3
 
 
-for inflight in (1, 2):
-    for mapper in (False, True):
-        for chunk in (64, 128, 256):
-            for full in (False, True):
-                fps, ms = run(8, inflight, mapper, chunk, full)
-                print("inflight %d mapper %d chunk %3d full_depth %d : %8.0f frames/s  %.2f ms/batch" % (inflight, mapper, chunk, full, fps, ms))
+cfgs = [(2, False, 128, False), (2, True, 128, False)] if len(sys.argv) > 2 else \
+    [(i, m, c, f) for i in (1, 2) for m in (False, True) for c in (64, 128, 256) for f in (False, True)]
+for inflight, mapper, chunk, full in cfgs:
+    trk[0].profile_enable(True)
+    trk[0].profile_read()
+    fps, ms = run(12, inflight, mapper, chunk, full)
+    print("inflight %d mapper %d chunk %3d full_depth %d : %8.0f frames/s  %.2f ms/batch" % (inflight, mapper, chunk, full, fps, ms))
+    st_ms, frames, runs = trk[0].profile_read()
+    trk[0].profile_enable(False)
+    print("   handle 0 stage ms per batch:", {k: round(v / max(runs, 1) * (F / max(frames / max(runs, 1), 1)), 3) for k, v in st_ms.items()}, "sum %.3f" % (sum(st_ms.values()) / max(frames, 1) * F))
