@@ -163,6 +163,12 @@ def run_reference(args):
     return 0
 
 
+# DRAM traffic of the single-launch stages, bytes per frame, from the ncu capture summarised in
+# profiles/r01_ncu_v3_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of a 256-frame launch / 256)
+NCU_DRAM_BYTES_PER_FRAME = {"fast": (231577856 + 41558528) / 256.0, "quadtree": (74913536 + 91995392) / 256.0,
+                            "orient_desc": (463287808 + 18053888) / 256.0}
+
+
 def workload_config(args, frames):
     return {"workload": "TUM fr3_walking-shaped synthetic RGB-D stream 640x480, ORBextractor(1000,1.2,8,20,7) + "
                         "SearchByProjection(cur,last,th=15) per frame, every %dth frame a keyframe inserted into the "
@@ -339,7 +345,11 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                         "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "frac": stages[dom]["frac"],
+                         "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * F if dom in NCU_DRAM_BYTES_PER_FRAME else None),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at 256 "
+                                           "frames/launch (profiles/r01_ncu_v3_summary.txt), scaled to this launch",
+                         "peak_source": peak_src,
                          "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
                                       "algorithmic_bytes_per_frame": pipeline_bytes(n_kp)},
                          "stages": stages},
