@@ -92,11 +92,11 @@ int orbx::init(const OrbxParams& p, int dev) {
 void orbx::free_geometry() {
   auto F = [](void* p) { if (p) cudaFree(p); };
   F(d_raw); F(d_blur); F(d_cells); F(d_cand); F(d_cellcnt); F(d_qkp); F(d_qnode); F(d_sel); F(d_selcnt);
-  F(d_candcnt); F(d_kps); F(d_desc); F(d_n); F(d_xt); F(d_yt); F(d_tmp); F(d_blur_tiles); F(d_blur_edges);
+  F(d_candcnt); F(d_kps); F(d_desc); F(d_n); F(d_xt); F(d_yt); F(d_xg); F(d_tmp); F(d_blur_tiles); F(d_blur_edges);
   d_blur_tiles = nullptr; d_blur_edges = nullptr;
   d_raw = d_blur = nullptr; d_cells = nullptr; d_cand = nullptr; d_cellcnt = nullptr; d_qkp = nullptr;
   d_qnode = nullptr; d_sel = nullptr; d_selcnt = nullptr; d_candcnt = nullptr; d_kps = nullptr; d_desc = nullptr;
-  d_n = nullptr; d_xt = d_yt = nullptr; d_tmp = nullptr; tmp_bytes = 0;
+  d_n = nullptr; d_xt = d_yt = nullptr; d_xg = nullptr; d_tmp = nullptr; tmp_bytes = 0;
   if (h_stage) cudaFreeHost(h_stage);
   h_stage = nullptr; stage_bytes = 0;
   rows = cols = maxF = 0;
@@ -133,6 +133,8 @@ int orbx::ensure_geometry(int r, int c, int F) {
   frame_bytes = align_up_sz(off, 256);
   // resize tables
   std::vector<int2> xt, yt;
+  std::vector<int4> xg;
+  resize_group_ok = true;
   for (int l = 1; l < nl; ++l) {
     xt_off[l] = (int)xt.size();
     yt_off[l] = (int)yt.size();
@@ -150,6 +152,22 @@ int orbx::ensure_geometry(int r, int c, int F) {
     };
     fill(lw[l], lw[l - 1], xt);
     fill(lh[l], lh[l - 1], yt);
+    // group table of k_resize_g
+    xg_off[l] = (int)xg.size();
+    for (int dx0 = 0; dx0 < lw[l]; dx0 += 4) {
+      const int2* t = xt.data() + xt_off[l];
+      int sx[4], cf[4];
+      for (int i = 0; i < 4; ++i) { const int2 e = t[std::min(dx0 + i, lw[l] - 1)]; sx[i] = e.x; cf[i] = e.y; }
+      for (int i = 1; i < 4; ++i) if (sx[i] < sx[0]) sx[i] = sx[0];   // (replicated tail entries never precede sx[0])
+      int sels = 0;
+      for (int i = 0; i < 4; ++i) {
+        const int dlt = sx[i] - sx[0];
+        if (dlt + 1 > 7) resize_group_ok = false;   // scale > 2: the byte-window path does not apply
+        sels |= (((dlt & 7) | (((dlt + 1) & 7) << 4)) & 0xff) << (8 * i);
+      }
+      xg.push_back(make_int4(sx[0] >> 2, 8 * (sx[0] & 3), sels, 0));
+      xg.push_back(make_int4(cf[0], cf[1], cf[2], cf[3]));
+    }
   }
   // FAST cells (:775-815) and quad-tree constants (:545-547)
   std::vector<CellDesc> cells;
@@ -270,6 +288,7 @@ int orbx::ensure_geometry(int r, int c, int F) {
   B200_CUDA(cudaMalloc(&d_n, sizeof(int) * Fz));
   B200_CUDA(cudaMalloc(&d_xt, sizeof(int2) * std::max<size_t>(xt.size(), 1)));
   B200_CUDA(cudaMalloc(&d_yt, sizeof(int2) * std::max<size_t>(yt.size(), 1)));
+  B200_CUDA(cudaMalloc(&d_xg, sizeof(int4) * std::max<size_t>(xg.size(), 1)));
   {
     std::vector<BlurTile> bt;
     for (int l = 0; l < nl; ++l)
@@ -291,6 +310,7 @@ int orbx::ensure_geometry(int r, int c, int F) {
   B200_CUDA(cudaMemcpyAsync(d_cells, cells.data(), sizeof(CellDesc) * ncells, cudaMemcpyHostToDevice, stream));
   if (!xt.empty()) B200_CUDA(cudaMemcpyAsync(d_xt, xt.data(), sizeof(int2) * xt.size(), cudaMemcpyHostToDevice, stream));
   if (!yt.empty()) B200_CUDA(cudaMemcpyAsync(d_yt, yt.data(), sizeof(int2) * yt.size(), cudaMemcpyHostToDevice, stream));
+  if (!xg.empty()) B200_CUDA(cudaMemcpyAsync(d_xg, xg.data(), sizeof(int4) * xg.size(), cudaMemcpyHostToDevice, stream));
   B200_CUDA(cudaStreamSynchronize(stream));
   // blurred pyramid view never changes; raw view's level 0 may alias the caller's buffer per call
   for (int l = 0; l < nl; ++l) {
@@ -334,7 +354,10 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
     dim3 blk(32, 8), grd((lw[l] + 127) / 128, (lh[l] + 7) / 8, F);
     // k_resize_w needs aligned source rows and 4 outputs within a 12-byte source window (scale factor <= 2)
     const bool src_aligned = prm.scale_factor <= 2.0f && (((uintptr_t)rawv.p[l - 1]) & 3) == 0 && (rawv.pitch[l - 1] & 3) == 0 && (rawv.fstride[l - 1] & 3) == 0;
-    if (src_aligned)
+    if (src_aligned && resize_group_ok)
+      k_resize_g<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lh[l - 1], rawv.p[l],
+                                         rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xg + xg_off[l], d_yt + yt_off[l]);
+    else if (src_aligned)
       k_resize_w<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lw[l - 1], lh[l - 1],
                                          rawv.p[l], rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xt + xt_off[l],
                                          d_yt + yt_off[l]);

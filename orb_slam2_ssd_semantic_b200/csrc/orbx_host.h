@@ -32,7 +32,7 @@ struct orbx {
   int lw[b200::MAX_LEVELS], lh[b200::MAX_LEVELS], lpitch[b200::MAX_LEVELS];
   size_t loff[b200::MAX_LEVELS];
   size_t frame_bytes = 0;
-  int xt_off[b200::MAX_LEVELS], yt_off[b200::MAX_LEVELS];
+  int xt_off[b200::MAX_LEVELS], yt_off[b200::MAX_LEVELS], xg_off[b200::MAX_LEVELS];
   b200::LevelTab ltab{};
   b200::PyrView rawv{}, blurv{};
   int ncells = 0, slots_per_frame = 0, sel_per_frame = 0, cap = 0, qt_cap = 0;
@@ -53,6 +53,8 @@ struct orbx {
   uint8_t* d_desc = nullptr;
   int* d_n = nullptr;
   int2 *d_xt = nullptr, *d_yt = nullptr;
+  bool resize_group_ok = true;
+  int4* d_xg = nullptr;   // per 4-output group: {first source word, 8*byte phase, PRMT selectors, -} + 4 coefficient pairs
   b200::BlurTile* d_blur_tiles = nullptr;
   b200::BlurEdge* d_blur_edges = nullptr;
   int n_blur_tiles = 0, n_blur_edges = 0, blur_edge_rows = 0;

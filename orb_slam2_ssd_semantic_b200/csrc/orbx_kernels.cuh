@@ -132,6 +132,50 @@ __global__ void __launch_bounds__(256) k_resize_w(const uint8_t* __restrict__ sr
   *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
 }
 
+// K1 (group-table path): a thread's 4 adjacent outputs start at a fixed destination column (a multiple of 4), so
+// everything that depends only on the columns is tabulated per GROUP: first source word, byte phase, the four PRMT
+// selectors (relative to the group's first source byte) and the four coefficient pairs -- two 128-bit loads.  The two
+// source rows are funnel-shifted into 8-byte windows that start at the group's first source byte; each output then
+// costs one PRMT + one IDP.2A per row plus the vertical pass.  Same integer arithmetic as k_resize (needs scale <= 2:
+// the 4 outputs read at most 8 consecutive source bytes).
+__global__ void __launch_bounds__(256) k_resize_g(const uint8_t* __restrict__ src, int spitch, size_t sfs, int sh,
+                                                  uint8_t* __restrict__ dst, int dpitch, size_t dfs, int dw, int dh,
+                                                  const int4* __restrict__ xg /* 2 per group */,
+                                                  const int2* __restrict__ yt) {
+  const int g = blockIdx.x * 32 + threadIdx.x;
+  const int dx0 = g * 4;
+  const int dy = blockIdx.y * 8 + threadIdx.y;
+  if (dx0 >= dw || dy >= dh) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
+  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
+  const int2 ty = __ldg(&yt[dy]);
+  const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
+  const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
+  const int4 ga = __ldg(&xg[2 * g]), gc = __ldg(&xg[2 * g + 1]);   // {word, 8*phase, selectors, -} / coefficients
+  const int wlast = (spitch >> 2) - 1;                              // never read past the row's last word
+  const int w0 = ga.x, w1 = min(ga.x + 1, wlast), w2 = min(ga.x + 2, wlast);
+  const unsigned* r0 = reinterpret_cast<const unsigned*>(s + (size_t)sy0 * spitch);
+  const unsigned* r1 = reinterpret_cast<const unsigned*>(s + (size_t)sy1 * spitch);
+  const unsigned a0 = __ldg(r0 + w0), a1 = __ldg(r0 + w1), a2 = __ldg(r0 + w2);
+  const unsigned c0 = __ldg(r1 + w0), c1 = __ldg(r1 + w1), c2 = __ldg(r1 + w2);
+  const unsigned ph = (unsigned)ga.y;
+  const unsigned A_lo = __funnelshift_r(a0, a1, ph), A_hi = __funnelshift_r(a1, a2, ph);   // bytes sx0 .. sx0+7
+  const unsigned C_lo = __funnelshift_r(c0, c1, ph), C_hi = __funnelshift_r(c1, c2, ph);
+  const unsigned sels = (unsigned)ga.z;
+  const int co[4] = {gc.x, gc.y, gc.z, gc.w};
+  unsigned out = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned sel = sels >> (8 * i);   // low two nibbles: bytes d_i, d_i+1 of the window
+    const unsigned p0 = __byte_perm(A_lo, A_hi, sel), p1 = __byte_perm(C_lo, C_hi, sel);
+    const int h0 = (int)__dp2a_lo((unsigned)co[i], p0, 0u);   // a0*s[x] + a1*s[x+1]
+    const int h1 = (int)__dp2a_lo((unsigned)co[i], p1, 0u);
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    out |= (unsigned)(v & 0xff) << (8 * i);
+  }
+  *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K2  per-cell FAST-9/16 + strict 3x3 NMS with the ini/min threshold fallback
 //     (cv::FAST TYPE_9_16 nonmax=true; call sites :818,:823; cell loop :798-838).
