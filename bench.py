@@ -273,11 +273,13 @@ def run_b200(args):
     outs = st.alloc_outputs(F, pinned=True)
     factor = np.float32(1.0 / synth.DEPTH_FACTOR)
     # Two tracker handles used alternately keep two batches in flight: the upload of batch k+1 and the download of
-    # batch k-1 overlap the kernels of batch k.  Every batch still crosses PCIe in both directions inside the timed
+    # batch k-1 overlap the kernels of batch k (orbs_chain_after orders the kernels of consecutive batches).  Every batch still crosses PCIe in both directions inside the timed
     # region, and its results are on the host (sync of its handle) before the batch after the next is submitted.
     st2 = StreamTracker(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, TH,
                         NNRATIO, True, F, device=local)
     trk = [st, st2]
+    for t in trk:
+        t.set_chunk_frames(F)   # whole-batch uploads: they overlap the other handle's kernels, not this handle's own
     outs2 = [outs, st2.alloc_outputs(F, pinned=True)]
 
     def submit(k):
@@ -286,6 +288,7 @@ def run_b200(args):
         pcm.insert_keyframes_u16(kf_d16, kf_rgb, factor, T[kfs], synth.FX, synth.FY, synth.CX, synth.CY)
         # tracker: H2D gray in chunks overlapped with extraction; the page-locked CV_16U depth is read under the
         # keypoints in place (zero-copy gather); D2H keypoints, descriptors, matches
+        trk[k & 1].chain_after(trk[(k + 1) & 1])   # kernels of batch k start when those of batch k-1 are done
         trk[k & 1].submit_batch_u16(st_gray, st_d16, factor, st_T, outs2[k & 1])
 
     def collect(k):

@@ -29,7 +29,7 @@ EXPORTS = [
     "orbx_profile_enable", "orbx_profile_read",
     "orbm_hamming", "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_search_by_projection_last",
     "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_by_bow_kf", "orbm_search_projected",
-    "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_u16", "orbs_submit_batch_u16", "orbs_device_inputs", "orbs_set_full_depth_upload", "orbs_set_chunk_frames", "b200orb_depth_u16_to_f32_device", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
+    "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_u16", "orbs_submit_batch_u16", "orbs_device_inputs", "orbs_set_full_depth_upload", "orbs_set_chunk_frames", "orbs_chain_after", "b200orb_depth_u16_to_f32_device", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
     "orbs_stream", "orbs_launch_count", "orbs_extractor",
     "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device", "ocm_insert_keyframes_device", "ocm_insert_keyframes_u16",
     "ocm_last_points", "ocm_num_leaves", "ocm_export_leaves", "ocm_query", "ocm_summary_count",
@@ -94,6 +94,7 @@ def lib() -> C.CDLL:
     L.orbs_submit_batch_u16.argtypes = [vp, vp, vp, C.c_float, vp, i, i, i, vp, vp, vp, vp, vp, i]
     L.orbs_set_full_depth_upload.argtypes = [vp, i]
     L.orbs_set_chunk_frames.argtypes = [vp, i]
+    L.orbs_chain_after.argtypes = [vp, vp]
     L.b200orb_depth_u16_to_f32_device.argtypes = [vp, vp, sz, C.c_float, vp]
     L.orbs_device_inputs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.orbs_track_batch_device.argtypes = [vp, vp, vp, vp, i, i, i]

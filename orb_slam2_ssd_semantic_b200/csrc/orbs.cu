@@ -118,6 +118,8 @@ struct orbs {
   cudaStream_t copy_stream = nullptr;
   cudaStream_t gather_stream = nullptr;   // in-place depth reads under the keypoints (sparse mode)
   cudaEvent_t sel_ev = nullptr, gather_ev = nullptr;
+  cudaEvent_t compute_done_ev = nullptr;   // recorded after the last kernel of a host-buffer batch (before its downloads)
+  orbs* chain_prev = nullptr;              // orbs_chain_after: the next batch's kernels wait for that handle's kernels
   uint16_t* d_kpd16 = nullptr;            // [maxF][cap] depth under the keypoints
   const uint16_t* sparse_d16 = nullptr;   // device alias of the caller's page-locked depth during a sparse call
   cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -136,6 +138,7 @@ struct orbs {
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (gather_stream) cudaStreamDestroy(gather_stream);
     if (sel_ev) cudaEventDestroy(sel_ev);
+    if (compute_done_ev) cudaEventDestroy(compute_done_ev);
     if (gather_ev) cudaEventDestroy(gather_ev);
     for (cudaEvent_t e : chunk_ev) if (e) cudaEventDestroy(e);
     delete ex;
@@ -300,6 +303,10 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
     // the copy stream may only overwrite d_gray once the previous call's kernels are done with it
     B200_CUDA(cudaEventRecord(h->chunk_ev[7], st));
     B200_CUDA(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[7], 0));
+    // orbs_chain_after: this batch's kernels start when the other handle's kernels are done -- the uploads enqueued
+    // below (copy stream) and that handle's downloads run meanwhile, and kernels of two batches never share the SMs
+    if (h->chain_prev && h->chain_prev->compute_done_ev) B200_CUDA(cudaStreamWaitEvent(st, h->chain_prev->compute_done_ev, 0));
+    h->chain_prev = nullptr;
     for (int c = 0; c < nchunk; ++c) {
       const size_t f0 = F * c / nchunk, f1 = F * (c + 1) / nchunk;
       B200_CUDA(cudaMemcpyAsync(h->d_gray + px * f0, gray + px * f0, px * (f1 - f0), cudaMemcpyHostToDevice, h->copy_stream));
@@ -325,6 +332,8 @@ static int track_batch_host(orbs_t* h, const uint8_t* gray, const float* depth, 
   }
   B200_CUDA(cudaMemcpyAsync(h->d_T, Tcw, F * 64, cudaMemcpyHostToDevice, st));
   B200_CHECK(h->run(h->d_gray, h->d_depth, h->d_T, nframes, d16_sparse, factor, /*extracted=*/true, d16_sparse ? h->d_kpd16 : nullptr));
+  if (!h->compute_done_ev) B200_CUDA(cudaEventCreateWithFlags(&h->compute_done_ev, cudaEventDisableTiming));
+  B200_CUDA(cudaEventRecord(h->compute_done_ev, st));
   const size_t hc = h->cap;
   if ((size_t)cap == hc) {
     B200_CUDA(cudaMemcpyAsync(kps, h->ex->d_kps, sizeof(OrbxKeyPoint) * hc * F, cudaMemcpyDeviceToHost, st));
@@ -391,6 +400,15 @@ int b200orb_depth_u16_to_f32_device(const uint16_t* d_src, float* d_dst, size_t 
 int orbs_set_chunk_frames(orbs_t* h, int frames) {
   if (!h || frames <= 0) { set_error("bad argument"); return B200ORB_EINVAL; }
   h->chunk_frames = frames;
+  return B200ORB_OK;
+}
+
+// The next host-buffer batch submitted to `h` starts its kernels only when the kernels of `prev`'s last submitted batch
+// are done (its uploads are not held back).  Two handles submitted alternately with this form a 3-stage pipeline:
+// upload of batch k+1 | kernels of batch k | download of batch k-1.
+int orbs_chain_after(orbs_t* h, orbs_t* prev) {
+  if (!h || !prev || h == prev || h->device != prev->device) { set_error("bad argument"); return B200ORB_EINVAL; }
+  h->chain_prev = prev;
   return B200ORB_OK;
 }
 

@@ -94,6 +94,10 @@ class StreamTracker:
         """Frames per upload chunk of the host-buffer calls (default 128)."""
         _lib.check(self._L.orbs_set_chunk_frames(self._h, int(frames)))
 
+    def chain_after(self, prev: "StreamTracker"):
+        """The next submitted batch starts its kernels when `prev`'s kernels are done (uploads are not held back)."""
+        _lib.check(self._L.orbs_chain_after(self._h, prev._h))
+
     def device_inputs(self):
         """(d_gray, d_depth) device pointers of the last host-buffer batch (depth as f32 metres)."""
         g, d = C.c_void_p(), C.c_void_p()

@@ -110,6 +110,7 @@ def test_two_batches_in_flight_equal_synchronous_calls():
         if k >= 2:
             trk[k & 1].sync()
             got.append([x.copy() for x in outs[k & 1]])
+        trk[k & 1].chain_after(trk[(k + 1) & 1])   # orbs_chain_after: kernels of consecutive batches in order
         trk[k & 1].submit_batch_u16(g.numpy(), d.numpy(), factor, T.numpy(), outs[k & 1])
     for k in range(max(0, len(batches) - 2), len(batches)):
         trk[k & 1].sync()

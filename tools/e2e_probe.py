@@ -25,7 +25,7 @@ pcm = PointCloudMapping(0.05)
 Tk = T.numpy()[kfs]
 
 
-def run(n, inflight, mapper, chunk, full_depth):
+def run(n, inflight, mapper, chunk, full_depth, chain=False):
     for t in trk:
         t.set_chunk_frames(chunk)
         t.set_full_depth_upload(full_depth)
@@ -33,6 +33,8 @@ def run(n, inflight, mapper, chunk, full_depth):
     def submit(k):
         if mapper:
             pcm.insert_keyframes_u16(kf_d16.numpy(), kf_rgb.numpy(), factor, Tk, synth.FX, synth.FY, synth.CX, synth.CY)
+        if chain and inflight > 1:
+            trk[k % inflight].chain_after(trk[(k - 1) % inflight])
         trk[k % inflight].submit_batch_u16(gray.numpy(), d16.numpy(), factor, T.numpy(), outs[k % inflight])
 
     def go(m):
@@ -52,13 +54,13 @@ def run(n, inflight, mapper, chunk, full_depth):
     return F * n / dt, dt / n * 1e3
 
 
-cfgs = [(2, False, 128, False), (2, True, 128, False)] if len(sys.argv) > 2 else \
-    [(i, m, c, f) for i in (1, 2) for m in (False, True) for c in (64, 128, 256) for f in (False, True)]
-for inflight, mapper, chunk, full in cfgs:
+cfgs = [(2, True, 128, False, False), (2, True, 128, False, True), (2, True, 256, False, True), (3, True, 256, False, True), (2, False, 256, False, True)] if len(sys.argv) > 2 else \
+    [(i, m, c, f, False) for i in (1, 2) for m in (False, True) for c in (64, 128, 256) for f in (False, True)]
+for inflight, mapper, chunk, full, chain in cfgs:
     trk[0].profile_enable(True)
     trk[0].profile_read()
-    fps, ms = run(12, inflight, mapper, chunk, full)
-    print("inflight %d mapper %d chunk %3d full_depth %d : %8.0f frames/s  %.2f ms/batch" % (inflight, mapper, chunk, full, fps, ms))
+    fps, ms = run(12, inflight, mapper, chunk, full, chain)
+    print("inflight %d mapper %d chunk %3d full_depth %d chain %d : %8.0f frames/s  %.2f ms/batch" % (inflight, mapper, chunk, full, chain, fps, ms))
     st_ms, frames, runs = trk[0].profile_read()
     trk[0].profile_enable(False)
     print("   handle 0 stage ms per batch:", {k: round(v / max(runs, 1) * (F / max(frames / max(runs, 1), 1)), 3) for k, v in st_ms.items()}, "sum %.3f" % (sum(st_ms.values()) / max(frames, 1) * F))
