@@ -144,7 +144,7 @@ __device__ __forceinline__ bool map_touch(const MapView& m, unsigned long long k
 // as ONE launch (blockIdx.y = job = bit index of the keyframe in the batch masks of the map).
 struct KfScratch {
   LeafTable leaf;
-  int *pix_slot, *bucket, *voxlist;
+  int *pix_slot, *pix_rank, *bucket, *voxlist;   // pix_rank: position of the pixel inside its cell's bucket
   int* counters;   // [0] pixels, [1] voxels (= points)
   float* pts;
   uint8_t *pts_rgb, *pts_label;
@@ -209,7 +209,7 @@ __global__ void k_ocm_bin(const KfJob* __restrict__ jobs, int* __restrict__ err)
   const unsigned long long key = ok ? leaf_key(c, x, y, z) : (EMPTY_KEY - 1ull - (unsigned long long)lane);
   const unsigned grp = __match_any_sync(0xffffffffu, key);
   const int leader = __ffs(grp) - 1;
-  int slot = -1;
+  int slot = -1, rank = 0;
   if (ok && lane == leader) {   // lowest lane of the group = smallest pixel index of the group
     bool fresh;
     const long long s = leaf_insert(lt, key, &fresh);
@@ -217,12 +217,16 @@ __global__ void k_ocm_bin(const KfJob* __restrict__ jobs, int* __restrict__ err)
     else {
       slot = (int)s;
       if (fresh) voxlist[atomicAdd(&counters[1], 1)] = slot;   // list of occupied cells: no table sweep later
-      atomicAdd(&lt.rec[s].count, __popc(grp));
+      rank = atomicAdd(&lt.rec[s].count, __popc(grp));          // the group's first position in the cell's bucket
       atomicMin(&lt.rec[s].first, pix);
     }
   }
   slot = __shfl_sync(0xffffffffu, slot, leader);
-  if (pix >= 0) pix_slot[pix] = ok ? slot : -1;
+  rank = __shfl_sync(0xffffffffu, rank, leader) + __popc(grp & ((1u << lane) - 1u));
+  if (pix >= 0) {
+    pix_slot[pix] = ok ? slot : -1;
+    J.s.pix_rank[pix] = rank;
+  }
 }
 
 // K11b: bucket ranges for the occupied cells (arbitrary order: the cloud is a set)
@@ -240,18 +244,10 @@ __global__ void k_ocm_ranges(const KfJob* __restrict__ jobs) {
 // K11c: scatter the pixel indices into their cell's bucket
 __global__ void k_ocm_scatter(const KfJob* __restrict__ jobs) {
   const KfJob& J = jobs[blockIdx.y];
-  const int* __restrict__ pix_slot = J.s.pix_slot;
-  const LeafTable lt = J.s.leaf;
-  int* __restrict__ bucket = J.s.bucket;
-  const int lane = threadIdx.x & 31;
   const int pix = tile_pixel(J.c.rows, J.c.cols);
-  const int s = (pix >= 0) ? pix_slot[pix] : -1;
-  const unsigned grp = __match_any_sync(0xffffffffu, (s >= 0) ? s : -1 - lane);
-  const int leader = __ffs(grp) - 1;
-  int base = 0;
-  if (s >= 0 && lane == leader) base = lt.rec[s].offset + atomicAdd(&lt.rec[s].cursor, __popc(grp));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  if (s >= 0) bucket[base + __popc(grp & ((1u << lane) - 1u))] = pix;
+  if (pix < 0) return;
+  const int s = J.s.pix_slot[pix];
+  if (s >= 0) J.s.bucket[J.s.leaf.rec[s].offset + J.s.pix_rank[pix]] = pix;   // positions were handed out by k_ocm_bin
 }
 
 // K11d: per cell: restore pixel order, sequential float centroid (PCL VoxelGrid), transform to the world frame in
@@ -547,7 +543,7 @@ struct ocm {
   }
   static void free_slot(KfScratch& k) {
     auto F = [](void* p) { if (p) cudaFree(p); };
-    F(k.leaf.rec); F(k.pix_slot); F(k.bucket); F(k.voxlist);
+    F(k.leaf.rec); F(k.pix_slot); F(k.pix_rank); F(k.bucket); F(k.voxlist);
     F(k.pts); F(k.pts_rgb); F(k.pts_label);
     k = KfScratch{};
   }
@@ -614,7 +610,7 @@ int ocm::ensure_scratch(int r, int c, int nslots) {
     const int id = (int)slots.size();
     k.leaf.mask = leaf_cap - 1;
     B200_CUDA(cudaMalloc(&k.leaf.rec, sizeof(LeafRec) * leaf_cap));
-    B200_CUDA(cudaMalloc(&k.pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&k.bucket, 4 * npix));
+    B200_CUDA(cudaMalloc(&k.pix_slot, 4 * npix)); B200_CUDA(cudaMalloc(&k.pix_rank, 4 * npix)); B200_CUDA(cudaMalloc(&k.bucket, 4 * npix));
     B200_CUDA(cudaMalloc(&k.voxlist, 4 * npix));
     B200_CUDA(cudaMalloc(&k.pts, 12 * npix)); B200_CUDA(cudaMalloc(&k.pts_rgb, 3 * npix)); B200_CUDA(cudaMalloc(&k.pts_label, npix));
     k.counters = d_counters + 4 * id;
