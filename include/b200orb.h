@@ -340,6 +340,28 @@ int ocm_sync(ocm_t* h);
 void* ocm_stream(ocm_t* h);
 long long ocm_launch_count(const ocm_t* h);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * T-variant dense map: the accumulated colour cloud of PointCloudMapping::viewer (src/pointcloudmapping.cc:395-500).
+ *   gcm_add_keyframe[_device]  generatePointCloud (:131-194: every pixel, no depth gate, world frame through Tcw^-1 in
+ *                              double) + removeNaNFromPointCloud + "*globalMap += *out_pt" (:482-485); depth f32 metres,
+ *                              colour image BGR u8 [rows][cols][3]
+ *   gcm_refilter               "voxel.setInputCloud(globalMap); voxel.filter(*tmp); globalMap->swap(*tmp)" (:490-493),
+ *                              VoxelGrid leaf = the constructor's resolution (:40)
+ *   gcm_export                 the points of globalMap (what viewer / global_color.pcd receive, :496-521), cell order
+ * B200ORB_EGEOM from gcm_refilter: the cell index space overflows int for this leaf (PCL leaves the cloud unfiltered). */
+typedef struct gcm gcm_t;
+int gcm_create(float leaf, int device, gcm_t** out);
+void gcm_destroy(gcm_t* h);
+int gcm_add_keyframe(gcm_t* h, const float* depth, const uint8_t* bgr, int rows, int cols, const float Tcw[16], float fx,
+                     float fy, float cx, float cy);
+int gcm_add_keyframe_device(gcm_t* h, const float* d_depth, const uint8_t* d_bgr, int rows, int cols, const float Tcw[16],
+                            float fx, float fy, float cx, float cy);
+int gcm_refilter(gcm_t* h);
+long long gcm_size(const gcm_t* h);
+int gcm_export(gcm_t* h, float* xyz, uint8_t* rgb, long long cap, long long* n);
+int gcm_sync(gcm_t* h);
+long long gcm_launch_count(const gcm_t* h);
+
 #ifdef __cplusplus
 }
 #endif

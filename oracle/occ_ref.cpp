@@ -267,4 +267,65 @@ void occ_ref_backproject_all(const float* depth, int rows, int cols, const float
     }
 }
 
+// T variant, global map refilter (src/pointcloudmapping.cc:485-493): globalMap += cloud (NaN points removed, order kept),
+// then pcl::VoxelGrid(leaf = resolution) over the whole accumulated cloud, globalMap.swap(filtered).
+// PCL VoxelGrid<PointXYZRGBA>::applyFilter restated: bounding box of the finite points, min_b/div_b from
+// floor(min*inv_leaf), linear cell index per point, sort by index, per cell the centroid of x,y,z (float sums in sorted
+// order, divided by the count as float) and of r,g,b (float sums, truncated), cells emitted in ascending index order.
+// std::sort leaves the order of equal indices open: the oracle keeps the input order (stable), like the P variant.
+// in: n points (non-finite ones are skipped like removeNaNFromPointCloud / the !is_dense branch do); returns the number of
+// output points, -1 if the index space overflows int (PCL warns and returns the input unfiltered), -2 if cap is too small.
+long long occ_ref_global_refilter(const float* xyz, const uint8_t* rgb, long long n, float leaf, float* out_xyz,
+                                  uint8_t* out_rgb, long long cap) {
+  const float inv = 1.0f / leaf;
+  float mn[3] = {3.4028235e38f, 3.4028235e38f, 3.4028235e38f}, mx[3] = {-3.4028235e38f, -3.4028235e38f, -3.4028235e38f};
+  long long nf = 0;
+  for (long long i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], p[k]); mx[k] = std::max(mx[k], p[k]); }
+    ++nf;
+  }
+  if (nf == 0) return 0;
+  const long long dx = (long long)((mx[0] - mn[0]) * inv) + 1, dy = (long long)((mx[1] - mn[1]) * inv) + 1,
+                  dz = (long long)((mx[2] - mn[2]) * inv) + 1;
+  if (dx * dy * dz > 2147483647LL) return -1;
+  int min_b[3], max_b[3], div_b[3];
+  for (int k = 0; k < 3; ++k) {
+    min_b[k] = (int)std::floor(mn[k] * inv);
+    max_b[k] = (int)std::floor(mx[k] * inv);
+    div_b[k] = max_b[k] - min_b[k] + 1;
+  }
+  const int mul[3] = {1, div_b[0], div_b[0] * div_b[1]};
+  std::vector<std::pair<int, long long>> iv;
+  iv.reserve((size_t)nf);
+  for (long long i = 0; i < n; ++i) {
+    const float* p = xyz + 3 * i;
+    if (!std::isfinite(p[0]) || !std::isfinite(p[1]) || !std::isfinite(p[2])) continue;
+    const int i0 = (int)(std::floor(p[0] * inv) - (float)min_b[0]);
+    const int i1 = (int)(std::floor(p[1] * inv) - (float)min_b[1]);
+    const int i2 = (int)(std::floor(p[2] * inv) - (float)min_b[2]);
+    iv.emplace_back(i0 * mul[0] + i1 * mul[1] + i2 * mul[2], i);
+  }
+  std::stable_sort(iv.begin(), iv.end(), [](const std::pair<int, long long>& a, const std::pair<int, long long>& b) { return a.first < b.first; });
+  long long m = 0;
+  for (size_t b = 0; b < iv.size();) {
+    size_t e = b;
+    float sx = 0, sy = 0, sz = 0, sr = 0, sg = 0, sb = 0;
+    while (e < iv.size() && iv[e].first == iv[b].first) {
+      const long long i = iv[e].second;
+      sx += xyz[3 * i]; sy += xyz[3 * i + 1]; sz += xyz[3 * i + 2];
+      sr += (float)rgb[3 * i]; sg += (float)rgb[3 * i + 1]; sb += (float)rgb[3 * i + 2];
+      ++e;
+    }
+    if (m >= cap) return -2;
+    const float fn = (float)(e - b);
+    out_xyz[3 * m] = sx / fn; out_xyz[3 * m + 1] = sy / fn; out_xyz[3 * m + 2] = sz / fn;
+    out_rgb[3 * m] = (uint8_t)(sr / fn); out_rgb[3 * m + 1] = (uint8_t)(sg / fn); out_rgb[3 * m + 2] = (uint8_t)(sb / fn);
+    ++m;
+    b = e;
+  }
+  return m;
+}
+
 }  // extern "C"

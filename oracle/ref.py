@@ -339,3 +339,20 @@ def backproject_all(depth, Tcw, fx, fy, cx, cy):
     out = np.zeros((depth.size, 3), np.float32)
     L.occ_ref_backproject_all(_p(depth), depth.shape[0], depth.shape[1], _p(T), fx, fy, cx, cy, _p(out))
     return out
+
+
+def global_refilter(xyz, rgb, leaf):
+    """T-variant global map refilter (src/pointcloudmapping.cc:491-493, PCL VoxelGrid) -> (xyz', rgb') in cell order."""
+    L = lib()
+    L.occ_ref_global_refilter.restype = C.c_longlong
+    L.occ_ref_global_refilter.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_void_p, C.c_void_p,
+                                          C.c_longlong]
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+    n = xyz.shape[0]
+    out = np.zeros((max(n, 1), 3), np.float32)
+    out_rgb = np.zeros((max(n, 1), 3), np.uint8)
+    m = L.occ_ref_global_refilter(_p(xyz), _p(rgb), n, float(np.float32(leaf)), _p(out), _p(out_rgb), max(n, 1))
+    if m < 0:
+        raise ValueError("global_refilter: %s" % ("index space overflows int" if m == -1 else "cap"))
+    return out[:m].copy(), out_rgb[:m].copy()

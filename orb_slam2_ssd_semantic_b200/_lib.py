@@ -31,6 +31,7 @@ EXPORTS = [
     "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_by_bow_kf", "orbm_search_projected",
     "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_u16", "orbs_submit_batch_u16", "orbs_device_inputs", "orbs_set_full_depth_upload", "orbs_set_chunk_frames", "orbs_chain_after", "b200orb_depth_u16_to_f32_device", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
     "orbs_stream", "orbs_launch_count", "orbs_extractor",
+    "gcm_create", "gcm_destroy", "gcm_add_keyframe", "gcm_add_keyframe_device", "gcm_refilter", "gcm_size", "gcm_export", "gcm_sync", "gcm_launch_count",
     "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device", "ocm_insert_keyframes_device", "ocm_insert_keyframes_u16",
     "ocm_last_points", "ocm_num_leaves", "ocm_export_leaves", "ocm_query", "ocm_summary_count",
     "ocm_export_summaries_device", "ocm_apply_summaries_device", "ocm_sync", "ocm_stream", "ocm_launch_count",
@@ -112,6 +113,18 @@ def lib() -> C.CDLL:
     L.ocm_destroy.restype = None
     L.ocm_insert_keyframe.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f, vp]
     L.ocm_insert_keyframe_device.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f, vp]
+    L.gcm_create.argtypes = [f, i, C.POINTER(vp)]
+    L.gcm_destroy.argtypes = [vp]
+    L.gcm_destroy.restype = None
+    L.gcm_add_keyframe.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f]
+    L.gcm_add_keyframe_device.argtypes = [vp, vp, vp, i, i, vp, f, f, f, f]
+    L.gcm_refilter.argtypes = [vp]
+    L.gcm_size.argtypes = [vp]
+    L.gcm_size.restype = C.c_longlong
+    L.gcm_export.argtypes = [vp, vp, vp, C.c_longlong, C.POINTER(C.c_longlong)]
+    L.gcm_sync.argtypes = [vp]
+    L.gcm_launch_count.argtypes = [vp]
+    L.gcm_launch_count.restype = C.c_longlong
     L.ocm_insert_keyframes_device.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp, f, f, f, f]
     L.ocm_insert_keyframes_u16.argtypes = [vp, vp, vp, i, i, i, f, vp, f, f, f, f]
     L.ocm_last_points.argtypes = [vp, vp, vp, i, C.POINTER(i)]

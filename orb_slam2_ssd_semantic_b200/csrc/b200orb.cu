@@ -3,3 +3,4 @@
 #include "orbm.cu"
 #include "orbs.cu"
 #include "ocm.cu"
+#include "gcm.cu"

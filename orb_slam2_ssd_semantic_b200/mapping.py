@@ -119,3 +119,50 @@ class PointCloudMapping:
     @property
     def handle(self):
         return self._h
+
+
+class GlobalCloudMapping:
+    """T-variant dense map (src/pointcloudmapping.cc): the accumulated colour cloud `globalMap`.
+
+    `insertKeyFrame` = generatePointCloud + removeNaN + `*globalMap += cloud`; `refilter` = the VoxelGrid(resolution)
+    pass over the whole map that the viewer thread runs after every batch of keyframes; `points()` = globalMap."""
+
+    def __init__(self, resolution: float = 0.04, device: int = 0):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        _lib.check(self._L.gcm_create(float(np.float32(resolution)), int(device), C.byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.gcm_destroy(h)
+            self._h = None
+
+    def insertKeyFrame(self, Tcw, depth, color_bgr, fx, fy, cx, cy):
+        depth = np.ascontiguousarray(depth, np.float32)
+        bgr = np.ascontiguousarray(color_bgr, np.uint8)
+        rows, cols = depth.shape
+        assert bgr.shape == (rows, cols, 3)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        _lib.check(self._L.gcm_add_keyframe(self._h, ptr(depth), ptr(bgr), rows, cols, ptr(T), float(fx), float(fy),
+                                            float(cx), float(cy)))
+
+    def insert_keyframe_device(self, d_depth: int, d_bgr: int, rows: int, cols: int, Tcw, fx, fy, cx, cy):
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        _lib.check(self._L.gcm_add_keyframe_device(self._h, C.c_void_p(d_depth), C.c_void_p(d_bgr), rows, cols, ptr(T),
+                                                   float(fx), float(fy), float(cx), float(cy)))
+
+    def refilter(self):
+        _lib.check(self._L.gcm_refilter(self._h))
+
+    def size(self) -> int:
+        return int(self._L.gcm_size(self._h))
+
+    def points(self):
+        """-> (xyz float32 [n,3], rgb uint8 [n,3]) of globalMap, in VoxelGrid cell order after a refilter."""
+        n = C.c_longlong(0)
+        _lib.check(self._L.gcm_export(self._h, None, None, 0, C.byref(n)))
+        xyz = np.zeros((max(n.value, 1), 3), np.float32)
+        rgb = np.zeros((max(n.value, 1), 3), np.uint8)
+        _lib.check(self._L.gcm_export(self._h, ptr(xyz), ptr(rgb), n.value, C.byref(n)))
+        return xyz[:n.value], rgb[:n.value]

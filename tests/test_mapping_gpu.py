@@ -148,3 +148,32 @@ def test_host_u16_keyframe_batch_equals_per_keyframe_inserts(oracle):
     assert len(pa) == len(pr) and (pa == pr).all() and np.abs(va - vr).max() <= 1e-5
     with pytest.raises(ValueError):
         a.insert_keyframes_u16(d16.astype(np.int32), rgb, factor, T, synth.FX, synth.FY, synth.CX, synth.CY)
+
+
+def test_global_cloud_refilter_matches_oracle(oracle):
+    """T variant (src/pointcloudmapping.cc:131-194, 482-493): every pixel back-projected (no gate), accumulated, and the
+    whole map re-filtered by VoxelGrid(resolution) after each batch -- point for point (cell order) against the oracle;
+    the second round filters the previous centroids together with the new keyframes."""
+    from orb_slam2_ssd_semantic_b200 import GlobalCloudMapping
+    scene = _scene(4)
+    leaf = 0.04
+    gpu = GlobalCloudMapping(leaf)
+    acc_xyz = np.zeros((0, 3), np.float32)
+    acc_rgb = np.zeros((0, 3), np.uint8)
+    for rnd in range(2):
+        for depth, bgr, T in scene[2 * rnd:2 * rnd + 2]:
+            d = depth.copy()
+            d[5, 7] = np.nan                       # removed by removeNaNFromPointCloud
+            gpu.insertKeyFrame(T, d, bgr, synth.FX, synth.FY, synth.CX, synth.CY)
+            pts = oracle.backproject_all(d, T, synth.FX, synth.FY, synth.CX, synth.CY)
+            acc_xyz = np.concatenate([acc_xyz, pts])
+            acc_rgb = np.concatenate([acc_rgb, bgr.reshape(-1, 3)[:, ::-1]])
+        assert gpu.size() == len(acc_xyz)
+        gpu.refilter()
+        acc_xyz, acc_rgb = oracle.global_refilter(acc_xyz, acc_rgb, leaf)
+        gx, gc = gpu.points()
+        assert len(gx) == len(acc_xyz) and len(acc_xyz) > 1000
+        assert np.abs(gx - acc_xyz).max() <= 1e-5       # bit-equal in practice: same order, same float sums
+        assert (gc == acc_rgb).all()
+    with pytest.raises(Exception):
+        GlobalCloudMapping(0.0)

@@ -199,3 +199,35 @@ def test_ot_export_round_trips_reference_octomap():
     assert (n2["v"] == nodes["v"]).all() and (n2["child"] == nodes["child"]).all()
     leaf = nodes["child"] == 0
     assert (n2["rgb"][leaf] == nodes["rgb"][leaf]).all()
+
+
+def test_global_refilter_against_numpy_restatement():
+    """occ_ref_global_refilter (PCL VoxelGrid over the accumulated T-variant map) against an independent numpy
+    restatement of the same published algorithm: bounding box -> min_b/div_b -> linear index -> stable sort -> float
+    sums in order."""
+    from oracle import ref
+    rng = np.random.default_rng(3)
+    xyz = rng.uniform(-1.5, 2.5, (6000, 3)).astype(np.float32)
+    xyz[17] = np.nan
+    xyz[400, 1] = np.inf
+    rgb = rng.integers(0, 256, (6000, 3)).astype(np.uint8)
+    leaf = np.float32(0.13)
+    o, c = ref.global_refilter(xyz, rgb, leaf)
+    inv = np.float32(1.0) / leaf
+    fin = np.isfinite(xyz).all(1)
+    P, Cc = xyz[fin], rgb[fin]
+    mb = np.floor(P.min(0) * inv).astype(np.int64)
+    div = np.floor(P.max(0) * inv).astype(np.int64) - mb + 1
+    ijk = (np.floor(P * inv) - mb.astype(np.float32)).astype(np.int64)
+    idx = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    order = np.argsort(idx, kind="stable")
+    u, st, cnt = np.unique(idx[order], return_index=True, return_counts=True)
+    assert len(u) == len(o) and len(o) > 500
+    for k in range(0, len(u), 37):
+        acc = np.zeros(3, np.float32)
+        accc = np.zeros(3, np.float32)
+        for j in order[st[k]:st[k] + cnt[k]]:
+            acc = acc + P[j]
+            accc = accc + Cc[j].astype(np.float32)
+        assert (o[k] == acc / np.float32(cnt[k])).all()
+        assert (c[k] == (accc / np.float32(cnt[k])).astype(np.uint8)).all()
