@@ -214,14 +214,16 @@ def test_search_projected_relocalisation_variant(oracle, stream_feats):
     ratio = maxd / dist3d
     lvl = np.clip(np.ceil(np.log(ratio) / np.log(np.float32(1.2))).astype(np.int32), 0, 7)   # PredictScale
     ok = (valid > 0) & (u >= 0) & (u <= 640) & (v >= 0) & (v <= 480) & (rng.random(len(Kk)) < 0.9)
-    for th, orbdist, ori in ((10.0, 100, True), (3.0, 64, True), (10.0, 100, False)):
-        q = QueriesView(ok.astype(np.uint8), u, v, (np.float32(th) * sf[lvl]).astype(np.float32), lvl - 1, lvl + 1, Dk,
+    # last tuple: SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:378-498, loop closing):
+    # levels [pred-1, pred], best <= TH_LOW = 50, no orientation check, any matched keypoint is skipped
+    for th, orbdist, ori, top in ((10.0, 100, True, 1), (3.0, 64, True, 1), (10.0, 100, False, 1), (10.0, 50, False, 0)):
+        q = QueriesView(ok.astype(np.uint8), u, v, (np.float32(th) * sf[lvl]).astype(np.float32), lvl - 1, lvl + top, Dk,
                         Kk["angle"])
         F = FrameView(Kc["x"], Kc["y"], Kc["octave"], Kc["angle"], ur, Dc, Tc, synth.FX, synth.FY, synth.CX, synth.CY,
                       synth.BF, 0.0, 640.0, 0.0, 480.0, sf, mp_obs=np.where(rng.random(len(Kc)) < 0.1, 0, -1).astype(np.int32))
         n_ref, ref = oracle.search_projected(F, q, orbdist, 1, ori)
         n_gpu, gpu = ORBmatcher(0.9, ori).SearchProjected(F, q, orbdist, 1)
-        assert n_ref > 30 and n_gpu == n_ref and (gpu == ref).all(), (th, orbdist, ori)
+        assert n_ref > 30 and n_gpu == n_ref and (gpu == ref).all(), (th, orbdist, ori, top)
     # claim rule 0 with a stereo gate == the LAST semantics on supplied geometry
     q = QueriesView(ok.astype(np.uint8), u, v, (np.float32(15.0) * sf[Kk["octave"]]).astype(np.float32), Kk["octave"] - 1,
                     Kk["octave"] + 1, Dk, Kk["angle"], uright=(u - np.float32(synth.BF) * invz).astype(np.float32),
