@@ -124,3 +124,41 @@ def test_two_batches_in_flight_equal_synchronous_calls():
             assert (g[3][f, :n[f]] == w[3][f, :n[f]]).all()
     with pytest.raises(ValueError):
         trk[0].submit_batch_u16(batches[0][0].numpy()[:, ::2], batches[0][1].numpy(), factor, batches[0][2].numpy(), outs[0])
+
+
+def test_full_size_batch_against_cpu_pipeline(oracle):
+    """The bench workload at full size (256 frames 640x480, every 12th frame a keyframe): per-frame keypoint and match
+    counts of the whole batch and the leaf count of the occupancy map against the multi-threaded CPU pipeline
+    (oracle/pipeline_ref.cpp); three frames spread over the batch are additionally compared keypoint by keypoint."""
+    import os
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping, StreamTracker
+    F, KF = 256, 12
+    ws = synth.WallStream(seed=1234, n=F)
+    frames = [ws.frame(t) for t in range(F)]
+    gray = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames])
+    rgb = np.stack([f[2] for f in frames])
+    T = np.stack([f[3] for f in frames]).astype(np.float32)
+    st = StreamTracker(1000, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, th=15.0, nnratio=0.9,
+                       max_frames=F)
+    kps, desc, nkp, c2l, nm = st.track_batch(gray, depth, T)
+    pcm = PointCloudMapping(0.05)
+    kfs = list(range(0, F, KF))
+    for t in kfs:
+        pcm.insertKeyFrame(T[t], depth[t], rgb[t], synth.FX, synth.FY, synth.CX, synth.CY)
+    nthreads = min(os.cpu_count() or 1, 64)
+    _, nkp_ref, nm_ref = oracle.pipeline_run(gray, depth, T, nthreads, rgb=rgb, kf_every=KF)
+    assert (nkp == nkp_ref).all() and nkp.min() > 900
+    assert (nm == nm_ref).all() and nm[1:].min() > 100
+    R = oracle.RefExtractor(1000, 1.2, 8, 20, 7)
+    for t in (0, 131, 255):
+        K, D = R(gray[t])
+        assert kps[t, :nkp[t]].tobytes() == K.tobytes() and (desc[t, :nkp[t]] == D).all()
+    ref_map = oracle.RefOccupancy()
+    for t in kfs:
+        ref_map.insert_keyframe(T[t], depth[t], rgb[t], synth.FX, synth.FY, synth.CX, synth.CY, None)
+    kr, lr = ref_map.export_leaves()
+    kg, lg, _ = pcm.export_leaves()
+    assert len(kg) == len(kr) and pcm.num_leaves() == len(kr)
+    pk = lambda k: np.sort(k.astype(np.uint64)[:, 0] | (k.astype(np.uint64)[:, 1] << np.uint64(16)) | (k.astype(np.uint64)[:, 2] << np.uint64(32)))
+    assert (pk(kg) == pk(kr)).all()
