@@ -843,6 +843,17 @@ __device__ __forceinline__ HRow blur_hrow_words(unsigned w0, unsigned w1, unsign
   return r;
 }
 
+// The same horizontal sums with byte dot products: output pixel i needs the 7 bytes i+1 .. i+7 of the 12-byte window;
+// bytes i+1..i+4 and i+5..i+8 are two funnel shifts of the three words (none for i = 3), and two IDP.4A against the
+// coefficient words (18,34,48,56) / (48,34,18,0) give the exact integer sum.  h[0..3] are at most 255*256 = 65280.
+__device__ __forceinline__ void blur_hrow_dp(unsigned w0, unsigned w1, unsigned w2, unsigned h[4]) {
+  constexpr unsigned cA = 18u | (34u << 8) | (48u << 16) | (56u << 24), cB = 48u | (34u << 8) | (18u << 16);
+  h[0] = __dp4a(__funnelshift_r(w0, w1, 8), cA, __dp4a(__funnelshift_r(w1, w2, 8), cB, 0u));
+  h[1] = __dp4a(__funnelshift_r(w0, w1, 16), cA, __dp4a(__funnelshift_r(w1, w2, 16), cB, 0u));
+  h[2] = __dp4a(__funnelshift_r(w0, w1, 24), cA, __dp4a(__funnelshift_r(w1, w2, 24), cB, 0u));
+  h[3] = __dp4a(w1, cA, __dp4a(w2, cB, 0u));
+}
+
 // interior column groups only (x0 >= 4 and x0 + 8 <= w): three aligned word loads, no border logic
 __device__ __forceinline__ HRow blur_hrow(const uint8_t* __restrict__ row, int x0) {
   const unsigned* p = reinterpret_cast<const unsigned*>(row + x0 - 4);
@@ -889,9 +900,7 @@ __global__ void __launch_bounds__(32) k_blur7_strip(PyrView src, PyrView dstv, c
       }
 #pragma unroll
       for (int k = 0; k < 7; ++k) {
-        const HRow r = blur_hrow_words(W[k][0], W[k][1], W[k][2]);
-        ring[(k + 6) % 7][0] = r.h02 & 0xffffu; ring[(k + 6) % 7][2] = r.h02 >> 16;
-        ring[(k + 6) % 7][1] = r.h13 & 0xffffu; ring[(k + 6) % 7][3] = r.h13 >> 16;
+        blur_hrow_dp(W[k][0], W[k][1], W[k][2], ring[(k + 6) % 7]);
         unsigned out = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
