@@ -164,9 +164,9 @@ def run_reference(args):
 
 
 # DRAM traffic of the single-launch stages, bytes per frame, from the ncu capture summarised in
-# profiles/r01_ncu_v3_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of a 256-frame launch / 256)
-NCU_DRAM_BYTES_PER_FRAME = {"fast": (231577856 + 41558528) / 256.0, "quadtree": (74913536 + 91995392) / 256.0,
-                            "orient_desc": (463287808 + 18053888) / 256.0}
+# profiles/r01_ncu_v5_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of a 256-frame launch / 256)
+NCU_DRAM_BYTES_PER_FRAME = {"fast": (231405824 + 41911808) / 256.0, "quadtree": (74866176 + 93454336) / 256.0,
+                            "orient_desc": (463207168 + 18829056) / 256.0}
 
 
 def workload_config(args, frames):
@@ -351,7 +351,7 @@ def run_b200(args):
                          "frac": stages[dom]["frac"],
                          "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * F if dom in NCU_DRAM_BYTES_PER_FRAME else None),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at 256 "
-                                           "frames/launch (profiles/r01_ncu_v3_summary.txt), scaled to this launch",
+                                           "frames/launch (profiles/r01_ncu_v5_summary.txt), scaled to this launch",
                          "peak_source": peak_src,
                          "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
                                       "algorithmic_bytes_per_frame": pipeline_bytes(n_kp)},
