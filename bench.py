@@ -51,7 +51,9 @@ def algorithmic_bytes(n_kp: float, n_cand: float) -> dict:
         "fast": S_PYR + 4 * n_cand,
         "quadtree": 4 * n_cand + 4 * n_kp,
         "blur": 2 * S_PYR,
-        "orient_desc": 4 * n_kp + 60 * n_kp,
+        # per keypoint: the 749 raw pixels of the r = 15 disc (IC_Angle), the 512 blurred sample pixels of the pattern,
+        # 4 B selection in, 60 B KeyPoint + descriptor out
+        "orient_desc": (749 + 512 + 4 + 60) * n_kp,
         "glue": 69 * n_kp,
         "match": 52 * n_kp + 52 * n_kp + 4 * (64 * 48 + 1) + 8 * n_kp,
     }
