@@ -352,15 +352,11 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
   // K1 pyramid
   for (int l = 1; l < nl; ++l) {
     dim3 blk(32, 8), grd((lw[l] + 127) / 128, (lh[l] + 7) / 8, F);
-    // k_resize_w needs aligned source rows and 4 outputs within a 12-byte source window (scale factor <= 2)
+    // k_resize_g needs aligned source rows and 4 outputs within an 8-byte source window (scale factor <= 2)
     const bool src_aligned = prm.scale_factor <= 2.0f && (((uintptr_t)rawv.p[l - 1]) & 3) == 0 && (rawv.pitch[l - 1] & 3) == 0 && (rawv.fstride[l - 1] & 3) == 0;
     if (src_aligned && resize_group_ok)
       k_resize_g<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lh[l - 1], rawv.p[l],
                                          rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xg + xg_off[l], d_yt + yt_off[l]);
-    else if (src_aligned)
-      k_resize_w<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lw[l - 1], lh[l - 1],
-                                         rawv.p[l], rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xt + xt_off[l],
-                                         d_yt + yt_off[l]);
     else
       k_resize<<<grd, blk, 0, stream>>>(rawv.p[l - 1], rawv.pitch[l - 1], rawv.fstride[l - 1], lw[l - 1], lh[l - 1],
                                        rawv.p[l], rawv.pitch[l], rawv.fstride[l], lw[l], lh[l], d_xt + xt_off[l],

@@ -89,49 +89,6 @@ __global__ void __launch_bounds__(256) k_resize(const uint8_t* __restrict__ src,
   *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
 }
 
-// K1 (fast path, 4-byte aligned source rows): each thread still produces 4 adjacent destination pixels, but fetches
-// the two source rows as aligned 32-bit words (the 4 outputs need at most 8 consecutive source bytes = 3 words), picks
-// every (s[x], s[x+1]) byte pair with ONE dynamic PRMT and does the horizontal pass with ONE two-way dot product
-// (IDP.2A: a0*s[x] + a1*s[x+1], 16-bit coefficients x 8-bit pixels) per row.  Same integer arithmetic as k_resize.
-__global__ void __launch_bounds__(256) k_resize_w(const uint8_t* __restrict__ src, int spitch, size_t sfs, int sw,
-                                                  int sh, uint8_t* __restrict__ dst, int dpitch, size_t dfs,
-                                                  int dw, int dh, const int2* __restrict__ xt,
-                                                  const int2* __restrict__ yt) {
-  const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-  const int dy = blockIdx.y * 8 + threadIdx.y;
-  if (dx0 >= dw || dy >= dh) return;
-  const uint8_t* s = src + (size_t)blockIdx.z * sfs;
-  uint8_t* d = dst + (size_t)blockIdx.z * dfs;
-  const int2 ty = __ldg(&yt[dy]);
-  const int sy0 = ty.x, sy1 = min(sy0 + 1, sh - 1);
-  const int b0 = (short)(ty.y & 0xffff), b1 = (short)(ty.y >> 16);
-  int2 tx[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) tx[i] = __ldg(&xt[min(dx0 + i, dw - 1)]);
-  const int xb = tx[0].x & ~3;                 // first source word; the 4 outputs read bytes xb .. xb+11 at most
-  const int wlast = (spitch >> 2) - 1;         // never read past the row's last word (pitch is a multiple of 4)
-  const int wi = xb >> 2;
-  const unsigned* r0 = reinterpret_cast<const unsigned*>(s + (size_t)sy0 * spitch);
-  const unsigned* r1 = reinterpret_cast<const unsigned*>(s + (size_t)sy1 * spitch);
-  const unsigned a0 = __ldg(r0 + wi), a1 = __ldg(r0 + min(wi + 1, wlast)), a2 = __ldg(r0 + min(wi + 2, wlast));
-  const unsigned c0 = __ldg(r1 + wi), c1 = __ldg(r1 + min(wi + 1, wlast)), c2 = __ldg(r1 + min(wi + 2, wlast));
-  unsigned out = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int off = tx[i].x - xb;                        // 0 .. 10: byte offset of s[x] inside the 12-byte window
-    // window bytes off, off+1 (off+1 may be one past the row end when x == sw-1; its coefficient is 0 then)
-    const unsigned lo = (off < 4) ? a0 : ((off < 8) ? a1 : a2), hi = (off < 4) ? a1 : ((off < 8) ? a2 : a2);
-    const unsigned lo1 = (off < 4) ? c0 : ((off < 8) ? c1 : c2), hi1 = (off < 4) ? c1 : ((off < 8) ? c2 : c2);
-    const unsigned sel = (unsigned)(off & 3) | ((unsigned)((off & 3) + 1) << 4);
-    const unsigned p0 = __byte_perm(lo, hi, sel), p1 = __byte_perm(lo1, hi1, sel);   // bytes 0,1 = s[x], s[x+1]
-    const int h0 = (int)__dp2a_lo((unsigned)tx[i].y, p0, 0u);   // a0*s[x] + a1*s[x+1]
-    const int h1 = (int)__dp2a_lo((unsigned)tx[i].y, p1, 0u);
-    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
-    out |= (unsigned)(v & 0xff) << (8 * i);
-  }
-  *reinterpret_cast<unsigned*>(d + (size_t)dy * dpitch + dx0) = out;   // pitch is a multiple of 16
-}
-
 // K1 (group-table path): a thread's 4 adjacent outputs start at a fixed destination column (a multiple of 4), so
 // everything that depends only on the columns is tabulated per GROUP: first source word, byte phase, the four PRMT
 // selectors (relative to the group's first source byte) and the four coefficient pairs -- two 128-bit loads.  The two
