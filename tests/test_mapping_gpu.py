@@ -177,3 +177,26 @@ def test_global_cloud_refilter_matches_oracle(oracle):
         assert (gc == acc_rgb).all()
     with pytest.raises(Exception):
         GlobalCloudMapping(0.0)
+
+
+def test_more_keyframes_than_batch_slots(oracle):
+    """One ocm_insert_keyframes_u16 call with 40 keyframes (the batch masks hold 32: the call is split into rounds and the
+    scratch slots are reused) builds the same map as 40 single inserts."""
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    base = _scene(5)
+    n = 40
+    d16 = np.stack([np.rint(base[i % 5][0].astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16) for i in range(n)])
+    rgb = np.ascontiguousarray(np.stack([base[i % 5][1] for i in range(n)]))
+    T = np.stack([base[i % 5][2] for i in range(n)]).astype(np.float32)
+    factor = np.float32(1.0 / synth.DEPTH_FACTOR)
+    a = PointCloudMapping(0.05)
+    a.insert_keyframes_u16(d16, rgb, factor, T, synth.FX, synth.FY, synth.CX, synth.CY)
+    a.sync()
+    b = PointCloudMapping(0.05)
+    depth = d16.astype(np.float32) * factor
+    for i in range(n):
+        b.insertKeyFrame(T[i], depth[i], rgb[i], synth.FX, synth.FY, synth.CX, synth.CY)
+    pa, va = _leaf_dict(*a.export_leaves()[:2])
+    pb, vb = _leaf_dict(*b.export_leaves()[:2])
+    assert len(pa) > 500 and (pa == pb).all() and (va == vb).all()
+    assert va.max() > 3.0     # repeated hits ran into the upper clamp: the replay order mattered
