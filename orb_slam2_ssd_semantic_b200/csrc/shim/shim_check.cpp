@@ -84,5 +84,12 @@ int main(int argc, char** argv) {
   pcm.insertKeyFrame(Tcw, 535.4f, 539.2f, 320.1f, 247.6f, img, depth, rgb);
   pcm.shutdown();
   std::printf("leaves %lld\n", (long long)pcm.numLeaves());
-  return (kps.size() >= 1000 && desc.rows == (int)kps.size() && pcm.numLeaves() > 0) ? 0 : 1;
+  PointCloudMappingT pcmT(0.04);                       // T variant: accumulated cloud + whole-map VoxelGrid refilter
+  pcmT.insertKeyFrame(Tcw, 535.4f, 539.2f, 320.1f, 247.6f, img, depth, rgb);
+  const long long raw = pcmT.globalMapSize();
+  pcmT.update();
+  pcmT.shutdown();
+  std::printf("global map %lld -> %lld points\n", raw, pcmT.globalMapSize());
+  return (kps.size() >= 1000 && desc.rows == (int)kps.size() && pcm.numLeaves() > 0 && raw == 480 * 640 &&
+          pcmT.globalMapSize() > 0 && pcmT.globalMapSize() < raw) ? 0 : 1;
 }
