@@ -177,7 +177,9 @@ def workload_config(args, frames):
                         "0.05 m occupancy map (BASELINE.json configs[1] + keyframe path of configs[3])" % KF_EVERY,
             "keyframes_per_step_per_gpu": len(range(0, frames, KF_EVERY)),
             "frames_per_step_per_gpu": frames, "nfeatures": NFEAT, "parallelism": "frame-sharded x%d" % args.gpus,
-            "l2": "inputs (%.0f MB gray+depth per step) exceed the 126 MB L2" % (frames * S_IN * 5 / 1e6)}
+            "l2": ("inputs (%.0f MB gray+depth per step) exceed the 126 MB L2" if frames * S_IN * 5 > 126e6 else
+                   "inputs (%.0f MB gray+depth per step) FIT the 126 MB L2: not a valid timing configuration, use the "
+                   "default --frames") % (frames * S_IN * 5 / 1e6)}
 
 
 def run_b200(args):
