@@ -43,7 +43,7 @@ def test_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     import orb_slam2_ssd_semantic_b200 as pkg
-    for ctor in (pkg.ORBextractor, pkg.ORBmatcher, pkg.StreamTracker, pkg.PointCloudMapping):
+    for ctor in (pkg.ORBextractor, pkg.ORBmatcher, pkg.StreamTracker, pkg.PointCloudMapping, pkg.GlobalCloudMapping):
         with pytest.raises(pkg.B200OrbError) as e:
             ctor()
         assert e.value.code == -4 and "no CPU fallback" in str(e.value)
