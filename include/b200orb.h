@@ -252,7 +252,8 @@ int orbs_track_batch_u16(orbs_t* h, const uint8_t* gray, const uint16_t* depth_u
 int orbs_set_full_depth_upload(orbs_t* h, int on);
 /* Pipelining aid for two handles used alternately: the next batch submitted to h starts its kernels only when the kernels
  * of prev's last submitted batch are done; h's uploads and prev's downloads proceed meanwhile, so the stages upload(k+1) |
- * kernels(k) | download(k-1) overlap without two batches' kernels sharing the SMs. */
+ * kernels(k) | download(k-1) overlap without two batches' kernels sharing the SMs.  The dependency is consumed by h's next
+ * submit; prev must stay alive until then. */
 int orbs_chain_after(orbs_t* h, orbs_t* prev);
 /* Frames per upload chunk of the host-buffer entries (default 128, at most 7 chunks per call): the extraction of a chunk
  * starts as soon as it has arrived while the next one is still crossing PCIe. */
