@@ -231,3 +231,37 @@ def test_global_refilter_against_numpy_restatement():
             accc = accc + Cc[j].astype(np.float32)
         assert (o[k] == acc / np.float32(cnt[k])).all()
         assert (c[k] == (accc / np.float32(cnt[k])).astype(np.uint8)).all()
+
+
+def test_occupancy_oracle_against_python_restatement(oracle):
+    """oracle/occ_ref.cpp against oracle/occ_py.py (second restatement, written from the reference text and SURVEY
+    App. A.6/A.7): points, leaf keys and clamped log-odds after three keyframes of a small image, with ground-labelled
+    pixels casting rays."""
+    from oracle.occ_py import PyOccupancy
+    rng = np.random.default_rng(11)
+    rows, cols = 40, 56
+    fx, fy, cx, cy = 48.0, 47.0, 27.6, 19.3
+    ref = oracle.RefOccupancy()
+    py = PyOccupancy()
+    for k in range(3):
+        yy, xx = np.mgrid[0:rows, 0:cols]
+        depth = (1.4 + 0.5 * np.sin(xx / 9.0 + k) * np.cos(yy / 7.0) + 0.02 * rng.standard_normal((rows, cols))).astype(np.float32)
+        depth[3, 5] = 0.2          # below depth_min
+        depth[10:12, 20:30] = 3.4  # above depth_max
+        rgb = rng.integers(0, 256, (rows, cols, 3)).astype(np.uint8)
+        label = np.zeros((rows, cols), np.uint8)
+        label[rows // 2:, :] = 1   # lower half is "ground": rays carve free space
+        a = 0.05 * k
+        T = np.eye(4, dtype=np.float32)
+        T[:3, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], np.float32)
+        T[:3, 3] = np.array([0.03 * k, -0.01 * k, 0.02 * k], np.float32)
+        n_ref = ref.insert_keyframe(T, depth, rgb, fx, fy, cx, cy, label)
+        n_py = py.insert_keyframe(T, depth, fx, fy, cx, cy, label)
+        pts, _, lab = ref.last_points()
+        assert n_ref == n_py == len(pts) > 500
+        assert (pts == py.points).all() and (lab == py.labels).all()
+    keys, lo = ref.export_leaves()
+    got = {tuple(int(v) for v in k): np.float32(x) for k, x in zip(keys, lo)}
+    assert len(got) == len(py.leaves) > 300
+    assert all(got[k] == py.leaves[k] for k in got)
+    assert sum(1 for v in got.values() if v < 0) > 50       # carved free cells exist
