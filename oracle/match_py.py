@@ -1,8 +1,9 @@
 """oracle/match_py.py -- TEST INFRASTRUCTURE, NOT PRODUCT.
 
 Second, independent restatement (pure Python + numpy float32 scalars; small cases only) of
-ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (reference src/ORBmatcher.cc:1578-1724) and the
-Frame grid helpers (src/Frame.cc:319-334,465-531).  It pins oracle/match_ref.cpp and generates the golden match
+ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (reference src/ORBmatcher.cc:1578-1724),
+SearchByProjection(Frame&, vector<MapPoint*>&, th) (:63-156), SearchByBoW(KF,F) (:217-363), SearchByBoW(KF,KF) (:665-812)
+and the Frame grid helpers (src/Frame.cc:319-334,465-531).  It pins oracle/match_ref.cpp and generates the golden match
 vectors under tests/golden/ (tools/make_golden.py).  Reads the same FrameView / LastView objects.
 """
 from __future__ import annotations
@@ -173,3 +174,144 @@ def search_by_projection_last(cur, last, th, mono=False, check_ori=True):
                     state[idx] = -1
                     nmatches -= 1
     return nmatches, np.array(state, np.int32)
+
+
+def _rot_bin(a_query, a_cur, factor):
+    r = f32(f32(a_query) - f32(a_cur))
+    if r < 0:
+        r = f32(r + f32(360.0))
+    b = c_round(float(f32(r * factor)))
+    return 0 if b == HISTO_LENGTH else b
+
+
+def search_by_projection_points(F, pts, th, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:63-156) on a
+    FrameView + TrackPointsView.  Returns (nmatches, frame->point index vector; -2 = untouched pre-existing point)."""
+    th = f32(th)
+    nnratio = f32(nnratio)
+    grid = Grid(F)
+    state = [-1] * F.n
+    obs = [0] * F.n
+    if F.mp_obs is not None:
+        for j in range(F.n):
+            if F.mp_obs[j] >= 0:
+                state[j], obs[j] = -2, int(F.mp_obs[j])
+    b_factor = th != f32(1.0)
+    nmatches = 0
+    for i in range(pts.n):
+        if not pts.track_in_view[i]:
+            continue
+        lvl = int(pts.scale_level[i])
+        r = f32(2.5) if pts.view_cos[i] > f32(0.998) else f32(4.0)     # RadiusByViewingCos :158-164
+        if b_factor:
+            r = f32(r * th)
+        win = f32(r * F.scale_factors[lvl])
+        cand = grid.query(f32(pts.proj_x[i]), f32(pts.proj_y[i]), win, lvl - 1, lvl)
+        if not cand:
+            continue
+        best, best_lvl, best2, best_lvl2, bidx = 256, -1, 256, -1, -1
+        for idx in cand:
+            if state[idx] != -1 and obs[idx] > 0:
+                continue
+            if F.uright[idx] > 0:
+                if abs(f32(f32(pts.proj_xr[i]) - F.uright[idx])) > win:
+                    continue
+            d = hamming(pts.mp_desc[i], F.desc[idx])
+            if d < best:
+                best2, best_lvl2 = best, best_lvl
+                best, best_lvl, bidx = d, int(F.octave[idx]), idx
+            elif d < best2:
+                best_lvl2, best2 = int(F.octave[idx]), d
+        if best <= TH_HIGH:
+            if best_lvl == best_lvl2 and f32(best) > f32(nnratio * f32(best2)):
+                continue
+            state[bidx] = i
+            obs[bidx] = int(pts.mp_obs[i]) if pts.mp_obs is not None else 1
+            nmatches += 1
+    return nmatches, np.array(state, np.int32)
+
+
+def _feature_vector(view):
+    return {int(view.node_ids[k]): [int(v) for v in view.idx[view.node_off[k]:view.node_off[k + 1]]]
+            for k in range(len(view.node_ids))}
+
+
+def _merge_join(fv1, fv2):
+    """The two-iterator walk over the ordered FeatureVector maps (:233-320 / :690-770): yields the index lists of equal
+    node ids in ascending node order (lower_bound jumps only skip unequal ids)."""
+    for node in sorted(set(fv1) & set(fv2)):
+        yield fv1[node], fv2[node]
+
+
+def search_by_bow(kf, f, nnratio=0.7, check_ori=True):
+    """SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&) (src/ORBmatcher.cc:217-363) on two BowViews (kf.valid = the
+    keyframe keypoint holds a good MapPoint).  Returns (nmatches, frame keypoint -> keyframe keypoint, -1 = none)."""
+    nnratio = f32(nnratio)
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    out = [-1] * f.n
+    rot = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    for idx_kf, idx_f in _merge_join(_feature_vector(kf), _feature_vector(f)):
+        for rk in idx_kf:
+            if kf.valid is not None and not kf.valid[rk]:
+                continue
+            best1, best2, bidx = 256, 256, -1
+            for rf in idx_f:
+                if out[rf] != -1:
+                    continue
+                d = hamming(kf.desc[rk], f.desc[rf])
+                if d < best1:
+                    best2, best1, bidx = best1, d, rf
+                elif d < best2:
+                    best2 = d
+            if best1 <= TH_LOW and f32(best1) < f32(nnratio * f32(best2)):
+                out[bidx] = rk
+                if check_ori:
+                    rot[_rot_bin(kf.angle[rk], f.angle[bidx], factor)].append(bidx)
+                nmatches += 1
+    if check_ori:
+        keep = three_maxima(rot)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for j in rot[b]:
+                    out[j] = -1
+                    nmatches -= 1
+    return nmatches, np.array(out, np.int32)
+
+
+def search_by_bow_kf(kf1, kf2, nnratio=0.75, check_ori=True):
+    """SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&) (src/ORBmatcher.cc:665-812).  Returns (nmatches,
+    keyframe-1 keypoint -> keyframe-2 keypoint, -1 = none)."""
+    nnratio = f32(nnratio)
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    out = [-1] * kf1.n
+    matched2 = [False] * kf2.n
+    rot = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    for idx1, idx2 in _merge_join(_feature_vector(kf1), _feature_vector(kf2)):
+        for i1 in idx1:
+            if kf1.valid is not None and not kf1.valid[i1]:
+                continue
+            best1, best2, bidx = 256, 256, -1
+            for i2 in idx2:
+                if matched2[i2] or (kf2.valid is not None and not kf2.valid[i2]):
+                    continue
+                d = hamming(kf1.desc[i1], kf2.desc[i2])
+                if d < best1:
+                    best2, best1, bidx = best1, d, i2
+                elif d < best2:
+                    best2 = d
+            if best1 < TH_LOW and f32(best1) < f32(nnratio * f32(best2)):     # strict '<' here (:741), '<=' in (KF,F)
+                out[i1] = bidx
+                matched2[bidx] = True
+                if check_ori:
+                    rot[_rot_bin(kf1.angle[i1], kf2.angle[bidx], factor)].append(i1)
+                nmatches += 1
+    if check_ori:
+        keep = three_maxima(rot)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for j in rot[b]:
+                    out[j] = -1
+                    nmatches -= 1
+    return nmatches, np.array(out, np.int32)

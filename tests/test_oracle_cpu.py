@@ -265,3 +265,58 @@ def test_occupancy_oracle_against_python_restatement(oracle):
     assert len(got) == len(py.leaves) > 300
     assert all(got[k] == py.leaves[k] for k in got)
     assert sum(1 for v in got.values() if v < 0) > 50       # carved free cells exist
+
+
+def test_other_searches_oracle_vs_python_restatements(oracle):
+    """oracle/match_ref.cpp against oracle/match_py.py (second restatement from the reference text) for
+    SearchByProjection(Frame&, vector<MapPoint*>&, th) (:63-156), SearchByBoW(KF,F) (:217-363) and SearchByBoW(KF,KF)
+    (:665-812) on random frames: pre-existing points, stereo gate, ratio test, orientation pruning on/off."""
+    from oracle import match_py
+    from orb_slam2_ssd_semantic_b200._abi import BowView, TrackPointsView
+    rng = np.random.default_rng(21)
+    sf = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2), np.float32)])).astype(np.float32)
+    tot = [0, 0, 0]
+    for case in range(6):
+        n = int(rng.integers(80, 200))
+        x = rng.uniform(5, 635, n).astype(np.float32)
+        y = rng.uniform(5, 475, n).astype(np.float32)
+        octv = rng.integers(0, 8, n).astype(np.int32)
+        desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        z = rng.uniform(0.5, 4, n).astype(np.float32)
+        ur = np.where(rng.random(n) < 0.7, x - synth.BF / z, -1).astype(np.float32)
+        F = FrameView(x, y, octv, rng.uniform(0, 360, n).astype(np.float32), ur, desc, np.eye(4, dtype=np.float32), synth.FX,
+                      synth.FY, synth.CX, synth.CY, synth.BF, 0, 640, 0, 480, sf)
+        if case % 2 == 0:
+            F.mp_obs = rng.integers(-1, 2, n).astype(np.int32)
+        m = int(rng.integers(80, 200))
+        sel = rng.integers(0, n, m)
+        d2 = desc[sel].copy()
+        d2[:, :3] ^= rng.integers(0, 256, size=(m, 3), dtype=np.uint8)
+        px = (x[sel] + rng.normal(0, 4, m)).astype(np.float32)
+        py = (y[sel] + rng.normal(0, 4, m)).astype(np.float32)
+        pts = TrackPointsView((rng.random(m) < 0.9).astype(np.uint8), px, py, (px - synth.BF / z[sel]).astype(np.float32),
+                              np.clip(octv[sel] + rng.integers(0, 2, m), 0, 7), rng.uniform(0.99, 1.0, m).astype(np.float32), d2,
+                              mp_obs=rng.integers(0, 2, m).astype(np.int32))
+        for th in (1.0, 3.0):
+            a = oracle.search_by_projection_points(F, pts, th, 0.8)
+            b = match_py.search_by_projection_points(F, pts, th, 0.8)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), ("points", case, th)
+            tot[0] += a[0]
+        nw = int(rng.integers(4, 40))
+        fv1, fv2 = {}, {}
+        for i, w in enumerate(rng.integers(0, nw, n)):
+            fv1.setdefault(int(w) * 3, []).append(i)
+        for i, w in enumerate(rng.integers(0, nw, m)):
+            fv2.setdefault(int(w) * 3 + (0 if rng.random() < 0.8 else 1), []).append(i)
+        ang2 = rng.uniform(0, 360, m).astype(np.float32)
+        K = BowView(desc, F.angle, fv1, valid=(rng.random(n) < 0.85).astype(np.uint8))
+        Fr = BowView(d2, ang2, fv2)
+        K2 = BowView(d2, ang2, fv2, valid=(rng.random(m) < 0.85).astype(np.uint8))
+        for ori in (True, False):
+            a, b = oracle.search_by_bow(K, Fr, 0.7, ori), match_py.search_by_bow(K, Fr, 0.7, ori)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), ("bow", case, ori)
+            tot[1] += a[0]
+            a, b = oracle.search_by_bow_kf(K, K2, 0.75, ori), match_py.search_by_bow_kf(K, K2, 0.75, ori)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), ("bow_kf", case, ori)
+            tot[2] += a[0]
+    assert min(tot) > 20, tot
