@@ -315,3 +315,55 @@ def search_by_bow_kf(kf1, kf2, nnratio=0.75, check_ori=True):
                     out[j] = -1
                     nmatches -= 1
     return nmatches, np.array(out, np.int32)
+
+
+def search_projected(F, q, max_dist, claim_rule=1, check_ori=True):
+    """The part the remaining projection overloads share, from the candidate query on, written after the loop bodies of
+    SearchByProjection(Frame&, KeyFrame*, set, th, ORBdist) (src/ORBmatcher.cc:1800-1850: rule 1, any MapPoint on the
+    candidate blocks it) and of the LAST overload (:1645-1693: rule 0, only MapPoints with Observations() > 0 block;
+    stereo gate when a predicted right coordinate is supplied).  q = QueriesView with per-query (u, v, radius, level
+    range, descriptor, angle).  Returns (nmatches, keypoint -> query index; -2 = untouched pre-existing point)."""
+    grid = Grid(F)
+    state = [-1] * F.n
+    obs = [0] * F.n
+    if F.mp_obs is not None:
+        for j in range(F.n):
+            if F.mp_obs[j] >= 0:
+                state[j], obs[j] = -2, int(F.mp_obs[j])
+    rot = [[] for _ in range(HISTO_LENGTH)]
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    nmatches = 0
+    for i in range(q.n):
+        if not q.valid[i]:
+            continue
+        u, v, radius = f32(q.u[i]), f32(q.v[i]), f32(q.radius[i])
+        if np.isnan(u) or np.isnan(v):
+            continue
+        cand = grid.query(u, v, radius, int(q.min_level[i]), int(q.max_level[i]))
+        if not cand:
+            continue
+        best, bidx = 256, -1
+        for i2 in cand:
+            if state[i2] != -1:                       # a MapPoint sits on the candidate
+                if claim_rule == 1 or obs[i2] > 0:
+                    continue
+            if q.uright is not None and F.uright[i2] > 0:
+                if abs(f32(f32(q.uright[i]) - F.uright[i2])) > radius:
+                    continue
+            d = hamming(q.desc[i], F.desc[i2])
+            if d < best:
+                best, bidx = d, i2
+        if best <= max_dist:
+            state[bidx] = i
+            obs[bidx] = int(q.obs[i]) if q.obs is not None else 1
+            nmatches += 1
+            if check_ori:
+                rot[_rot_bin(q.angle[i], F.angle[bidx], factor)].append(bidx)
+    if check_ori:
+        keep = three_maxima(rot)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for idx in rot[b]:
+                    state[idx] = -1
+                    nmatches -= 1
+    return nmatches, np.array(state, np.int32)

@@ -320,3 +320,42 @@ def test_other_searches_oracle_vs_python_restatements(oracle):
             assert a[0] == b[0] and (a[1] == b[1]).all(), ("bow_kf", case, ori)
             tot[2] += a[0]
     assert min(tot) > 20, tot
+
+
+def test_generic_projected_search_oracle_vs_python_restatement(oracle):
+    """match_ref_projected (the loop body the relocalisation / loop-closing projection overloads share) against
+    oracle/match_py.search_projected: both claim rules, with and without the stereo gate / orientation pruning."""
+    from oracle import match_py
+    from orb_slam2_ssd_semantic_b200._abi import QueriesView
+    rng = np.random.default_rng(33)
+    sf = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2), np.float32)])).astype(np.float32)
+    tot = 0
+    for case in range(8):
+        n = int(rng.integers(80, 220))
+        x = rng.uniform(5, 635, n).astype(np.float32)
+        y = rng.uniform(5, 475, n).astype(np.float32)
+        octv = rng.integers(0, 8, n).astype(np.int32)
+        desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        z = rng.uniform(0.5, 4, n).astype(np.float32)
+        ur = np.where(rng.random(n) < 0.7, x - synth.BF / z, -1).astype(np.float32)
+        F = FrameView(x, y, octv, rng.uniform(0, 360, n).astype(np.float32), ur, desc, np.eye(4, dtype=np.float32), synth.FX,
+                      synth.FY, synth.CX, synth.CY, synth.BF, 0, 640, 0, 480, sf)
+        if case % 2 == 0:
+            F.mp_obs = rng.integers(-1, 2, n).astype(np.int32)
+        m = int(rng.integers(80, 220))
+        sel = rng.integers(0, n, m)
+        d2 = desc[sel].copy()
+        d2[:, :3] ^= rng.integers(0, 256, size=(m, 3), dtype=np.uint8)
+        u = (x[sel] + rng.normal(0, 4, m)).astype(np.float32)
+        v = (y[sel] + rng.normal(0, 4, m)).astype(np.float32)
+        lvl = np.clip(octv[sel] + rng.integers(-1, 2, m), 0, 7)
+        for rule, (md, ori) in enumerate([(100, True), (64, False)]):
+            q = QueriesView((rng.random(m) < 0.9).astype(np.uint8), u, v, (np.float32(8.0) * sf[lvl]).astype(np.float32),
+                            lvl - 1, lvl + 1, d2, rng.uniform(0, 360, m).astype(np.float32),
+                            uright=(u - synth.BF / z[sel]).astype(np.float32) if case % 3 == 0 else None,
+                            obs=rng.integers(0, 2, m).astype(np.int32) if rule == 0 else None)
+            a = oracle.search_projected(F, q, md, rule, ori)
+            b = match_py.search_projected(F, q, md, rule, ori)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), (case, rule)
+            tot += a[0]
+    assert tot > 300
