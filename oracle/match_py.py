@@ -367,3 +367,33 @@ def search_projected(F, q, max_dist, claim_rule=1, check_ori=True):
                     state[idx] = -1
                     nmatches -= 1
     return nmatches, np.array(state, np.int32)
+
+
+def stereo_unproject(kps_xy, depth, Tcw, fx, fy, cx, cy, bf):
+    """Frame::ComputeStereoFromRGBD (src/Frame.cc:850-871) + Frame::UnprojectStereo (:879-899) for every keypoint:
+    d = imDepth.at<float>(v, u) (float coordinates truncated by the int conversion), uRight = x - bf / d,
+    x3Dc = ((u - cx) z invfx, (v - cy) z invfy, z) with invfx = 1.0f / fx (:215-216), world = mRwc x3Dc + mOw with
+    mRwc = mRcw.t() and mOw = -mRcw.t() mtcw (:308-311; cv::Mat products: float accumulation, '+ C' in double; the
+    3x3 * 3x1 product of mOw accumulates in double).  -> (uright, depth, xw, valid)."""
+    fx, fy, cx, cy, bf = (f32(v) for v in (fx, fy, cx, cy, bf))
+    invfx, invfy = f32(f32(1.0) / fx), f32(f32(1.0) / fy)
+    T = np.asarray(Tcw, np.float32).reshape(4, 4)
+    Rcw, tcw = T[:3, :3], T[:3, 3]
+    Ow = [f32(-sum(float(Rcw[k, i]) * float(tcw[k]) for k in range(3))) for i in range(3)]
+    n = len(kps_xy)
+    ur = np.full(n, -1, np.float32)
+    dp = np.full(n, -1, np.float32)
+    xw = np.zeros((n, 3), np.float32)
+    va = np.zeros(n, np.uint8)
+    for i, (u, v) in enumerate(kps_xy):
+        u, v = f32(u), f32(v)
+        d = f32(depth[int(v), int(u)])
+        if d > 0:
+            dp[i] = d
+            ur[i] = f32(u - f32(bf / d))
+            x = f32(f32(f32(u - cx) * d) * invfx)
+            y = f32(f32(f32(v - cy) * d) * invfy)
+            for r in range(3):
+                xw[i, r] = gemm3([Rcw[0, r], Rcw[1, r], Rcw[2, r]], [x, y, d], Ow[r])
+            va[i] = 1
+    return ur, dp, xw, va

@@ -359,3 +359,21 @@ def test_generic_projected_search_oracle_vs_python_restatement(oracle):
             assert a[0] == b[0] and (a[1] == b[1]).all(), (case, rule)
             tot += a[0]
     assert tot > 300
+
+
+def test_stereo_unproject_oracle_vs_python_restatement(oracle):
+    """frame_ref_stereo_unproject (ComputeStereoFromRGBD + UnprojectStereo, src/Frame.cc:850-899) against the second
+    restatement in oracle/match_py.py, bit for bit, including keypoints without depth."""
+    from oracle import match_py
+    ws = synth.WallStream(seed=4, n=2)
+    rng = np.random.default_rng(2)
+    for t in range(2):
+        gray, depth, rgb, T = ws.frame(t * 9)
+        depth = depth.copy()
+        depth[rng.random(depth.shape) < 0.3] = 0
+        K, _ = oracle.RefExtractor(500, 1.2, 8, 20, 7)(gray)
+        a = oracle.stereo_unproject(K, depth, T, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+        b = match_py.stereo_unproject(list(zip(K["x"], K["y"])), depth, T, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
+        assert 0.5 * len(K) < a[3].sum() < 0.9 * len(K)
+        for x, y in zip(a, b):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
