@@ -4,8 +4,11 @@
 // Written as templates over the reference's own Frame / MapPoint types so this header does not need Frame.h:
 //   #include "Frame.h"  #include "MapPoint.h"  #include "shim/ORBmatcher.h"
 //   namespace ORB_SLAM2 { typedef ORBmatcherT<Frame, MapPoint> ORBmatcher; }
-// Implemented overloads: SearchByProjection(Frame&, const Frame&, th, bMono) (src/ORBmatcher.cc:1578-1724) and
-// SearchByProjection(Frame&, const std::vector<MapPoint*>&, th) (:63-156); DescriptorDistance (:1968-1984).
+// Implemented overloads: SearchByProjection(Frame&, const Frame&, th, bMono) (src/ORBmatcher.cc:1578-1724),
+// SearchByProjection(Frame&, const std::vector<MapPoint*>&, th) (:63-156), SearchByBoW(KeyFrame*, Frame&, ...) (:217-363),
+// SearchByBoW(KeyFrame*, KeyFrame*, ...) (:665-812); DescriptorDistance (:1968-1984).  The KeyFrame type is a template
+// parameter of the BoW methods (its mFeatVec is any ordered map node id -> vector of keypoint indices, like
+// DBoW2::FeatureVector).
 #ifndef ORBMATCHER_SHIM_H
 #define ORBMATCHER_SHIM_H
 
@@ -103,7 +106,78 @@ class ORBmatcherT {
     return nmatches;
   }
 
+  // src/ORBmatcher.cc:217-363: vpMapPointMatches[i] = MapPoint of the keyframe keypoint matched to frame keypoint i
+  template <class KeyFrame>
+  int SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    FlatBow kf, fr;
+    flatten_bow(pKF->mDescriptors, pKF->mvKeysUn, pKF->mFeatVec, &vpMapPointsKF, kf);
+    flatten_bow(F.mDescriptors, F.mvKeys, F.mFeatVec, (const std::vector<MapPoint*>*)nullptr, fr);   // mvKeys: :308
+    std::vector<int32_t> f2kf(fr.view.n > 0 ? fr.view.n : 1, -1);
+    int nmatches = 0;
+    if (orbm_search_by_bow(h_, &kf.view, &fr.view, mfNNratio, mbCheckOrientation ? 1 : 0, f2kf.data(), &nmatches) != B200ORB_OK)
+      throw std::runtime_error(std::string("ORBmatcher(B200): ") + b200orb_last_error());
+    vpMapPointMatches.assign((size_t)F.N, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < F.N; ++i)
+      if (f2kf[i] >= 0) vpMapPointMatches[i] = vpMapPointsKF[f2kf[i]];
+    return nmatches;
+  }
+
+  // src/ORBmatcher.cc:665-812: vpMatches12[i] = MapPoint of the pKF2 keypoint matched to pKF1 keypoint i
+  template <class KeyFrame>
+  int SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches(), vpMapPoints2 = pKF2->GetMapPointMatches();
+    FlatBow k1, k2;
+    flatten_bow(pKF1->mDescriptors, pKF1->mvKeysUn, pKF1->mFeatVec, &vpMapPoints1, k1);
+    flatten_bow(pKF2->mDescriptors, pKF2->mvKeysUn, pKF2->mFeatVec, &vpMapPoints2, k2);
+    std::vector<int32_t> m12(k1.view.n > 0 ? k1.view.n : 1, -1);
+    int nmatches = 0;
+    if (orbm_search_by_bow_kf(h_, &k1.view, &k2.view, mfNNratio, mbCheckOrientation ? 1 : 0, m12.data(), &nmatches) != B200ORB_OK)
+      throw std::runtime_error(std::string("ORBmatcher(B200): ") + b200orb_last_error());
+    vpMatches12.assign(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+    for (size_t i = 0; i < vpMapPoints1.size(); ++i)
+      if (m12[i] >= 0) vpMatches12[i] = vpMapPoints2[m12[i]];
+    return nmatches;
+  }
+
  protected:
+  struct FlatBow {
+    std::vector<uint8_t> desc, valid;
+    std::vector<float> ang;
+    std::vector<uint32_t> node_ids, idx;
+    std::vector<int32_t> node_off;
+    OrbmBow view;
+  };
+  // descriptors + angles + the FeatureVector (ordered map: ascending node ids) flattened; mps == NULL: no validity mask
+  template <class Keys, class FeatVec>
+  static void flatten_bow(const cv::Mat& descriptors, const Keys& keys, const FeatVec& fv, const std::vector<MapPoint*>* mps,
+                          FlatBow& o) {
+    const int n = (int)keys.size();
+    o.desc.resize((size_t)(n > 0 ? n : 1) * 32);
+    o.ang.resize(n > 0 ? n : 1);
+    for (int i = 0; i < n; ++i) {
+      std::memcpy(&o.desc[(size_t)i * 32], descriptors.ptr(i), 32);
+      o.ang[i] = keys[i].angle;
+    }
+    if (mps) {
+      o.valid.assign(n > 0 ? n : 1, 0);
+      for (int i = 0; i < n; ++i) {
+        MapPoint* p = (*mps)[i];
+        o.valid[i] = (p && !p->isBad()) ? 1 : 0;
+      }
+    }
+    o.node_off.assign(1, 0);
+    for (typename FeatVec::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+      o.node_ids.push_back((uint32_t)it->first);
+      for (size_t k = 0; k < it->second.size(); ++k) o.idx.push_back((uint32_t)it->second[k]);
+      o.node_off.push_back((int32_t)o.idx.size());
+    }
+    if (o.idx.empty()) o.idx.push_back(0);
+    if (o.node_ids.empty()) o.node_ids.push_back(0);
+    OrbmBow& v = o.view;
+    v.n = n; v.desc = o.desc.data(); v.angle = o.ang.data(); v.valid = mps ? o.valid.data() : nullptr;
+    v.n_nodes = (int)o.node_off.size() - 1; v.node_ids = o.node_ids.data(); v.node_off = o.node_off.data(); v.idx = o.idx.data();
+  }
   struct FlatFrame {
     int n = 0;
     std::vector<float> x, y, ang, ur, sf;

@@ -2,6 +2,7 @@
 // Built and run by tests/test_abi_cpu.py (compile + link only on the CPU box) and tests/test_shim_gpu.py.
 #define B200_SHIM_STANDIN
 #include <cstdio>
+#include <map>
 
 #include "ORBextractor.h"
 #include "pointcloudmapping.h"
@@ -19,8 +20,10 @@ struct MockMapPoint {
   int Observations() { return obs; }
   bool isBad() { return false; }
 };
+typedef std::map<unsigned int, std::vector<unsigned int> > MockFeatureVector;   // DBoW2::FeatureVector's shape
 struct MockFrame {
   int N = 0;
+  MockFeatureVector mFeatVec;
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
   std::vector<float> mvuRight, mvScaleFactors;
   std::vector<MockMapPoint*> mvpMapPoints;
@@ -30,9 +33,23 @@ struct MockFrame {
   static float mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
 float MockFrame::mnMinX = 0, MockFrame::mnMaxX = 640, MockFrame::mnMinY = 0, MockFrame::mnMaxY = 480;
+struct MockKeyFrame {   // the members SearchByBoW reads (include/KeyFrame.h)
+  std::vector<cv::KeyPoint> mvKeysUn;
+  cv::Mat mDescriptors;
+  MockFeatureVector mFeatVec;
+  std::vector<MockMapPoint*> mps;
+  std::vector<MockMapPoint*> GetMapPointMatches() { return mps; }
+};
 typedef ORB_SLAM2::ORBmatcherT<MockFrame, MockMapPoint> MockMatcher;
 
 int main(int argc, char** argv) {
+  if (argc > 1000) {   // never taken: instantiates the BoW overloads of the matcher shim so that they are compile-checked
+    MockMatcher m(0.7f, true);
+    MockKeyFrame k1, k2;
+    MockFrame f;
+    std::vector<MockMapPoint*> out;
+    return m.SearchByBoW(&k1, f, out) + m.SearchByBoW(&k1, &k2, out);
+  }
   if (b200orb_device_count() == 0) {
     try {
       ORB_SLAM2::ORBextractor e(1000, 1.2f, 8, 20, 7);
