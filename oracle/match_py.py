@@ -397,3 +397,56 @@ def stereo_unproject(kps_xy, depth, Tcw, fx, fy, cx, cy, bf):
                 xw[i, r] = gemm3([Rcw[0, r], Rcw[1, r], Rcw[2, r]], [x, y, d], Ow[r])
             va[i] = 1
     return ur, dp, xw, va
+
+
+def search_for_initialization(F1, F2, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:523-660): level-0
+    keypoints of F1 search F2 in a fixed window around their previous match; a strictly closer match steals an F2
+    keypoint that is already matched; ratio test against the second best; orientation pruning only clears entries
+    that are still matched.  Returns (nmatches, matches12, updated vbPrevMatched)."""
+    nnratio = f32(nnratio)
+    factor = f32(f32(1.0) / f32(HISTO_LENGTH))
+    grid = Grid(F2)
+    INT_MAX = 2147483647
+    m12 = [-1] * F1.n
+    m21 = [-1] * F2.n
+    mdist = [INT_MAX] * F2.n
+    prev = np.array(prev_xy, np.float32).reshape(-1, 2).copy()
+    rot = [[] for _ in range(HISTO_LENGTH)]
+    nmatches = 0
+    for i1 in range(F1.n):
+        level1 = int(F1.octave[i1])
+        if level1 > 0:
+            continue
+        cand = grid.query(f32(prev[i1, 0]), f32(prev[i1, 1]), f32(window), level1, level1)
+        if not cand:
+            continue
+        best, best2, bidx = INT_MAX, INT_MAX, -1
+        for i2 in cand:
+            d = hamming(F1.desc[i1], F2.desc[i2])
+            if mdist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bidx = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= TH_LOW and f32(best) < f32(f32(best2) * nnratio):
+            if m21[bidx] >= 0:
+                m12[m21[bidx]] = -1
+                nmatches -= 1
+            m12[i1], m21[bidx], mdist[bidx] = bidx, i1, best
+            nmatches += 1
+            if check_ori:
+                rot[_rot_bin(F1.angle[i1], F2.angle[bidx], factor)].append(i1)
+    if check_ori:
+        keep = three_maxima(rot)
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for i1 in rot[b]:
+                    if m12[i1] >= 0:
+                        m12[i1] = -1
+                        nmatches -= 1
+    for i1 in range(F1.n):
+        if m12[i1] >= 0:
+            prev[i1] = (F2.x[m12[i1]], F2.y[m12[i1]])
+    return nmatches, np.array(m12, np.int32), prev

@@ -287,6 +287,62 @@ int match_ref_projected(const OrbmFrame* cur, const OrbmQueries* q, int max_dist
   return 0;
 }
 
+// SearchForInitialization(Frame& F1, Frame& F2, vector<Point2f>& vbPrevMatched, vector<int>& vnMatches12, int windowSize),
+// src/ORBmatcher.cc:523-660 (monocular initialisation; not behind the C-ABI yet -- the oracle is here so that the
+// kernel of the next round has its checker).  F1 supplies keypoints (octave, angle) and descriptors, F2 additionally
+// its grid; prev_xy[n1][2] is vbPrevMatched (in/out), matches12[n1] the result.  Differences from the projection
+// searches: level 0 only, a closer match STEALS an already matched F2 keypoint (vMatchedDistance), ratio test against
+// the second best, and the orientation prune only clears entries that are still matched.
+int match_ref_initialization(const OrbmFrame* F1, const OrbmFrame* F2, float* prev_xy, int window, float nnratio,
+                             int check_ori, int32_t* matches12, int* nmatches_out) {
+  int nmatches = 0;
+  std::vector<int> rotHist[HISTO_LENGTH];
+  Grid* grid = new Grid();
+  grid->build(F2);
+  std::vector<int> vnMatches12(F1->n, -1), vnMatches21(F2->n, -1), vMatchedDistance(F2->n, 2147483647);
+  std::vector<int> cand;
+  for (int i1 = 0; i1 < F1->n; ++i1) {
+    const int level1 = F1->octave[i1];
+    if (level1 > 0) continue;
+    grid->query(prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window, level1, level1, cand);
+    if (cand.empty()) continue;
+    const uint8_t* d1 = F1->desc + 32 * (size_t)i1;
+    int bestDist = 2147483647, bestDist2 = 2147483647, bestIdx2 = -1;
+    for (int i2 : cand) {
+      const int dist = desc_dist(d1, F2->desc + 32 * (size_t)i2);
+      if (vMatchedDistance[i2] <= dist) continue;
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+      else if (dist < bestDist2) bestDist2 = dist;
+    }
+    if (bestDist <= TH_LOW) {
+      if (bestDist < (float)bestDist2 * nnratio) {
+        if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+        vnMatches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (check_ori) rotHist[rot_bin(F1->angle[i1], F2->angle[bestIdx2])].push_back(i1);
+      }
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+    }
+  }
+  for (int i1 = 0; i1 < F1->n; ++i1) {
+    matches12[i1] = vnMatches12[i1];
+    if (vnMatches12[i1] >= 0) { prev_xy[2 * i1] = F2->x[vnMatches12[i1]]; prev_xy[2 * i1 + 1] = F2->y[vnMatches12[i1]]; }
+  }
+  *nmatches_out = nmatches;
+  delete grid;
+  return 0;
+}
+
 // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:217-363
 int match_ref_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
                   int* nmatches_out) {

@@ -356,3 +356,18 @@ def global_refilter(xyz, rgb, leaf):
     if m < 0:
         raise ValueError("global_refilter: %s" % ("index space overflows int" if m == -1 else "cap"))
     return out[:m].copy(), out_rgb[:m].copy()
+
+
+def search_for_initialization(F1, F2, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    """SearchForInitialization (src/ORBmatcher.cc:523-660) -> (nmatches, matches12, updated vbPrevMatched)."""
+    from orb_slam2_ssd_semantic_b200 import _abi
+    L = _mlib()
+    L.match_ref_initialization.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmFrame), C.c_void_p, C.c_int,
+                                           C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    prev = np.ascontiguousarray(prev_xy, np.float32).reshape(-1, 2).copy()
+    out = np.full(F1.n, -1, np.int32)
+    nm = C.c_int(0)
+    a, b = F1.struct(), F2.struct()
+    L.match_ref_initialization(C.byref(a), C.byref(b), _p(prev), int(window), float(nnratio), int(check_ori), _p(out),
+                               C.byref(nm))
+    return nm.value, out, prev

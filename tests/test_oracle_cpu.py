@@ -377,3 +377,37 @@ def test_stereo_unproject_oracle_vs_python_restatement(oracle):
         assert 0.5 * len(K) < a[3].sum() < 0.9 * len(K)
         for x, y in zip(a, b):
             assert np.asarray(x).tobytes() == np.asarray(y).tobytes()
+
+
+def test_search_for_initialization_oracle_vs_python_restatement(oracle):
+    """match_ref_initialization (SearchForInitialization, src/ORBmatcher.cc:523-660; oracle only so far, the kernel is
+    next round's work) against the second restatement: steal-if-closer rule, ratio test, prune of still-matched entries."""
+    from oracle import match_py
+    rng = np.random.default_rng(41)
+    sf = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2), np.float32)])).astype(np.float32)
+    tot = 0
+    for case in range(8):
+        n = int(rng.integers(150, 400))
+        x = rng.uniform(5, 635, n).astype(np.float32)
+        y = rng.uniform(5, 475, n).astype(np.float32)
+        octv = rng.integers(0, 3, n).astype(np.int32)           # a third of the keypoints on level 0
+        desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+        ang = rng.uniform(0, 360, n).astype(np.float32)
+        mk = lambda xx, yy, dd, aa: FrameView(xx, yy, octv, aa, np.full(n, -1, np.float32), dd, np.eye(4, dtype=np.float32),
+                                              synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, 0, 640, 0, 480, sf)
+        F1 = mk(x, y, desc, ang)
+        d2 = desc.copy()
+        flip = rng.integers(0, 256, size=(n, 2), dtype=np.uint8)
+        d2[:, :2] ^= flip
+        dup = rng.integers(0, n, n // 6)                        # near-duplicate descriptors: contested F2 keypoints
+        d2[dup] = d2[(dup + 1) % n]
+        F2 = mk((x + rng.normal(0, 6, n)).astype(np.float32), (y + rng.normal(0, 6, n)).astype(np.float32), d2,
+                (ang + rng.normal(0, 4, n)).astype(np.float32) % np.float32(360))
+        prev = np.stack([x, y], 1)
+        for window, ori in ((100, True), (30, False)):
+            a = oracle.search_for_initialization(F1, F2, prev, window, 0.9, ori)
+            b = match_py.search_for_initialization(F1, F2, prev, window, 0.9, ori)
+            assert a[0] == b[0] and (a[1] == b[1]).all() and a[2].tobytes() == b[2].tobytes(), (case, window, ori)
+            assert a[0] == (a[1] >= 0).sum()
+            tot += a[0]
+    assert tot > 200
