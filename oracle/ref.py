@@ -371,3 +371,164 @@ def search_for_initialization(F1, F2, prev_xy, window=100, nnratio=0.9, check_or
     L.match_ref_initialization(C.byref(a), C.byref(b), _p(prev), int(window), float(nnratio), int(check_ori), _p(out),
                                C.byref(nm))
     return nm.value, out, prev
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref/librefsrc.so: the REFERENCE'S OWN sources (src/ORBextractor.cc, ORBmatcher.cc, Frame.cc, KeyFrame.cc,
+# MapPoint.cc, Map.cc) compiled unmodified against oracle/standin/ (see oracle/Makefile, target `ref`).  Same call
+# signatures as the restatement above, so tests can assert restatement == reference sources.
+_REFSO = os.path.join(_HERE, "_ref", "librefsrc.so")
+_reflib = None
+
+
+def refsrc_available() -> bool:
+    return os.path.exists(_REFSO) or os.path.exists("/root/reference/src/ORBextractor.cc")
+
+
+def reflib() -> C.CDLL:
+    global _reflib
+    if _reflib is None:
+        if not os.path.exists(_REFSO):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        from orb_slam2_ssd_semantic_b200 import _abi
+        L = C.CDLL(_REFSO)
+        L.refsrc_orb_create.restype = C.c_void_p
+        L.refsrc_orb_create.argtypes = [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.refsrc_orb_destroy.argtypes = [C.c_void_p]
+        L.refsrc_orb_extract.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p]
+        L.refsrc_orb_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.refsrc_orb_level_dims.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.refsrc_orb_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.refsrc_orb_distribute.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_int]
+        L.refsrc_hamming.argtypes = [C.c_void_p, C.c_void_p]
+        PF, PL, PT, PB = (C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmLast), C.POINTER(_abi.OrbmTrackPoints),
+                          C.POINTER(_abi.OrbmBow))
+        L.refsrc_projection_last.argtypes = [PF, PL, C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.refsrc_projection_points.argtypes = [PF, PT, C.c_float, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+        L.refsrc_bow.argtypes = [PB, PB, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.refsrc_bow_kf.argtypes = [PB, PB, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.refsrc_initialization.argtypes = [PF, PF, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        L.refsrc_frame_rgbd.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p] + [C.c_float] * 5 + [C.c_void_p] * 7 + [C.c_int, C.c_void_p])
+        L.refsrc_is_in_frustum.argtypes = [PF, C.c_int] + [C.c_void_p] * 4 + [C.c_float] + [C.c_void_p] * 6
+        _reflib = L
+    return _reflib
+
+
+class SrcExtractor:
+    """ORB_SLAM2::ORBextractor of the reference (src/ORBextractor.cc compiled unmodified)."""
+
+    def __init__(self, nfeatures=1000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7):
+        self.L = reflib()
+        self.nlevels = nlevels
+        self.h = self.L.refsrc_orb_create(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self.cap = nfeatures + 16 * nlevels + 64
+        t = [np.zeros(nlevels, np.float32) for _ in range(4)] + [np.zeros(nlevels, np.int32), np.zeros(16, np.int32)]
+        self.L.refsrc_orb_tables(self.h, *[_p(a) for a in t])
+        (self.mvScaleFactor, self.mvInvScaleFactor, self.mvLevelSigma2, self.mvInvLevelSigma2,
+         self.mnFeaturesPerLevel, self.umax) = t
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.refsrc_orb_destroy(self.h)
+            self.h = None
+
+    def __call__(self, image: np.ndarray):
+        image = np.asarray(image)
+        assert image.dtype == np.uint8 and image.ndim == 2
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int(0)
+        rc = self.L.refsrc_orb_extract(self.h, image.ctypes.data, image.shape[0], image.shape[1], image.strides[0],
+                                       _p(kps), _p(desc), self.cap, C.byref(n))
+        assert rc == 0
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def level(self, l: int, bordered: bool = False) -> np.ndarray:
+        w, h = C.c_int(0), C.c_int(0)
+        assert self.L.refsrc_orb_level_dims(self.h, l, C.byref(w), C.byref(h)) == 0
+        B = 19 if bordered else 0
+        out = np.zeros((h.value + 2 * B, w.value + 2 * B), np.uint8)
+        self.L.refsrc_orb_get_level(self.h, l, int(bordered), _p(out))
+        return out
+
+
+def src_distribute(kps, minX, maxX, minY, maxY, N):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros(len(kps) + 8, KP_DTYPE)
+    n = reflib().refsrc_orb_distribute(_p(kps), len(kps), minX, maxX, minY, maxY, N, _p(out), len(out))
+    assert n >= 0
+    return out[:n].copy()
+
+
+def src_hamming(a, b) -> int:
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return int(reflib().refsrc_hamming(_p(a), _p(b)))
+
+
+def src_search_by_projection_last(cur, last, th, mono=False, nnratio=0.9, check_ori=True):
+    out = np.full(cur.n, -1, np.int32)
+    nm = C.c_int(0)
+    cs, ls = cur.struct(), last.struct()
+    reflib().refsrc_projection_last(C.byref(cs), C.byref(ls), float(th), int(mono), float(nnratio), int(check_ori),
+                                    _p(out), C.byref(nm))
+    return nm.value, out
+
+
+def src_search_by_projection_points(F, pts, th, nnratio=0.8):
+    out = np.full(F.n, -1, np.int32)
+    nm = C.c_int(0)
+    fs, ps = F.struct(), pts.struct()
+    reflib().refsrc_projection_points(C.byref(fs), C.byref(ps), float(th), float(nnratio), _p(out), C.byref(nm))
+    return nm.value, out
+
+
+def src_search_by_bow(kf, f, nnratio=0.7, check_ori=True):
+    out = np.full(f.n, -1, np.int32)
+    nm = C.c_int(0)
+    ks, fs = kf.struct(), f.struct()
+    reflib().refsrc_bow(C.byref(ks), C.byref(fs), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+    return nm.value, out
+
+
+def src_search_by_bow_kf(kf1, kf2, nnratio=0.75, check_ori=True):
+    out = np.full(kf1.n, -1, np.int32)
+    nm = C.c_int(0)
+    a, b = kf1.struct(), kf2.struct()
+    reflib().refsrc_bow_kf(C.byref(a), C.byref(b), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+    return nm.value, out
+
+
+def src_search_for_initialization(F1, F2, prev_xy, window=100, nnratio=0.9, check_ori=True):
+    prev = np.ascontiguousarray(prev_xy, np.float32).reshape(-1, 2).copy()
+    out = np.full(F1.n, -1, np.int32)
+    nm = C.c_int(0)
+    a, b = F1.struct(), F2.struct()
+    reflib().refsrc_initialization(C.byref(a), C.byref(b), _p(prev), int(window), float(nnratio), int(check_ori),
+                                   _p(out), C.byref(nm))
+    return nm.value, out, prev
+
+
+def src_frame_rgbd(gray, depth, Tcw, fx, fy, cx, cy, bf, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7,
+                   dist=None):
+    """The reference's RGB-D Frame constructor (src/Frame.cc:176-240) + UnprojectStereo per keypoint."""
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+    cap = nfeatures + 16 * nlevels + 64
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    ur, dp, xw, va = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros((cap, 3), np.float32), np.zeros(cap, np.uint8)
+    n = C.c_int(0)
+    d4 = None if dist is None else np.ascontiguousarray(dist, np.float32)
+    rc = reflib().refsrc_frame_rgbd(_p(gray), _p(depth), gray.shape[0], gray.shape[1], nfeatures, scale, nlevels, ini_th,
+                                    min_th, _p(T), fx, fy, cx, cy, bf, None if d4 is None else _p(d4), _p(kps), _p(desc),
+                                    _p(ur), _p(dp), _p(xw), _p(va), cap, C.byref(n))
+    assert rc == 0
+    m = n.value
+    return kps[:m].copy(), desc[:m].copy(), ur[:m].copy(), dp[:m].copy(), xw[:m].copy(), va[:m].copy()

@@ -1,0 +1,449 @@
+// oracle/refsrc_harness.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT.
+//
+// C entry points around the REFERENCE'S OWN translation units, compiled unmodified from /root/reference into
+// oracle/_ref/ (see oracle/Makefile, target `ref`): src/ORBextractor.cc, src/ORBmatcher.cc, src/Frame.cc,
+// src/KeyFrame.cc, src/MapPoint.cc, src/Map.cc.  Each entry takes the same flat views as the restatement in
+// oracle/match_ref.cpp / orb_ref.cpp (the C-ABI structs of include/b200orb.h), builds real ORB_SLAM2::Frame /
+// KeyFrame / MapPoint objects from them, calls the real member function and flattens the pointer state it leaves.
+// tests/test_oracle_cpu.py asserts restatement == this, bit for bit; that is what pins the oracle to reference code.
+//
+// Nothing here restates reference logic.  `#define private public` only opens the classes so that a Frame can be
+// filled from arrays instead of from an image (the class layout is unchanged; the reference's .cc files are compiled
+// without it).  OpenCV / DBoW2 are stand-ins (oracle/standin/), third-party arithmetic stated there.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <list>
+#include <map>
+#include <mutex>
+#include <new>
+#include <set>
+#include <sstream>
+#include <thread>
+#include <vector>
+
+#include "../include/b200orb.h"
+
+#define private public
+#define protected public
+#include "ORBextractor.h"
+#include "ORBmatcher.h"
+#include "Frame.h"
+#include "KeyFrame.h"
+#include "MapPoint.h"
+#include "Map.h"
+#include "KeyFrameDatabase.h"
+#undef private
+#undef protected
+
+namespace ORB_SLAM2 {
+// the only out-of-path symbol the six translation units leave undefined (KeyFrame::SetBadFlag -> database erase)
+void KeyFrameDatabase::erase(KeyFrame*) {}
+}  // namespace ORB_SLAM2
+
+using namespace ORB_SLAM2;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Monotonic storage for the quad-tree's list nodes.  DistributeOctTree orders equal-size nodes by their HEAP ADDRESS
+// (src/ORBextractor.cc:686 sorts pair<int, ExtractorNode*>), so the reference's keypoint order depends on the allocator
+// of the build it runs in.  Here every std::list<ExtractorNode> node comes from a bump arena that
+// never reuses memory inside one call, which makes "higher address" == "created later": the reference itself, made
+// deterministic, and the rule the restatement and the kernels document ("later-created node first").
+// Bound inside this library only (-Wl,-Bsymbolic); everything else goes to malloc/free.
+namespace {
+const size_t kNodeBytes = sizeof(std::_List_node<ExtractorNode>);
+const size_t kArenaBytes = 64u << 20;
+char* g_arena = nullptr;
+size_t g_arena_used = 0;
+bool g_arena_on = false;
+inline void arena_reset() {
+  if (!g_arena) g_arena = (char*)malloc(kArenaBytes);
+  g_arena_used = 0;
+  g_arena_on = true;
+}
+}  // namespace
+void* operator new(size_t n) {
+  if (g_arena_on && n == kNodeBytes && g_arena_used + ((n + 15) & ~size_t(15)) <= kArenaBytes) {
+    void* p = g_arena + g_arena_used;
+    g_arena_used += (n + 15) & ~size_t(15);
+    return p;
+  }
+  void* p = malloc(n ? n : 1);
+  if (!p) throw std::bad_alloc();
+  return p;
+}
+void operator delete(void* p) noexcept {
+  if (g_arena && (char*)p >= g_arena && (char*)p < g_arena + kArenaBytes) return;
+  free(p);
+}
+void operator delete(void* p, size_t) noexcept { operator delete(p); }
+
+namespace {
+
+std::mutex g_mu;   // Frame keeps intrinsics / bounds in statics: one harness call at a time
+Map g_map;
+
+cv::Mat mat44(const float* T) {
+  cv::Mat m(4, 4, CV_32F);
+  memcpy(m.data, T, 16 * sizeof(float));
+  return m;
+}
+cv::Mat desc_row(const uint8_t* d) {
+  cv::Mat m(1, 32, CV_8U);
+  memcpy(m.data, d, 32);
+  return m;
+}
+
+// A Frame filled from the flat view exactly as the RGB-D constructor leaves it (src/Frame.cc:176-240) minus the
+// extraction itself: keypoints, descriptors, uRight, scale tables, statics, grid, pose.
+Frame* make_frame(const OrbmFrame* f, const float* depth = nullptr) {
+  Frame* F = new Frame();
+  F->mpORBvocabulary = nullptr; F->mpORBextractorLeft = nullptr; F->mpORBextractorRight = nullptr;
+  F->mnId = Frame::nNextId++;
+  F->mTimeStamp = 0;
+  F->mbf = f->bf; F->mb = f->b; F->mThDepth = 40.0f * f->b;
+  F->N = f->n;
+  F->mvKeys.resize(f->n); F->mvKeysUn.resize(f->n);
+  for (int i = 0; i < f->n; ++i) {
+    cv::KeyPoint kp(f->x[i], f->y[i], 31.f, f->angle[i], 0.f, f->octave[i]);
+    F->mvKeys[i] = kp; F->mvKeysUn[i] = kp;
+  }
+  F->mvuRight.assign(f->uright, f->uright + f->n);
+  F->mvDepth.assign(f->n, -1.f);
+  if (depth) F->mvDepth.assign(depth, depth + f->n);
+  F->mDescriptors.create(f->n, 32, CV_8U);
+  if (f->n) memcpy(F->mDescriptors.data, f->desc, (size_t)f->n * 32);
+  F->mvpMapPoints.assign(f->n, static_cast<MapPoint*>(NULL));
+  F->mvbOutlier.assign(f->n, false);
+  F->mnScaleLevels = f->nlevels;
+  F->mfScaleFactor = f->nlevels > 1 ? f->scale_factors[1] : 1.2f;
+  F->mfLogScaleFactor = log(F->mfScaleFactor);
+  F->mvScaleFactors.assign(f->scale_factors, f->scale_factors + f->nlevels);
+  F->mvInvScaleFactors.resize(f->nlevels); F->mvLevelSigma2.resize(f->nlevels); F->mvInvLevelSigma2.resize(f->nlevels);
+  for (int l = 0; l < f->nlevels; ++l) {
+    F->mvInvScaleFactors[l] = 1.0f / F->mvScaleFactors[l];
+    F->mvLevelSigma2[l] = F->mvScaleFactors[l] * F->mvScaleFactors[l];
+    F->mvInvLevelSigma2[l] = 1.0f / F->mvLevelSigma2[l];
+  }
+  Frame::fx = f->fx; Frame::fy = f->fy; Frame::cx = f->cx; Frame::cy = f->cy;
+  Frame::invfx = 1.0f / f->fx; Frame::invfy = 1.0f / f->fy;
+  Frame::mnMinX = f->min_x; Frame::mnMaxX = f->max_x; Frame::mnMinY = f->min_y; Frame::mnMaxY = f->max_y;
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+  Frame::mbInitialComputations = false;
+  F->mK = cv::Mat::eye(3, 3, CV_32F);
+  F->mK.at<float>(0, 0) = f->fx; F->mK.at<float>(1, 1) = f->fy; F->mK.at<float>(0, 2) = f->cx; F->mK.at<float>(1, 2) = f->cy;
+  F->mDistCoef = cv::Mat::zeros(4, 1, CV_32F);
+  F->AssignFeaturesToGrid();
+  F->SetPose(mat44(f->Tcw));
+  return F;
+}
+
+Frame* g_proto = nullptr;   // a one-keypoint frame MapPoints are constructed against
+MapPoint* make_point(const float* xw, const uint8_t* desc, int obs) {
+  if (!g_proto) {
+    static float one = 1.f, zerof = 0.f, sf[8] = {1, 1.2f, 1.44f, 1.728f, 2.0736f, 2.48832f, 2.985984f, 3.5831808f};
+    static int32_t zi = 0;
+    static uint8_t zd[32] = {0};
+    OrbmFrame p;
+    memset(&p, 0, sizeof(p));
+    p.n = 1; p.x = &one; p.y = &one; p.octave = &zi; p.angle = &zerof; p.uright = &zerof; p.desc = zd;
+    const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    memcpy(p.Tcw, I, sizeof(I));
+    p.fx = p.fy = 500; p.cx = 320; p.cy = 240; p.bf = 40; p.b = 0.08f; p.min_x = 0; p.max_x = 640; p.min_y = 0; p.max_y = 480;
+    p.scale_factors = sf; p.nlevels = 8;
+    g_proto = make_frame(&p);
+  }
+  cv::Mat pos(3, 1, CV_32F);
+  const float far[3] = {0.1f, 0.2f, 1.0f};
+  memcpy(pos.data, xw ? xw : far, 12);
+  MapPoint* mp = new MapPoint(pos, &g_map, g_proto, 0);
+  if (desc) desc_row(desc).copyTo(mp->mDescriptor);
+  mp->nObs = obs;
+  return mp;
+}
+
+void restore_statics(const OrbmFrame* f) {   // make_point's proto frame overwrote them on first use
+  Frame::fx = f->fx; Frame::fy = f->fy; Frame::cx = f->cx; Frame::cy = f->cy;
+  Frame::invfx = 1.0f / f->fx; Frame::invfy = 1.0f / f->fy;
+  Frame::mnMinX = f->min_x; Frame::mnMaxX = f->max_x; Frame::mnMinY = f->min_y; Frame::mnMaxY = f->max_y;
+  Frame::mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(Frame::mnMaxX - Frame::mnMinX);
+  Frame::mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(Frame::mnMaxY - Frame::mnMinY);
+}
+
+// pre-existing map points of the current frame (cur->mp_obs >= 0): reported as -2 while they survive
+void seed_existing(Frame* F, const OrbmFrame* f, std::map<MapPoint*, int>& id) {
+  if (!f->mp_obs) return;
+  for (int j = 0; j < f->n; ++j)
+    if (f->mp_obs[j] >= 0) { MapPoint* mp = make_point(nullptr, nullptr, f->mp_obs[j]); F->mvpMapPoints[j] = mp; id[mp] = -2; }
+}
+void flatten(const std::vector<MapPoint*>& v, const std::map<MapPoint*, int>& id, int32_t* out) {
+  for (size_t j = 0; j < v.size(); ++j) out[j] = v[j] ? id.at(v[j]) : -1;
+}
+void set_featvec(DBoW2::FeatureVector& fv, const OrbmBow* b) {
+  fv.clear();
+  for (int k = 0; k < b->n_nodes; ++k)
+    for (int j = b->node_off[k]; j < b->node_off[k + 1]; ++j) fv.addFeature(b->node_ids[k], b->idx[j]);
+}
+OrbmFrame bow_as_frame(const OrbmBow* b, std::vector<float>& zeros, std::vector<int32_t>& zi) {
+  static float sf[8] = {1, 1.2f, 1.44f, 1.728f, 2.0736f, 2.48832f, 2.985984f, 3.5831808f};
+  zeros.assign(b->n, 0.f); zi.assign(b->n, 0);
+  OrbmFrame p;
+  memset(&p, 0, sizeof(p));
+  p.n = b->n; p.x = zeros.data(); p.y = zeros.data(); p.octave = zi.data(); p.angle = b->angle; p.uright = zeros.data();
+  p.desc = b->desc;
+  const float I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  memcpy(p.Tcw, I, sizeof(I));
+  p.fx = p.fy = 500; p.cx = 320; p.cy = 240; p.bf = 40; p.b = 0.08f; p.min_x = 0; p.max_x = 640; p.min_y = 0; p.max_y = 480;
+  p.scale_factors = sf; p.nlevels = 8;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ORBextractor (src/ORBextractor.cc, whole file)
+void* refsrc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+  return new ORBextractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+}
+void refsrc_orb_destroy(void* h) { delete (ORBextractor*)h; }
+int refsrc_orb_extract(void* h, const uint8_t* img, int rows, int cols, int stride, void* kps, uint8_t* desc, int cap,
+                       int* n_out) {
+  ORBextractor* e = (ORBextractor*)h;
+  std::lock_guard<std::mutex> lk(g_mu);
+  arena_reset();
+  cv::Mat image(rows, cols, CV_8UC1, (void*)img, (size_t)stride);
+  std::vector<cv::KeyPoint> keys;
+  cv::Mat descriptors;
+  (*e)(image, cv::Mat(), keys, descriptors);
+  *n_out = (int)keys.size();
+  if ((int)keys.size() > cap) return -2;
+  static_assert(sizeof(cv::KeyPoint) == 28, "cv::KeyPoint layout");
+  if (!keys.empty()) {
+    memcpy(kps, keys.data(), keys.size() * sizeof(cv::KeyPoint));
+    for (size_t i = 0; i < keys.size(); ++i) memcpy(desc + 32 * i, descriptors.ptr((int)i), 32);
+  }
+  return 0;
+}
+void refsrc_orb_tables(void* h, float* sf, float* invsf, float* sigma2, float* invsigma2, int* nfeat, int* umax) {
+  ORBextractor* e = (ORBextractor*)h;
+  for (int l = 0; l < e->nlevels; ++l) {
+    sf[l] = e->mvScaleFactor[l]; invsf[l] = e->mvInvScaleFactor[l]; sigma2[l] = e->mvLevelSigma2[l];
+    invsigma2[l] = e->mvInvLevelSigma2[l]; nfeat[l] = e->mnFeaturesPerLevel[l];
+  }
+  for (int v = 0; v < 16; ++v) umax[v] = e->umax[v];
+}
+int refsrc_orb_level_dims(void* h, int level, int* w, int* hgt) {
+  ORBextractor* e = (ORBextractor*)h;
+  if (level < 0 || level >= e->nlevels || e->mvImagePyramid[level].empty()) return -1;
+  *w = e->mvImagePyramid[level].cols; *hgt = e->mvImagePyramid[level].rows;
+  return 0;
+}
+// mvImagePyramid[level]; bordered=1 returns the (w+38)x(h+38) parent buffer the ROI lives in (src/ORBextractor.cc:1125-1129)
+void refsrc_orb_get_level(void* h, int level, int bordered, uint8_t* dst) {
+  ORBextractor* e = (ORBextractor*)h;
+  const cv::Mat& m = e->mvImagePyramid[level];
+  const int B = bordered ? 19 : 0;
+  const int W = m.cols + 2 * B, H = m.rows + 2 * B;
+  const uint8_t* base = m.data - (size_t)B * m.step - B;
+  for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * W, base + (size_t)y * m.step, (size_t)W);
+}
+// ORBextractor::DistributeOctTree (src/ORBextractor.cc:540-765) on a caller-supplied candidate list
+int refsrc_orb_distribute(const void* in, int n_in, int minX, int maxX, int minY, int maxY, int N, void* out, int cap) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  arena_reset();
+  ORBextractor e(std::max(N, 1), 1.2f, 8, 20, 7);
+  std::vector<cv::KeyPoint> v((const cv::KeyPoint*)in, (const cv::KeyPoint*)in + n_in);
+  std::vector<cv::KeyPoint> r = e.DistributeOctTree(v, minX, maxX, minY, maxY, N, 0);
+  if ((int)r.size() > cap) return -2;
+  if (!r.empty()) memcpy(out, r.data(), r.size() * sizeof(cv::KeyPoint));
+  return (int)r.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ORBmatcher (src/ORBmatcher.cc) -- same signatures as match_ref_* in oracle/match_ref.cpp
+int refsrc_hamming(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }
+
+// SearchByProjection(Frame&, const Frame&, th, bMono), src/ORBmatcher.cc:1578-1724
+int refsrc_projection_last(const OrbmFrame* cur, const OrbmLast* last, float th, int mono, float nnratio, int check_ori,
+                           int32_t* cur2last, int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::map<MapPoint*, int> id;
+  make_point(nullptr, nullptr, 0);   // force the proto frame before the statics are set for `cur`
+  // the last frame: only N, mvpMapPoints, mvbOutlier, mvKeys[i].octave, mvKeysUn[i].angle and mTcw are read
+  std::vector<float> zf(last->n, 0.f);
+  std::vector<uint8_t> zd((size_t)std::max(last->n, 1) * 32, 0);
+  OrbmFrame lv = *cur;
+  lv.n = last->n; lv.x = zf.data(); lv.y = zf.data(); lv.octave = last->octave; lv.angle = last->angle; lv.uright = zf.data();
+  lv.desc = zd.data(); lv.mp_obs = nullptr;
+  memcpy(lv.Tcw, last->Tcw, sizeof(lv.Tcw));
+  Frame* L = make_frame(&lv);
+  for (int i = 0; i < last->n; ++i)
+    if (last->valid[i]) {
+      MapPoint* mp = make_point(last->xw + 3 * i, last->mp_desc + 32 * (size_t)i, last->mp_obs ? last->mp_obs[i] : 0);
+      L->mvpMapPoints[i] = mp; id[mp] = i;
+    }
+  Frame* C = make_frame(cur);
+  seed_existing(C, cur, id);
+  restore_statics(cur);
+  ORBmatcher m(nnratio, check_ori != 0);
+  *nmatches_out = m.SearchByProjection(*C, *L, th, mono != 0);
+  flatten(C->mvpMapPoints, id, cur2last);
+  for (auto& kv : id) delete kv.first;
+  delete C; delete L;
+  return 0;
+}
+
+// SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:63-156
+int refsrc_projection_points(const OrbmFrame* F, const OrbmTrackPoints* pts, float th, float nnratio, int32_t* f2pt,
+                             int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::map<MapPoint*, int> id;
+  make_point(nullptr, nullptr, 0);
+  std::vector<MapPoint*> v(pts->n);
+  for (int i = 0; i < pts->n; ++i) {
+    MapPoint* mp = make_point(nullptr, pts->mp_desc + 32 * (size_t)i, pts->mp_obs ? pts->mp_obs[i] : 1);
+    mp->mbTrackInView = pts->track_in_view[i] != 0;
+    mp->mTrackProjX = pts->proj_x[i]; mp->mTrackProjY = pts->proj_y[i]; mp->mTrackProjXR = pts->proj_xr[i];
+    mp->mnTrackScaleLevel = pts->scale_level[i]; mp->mTrackViewCos = pts->view_cos[i];
+    v[i] = mp; id[mp] = i;
+  }
+  Frame* C = make_frame(F);
+  seed_existing(C, F, id);
+  restore_statics(F);
+  ORBmatcher m(nnratio, true);
+  *nmatches_out = m.SearchByProjection(*C, v, th);
+  flatten(C->mvpMapPoints, id, f2pt);
+  for (auto& kv : id) delete kv.first;
+  delete C;
+  return 0;
+}
+
+// SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:217-363
+int refsrc_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf, int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::map<MapPoint*, int> id;
+  make_point(nullptr, nullptr, 0);
+  std::vector<float> z1, z2; std::vector<int32_t> i1, i2;
+  OrbmFrame v1 = bow_as_frame(kf, z1, i1), v2 = bow_as_frame(f, z2, i2);
+  Frame* FK = make_frame(&v1);
+  for (int i = 0; i < kf->n; ++i)
+    if (kf->valid[i]) { MapPoint* mp = make_point(nullptr, nullptr, 1); FK->mvpMapPoints[i] = mp; id[mp] = i; }
+  set_featvec(FK->mFeatVec, kf);
+  KeyFrame* K = new KeyFrame(*FK, &g_map, nullptr);
+  Frame* F = make_frame(&v2);
+  set_featvec(F->mFeatVec, f);
+  std::vector<MapPoint*> out;
+  ORBmatcher m(nnratio, check_ori != 0);
+  *nmatches_out = m.SearchByBoW(K, *F, out);
+  flatten(out, id, f2kf);
+  for (auto& kv : id) delete kv.first;
+  delete K; delete F; delete FK;
+  return 0;
+}
+
+// SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), src/ORBmatcher.cc:665-812
+int refsrc_bow_kf(const OrbmBow* k1, const OrbmBow* k2, float nnratio, int check_ori, int32_t* matches12, int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  std::map<MapPoint*, int> id;
+  make_point(nullptr, nullptr, 0);
+  std::vector<float> z1, z2; std::vector<int32_t> i1, i2;
+  OrbmFrame v1 = bow_as_frame(k1, z1, i1), v2 = bow_as_frame(k2, z2, i2);
+  Frame* F1 = make_frame(&v1);
+  Frame* F2 = make_frame(&v2);
+  std::vector<MapPoint*> own;
+  for (int i = 0; i < k1->n; ++i)
+    if (k1->valid[i]) { MapPoint* mp = make_point(nullptr, nullptr, 1); F1->mvpMapPoints[i] = mp; own.push_back(mp); }
+  for (int i = 0; i < k2->n; ++i)
+    if (k2->valid[i]) { MapPoint* mp = make_point(nullptr, nullptr, 1); F2->mvpMapPoints[i] = mp; id[mp] = i; }
+  set_featvec(F1->mFeatVec, k1);
+  set_featvec(F2->mFeatVec, k2);
+  KeyFrame* K1 = new KeyFrame(*F1, &g_map, nullptr);
+  KeyFrame* K2 = new KeyFrame(*F2, &g_map, nullptr);
+  std::vector<MapPoint*> out;
+  ORBmatcher m(nnratio, check_ori != 0);
+  *nmatches_out = m.SearchByBoW(K1, K2, out);
+  flatten(out, id, matches12);
+  for (auto& kv : id) delete kv.first;
+  for (auto p : own) delete p;
+  delete K1; delete K2; delete F1; delete F2;
+  return 0;
+}
+
+// SearchForInitialization(Frame&, Frame&, vector<Point2f>&, vector<int>&, windowSize), src/ORBmatcher.cc:523-651
+int refsrc_initialization(const OrbmFrame* f1, const OrbmFrame* f2, float* prev_xy, int window, float nnratio, int check_ori,
+                          int32_t* matches12, int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Frame* F1 = make_frame(f1);
+  Frame* F2 = make_frame(f2);
+  std::vector<cv::Point2f> prev(f1->n);
+  for (int i = 0; i < f1->n; ++i) prev[i] = cv::Point2f(prev_xy[2 * i], prev_xy[2 * i + 1]);
+  std::vector<int> m12;
+  ORBmatcher m(nnratio, check_ori != 0);
+  *nmatches_out = m.SearchForInitialization(*F1, *F2, prev, m12, window);
+  for (int i = 0; i < f1->n; ++i) { matches12[i] = m12[i]; prev_xy[2 * i] = prev[i].x; prev_xy[2 * i + 1] = prev[i].y; }
+  delete F1; delete F2;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame glue through the REAL RGB-D constructor (src/Frame.cc:176-240): ExtractORB, UndistortKeyPoints,
+// ComputeStereoFromRGBD (:850-871), AssignFeaturesToGrid, then UnprojectStereo (:879-899) per keypoint.
+// depth f32 metres.  Outputs per keypoint: cv::KeyPoint (mvKeysUn), descriptor, uRight, depth, world point, valid.
+int refsrc_frame_rgbd(const uint8_t* gray, const float* depth, int rows, int cols, int nfeatures, float scaleFactor,
+                      int nlevels, int iniTh, int minTh, const float* Tcw, float fx, float fy, float cx, float cy,
+                      float bf, const float* dist4, void* kps_un, uint8_t* desc, float* uright, float* kdepth, float* xw,
+                      uint8_t* valid, int cap, int* n_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  arena_reset();
+  ORBextractor ex(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+  cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+  K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy;
+  cv::Mat D(4, 1, CV_32F);
+  for (int i = 0; i < 4; ++i) D.at<float>(i) = dist4 ? dist4[i] : 0.f;
+  cv::Mat g(rows, cols, CV_8UC1, (void*)gray), d(rows, cols, CV_32F, (void*)depth);
+  Frame::mbInitialComputations = true;
+  const float thDepth = bf * 40.0f / fx;
+  Frame F(g, d, 0.0, &ex, nullptr, K, D, bf, thDepth);
+  F.SetPose(mat44(Tcw));
+  *n_out = F.N;
+  if (F.N > cap) return -2;
+  for (int i = 0; i < F.N; ++i) {
+    memcpy((char*)kps_un + 28 * (size_t)i, &F.mvKeysUn[i], 28);
+    memcpy(desc + 32 * (size_t)i, F.mDescriptors.ptr(i), 32);
+    uright[i] = F.mvuRight[i]; kdepth[i] = F.mvDepth[i];
+    cv::Mat x = F.UnprojectStereo(i);
+    valid[i] = !x.empty();
+    for (int k = 0; k < 3; ++k) xw[3 * i + k] = x.empty() ? 0.f : x.at<float>(k);
+  }
+  return 0;
+}
+
+// Frame::isInFrustum (src/Frame.cc:387-451) for a list of world points with given normal / distance bounds.
+// out per point: in_view, proj_x, proj_y, proj_xr, scale_level, view_cos
+int refsrc_is_in_frustum(const OrbmFrame* f, int n, const float* xw, const float* normal, const float* min_dist,
+                         const float* max_dist, float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y,
+                         float* proj_xr, int32_t* scale_level, float* view_cos) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  Frame* F = make_frame(f);
+  restore_statics(f);
+  for (int i = 0; i < n; ++i) {
+    MapPoint* mp = make_point(xw + 3 * i, nullptr, 1);
+    memcpy(mp->mNormalVector.data, normal + 3 * i, 12);
+    mp->mfMinDistance = min_dist[i]; mp->mfMaxDistance = max_dist[i];   // raw mfMinDistance / mfMaxDistance
+    mp->mTrackProjX = mp->mTrackProjY = mp->mTrackProjXR = 0; mp->mnTrackScaleLevel = 0; mp->mTrackViewCos = 0;
+    in_view[i] = F->isInFrustum(mp, viewing_cos_limit);
+    proj_x[i] = mp->mTrackProjX; proj_y[i] = mp->mTrackProjY; proj_xr[i] = mp->mTrackProjXR;
+    scale_level[i] = mp->mnTrackScaleLevel; view_cos[i] = mp->mTrackViewCos;
+    delete mp;
+  }
+  delete F;
+  return 0;
+}
+
+}  // extern "C"
