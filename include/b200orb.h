@@ -337,6 +337,34 @@ int ocm_export_summaries_device(ocm_t* h, uint64_t* d_keys, float* d_a, float* d
 /* Compose the summaries of a LATER shard onto this map (apply in keyframe order: shard 0, 1, ...). */
 int ocm_apply_summaries_device(ocm_t* h, const uint64_t* d_keys, const float* d_a, const float* d_lo,
                                const float* d_hi, int64_t n);
+/* The same with a per-pixel ground label batch d_label[F][rows][cols] (NULL = all non-ground); keyframe i reads label
+ * image label_idx[i] (NULL = depth_idx).  Labels stand in for the reference's RANSAC floor split
+ * (perfect/src/MapDrawer.cc:686-774): ground points only clear space along their rays (:961-969). */
+int ocm_insert_keyframes_labeled_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, const uint8_t* d_label,
+                                        int rows, int cols, const int32_t* depth_idx, const int32_t* rgb_idx,
+                                        const int32_t* label_idx, int n, const float* Tcw, float fx, float fy, float cx,
+                                        float cy);
+int ocm_insert_keyframes_u16_labeled(ocm_t* h, const uint16_t* depth_u16, const uint8_t* rgb, const uint8_t* label, int rows,
+                                     int cols, int n, float depth_factor, const float* Tcw, float fx, float fy, float cx,
+                                     float cy);
+/* ocm_merge_nccl (SURVEY §8(b),(e)): the one exchange step of the frame-sharded mode.  Every rank has inserted its own
+ * keyframes (a contiguous range, rank order = keyframe order) since the last merge; the call all-gathers the per-voxel
+ * clamp-add summaries of that epoch (24-byte records: key u64, a, lo, hi f32, colour u32) over NCCL / NVLink and replays
+ * the shards of ALL ranks in rank order on the values of the last merge, so every rank ends with the map a single process
+ * inserting all keyframes in order would hold (log-odds equal up to float re-association, << 1e-5).  One host
+ * synchronisation (the counts); everything else is enqueued on the map's stream.  comm = ncclComm_t (NULL: single rank,
+ * the call just closes the epoch); stream = a cudaStream_t the merge is ordered after / before (NULL: the map's own). */
+typedef struct {
+  int world, rank;
+  int64_t records_sent, records_total;     /* voxels this rank sent / all ranks together */
+  int64_t bytes_sent, bytes_received;      /* 24 B per record */
+} OcmMergeStats;
+int ocm_merge_nccl(ocm_t* h, void* nccl_comm, void* stream, OcmMergeStats* stats);
+/* Helpers to obtain an ncclComm_t without linking NCCL: rank 0 calls ocm_nccl_unique_id and hands the 128 bytes to the
+ * other ranks through whatever plumbing the host has (torch.distributed.broadcast in the Python mirror). */
+int ocm_nccl_unique_id(uint8_t id[128]);
+int ocm_nccl_comm_create(const uint8_t id[128], int rank, int world, int device, void** nccl_comm);
+int ocm_nccl_comm_destroy(void* nccl_comm);
 int ocm_sync(ocm_t* h);
 void* ocm_stream(ocm_t* h);
 long long ocm_launch_count(const ocm_t* h);

@@ -65,6 +65,8 @@ class PyOccupancy:
             labs.append(lab)
         self.points = np.array(pts, np.float32).reshape(-1, 3)
         self.labels = np.array(labs, np.uint8)
+        if len(self.labels) < 50:      # perfect/src/MapDrawer.cc:676-680: a cloud of < 50 points is all ground
+            self.labels[:] = 1
         return self.points
 
     # ---- octomap -------------------------------------------------------------------------------------------------
@@ -86,10 +88,9 @@ class PyOccupancy:
         out = [ko]
         o = [F32(v) for v in origin]
         direction = [F32(F32(end[i]) - o[i]) for i in range(3)]
-        n2 = 0.0
-        for i in range(3):
-            n2 += float(F32(direction[i] * direction[i]))
-        length = F32(math.sqrt(n2))
+        # octomath Vector3::norm_sq() (octomap 1.9.x): x*x + y*y + z*z in float, widened for the sqrt only
+        n2 = F32(F32(F32(direction[0] * direction[0]) + F32(direction[1] * direction[1])) + F32(direction[2] * direction[2]))
+        length = F32(math.sqrt(float(n2)))
         direction = [F32(direction[i] / length) for i in range(3)]
         step, tmax, tdelta, cur = [0] * 3, [0.0] * 3, [0.0] * 3, list(ko)
         for i in range(3):

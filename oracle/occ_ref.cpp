@@ -13,6 +13,8 @@
 // pixel row-major order; the RANSAC ground split is replaced by a supplied per-pixel label (voxel label = label of
 // its first pixel).
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -64,9 +66,10 @@ struct OccMap {
     if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return true;
     ray.push_back(pack(ko));
     float dir[3] = {e[0] - o[0], e[1] - o[1], e[2] - o[2]};
-    double n2 = 0;
-    for (int i = 0; i < 3; ++i) n2 += dir[i] * dir[i];   // float product added into a double
-    const float length = (float)std::sqrt(n2);
+    // octomath::Vector3::norm() of octomap 1.9.x: sqrt(norm_sq()) with norm_sq() = x*x + y*y + z*z evaluated in FLOAT
+    // (the components are floats), widened to double only for the sqrt; 1.6-1.8 summed the float products in a double
+    const float n2 = dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2];
+    const float length = (float)std::sqrt((double)n2);
     for (int i = 0; i < 3; ++i) dir[i] /= length;
     int step[3];
     double tMax[3], tDelta[3];
@@ -166,6 +169,9 @@ struct OccMap {
     }
     pts_rgb = raw_rgb;
     pts_label = raw_label;
+    // perfect/src/MapDrawer.cc:676-680: "if(temp.size()<50) ground = temp" -- a cloud of fewer than 50 points skips the
+    // plane extraction and is ALL ground (free rays only, no occupied endpoints), whatever a label would say
+    if (np < 50) std::fill(pts_label.begin(), pts_label.end(), (uint8_t)1);
   }
 
   // MapDrawer::InsertScan :946-1025 (+ UpdateOctomap's sensorOrigin quirk :619,631-632: translation of Tcw)
@@ -212,6 +218,34 @@ int occ_ref_insert_keyframe(void* h, const float* depth, const uint8_t* rgb, int
   m->generate(depth, rgb, rows, cols, Tcw, fx, fy, cx, cy, label);
   m->insert_scan(Tcw);
   return (int)(m->pts.size() / 3);
+}
+// Baseline driver for a batch of keyframes: GeneratePointCloud (back-projection + VoxelGrid + transform) of the keyframes
+// runs on `nthreads` host threads -- keyframes are independent up to that point, and the reference parallelises its own
+// back-projection loop with OpenMP (src/pointcloudmapping.cc:169) -- while InsertScan into the one shared tree stays
+// sequential in keyframe order, as it has to.  label may be NULL; label_stride = pixels between label images.
+int occ_ref_insert_keyframes_mt(void* h, const float* depth, const uint8_t* rgb, const uint8_t* label, int rows, int cols,
+                                const int* idx, int n, const float* Tcw, float fx, float fy, float cx, float cy, int nthreads) {
+  OccMap* m = (OccMap*)h;
+  const size_t px = (size_t)rows * cols;
+  std::vector<OccMap*> parts(n, nullptr);
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < std::max(1, std::min(nthreads, n)); ++t)
+    th.emplace_back([&]() {
+      for (int i = next++; i < n; i = next++) {
+        OccMap* q = new OccMap(m->p);
+        q->generate(depth + px * idx[i], rgb + px * 3 * idx[i], rows, cols, Tcw + 16 * i, fx, fy, cx, cy,
+                    label ? label + px * idx[i] : nullptr);
+        parts[i] = q;
+      }
+    });
+  for (auto& t : th) t.join();
+  for (int i = 0; i < n; ++i) {
+    m->pts.swap(parts[i]->pts); m->pts_rgb.swap(parts[i]->pts_rgb); m->pts_label.swap(parts[i]->pts_label);
+    m->insert_scan(Tcw + 16 * i);
+    delete parts[i];
+  }
+  return n;
 }
 int occ_ref_last_points(void* h, float* xyz, uint8_t* rgb, uint8_t* label, int cap) {
   OccMap* m = (OccMap*)h;

@@ -307,6 +307,20 @@ class RefOccupancy:
         return self.L.occ_ref_insert_keyframe(self.h, _p(depth), _p(rgb), depth.shape[0], depth.shape[1], _p(T), fx, fy,
                                               cx, cy, None if lab is None else _p(lab))
 
+    def insert_keyframes_mt(self, depth, rgb, label, idx, Tcw, fx, fy, cx, cy, nthreads):
+        """Batch form for the CPU baseline: GeneratePointCloud of the keyframes on `nthreads` threads, InsertScan in
+        order.  depth [F,rows,cols] f32, rgb [F,rows,cols,3], label [F,rows,cols] u8 or None, idx = frames to insert,
+        Tcw [len(idx),4,4]."""
+        depth = np.ascontiguousarray(depth, np.float32)
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        lab = None if label is None else np.ascontiguousarray(label, np.uint8)
+        idx = np.ascontiguousarray(idx, np.int32)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(len(idx), 16)
+        self.L.occ_ref_insert_keyframes_mt.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p] + \
+            [C.c_float] * 4 + [C.c_int]
+        self.L.occ_ref_insert_keyframes_mt(self.h, _p(depth), _p(rgb), None if lab is None else _p(lab), depth.shape[1],
+                                           depth.shape[2], _p(idx), len(idx), _p(T), fx, fy, cx, cy, int(nthreads))
+
     def last_points(self):
         cap = 1 << 20
         xyz = np.zeros((cap, 3), np.float32)
@@ -532,3 +546,22 @@ def src_frame_rgbd(gray, depth, Tcw, fx, fy, cx, cy, bf, nfeatures=1000, scale=1
     assert rc == 0
     m = n.value
     return kps[:m].copy(), desc[:m].copy(), ur[:m].copy(), dp[:m].copy(), xw[:m].copy(), va[:m].copy()
+
+
+def src_pipeline_run(gray, depth, Tcw, nthreads, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20, min_th=7, fx=535.4,
+                     fy=539.2, cx=320.1, cy=247.6, bf=40.0, th=15.0, nnratio=0.9, check_ori=True):
+    """CPU baseline through the reference's OWN tracking sources (oracle/_ref/librefsrc.so): RGB-D Frame constructor +
+    SearchByProjection(cur, last) per frame, frame-parallel -> (seconds, nkp, nmatch)."""
+    L = reflib()
+    L.refsrc_pipeline_run.restype = C.c_double
+    L.refsrc_pipeline_run.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + \
+        [C.c_float] * 7 + [C.c_int] * 2 + [C.c_void_p] * 2
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.float32)
+    T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16)
+    n, rows, cols = gray.shape
+    nkp = np.zeros(n, np.int32)
+    nm = np.zeros(n, np.int32)
+    sec = L.refsrc_pipeline_run(_p(gray), _p(depth), _p(T), n, rows, cols, nfeatures, scale, nlevels, ini_th, min_th, fx,
+                                fy, cx, cy, bf, th, nnratio, int(check_ori), nthreads, _p(nkp), _p(nm))
+    return sec, nkp, nm

@@ -11,6 +11,8 @@
 // filled from arrays instead of from an image (the class layout is unchanged; the reference's .cc files are compiled
 // without it).  OpenCV / DBoW2 are stand-ins (oracle/standin/), third-party arithmetic stated there.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -54,20 +56,26 @@ using namespace ORB_SLAM2;
 // Bound inside this library only (-Wl,-Bsymbolic); everything else goes to malloc/free.
 namespace {
 const size_t kNodeBytes = sizeof(std::_List_node<ExtractorNode>);
-const size_t kArenaBytes = 64u << 20;
-char* g_arena = nullptr;
-size_t g_arena_used = 0;
-bool g_arena_on = false;
+const size_t kArenaBytes = 16u << 20;          // one per thread that extracts (a frame needs ~2 MB of list nodes)
+const int kMaxArenas = 512;
+char* g_arenas[kMaxArenas];
+std::atomic<int> g_narenas(0);
+thread_local char* t_arena = nullptr;
+thread_local size_t t_arena_used = 0;
+thread_local bool t_arena_on = false;
 inline void arena_reset() {
-  if (!g_arena) g_arena = (char*)malloc(kArenaBytes);
-  g_arena_used = 0;
-  g_arena_on = true;
+  if (!t_arena) {
+    const int id = g_narenas.fetch_add(1);
+    if (id < kMaxArenas) { t_arena = (char*)malloc(kArenaBytes); g_arenas[id] = t_arena; }
+  }
+  t_arena_used = 0;
+  t_arena_on = t_arena != nullptr;
 }
 }  // namespace
 void* operator new(size_t n) {
-  if (g_arena_on && n == kNodeBytes && g_arena_used + ((n + 15) & ~size_t(15)) <= kArenaBytes) {
-    void* p = g_arena + g_arena_used;
-    g_arena_used += (n + 15) & ~size_t(15);
+  if (t_arena_on && n == kNodeBytes && t_arena_used + ((n + 15) & ~size_t(15)) <= kArenaBytes) {
+    void* p = t_arena + t_arena_used;
+    t_arena_used += (n + 15) & ~size_t(15);
     return p;
   }
   void* p = malloc(n ? n : 1);
@@ -75,7 +83,11 @@ void* operator new(size_t n) {
   return p;
 }
 void operator delete(void* p) noexcept {
-  if (g_arena && (char*)p >= g_arena && (char*)p < g_arena + kArenaBytes) return;
+  const int na = std::min(g_narenas.load(std::memory_order_relaxed), kMaxArenas);
+  for (int i = 0; i < na; ++i) {
+    const char* b = g_arenas[i];
+    if (b && (char*)p >= b && (char*)p < b + kArenaBytes) return;
+  }
   free(p);
 }
 void operator delete(void* p, size_t) noexcept { operator delete(p); }
@@ -421,6 +433,80 @@ int refsrc_frame_rgbd(const uint8_t* gray, const float* depth, int rows, int col
     for (int k = 0; k < 3; ++k) xw[3 * i + k] = x.empty() ? 0.f : x.at<float>(k);
   }
   return 0;
+}
+
+// CPU baseline through the reference's own tracking sources: per frame the RGB-D Frame constructor (ORBextractor,
+// ComputeStereoFromRGBD, AssignFeaturesToGrid), then per consecutive pair the map points Tracking would hold for the last
+// frame (a MapPoint per keypoint with depth, src/Tracking.cc:1285-1322 UpdateLastFrame style) and
+// ORBmatcher::SearchByProjection(cur, last, th, false).  Frame-parallel on `nthreads` threads (one ORBextractor per thread,
+// like src/Frame.cc:121-124); Frame's statics are written once before the threads start.  depth f32 metres.
+// Returns seconds (steady_clock, like perfect/Examples/RGB-D/rgbd_tum.cc:92-111).
+double refsrc_pipeline_run(const uint8_t* gray, const float* depth, const float* Tcw, int n, int rows, int cols, int nfeatures,
+                           float scaleFactor, int nlevels, int iniTh, int minTh, float fx, float fy, float cx, float cy,
+                           float bf, float th, float nnratio, int check_ori, int nthreads, int* nkp, int* nmatch) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  cv::Mat K = cv::Mat::eye(3, 3, CV_32F);
+  K.at<float>(0, 0) = fx; K.at<float>(1, 1) = fy; K.at<float>(0, 2) = cx; K.at<float>(1, 2) = cy;
+  cv::Mat D = cv::Mat::zeros(4, 1, CV_32F);
+  const float thDepth = bf * 40.0f / fx;
+  const size_t px = (size_t)rows * cols;
+  {   // first frame constructed once up front: it performs Frame's one-off static initialisation (src/Frame.cc:214-231)
+    ORBextractor ex(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+    Frame::mbInitialComputations = true;
+    arena_reset();
+    cv::Mat g(rows, cols, CV_8UC1, (void*)gray), d(rows, cols, CV_32F, (void*)depth);
+    Frame F(g, d, 0.0, &ex, nullptr, K, D, bf, thDepth);
+  }
+  std::vector<Frame*> frames(n, nullptr);
+  auto t0 = std::chrono::steady_clock::now();
+  {
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&]() {
+        ORBextractor ex(nfeatures, scaleFactor, nlevels, iniTh, minTh);
+        cv::Mat Kt = K.clone(), Dt = D.clone();
+        for (int i = next++; i < n; i = next++) {
+          arena_reset();
+          cv::Mat g(rows, cols, CV_8UC1, (void*)(gray + px * i)), d(rows, cols, CV_32F, (void*)(depth + px * i));
+          Frame* F = new Frame(g, d, (double)i, &ex, nullptr, Kt, Dt, bf, thDepth);
+          F->mpORBextractorLeft = nullptr;
+          F->SetPose(mat44(Tcw + 16 * i));
+          frames[i] = F;
+          nkp[i] = F->N;
+        }
+      });
+    for (auto& t : pool) t.join();
+  }
+  nmatch[0] = 0;
+  {
+    std::atomic<int> next(1);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+      pool.emplace_back([&]() {
+        for (int i = next++; i < n; i = next++) {
+          Frame last(*frames[i - 1]);
+          Frame cur(*frames[i]);
+          std::vector<MapPoint*> mine;
+          for (int k = 0; k < last.N; ++k) {
+            if (last.mvDepth[k] <= 0) continue;
+            cv::Mat x3D = last.UnprojectStereo(k);
+            MapPoint* mp = new MapPoint(x3D, &g_map, &last, k);
+            mp->nObs = 1;
+            last.mvpMapPoints[k] = mp;
+            mine.push_back(mp);
+          }
+          ORBmatcher m(nnratio, check_ori != 0);
+          nmatch[i] = m.SearchByProjection(cur, last, th, false);
+          for (MapPoint* p : mine) delete p;
+        }
+      });
+    for (auto& t : pool) t.join();
+  }
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (Frame* F : frames) delete F;
+  return sec;
 }
 
 // Frame::isInFrustum (src/Frame.cc:387-451) for a list of world points with given normal / distance bounds.

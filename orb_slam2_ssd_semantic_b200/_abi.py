@@ -188,3 +188,8 @@ class QueriesView:
         s.min_level, s.max_level, s.uright = ptr(self.min_level), ptr(self.max_level), ptr(self.uright)
         s.desc, s.angle, s.obs = ptr(self.desc), ptr(self.angle), ptr(self.obs)
         return s
+
+
+class OcmMergeStats(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("records_sent", C.c_int64), ("records_total", C.c_int64),
+                ("bytes_sent", C.c_int64), ("bytes_received", C.c_int64)]

@@ -35,6 +35,8 @@ EXPORTS = [
     "ocm_default_params", "ocm_create", "ocm_destroy", "ocm_insert_keyframe", "ocm_insert_keyframe_device", "ocm_insert_keyframes_device", "ocm_insert_keyframes_u16",
     "ocm_last_points", "ocm_num_leaves", "ocm_export_leaves", "ocm_query", "ocm_summary_count",
     "ocm_export_summaries_device", "ocm_apply_summaries_device", "ocm_sync", "ocm_stream", "ocm_launch_count",
+    "ocm_insert_keyframes_labeled_device", "ocm_insert_keyframes_u16_labeled", "ocm_merge_nccl", "ocm_nccl_unique_id",
+    "ocm_nccl_comm_create", "ocm_nccl_comm_destroy",
 ]
 
 
@@ -127,6 +129,12 @@ def lib() -> C.CDLL:
     L.gcm_launch_count.restype = C.c_longlong
     L.ocm_insert_keyframes_device.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp, f, f, f, f]
     L.ocm_insert_keyframes_u16.argtypes = [vp, vp, vp, i, i, i, f, vp, f, f, f, f]
+    L.ocm_insert_keyframes_labeled_device.argtypes = [vp, vp, vp, vp, i, i, vp, vp, vp, i, vp, f, f, f, f]
+    L.ocm_insert_keyframes_u16_labeled.argtypes = [vp, vp, vp, vp, i, i, i, f, vp, f, f, f, f]
+    L.ocm_merge_nccl.argtypes = [vp, vp, vp, vp]
+    L.ocm_nccl_unique_id.argtypes = [vp]
+    L.ocm_nccl_comm_create.argtypes = [vp, i, i, i, C.POINTER(vp)]
+    L.ocm_nccl_comm_destroy.argtypes = [vp]
     L.ocm_last_points.argtypes = [vp, vp, vp, i, C.POINTER(i)]
     L.ocm_num_leaves.argtypes = [vp]
     L.ocm_num_leaves.restype = C.c_int64

@@ -18,6 +18,9 @@
 #include <new>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -115,6 +118,11 @@ struct MapView {
   unsigned* bm_rgb;
   int* touched;
   int* ntouched;
+  // merge epochs (ocm_merge_nccl): value of the voxel at the last merge, and the list of voxels whose summary left the
+  // identity since then (what this rank has to send)
+  float* base;
+  int* elist;
+  int* nelist;
 };
 
 // Record "keyframe j of the batch observed voxel `key` as occupied / free".  Order-free (atomicOr), so every keyframe
@@ -345,10 +353,12 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* 
   const uint8_t* __restrict__ pts_rgb = J.s.pts_rgb;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= counters[1]) return;
+  // perfect/src/MapDrawer.cc:676-680: a cloud of fewer than 50 points skips the plane extraction and is ALL ground
+  const bool all_ground = counters[1] < 50;
   const float e[3] = {pts[(size_t)v * 3], pts[(size_t)v * 3 + 1], pts[(size_t)v * 3 + 2]};
   int ke[3];
   const bool end_ok = coord_to_key(c, e[0], ke[0]) && coord_to_key(c, e[1], ke[1]) && coord_to_key(c, e[2], ke[2]);
-  if (!pts_label[v]) {
+  if (!pts_label[v] && !all_ground) {
     if (end_ok) {
       const unsigned rgb = (unsigned)pts_rgb[(size_t)v * 3] | ((unsigned)pts_rgb[(size_t)v * 3 + 1] << 8) |
                            ((unsigned)pts_rgb[(size_t)v * 3 + 2] << 16);
@@ -363,10 +373,9 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* 
   if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return;
   if (!map_touch(m, pack_key(ko[0], ko[1], ko[2]), j, false, 0u)) atomicExch(err, 4);
   float dir[3] = {e[0] - c.origin[0], e[1] - c.origin[1], e[2] - c.origin[2]};
-  double n2 = 0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) n2 += (double)(dir[i] * dir[i]);
-  const float length = (float)sqrt(n2);
+  // octomath::Vector3::norm() of octomap 1.9.x: norm_sq() = x*x + y*y + z*z in float, widened for the sqrt only
+  const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])), __fmul_rn(dir[2], dir[2]));
+  const float length = (float)sqrt((double)n2);
 #pragma unroll
   for (int i = 0; i < 3; ++i) dir[i] = dir[i] / length;
   int step[3], cur[3] = {ko[0], ko[1], ko[2]};
@@ -410,6 +419,7 @@ __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cma
     m.bm[s] = 0ull;
     const unsigned hit = (unsigned)(w >> 32), miss = (unsigned)w & ~hit;
     float v = m.val[s], a = m.a[s], lo = m.lo[s], hi = m.hi[s];
+    if (a == 0.f && lo == -INFINITY) m.elist[atomicAdd(m.nelist, 1)] = s;   // first update of this merge epoch
     unsigned all = hit | miss;
     while (all) {
       const int j = __ffs(all) - 1;
@@ -421,7 +431,7 @@ __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cma
       hi = fminf(fmaxf(hi + d, cmin), cmax);
     }
     m.val[s] = v; m.a[s] = a; m.lo[s] = lo; m.hi[s] = hi;
-    if (hit) { m.rgb[s] = m.bm_rgb[s] & 0xffffffu; m.bm_rgb[s] = 0u; }
+    if (hit) { m.rgb[s] = (m.bm_rgb[s] & 0xffffffu) | 0x01000000u; m.bm_rgb[s] = 0u; }   // top byte 1: coloured this epoch
   }
 }
 
@@ -485,10 +495,73 @@ __global__ void k_ocm_apply_summaries(OcmConst c, MapView m, const unsigned long
   if (!found) { atomicExch(err, 4); return; }
   // value: v <- g(v); summary: f <- g o f  with g = (a, lo, hi)
   const float ga = a[i], gl = lo[i], gh = hi[i];
+  if (m.a[s] == 0.f && m.lo[s] == -INFINITY) m.elist[atomicAdd(m.nelist, 1)] = (int)s;
   m.val[s] = fminf(fmaxf(m.val[s] + ga, gl), gh);
   m.a[s] = m.a[s] + ga;
   m.lo[s] = fminf(fmaxf(m.lo[s] + ga, gl), gh);
   m.hi[s] = fminf(fmaxf(m.hi[s] + ga, gl), gh);
+}
+
+// ---- epoch merge (ocm_merge_nccl) -------------------------------------------------------------------------------------
+// One shard = SoA records {key u64, a, lo, hi f32, rgb u32} of the voxels a rank updated since the last merge (24 B each).
+struct MergeShard {
+  unsigned long long* keys;
+  float *a, *lo, *hi;
+  unsigned* rgb;
+};
+__host__ __device__ inline MergeShard merge_shard_at(void* region, long long n) {
+  MergeShard r;
+  char* p = (char*)region;
+  r.keys = (unsigned long long*)p; p += 8 * n;
+  r.a = (float*)p; p += 4 * n;
+  r.lo = (float*)p; p += 4 * n;
+  r.hi = (float*)p; p += 4 * n;
+  r.rgb = (unsigned*)p;
+  return r;
+}
+// pack this rank's epoch summaries and roll its own voxels back to the value of the last merge: afterwards EVERY rank
+// replays ALL shards (its own included) in rank order on the same base values, so all ranks end with identical maps
+__global__ void k_merge_pack(MapView m, int n, MergeShard o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = m.elist[i];
+  o.keys[i] = m.keys[s];
+  o.a[i] = m.a[s]; o.lo[i] = m.lo[s]; o.hi[i] = m.hi[s];
+  const unsigned c = m.rgb[s];
+  const bool fresh = (c >> 24) == 1u;
+  o.rgb[i] = fresh ? (c & 0xffffffu) : 0xffffffffu;
+  if (fresh) m.rgb[s] = c & 0xffffffu;
+  m.val[s] = m.base[s];
+  m.a[s] = 0.f; m.lo[s] = -INFINITY; m.hi[s] = INFINITY;
+}
+// apply one shard: v <- min(max(v + a, lo), hi) per voxel (keys of a shard are distinct; shards run as consecutive launches)
+__global__ void k_merge_apply(MapView m, long long n, MergeShard g, int* __restrict__ slots, int* __restrict__ err) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = g.keys[i];
+  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  bool found = false;
+  for (long long probe = 0; probe <= m.mask; ++probe) {
+    const unsigned long long cur = m.keys[s];
+    if (cur == key) { found = true; break; }
+    if (cur == EMPTY_KEY) {
+      const unsigned long long old = atomicCAS(&m.keys[s], EMPTY_KEY, key);
+      if (old == EMPTY_KEY) { atomicAdd(m.nleaves, 1); found = true; break; }
+      if (old == key) { found = true; break; }
+    }
+    s = (s + 1) & m.mask;
+  }
+  if (!found) { atomicExch(err, 4); slots[i] = -1; return; }
+  m.val[s] = fminf(fmaxf(m.val[s] + g.a[i], g.lo[i]), g.hi[i]);
+  const unsigned c = g.rgb[i];
+  if (c != 0xffffffffu) m.rgb[s] = c;
+  slots[i] = (int)s;
+}
+__global__ void k_merge_commit(MapView m, long long n, const int* __restrict__ slots) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = slots[i];
+  if (s >= 0) m.base[s] = m.val[s];
 }
 
 __global__ void k_ocm_query(MapView m, unsigned long long key, float* out, int* found) {
@@ -527,16 +600,26 @@ struct ocm {
   uint16_t* d_kf_d16 = nullptr;   // staging of ocm_insert_keyframes_u16
   float* d_kf_depth = nullptr;
   uint8_t* d_kf_rgb = nullptr;
+  uint8_t* d_kf_label = nullptr;
   size_t kf_cap = 0;
   long long* d_export_counter = nullptr;
+  // ocm_merge_nccl staging (grown on demand)
+  void *mg_send = nullptr, *mg_recv = nullptr;
+  int* mg_slots = nullptr;
+  int* mg_counts = nullptr;        // device, one int per rank
+  int* mg_counts_h = nullptr;      // page-locked mirror
+  long long mg_send_cap = 0, mg_recv_cap = 0;
+  int mg_world_cap = 0;
 
   ~ocm() {
     DeviceGuard g(device);
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves); F(map.bm); F(map.bm_rgb);
-    F(map.touched); F(map.ntouched);
+    F(map.touched); F(map.ntouched); F(map.base); F(map.elist); F(map.nelist);
+    F(mg_send); F(mg_recv); F(mg_slots); F(mg_counts);
+    if (mg_counts_h) cudaFreeHost(mg_counts_h);
     free_scratch();
-    F(d_counters); F(d_err); F(d_export_counter); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb); F(d_jobs);
+    F(d_counters); F(d_err); F(d_export_counter); F(d_kf_d16); F(d_kf_depth); F(d_kf_rgb); F(d_kf_label); F(d_jobs);
     if (h_jobs) cudaFreeHost(h_jobs);
     for (cudaEvent_t e : job_ev) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
@@ -744,6 +827,9 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   if ((e = cudaMalloc(&h->map.bm_rgb, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.touched, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.ntouched, 4)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.base, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.elist, 4 * C)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.nelist, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_counters, 16 * ocm::MAX_SLOTS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_export_counter, 8)) != cudaSuccess) return fail(e);
@@ -754,6 +840,8 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   cudaMemsetAsync(h->map.bm, 0, 8 * C, h->stream);
   cudaMemsetAsync(h->map.bm_rgb, 0, 4 * C, h->stream);
   cudaMemsetAsync(h->map.ntouched, 0, 4, h->stream);
+  cudaMemsetAsync(h->map.base, 0, 4 * C, h->stream);
+  cudaMemsetAsync(h->map.nelist, 0, 4, h->stream);
   cudaMemsetAsync(h->d_err, 0, 4, h->stream);
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e);
   *out = h;
@@ -768,26 +856,41 @@ int ocm_insert_keyframe_device(ocm_t* h, const float* d_depth, const uint8_t* d_
   return h->insert(d_depth, d_rgb, d_label, rows, cols, Tcw, fx, fy, cx, cy);
 }
 
-int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
-                                const int32_t* depth_idx, const int32_t* rgb_idx, int n, const float* Tcw, float fx,
-                                float fy, float cx, float cy) {
+int ocm_insert_keyframes_labeled_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, const uint8_t* d_label,
+                                        int rows, int cols, const int32_t* depth_idx, const int32_t* rgb_idx,
+                                        const int32_t* label_idx, int n, const float* Tcw, float fx, float fy, float cx,
+                                        float cy) {
   if (!h || !d_depth || !d_rgb || !depth_idx || !Tcw || rows <= 0 || cols <= 0 || n < 0) { set_error("bad argument"); return B200ORB_EINVAL; }
   DeviceGuard g(h->device);
   const size_t npix = (size_t)rows * cols;
   std::vector<const float*> dd(n);
-  std::vector<const uint8_t*> dc(n);
+  std::vector<const uint8_t*> dc(n), dl(n);
   for (int i = 0; i < n; ++i) {
-    const int di = depth_idx[i], ri = rgb_idx ? rgb_idx[i] : depth_idx[i];
-    if (di < 0 || ri < 0) { set_error("negative frame index"); return B200ORB_EINVAL; }
+    const int di = depth_idx[i], ri = rgb_idx ? rgb_idx[i] : depth_idx[i], li = label_idx ? label_idx[i] : depth_idx[i];
+    if (di < 0 || ri < 0 || li < 0) { set_error("negative frame index"); return B200ORB_EINVAL; }
     dd[i] = d_depth + npix * di;
     dc[i] = d_rgb + npix * 3 * ri;
+    dl[i] = d_label ? d_label + npix * li : nullptr;
   }
   if (n == 0) return B200ORB_OK;
-  return h->insert_batch(n, dd.data(), dc.data(), nullptr, rows, cols, Tcw, fx, fy, cx, cy);
+  return h->insert_batch(n, dd.data(), dc.data(), d_label ? dl.data() : nullptr, rows, cols, Tcw, fx, fy, cx, cy);
+}
+
+int ocm_insert_keyframes_device(ocm_t* h, const float* d_depth, const uint8_t* d_rgb, int rows, int cols,
+                                const int32_t* depth_idx, const int32_t* rgb_idx, int n, const float* Tcw, float fx,
+                                float fy, float cx, float cy) {
+  return ocm_insert_keyframes_labeled_device(h, d_depth, d_rgb, nullptr, rows, cols, depth_idx, rgb_idx, nullptr, n, Tcw, fx,
+                                             fy, cx, cy);
 }
 
 int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t* rgb, int rows, int cols, int n,
                              float depth_factor, const float* Tcw, float fx, float fy, float cx, float cy) {
+  return ocm_insert_keyframes_u16_labeled(h, depth_u16, rgb, nullptr, rows, cols, n, depth_factor, Tcw, fx, fy, cx, cy);
+}
+
+int ocm_insert_keyframes_u16_labeled(ocm_t* h, const uint16_t* depth_u16, const uint8_t* rgb, const uint8_t* label, int rows,
+                                     int cols, int n, float depth_factor, const float* Tcw, float fx, float fy, float cx,
+                                     float cy) {
   if (!h || !depth_u16 || !rgb || !Tcw || rows <= 0 || cols <= 0 || n < 0) { set_error("bad argument"); return B200ORB_EINVAL; }
   if (n == 0) return B200ORB_OK;
   DeviceGuard g(h->device);
@@ -796,20 +899,22 @@ int ocm_insert_keyframes_u16(ocm_t* h, const uint16_t* depth_u16, const uint8_t*
   B200_CHECK(h->ensure_scratch(rows, cols));
   if (tot > h->kf_cap) {   // staging for n keyframes (grown on demand; reused by every later call)
     B200_CUDA(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_kf_d16); cudaFree(h->d_kf_depth); cudaFree(h->d_kf_rgb);
-    h->d_kf_d16 = nullptr; h->d_kf_depth = nullptr; h->d_kf_rgb = nullptr; h->kf_cap = 0;
+    cudaFree(h->d_kf_d16); cudaFree(h->d_kf_depth); cudaFree(h->d_kf_rgb); cudaFree(h->d_kf_label);
+    h->d_kf_d16 = nullptr; h->d_kf_depth = nullptr; h->d_kf_rgb = nullptr; h->d_kf_label = nullptr; h->kf_cap = 0;
     B200_CUDA(cudaMalloc(&h->d_kf_d16, tot * 2)); B200_CUDA(cudaMalloc(&h->d_kf_depth, tot * 4)); B200_CUDA(cudaMalloc(&h->d_kf_rgb, tot * 3));
+    B200_CUDA(cudaMalloc(&h->d_kf_label, tot));
     h->kf_cap = tot;
   }
+  if (label) B200_CUDA(cudaMemcpyAsync(h->d_kf_label, label, tot, cudaMemcpyHostToDevice, h->stream));
   B200_CUDA(cudaMemcpyAsync(h->d_kf_d16, depth_u16, tot * 2, cudaMemcpyHostToDevice, h->stream));
   B200_CUDA(cudaMemcpyAsync(h->d_kf_rgb, rgb, tot * 3, cudaMemcpyHostToDevice, h->stream));
   k_depth_u16_to_f32<<<(unsigned)((tot / 4 + 255) / 256), 256, 0, h->stream>>>(
       reinterpret_cast<const ushort4*>(h->d_kf_d16), reinterpret_cast<float4*>(h->d_kf_depth), depth_factor, tot / 4);
   ++h->launches;
   std::vector<const float*> dd(n);
-  std::vector<const uint8_t*> dc(n);
-  for (int i = 0; i < n; ++i) { dd[i] = h->d_kf_depth + npix * i; dc[i] = h->d_kf_rgb + npix * 3 * i; }
-  return h->insert_batch(n, dd.data(), dc.data(), nullptr, rows, cols, Tcw, fx, fy, cx, cy);
+  std::vector<const uint8_t*> dc(n), dl(n);
+  for (int i = 0; i < n; ++i) { dd[i] = h->d_kf_depth + npix * i; dc[i] = h->d_kf_rgb + npix * 3 * i; dl[i] = h->d_kf_label + npix * i; }
+  return h->insert_batch(n, dd.data(), dc.data(), label ? dl.data() : nullptr, rows, cols, Tcw, fx, fy, cx, cy);
 }
 
 int ocm_insert_keyframe(ocm_t* h, const float* depth, const uint8_t* rgb, int rows, int cols, const float Tcw[16],
@@ -927,6 +1032,178 @@ int ocm_apply_summaries_device(ocm_t* h, const uint64_t* d_keys, const float* d_
   ++h->launches;
   B200_CUDA(cudaGetLastError());
   return h->check_err();
+}
+
+// ---- multi-GPU map merge over NCCL (SURVEY §8(b) ocm_merge_nccl, §8(e)) ---------------------------------------------
+// NCCL is bound at run time (dlopen of libnccl.so.2 -- the copy torch already loaded when there is one), so the library
+// has no link-time dependency on it and single-GPU users never touch it.
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* L = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!L) L = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (L) {
+      api.lib = L;
+      *(void**)&api.GetUniqueId = dlsym(L, "ncclGetUniqueId");
+      *(void**)&api.CommInitRank = dlsym(L, "ncclCommInitRank");
+      *(void**)&api.CommDestroy = dlsym(L, "ncclCommDestroy");
+      *(void**)&api.CommCount = dlsym(L, "ncclCommCount");
+      *(void**)&api.CommUserRank = dlsym(L, "ncclCommUserRank");
+      *(void**)&api.AllGather = dlsym(L, "ncclAllGather");
+      *(void**)&api.Broadcast = dlsym(L, "ncclBroadcast");
+      *(void**)&api.GroupStart = dlsym(L, "ncclGroupStart");
+      *(void**)&api.GroupEnd = dlsym(L, "ncclGroupEnd");
+      *(void**)&api.GetErrorString = dlsym(L, "ncclGetErrorString");
+      if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.Broadcast || !api.GroupStart || !api.GroupEnd ||
+          !api.CommCount || !api.CommUserRank || !api.CommDestroy || !api.GetErrorString)
+        api.lib = nullptr;
+    }
+  }
+  if (!api.lib) { set_error("NCCL not available (dlopen libnccl.so.2 failed)"); return nullptr; }
+  return &api;
+}
+#define B200_NCCL(api, expr)                                                                       \
+  do {                                                                                             \
+    ncclResult_t _r = (expr);                                                                      \
+    if (_r != ncclSuccess) { set_error("%s -> %s", #expr, (api)->GetErrorString(_r)); return B200ORB_ECUDA; } \
+  } while (0)
+
+int ocm_nccl_unique_id(uint8_t id[128]) {
+  NcclApi* N = nccl_api();
+  if (!N || !id) return B200ORB_EINVAL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+  ncclUniqueId u;
+  B200_NCCL(N, N->GetUniqueId(&u));
+  memcpy(id, &u, 128);
+  return B200ORB_OK;
+}
+int ocm_nccl_comm_create(const uint8_t id[128], int rank, int world, int device, void** comm) {
+  NcclApi* N = nccl_api();
+  if (!N || !id || !comm || world < 1 || rank < 0 || rank >= world) { if (N) set_error("bad argument"); return B200ORB_EINVAL; }
+  B200_CHECK(check_device(device));
+  DeviceGuard g(device);
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  ncclComm_t c = nullptr;
+  B200_NCCL(N, N->CommInitRank(&c, world, u, rank));
+  *comm = (void*)c;
+  return B200ORB_OK;
+}
+int ocm_nccl_comm_destroy(void* comm) {
+  NcclApi* N = nccl_api();
+  if (!N) return B200ORB_EINVAL;
+  if (comm) N->CommDestroy((ncclComm_t)comm);
+  return B200ORB_OK;
+}
+
+int ocm_merge_nccl(ocm_t* h, void* comm_, void* stream_, OcmMergeStats* st) {
+  if (!h) { set_error("null argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  cudaStream_t S = h->stream;
+  if (stream_ && (cudaStream_t)stream_ != S) {   // order after the caller's stream
+    cudaEvent_t ev;
+    B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    B200_CUDA(cudaEventRecord(ev, (cudaStream_t)stream_));
+    B200_CUDA(cudaStreamWaitEvent(S, ev, 0));
+    cudaEventDestroy(ev);
+  }
+  NcclApi* N = nullptr;
+  ncclComm_t comm = (ncclComm_t)comm_;
+  int world = 1, rank = 0;
+  if (comm) {
+    N = nccl_api();
+    if (!N) return B200ORB_EINVAL;
+    B200_NCCL(N, N->CommCount(comm, &world));
+    B200_NCCL(N, N->CommUserRank(comm, &rank));
+  }
+  if (world > h->mg_world_cap) {
+    if (h->mg_counts) cudaFree(h->mg_counts);
+    if (h->mg_counts_h) cudaFreeHost(h->mg_counts_h);
+    B200_CUDA(cudaMalloc(&h->mg_counts, 4 * world));
+    B200_CUDA(cudaHostAlloc(&h->mg_counts_h, 4 * world, cudaHostAllocDefault));
+    h->mg_world_cap = world;
+  }
+  // 1. counts: one int per rank (the only host synchronisation of the merge)
+  if (comm) B200_NCCL(N, N->AllGather(h->map.nelist, h->mg_counts, 1, ncclInt32, comm, S));
+  else B200_CUDA(cudaMemcpyAsync(h->mg_counts, h->map.nelist, 4, cudaMemcpyDeviceToDevice, S));
+  B200_CUDA(cudaMemcpyAsync(h->mg_counts_h, h->mg_counts, 4 * world, cudaMemcpyDeviceToHost, S));
+  B200_CUDA(cudaStreamSynchronize(S));
+  std::vector<long long> off(world + 1, 0);   // byte offsets of the shards in the receive buffer (16-byte aligned)
+  long long total = 0;
+  for (int r = 0; r < world; ++r) {
+    off[r + 1] = (long long)align_up_sz((size_t)(off[r] + 24ll * h->mg_counts_h[r]), 16);
+    total += h->mg_counts_h[r];
+  }
+  const long long n_own = h->mg_counts_h[rank];
+  if (24 * n_own > h->mg_send_cap) {
+    if (h->mg_send) cudaFree(h->mg_send);
+    h->mg_send_cap = std::max(24 * n_own * 2, 1ll << 20);
+    B200_CUDA(cudaMalloc(&h->mg_send, h->mg_send_cap));
+  }
+  if (off[world] > h->mg_recv_cap) {
+    if (h->mg_recv) cudaFree(h->mg_recv);
+    if (h->mg_slots) cudaFree(h->mg_slots);
+    h->mg_recv_cap = std::max(off[world] * 2, 1ll << 20);
+    B200_CUDA(cudaMalloc(&h->mg_recv, h->mg_recv_cap));
+    B200_CUDA(cudaMalloc(&h->mg_slots, h->mg_recv_cap / 24 * 4 + 64));
+  }
+  // 2. pack own summaries, roll own voxels back to the last merge
+  if (n_own > 0) {
+    k_merge_pack<<<(unsigned)((n_own + 255) / 256), 256, 0, S>>>(h->map, (int)n_own, merge_shard_at(h->mg_send, n_own));
+    ++h->launches;
+  }
+  B200_CUDA(cudaMemsetAsync(h->map.nelist, 0, 4, S));
+  // 3. exchange: every rank broadcasts its shard (exact sizes, one grouped NCCL call over NVLink)
+  if (comm && world > 1) {
+    B200_NCCL(N, N->GroupStart());
+    for (int r = 0; r < world; ++r) {
+      const size_t bytes = 24 * (size_t)h->mg_counts_h[r];
+      if (bytes == 0) continue;
+      B200_NCCL(N, N->Broadcast(r == rank ? h->mg_send : nullptr, (char*)h->mg_recv + off[r], bytes, ncclUint8, r, comm, S));
+    }
+    B200_NCCL(N, N->GroupEnd());
+  } else if (n_own > 0) {
+    B200_CUDA(cudaMemcpyAsync(h->mg_recv, h->mg_send, 24 * n_own, cudaMemcpyDeviceToDevice, S));
+  }
+  // 4. replay all shards in rank (= keyframe) order, then make the result the base of the next epoch
+  long long done = 0;
+  for (int r = 0; r < world; ++r) {
+    const long long n = h->mg_counts_h[r];
+    if (n == 0) continue;
+    k_merge_apply<<<(unsigned)((n + 255) / 256), 256, 0, S>>>(h->map, n, merge_shard_at((char*)h->mg_recv + off[r], n),
+                                                             h->mg_slots + done, h->d_err);
+    ++h->launches;
+    done += n;
+  }
+  if (total > 0) {
+    k_merge_commit<<<(unsigned)((total + 255) / 256), 256, 0, S>>>(h->map, total, h->mg_slots);
+    ++h->launches;
+  }
+  B200_CUDA(cudaGetLastError());
+  if (stream_ && (cudaStream_t)stream_ != S) {
+    cudaEvent_t ev;
+    B200_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    B200_CUDA(cudaEventRecord(ev, S));
+    B200_CUDA(cudaStreamWaitEvent((cudaStream_t)stream_, ev, 0));
+    cudaEventDestroy(ev);
+  }
+  if (st) { st->world = world; st->rank = rank; st->records_sent = n_own; st->records_total = total; st->bytes_sent = 24 * n_own; st->bytes_received = 24 * (total - n_own); }
+  return B200ORB_OK;
 }
 
 int ocm_sync(ocm_t* h) {

@@ -84,6 +84,9 @@ def merge_occupancy(pcm, group=None, device=None):
     pcm.sync()
     k = cnt.value
     shards = all_gather_summaries(keys[:k], a[:k], lo[:k], hi[:k], group)
+    # the gathers ran on torch's current stream; the apply kernels run on the map's own (non-blocking) stream
+    if keys.is_cuda:
+        torch.cuda.current_stream(dev).synchronize()
     merged = PointCloudMapping(pcm.resolution, pcm.params.prob_hit, pcm.params.prob_miss, pcm.params.clamp_min,
                                pcm.params.clamp_max, pcm.params.depth_min, pcm.params.depth_max, pcm.params.y_max,
                                pcm.params.leaf, pcm.params.map_capacity, device=dev.index or 0)

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import OcmParams, ptr
+from ._abi import OcmMergeStats, OcmParams, ptr
 
 
 class PointCloudMapping:
@@ -51,17 +51,56 @@ class PointCloudMapping:
                                                       C.c_void_p(d_label) if d_label else None))
 
     def insert_keyframes_device(self, d_depth: int, d_rgb: int, rows: int, cols: int, frame_idx, Tcw, fx, fy, cx, cy,
-                                rgb_idx=None):
+                                rgb_idx=None, d_label: int = 0, label_idx=None):
         """Keyframes (order = insertion order) of an RGB-D batch resident in HBM; one enqueue.  Keyframe i reads depth
-        image frame_idx[i] and colour image rgb_idx[i] (default: the same index)."""
+        image frame_idx[i], colour image rgb_idx[i] and (when d_label is given) ground-label image label_idx[i]
+        (default: the same index)."""
         idx = np.ascontiguousarray(frame_idx, np.int32)
         ridx = None if rgb_idx is None else np.ascontiguousarray(rgb_idx, np.int32)
+        lidx = None if label_idx is None else np.ascontiguousarray(label_idx, np.int32)
         T = np.ascontiguousarray(Tcw, np.float32).reshape(len(idx), 16)
-        _lib.check(self._L.ocm_insert_keyframes_device(self._h, C.c_void_p(d_depth), C.c_void_p(d_rgb), rows, cols, ptr(idx),
-                                                       ptr(ridx), len(idx), ptr(T), float(fx), float(fy), float(cx),
-                                                       float(cy)))
+        _lib.check(self._L.ocm_insert_keyframes_labeled_device(
+            self._h, C.c_void_p(d_depth), C.c_void_p(d_rgb), C.c_void_p(d_label) if d_label else None, rows, cols, ptr(idx),
+            ptr(ridx), ptr(lidx), len(idx), ptr(T), float(fx), float(fy), float(cx), float(cy)))
 
-    def insert_keyframes_u16(self, depth_u16: np.ndarray, rgb: np.ndarray, depth_factor: float, Tcw, fx, fy, cx, cy):
+    # ---- multi-GPU merge (ocm_merge_nccl) ----
+    def nccl_init(self, rank: int, world: int, device: int, group=None):
+        """Create this map's NCCL communicator: rank 0 draws the unique id, torch.distributed (plumbing only; gloo or
+        nccl) hands it to the other ranks."""
+        import torch
+        import torch.distributed as dist
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            _lib.check(self._L.ocm_nccl_unique_id(ptr(uid)))
+        obj = [uid.tobytes()]
+        if world > 1:
+            dist.broadcast_object_list(obj, src=0, group=group)
+        uid = np.frombuffer(obj[0], np.uint8).copy()
+        self._comm = C.c_void_p()
+        _lib.check(self._L.ocm_nccl_comm_create(ptr(uid), int(rank), int(world), int(device), C.byref(self._comm)))
+        return self._comm
+
+    def merge(self, stream: int = 0):
+        """ocm_merge_nccl: close the epoch -- exchange the summaries of everything inserted since the last merge with
+        the other ranks and replay all shards in rank order.  Returns OcmMergeStats."""
+        st = OcmMergeStats()
+        comm = getattr(self, "_comm", None)
+        _lib.check(self._L.ocm_merge_nccl(self._h, comm, C.c_void_p(stream) if stream else None, C.byref(st)))
+        return st
+
+    def UpdateOctomap(self, keyframes):
+        """MapDrawer::UpdateOctomap (perfect/src/MapDrawer.cc:610-638): inserts keyframes [lastKeyframeSize, N-1) of the
+        list -- the NEWEST keyframe is never inserted (`i < N-1`, :615) -- and remembers N-1.  `keyframes` is the whole
+        list so far, each (Tcw, depth, rgb, fx, fy, cx, cy[, ground_label])."""
+        N = len(keyframes)
+        last = getattr(self, "lastKeyframeSize", 0)
+        if N > 1:
+            for i in range(last, N - 1):
+                self.insertKeyFrame(*keyframes[i])
+            self.lastKeyframeSize = N - 1
+
+    def insert_keyframes_u16(self, depth_u16: np.ndarray, rgb: np.ndarray, depth_factor: float, Tcw, fx, fy, cx, cy,
+                             label: np.ndarray = None):
         """Keyframes from HOST buffers as the reference's callers hold them: CV_16U depth [n,rows,cols] (converted with
         depth_factor = 1/DepthMapFactor on the device) and colour [n,rows,cols,3].  Asynchronous: the arrays (page-locked
         for a truly asynchronous upload) must stay untouched until sync()."""
@@ -70,9 +109,11 @@ class PointCloudMapping:
         n, rows, cols = depth_u16.shape
         assert rgb.shape == (n, rows, cols, 3)
         T = np.ascontiguousarray(Tcw, np.float32).reshape(n, 16)
-        _lib.check(self._L.ocm_insert_keyframes_u16(self._h, ptr(depth_u16), ptr(rgb), rows, cols, n,
-                                                    float(np.float32(depth_factor)), ptr(T), float(fx), float(fy), float(cx),
-                                                    float(cy)))
+        if label is not None and (label.dtype != np.uint8 or not label.flags.c_contiguous or label.shape != (n, rows, cols)):
+            raise ValueError("label must be a C-contiguous uint8 [n, rows, cols] array")
+        _lib.check(self._L.ocm_insert_keyframes_u16_labeled(self._h, ptr(depth_u16), ptr(rgb), ptr(label), rows, cols, n,
+                                                            float(np.float32(depth_factor)), ptr(T), float(fx), float(fy),
+                                                            float(cx), float(cy)))
 
     def last_points(self):
         n = C.c_int(0)

@@ -146,3 +146,88 @@ class WallStream:
         dq = np.rint(depth.astype(np.float64) * DEPTH_FACTOR).astype(np.uint16)
         depth = (dq.astype(np.float32) * np.float32(1.0 / DEPTH_FACTOR)).astype(np.float32)
         return gray, depth, rgb, self.pose(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# Room box stream: textured planes of a 6 x 3 x 6 m room rendered by ray-plane intersection
+# ------------------------------------------------------------------------------------------------
+class RoomStream:
+    """Camera inside a 6 m (x) x 3 m (y, pointing DOWN like the camera's y axis) x 6 m (z) room whose six faces carry
+    textures.  The camera centre moves on a 0.5 m Lissajous around the room centre, 1.2 m above the floor, and pans
+    (yaw) / nods (pitch) / rolls by at most ~1.3 deg per frame, so walls, floor and ceiling enter and leave the
+    0.5 - 3.0 m gate of the occupancy path and the scene is not a single plane.  Every pixel's ray is intersected with
+    the six planes exactly, so depth (z_c), the ground-truth pose and the GT floor mask (ground label of InsertScan's
+    mode B, perfect/src/MapDrawer.cc:961-969) are exact."""
+
+    HALF = np.array([3.0, 0.0, 3.0])
+    Y_FLOOR, Y_CEIL = 1.2, -1.8
+
+    def __init__(self, seed: int = 1234, n: int = 827, h: int = H, w: int = W, ppm: float = 230.0, period: float = 200.0):
+        self.seed, self.n, self.h, self.w, self.ppm, self.period = seed, n, h, w, ppm, period
+        ts = int(6.0 * ppm) + 8
+        self.ts = ts
+        # six faces: x = -3, x = +3, z = -3, z = +3 (walls, 6 x 3 m), floor, ceiling (6 x 6 m)
+        self.tex = [texture(seed + 10 * k, int(3.0 * ppm) + 8 if k < 4 else ts, ts, nrect=1500 if k < 4 else 3000,
+                            nline=700 if k < 4 else 1400) for k in range(6)]
+
+    def pose(self, t: int) -> np.ndarray:
+        a = 2 * np.pi * t / self.period
+        twc = np.array([0.5 * np.sin(a), 0.08 * np.sin(2 * a), 0.5 * np.sin(1.5 * a + 0.4)])
+        yaw = np.deg2rad(40.0) * np.sin(a) + 2 * np.pi * t / (8 * self.period)
+        pitch = -(np.deg2rad(8.0) * np.sin(0.7 * a + 1.0) + np.deg2rad(12.0))   # y points down: negative = looking down at the floor
+        roll = np.deg2rad(2.0) * np.sin(3 * a)
+        cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+        Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+        Rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+        Rz = np.array([[cr, -sr, 0], [sr, cr, 0], [0, 0, 1]])
+        Rwc = Ry @ Rx @ Rz
+        T = np.eye(4)
+        T[:3, :3] = Rwc.T
+        T[:3, 3] = -Rwc.T @ twc
+        return T.astype(np.float32)
+
+    def frame(self, t: int, with_label: bool = False):
+        """-> gray u8, depth f32 metres (TUM-quantised), rgb u8 (h,w,3), Tcw f32 4x4 [, floor label u8 (h,w)]."""
+        T = self.pose(t).astype(np.float64)
+        Rcw, tcw = T[:3, :3], T[:3, 3]
+        Rwc = Rcw.T
+        twc = -Rwc @ tcw
+        v, u = np.mgrid[0:self.h, 0:self.w].astype(np.float64)
+        rays = np.stack([(u - CX) / FX, (v - CY) / FY, np.ones_like(u)], -1) @ Rwc.T   # unit z_c per ray
+        best = np.full((self.h, self.w), np.inf)
+        face = np.zeros((self.h, self.w), np.int8)
+        planes = [(0, -3.0), (0, 3.0), (2, -3.0), (2, 3.0), (1, self.Y_FLOOR), (1, self.Y_CEIL)]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            for k, (ax, c) in enumerate(planes):
+                lam = (c - twc[ax]) / rays[..., ax]
+                ok = (lam > 1e-6) & (lam < best)
+                best = np.where(ok, lam, best)
+                face = np.where(ok, k, face).astype(np.int8)
+        Xw = twc + rays * best[..., None]
+        val = np.zeros((self.h, self.w))
+        for k, (ax, c) in enumerate(planes):
+            m = face == k
+            if not m.any():
+                continue
+            P = Xw[m]
+            if ax == 0:
+                a_, b_ = P[:, 2] + 3.0, P[:, 1] - self.Y_CEIL
+            elif ax == 2:
+                a_, b_ = P[:, 0] + 3.0, P[:, 1] - self.Y_CEIL
+            else:
+                a_, b_ = P[:, 0] + 3.0, P[:, 2] + 3.0
+            tex = self.tex[k]
+            tx, ty = a_ * self.ppm + 2.0, b_ * self.ppm + 2.0
+            x0 = np.clip(np.floor(tx).astype(int), 0, tex.shape[1] - 2)
+            y0 = np.clip(np.floor(ty).astype(int), 0, tex.shape[0] - 2)
+            fx_, fy_ = np.clip(tx - x0, 0, 1), np.clip(ty - y0, 0, 1)
+            val[m] = (tex[y0, x0] * (1 - fx_) + tex[y0, x0 + 1] * fx_) * (1 - fy_) + \
+                     (tex[y0 + 1, x0] * (1 - fx_) + tex[y0 + 1, x0 + 1] * fx_) * fy_
+        rng = np.random.Generator(np.random.PCG64(10 ** 6 + t))
+        gray = np.clip(np.rint(val + rng.normal(0, 2.0, size=val.shape)), 0, 255).astype(np.uint8)
+        rgb = np.stack([gray, np.clip(gray.astype(np.int32) + 10, 0, 255).astype(np.uint8), (255 - gray)], -1).astype(np.uint8)
+        dq = np.rint(np.minimum(best, 13.0) * DEPTH_FACTOR).astype(np.uint16)
+        depth = (dq.astype(np.float32) * np.float32(1.0 / DEPTH_FACTOR)).astype(np.float32)
+        if with_label:
+            return gray, depth, rgb, self.pose(t), (face == 4).astype(np.uint8)
+        return gray, depth, rgb, self.pose(t)

@@ -256,3 +256,17 @@ def test_rgbd_frame_constructor_equals_reference_sources(src):
         assert 0.5 * len(K) < va.sum() < 0.9 * len(K)
         assert ur.tobytes() == ur2.tobytes() and dp.tobytes() == dp2.tobytes()
         assert (va == va2).all() and xw[va > 0].tobytes() == xw2[va2 > 0].tobytes()
+
+
+def test_tracking_pipeline_equals_reference_sources(src):
+    """The CPU-baseline drivers agree: oracle/pipeline_ref.cpp (port) and refsrc_pipeline_run (the reference's own Frame
+    constructor + SearchByProjection(cur, last) over a non-planar RGB-D stream) give the same keypoint and match counts
+    per frame -- so `bench.py --impl reference` may time either as the same work."""
+    rs = synth.RoomStream(seed=3, n=40)
+    fr = [rs.frame(3 * t) for t in range(6)]
+    gray, depth, T = np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr]), np.stack([f[3] for f in fr])
+    kw = dict(fx=synth.FX, fy=synth.FY, cx=synth.CX, cy=synth.CY, bf=synth.BF)
+    a = src.pipeline_run(gray, depth, T, 2, 1000, **kw)
+    b = src.src_pipeline_run(gray, depth, T, 2, 1000, **kw)
+    assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
+    assert a[2][1:].min() > 100
