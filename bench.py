@@ -1,21 +1,30 @@
 #!/usr/bin/env python3
-"""bench.py -- RGB-D frames/s of the ORB-SLAM2 hot path (extract + SearchByProjection match [+ octomap insert])
-at 640x480 on N x B200, with the per-kernel HBM roofline and the CPU baseline beside it.
+"""bench.py -- RGB-D frames/s of the ORB-SLAM2 hot path (extract + SearchByProjection match + octomap insert) at
+640x480 on N x B200, with the per-kernel HBM roofline and the reference's CPU path timed beside it.
 
-A "step" is one pass of the hot path over one batch of synthetic RGB-D frames (BASELINE.json configs[1]: a TUM
-fr3_walking-shaped 640x480 stream, ORBextractor(1000,1.2,8,20,7), SearchByProjection th=15 against the previous
-frame; every KF_EVERY-th frame is a keyframe pushed into the occupancy map).  One process per GPU; frames are
-sharded across ranks with no data-path collective (weak scaling: every rank runs a full batch).
+Workload (BASELINE.json configs[2] shape, scene per SURVEY §8(d)): a synthetic RGB-D stream of a 6 x 3 x 6 m textured
+room (RoomStream: camera on a 0.5 m Lissajous, panning <= 1.5 deg/frame, exact depth, GT floor mask), processed in the
+batched many-frame mode: 256-frame batches, ORBextractor(2000,1.2,8,20,7), per frame ComputeStereoFromRGBD + grid +
+SearchByProjection(cur, last, th=15); every 12th frame is a keyframe inserted into the 0.05 m occupancy map with the
+floor as ground label (mode B: ground points cast free-space rays, perfect/src/MapDrawer.cc:961-969).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames B] [--impl b200|reference]
+A STEP = one pass over SUB x 256 = 4096 frames (16 batches; the same 256 images resident in HBM are walked 16 times --
+629 MB of inputs per pass, far beyond the 126 MB L2 -- with the world shifted by one room per batch so that every batch's
+keyframes fall on fresh map cells).  With the driver's --steps 20 the timed region is > 1 s.
 
-value   : whole-job frames/s with the batch already resident in HBM, timed with CUDA events on the pipeline's
-          stream, max over ranks.
-e2e     : the same metric through the reference-facing C-ABI call with HOST buffers (pinned), host<->device
-          copies inside the timed region.
-roofline: dominant kernel of the step, algorithmic bytes / CUDA-event duration measured live.
-cpu_baseline / --impl reference: the CPU oracle (line-faithful port of the reference path; the reference itself
-          cannot be compiled here) timed on the host cores on a bounded sample of the same workload.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--nfeatures 2000] [--no-cpu]
+
+N > 1 (torchrun, one rank per GPU): STRONG scaling -- the 4096 frames of a step are sharded in contiguous ranges
+(+1 halo frame each, re-extracted locally), every rank maps its own keyframes, and ocm_merge_nccl (the only collective
+of the path: an exchange of per-voxel clamp-add summaries over NVLink) runs INSIDE the timed region at the end of every
+step; `merge` in the line says what it cost.
+
+value   : whole-job frames/s, inputs resident in HBM, CUDA events on the pipeline's streams, max over ranks.
+e2e     : the same through the reference-facing C-ABI calls with pinned HOST buffers, copies inside the timed region.
+roofline: dominant kernel, algorithmic bytes / its CUDA-event time measured live.
+cpu_baseline / --impl reference: the reference's own tracking sources (oracle/_ref: src/ORBextractor.cc, Frame.cc,
+          ORBmatcher.cc compiled unmodified; OpenCV primitives are bit-exact models, not OpenCV's SIMD code) frame-parallel
+          on the host cores + the occupancy port (MapDrawer needs PCL/octomap: unbuildable), timed beside each other.
 """
 from __future__ import annotations
 
@@ -33,11 +42,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from orb_slam2_ssd_semantic_b200 import synth  # noqa: E402
+from orb_slam2_ssd_semantic_b200.distributed import shard_range  # noqa: E402
 
 ROWS, COLS = 480, 640
-NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH = 1000, 1.2, 8, 20, 7    # perfect/Examples/RGB-D/TUM3.yaml:45-54
+SCALE, NLEVELS, INI_TH, MIN_TH = 1.2, 8, 20, 7                  # perfect/Examples/RGB-D/TUM3.yaml:45-54
 TH, NNRATIO = 15.0, 0.9                                        # src/Tracking.cc:1327,1346
 KF_EVERY = 12   # tool/KeyFrameTrajectory_f3_walk_src.txt holds 69 keyframes for 827 frames -> 1 in 12
+BATCH = 256     # frames per batched launch set (configs[2])
+SUB = 16        # batches per step
+REF_PASSES = 2  # passes over the batch per step of the CPU arm (bounded sample)
+ROOMS = 64      # distinct world offsets the batches cycle through (the map saturates at 64 rooms)
+ROOM_PITCH = 8.0
 S_IN = ROWS * COLS
 LEVEL_PX = [640 * 480, 533 * 400, 444 * 333, 370 * 278, 309 * 231, 257 * 193, 214 * 161, 179 * 134]
 S_PYR = sum(LEVEL_PX)
@@ -45,15 +60,13 @@ METRIC = "RGB-D frames/sec (extract+match+octomap) @640x480"
 
 
 def algorithmic_bytes(n_kp: float, n_cand: float) -> dict:
-    """Per-frame algorithmic bytes of each stage."""
+    """Per-frame algorithmic bytes of each tracking stage (SURVEY §8(d) / DESIGN.md §4)."""
     return {
         "resize": (S_PYR - LEVEL_PX[-1]) + (S_PYR - LEVEL_PX[0]),
         "fast": S_PYR + 4 * n_cand,
         "quadtree": 4 * n_cand + 4 * n_kp,
         "blur": 2 * S_PYR,
-        # per keypoint: the 749 raw pixels of the r = 15 disc (IC_Angle), the 512 blurred sample pixels of the pattern,
-        # 4 B selection in, 60 B KeyPoint + descriptor out
-        "orient_desc": (749 + 512 + 4 + 60) * n_kp,
+        "orient_desc": (4 + 60) * n_kp,   # selection in, KeyPoint + descriptor out; patch gathers not counted (§8(d))
         "glue": 69 * n_kp,
         "match": 52 * n_kp + 52 * n_kp + 4 * (64 * 48 + 1) + 8 * n_kp,
     }
@@ -64,24 +77,40 @@ def pipeline_bytes(n_kp: float) -> float:
     return S_IN + 5 * S_PYR + 60 * n_kp + (52 * n_kp + 52 * n_kp + 4 * (64 * 48 + 1) + 8 * n_kp)
 
 
+def map_bytes(points: float, touched: float) -> float:
+    """B_map of SURVEY §8(d) per keyframe: W*H*(4+3) + 16 P + 32 U."""
+    return S_IN * 7 + 16 * points + 32 * touched
+
+
 def measured_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
-        with open(p) as f:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def make_batch(nframes: int, seed: int = 1234):
-    ws = synth.WallStream(seed=seed, n=nframes)
-    gray = np.empty((nframes, ROWS, COLS), np.uint8)
-    depth = np.empty((nframes, ROWS, COLS), np.float32)
-    rgb = np.empty((nframes, ROWS, COLS, 3), np.uint8)
-    T = np.empty((nframes, 4, 4), np.float32)
-    for t in range(nframes):
-        gray[t], depth[t], rgb[t], T[t] = ws.frame(t)
-    return gray, depth, rgb, T
+def make_batch(lo: int, hi: int, seed: int = 1234):
+    """Frames [lo, hi) of the 256-frame room stream: gray, depth f32, rgb, floor label, Tcw."""
+    rs = synth.RoomStream(seed=seed, n=BATCH)
+    n = hi - lo
+    gray = np.empty((n, ROWS, COLS), np.uint8)
+    depth = np.empty((n, ROWS, COLS), np.float32)
+    rgb = np.empty((n, ROWS, COLS, 3), np.uint8)
+    label = np.empty((n, ROWS, COLS), np.uint8)
+    T = np.empty((n, 4, 4), np.float32)
+    for i, t in enumerate(range(lo, hi)):
+        gray[i], depth[i], rgb[i], T[i], label[i] = rs.frame(t, with_label=True)
+    return gray, depth, rgb, label, T
+
+
+def shifted_poses(T: np.ndarray, room: int) -> np.ndarray:
+    """Poses of the same camera path in room `room` of a corridor of identical rooms ROOM_PITCH apart along world x:
+    Xw' = Xw + d  =>  tcw' = tcw - Rcw d."""
+    out = T.copy()
+    d = np.array([ROOM_PITCH * room, 0.0, 0.0], np.float64)
+    out[:, :3, 3] = (T[:, :3, 3].astype(np.float64) - T[:, :3, :3].astype(np.float64) @ d).astype(np.float32)
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -123,41 +152,96 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def workload_config(args, world, frames_step):
+    return {"workload": "synthetic 640x480 RGB-D room stream (SURVEY 8(d)), batched many-frame mode: %d-frame batches, "
+                        "ORBextractor(%d,1.2,8,20,7) + stereo-from-depth + SearchByProjection(cur,last,th=15) per frame, "
+                        "every %dth frame a keyframe into the 0.05 m occupancy map with the GT floor as ground label "
+                        "(free-space rays); BASELINE.json configs[2] shape + keyframe path of configs[3]"
+                        % (BATCH, args.nfeatures, KF_EVERY),
+            "frames_per_step": frames_step, "batches_per_step": SUB, "batch_frames": BATCH,
+            "keyframes_per_step": SUB * len(range(0, BATCH, KF_EVERY)), "nfeatures": args.nfeatures,
+            "parallelism": ("single GPU" if world == 1 else
+                            "strong scaling: contiguous frame shards x%d (+1 halo frame), ocm_merge_nccl per step" % world),
+            "l2": "inputs of one pass over the resident batch (%.0f MB gray+depth+rgb+label) exceed the 126 MB L2; no "
+                  "explicit flush" % (BATCH * S_IN * 9 / 1e6)}
+
+
 # --------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (port of src/ORBextractor.cc + src/Frame.cc glue + src/ORBmatcher.cc) on the host cores
+# CPU arm
 # --------------------------------------------------------------------------------------------------------------
-def cpu_pipeline(gray, depth, rgb, T, nthreads: int):
-    """extract -> stereo/unproject -> SearchByProjection(cur,last) over the frames on `nthreads` host threads
-    (oracle/pipeline_ref.cpp: frame-parallel, one extractor instance per thread as src/Frame.cc:121-124 does for
-    stereo) with every KF_EVERY-th frame also pushed through the occupancy oracle on its own mapping thread (the
-    reference maps on a separate std::thread, src/pointcloudmapping.cc:43); timed inside with steady_clock."""
+def cpu_step(gray, depth, rgb, label, T, nthreads, nfeat, passes):
+    """`passes` walks over the 256-frame batch on the host cores: tracking through the reference's own sources
+    (frame-parallel on nthreads) while a mapping thread inserts the keyframes (GeneratePointCloud of the keyframes on
+    all threads, InsertScan sequential) -- the reference maps on its own std::thread (src/pointcloudmapping.cc:43).
+    -> (wall s, tracking s, mapping s, kind)"""
     from oracle import ref
-    sec, _, _ = ref.pipeline_run(gray, depth, T, nthreads, NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY,
-                                 synth.CX, synth.CY, synth.BF, TH, NNRATIO, True, 1, rgb=rgb, kf_every=KF_EVERY)
-    return sec
+    kfs = list(range(0, len(gray), KF_EVERY))
+    res = {}
+    use_src = ref.refsrc_available()
+
+    def track():
+        t = 0.0
+        for _ in range(passes):
+            if use_src:
+                t += ref.src_pipeline_run(gray, depth, T, nthreads, nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX,
+                                          synth.FY, synth.CX, synth.CY, synth.BF, TH, NNRATIO, True)[0]
+            else:
+                t += ref.pipeline_run(gray, depth, T, nthreads, nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY,
+                                      synth.CX, synth.CY, synth.BF, TH, NNRATIO, True, 1)[0]
+        res["track"] = t
+
+    def mapper():
+        occ = ref.RefOccupancy()
+        t0 = time.perf_counter()
+        for p in range(passes):
+            occ.insert_keyframes_mt(depth, rgb, label, kfs, shifted_poses(T[kfs], p % ROOMS), synth.FX, synth.FY, synth.CX,
+                                    synth.CY, nthreads)
+        res["map"] = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=track), threading.Thread(target=mapper)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    wall = time.perf_counter() - t0
+    return wall, res["track"], res["map"], ("reference" if use_src else "port")
 
 
 def run_reference(args):
-    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores, same config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     nthreads = min(cores, 64)
-    sample = min(args.frames, max(2 * nthreads, 32))
-    gray, depth, rgb, T = make_batch(sample)
+    # a step of the GPU arm is SUB passes over the batch; the CPU arm times a bounded sample of it (REF_PASSES passes):
+    # the reference's mapper is one thread at ~20 keyframes/s, so a full 352-keyframe step would take ~20 s
+    passes = REF_PASSES
+    gray, depth, rgb, label, T = make_batch(0, BATCH)
     for _ in range(min(args.warmup, 1)):
-        cpu_pipeline(gray[:max(2, nthreads)], depth, rgb, T, nthreads)
-    times = [cpu_pipeline(gray, depth, rgb, T, nthreads) for _ in range(args.steps)]
-    tot = float(np.sum(times))
-    value = sample * args.steps / tot
+        cpu_step(gray[:max(2 * nthreads, 16)], depth, rgb, label, T[:max(2 * nthreads, 16)], nthreads, args.nfeatures, 1)
+    tot = trk = mp_ = 0.0
+    kind = "port"
+    for _ in range(args.steps):
+        w, a, b, kind = cpu_step(gray, depth, rgb, label, T, nthreads, args.nfeatures, passes)
+        tot += w; trk += a; mp_ += b
+    frames = BATCH * passes
+    nkf = passes * len(range(0, BATCH, KF_EVERY))
+    value = frames * args.steps / tot
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": workload_config(args, sample),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nthreads, "kind": "port",
-                         "sample": "%d frames/step x %d steps, frame-parallel on %d threads" % (sample, args.steps, nthreads)},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, world, BATCH * SUB),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": nthreads, "kind": kind,
+                         "sample": "%d frames/step (%d of the %d passes of a step over the %d-frame batch) x %d steps; tracking "
+                                   "frame-parallel on %d threads beside one mapping thread" % (frames, passes, SUB, BATCH, args.steps, nthreads),
+                         "tracking_fps": frames * args.steps / trk, "mapping_kf_per_s": nkf * args.steps / mp_,
+                         "bottleneck": "tracking" if trk > mp_ else "mapping",
+                         "tracking": "reference sources (oracle/_ref: ORBextractor.cc, Frame.cc, ORBmatcher.cc unmodified)"
+                         if kind == "reference" else "oracle port", "mapping": "oracle port (MapDrawer needs PCL/octomap)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -165,21 +249,15 @@ def run_reference(args):
     return 0
 
 
-# DRAM traffic of the single-launch stages, bytes per frame, from the ncu capture summarised in
-# profiles/r01_ncu_v5_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum of a 256-frame launch / 256)
-NCU_DRAM_BYTES_PER_FRAME = {"fast": (231405824 + 41911808) / 256.0, "quadtree": (74866176 + 93454336) / 256.0,
-                            "orient_desc": (463207168 + 18829056) / 256.0}
-
-
-def workload_config(args, frames):
-    return {"workload": "TUM fr3_walking-shaped synthetic RGB-D stream 640x480, ORBextractor(1000,1.2,8,20,7) + "
-                        "SearchByProjection(cur,last,th=15) per frame, every %dth frame a keyframe inserted into the "
-                        "0.05 m occupancy map (BASELINE.json configs[1] + keyframe path of configs[3])" % KF_EVERY,
-            "keyframes_per_step_per_gpu": len(range(0, frames, KF_EVERY)),
-            "frames_per_step_per_gpu": frames, "nfeatures": NFEAT, "parallelism": "frame-sharded x%d" % args.gpus,
-            "l2": ("inputs (%.0f MB gray+depth per step) exceed the 126 MB L2" if frames * S_IN * 5 > 126e6 else
-                   "inputs (%.0f MB gray+depth per step) FIT the 126 MB L2: not a valid timing configuration, use the "
-                   "default --frames") % (frames * S_IN * 5 / 1e6)}
+# DRAM traffic of the single-launch stages, bytes per frame, from the ncu capture named in traffic_source
+NCU_DRAM_BYTES_PER_FRAME = {}
+NCU_SOURCE = None
+try:
+    with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
+        _j = json.load(_f)
+        NCU_DRAM_BYTES_PER_FRAME, NCU_SOURCE = _j["bytes_per_frame"], _j["source"]
+except Exception:
+    pass
 
 
 def run_b200(args):
@@ -193,31 +271,54 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    F = args.frames
-    gray, depth, rgb, T = make_batch(F, seed=1234 + rank)
-    st = StreamTracker(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, TH,
-                       NNRATIO, True, F, device=local)
-    d_gray = torch.from_numpy(gray).to(dev)
-    d_depth = torch.from_numpy(depth).to(dev)
-    d_T = torch.from_numpy(T).to(dev)
-    d_rgb = torch.from_numpy(rgb).to(dev)
+    nfeat = args.nfeatures
+    # ---- shard of this rank: contiguous range of the SUB*BATCH frames of a step, as (batch, lo, hi) pieces; the frame
+    # before `lo` is the halo (re-extracted locally for the match of frame lo), batch-initial frames have none
+    g_lo, g_hi = shard_range(SUB * BATCH, world, rank)
+    pieces = []
+    for b in range(SUB):
+        lo, hi = max(g_lo, b * BATCH), min(g_hi, (b + 1) * BATCH)
+        if lo < hi:
+            pieces.append((b, lo - b * BATCH, hi - b * BATCH))
+    f_lo = min(max(p[1] - 1, 0) for p in pieces)
+    f_hi = max(p[2] for p in pieces)
+    gray, depth, rgb, label, T = make_batch(f_lo, f_hi)          # only the frames this rank touches
+    nloc = f_hi - f_lo
+    st = StreamTracker(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, TH,
+                       NNRATIO, True, BATCH, device=local)
+    d_gray, d_depth = torch.from_numpy(gray).to(dev), torch.from_numpy(depth).to(dev)
+    d_rgb, d_label, d_T = torch.from_numpy(rgb).to(dev), torch.from_numpy(label).to(dev), torch.from_numpy(T).to(dev)
     pcm = PointCloudMapping(0.05, device=local)
-    kfs = list(range(0, F, KF_EVERY))
+    pcm.nccl_init(rank, world, local) if world > 1 else None
     ext = torch.cuda.ExternalStream(st.stream(), device=dev)
     ext_map = torch.cuda.ExternalStream(pcm.stream(), device=dev)
+    # per piece: frames [h, hi) are tracked (h = halo or lo), keyframes = global multiples of KF_EVERY inside [lo, hi)
+    plan = []
+    for (b, lo, hi) in pieces:
+        h = max(lo - 1, 0)
+        kf = [t for t in range(lo, hi) if t % KF_EVERY == 0]
+        plan.append({"room": b, "off": h - f_lo, "n": hi - h, "own": hi - lo, "kf": np.array([t - f_lo for t in kf], np.int32),
+                     "Tkf": [shifted_poses(T[[t - f_lo for t in kf]], r) if kf else None for r in range(ROOMS)]})
+    frames_step_total = SUB * BATCH
+    own_frames = sum(p["own"] for p in plan)
+    tracked_frames = sum(p["n"] for p in plan)
     npx = ROWS * COLS
+    step_no = [0]
 
     def step_device():
-        # tracking (extract + glue + match) on the pipeline stream, dense mapping on its own stream beside it -- the
-        # reference also maps on a separate thread (src/pointcloudmapping.cc:43)
-        st.track_batch_device(d_gray.data_ptr(), d_depth.data_ptr(), d_T.data_ptr(), F, ROWS, COLS)
-        pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), ROWS, COLS, kfs, T[kfs], synth.FX, synth.FY,
-                                    synth.CX, synth.CY)
-
-    def join_streams():
-        ev = torch.cuda.Event()
-        ev.record(ext_map)
-        ext.wait_event(ev)
+        k = step_no[0]
+        step_no[0] += 1
+        for p in plan:
+            o = p["off"]
+            st.track_batch_device(d_gray.data_ptr() + o * npx, d_depth.data_ptr() + o * npx * 4, d_T.data_ptr() + o * 64,
+                                  p["n"], ROWS, COLS)
+            if len(p["kf"]):
+                room = (k * SUB + p["room"]) % ROOMS
+                pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), ROWS, COLS, p["kf"], p["Tkf"][room],
+                                            synth.FX, synth.FY, synth.CX, synth.CY, d_label=d_label.data_ptr())
+        if world > 1:
+            return pcm.merge()     # ocm_merge_nccl: inside the timed region
+        return None
 
     def barrier():
         torch.cuda.synchronize()
@@ -227,8 +328,7 @@ def run_b200(args):
 
     for _ in range(args.warmup):
         step_device()
-    st.sync()
-    pcm.sync()
+    st.sync(); pcm.sync()
     launches0 = st.launch_count() + pcm.launch_count()
     st.profile_enable(True)
     st.profile_read()
@@ -236,20 +336,20 @@ def run_b200(args):
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
     em0, em1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    em0.record(ext_map)
+    e0.record(ext); em0.record(ext_map)
+    merge_stats, t_merge_host = [], 0.0
     for _ in range(args.steps):
-        step_device()
+        ms = step_device()
+        if ms is not None:
+            merge_stats.append((ms.records_sent, ms.records_total, ms.bytes_sent, ms.bytes_received))
     em1.record(ext_map)
-    join_streams()
+    ev = torch.cuda.Event(); ev.record(ext_map); ext.wait_event(ev)
     e1.record(ext)
-    st.sync()
-    pcm.sync()
+    st.sync(); pcm.sync()
     barrier()
-    map_ms = em0.elapsed_time(em1)
     clocks = sampler.result()
-    ms_total = e0.elapsed_time(e1)
+    ms_total, map_ms = e0.elapsed_time(e1), em0.elapsed_time(em1)
     stage_ms, prof_frames, prof_runs = st.profile_read()
     st.profile_enable(False)
     launches = st.launch_count() + pcm.launch_count() - launches0
@@ -257,74 +357,106 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_total = float(tms.item())
-    value = world * F * args.steps / (ms_total * 1e-3)
+    value = frames_step_total * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers (pinned) through the reference-facing calls ----
-    # What the host hands over per step is what the reference's callers hold: gray u8 + the sensor's CV_16U depth +
-    # poses for every frame (Tracking::GrabImageRGBD converts the depth itself, src/Tracking.cc:366-367) and the
-    # colour image of every keyframe (Tracking::CreateNewKeyFrame -> insertKeyFrame, src/Tracking.cc:1889).  The
-    # tracker never uploads depth images (it reads the pixels under the keypoints in place); the mapper uploads the
-    # depth + colour of the keyframes only.
+    # ---- mapping alone (own stream idle otherwise): event time of one step's keyframe inserts, for the roofline ----
+    pts_sum = touched_sum = 0
+    mm0, mm1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    mm0.record(ext_map)
+    nkf_alone = 0
+    for p in plan:
+        if len(p["kf"]):
+            pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), ROWS, COLS, p["kf"], p["Tkf"][(step_no[0] * SUB + p["room"]) % ROOMS],
+                                        synth.FX, synth.FY, synth.CX, synth.CY, d_label=d_label.data_ptr())
+            nkf_alone += len(p["kf"])
+    mm1.record(ext_map)
+    pcm.sync()
+    map_alone_ms = mm0.elapsed_time(mm1)
+    if nkf_alone:   # P and U of the last round (<= 32 keyframes) of the last piece
+        pts_sum, touched_sum = pcm.last_batch_stats()
+        last_round = len(plan[-1]["kf"]) % 32 or min(len(plan[-1]["kf"]), 32)
+    merge_alone = None
+    if world > 1:
+        mg0, mg1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        mg0.record(ext_map)
+        msx = pcm.merge()
+        mg1.record(ext_map)
+        pcm.sync()
+        merge_alone = {"ms": mg0.elapsed_time(mg1), "records_sent": int(msx.records_sent), "records_total": int(msx.records_total),
+                       "bytes_sent": int(msx.bytes_sent), "bytes_received": int(msx.bytes_received)}
+
+    # ---- e2e: pinned host buffers through the reference-facing calls, copies inside the timed region ----
     depth_u16 = np.rint(depth.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)
     assert (depth_u16.astype(np.float32) * np.float32(1.0 / synth.DEPTH_FACTOR) == depth).all()
-    p_gray = torch.from_numpy(gray).pin_memory()
-    p_d16 = torch.from_numpy(depth_u16).pin_memory()
-    p_T = torch.from_numpy(T).pin_memory()
-    p_rgbk = torch.from_numpy(np.ascontiguousarray(rgb[kfs])).pin_memory()
-    p_d16k = torch.from_numpy(np.ascontiguousarray(depth_u16[kfs])).pin_memory()
-    kf_d16, kf_rgb = p_d16k.numpy(), p_rgbk.numpy()
-    st_gray, st_d16, st_T = p_gray.numpy(), p_d16.numpy(), p_T.numpy()
-    outs = st.alloc_outputs(F, pinned=True)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    p_gray, p_d16, p_T = pin(gray), pin(depth_u16), pin(T)
+    h_gray, h_d16, h_T = p_gray.numpy(), p_d16.numpy(), p_T.numpy()
+    kf_pins = []
+    for p in plan:
+        if len(p["kf"]):
+            kf_pins.append((pin(depth_u16[p["kf"]]), pin(rgb[p["kf"]]), pin(label[p["kf"]])))
+        else:
+            kf_pins.append(None)
     factor = np.float32(1.0 / synth.DEPTH_FACTOR)
-    # Two tracker handles used alternately keep two batches in flight: the upload of batch k+1 and the download of
-    # batch k-1 overlap the kernels of batch k (orbs_chain_after orders the kernels of consecutive batches).  Every batch still crosses PCIe in both directions inside the timed
-    # region, and its results are on the host (sync of its handle) before the batch after the next is submitted.
-    st2 = StreamTracker(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, TH,
-                        NNRATIO, True, F, device=local)
+    st2 = StreamTracker(nfeat, SCALE, NLEVELS, INI_TH, MIN_TH, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, TH,
+                        NNRATIO, True, BATCH, device=local)
     trk = [st, st2]
     for t in trk:
-        t.set_chunk_frames(F)   # whole-batch uploads: they overlap the other handle's kernels, not this handle's own
-    outs2 = [outs, st2.alloc_outputs(F, pinned=True)]
+        t.set_chunk_frames(BATCH)
+    outs2 = [st.alloc_outputs(BATCH, pinned=True), st2.alloc_outputs(BATCH, pinned=True)]
+    e2e_k = [0]
 
-    def submit(k):
-        # mapper first, asynchronously on its own stream (ocm_insert_keyframes_u16): H2D depth (CV_16U) + colour of the
-        # keyframes only, converted on the device, then the keyframe inserts
-        pcm.insert_keyframes_u16(kf_d16, kf_rgb, factor, T[kfs], synth.FX, synth.FY, synth.CX, synth.CY)
-        # tracker: H2D gray in chunks overlapped with extraction; the page-locked CV_16U depth is read under the
-        # keypoints in place (zero-copy gather); D2H keypoints, descriptors, matches
-        trk[k & 1].chain_after(trk[(k + 1) & 1])   # kernels of batch k start when those of batch k-1 are done
-        trk[k & 1].submit_batch_u16(st_gray, st_d16, factor, st_T, outs2[k & 1])
+    def submit(j, p, kp):
+        # mapper first, asynchronously on its own stream: H2D depth (CV_16U) + colour + label of the keyframes only
+        if kp is not None:
+            room = (e2e_k[0] * SUB + p["room"]) % ROOMS
+            pcm.insert_keyframes_u16(kp[0].numpy(), kp[1].numpy(), factor, p["Tkf"][room], synth.FX, synth.FY, synth.CX,
+                                     synth.CY, label=kp[2].numpy())
+        o, n = p["off"], p["n"]
+        trk[j & 1].chain_after(trk[(j + 1) & 1])
+        trk[j & 1].submit_batch_u16(h_gray[o:o + n], h_d16[o:o + n], factor, h_T[o:o + n], tuple(a[:n] for a in outs2[j & 1]))
 
-    def collect(k):
-        trk[k & 1].sync()
-        return outs2[k & 1]
-
-    def run_host(n):
-        submit(0)
-        for k in range(1, n):
-            submit(k)
-            collect(k - 1)
-        o = collect(n - 1)
+    def run_host(nsteps):
+        j = 0
+        last = None
+        for _ in range(nsteps):
+            for p, kp in zip(plan, kf_pins):
+                submit(j, p, kp)
+                if j > 0:
+                    trk[(j - 1) & 1].sync()
+                last = (j & 1, p["n"])
+                j += 1
+            if world > 1:
+                pcm.merge()
+            e2e_k[0] += 1
+        trk[(j - 1) & 1].sync()
         pcm.sync()
-        return o
+        return last
 
-    run_host(3)
+    run_host(1)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(10, args.steps)   # enough batches that filling / draining the two-deep pipeline is amortised
-    out = run_host(e2e_steps)
+    e2e_steps = max(2, min(args.steps, 10))
+    which, nlast = run_host(e2e_steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * F * e2e_steps / float(te.item())
-    kps, desc, nkp, c2l, nm = out
-    # gray + poses + one 32-byte PCIe sector per keypoint of the in-place depth gather + keyframe depth (u16) and colour
-    h2d = gray.nbytes + T.nbytes + int(nkp.sum()) * 32 + p_d16k.numel() * 2 + p_rgbk.numel()
-    d2h = kps.nbytes + desc.nbytes + nkp.nbytes + c2l.nbytes + nm.nbytes
+    e2e_value = frames_step_total * e2e_steps / float(te.item())
+    kps, desc, nkp, c2l, nm = [a[:nlast] for a in outs2[which]]
     n_kp = float(nkp.mean())
-    n_match = float(nm[1:].mean())
+    n_match = float(nm[1:].mean()) if nlast > 1 else 0.0
+    nkf_rank = sum(len(p["kf"]) for p in plan)
+    # per step and rank: gray + poses + one 32-byte sector per keypoint of the in-place depth gather, and per keyframe
+    # depth u16 + colour + label
+    h2d = tracked_frames * (S_IN + 64) + int(n_kp * 32) * tracked_frames + nkf_rank * S_IN * (2 + 3 + 1)
+    d2h = tracked_frames * (st.cap * (28 + 32 + 4) + 8)
+    th2d = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(th2d, op=dist.ReduceOp.SUM)
+    h2d, d2h = int(th2d[0].item()), int(th2d[1].item())
 
     if rank == 0:
         from orb_slam2_ssd_semantic_b200 import _lib
@@ -335,42 +467,58 @@ def run_b200(args):
         ab = algorithmic_bytes(n_kp, n_cand)
         peak, peak_src = measured_peak()
         stages = {}
+        prof_frames = max(prof_frames, 1)
         for k, v in stage_ms.items():
-            per_launch_ms = v / max(prof_runs, 1)
-            gbs = ab[k] * F / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-            stages[k] = {"ms_per_step": per_launch_ms, "algorithmic_bytes_per_frame": ab[k], "gbs": gbs,
-                         "frac": gbs / peak}
-        dom = max(stage_ms, key=lambda k: stage_ms[k])
-        pipe_gbs = pipeline_bytes(n_kp) * F * args.steps / (ms_total * 1e-3) / 1e9
+            gbs = ab[k] * prof_frames / (v * 1e-3) / 1e9 if v > 0 else 0.0
+            stages[k] = {"ms_per_step": v / args.steps, "algorithmic_bytes_per_frame": ab[k], "gbs": gbs, "frac": gbs / peak}
+        if nkf_alone:
+            bmap = map_bytes(pts_sum / max(last_round, 1), touched_sum / max(last_round, 1))
+            gbs = bmap * nkf_alone / (map_alone_ms * 1e-3) / 1e9
+            stages["mapping"] = {"ms_per_step": map_alone_ms, "algorithmic_bytes_per_keyframe": bmap, "gbs": gbs, "frac": gbs / peak,
+                                 "keyframes": nkf_alone, "points_per_keyframe": pts_sum / max(last_round, 1),
+                                 "voxels_updated_per_keyframe": touched_sum / max(last_round, 1),
+                                 "note": "timed alone on the map's stream after the run; in the step it overlaps tracking"}
+        dom = max(stages, key=lambda k: stages[k]["ms_per_step"])
+        pipe_gbs = pipeline_bytes(n_kp) * tracked_frames * args.steps / (ms_total * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": workload_config(args, F),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": workload_config(args, world, frames_step_total),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "batches_in_flight": 2, "steps": e2e_steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": stages[dom]["frac"],
-                         "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * F if dom in NCU_DRAM_BYTES_PER_FRAME else None),
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at 256 "
-                                           "frames/launch (profiles/r01_ncu_v5_summary.txt), scaled to this launch",
-                         "peak_source": peak_src,
+                         "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * prof_frames / max(prof_runs, 1)
+                                     if dom in NCU_DRAM_BYTES_PER_FRAME else None),
+                         "traffic_source": NCU_SOURCE, "peak_source": peak_src,
                          "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
-                                      "algorithmic_bytes_per_frame": pipeline_bytes(n_kp)},
+                                      "algorithmic_bytes_per_frame": pipeline_bytes(n_kp),
+                                      "note": "B_ext + B_match per tracked frame / whole timed region (mapping overlapped)"},
                          "stages": stages},
             "stats": {"keypoints_per_frame": n_kp, "fast_candidates_frame0": n_cand, "matches_per_frame": n_match,
                       "map_leaves": pcm.num_leaves(), "mapping_stream_ms_per_step": map_ms / args.steps,
-                      "keyframes_per_step": len(kfs)},
+                      "frames_tracked_per_step_rank0": tracked_frames, "frames_owned_per_step_rank0": own_frames,
+                      "keyframes_per_step_rank0": nkf_rank, "launches_per_step": launches / args.steps},
         }
+        if world > 1:
+            m = np.array(merge_stats, np.float64).mean(0) if merge_stats else np.zeros(4)
+            line["merge"] = {"collective": "ocm_merge_nccl: AllGather(counts) + grouped Broadcast of 24-byte voxel records, "
+                                           "replayed in rank order", "in_timed_region": True, "per_step": True,
+                             "records_sent_per_step_rank0": m[0], "records_total_per_step": m[1],
+                             "bytes_sent_per_step_rank0": m[2], "bytes_received_per_step_rank0": m[3], "alone": merge_alone}
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             nthreads = min(cores, 64)
-            sample = min(F, max(2 * nthreads, 32))
-            t_cpu = cpu_pipeline(gray[:sample], depth[:sample], rgb[:sample], T[:sample], nthreads)
-            line["cpu_baseline"] = {"value": sample / t_cpu, "unit": "frames/s", "cores": nthreads, "kind": "port",
-                                    "sample": "%d frames, frame-parallel on %d host threads (oracle/ C++ port)" % (sample, nthreads)}
+            w, a, b, kind = cpu_step(gray, depth, rgb, label, T, nthreads, nfeat, 1)
+            nkf = len(range(0, BATCH, KF_EVERY))
+            line["cpu_baseline"] = {"value": BATCH / w, "unit": "frames/s", "cores": nthreads, "kind": kind,
+                                    "sample": "one pass over the %d-frame batch (1/%d of a step), tracking frame-parallel on %d "
+                                              "host threads beside one mapping thread" % (BATCH, SUB, nthreads),
+                                    "tracking_fps": BATCH / a, "mapping_kf_per_s": nkf / b,
+                                    "bottleneck": "tracking" if a > b else "mapping"}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -381,9 +529,9 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--nfeatures", type=int, default=2000, help="ORBextractor nfeatures (configs[2]: 2000; TUM yaml: 1000)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

@@ -36,7 +36,7 @@ EXPORTS = [
     "ocm_last_points", "ocm_num_leaves", "ocm_export_leaves", "ocm_query", "ocm_summary_count",
     "ocm_export_summaries_device", "ocm_apply_summaries_device", "ocm_sync", "ocm_stream", "ocm_launch_count",
     "ocm_insert_keyframes_labeled_device", "ocm_insert_keyframes_u16_labeled", "ocm_merge_nccl", "ocm_nccl_unique_id",
-    "ocm_nccl_comm_create", "ocm_nccl_comm_destroy",
+    "ocm_nccl_comm_create", "ocm_nccl_comm_destroy", "ocm_last_batch_stats",
 ]
 
 
@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
     L.ocm_nccl_unique_id.argtypes = [vp]
     L.ocm_nccl_comm_create.argtypes = [vp, i, i, i, C.POINTER(vp)]
     L.ocm_nccl_comm_destroy.argtypes = [vp]
+    L.ocm_last_batch_stats.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ocm_last_points.argtypes = [vp, vp, vp, i, C.POINTER(i)]
     L.ocm_num_leaves.argtypes = [vp]
     L.ocm_num_leaves.restype = C.c_int64

@@ -1206,6 +1206,21 @@ int ocm_merge_nccl(ocm_t* h, void* comm_, void* stream_, OcmMergeStats* st) {
   return B200ORB_OK;
 }
 
+int ocm_last_batch_stats(ocm_t* h, int64_t* points, int64_t* voxels_touched) {
+  if (!h) { set_error("null argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  std::vector<int> c(4 * ocm::MAX_SLOTS, 0);
+  int nt = 0;
+  B200_CUDA(cudaMemcpyAsync(c.data(), h->d_counters, 16 * ocm::MAX_SLOTS, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(&nt, h->map.ntouched, 4, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  long long p = 0;
+  for (int j = 0; j <= h->last_slot && j < ocm::MAX_SLOTS; ++j) p += c[4 * j + 1];
+  if (points) *points = p;
+  if (voxels_touched) *voxels_touched = nt;
+  return B200ORB_OK;
+}
+
 int ocm_sync(ocm_t* h) {
   if (!h) return B200ORB_EINVAL;
   DeviceGuard g(h->device);

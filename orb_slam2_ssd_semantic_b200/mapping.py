@@ -88,6 +88,12 @@ class PointCloudMapping:
         _lib.check(self._L.ocm_merge_nccl(self._h, comm, C.c_void_p(stream) if stream else None, C.byref(st)))
         return st
 
+    def last_batch_stats(self):
+        """(points, voxels touched) of the last round (<= 32 keyframes) of a batch insert."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _lib.check(self._L.ocm_last_batch_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def UpdateOctomap(self, keyframes):
         """MapDrawer::UpdateOctomap (perfect/src/MapDrawer.cc:610-638): inserts keyframes [lastKeyframeSize, N-1) of the
         list -- the NEWEST keyframe is never inserted (`i < N-1`, :615) -- and remembers N-1.  `keyframes` is the whole
