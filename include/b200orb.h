@@ -216,6 +216,49 @@ int orbm_search_by_bow(orbm_t* h, const OrbmBow* kf, const OrbmBow* f, float nnr
 int orbm_search_by_bow_kf(orbm_t* h, const OrbmBow* kf1, const OrbmBow* kf2, float nnratio, int check_ori,
                           int32_t* matches12, int* nmatches);
 
+/* Per-query best keypoint of a keyframe, with NO claim state: the device part of
+ *   Fuse(KeyFrame*, const vector<MapPoint*>&, th)            src/ORBmatcher.cc:1031-1182   gate 1 (reprojection chi-square,
+ *                                                            :1118-1146: needs q->uright = u - bf*invz and inv_level_sigma2)
+ *   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)       src/ORBmatcher.cc:1198-1318   gate 0
+ *   SearchBySim3 (each direction)                            src/ORBmatcher.cc:1334-1558   gate 0
+ * The caller (shim) projects its MapPoints and passes the distance / viewing-angle gates, PredictScale and the radius
+ * exactly as those loop heads do (queries: u, v, radius, min_level = nPredictedLevel-1, max_level = nPredictedLevel,
+ * descriptor); the device walks KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:659-698), applies the level range and the
+ * gate and returns the FIRST minimum of the Hamming distance: best_idx[i] (-1: no candidate), best_dist[i].  What happens
+ * with a match (Replace / AddObservation / mutual-consistency test) stays with the caller, in the reference's order --
+ * none of it feeds back into later queries' candidate sets. */
+int orbm_search_best(orbm_t* h, const OrbmFrame* kf, const OrbmQueries* q, int gate, const float* inv_level_sigma2,
+                     int32_t* best_idx, int32_t* best_dist);
+
+/* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vector<Point2f>& vbPrevMatched, vector<int>& vnMatches12,
+ * int windowSize) (src/ORBmatcher.cc:523-651).  F1 supplies octave / angle / descriptors, F2 additionally its grid;
+ * prev_xy[n1][2] = vbPrevMatched (in / out); matches12[n1] = vnMatches12. */
+int orbm_search_for_initialization(orbm_t* h, const OrbmFrame* f1, const OrbmFrame* f2, float* prev_xy, int window,
+                                   float nnratio, int check_ori, int32_t* matches12, int* nmatches);
+
+/* ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12, vector<pair<size_t,size_t>>&,
+ * bOnlyStereo) (src/ORBmatcher.cc:827-1019).  Both keyframes flattened with their FeatureVector (as OrbmBow), undistorted
+ * keypoints, right coordinates and MapPoint occupancy; F12 row-major 3x3; (ex, ey) = the epipole the caller computes from
+ * the two poses (:835-839); scale_factors2 / level_sigma2_2 = pKF2->mvScaleFactors / mvLevelSigma2.  matches12[k1->n] =
+ * pKF2 keypoint matched to pKF1 keypoint i or -1 (the caller turns it into vMatchedPairs in index order). */
+typedef struct {
+  int n;
+  const uint8_t* desc;         /* n x 32 */
+  const float* x;              /* mvKeysUn[i].pt */
+  const float* y;
+  const float* angle;
+  const float* uright;         /* mvuRight (>= 0: stereo) */
+  const int32_t* octave;
+  const uint8_t* has_mp;       /* GetMapPoint(i) != NULL */
+  int n_nodes;
+  const uint32_t* node_ids;
+  const int32_t* node_off;
+  const uint32_t* idx;
+} OrbmTriKF;
+int orbm_search_for_triangulation(orbm_t* h, const OrbmTriKF* kf1, const OrbmTriKF* kf2, const float F12[9], float ex,
+                                  float ey, const float* scale_factors2, const float* level_sigma2_2, int nlevels,
+                                  int only_stereo, int check_ori, int32_t* matches12, int* nmatches);
+
 /* ------------------------------------------------------------------------------------------------
  * Stream pipeline (batched many-frame mode of north_star): per frame t of a batch, what
  * Tracking::GrabImageRGBD -> Frame::Frame(RGB-D) -> TrackWithMotionModel's SearchByProjection do

@@ -343,6 +343,116 @@ int match_ref_initialization(const OrbmFrame* F1, const OrbmFrame* F2, float* pr
   return 0;
 }
 
+// The candidate loop that Fuse (src/ORBmatcher.cc:1106-1155, gate 1), Fuse with Sim3 (:1268-1287) and both directions of
+// SearchBySim3 (:1421-1444, :1494-1517) share: KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:659-698: no level filter
+// inside), level range [min_level, max_level] = [nPredictedLevel-1, nPredictedLevel] in the loop, the Fuse reprojection
+// gate, first minimum of the Hamming distance.  No claim state.  best_dist = INT_MAX when there is no candidate.
+int match_ref_best(const OrbmFrame* kf, const OrbmQueries* q, int gate, const float* inv_level_sigma2, int32_t* best_idx,
+                   int32_t* best_dist) {
+  Grid* grid = new Grid();
+  grid->build(kf);
+  std::vector<int> cand;
+  for (int i = 0; i < q->n; ++i) {
+    best_idx[i] = -1; best_dist[i] = 2147483647;
+    if (!q->valid[i]) continue;
+    const float u = q->u[i], v = q->v[i];
+    if (std::isnan(u) || std::isnan(v)) continue;
+    grid->query(u, v, q->radius[i], -1, -1, cand);
+    const uint8_t* dMP = q->desc + 32 * (size_t)i;
+    int bestDist = 2147483647, bestIdx = -1;
+    for (int idx : cand) {
+      const int kpLevel = kf->octave[idx];
+      if (kpLevel < q->min_level[i] || kpLevel > q->max_level[i]) continue;
+      if (gate == 1) {
+        const float kpx = kf->x[idx], kpy = kf->y[idx];
+        if (kf->uright[idx] >= 0) {
+          const float ur = q->uright[i];
+          const float kpr = kf->uright[idx];
+          const float ex = u - kpx, ey = v - kpy, er = ur - kpr;
+          const float e2 = ex * ex + ey * ey + er * er;
+          if (e2 * inv_level_sigma2[kpLevel] > 7.8) continue;
+        } else {
+          const float ex = u - kpx, ey = v - kpy;
+          const float e2 = ex * ex + ey * ey;
+          if (e2 * inv_level_sigma2[kpLevel] > 5.99) continue;
+        }
+      }
+      const int dist = desc_dist(dMP, kf->desc + 32 * (size_t)idx);
+      if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+    }
+    best_idx[i] = bestIdx; best_dist[i] = bestDist;
+  }
+  delete grid;
+  return 0;
+}
+
+// SearchForTriangulation(KeyFrame*, KeyFrame*, cv::Mat F12, vector<pair<size_t,size_t>>&, bOnlyStereo),
+// src/ORBmatcher.cc:827-1019 (+ CheckDistEpipolarLine :175-194).  (ex, ey) = epipole of camera 1 in image 2 (:835-839).
+// The reference never sets vbMatched2, so several pKF1 keypoints may end on the same pKF2 keypoint.
+int match_ref_triangulation(const OrbmTriKF* k1, const OrbmTriKF* k2, const float* F12, float ex, float ey,
+                            const float* sf2, const float* sigma2_2, int only_stereo, int check_ori, int32_t* matches12,
+                            int* nmatches_out) {
+  int nmatches = 0;
+  std::vector<int> vMatches12(k1->n, -1);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  int a = 0, b = 0;
+  while (a < k1->n_nodes && b < k2->n_nodes) {
+    if (k1->node_ids[a] == k2->node_ids[b]) {
+      for (int i1 = k1->node_off[a]; i1 < k1->node_off[a + 1]; ++i1) {
+        const int idx1 = (int)k1->idx[i1];
+        if (k1->has_mp && k1->has_mp[idx1]) continue;
+        const bool bStereo1 = k1->uright[idx1] >= 0;
+        if (only_stereo && !bStereo1) continue;
+        const uint8_t* d1 = k1->desc + 32 * (size_t)idx1;
+        int bestDist = TH_LOW, bestIdx2 = -1;
+        for (int i2 = k2->node_off[b]; i2 < k2->node_off[b + 1]; ++i2) {
+          const int idx2 = (int)k2->idx[i2];
+          if (k2->has_mp && k2->has_mp[idx2]) continue;
+          const bool bStereo2 = k2->uright[idx2] >= 0;
+          if (only_stereo && !bStereo2) continue;
+          const int dist = desc_dist(d1, k2->desc + 32 * (size_t)idx2);
+          if (dist > TH_LOW || dist > bestDist) continue;
+          if (!bStereo1 && !bStereo2) {
+            const float distex = ex - k2->x[idx2], distey = ey - k2->y[idx2];
+            if (distex * distex + distey * distey < 100 * sf2[k2->octave[idx2]]) continue;
+          }
+          // CheckDistEpipolarLine
+          const float x1 = k1->x[idx1], y1 = k1->y[idx1];
+          const float la = x1 * F12[0] + y1 * F12[3] + F12[6];
+          const float lb = x1 * F12[1] + y1 * F12[4] + F12[7];
+          const float lc = x1 * F12[2] + y1 * F12[5] + F12[8];
+          const float num = la * k2->x[idx2] + lb * k2->y[idx2] + lc;
+          const float den = la * la + lb * lb;
+          if (den == 0) continue;
+          const float dsqr = num * num / den;
+          if (dsqr < 3.84 * sigma2_2[k2->octave[idx2]]) { bestIdx2 = idx2; bestDist = dist; }
+        }
+        if (bestIdx2 >= 0) {
+          vMatches12[idx1] = bestIdx2;
+          nmatches++;
+          if (check_ori) rotHist[rot_bin(k1->angle[idx1], k2->angle[bestIdx2])].push_back(idx1);
+        }
+      }
+      ++a; ++b;
+    } else if (k1->node_ids[a] < k2->node_ids[b]) {
+      a = (int)(std::lower_bound(k1->node_ids, k1->node_ids + k1->n_nodes, k2->node_ids[b]) - k1->node_ids);
+    } else {
+      b = (int)(std::lower_bound(k2->node_ids, k2->node_ids + k2->n_nodes, k1->node_ids[a]) - k2->node_ids);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; ++i) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) { vMatches12[idx1] = -1; nmatches--; }
+    }
+  }
+  for (int i = 0; i < k1->n; ++i) matches12[i] = vMatches12[i];
+  *nmatches_out = nmatches;
+  return 0;
+}
+
 // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:217-363
 int match_ref_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
                   int* nmatches_out) {

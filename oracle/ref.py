@@ -565,3 +565,246 @@ def src_pipeline_run(gray, depth, Tcw, nthreads, nfeatures=1000, scale=1.2, nlev
     sec = L.refsrc_pipeline_run(_p(gray), _p(depth), _p(T), n, rows, cols, nfeatures, scale, nlevels, ini_th, min_th, fx,
                                 fy, cx, cy, bf, th, nnratio, int(check_ori), nthreads, _p(nkp), _p(nm))
     return sec, nkp, nm
+
+
+# ------------------------------------------------------------------------------------------------
+# flat oracles of the remaining matcher members + their reference-source / shim counterparts
+class RefMapPoints(C.Structure):
+    _fields_ = [("n", C.c_int), ("valid", C.c_void_p), ("bad", C.c_void_p), ("xw", C.c_void_p), ("normal", C.c_void_p),
+                ("min_dist", C.c_void_p), ("max_dist", C.c_void_p), ("desc", C.c_void_p), ("obs", C.c_void_p)]
+
+
+class MapPointsView:
+    def __init__(self, xw, desc, valid=None, bad=None, normal=None, min_dist=None, max_dist=None, obs=None):
+        f = lambda a, t: None if a is None else np.ascontiguousarray(a, t)
+        self.xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+        self.n = len(self.xw)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.valid, self.bad = f(valid, np.uint8), f(bad, np.uint8)
+        self.normal = None if normal is None else np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+        self.min_dist, self.max_dist, self.obs = f(min_dist, np.float32), f(max_dist, np.float32), f(obs, np.int32)
+
+    def struct(self):
+        s = RefMapPoints()
+        s.n = self.n
+        g = lambda a: None if a is None else a.ctypes.data
+        s.valid, s.bad, s.xw, s.normal = g(self.valid), g(self.bad), g(self.xw), g(self.normal)
+        s.min_dist, s.max_dist, s.desc, s.obs = g(self.min_dist), g(self.max_dist), g(self.desc), g(self.obs)
+        return s
+
+
+def search_best(KF, queries, gate=0, inv_level_sigma2=None):
+    from orb_slam2_ssd_semantic_b200 import _abi
+    L = _mlib()
+    L.match_ref_best.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmQueries), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    bi = np.full(max(queries.n, 1), -1, np.int32)
+    bd = np.full(max(queries.n, 1), 2 ** 31 - 1, np.int32)
+    ks, qs = KF.struct(), queries.struct()
+    is2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+    L.match_ref_best(C.byref(ks), C.byref(qs), int(gate), None if is2 is None else _p(is2), _p(bi), _p(bd))
+    return bi[:queries.n], bd[:queries.n]
+
+
+def search_for_triangulation(k1, k2, F12, epipole, sf2, sigma2_2, only_stereo=False, check_ori=True):
+    from orb_slam2_ssd_semantic_b200 import _abi
+    L = _mlib()
+    L.match_ref_triangulation.argtypes = [C.POINTER(_abi.OrbmTriKF), C.POINTER(_abi.OrbmTriKF), C.c_void_p, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf = np.ascontiguousarray(sf2, np.float32)
+    s2 = np.ascontiguousarray(sigma2_2, np.float32)
+    out = np.full(max(k1.n, 1), -1, np.int32)
+    nm = C.c_int(0)
+    a, b = k1.struct(), k2.struct()
+    L.match_ref_triangulation(C.byref(a), C.byref(b), _p(F), float(epipole[0]), float(epipole[1]), _p(sf), _p(s2),
+                              int(only_stereo), int(check_ori), _p(out), C.byref(nm))
+    return nm.value, out[:k1.n]
+
+
+_SHIMSO = os.path.join(_HERE, "_ref", "libshimsrc.so")
+_shimlib = None
+
+
+def shimlib() -> C.CDLL:
+    """oracle/_ref/libshimsrc.so: the reference's Frame.cc / KeyFrame.cc / MapPoint.cc compiled against the B200 shims
+    (needs a GPU at run time)."""
+    global _shimlib
+    if _shimlib is None:
+        if not os.path.exists(_SHIMSO):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "shim"])
+        _shimlib = C.CDLL(_SHIMSO)
+    return _shimlib
+
+
+class SrcMembers:
+    """The remaining ORBmatcher members run on real Frame / KeyFrame / MapPoint graphs: prefix 'refsrc' = the reference's
+    own ORBmatcher.cc, prefix 'shimsrc' = the B200 shim class on the same reference objects."""
+
+    def __init__(self, prefix="refsrc"):
+        self.L = reflib() if prefix == "refsrc" else shimlib()
+        self.p = prefix
+
+    def _f(self, name):
+        return getattr(self.L, self.p + "_" + name)
+
+    def search_by_projection_last(self, cur, last, th, mono=False, nnratio=0.9, check_ori=True):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("projection_last")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmLast), C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        out = np.full(cur.n, -1, np.int32)
+        nm = C.c_int(0)
+        cs, ls = cur.struct(), last.struct()
+        f(C.byref(cs), C.byref(ls), float(th), int(mono), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+        return nm.value, out
+
+    def search_by_projection_points(self, F, pts, th, nnratio=0.8):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("projection_points")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmTrackPoints), C.c_float, C.c_float, C.c_void_p, C.POINTER(C.c_int)]
+        out = np.full(F.n, -1, np.int32)
+        nm = C.c_int(0)
+        fs, ps = F.struct(), pts.struct()
+        f(C.byref(fs), C.byref(ps), float(th), float(nnratio), _p(out), C.byref(nm))
+        return nm.value, out
+
+    def search_by_bow(self, kf, fr, nnratio=0.7, check_ori=True, kfkf=False):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("bow_kf" if kfkf else "bow")
+        f.argtypes = [C.POINTER(_abi.OrbmBow), C.POINTER(_abi.OrbmBow), C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        out = np.full(kf.n if kfkf else fr.n, -1, np.int32)
+        nm = C.c_int(0)
+        a, b = kf.struct(), fr.struct()
+        f(C.byref(a), C.byref(b), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+        return nm.value, out
+
+    def search_for_initialization(self, F1, F2, prev_xy, window=100, nnratio=0.9, check_ori=True):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("initialization")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmFrame), C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        prev = np.ascontiguousarray(prev_xy, np.float32).reshape(-1, 2).copy()
+        out = np.full(F1.n, -1, np.int32)
+        nm = C.c_int(0)
+        a, b = F1.struct(), F2.struct()
+        f(C.byref(a), C.byref(b), _p(prev), int(window), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+        return nm.value, out, prev
+
+    def projection_kf(self, cur, kf, kf_mps, already_found, th, orb_dist, nnratio=0.9, check_ori=True):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("projection_kf")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmFrame), C.POINTER(RefMapPoints), C.c_void_p, C.c_float, C.c_int,
+                      C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+        out = np.full(cur.n, -1, np.int32)
+        nm = C.c_int(0)
+        cs, ks, ms = cur.struct(), kf.struct(), kf_mps.struct()
+        af = np.ascontiguousarray(already_found, np.uint8)
+        f(C.byref(cs), C.byref(ks), C.byref(ms), _p(af), float(th), int(orb_dist), float(nnratio), int(check_ori), _p(out), C.byref(nm))
+        return nm.value, out
+
+    def projection_sim3(self, kf, Scw, pts, matched, th):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("projection_sim3")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.c_void_p, C.POINTER(RefMapPoints), C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        m = np.ascontiguousarray(matched, np.int32).copy()
+        S = np.ascontiguousarray(Scw, np.float32).reshape(16)
+        nm = C.c_int(0)
+        ks, ps = kf.struct(), pts.struct()
+        f(C.byref(ks), _p(S), C.byref(ps), _p(m), int(th), C.byref(nm))
+        return nm.value, m
+
+    def fuse(self, kf, kf_mps, pts, in_kf, th, depth=None):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("fuse")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(RefMapPoints), C.POINTER(RefMapPoints), C.c_void_p, C.c_float, C.c_void_p,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        slot = np.full(kf.n, -1, np.int32)
+        rep = np.full(pts.n, -1, np.int32)
+        krep = np.full(kf.n, -1, np.int32)
+        nm = C.c_int(0)
+        ks, ms, ps = kf.struct(), kf_mps.struct(), pts.struct()
+        ik = np.ascontiguousarray(in_kf, np.uint8)
+        f(C.byref(ks), C.byref(ms), C.byref(ps), _p(ik), float(th), None, _p(slot), _p(rep), _p(krep), C.byref(nm))
+        return nm.value, slot, rep, krep
+
+    def fuse_sim3(self, kf, kf_mps, Scw, pts, th):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("fuse_sim3")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(RefMapPoints), C.c_void_p, C.POINTER(RefMapPoints), C.c_float, C.c_void_p,
+                      C.c_void_p, C.POINTER(C.c_int)]
+        slot = np.full(kf.n, -1, np.int32)
+        rep = np.full(pts.n, -1, np.int32)
+        nm = C.c_int(0)
+        S = np.ascontiguousarray(Scw, np.float32).reshape(16)
+        ks, ms, ps = kf.struct(), kf_mps.struct(), pts.struct()
+        f(C.byref(ks), C.byref(ms), _p(S), C.byref(ps), float(th), _p(slot), _p(rep), C.byref(nm))
+        return nm.value, slot, rep
+
+    def search_by_sim3(self, kf1, kf2, mp1, mp2, matches12, s12, R12, t12, th):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("search_by_sim3")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmFrame), C.POINTER(RefMapPoints), C.POINTER(RefMapPoints), C.c_void_p,
+                      C.c_float, C.c_void_p, C.c_void_p, C.c_float, C.POINTER(C.c_int)]
+        m = np.ascontiguousarray(matches12, np.int32).copy()
+        R = np.ascontiguousarray(R12, np.float32).reshape(9)
+        t = np.ascontiguousarray(t12, np.float32).reshape(3)
+        nm = C.c_int(0)
+        a, b, p1, p2 = kf1.struct(), kf2.struct(), mp1.struct(), mp2.struct()
+        f(C.byref(a), C.byref(b), C.byref(p1), C.byref(p2), _p(m), float(s12), _p(R), _p(t), float(th), C.byref(nm))
+        return nm.value, m
+
+    def triangulation(self, k1, k2, Tcw1, Tcw2, cam, F12, only_stereo=False, nnratio=0.6, check_ori=True):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("triangulation")
+        f.argtypes = [C.POINTER(_abi.OrbmTriKF), C.POINTER(_abi.OrbmTriKF), C.c_void_p, C.c_void_p, C.POINTER(_abi.OrbmFrame), C.c_void_p,
+                      C.c_int, C.c_float, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]
+        out = np.full(max(k1.n, 1), -1, np.int32)
+        ep = np.zeros(2, np.float32)
+        nm = C.c_int(0)
+        a, b, cs = k1.struct(), k2.struct(), cam.struct()
+        T1 = np.ascontiguousarray(Tcw1, np.float32).reshape(16)
+        T2 = np.ascontiguousarray(Tcw2, np.float32).reshape(16)
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        f(C.byref(a), C.byref(b), _p(T1), _p(T2), C.byref(cs), _p(F), int(only_stereo), float(nnratio), int(check_ori), _p(out),
+          C.byref(nm), _p(ep))
+        return nm.value, out[:k1.n], ep
+
+    def kf_best(self, kf, queries):
+        from orb_slam2_ssd_semantic_b200 import _abi
+        f = self._f("kf_best")
+        f.argtypes = [C.POINTER(_abi.OrbmFrame), C.POINTER(_abi.OrbmQueries), C.c_void_p, C.c_void_p]
+        bi = np.full(max(queries.n, 1), -1, np.int32)
+        bd = np.full(max(queries.n, 1), 2 ** 31 - 1, np.int32)
+        ks, qs = kf.struct(), queries.struct()
+        f(C.byref(ks), C.byref(qs), _p(bi), _p(bd))
+        return bi[:queries.n], bd[:queries.n]
+
+    def frame_rgbd(self, gray, depth, Tcw, fx, fy, cx, cy, bf, nfeatures=1000):
+        f = self._f("frame_rgbd")
+        f.argtypes = ([C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_void_p] +
+                      [C.c_float] * 5 + [C.c_void_p] * 7 + [C.c_int, C.c_void_p])
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        cap = nfeatures + 16 * 8 + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        ur, dp, xw, va = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros((cap, 3), np.float32), np.zeros(cap, np.uint8)
+        n = C.c_int(0)
+        rc = f(_p(gray), _p(depth), gray.shape[0], gray.shape[1], nfeatures, 1.2, 8, 20, 7, _p(T), fx, fy, cx, cy, bf, None,
+               _p(kps), _p(desc), _p(ur), _p(dp), _p(xw), _p(va), cap, C.byref(n))
+        assert rc == 0
+        m = n.value
+        return kps[:m].copy(), desc[:m].copy(), ur[:m].copy(), dp[:m].copy(), xw[:m].copy(), va[:m].copy()
+
+    def pipeline_run(self, gray, depth, Tcw, nthreads, nfeatures, fx, fy, cx, cy, bf, th=15.0, nnratio=0.9):
+        f = self._f("pipeline_run")
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_int, C.c_float, C.c_int, C.c_int, C.c_int] + [C.c_float] * 7 + \
+            [C.c_int] * 2 + [C.c_void_p] * 2
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.float32)
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(-1, 16)
+        n, rows, cols = gray.shape
+        nkp, nm = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        sec = f(_p(gray), _p(depth), _p(T), n, rows, cols, nfeatures, 1.2, 8, 20, 7, fx, fy, cx, cy, bf, th, nnratio, 1, nthreads,
+                _p(nkp), _p(nm))
+        return sec, nkp, nm

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../include/b200orb.h"
+#include "refsrc_api.h"
 
 #define private public
 #define protected public
@@ -47,6 +48,15 @@ void KeyFrameDatabase::erase(KeyFrame*) {}
 
 using namespace ORB_SLAM2;
 
+// The same harness is compiled twice: against the reference's own ORBextractor / ORBmatcher (exports refsrc_*) and, with
+// -DREFSRC_SHIM and the B200 shim headers shadowing include/ORBextractor.h and include/ORBmatcher.h, against the shims
+// (exports shimsrc_*): the reference's Frame.cc / KeyFrame.cc / MapPoint.cc then run unchanged on top of libb200orb.so.
+#ifdef REFSRC_SHIM
+#define X(name) shimsrc_##name
+#else
+#define X(name) refsrc_##name
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Monotonic storage for the quad-tree's list nodes.  DistributeOctTree orders equal-size nodes by their HEAP ADDRESS
 // (src/ORBextractor.cc:686 sorts pair<int, ExtractorNode*>), so the reference's keypoint order depends on the allocator
@@ -55,7 +65,11 @@ using namespace ORB_SLAM2;
 // deterministic, and the rule the restatement and the kernels document ("later-created node first").
 // Bound inside this library only (-Wl,-Bsymbolic); everything else goes to malloc/free.
 namespace {
+#ifdef REFSRC_SHIM
+const size_t kNodeBytes = 0;   // no quad-tree on the host in the shim build
+#else
 const size_t kNodeBytes = sizeof(std::_List_node<ExtractorNode>);
+#endif
 const size_t kArenaBytes = 16u << 20;          // one per thread that extracts (a frame needs ~2 MB of list nodes)
 const int kMaxArenas = 512;
 char* g_arenas[kMaxArenas];
@@ -73,7 +87,7 @@ inline void arena_reset() {
 }
 }  // namespace
 void* operator new(size_t n) {
-  if (t_arena_on && n == kNodeBytes && t_arena_used + ((n + 15) & ~size_t(15)) <= kArenaBytes) {
+  if (t_arena_on && kNodeBytes && n == kNodeBytes && t_arena_used + ((n + 15) & ~size_t(15)) <= kArenaBytes) {
     void* p = t_arena + t_arena_used;
     t_arena_used += (n + 15) & ~size_t(15);
     return p;
@@ -219,11 +233,11 @@ extern "C" {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // ORBextractor (src/ORBextractor.cc, whole file)
-void* refsrc_orb_create(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
+void* X(orb_create)(int nfeatures, float scaleFactor, int nlevels, int iniTh, int minTh) {
   return new ORBextractor(nfeatures, scaleFactor, nlevels, iniTh, minTh);
 }
-void refsrc_orb_destroy(void* h) { delete (ORBextractor*)h; }
-int refsrc_orb_extract(void* h, const uint8_t* img, int rows, int cols, int stride, void* kps, uint8_t* desc, int cap,
+void X(orb_destroy)(void* h) { delete (ORBextractor*)h; }
+int X(orb_extract)(void* h, const uint8_t* img, int rows, int cols, int stride, void* kps, uint8_t* desc, int cap,
                        int* n_out) {
   ORBextractor* e = (ORBextractor*)h;
   std::lock_guard<std::mutex> lk(g_mu);
@@ -241,7 +255,8 @@ int refsrc_orb_extract(void* h, const uint8_t* img, int rows, int cols, int stri
   }
   return 0;
 }
-void refsrc_orb_tables(void* h, float* sf, float* invsf, float* sigma2, float* invsigma2, int* nfeat, int* umax) {
+#ifndef REFSRC_SHIM   // internals of the reference's extractor class (the shim has its own, C-ABI backed, members)
+void X(orb_tables)(void* h, float* sf, float* invsf, float* sigma2, float* invsigma2, int* nfeat, int* umax) {
   ORBextractor* e = (ORBextractor*)h;
   for (int l = 0; l < e->nlevels; ++l) {
     sf[l] = e->mvScaleFactor[l]; invsf[l] = e->mvInvScaleFactor[l]; sigma2[l] = e->mvLevelSigma2[l];
@@ -249,14 +264,14 @@ void refsrc_orb_tables(void* h, float* sf, float* invsf, float* sigma2, float* i
   }
   for (int v = 0; v < 16; ++v) umax[v] = e->umax[v];
 }
-int refsrc_orb_level_dims(void* h, int level, int* w, int* hgt) {
+int X(orb_level_dims)(void* h, int level, int* w, int* hgt) {
   ORBextractor* e = (ORBextractor*)h;
   if (level < 0 || level >= e->nlevels || e->mvImagePyramid[level].empty()) return -1;
   *w = e->mvImagePyramid[level].cols; *hgt = e->mvImagePyramid[level].rows;
   return 0;
 }
 // mvImagePyramid[level]; bordered=1 returns the (w+38)x(h+38) parent buffer the ROI lives in (src/ORBextractor.cc:1125-1129)
-void refsrc_orb_get_level(void* h, int level, int bordered, uint8_t* dst) {
+void X(orb_get_level)(void* h, int level, int bordered, uint8_t* dst) {
   ORBextractor* e = (ORBextractor*)h;
   const cv::Mat& m = e->mvImagePyramid[level];
   const int B = bordered ? 19 : 0;
@@ -265,7 +280,7 @@ void refsrc_orb_get_level(void* h, int level, int bordered, uint8_t* dst) {
   for (int y = 0; y < H; ++y) memcpy(dst + (size_t)y * W, base + (size_t)y * m.step, (size_t)W);
 }
 // ORBextractor::DistributeOctTree (src/ORBextractor.cc:540-765) on a caller-supplied candidate list
-int refsrc_orb_distribute(const void* in, int n_in, int minX, int maxX, int minY, int maxY, int N, void* out, int cap) {
+int X(orb_distribute)(const void* in, int n_in, int minX, int maxX, int minY, int maxY, int N, void* out, int cap) {
   std::lock_guard<std::mutex> lk(g_mu);
   arena_reset();
   ORBextractor e(std::max(N, 1), 1.2f, 8, 20, 7);
@@ -276,12 +291,14 @@ int refsrc_orb_distribute(const void* in, int n_in, int minX, int maxX, int minY
   return (int)r.size();
 }
 
+#endif   // !REFSRC_SHIM
+
 // ---------------------------------------------------------------------------------------------------------------------
 // ORBmatcher (src/ORBmatcher.cc) -- same signatures as match_ref_* in oracle/match_ref.cpp
-int refsrc_hamming(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }
+int X(hamming)(const uint8_t* a, const uint8_t* b) { return ORBmatcher::DescriptorDistance(desc_row(a), desc_row(b)); }
 
 // SearchByProjection(Frame&, const Frame&, th, bMono), src/ORBmatcher.cc:1578-1724
-int refsrc_projection_last(const OrbmFrame* cur, const OrbmLast* last, float th, int mono, float nnratio, int check_ori,
+int X(projection_last)(const OrbmFrame* cur, const OrbmLast* last, float th, int mono, float nnratio, int check_ori,
                            int32_t* cur2last, int* nmatches_out) {
   std::lock_guard<std::mutex> lk(g_mu);
   std::map<MapPoint*, int> id;
@@ -311,7 +328,7 @@ int refsrc_projection_last(const OrbmFrame* cur, const OrbmLast* last, float th,
 }
 
 // SearchByProjection(Frame&, const vector<MapPoint*>&, th), src/ORBmatcher.cc:63-156
-int refsrc_projection_points(const OrbmFrame* F, const OrbmTrackPoints* pts, float th, float nnratio, int32_t* f2pt,
+int X(projection_points)(const OrbmFrame* F, const OrbmTrackPoints* pts, float th, float nnratio, int32_t* f2pt,
                              int* nmatches_out) {
   std::lock_guard<std::mutex> lk(g_mu);
   std::map<MapPoint*, int> id;
@@ -336,7 +353,7 @@ int refsrc_projection_points(const OrbmFrame* F, const OrbmTrackPoints* pts, flo
 }
 
 // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:217-363
-int refsrc_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf, int* nmatches_out) {
+int X(bow)(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf, int* nmatches_out) {
   std::lock_guard<std::mutex> lk(g_mu);
   std::map<MapPoint*, int> id;
   make_point(nullptr, nullptr, 0);
@@ -359,7 +376,7 @@ int refsrc_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori
 }
 
 // SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&), src/ORBmatcher.cc:665-812
-int refsrc_bow_kf(const OrbmBow* k1, const OrbmBow* k2, float nnratio, int check_ori, int32_t* matches12, int* nmatches_out) {
+int X(bow_kf)(const OrbmBow* k1, const OrbmBow* k2, float nnratio, int check_ori, int32_t* matches12, int* nmatches_out) {
   std::lock_guard<std::mutex> lk(g_mu);
   std::map<MapPoint*, int> id;
   make_point(nullptr, nullptr, 0);
@@ -387,7 +404,7 @@ int refsrc_bow_kf(const OrbmBow* k1, const OrbmBow* k2, float nnratio, int check
 }
 
 // SearchForInitialization(Frame&, Frame&, vector<Point2f>&, vector<int>&, windowSize), src/ORBmatcher.cc:523-651
-int refsrc_initialization(const OrbmFrame* f1, const OrbmFrame* f2, float* prev_xy, int window, float nnratio, int check_ori,
+int X(initialization)(const OrbmFrame* f1, const OrbmFrame* f2, float* prev_xy, int window, float nnratio, int check_ori,
                           int32_t* matches12, int* nmatches_out) {
   std::lock_guard<std::mutex> lk(g_mu);
   Frame* F1 = make_frame(f1);
@@ -406,7 +423,7 @@ int refsrc_initialization(const OrbmFrame* f1, const OrbmFrame* f2, float* prev_
 // Frame glue through the REAL RGB-D constructor (src/Frame.cc:176-240): ExtractORB, UndistortKeyPoints,
 // ComputeStereoFromRGBD (:850-871), AssignFeaturesToGrid, then UnprojectStereo (:879-899) per keypoint.
 // depth f32 metres.  Outputs per keypoint: cv::KeyPoint (mvKeysUn), descriptor, uRight, depth, world point, valid.
-int refsrc_frame_rgbd(const uint8_t* gray, const float* depth, int rows, int cols, int nfeatures, float scaleFactor,
+int X(frame_rgbd)(const uint8_t* gray, const float* depth, int rows, int cols, int nfeatures, float scaleFactor,
                       int nlevels, int iniTh, int minTh, const float* Tcw, float fx, float fy, float cx, float cy,
                       float bf, const float* dist4, void* kps_un, uint8_t* desc, float* uright, float* kdepth, float* xw,
                       uint8_t* valid, int cap, int* n_out) {
@@ -441,7 +458,7 @@ int refsrc_frame_rgbd(const uint8_t* gray, const float* depth, int rows, int col
 // ORBmatcher::SearchByProjection(cur, last, th, false).  Frame-parallel on `nthreads` threads (one ORBextractor per thread,
 // like src/Frame.cc:121-124); Frame's statics are written once before the threads start.  depth f32 metres.
 // Returns seconds (steady_clock, like perfect/Examples/RGB-D/rgbd_tum.cc:92-111).
-double refsrc_pipeline_run(const uint8_t* gray, const float* depth, const float* Tcw, int n, int rows, int cols, int nfeatures,
+double X(pipeline_run)(const uint8_t* gray, const float* depth, const float* Tcw, int n, int rows, int cols, int nfeatures,
                            float scaleFactor, int nlevels, int iniTh, int minTh, float fx, float fy, float cx, float cy,
                            float bf, float th, float nnratio, int check_ori, int nthreads, int* nkp, int* nmatch) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -511,7 +528,7 @@ double refsrc_pipeline_run(const uint8_t* gray, const float* depth, const float*
 
 // Frame::isInFrustum (src/Frame.cc:387-451) for a list of world points with given normal / distance bounds.
 // out per point: in_view, proj_x, proj_y, proj_xr, scale_level, view_cos
-int refsrc_is_in_frustum(const OrbmFrame* f, int n, const float* xw, const float* normal, const float* min_dist,
+int X(is_in_frustum)(const OrbmFrame* f, int n, const float* xw, const float* normal, const float* min_dist,
                          const float* max_dist, float viewing_cos_limit, uint8_t* in_view, float* proj_x, float* proj_y,
                          float* proj_xr, int32_t* scale_level, float* view_cos) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -529,6 +546,255 @@ int refsrc_is_in_frustum(const OrbmFrame* f, int n, const float* xw, const float
     delete mp;
   }
   delete F;
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The remaining ORBmatcher members on real KeyFrame / MapPoint graphs
+namespace {
+struct Points {
+  std::vector<MapPoint*> v;
+  std::map<MapPoint*, int> id;
+  ~Points() { for (auto p : v) delete p; }
+};
+void make_points(const RefMapPoints* r, Points& out, int id_base = 0) {
+  out.v.assign(r->n, static_cast<MapPoint*>(NULL));
+  for (int i = 0; i < r->n; ++i) {
+    if (r->valid && !r->valid[i]) continue;
+    MapPoint* mp = make_point(r->xw + 3 * i, r->desc ? r->desc + 32 * (size_t)i : nullptr, r->obs ? r->obs[i] : 1);
+    if (r->normal) memcpy(mp->mNormalVector.data, r->normal + 3 * i, 12);
+    mp->mfMinDistance = r->min_dist ? r->min_dist[i] : 0.f;
+    mp->mfMaxDistance = r->max_dist ? r->max_dist[i] : 1e9f;
+    if (r->bad && r->bad[i]) mp->mbBad = true;
+    out.v[i] = mp; out.id[mp] = id_base + i;
+  }
+}
+// KeyFrame from a flat frame view whose keypoint j holds MapPoint kfmp.v[j] (registered as an observation so that
+// Replace / IsInKeyFrame / GetIndexInKeyFrame work on the real graph)
+KeyFrame* make_keyframe(const OrbmFrame* f, Points* kfmp, Frame** keep, const float* depth = nullptr) {
+  Frame* F = make_frame(f, depth);
+  KeyFrame* K = new KeyFrame(*F, &g_map, nullptr);
+  if (kfmp)
+    for (int j = 0; j < f->n && j < (int)kfmp->v.size(); ++j)
+      if (kfmp->v[j]) {
+        K->AddMapPoint(kfmp->v[j], j);
+        const int keep_obs = kfmp->v[j]->nObs;
+        kfmp->v[j]->AddObservation(K, j);
+        kfmp->v[j]->nObs = keep_obs;          // Observations() as the view states it
+      }
+  *keep = F;
+  return K;
+}
+}  // namespace
+
+// SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist), src/ORBmatcher.cc:1757-1899 (relocalisation).
+// kf_mps: one entry per keyframe keypoint; already_found[i] != 0 puts that MapPoint into sAlreadyFound.
+int X(projection_kf)(const OrbmFrame* cur, const OrbmFrame* kf, const RefMapPoints* kf_mps, const uint8_t* already_found,
+                     float th, int orb_dist, float nnratio, int check_ori, int32_t* cur2kf, int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  Points P;
+  make_points(kf_mps, P);
+  Frame* FK;
+  KeyFrame* K = make_keyframe(kf, &P, &FK);
+  Frame* C = make_frame(cur);
+  Points pre;
+  std::map<MapPoint*, int> id = P.id;
+  seed_existing(C, cur, id);
+  restore_statics(cur);
+  std::set<MapPoint*> found;
+  for (int i = 0; i < kf_mps->n; ++i)
+    if (already_found && already_found[i] && P.v[i]) found.insert(P.v[i]);
+  ORBmatcher m(nnratio, check_ori != 0);
+  *nmatches_out = m.SearchByProjection(*C, K, found, th, orb_dist);
+  flatten(C->mvpMapPoints, id, cur2kf);
+  for (auto& kv : id) if (!P.id.count(kv.first)) delete kv.first;
+  delete C; delete K; delete FK;
+  return 0;
+}
+
+// SearchByProjection(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, vector<MapPoint*>& vpMatched, int th),
+// src/ORBmatcher.cc:378-498 (loop closing).  matched_io[kf->n]: index into pts of the MapPoint already matched to the
+// keypoint, -1 none, -2 some MapPoint that is not in pts; updated in place.
+int X(projection_sim3)(const OrbmFrame* kf, const float* Scw, const RefMapPoints* pts, int32_t* matched_io, int th,
+                       int* nmatches_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  Points P;
+  make_points(pts, P);
+  for (int i = 0; i < pts->n; ++i)   // the reference dereferences every entry (:408-409): a missing point becomes a bad one
+    if (!P.v[i]) { P.v[i] = make_point(nullptr, nullptr, 1); P.v[i]->mbBad = true; P.id[P.v[i]] = i; }
+  Frame* FK;
+  KeyFrame* K = make_keyframe(kf, nullptr, &FK);
+  restore_statics(kf);
+  std::vector<MapPoint*> vpMatched(kf->n, static_cast<MapPoint*>(NULL));
+  std::map<MapPoint*, int> id = P.id;
+  std::vector<MapPoint*> others;
+  for (int j = 0; j < kf->n; ++j) {
+    if (matched_io[j] >= 0) vpMatched[j] = P.v[matched_io[j]];
+    else if (matched_io[j] == -2) { MapPoint* o = make_point(nullptr, nullptr, 1); others.push_back(o); id[o] = -2; vpMatched[j] = o; }
+  }
+  ORBmatcher m(0.75f, true);
+  *nmatches_out = m.SearchByProjection(K, mat44(Scw), P.v, vpMatched, th);
+  flatten(vpMatched, id, matched_io);
+  for (auto o : others) delete o;
+  delete K; delete FK;
+  return 0;
+}
+
+// Fuse(KeyFrame*, const vector<MapPoint*>&, th), src/ORBmatcher.cc:1031-1182.  kf_mps: the keyframe's own MapPoints (one
+// per keypoint, valid = 0 where none); pts: the candidates; in_kf[i] != 0 makes candidate i an observation of the keyframe
+// already (IsInKeyFrame).  Outputs: slot_owner[kf->n] = who sits on each keypoint afterwards (-1 nobody, i = candidate i,
+// 1000000 + j = the keyframe's original MapPoint j), replaced_by[pts->n] = same coding for GetReplaced() of candidate i
+// (-1: not replaced), kf_replaced_by[kf->n] likewise for the original MapPoints.
+int X(fuse)(const OrbmFrame* kf, const RefMapPoints* kf_mps, const RefMapPoints* pts, const uint8_t* in_kf, float th,
+            const float* depth, int32_t* slot_owner, int32_t* replaced_by, int32_t* kf_replaced_by, int* nfused_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  Points KP, P;
+  make_points(kf_mps, KP, 1000000);
+  make_points(pts, P, 0);
+  Frame* FK;
+  KeyFrame* K = make_keyframe(kf, &KP, &FK, depth);
+  restore_statics(kf);
+  // a far-away second keyframe holds the candidates flagged in_kf?  No: IsInKeyFrame(pKF) must be true for THIS keyframe:
+  // register the observation on a keypoint slot that holds nobody (the flag only has to exist)
+  for (int i = 0; i < pts->n; ++i)
+    if (in_kf && in_kf[i] && P.v[i]) { const int keep = P.v[i]->nObs; P.v[i]->mObservations[K] = (size_t)0; P.v[i]->nObs = keep; }
+  ORBmatcher m(0.6f, true);
+  *nfused_out = m.Fuse(K, P.v, th);
+  std::map<MapPoint*, int> id = P.id;
+  id.insert(KP.id.begin(), KP.id.end());
+  const std::vector<MapPoint*> now = K->GetMapPointMatches();
+  for (int j = 0; j < kf->n; ++j) slot_owner[j] = now[j] ? id.at(now[j]) : -1;
+  for (int i = 0; i < pts->n; ++i) { MapPoint* r = P.v[i] ? P.v[i]->GetReplaced() : nullptr; replaced_by[i] = r ? id.at(r) : -1; }
+  for (int j = 0; j < kf->n; ++j) { MapPoint* r = KP.v[j] ? KP.v[j]->GetReplaced() : nullptr; kf_replaced_by[j] = r ? id.at(r) : -1; }
+  delete K; delete FK;
+  return 0;
+}
+
+// Fuse(KeyFrame*, cv::Mat Scw, const vector<MapPoint*>&, float th, vector<MapPoint*>& vpReplacePoint),
+// src/ORBmatcher.cc:1198-1318.  replace_out[pts->n]: 1000000 + j when vpReplacePoint[i] is the keyframe's MapPoint j.
+int X(fuse_sim3)(const OrbmFrame* kf, const RefMapPoints* kf_mps, const float* Scw, const RefMapPoints* pts, float th,
+                 int32_t* slot_owner, int32_t* replace_out, int* nfused_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  Points KP, P;
+  make_points(kf_mps, KP, 1000000);
+  make_points(pts, P, 0);
+  Frame* FK;
+  KeyFrame* K = make_keyframe(kf, &KP, &FK);
+  restore_statics(kf);
+  std::vector<MapPoint*> rep(pts->n, static_cast<MapPoint*>(NULL));
+  ORBmatcher m(0.8f, true);
+  *nfused_out = m.Fuse(K, mat44(Scw), P.v, th, rep);
+  std::map<MapPoint*, int> id = P.id;
+  id.insert(KP.id.begin(), KP.id.end());
+  const std::vector<MapPoint*> now = K->GetMapPointMatches();
+  for (int j = 0; j < kf->n; ++j) slot_owner[j] = now[j] ? id.at(now[j]) : -1;
+  for (int i = 0; i < pts->n; ++i) replace_out[i] = rep[i] ? id.at(rep[i]) : -1;
+  delete K; delete FK;
+  return 0;
+}
+
+// SearchBySim3(KeyFrame*, KeyFrame*, vector<MapPoint*>& vpMatches12, s12, R12, t12, th), src/ORBmatcher.cc:1334-1558.
+// mp1 / mp2: the keyframes' MapPoints (one per keypoint); matches12_io[kf1->n]: pKF2 keypoint whose MapPoint is already
+// matched to pKF1 keypoint i (-1 none), updated in place with the new matches.
+int X(search_by_sim3)(const OrbmFrame* kf1, const OrbmFrame* kf2, const RefMapPoints* mp1, const RefMapPoints* mp2,
+                      int32_t* matches12_io, float s12, const float* R12, const float* t12, float th, int* nfound_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  Points P1, P2;
+  make_points(mp1, P1, 1000000);
+  make_points(mp2, P2, 0);
+  Frame *F1, *F2;
+  KeyFrame* K1 = make_keyframe(kf1, &P1, &F1);
+  KeyFrame* K2 = make_keyframe(kf2, &P2, &F2);
+  restore_statics(kf1);
+  std::vector<MapPoint*> v12(kf1->n, static_cast<MapPoint*>(NULL));
+  for (int i = 0; i < kf1->n; ++i)
+    if (matches12_io[i] >= 0) v12[i] = P2.v[matches12_io[i]];
+  cv::Mat R(3, 3, CV_32F), t(3, 1, CV_32F);
+  memcpy(R.data, R12, 36); memcpy(t.data, t12, 12);
+  ORBmatcher m(0.75f, true);
+  *nfound_out = m.SearchBySim3(K1, K2, v12, s12, R, t, th);
+  flatten(v12, P2.id, matches12_io);
+  delete K1; delete K2; delete F1; delete F2;
+  return 0;
+}
+
+// SearchForTriangulation(KeyFrame*, KeyFrame*, cv::Mat F12, vector<pair<size_t,size_t>>&, bOnlyStereo),
+// src/ORBmatcher.cc:827-1019.  k1 / k2 carry keypoints, right coordinates, MapPoint occupancy and the FeatureVector;
+// Tcw1 / Tcw2 the poses (for the epipole).  epipole_out[2] = (ex, ey) as the function computes it.
+int X(triangulation)(const OrbmTriKF* k1, const OrbmTriKF* k2, const float* Tcw1, const float* Tcw2, const OrbmFrame* cam,
+                     const float* F12, int only_stereo, float nnratio, int check_ori, int32_t* matches12, int* nmatches_out,
+                     float* epipole_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  make_point(nullptr, nullptr, 0);
+  auto build = [&](const OrbmTriKF* k, const float* Tcw, Frame** keep, Points& P) {
+    OrbmFrame v = *cam;
+    v.n = k->n; v.x = k->x; v.y = k->y; v.octave = k->octave; v.angle = k->angle; v.uright = k->uright; v.desc = k->desc;
+    v.mp_obs = nullptr;
+    memcpy(v.Tcw, Tcw, 64);
+    Frame* F = make_frame(&v);
+    OrbmBow b;
+    memset(&b, 0, sizeof(b));
+    b.n_nodes = k->n_nodes; b.node_ids = k->node_ids; b.node_off = k->node_off; b.idx = k->idx;
+    set_featvec(F->mFeatVec, &b);
+    P.v.assign(k->n, static_cast<MapPoint*>(NULL));
+    for (int i = 0; i < k->n; ++i)
+      if (k->has_mp && k->has_mp[i]) P.v[i] = make_point(nullptr, nullptr, 1);
+    KeyFrame* K = new KeyFrame(*F, &g_map, nullptr);
+    for (int i = 0; i < k->n; ++i) if (P.v[i]) K->AddMapPoint(P.v[i], i);
+    *keep = F;
+    return K;
+  };
+  Points P1, P2;
+  Frame *F1, *F2;
+  KeyFrame* K1 = build(k1, Tcw1, &F1, P1);
+  KeyFrame* K2 = build(k2, Tcw2, &F2, P2);
+  restore_statics(cam);
+  cv::Mat F(3, 3, CV_32F);
+  memcpy(F.data, F12, 36);
+  std::vector<std::pair<size_t, size_t>> pairs;
+  ORBmatcher m(nnratio, check_ori != 0);
+  *nmatches_out = m.SearchForTriangulation(K1, K2, F, pairs, only_stereo != 0);
+  for (int i = 0; i < k1->n; ++i) matches12[i] = -1;
+  for (auto& pr : pairs) matches12[pr.first] = (int32_t)pr.second;
+  if (epipole_out) {   // the same expressions as :835-839
+    cv::Mat Cw = K1->GetCameraCenter();
+    cv::Mat R2w = K2->GetRotation();
+    cv::Mat t2w = K2->GetTranslation();
+    cv::Mat C2 = R2w * Cw + t2w;
+    const float invz = 1.0f / C2.at<float>(2);
+    epipole_out[0] = K2->fx * C2.at<float>(0) * invz + K2->cx;
+    epipole_out[1] = K2->fy * C2.at<float>(1) * invz + K2->cy;
+  }
+  delete K1; delete K2; delete F1; delete F2;
+  return 0;
+}
+
+// KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:659-698) + ORBmatcher::DescriptorDistance for a list of queries: the
+// candidate walk the BEST searches share, without any gate.  best_dist = INT_MAX when no candidate.
+int X(kf_best)(const OrbmFrame* kf, const OrbmQueries* q, int32_t* best_idx, int32_t* best_dist) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  Frame* FK;
+  KeyFrame* K = make_keyframe(kf, nullptr, &FK);
+  restore_statics(kf);
+  for (int i = 0; i < q->n; ++i) {
+    best_idx[i] = -1; best_dist[i] = 2147483647;
+    if (!q->valid[i]) continue;
+    const std::vector<size_t> vIndices = K->GetFeaturesInArea(q->u[i], q->v[i], q->radius[i]);
+    const cv::Mat dMP = desc_row(q->desc + 32 * (size_t)i);
+    for (size_t idx : vIndices) {
+      const int lvl = K->mvKeysUn[idx].octave;
+      if (lvl < q->min_level[i] || lvl > q->max_level[i]) continue;
+      const int dist = ORBmatcher::DescriptorDistance(dMP, K->mDescriptors.row((int)idx));
+      if (dist < best_dist[i]) { best_dist[i] = dist; best_idx[i] = (int32_t)idx; }
+    }
+  }
+  delete K; delete FK;
   return 0;
 }
 

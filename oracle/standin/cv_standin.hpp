@@ -335,10 +335,14 @@ inline Mat gemm_eval(const Mat& A, const Mat& B, double alpha, const Mat* C, dou
 
 struct Mat::TExpr {   // alpha * A^T, unevaluated
   Mat a; double alpha;
-  operator Mat() const {
+  operator Mat() const {   // transpose, then convertTo(alpha) when scaled (float product for CV_32F)
     Mat d(a.cols, a.rows, a.type());
     for (int i = 0; i < a.rows; ++i)
-      for (int j = 0; j < a.cols; ++j) d.set_d(j, i, alpha == 1.0 ? a.get_d(i, j) : a.get_d(i, j) * alpha);
+      for (int j = 0; j < a.cols; ++j) {
+        if (alpha == 1.0) d.set_d(j, i, a.get_d(i, j));
+        else if (a.depth() == CV_32F) d.at<float>(j, i) = a.at<float>(i, j) * (float)alpha;
+        else d.set_d(j, i, a.get_d(i, j) * alpha);
+      }
     return d;
   }
   TExpr operator-() const { return TExpr{a, -alpha}; }
@@ -373,16 +377,21 @@ template <typename F> inline Mat elementwise(const Mat& a, const Mat& b, F f) {
 }
 inline Mat operator+(const Mat& a, const Mat& b) { return elementwise(a, b, [](auto x, auto y) { return x + y; }); }
 inline Mat operator-(const Mat& a, const Mat& b) { return elementwise(a, b, [](auto x, auto y) { return x - y; }); }
-inline Mat scaled(const Mat& a, double s) {   // convertTo with alpha: float(double(x) * s)
-  Mat d(a.rows, a.cols, a.type());
+inline Mat scaled(const Mat& a, double s) {   // MatExpr alpha*A -> A.convertTo(type, alpha): for CV_32F the scale is
+  Mat d(a.rows, a.cols, a.type());            // narrowed to float and the product formed in float (cvtScale 32f->32f)
   for (int i = 0; i < a.rows; ++i)
-    for (int j = 0; j < a.cols * a.channels(); ++j) d.set_d(i, j, a.get_d(i, j) * s);
+    for (int j = 0; j < a.cols * a.channels(); ++j) {
+      if (a.depth() == CV_32F) d.ptr<float>(i)[j] = a.ptr<float>(i)[j] * (float)s;
+      else d.set_d(i, j, a.get_d(i, j) * s);
+    }
   return d;
 }
 inline Mat operator*(const Mat& a, double s) { return scaled(a, s); }
 inline Mat operator*(double s, const Mat& a) { return scaled(a, s); }
 inline Mat operator*(double s, const MatInit& a) { return scaled(Mat(a), s); }
 inline Mat operator/(const Mat& a, double s) { return scaled(a, 1.0 / s); }   // MatExpr: A/s == A*(1/s)
+inline Mat::TExpr operator*(double s, const Mat::TExpr& t) { return Mat::TExpr{t.a, t.alpha * s}; }
+inline Mat::TExpr operator*(const Mat::TExpr& t, double s) { return Mat::TExpr{t.a, t.alpha * s}; }
 inline Mat operator-(const Mat& a) { return scaled(a, -1.0); }
 
 inline double norm(const Mat& a, int normType = NORM_L2) {

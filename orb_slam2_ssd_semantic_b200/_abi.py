@@ -193,3 +193,41 @@ class QueriesView:
 class OcmMergeStats(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("records_sent", C.c_int64), ("records_total", C.c_int64),
                 ("bytes_sent", C.c_int64), ("bytes_received", C.c_int64)]
+
+
+class OrbmTriKF(C.Structure):
+    _fields_ = [("n", C.c_int), ("desc", vp), ("x", vp), ("y", vp), ("angle", vp), ("uright", vp), ("octave", vp), ("has_mp", vp),
+                ("n_nodes", C.c_int), ("node_ids", vp), ("node_off", vp), ("idx", vp)]
+
+
+class TriKFView:
+    """A keyframe as SearchForTriangulation reads it: undistorted keypoints, right coordinates, MapPoint occupancy and
+    the DBoW2::FeatureVector flattened (node ids ascending)."""
+
+    def __init__(self, x, y, octave, angle, uright, desc, has_mp, feat_vec: dict):
+        self.x = np.ascontiguousarray(x, np.float32)
+        self.y = np.ascontiguousarray(y, np.float32)
+        self.octave = np.ascontiguousarray(octave, np.int32)
+        self.angle = np.ascontiguousarray(angle, np.float32)
+        self.uright = np.ascontiguousarray(uright, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.has_mp = np.ascontiguousarray(has_mp, np.uint8)
+        ids = sorted(feat_vec.keys())
+        self.node_ids = np.array(ids if ids else [0], np.uint32)
+        off, idx = [0], []
+        for k in ids:
+            idx.extend(int(v) for v in feat_vec[k])
+            off.append(len(idx))
+        self.node_off = np.array(off, np.int32)
+        self.idx = np.array(idx if idx else [0], np.uint32)
+        self.n_nodes = len(ids)
+        self.n = len(self.x)
+
+    def struct(self) -> OrbmTriKF:
+        s = OrbmTriKF()
+        s.n = self.n
+        s.desc, s.x, s.y, s.angle, s.uright = ptr(self.desc), ptr(self.x), ptr(self.y), ptr(self.angle), ptr(self.uright)
+        s.octave, s.has_mp = ptr(self.octave), ptr(self.has_mp)
+        s.n_nodes = self.n_nodes
+        s.node_ids, s.node_off, s.idx = ptr(self.node_ids), ptr(self.node_off), ptr(self.idx)
+        return s

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "orbm_host.h"
+#include "orbm_extra.cuh"
 
 using namespace b200;
 
@@ -308,6 +309,161 @@ int orbm_search_projected(orbm_t* h, const OrbmFrame* cur, const OrbmQueries* q,
   h->launches += 3;
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync(cur2q, d_out, sizeof(int) * nc, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int orbm_search_best(orbm_t* h, const OrbmFrame* kf, const OrbmQueries* q, int gate, const float* inv_level_sigma2,
+                     int32_t* best_idx, int32_t* best_dist) {
+  if (!h || !kf || !q || !best_idx || !best_dist) { set_error("null argument"); return B200ORB_EINVAL; }
+  B200_CHECK(check_cur(kf));
+  if (q->n < 0) { set_error("bad query count"); return B200ORB_EINVAL; }
+  for (int i = 0; i < q->n; ++i) { best_idx[i] = -1; best_dist[i] = 0x7fffffff; }
+  if (kf->n == 0 || q->n == 0) return B200ORB_OK;
+  if (!q->valid || !q->u || !q->v || !q->radius || !q->min_level || !q->max_level || !q->desc) { set_error("null query array"); return B200ORB_EINVAL; }
+  if (gate == 1 && (!inv_level_sigma2 || !q->uright)) { set_error("the Fuse gate needs inv_level_sigma2 and the predicted right coordinates"); return B200ORB_EINVAL; }
+  if (gate != 0 && gate != 1) { set_error("bad gate"); return B200ORB_EINVAL; }
+  MatchCam cam;
+  B200_CHECK(fill_cam(kf, 0.f, 0, 0.f, 0, &cam));
+  DeviceGuard g(h->device);
+  const size_t nc = kf->n, nq = q->n;
+  const size_t need = nc * (4 * 4 + 4 + 32 + 4 + 4 + 4) + nq * (1 + 4 * 6 + 8 + 32 + 8) + 4 * (GRID_CELLS + 1) + 64 * 256 + 8192;
+  B200_CHECK(h->reserve(need));
+  Carver cm(h->d_arena);
+  CurView cv;
+  int *d_goff, *d_gidx;
+  OrbmFrame kf2 = *kf;
+  kf2.mp_obs = nullptr;
+  B200_CHECK(upload_cur(h, cm, &kf2, &cv, &d_goff, &d_gidx));
+  uint8_t* d_valid = cm.take<uint8_t>(nq); float* d_u = cm.take<float>(nq); float* d_v = cm.take<float>(nq);
+  float* d_r = cm.take<float>(nq); int* d_mn = cm.take<int>(nq); int* d_mx = cm.take<int>(nq);
+  float* d_ur = q->uright ? cm.take<float>(nq) : nullptr; uint8_t* d_desc = cm.take<uint8_t>(nq * 32);
+  float* d_is2 = cm.take<float>(MAX_LEVELS);
+  int* d_bi = cm.take<int>(nq); int* d_bd = cm.take<int>(nq);
+  UP(d_valid, q->valid, nq, uint8_t); UP(d_u, q->u, nq, float); UP(d_v, q->v, nq, float); UP(d_r, q->radius, nq, float);
+  UP(d_mn, q->min_level, nq, int); UP(d_mx, q->max_level, nq, int); UP(d_desc, q->desc, nq * 32, uint8_t);
+  if (d_ur) UP(d_ur, q->uright, nq, float);
+  if (gate == 1) UP(d_is2, inv_level_sigma2, kf->nlevels, float);
+  QueriesView qv{d_valid, d_u, d_v, d_r, d_ur, nullptr, d_mn, d_mx, nullptr, d_desc, (int)nq};
+  BestGate bg{gate, d_is2, cv.uright};
+  k_grid_build<<<1, 256, 0, h->stream>>>(cv.x, cv.y, cv.n, cv.stride, cam.min_x, cam.max_x, cam.min_y, cam.max_y, d_goff, d_gidx);
+  k_best_generic<<<((int)nq + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, h->stream>>>(cv, qv, cam, bg, d_bi, d_bd);
+  h->launches += 2;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(best_idx, d_bi, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(best_dist, d_bd, sizeof(int) * nq, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int orbm_search_for_initialization(orbm_t* h, const OrbmFrame* f1, const OrbmFrame* f2, float* prev_xy, int window,
+                                   float nnratio, int check_ori, int32_t* matches12, int* nmatches) {
+  if (!h || !f1 || !f2 || !prev_xy || !matches12 || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
+  B200_CHECK(check_cur(f1));
+  B200_CHECK(check_cur(f2));
+  *nmatches = 0;
+  for (int i = 0; i < f1->n; ++i) matches12[i] = -1;
+  if (f1->n == 0 || f2->n == 0) return B200ORB_OK;
+  MatchCam cam;
+  B200_CHECK(fill_cam(f2, 0.f, 0, nnratio, check_ori, &cam));
+  DeviceGuard g(h->device);
+  const size_t n1 = f1->n, n2 = f2->n;
+  const size_t need = n2 * (4 * 4 + 4 + 32 + 4 + 4 + 4 + 8) + n1 * (4 + 4 + 32 + 8 + 4 + 4) + 4 * (GRID_CELLS + 1) + 64 * 256 + 8192;
+  B200_CHECK(h->reserve(need));
+  Carver cm(h->d_arena);
+  CurView cv;
+  int *d_goff, *d_gidx;
+  OrbmFrame f2c = *f2;
+  f2c.mp_obs = nullptr;
+  B200_CHECK(upload_cur(h, cm, &f2c, &cv, &d_goff, &d_gidx));
+  int* d_oct1 = cm.take<int>(n1); float* d_ang1 = cm.take<float>(n1); uint8_t* d_desc1 = cm.take<uint8_t>(n1 * 32);
+  float* d_prev = cm.take<float>(n1 * 2); int* d_md = cm.take<int>(n2); int* d_m21 = cm.take<int>(n2);
+  int* d_bin = cm.take<int>(n1); int* d_out = cm.take<int>(n1); int* d_nm = cm.take<int>(1);
+  UP(d_oct1, f1->octave, n1, int); UP(d_ang1, f1->angle, n1, float); UP(d_desc1, f1->desc, n1 * 32, uint8_t);
+  UP(d_prev, prev_xy, n1 * 2, float);
+  InitView iv{d_oct1, d_ang1, d_desc1, d_prev, (int)n1, d_md, d_m21, d_bin};
+  k_grid_build<<<1, 256, 0, h->stream>>>(cv.x, cv.y, cv.n, cv.stride, cam.min_x, cam.max_x, cam.min_y, cam.max_y, d_goff, d_gidx);
+  k_init_search<<<1, 32, 0, h->stream>>>(cv, iv, cam, window, nnratio, check_ori, d_out, d_nm);
+  h->launches += 2;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(matches12, d_out, sizeof(int) * n1, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(prev_xy, d_prev, sizeof(float) * 2 * n1, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int orbm_search_for_triangulation(orbm_t* h, const OrbmTriKF* k1, const OrbmTriKF* k2, const float F12[9], float ex, float ey,
+                                  const float* scale_factors2, const float* level_sigma2_2, int nlevels, int only_stereo,
+                                  int check_ori, int32_t* matches12, int* nmatches) {
+  if (!h || !k1 || !k2 || !F12 || !scale_factors2 || !level_sigma2_2 || !matches12 || !nmatches) { set_error("null argument"); return B200ORB_EINVAL; }
+  if (k1->n < 0 || k2->n < 0 || k1->n_nodes < 0 || k2->n_nodes < 0 || k2->n >= (1 << 22) || nlevels < 1 || nlevels > MAX_LEVELS) { set_error("bad counts"); return B200ORB_EINVAL; }
+  *nmatches = 0;
+  for (int i = 0; i < k1->n; ++i) matches12[i] = -1;
+  if (k1->n == 0 || k2->n == 0 || k1->n_nodes == 0 || k2->n_nodes == 0) return B200ORB_OK;
+  for (int i = 0; i < k2->n; ++i)
+    if (k2->octave[i] < 0 || k2->octave[i] >= nlevels) { set_error("octave out of range"); return B200ORB_EINVAL; }
+  // merge-join of the FeatureVectors (:861-983); per pKF1 keypoint without MapPoint (and stereo when bOnlyStereo) one query
+  std::vector<int> q1, qb, qe;
+  {
+    int a = 0, b = 0;
+    while (a < k1->n_nodes && b < k2->n_nodes) {
+      const uint32_t ka = k1->node_ids[a], kb = k2->node_ids[b];
+      if (ka == kb) {
+        for (int i = k1->node_off[a]; i < k1->node_off[a + 1]; ++i) {
+          const uint32_t r = k1->idx[i];
+          if (r >= (uint32_t)k1->n) { set_error("KF1 index out of range"); return B200ORB_EINVAL; }
+          if (k1->has_mp && k1->has_mp[r]) continue;
+          if (only_stereo && !(k1->uright[r] >= 0)) continue;
+          q1.push_back((int)r); qb.push_back(k2->node_off[b]); qe.push_back(k2->node_off[b + 1]);
+        }
+        ++a; ++b;
+      } else if (ka < kb) {
+        a = (int)(std::lower_bound(k1->node_ids, k1->node_ids + k1->n_nodes, kb) - k1->node_ids);
+      } else {
+        b = (int)(std::lower_bound(k2->node_ids, k2->node_ids + k2->n_nodes, ka) - k2->node_ids);
+      }
+    }
+  }
+  const size_t nq = q1.size(), nfi = (size_t)k2->node_off[k2->n_nodes];
+  if (nq == 0) return B200ORB_OK;
+  for (size_t i = 0; i < nfi; ++i)
+    if (k2->idx[i] >= (uint32_t)k2->n) { set_error("KF2 index out of range"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  const size_t n1 = k1->n, n2 = k2->n;
+  const size_t need = nq * 12 + nfi * 4 + n1 * (32 + 16 + 4) + n2 * (32 + 16 + 4 + 1) + 64 * 256 + 8192;
+  B200_CHECK(h->reserve(need));
+  Carver cm(h->d_arena);
+  int* d_q1 = cm.take<int>(nq); int* d_qb = cm.take<int>(nq); int* d_qe = cm.take<int>(nq); unsigned* d_fidx = cm.take<unsigned>(nfi);
+  uint8_t* d_d1 = cm.take<uint8_t>(n1 * 32); uint8_t* d_d2 = cm.take<uint8_t>(n2 * 32);
+  float *d_x1 = cm.take<float>(n1), *d_y1 = cm.take<float>(n1), *d_a1 = cm.take<float>(n1), *d_u1 = cm.take<float>(n1);
+  float *d_x2 = cm.take<float>(n2), *d_y2 = cm.take<float>(n2), *d_a2 = cm.take<float>(n2), *d_u2 = cm.take<float>(n2);
+  int* d_o2 = cm.take<int>(n2); uint8_t* d_b2 = cm.take<uint8_t>(n2);
+  int* d_out = cm.take<int>(n1); int* d_nm = cm.take<int>(1);
+  std::vector<uint8_t> blocked(n2, 0);
+  if (k2->has_mp) memcpy(blocked.data(), k2->has_mp, n2);
+  UP(d_q1, q1.data(), nq, int); UP(d_qb, qb.data(), nq, int); UP(d_qe, qe.data(), nq, int); UP(d_fidx, k2->idx, nfi, unsigned);
+  UP(d_d1, k1->desc, n1 * 32, uint8_t); UP(d_d2, k2->desc, n2 * 32, uint8_t);
+  UP(d_x1, k1->x, n1, float); UP(d_y1, k1->y, n1, float); UP(d_a1, k1->angle, n1, float); UP(d_u1, k1->uright, n1, float);
+  UP(d_x2, k2->x, n2, float); UP(d_y2, k2->y, n2, float); UP(d_a2, k2->angle, n2, float); UP(d_u2, k2->uright, n2, float);
+  UP(d_o2, k2->octave, n2, int); UP(d_b2, blocked.data(), n2, uint8_t);
+  B200_CUDA(cudaMemsetAsync(d_out, 0xff, sizeof(int) * n1, h->stream));
+  TriView t;
+  memset(&t, 0, sizeof(t));
+  t.q_idx1 = d_q1; t.f_beg = d_qb; t.f_end = d_qe; t.f_idx = d_fidx; t.desc1 = d_d1; t.desc2 = d_d2;
+  t.x1 = d_x1; t.y1 = d_y1; t.ang1 = d_a1; t.ur1 = d_u1; t.x2 = d_x2; t.y2 = d_y2; t.ang2 = d_a2; t.ur2 = d_u2; t.oct2 = d_o2;
+  t.blocked2 = d_b2;
+  for (int i = 0; i < 9; ++i) t.F12[i] = F12[i];
+  t.ex = ex; t.ey = ey;
+  for (int i = 0; i < nlevels; ++i) { t.sf2[i] = scale_factors2[i]; t.sigma2_2[i] = level_sigma2_2[i]; }
+  t.only_stereo = only_stereo; t.nq = (int)nq; t.n1 = (int)n1;
+  B200_CUDA(cudaStreamSynchronize(h->stream));   // `blocked` (host vector) has been read by the upload
+  k_tri_best<<<((int)nq + CAND_WARPS - 1) / CAND_WARPS, CAND_WARPS * 32, 0, h->stream>>>(t, d_out);
+  k_tri_prune<<<1, 32, 0, h->stream>>>(t, check_ori, d_out, d_nm);
+  h->launches += 2;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(matches12, d_out, sizeof(int) * n1, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return B200ORB_OK;

@@ -4,8 +4,11 @@
 //   Tracking.cc:210-218   new ORBextractor(nFeatures, fScaleFactor, nLevels, fIniThFAST, fMinThFAST)
 //   Frame.cc:340,342      (*mpORBextractorLeft)(im, cv::Mat(), mvKeys, mDescriptors)
 //   Frame.cc:111-117      GetLevels() / GetScaleFactors() / ...
-// Build with the real OpenCV headers in the reference's tree; for the syntax check in this repo (no OpenCV here)
-// shim/cv_standin.h provides the handful of cv:: types the shim touches (define B200_SHIM_STANDIN).
+// Build with the OpenCV headers the reference already uses.  (This repo has no OpenCV C++; its tests compile the shims
+// against the stand-in headers of oracle/standin/, together with the reference's own Frame.cc / KeyFrame.cc / MapPoint.cc.)
+// mvImagePyramid is read back by the stereo matcher only (src/Frame.cc:649,761-778); it is filled lazily by
+// SyncImagePyramid(), or after every operator() when ORBextractor::EagerPyramid() = true (or B200ORB_EAGER_PYRAMID=1) is
+// set once at start-up -- stereo callers do that and stay otherwise unchanged.
 #ifndef ORBEXTRACTOR_H
 #define ORBEXTRACTOR_H
 
@@ -13,13 +16,12 @@
 #include <string>
 #include <vector>
 
-#ifdef B200_SHIM_STANDIN
-#include "cv_standin.h"
-#else
-#include <opencv2/opencv.hpp>
-#endif
+#include <cstdlib>
+#include <cstring>
 
-#include "../../../include/b200orb.h"
+#include <opencv2/opencv.hpp>
+
+#include "b200orb.h"
 
 namespace ORB_SLAM2 {
 
@@ -69,8 +71,14 @@ class ORBextractor {
       const OrbxKeyPoint& k = kps_[i];
       _keypoints.push_back(cv::KeyPoint(k.x, k.y, k.size, k.angle, k.response, k.octave, k.class_id));
     }
-    // mvImagePyramid is public and read back by the stereo matcher only (src/Frame.cc:649,761-778): fill lazily
     pyramid_valid_ = false;
+    if (EagerPyramid()) SyncImagePyramid();
+  }
+
+  // process-wide switch: fill the public mvImagePyramid member after every extraction (stereo callers)
+  static bool& EagerPyramid() {
+    static bool on = [] { const char* e = std::getenv("B200ORB_EAGER_PYRAMID"); return e && e[0] == '1'; }();
+    return on;
   }
 
   int inline GetLevels() { return nlevels; }
@@ -80,7 +88,7 @@ class ORBextractor {
   std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
   std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-  // include/ORBextractor.h:80.  Call SyncImagePyramid() before reading it (stereo path only).
+  // include/ORBextractor.h:80 (see EagerPyramid above)
   std::vector<cv::Mat> mvImagePyramid;
   void SyncImagePyramid() {
     if (pyramid_valid_) return;

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._abi import BowView, FrameView, LastView, QueriesView, TrackPointsView, ptr  # noqa: F401
+from ._abi import BowView, FrameView, LastView, QueriesView, TrackPointsView, TriKFView, ptr  # noqa: F401
 
 
 class ORBmatcher:
@@ -90,6 +90,40 @@ class ORBmatcher:
         _lib.check(self._L.orbm_search_by_bow_kf(self._h, C.byref(a), C.byref(b), self.mfNNratio,
                                                  int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out
+
+    def SearchBest(self, KF: FrameView, queries: QueriesView, gate: int = 0, inv_level_sigma2=None):
+        """Per-query best keypoint of a keyframe, no claim state: the device part of both Fuse overloads (gate 1 / 0,
+        src/ORBmatcher.cc:1031-1182, 1198-1318) and of SearchBySim3 (:1334-1558) -> (best_idx, best_dist)."""
+        bi = np.full(max(queries.n, 1), -1, np.int32)
+        bd = np.full(max(queries.n, 1), 2 ** 31 - 1, np.int32)
+        ks, qs = KF.struct(), queries.struct()
+        is2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        _lib.check(self._L.orbm_search_best(self._h, C.byref(ks), C.byref(qs), int(gate), ptr(is2), ptr(bi), ptr(bd)))
+        return bi[:queries.n], bd[:queries.n]
+
+    def SearchForInitialization(self, F1: FrameView, F2: FrameView, vbPrevMatched, windowSize: int = 10):
+        """src/ORBmatcher.cc:523-651 -> (nmatches, vnMatches12, updated vbPrevMatched)."""
+        prev = np.ascontiguousarray(vbPrevMatched, np.float32).reshape(-1, 2).copy()
+        out = np.full(max(F1.n, 1), -1, np.int32)
+        nm = C.c_int(0)
+        a, b = F1.struct(), F2.struct()
+        _lib.check(self._L.orbm_search_for_initialization(self._h, C.byref(a), C.byref(b), ptr(prev), int(windowSize),
+                                                          self.mfNNratio, int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        return nm.value, out[:F1.n], prev
+
+    def SearchForTriangulation(self, pKF1: TriKFView, pKF2: TriKFView, F12, epipole, scale_factors2, level_sigma2_2,
+                               bOnlyStereo: bool = False):
+        """src/ORBmatcher.cc:827-1019 -> (nmatches, matches12); epipole = (ex, ey) of :835-839."""
+        F = np.ascontiguousarray(F12, np.float32).reshape(9)
+        sf = np.ascontiguousarray(scale_factors2, np.float32)
+        s2 = np.ascontiguousarray(level_sigma2_2, np.float32)
+        out = np.full(max(pKF1.n, 1), -1, np.int32)
+        nm = C.c_int(0)
+        a, b = pKF1.struct(), pKF2.struct()
+        _lib.check(self._L.orbm_search_for_triangulation(self._h, C.byref(a), C.byref(b), ptr(F), float(epipole[0]),
+                                                         float(epipole[1]), ptr(sf), ptr(s2), len(sf), int(bOnlyStereo),
+                                                         int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
+        return nm.value, out[:pKF1.n]
 
     def launch_count(self) -> int:
         return int(self._L.orbm_launch_count(self._h))

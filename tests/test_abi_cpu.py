@@ -67,8 +67,23 @@ def test_cpp_shims_compile_link_and_fail_loudly(tmp_path):
     libdir = os.path.join(ROOT, "orb_slam2_ssd_semantic_b200")
     exe = str(tmp_path / "shim_check")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(shim, "shim_check.cpp"),
+                           "-I" + os.path.join(ROOT, "oracle", "standin"), "-I" + os.path.join(ROOT, "include"),
                            "-L" + libdir, "-lb200orb", "-Wl,-rpath," + libdir])
     if torch.cuda.is_available():
         pytest.skip("GPU present: exercised by tests/test_shim_gpu.py")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "loud failure" in out.stdout and "no CPU fallback" in out.stdout
+
+
+def test_shims_compile_against_the_reference_sources():
+    """All three shim headers in their one and only (production) form: shim/ORBextractor.h + shim/ORBmatcher.h are what
+    the reference's own src/Frame.cc, KeyFrame.cc, MapPoint.cc, Map.cc are compiled against for oracle/_ref/libshimsrc.so
+    (oracle/Makefile, target `shim`); the library must link against libb200orb.so and export every shimsrc_* entry."""
+    import subprocess
+    if not os.path.exists("/root/reference/src/Frame.cc"):
+        pytest.skip("the reference is not on this box")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "shim"])
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libshimsrc.so"))
+    for name in ("projection_last", "projection_points", "projection_kf", "projection_sim3", "bow", "bow_kf", "initialization",
+                 "triangulation", "search_by_sim3", "fuse", "fuse_sim3", "frame_rgbd", "pipeline_run", "orb_extract"):
+        assert hasattr(L, "shimsrc_" + name), name

@@ -248,3 +248,25 @@ def test_search_by_bow_keyframe_keyframe(oracle, stream_feats, nwords):
         n_gpu, gpu = ORBmatcher(ratio, ori).SearchByBoWKF(k1, k2)
         assert n_gpu == n_ref and (gpu == ref).all(), (nwords, ratio, ori)
     assert n_ref > 5
+
+
+@pytest.mark.parametrize("path", sorted(__import__("glob").glob(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", "match_mapbin_*.npz"))))
+def test_projection_last_on_reference_mapbin_keyframes(oracle, path):
+    """GPU SearchByProjection(cur, last) on REAL keyframes of the reference's map.bin (tests/golden/match_mapbin_*.npz:
+    real ORB keypoints, descriptors, map points) == the committed golden == the oracle, at three window sizes."""
+    from orb_slam2_ssd_semantic_b200 import ORBmatcher
+    from orb_slam2_ssd_semantic_b200._abi import FrameView, LastView
+    z = np.load(path)
+    fx, fy, cx, cy, bf = [float(v) for v in z["cam"]]
+    cur = FrameView(z["cur_x"], z["cur_y"], z["cur_oct"], z["cur_angle"], z["cur_uright"], z["cur_desc"], z["cur_Tcw"], fx, fy, cx,
+                    cy, bf, 0.0, 640.0, 0.0, 480.0, z["sf"])
+    last = LastView(z["last_xw"], z["last_valid"], z["last_oct"], z["last_angle"], z["last_desc"], z["last_Tcw"],
+                    mp_obs=np.ones(len(z["last_valid"]), np.int32))
+    m = ORBmatcher(0.9, True)
+    n, c2l = m.SearchByProjection(cur, last, float(z["th"]))
+    assert n == int(z["nmatches"]) and (c2l == z["cur2last"]).all() and n > 100
+    for th in (7.0, 30.0):
+        for mono in (False, True):
+            a = m.SearchByProjection(cur, last, th, mono)
+            b = oracle.search_by_projection_last(cur, last, th, mono, 0.9, True)
+            assert a[0] == b[0] and (a[1] == b[1]).all(), (th, mono)

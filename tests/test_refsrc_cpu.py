@@ -270,3 +270,80 @@ def test_tracking_pipeline_equals_reference_sources(src):
     b = src.src_pipeline_run(gray, depth, T, 2, 1000, **kw)
     assert (a[1] == b[1]).all() and (a[2] == b[2]).all()
     assert a[2][1:].min() > 100
+
+
+# ---- the remaining ORBmatcher members -------------------------------------------------------------------------------
+def test_best_search_equals_reference_sources(src):
+    """match_ref_best (the candidate loop Fuse x2 / SearchBySim3 share, no gate) against the reference's own
+    KeyFrame::GetFeaturesInArea + DescriptorDistance walked in the same order."""
+    from tests import members_gen as G
+    rng = np.random.default_rng(71)
+    M = src.SrcMembers("refsrc")
+    hits = 0
+    for case in range(6):
+        F, _ = _random_frame(rng, int(rng.integers(150, 600)), False)
+        q = G.best_queries(rng, F)
+        a = src.search_best(F, q, 0)
+        b = M.kf_best(F, q)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all(), case
+        hits += int((a[0] >= 0).sum())
+    assert hits > 500
+
+
+def test_triangulation_equals_reference_sources(src):
+    """match_ref_triangulation against ORBmatcher::SearchForTriangulation of the reference on two real KeyFrames
+    (mono / stereo mixes, occupied keypoints, bOnlyStereo, orientation check on / off)."""
+    from tests import members_gen as G
+    rng = np.random.default_rng(73)
+    M = src.SrcMembers("refsrc")
+    tot = 0
+    for case in range(8):
+        k1, k2, T1, T2, cam, F12 = G.tri_pair(rng, mono_frac=[0.6, 0.0, 1.0, 0.3][case % 4])
+        only_stereo, ori = case % 4 == 1, case % 3 != 2
+        n_ref, m_ref, ep = M.triangulation(k1, k2, T1, T2, cam, F12, only_stereo, 0.6, ori)
+        n_or, m_or = src.search_for_triangulation(k1, k2, F12, ep, G.SF, G.SF * G.SF, only_stereo, ori)
+        assert n_ref == n_or and (m_ref == m_or).all(), case
+        assert n_ref == (m_ref >= 0).sum()
+        tot += n_ref
+    assert tot > 300
+
+
+def test_reference_members_run_on_synthetic_graphs(src):
+    """The harness around Fuse / Fuse(Sim3) / SearchBySim3 / the relocalisation and loop-closing projections produces
+    non-trivial results on the synthetic graphs the GPU suite compares the shims on (sanity of the generator)."""
+    from tests import members_gen as G
+    rng = np.random.default_rng(79)
+    M = src.SrcMembers("refsrc")
+    n = 500
+    X = G.world_points(rng, n)
+    desc = rng.integers(0, 256, size=(n, 32), dtype=np.uint8)
+    T = G.pose(rng)
+    octs = rng.integers(0, 4, n)
+    KF, owner = G.frame_of(rng, T, X, desc, octaves=octs)
+    # the keyframe's own MapPoints: the world point behind each keypoint (60 % of them)
+    has = (owner >= 0) & (rng.random(KF.n) < 0.6)
+    Xk = np.where(has[:, None], X[np.maximum(owner, 0)], 0.0)
+    kf_mps = G.map_points(rng, Xk, KF.desc, G.camera_centre(T), src, octaves=KF.octave)
+    kf_mps.valid = has.astype(np.uint8)
+    pts = G.map_points(rng, X + rng.normal(0, 0.004, X.shape), desc, G.camera_centre(T), src, octaves=octs)
+    nf, slot, rep, krep = M.fuse(KF, kf_mps, pts, (rng.random(n) < 0.05).astype(np.uint8), 3.0)
+    assert nf > 50 and (rep >= 0).sum() > 5 and (krep >= 0).sum() > 5 and (slot[(slot >= 0) & (slot < 1000000)] >= 0).sum() > 10
+    S = T.copy()
+    S[:3, :] *= np.float32(1.3)
+    nf2, slot2, rep2 = M.fuse_sim3(KF, kf_mps, S, pts, 4.0)
+    assert nf2 > 50 and (rep2 >= 1000000).sum() > 10
+    nm, matched = M.projection_sim3(KF, S, pts, np.where(rng.random(KF.n) < 0.1, -2, -1).astype(np.int32), 10)
+    assert nm > 50
+    cur, _ = G.frame_of(rng, G.pose(rng), X, desc, octaves=octs)
+    cur.mp_obs = np.where(rng.random(cur.n) < 0.1, 1, -1).astype(np.int32)
+    nm2, c2k = M.projection_kf(cur, KF, kf_mps, (rng.random(KF.n) < 0.1).astype(np.uint8), 15.0, 100)
+    assert nm2 > 30
+    T2 = G.pose(rng, 0.2, 3.0)
+    KF2, owner2 = G.frame_of(rng, T2, X, desc, octaves=octs)
+    has2 = (owner2 >= 0) & (rng.random(KF2.n) < 0.6)
+    mp2 = G.map_points(rng, np.where(has2[:, None], X[np.maximum(owner2, 0)], 0.0), KF2.desc, G.camera_centre(T2), src,
+                       octaves=KF2.octave)
+    mp2.valid = has2.astype(np.uint8)
+    T12 = T.astype(np.float64) @ np.linalg.inv(T2.astype(np.float64))
+    nf3, m12 = M.search_by_sim3(KF, KF2, kf_mps, mp2, np.full(KF.n, -1, np.int32), 1.0, T12[:3, :3], T12[:3, 3], 7.5)
+    assert nf3 > 20 and (m12 >= 0).sum() == nf3
