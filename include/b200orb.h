@@ -259,6 +259,27 @@ int orbm_search_for_triangulation(orbm_t* h, const OrbmTriKF* kf1, const OrbmTri
                                   float ey, const float* scale_factors2, const float* level_sigma2_2, int nlevels,
                                   int only_stereo, int check_ori, int32_t* matches12, int* nmatches);
 
+/* Frame::isInFrustum (src/Frame.cc:387-451) for n MapPoints at once -- what Tracking::SearchLocalPoints runs per local
+ * MapPoint before SearchByProjection(Frame&, vector<MapPoint*>&, th) (src/Tracking.cc:1931-1946): projection, image and
+ * distance-invariance gates, viewing-angle gate, MapPoint::PredictScale.  The outputs are exactly the per-MapPoint fields
+ * OrbmTrackPoints wants (mbTrackInView, mTrackProjX/Y/XR, mnTrackScaleLevel, mTrackViewCos); entries not in view are 0.
+ * log_scale_factor = Frame::mfLogScaleFactor; min_dist / max_dist = mfMinDistance / mfMaxDistance (raw members). */
+typedef struct {
+  int n;
+  const float* xw;        /* n x 3 GetWorldPos() */
+  const float* normal;    /* n x 3 GetNormal() */
+  const float* min_dist;  /* mfMinDistance */
+  const float* max_dist;  /* mfMaxDistance */
+} OrbmFrustumPoints;
+int orbm_is_in_frustum(orbm_t* h, const OrbmFrame* f, const OrbmFrustumPoints* p, float viewing_cos_limit,
+                       float log_scale_factor, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr,
+                       int32_t* scale_level, float* view_cos);
+
+/* Frame::UndistortKeyPoints (src/Frame.cc:559-590): cv::undistortPoints(pts, pts, mK, mDistCoef, Mat(), mK) on n keypoint
+ * positions (xy interleaved); K row-major 3x3, dist = k1 k2 p1 p2 [k3].  dist[0] == 0 copies the input (:561-565). */
+int orbm_undistort_keypoints(orbm_t* h, const float* xy_in, int n, const float K[9], const float* dist, int ndist,
+                             float* xy_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Stream pipeline (batched many-frame mode of north_star): per frame t of a batch, what
  * Tracking::GrabImageRGBD -> Frame::Frame(RGB-D) -> TrackWithMotionModel's SearchByProjection do

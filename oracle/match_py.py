@@ -373,13 +373,14 @@ def stereo_unproject(kps_xy, depth, Tcw, fx, fy, cx, cy, bf):
     """Frame::ComputeStereoFromRGBD (src/Frame.cc:850-871) + Frame::UnprojectStereo (:879-899) for every keypoint:
     d = imDepth.at<float>(v, u) (float coordinates truncated by the int conversion), uRight = x - bf / d,
     x3Dc = ((u - cx) z invfx, (v - cy) z invfy, z) with invfx = 1.0f / fx (:215-216), world = mRwc x3Dc + mOw with
-    mRwc = mRcw.t() and mOw = -mRcw.t() mtcw (:308-311; cv::Mat products: float accumulation, '+ C' in double; the
-    3x3 * 3x1 product of mOw accumulates in double).  -> (uright, depth, xw, valid)."""
+    mRwc = mRcw.t() and mOw = -mRwc mtcw (src/Frame.cc:373; cv::Mat products of evaluated matrices: float accumulation,
+    '+ C' in double).  -> (uright, depth, xw, valid)."""
     fx, fy, cx, cy, bf = (f32(v) for v in (fx, fy, cx, cy, bf))
     invfx, invfy = f32(f32(1.0) / fx), f32(f32(1.0) / fy)
     T = np.asarray(Tcw, np.float32).reshape(4, 4)
     Rcw, tcw = T[:3, :3], T[:3, 3]
-    Ow = [f32(-sum(float(Rcw[k, i]) * float(tcw[k]) for k in range(3))) for i in range(3)]
+    # mOw = -mRwc*mtcw (src/Frame.cc:373): evaluated transpose -> small-matrix gemm, float accumulation
+    Ow = [f32(-f32(f32(f32(Rcw[0, i] * tcw[0]) + f32(Rcw[1, i] * tcw[1])) + f32(Rcw[2, i] * tcw[2]))) for i in range(3)]
     n = len(kps_xy)
     ur = np.full(n, -1, np.float32)
     dp = np.full(n, -1, np.float32)

@@ -453,6 +453,49 @@ int match_ref_triangulation(const OrbmTriKF* k1, const OrbmTriKF* k2, const floa
   return 0;
 }
 
+// Frame::isInFrustum (src/Frame.cc:387-451) + MapPoint::PredictScale (src/MapPoint.cc:463-478) for n MapPoints.
+// min_dist / max_dist = the raw members mfMinDistance / mfMaxDistance.  Entries that are not in view keep 0.
+int match_ref_is_in_frustum(const OrbmFrame* f, int n, const float* xw, const float* normal, const float* min_dist,
+                            const float* max_dist, float viewingCosLimit, float log_scale_factor, uint8_t* in_view,
+                            float* proj_x, float* proj_y, float* proj_xr, int32_t* scale_level, float* view_cos) {
+  const float* T = f->Tcw;
+  float Ow[3];
+  for (int a = 0; a < 3; ++a) {   // mOw = -mRwc*mtcw (src/Frame.cc:373): evaluated transpose -> small-matrix gemm, float sum
+    const float t = T[0 * 4 + a] * T[3] + T[1 * 4 + a] * T[7] + T[2 * 4 + a] * T[11];
+    Ow[a] = -t;
+  }
+  for (int i = 0; i < n; ++i) {
+    in_view[i] = 0; proj_x[i] = proj_y[i] = proj_xr[i] = view_cos[i] = 0.f; scale_level[i] = 0;
+    const float* P = xw + 3 * i;
+    const float PcX = gemm3(T + 0, P[0], P[1], P[2], T[3]);
+    const float PcY = gemm3(T + 4, P[0], P[1], P[2], T[7]);
+    const float PcZ = gemm3(T + 8, P[0], P[1], P[2], T[11]);
+    if (PcZ < 0.0f) continue;
+    const float invz = 1.0f / PcZ;
+    const float u = f->fx * PcX * invz + f->cx;
+    const float v = f->fy * PcY * invz + f->cy;
+    if (u < f->min_x || u > f->max_x) continue;
+    if (v < f->min_y || v > f->max_y) continue;
+    const float maxDistance = 1.2f * max_dist[i];
+    const float minDistance = 0.8f * min_dist[i];
+    const float PO[3] = {P[0] - Ow[0], P[1] - Ow[1], P[2] - Ow[2]};
+    double n2 = 0, dot = 0;
+    for (int a = 0; a < 3; ++a) { n2 += (double)PO[a] * (double)PO[a]; dot += (double)PO[a] * (double)normal[3 * i + a]; }
+    const float dist = (float)std::sqrt(n2);                 // cv::norm: double accumulation
+    if (dist < minDistance || dist > maxDistance) continue;
+    const float viewCos = (float)(dot / dist);               // Mat::dot returns double
+    if (viewCos < viewingCosLimit) continue;
+    const float ratio = max_dist[i] / dist;
+    int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);   // float log, float division, float ceil
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= f->nlevels) nScale = f->nlevels - 1;
+    in_view[i] = 1;
+    proj_x[i] = u; proj_y[i] = v; proj_xr[i] = u - f->bf * invz;
+    scale_level[i] = nScale; view_cos[i] = viewCos;
+  }
+  return 0;
+}
+
 // SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&), src/ORBmatcher.cc:217-363
 int match_ref_bow(const OrbmBow* kf, const OrbmBow* f, float nnratio, int check_ori, int32_t* f2kf,
                   int* nmatches_out) {
@@ -561,15 +604,16 @@ void frame_ref_stereo_unproject(const float* kps, int kp_stride, int n, const fl
                                 float* depth_out, float* xw, uint8_t* valid) {
   (void)rows;
   const float invfx = 1.0f / fx, invfy = 1.0f / fy;   // src/Frame.cc:215-216
-  // mRwc = mRcw.t(); mOw = -mRcw.t()*mtcw (src/Frame.cc:364-370)
+  // mRwc = mRcw.t(); mOw = -mRwc*mtcw (src/Frame.cc:364-373: the product of the EVALUATED transpose goes through the
+  // small-matrix gemm path -- float accumulation, alpha = -1; upstream ORB-SLAM2 writes -mRcw.t()*mtcw, which would
+  // accumulate in double; pinned by tests/test_refsrc_cpu.py against the reference's own Frame.cc)
   const float Rcw[9] = {Tcw[0], Tcw[1], Tcw[2], Tcw[4], Tcw[5], Tcw[6], Tcw[8], Tcw[9], Tcw[10]};
   const float tcw[3] = {Tcw[3], Tcw[7], Tcw[11]};
   float Rwc[9], Ow[3];
   for (int i = 0; i < 3; ++i) {
     for (int k = 0; k < 3; ++k) Rwc[i * 3 + k] = Rcw[k * 3 + i];
-    double s = 0;
-    for (int k = 0; k < 3; ++k) s += (double)Rcw[k * 3 + i] * (double)tcw[k];
-    Ow[i] = (float)(-s);
+    const float t = Rwc[i * 3 + 0] * tcw[0] + Rwc[i * 3 + 1] * tcw[1] + Rwc[i * 3 + 2] * tcw[2];
+    Ow[i] = -t;
   }
   for (int i = 0; i < n; ++i) {
     const float u = kps[(size_t)i * kp_stride], v = kps[(size_t)i * kp_stride + 1];

@@ -469,4 +469,16 @@ int orb_ref_distribute(const void* in, int n_in, int minX, int maxX, int minY, i
   return (int)vo.size();
 }
 
+// Frame::UndistortKeyPoints (src/Frame.cc:559-590) on xy pairs: cv::undistortPoints(K, dist, R = I, P = K)
+void orb_ref_undistort(const float* xy_in, int n, const float* K, const float* dist, int ndist, float* xy_out) {
+  if (ndist == 0 || dist[0] == 0.0f) { memcpy(xy_out, xy_in, sizeof(float) * 2 * (size_t)n); return; }
+  double k[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < ndist && i < 5; ++i) k[i] = dist[i];
+  for (int i = 0; i < n; ++i) {
+    double x, y;
+    undistort_point(xy_in[2 * i], xy_in[2 * i + 1], K[0], K[4], K[2], K[5], k, &x, &y);
+    xy_out[2 * i] = (float)x; xy_out[2 * i + 1] = (float)y;
+  }
+}
+
 }  // extern "C"

@@ -808,3 +808,38 @@ class SrcMembers:
         sec = f(_p(gray), _p(depth), _p(T), n, rows, cols, nfeatures, 1.2, 8, 20, 7, fx, fy, cx, cy, bf, th, nnratio, 1, nthreads,
                 _p(nkp), _p(nm))
         return sec, nkp, nm
+
+
+def is_in_frustum(F, xw, normal, min_dist, max_dist, cos_limit, log_sf, which="oracle"):
+    """Frame::isInFrustum for n points -> (in_view, proj_x, proj_y, proj_xr, scale_level, view_cos).
+    which = 'oracle' (restatement) or 'refsrc' (the reference's own Frame.cc / MapPoint.cc)."""
+    from orb_slam2_ssd_semantic_b200 import _abi
+    xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+    nr = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+    mn, mx = np.ascontiguousarray(min_dist, np.float32), np.ascontiguousarray(max_dist, np.float32)
+    n = len(xw)
+    iv = np.zeros(n, np.uint8)
+    px, py, pxr, vc = [np.zeros(n, np.float32) for _ in range(4)]
+    lvl = np.zeros(n, np.int32)
+    fs = F.struct()
+    if which == "oracle":
+        L = _mlib()
+        L.match_ref_is_in_frustum.argtypes = [C.POINTER(_abi.OrbmFrame), C.c_int] + [C.c_void_p] * 4 + [C.c_float, C.c_float] + [C.c_void_p] * 6
+        L.match_ref_is_in_frustum(C.byref(fs), n, _p(xw), _p(nr), _p(mn), _p(mx), float(cos_limit), float(log_sf), _p(iv), _p(px), _p(py),
+                                  _p(pxr), _p(lvl), _p(vc))
+    else:
+        reflib().refsrc_is_in_frustum(C.byref(fs), n, _p(xw), _p(nr), _p(mn), _p(mx), float(cos_limit), _p(iv), _p(px), _p(py), _p(pxr),
+                                      _p(lvl), _p(vc))
+    return iv, px, py, pxr, lvl, vc
+
+
+def undistort(xy, K, dist):
+    """Frame::UndistortKeyPoints on xy pairs (oracle restatement of cv::undistortPoints)."""
+    L = lib()
+    L.orb_ref_undistort.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    K = np.ascontiguousarray(K, np.float32).reshape(9)
+    d = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros_like(xy)
+    L.orb_ref_undistort(_p(xy), len(xy), _p(K), _p(d), len(d), _p(out))
+    return out

@@ -227,4 +227,24 @@ inline void copy_make_border_101_u8(const uint8_t* src, int w, int h, int sstrid
     memcpy(dst + (size_t)(top + h + y) * dstride, dst + (size_t)(top + reflect101(h + y, h)) * dstride, (size_t)W);
 }
 
+// cv::undistortPoints(src, dst, K, dist(k1 k2 p1 p2 k3), R = I, P = K) for one point: the classic fixed-point iteration, 5
+// iterations (OpenCV's default termination criteria), all in double; the caller stores the result as float.
+inline void undistort_point(double u, double v, double fx, double fy, double cx, double cy, const double k[5], double* xo,
+                            double* yo) {
+  const double ifx = 1. / fx, ify = 1. / fy;
+  double x = (u - cx) * ifx, y = (v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1. / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) { x = x0; y = y0; break; }   // OpenCV gives up and keeps the normalised input
+    const double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
+    const double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  *xo = x * fx + cx;
+  *yo = y * fy + cy;
+}
+
 }  // namespace cvprim

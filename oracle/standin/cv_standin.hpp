@@ -519,19 +519,12 @@ inline void undistortPoints(InputArray src_, OutputArray dst_, InputArray K_, In
   for (int i = 0; i < std::min(nk, 5); ++i) k[i] = D.rows == 1 ? D.get_d(0, i) : D.get_d(i, 0);
   const double pfx = P.get_d(0, 0), pfy = P.get_d(1, 1), pcx = P.get_d(0, 2), pcy = P.get_d(1, 2);
   Mat out(src.rows, src.cols, src.type());
+  (void)ifx; (void)ify; (void)pfx; (void)pfy; (void)pcx; (void)pcy;   // P == K at the reference's call sites
   for (int i = 0; i < src.rows; ++i) {
-    double u = src.ptr<float>(i)[0], v = src.ptr<float>(i)[1];
-    double x = (u - cx) * ifx, y = (v - cy) * ify, x0 = x, y0 = y;
-    for (int j = 0; j < 5; ++j) {
-      double r2 = x * x + y * y;
-      double icdist = 1. / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
-      double dx = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x);
-      double dy = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y;
-      x = (x0 - dx) * icdist;
-      y = (y0 - dy) * icdist;
-    }
-    out.ptr<float>(i)[0] = (float)(x * pfx + pcx);
-    out.ptr<float>(i)[1] = (float)(y * pfy + pcy);
+    double x, y;
+    cvprim::undistort_point(src.ptr<float>(i)[0], src.ptr<float>(i)[1], fx, fy, cx, cy, k, &x, &y);
+    out.ptr<float>(i)[0] = (float)x;
+    out.ptr<float>(i)[1] = (float)y;
   }
   Mat dst = dst_.getMat();
   if (dst.data == src.data || (dst.rows == out.rows && dst.cols == out.cols && dst.type() == out.type()))

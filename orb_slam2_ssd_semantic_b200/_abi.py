@@ -231,3 +231,7 @@ class TriKFView:
         s.n_nodes = self.n_nodes
         s.node_ids, s.node_off, s.idx = ptr(self.node_ids), ptr(self.node_off), ptr(self.idx)
         return s
+
+
+class OrbmFrustumPoints(C.Structure):
+    _fields_ = [("n", C.c_int), ("xw", vp), ("normal", vp), ("min_dist", vp), ("max_dist", vp)]

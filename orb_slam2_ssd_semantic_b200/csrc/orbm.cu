@@ -1,5 +1,6 @@
 // orbm.cu -- host side + C-ABI of the B200 ORB matcher (reference: src/ORBmatcher.cc, include/ORBmatcher.h).
 #include <algorithm>
+#include <cmath>
 #include <new>
 #include <vector>
 
@@ -465,6 +466,91 @@ int orbm_search_for_triangulation(orbm_t* h, const OrbmTriKF* k1, const OrbmTriK
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync(matches12, d_out, sizeof(int) * n1, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaMemcpyAsync(nmatches, d_nm, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+// smallest-to-largest thresholds t_k on ratio with  ceil(logf(ratio) / L) <= k  <=>  ratio <= t_k : MapPoint::PredictScale
+// (src/MapPoint.cc:463-478) evaluates ceil(log(ratio)/mfLogScaleFactor) with the HOST's libm; bisecting the float line with
+// that very function gives the device an exact, transcendental-free form of it
+static void predict_scale_thresholds(float log_scale_factor, int nlevels, float* thr) {
+  auto level = [&](float r) { return (int)std::ceil(std::log(r) / log_scale_factor); };
+  for (int k = 0; k < nlevels - 1; ++k) {
+    uint32_t lo = 0x00000001u, hi = 0x7f7fffffu;   // positive finite floats, ordered like their bit patterns
+    float flo, fhi;
+    memcpy(&fhi, &hi, 4);
+    if (level(fhi) <= k) { thr[k] = fhi; continue; }
+    memcpy(&flo, &lo, 4);
+    if (level(flo) > k) { thr[k] = 0.f; continue; }
+    while (hi - lo > 1) {   // invariant: level(lo) <= k < level(hi)
+      const uint32_t mid = lo + (hi - lo) / 2;
+      float fm;
+      memcpy(&fm, &mid, 4);
+      if (level(fm) <= k) lo = mid; else hi = mid;
+    }
+    memcpy(&thr[k], &lo, 4);
+  }
+}
+
+int orbm_is_in_frustum(orbm_t* h, const OrbmFrame* f, const OrbmFrustumPoints* p, float viewing_cos_limit,
+                       float log_scale_factor, uint8_t* in_view, float* proj_x, float* proj_y, float* proj_xr,
+                       int32_t* scale_level, float* view_cos) {
+  if (!h || !f || !p || !in_view || !proj_x || !proj_y || !proj_xr || !scale_level || !view_cos) { set_error("null argument"); return B200ORB_EINVAL; }
+  if (p->n < 0 || f->nlevels < 1 || f->nlevels > MAX_LEVELS || !(log_scale_factor > 0)) { set_error("bad argument"); return B200ORB_EINVAL; }
+  if (p->n == 0) return B200ORB_OK;
+  if (!p->xw || !p->normal || !p->min_dist || !p->max_dist) { set_error("null point array"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  const size_t n = p->n;
+  B200_CHECK(h->reserve(n * (12 + 12 + 4 + 4 + 1 + 4 * 5) + 8192));
+  Carver cm(h->d_arena);
+  float* d_xw = cm.take<float>(n * 3); float* d_nrm = cm.take<float>(n * 3); float* d_mn = cm.take<float>(n); float* d_mx = cm.take<float>(n);
+  uint8_t* d_in = cm.take<uint8_t>(n); float* d_px = cm.take<float>(n); float* d_py = cm.take<float>(n); float* d_pxr = cm.take<float>(n);
+  int* d_lvl = cm.take<int>(n); float* d_vc = cm.take<float>(n);
+  UP(d_xw, p->xw, n * 3, float); UP(d_nrm, p->normal, n * 3, float); UP(d_mn, p->min_dist, n, float); UP(d_mx, p->max_dist, n, float);
+  B200_CUDA(cudaMemsetAsync(d_px, 0, 4 * n, h->stream)); B200_CUDA(cudaMemsetAsync(d_py, 0, 4 * n, h->stream));
+  B200_CUDA(cudaMemsetAsync(d_pxr, 0, 4 * n, h->stream)); B200_CUDA(cudaMemsetAsync(d_lvl, 0, 4 * n, h->stream));
+  B200_CUDA(cudaMemsetAsync(d_vc, 0, 4 * n, h->stream));
+  FrustumView v;
+  memset(&v, 0, sizeof(v));
+  v.xw = d_xw; v.normal = d_nrm; v.min_dist = d_mn; v.max_dist = d_mx; v.n = (int)n;
+  memcpy(v.Tcw, f->Tcw, 64);
+  v.fx = f->fx; v.fy = f->fy; v.cx = f->cx; v.cy = f->cy; v.bf = f->bf;
+  v.min_x = f->min_x; v.max_x = f->max_x; v.min_y = f->min_y; v.max_y = f->max_y;
+  v.cos_limit = viewing_cos_limit; v.nlevels = f->nlevels;
+  predict_scale_thresholds(log_scale_factor, f->nlevels, v.level_thr);
+  k_is_in_frustum<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(v, d_in, d_px, d_py, d_pxr, d_lvl, d_vc);
+  ++h->launches;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(in_view, d_in, n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(proj_x, d_px, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(proj_y, d_py, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(proj_xr, d_pxr, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(scale_level, d_lvl, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(view_cos, d_vc, 4 * n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return B200ORB_OK;
+}
+
+int orbm_undistort_keypoints(orbm_t* h, const float* xy_in, int n, const float K[9], const float* dist, int ndist,
+                             float* xy_out) {
+  if (!h || !K || (n > 0 && (!xy_in || !xy_out)) || n < 0 || ndist < 0 || ndist > 5 || (ndist > 0 && !dist)) { set_error("bad argument"); return B200ORB_EINVAL; }
+  if (n == 0) return B200ORB_OK;
+  if (ndist == 0 || dist[0] == 0.0f) {   // src/Frame.cc:561-565: mvKeysUn = mvKeys
+    memcpy(xy_out, xy_in, sizeof(float) * 2 * (size_t)n);
+    return B200ORB_OK;
+  }
+  DeviceGuard g(h->device);
+  B200_CHECK(h->reserve((size_t)n * 16 + 4096));
+  Carver cm(h->d_arena);
+  float* d_in = cm.take<float>((size_t)n * 2); float* d_out = cm.take<float>((size_t)n * 2);
+  UP(d_in, xy_in, (size_t)n * 2, float);
+  UndistortParams p;
+  p.fx = K[0]; p.fy = K[4]; p.cx = K[2]; p.cy = K[5];
+  for (int i = 0; i < 5; ++i) p.k[i] = i < ndist ? (double)dist[i] : 0.0;
+  k_undistort_points<<<(n + 255) / 256, 256, 0, h->stream>>>(p, d_in, d_out, n);
+  ++h->launches;
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(xy_out, d_out, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   return B200ORB_OK;
 }

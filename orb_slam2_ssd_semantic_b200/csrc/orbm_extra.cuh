@@ -243,4 +243,86 @@ __global__ void __launch_bounds__(32) k_init_search(CurView f2, InitView v, Matc
   if (lane == 0) *nmatch = cnt;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame glue: Frame::isInFrustum (src/Frame.cc:387-451) and Frame::UndistortKeyPoints (src/Frame.cc:559-590)
+// ---------------------------------------------------------------------------------------------------------------------
+struct FrustumView {
+  const float *xw, *normal, *min_dist, *max_dist;   // GetWorldPos(), GetNormal(), mfMinDistance, mfMaxDistance
+  int n;
+  float Tcw[16];
+  float fx, fy, cx, cy, bf, min_x, max_x, min_y, max_y;
+  float cos_limit;
+  float level_thr[MAX_LEVELS];   // PredictScale as thresholds on ratio = mfMaxDistance / dist (built on the host with libm)
+  int nlevels;
+};
+
+__global__ void k_is_in_frustum(FrustumView f, uint8_t* __restrict__ in_view, float* __restrict__ px, float* __restrict__ py,
+                                float* __restrict__ pxr, int* __restrict__ level, float* __restrict__ vcos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f.n) return;
+  in_view[i] = 0;
+  const float* T = f.Tcw;
+  const float P[3] = {f.xw[3 * i], f.xw[3 * i + 1], f.xw[3 * i + 2]};
+  const float PcX = gemm3(T + 0, P[0], P[1], P[2], T[3]);      // mRcw*P+mtcw
+  const float PcY = gemm3(T + 4, P[0], P[1], P[2], T[7]);
+  const float PcZ = gemm3(T + 8, P[0], P[1], P[2], T[11]);
+  if (PcZ < 0.0f) return;
+  const float invz = __fdiv_rn(1.0f, PcZ);
+  const float u = __fadd_rn(__fmul_rn(__fmul_rn(f.fx, PcX), invz), f.cx);
+  const float v = __fadd_rn(__fmul_rn(__fmul_rn(f.fy, PcY), invz), f.cy);
+  if (u < f.min_x || u > f.max_x) return;
+  if (v < f.min_y || v > f.max_y) return;
+  const float maxDistance = __fmul_rn(1.2f, f.max_dist[i]);     // GetMaxDistanceInvariance (src/MapPoint.cc:436-437)
+  const float minDistance = __fmul_rn(0.8f, f.min_dist[i]);
+  float Ow[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a)   // mOw = -mRwc*mtcw (src/Frame.cc:373): small-matrix gemm, float accumulation
+    Ow[a] = -__fadd_rn(__fadd_rn(__fmul_rn(T[0 * 4 + a], T[3]), __fmul_rn(T[1 * 4 + a], T[7])), __fmul_rn(T[2 * 4 + a], T[11]));
+  const float PO[3] = {__fsub_rn(P[0], Ow[0]), __fsub_rn(P[1], Ow[1]), __fsub_rn(P[2], Ow[2])};
+  double n2 = 0, dot = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    n2 = __dadd_rn(n2, __dmul_rn((double)PO[a], (double)PO[a]));
+    dot = __dadd_rn(dot, __dmul_rn((double)PO[a], (double)f.normal[3 * i + a]));
+  }
+  const float dist = (float)sqrt(n2);
+  if (dist < minDistance || dist > maxDistance) return;
+  const float viewCos = (float)__ddiv_rn(dot, (double)dist);
+  if (viewCos < f.cos_limit) return;
+  const float ratio = __fdiv_rn(f.max_dist[i], dist);           // MapPoint::PredictScale (src/MapPoint.cc:463-478)
+  int lvl = 0;
+  for (int k = 0; k < f.nlevels - 1; ++k) lvl += (ratio > f.level_thr[k]) ? 1 : 0;
+  in_view[i] = 1;
+  px[i] = u; py[i] = v;
+  pxr[i] = __fsub_rn(u, __fmul_rn(f.bf, invz));
+  level[i] = lvl;
+  vcos[i] = viewCos;
+}
+
+// cv::undistortPoints(src, dst, K, distCoeffs, R = I, P = K): 5 fixed-point iterations in double (OpenCV's default
+// termination criteria), result stored as float.  k = k1 k2 p1 p2 k3.
+struct UndistortParams { double fx, fy, cx, cy, k[5]; };
+__global__ void k_undistort_points(UndistortParams p, const float* __restrict__ in, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double ifx = __ddiv_rn(1.0, p.fx), ify = __ddiv_rn(1.0, p.fy);
+  const double u = in[2 * i], v = in[2 * i + 1];
+  double x = __dmul_rn(__dsub_rn(u, p.cx), ifx), y = __dmul_rn(__dsub_rn(v, p.cy), ify);
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    const double poly = __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.k[4], r2), p.k[1]), r2), p.k[0]), r2);
+    const double icdist = __ddiv_rn(1.0, __dadd_rn(1.0, poly));
+    if (icdist < 0) { x = x0; y = y0; break; }
+    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p.k[2]), x), y),
+                                __dmul_rn(p.k[3], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+    const double dy = __dadd_rn(__dmul_rn(p.k[2], __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                __dmul_rn(__dmul_rn(__dmul_rn(2.0, p.k[3]), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+  }
+  out[2 * i] = (float)__dadd_rn(__dmul_rn(x, p.fx), p.cx);
+  out[2 * i + 1] = (float)__dadd_rn(__dmul_rn(y, p.fy), p.cy);
+}
+
 }  // namespace b200

@@ -49,10 +49,10 @@ __global__ void __launch_bounds__(256) k_frame_glue(const OrbxKeyPoint* __restri
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const float Rwc[3] = {T[0 * 4 + r], T[1 * 4 + r], T[2 * 4 + r]};   // mRwc = mRcw.t()
-      double s = 0;                                                       // mOw = -mRcw.t()*mtcw (double gemm)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s = __dadd_rn(s, __dmul_rn((double)T[k * 4 + r], (double)T[k * 4 + 3]));
-      o.xw[g * 3 + r] = gemm3(Rwc, x, y, d, __double2float_rn(-s));
+      // mOw = -mRwc*mtcw (src/Frame.cc:373 -- this fork multiplies the EVALUATED transpose, so the product takes the
+      // small-matrix gemm path: float accumulation left to right, alpha = -1)
+      const float ow = -__fadd_rn(__fadd_rn(__fmul_rn(Rwc[0], T[3]), __fmul_rn(Rwc[1], T[7])), __fmul_rn(Rwc[2], T[11]));
+      o.xw[g * 3 + r] = gemm3(Rwc, x, y, d, ow);
     }
     ok = 1;
   }

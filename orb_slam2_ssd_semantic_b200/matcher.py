@@ -125,5 +125,31 @@ class ORBmatcher:
                                                          int(self.mbCheckOrientation), ptr(out), C.byref(nm)))
         return nm.value, out[:pKF1.n]
 
+    def IsInFrustum(self, F: FrameView, xw, normal, min_dist, max_dist, viewingCosLimit: float, log_scale_factor: float):
+        """Frame::isInFrustum (src/Frame.cc:387-451) for n MapPoints -> a TrackPointsView-ready tuple
+        (in_view, proj_x, proj_y, proj_xr, scale_level, view_cos)."""
+        from ._abi import OrbmFrustumPoints
+        xw = np.ascontiguousarray(xw, np.float32).reshape(-1, 3)
+        nr = np.ascontiguousarray(normal, np.float32).reshape(-1, 3)
+        mn, mx = np.ascontiguousarray(min_dist, np.float32), np.ascontiguousarray(max_dist, np.float32)
+        n = len(xw)
+        p = OrbmFrustumPoints(n, ptr(xw), ptr(nr), ptr(mn), ptr(mx))
+        iv = np.zeros(max(n, 1), np.uint8)
+        px, py, pxr, vc = [np.zeros(max(n, 1), np.float32) for _ in range(4)]
+        lvl = np.zeros(max(n, 1), np.int32)
+        fs = F.struct()
+        _lib.check(self._L.orbm_is_in_frustum(self._h, C.byref(fs), C.byref(p), float(viewingCosLimit), float(log_scale_factor),
+                                              ptr(iv), ptr(px), ptr(py), ptr(pxr), ptr(lvl), ptr(vc)))
+        return iv[:n], px[:n], py[:n], pxr[:n], lvl[:n], vc[:n]
+
+    def UndistortKeyPoints(self, xy, K, dist):
+        """Frame::UndistortKeyPoints (src/Frame.cc:559-590) on n x 2 keypoint positions."""
+        xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        K = np.ascontiguousarray(K, np.float32).reshape(9)
+        d = np.ascontiguousarray(dist, np.float32)
+        out = np.zeros_like(xy)
+        _lib.check(self._L.orbm_undistort_keypoints(self._h, ptr(xy), len(xy), ptr(K), ptr(d), len(d), ptr(out)))
+        return out
+
     def launch_count(self) -> int:
         return int(self._L.orbm_launch_count(self._h))

@@ -223,3 +223,36 @@ def test_reference_frame_constructor_and_pipeline_through_shims(both):
     pa = R.pipeline_run(gray, depth, T, 2, 1000, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
     pb = S.pipeline_run(gray, depth, T, 2, 1000, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF)
     assert (pa[1] == pb[1]).all() and (pa[2] == pb[2]).all() and pa[2][1:].min() > 100
+
+
+def test_frame_glue_is_in_frustum_and_undistort_match_oracle(matcher, oracle):
+    """orbm_is_in_frustum (Frame::isInFrustum + PredictScale) and orbm_undistort_keypoints (Frame::UndistortKeyPoints)
+    against the flat oracles (pinned to the reference's Frame.cc / MapPoint.cc in tests/test_refsrc_cpu.py)."""
+    rng = np.random.default_rng(191)
+    m = matcher(0.8, True)
+    for case in range(4):
+        n = 20000
+        X = G.world_points(rng, n)
+        X[: n // 10, 2] *= -1
+        T = G.pose(rng, 0.3, 8.0)
+        F, _ = _rframe(rng, 50)
+        F.Tcw = T.reshape(16)
+        PO = X - G.camera_centre(T)
+        dist = np.linalg.norm(PO, axis=1)
+        normal = PO / dist[:, None] + rng.normal(0, 0.5, (n, 3))
+        normal /= np.linalg.norm(normal, axis=1)[:, None]
+        lvl = rng.integers(0, 9, n)
+        maxd = (dist * 1.2 ** lvl * rng.uniform(0.999, 1.001, n)).astype(np.float32)   # ratios AT the level boundaries
+        mind = (maxd / 1.2 ** 7 * rng.uniform(0.5, 1.4, n)).astype(np.float32)
+        lsf = float(np.log(np.float32(1.2)))
+        a = m.IsInFrustum(F, X, normal, mind, maxd, 0.5, lsf)
+        b = oracle.is_in_frustum(F, X, normal, mind, maxd, 0.5, lsf, "oracle")
+        assert 0.15 * n < b[0].sum() < 0.9 * n
+        for x, y in zip(a, b):
+            assert np.asarray(x).tobytes() == np.asarray(y).tobytes(), case
+    Kmat = np.array([synth.FX, 0, synth.CX, 0, synth.FY, synth.CY, 0, 0, 1], np.float32)
+    xy = np.stack([rng.uniform(0, 640, 5000), rng.uniform(0, 480, 5000)], 1).astype(np.float32)
+    for dist in ([-0.28, 0.07, 0.0002, 0.0001], [0.26, -0.95, -0.005, 0.003, 1.16], [0.0, 0.1, 0, 0]):
+        a = m.UndistortKeyPoints(xy, Kmat, np.array(dist, np.float32))
+        b = oracle.undistort(xy, Kmat, np.array(dist, np.float32))
+        assert a.tobytes() == b.tobytes(), dist

@@ -347,3 +347,45 @@ def test_reference_members_run_on_synthetic_graphs(src):
     T12 = T.astype(np.float64) @ np.linalg.inv(T2.astype(np.float64))
     nf3, m12 = M.search_by_sim3(KF, KF2, kf_mps, mp2, np.full(KF.n, -1, np.int32), 1.0, T12[:3, :3], T12[:3, 3], 7.5)
     assert nf3 > 20 and (m12 >= 0).sum() == nf3
+
+
+def test_frame_glue_equals_reference_sources(src):
+    """Frame::isInFrustum + MapPoint::PredictScale and Frame::UndistortKeyPoints: the flat oracles against the reference's
+    own Frame.cc / MapPoint.cc (isInFrustum per point on a real Frame; UndistortKeyPoints through the real RGB-D Frame
+    constructor with a distorted camera)."""
+    from tests import members_gen as G
+    rng = np.random.default_rng(91)
+    for case in range(4):
+        n = 3000
+        X = G.world_points(rng, n)
+        X[: n // 10, 2] *= -1                       # behind the camera
+        T = G.pose(rng, 0.3, 8.0)
+        F, _ = _random_frame(rng, 50, False)
+        F.Tcw = T.reshape(16)
+        PO = X - G.camera_centre(T)
+        dist = np.linalg.norm(PO, axis=1)
+        normal = PO / dist[:, None] + rng.normal(0, 0.5, (n, 3))
+        normal /= np.linalg.norm(normal, axis=1)[:, None]
+        lvl = rng.integers(0, 9, n)
+        maxd = (dist * 1.2 ** lvl * rng.uniform(0.97, 1.03, n)).astype(np.float32)   # ratios close to the level boundaries
+        mind = (maxd / 1.2 ** 7 * rng.uniform(0.5, 1.4, n)).astype(np.float32)
+        a = src.is_in_frustum(F, X, normal, mind, maxd, 0.5, np.log(np.float32(1.2)), "oracle")
+        b = src.is_in_frustum(F, X, normal, mind, maxd, 0.5, np.log(np.float32(1.2)), "refsrc")
+        assert 0.15 * n < a[0].sum() < 0.9 * n
+        assert (a[0] == b[0]).all()
+        m = a[0] > 0
+        for x, y in zip(a[1:], b[1:]):
+            assert x[m].tobytes() == y[m].tobytes(), case
+        assert len(np.unique(a[4][m])) >= 6
+    # UndistortKeyPoints through the real Frame constructor
+    rs = synth.RoomStream(seed=9, n=4)
+    gray, depth, rgb, T = rs.frame(2)
+    dist4 = np.array([-0.28, 0.07, 0.0002, 0.0001], np.float32)
+    K, D = src.RefExtractor(800, 1.2, 8, 20, 7)(gray)
+    Kun, D2, ur, dp, xw, va = src.src_frame_rgbd(gray, depth, T, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, nfeatures=800,
+                                                 dist=dist4)
+    assert len(K) == len(Kun) and (D == D2).all()
+    Kmat = np.array([synth.FX, 0, synth.CX, 0, synth.FY, synth.CY, 0, 0, 1], np.float32)
+    un = src.undistort(np.stack([K["x"], K["y"]], 1), Kmat, dist4)
+    assert un[:, 0].tobytes() == Kun["x"].tobytes() and un[:, 1].tobytes() == Kun["y"].tobytes()
+    assert np.abs(un[:, 0] - K["x"]).max() > 1.0      # the distortion does move points
