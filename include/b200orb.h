@@ -281,6 +281,25 @@ int orbm_undistort_keypoints(orbm_t* h, const float* xy_in, int n, const float K
                              float* xy_out);
 
 /* ------------------------------------------------------------------------------------------------
+ * BoW transform -- Frame::ComputeBoW / KeyFrame::ComputeBoW (src/Frame.cc:546-555, src/KeyFrame.cc:75-84):
+ * mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) of DBoW2's TemplatedVocabulary (k-ary tree; ORBvoc: k = 10,
+ * L = 6).  orbv_create uploads the tree: node 0 = root, parent[i] < i, children visited in ascending node id, leaves are
+ * the words numbered in ascending node id, desc n_nodes x 32, weight = node weights (TF-IDF: the idf of the word).
+ * orbv_transform descends every descriptor (first child at minimal Hamming distance per level) and returns per feature
+ * the word id, the word's weight and the id of the ancestor `levelsup` levels above the leaves (0 = root when L - levelsup
+ * <= 0).  The caller builds the maps in feature order exactly like TemplatedVocabulary::transform does:
+ *   if (weight > 0) { BowVector.addWeight(word, weight); FeatureVector.addFeature(node, i); }  then  BowVector.normalize(L1).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct orbv orbv_t;
+int orbv_create(int device, int k, int L, int n_nodes, const int32_t* parent, const uint8_t* desc, const double* weight,
+                const int32_t* word_id /* per node, read at leaves; NULL = leaves numbered in ascending node id */, orbv_t** out);
+void orbv_destroy(orbv_t* h);
+int orbv_num_words(const orbv_t* h);
+long long orbv_launch_count(const orbv_t* h);
+int orbv_transform(orbv_t* h, const uint8_t* desc, int n, int levelsup, uint32_t* word_id, double* word_weight,
+                   uint32_t* node_id);
+
+/* ------------------------------------------------------------------------------------------------
  * Stream pipeline (batched many-frame mode of north_star): per frame t of a batch, what
  * Tracking::GrabImageRGBD -> Frame::Frame(RGB-D) -> TrackWithMotionModel's SearchByProjection do
  * (src/Tracking.cc:331-375,1324-1352; src/Frame.cc:176-240): extract, ComputeStereoFromRGBD

@@ -843,3 +843,85 @@ def undistort(xy, K, dist):
     out = np.zeros_like(xy)
     L.orb_ref_undistort(_p(xy), len(xy), _p(K), _p(d), len(d), _p(out))
     return out
+
+
+def synth_vocabulary(seed=3, k=10, L=3, stop_frac=0.05):
+    """A synthetic DBoW2-shaped vocabulary: k-ary tree of depth L, children = parent descriptor with ~24 random bits
+    flipped, positive idf-like leaf weights (a few 0 = stopped words).  -> (parent, node_desc, weight) in node-id order
+    (breadth first, so parent[i] < i and siblings have ascending ids)."""
+    rng = np.random.default_rng(seed)
+    parent, desc, level = [0], [np.zeros(32, np.uint8)], [0]
+    frontier = [0]
+    for lvl in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            for _ in range(k):
+                d = desc[p].copy() if p else rng.integers(0, 256, 32, dtype=np.uint8)
+                if p:
+                    bits = rng.integers(0, 256, 24 // lvl + 4)
+                    for b in bits:
+                        d[b >> 3] ^= np.uint8(1 << (b & 7))
+                parent.append(p); desc.append(d); level.append(lvl)
+                nxt.append(len(parent) - 1)
+        frontier = nxt
+    n = len(parent)
+    weight = np.where(np.array(level) == L, rng.uniform(0.5, 9.0, n), 0.0)
+    weight[(np.array(level) == L) & (rng.random(n) < stop_frac)] = 0.0
+    return np.array(parent, np.int32), np.stack(desc).astype(np.uint8), weight.astype(np.float64)
+
+
+def bow_transform_py(k, L, parent, node_desc, weight, desc, levelsup=4):
+    """Pure-numpy restatement of TemplatedVocabulary::transform (TF-IDF, L1) -> (bow dict, featvec dict)."""
+    n_nodes = len(parent)
+    children = [[] for _ in range(n_nodes)]
+    for i in range(1, n_nodes):
+        children[parent[i]].append(i)
+    word_of, nw = {}, 0
+    for i in range(1, n_nodes):
+        if not children[i]:
+            word_of[i] = nw
+            nw += 1
+    bits = np.unpackbits(node_desc, axis=1)
+    bow, fv = {}, {}
+    for fi, d in enumerate(np.asarray(desc, np.uint8).reshape(-1, 32)):
+        db = np.unpackbits(d)
+        cur, lvl, nid = 0, 0, 0
+        while children[cur]:
+            lvl += 1
+            ch = children[cur]
+            dist = (bits[ch] != db).sum(1)
+            cur = ch[int(np.argmin(dist))]          # argmin: first minimum
+            if lvl == L - levelsup:
+                nid = cur
+        w = float(weight[cur])
+        if w > 0:
+            bow[word_of[cur]] = bow.get(word_of[cur], 0.0) + w
+            fv.setdefault(nid, []).append(fi)
+    norm = 0.0
+    for key in sorted(bow):
+        norm += abs(bow[key])
+    if norm > 0:
+        for key in bow:
+            bow[key] /= norm
+    return bow, fv
+
+
+def src_bow_transform(k, L, parent, node_desc, weight, desc, prefix="refsrc"):
+    """Frame::ComputeBoW of the reference (prefix refsrc: stand-in DBoW2 on the CPU; shimsrc: shim ORBVocabulary on the
+    GPU) -> (bow dict, featvec dict)."""
+    Lb = reflib() if prefix == "refsrc" else shimlib()
+    f = getattr(Lb, prefix + "_bow_transform")
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+    parent = np.ascontiguousarray(parent, np.int32)
+    node_desc = np.ascontiguousarray(node_desc, np.uint8)
+    weight = np.ascontiguousarray(weight, np.float64)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(desc)
+    words, values = np.zeros(n + 1, np.uint32), np.zeros(n + 1, np.float64)
+    node_ids, node_off, idx = np.zeros(n + 1, np.uint32), np.zeros(n + 2, np.int32), np.zeros(n + 1, np.uint32)
+    nw, nn = C.c_int(0), C.c_int(0)
+    f(k, L, len(parent), _p(parent), _p(node_desc), _p(weight), _p(desc), n, 4, _p(words), _p(values), C.byref(nw), _p(node_ids),
+      _p(node_off), _p(idx), C.byref(nn))
+    bow = {int(words[i]): float(values[i]) for i in range(nw.value)}
+    fv = {int(node_ids[j]): [int(v) for v in idx[node_off[j]:node_off[j + 1]]] for j in range(nn.value)}
+    return bow, fv

@@ -38,6 +38,7 @@
 #include "MapPoint.h"
 #include "Map.h"
 #include "KeyFrameDatabase.h"
+#include "ORBVocabulary.h"
 #undef private
 #undef protected
 
@@ -795,6 +796,46 @@ int X(kf_best)(const OrbmFrame* kf, const OrbmQueries* q, int32_t* best_idx, int
     }
   }
   delete K; delete FK;
+  return 0;
+}
+
+
+// Frame::ComputeBoW (src/Frame.cc:546-555) on a real Frame with a vocabulary built from flat arrays (node 0 = root,
+// parent[i] < i, leaves = words in ascending id): -> the BowVector as (word, value) pairs in map order and the
+// FeatureVector flattened (node ids ascending, feature indices per node in insertion order).
+int X(bow_transform)(int k, int L, int n_nodes, const int32_t* parent, const uint8_t* node_desc, const double* weight,
+                     const uint8_t* desc, int n, int levelsup_unused, uint32_t* words, double* values, int* n_words,
+                     uint32_t* node_ids, int32_t* node_off, uint32_t* idx, int* n_nodes_out) {
+  (void)levelsup_unused;   // ComputeBoW hard-codes 4
+  std::lock_guard<std::mutex> lk(g_mu);
+  ORBVocabulary voc(k, L, DBoW2::TF_IDF, DBoW2::L1_NORM);
+  std::vector<DBoW2::NodeId> par(n_nodes);
+  std::vector<cv::Mat> nd(n_nodes);
+  std::vector<DBoW2::WordValue> w(weight, weight + n_nodes);
+  for (int i = 0; i < n_nodes; ++i) { par[i] = (DBoW2::NodeId)parent[i]; nd[i] = desc_row(node_desc + 32 * (size_t)i); }
+  voc.build(k, L, par, nd, w);
+  std::vector<float> zf(n, 0.f);
+  std::vector<int32_t> zi(n, 0);
+  OrbmBow b;
+  memset(&b, 0, sizeof(b));
+  b.n = n; b.desc = desc; b.angle = zf.data();
+  OrbmFrame v = bow_as_frame(&b, zf, zi);
+  Frame* F = make_frame(&v);
+  F->mpORBvocabulary = &voc;
+  F->ComputeBoW();
+  int nw = 0;
+  for (auto& kv : F->mBowVec) { words[nw] = kv.first; values[nw] = kv.second; ++nw; }
+  *n_words = nw;
+  int nn = 0, ni = 0;
+  node_off[0] = 0;
+  for (auto& kv : F->mFeatVec) {
+    node_ids[nn] = kv.first;
+    for (unsigned int f : kv.second) idx[ni++] = f;
+    node_off[++nn] = ni;
+  }
+  *n_nodes_out = nn;
+  F->mpORBvocabulary = nullptr;
+  delete F;
   return 0;
 }
 

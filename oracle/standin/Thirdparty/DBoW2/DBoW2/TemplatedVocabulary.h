@@ -37,7 +37,8 @@ template <class TDescriptor, class F> class TemplatedVocabulary {
     for (size_t i = 0; i < m_nodes.size(); ++i)
       if (i && m_nodes[i].isLeaf()) { m_nodes[i].word_id = (WordId)m_words.size(); m_words.push_back(&m_nodes[i]); }
   }
-  void transform(const std::vector<TDescriptor>& features, BowVector& v, FeatureVector& fv, int levelsup) const {
+  virtual ~TemplatedVocabulary() {}
+  virtual void transform(const std::vector<TDescriptor>& features, BowVector& v, FeatureVector& fv, int levelsup) const {
     v.clear(); fv.clear();
     if (empty()) return;
     const bool must = (m_scoring == L1_NORM || m_scoring == L2_NORM);
@@ -87,6 +88,7 @@ template <class TDescriptor, class F> class TemplatedVocabulary {
     }
     return -score / 2.0;
   }
+protected:
   int m_k, m_L;
   WeightingType m_weighting;
   ScoringType m_scoring;

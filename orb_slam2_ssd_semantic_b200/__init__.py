@@ -9,5 +9,6 @@ from .extractor import KP_DTYPE, ORBextractor  # noqa: F401
 from .matcher import ORBmatcher, FrameView, LastView, TrackPointsView, BowView, QueriesView  # noqa: F401
 from .pipeline import StreamTracker  # noqa: F401
 from .mapping import GlobalCloudMapping, PointCloudMapping  # noqa: F401
+from .vocabulary import ORBVocabulary  # noqa: F401
 
 __all__ = ["ORBextractor", "KP_DTYPE", "B200OrbError", "lib", "library_path"]

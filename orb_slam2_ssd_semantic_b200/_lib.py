@@ -28,7 +28,7 @@ EXPORTS = [
     "orbx_get_level", "orbx_scale_tables", "orbx_candidates_per_level", "orbx_launch_count",
     "orbx_profile_enable", "orbx_profile_read",
     "orbm_hamming", "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_search_by_projection_last",
-    "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_by_bow_kf", "orbm_search_projected", "orbm_search_best", "orbm_search_for_initialization", "orbm_search_for_triangulation", "orbm_is_in_frustum", "orbm_undistort_keypoints",
+    "orbm_search_by_projection_points", "orbm_search_by_bow", "orbm_search_by_bow_kf", "orbm_search_projected", "orbm_search_best", "orbm_search_for_initialization", "orbm_search_for_triangulation", "orbm_is_in_frustum", "orbm_undistort_keypoints", "orbv_create", "orbv_destroy", "orbv_num_words", "orbv_launch_count", "orbv_transform",
     "orbs_create", "orbs_destroy", "orbs_track_batch", "orbs_track_batch_u16", "orbs_submit_batch_u16", "orbs_device_inputs", "orbs_set_full_depth_upload", "orbs_set_chunk_frames", "orbs_chain_after", "b200orb_depth_u16_to_f32_device", "orbs_track_batch_device", "orbs_device_results", "orbs_sync",
     "orbs_stream", "orbs_launch_count", "orbs_extractor",
     "gcm_create", "gcm_destroy", "gcm_add_keyframe", "gcm_add_keyframe_device", "gcm_refilter", "gcm_size", "gcm_export", "gcm_sync", "gcm_launch_count",
@@ -95,6 +95,13 @@ def lib() -> C.CDLL:
                                                 i, i, vp, C.POINTER(i)]
     L.orbm_is_in_frustum.argtypes = [vp, C.POINTER(OrbmFrame), C.POINTER(OrbmFrustumPoints), C.c_float, C.c_float] + [vp] * 6
     L.orbm_undistort_keypoints.argtypes = [vp, vp, i, vp, vp, i, vp]
+    L.orbv_create.argtypes = [i, i, i, i, vp, vp, vp, vp, C.POINTER(vp)]
+    L.orbv_destroy.argtypes = [vp]
+    L.orbv_destroy.restype = None
+    L.orbv_num_words.argtypes = [vp]
+    L.orbv_launch_count.argtypes = [vp]
+    L.orbv_launch_count.restype = C.c_longlong
+    L.orbv_transform.argtypes = [vp, vp, i, i, vp, vp, vp]
     L.orbs_create.argtypes = [C.POINTER(OrbsParams), i, C.POINTER(vp)]
     L.orbs_destroy.argtypes = [vp]
     L.orbs_destroy.restype = None

@@ -4,3 +4,4 @@
 #include "orbs.cu"
 #include "ocm.cu"
 #include "gcm.cu"
+#include "orbv.cu"

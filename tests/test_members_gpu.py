@@ -256,3 +256,23 @@ def test_frame_glue_is_in_frustum_and_undistort_match_oracle(matcher, oracle):
         a = m.UndistortKeyPoints(xy, Kmat, np.array(dist, np.float32))
         b = oracle.undistort(xy, Kmat, np.array(dist, np.float32))
         assert a.tobytes() == b.tobytes(), dist
+
+
+def test_bow_transform_matches_reference_sources(both, oracle):
+    """orbv_transform + the map assembly of the Python mirror, and the shim ORBVocabulary under the reference's own
+    Frame::ComputeBoW, against Frame::ComputeBoW on the CPU (DBoW2 stand-in): identical BowVector (bit-equal doubles)
+    and FeatureVector."""
+    from orb_slam2_ssd_semantic_b200 import ORBVocabulary
+    for (k, L, seed) in [(10, 5, 3), (6, 6, 4), (10, 4, 5), (4, 3, 6)]:
+        parent, nd, w = oracle.synth_vocabulary(seed, k, L)
+        rng = np.random.default_rng(seed)
+        leaves = np.nonzero(w > 0)[0]
+        desc = nd[rng.choice(leaves, 2000)].copy()
+        desc[:, :2] ^= rng.integers(0, 256, size=(2000, 2), dtype=np.uint8)
+        ref_bow, ref_fv = oracle.src_bow_transform(k, L, parent, nd, w, desc, "refsrc")
+        voc = ORBVocabulary(k, L, parent, nd, w)
+        bow, fv = voc.transform(desc, 4)
+        assert bow.keys() == ref_bow.keys() and all(bow[x] == ref_bow[x] for x in bow), (k, L)
+        assert fv == ref_fv, (k, L)
+        sbow, sfv = oracle.src_bow_transform(k, L, parent, nd, w, desc, "shimsrc")
+        assert sbow == ref_bow and sfv == ref_fv, (k, L)

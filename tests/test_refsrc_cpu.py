@@ -389,3 +389,21 @@ def test_frame_glue_equals_reference_sources(src):
     un = src.undistort(np.stack([K["x"], K["y"]], 1), Kmat, dist4)
     assert un[:, 0].tobytes() == Kun["x"].tobytes() and un[:, 1].tobytes() == Kun["y"].tobytes()
     assert np.abs(un[:, 0] - K["x"]).max() > 1.0      # the distortion does move points
+
+
+def test_bow_transform_restatements_agree(src):
+    """Frame::ComputeBoW of the reference on the DBoW2 stand-in (TemplatedVocabulary::transform restated from DBoW2's
+    published algorithm; DBoW2 itself is not shipped with the reference) against an independent numpy restatement: same
+    words, bit-equal L1-normalised weights, same FeatureVector (node ids 4 levels above the leaves)."""
+    for (k, L, seed) in [(10, 5, 3), (6, 6, 4), (10, 4, 5), (4, 3, 6)]:
+        parent, nd, w = src.synth_vocabulary(seed, k, L)
+        rng = np.random.default_rng(seed)
+        leaves = np.nonzero(w > 0)[0]
+        desc = nd[rng.choice(leaves, 700)].copy()
+        desc[:, :2] ^= rng.integers(0, 256, size=(700, 2), dtype=np.uint8)
+        a = src.src_bow_transform(k, L, parent, nd, w, desc)
+        b = src.bow_transform_py(k, L, parent, nd, w, desc)
+        assert a[0].keys() == b[0].keys() and all(a[0][x] == b[0][x] for x in a[0]), (k, L)
+        assert a[1] == b[1], (k, L)
+        assert len(a[0]) > 50 and abs(sum(a[0].values()) - 1.0) < 1e-9
+        assert len(a[1]) >= (1 if L <= 4 else 6)
