@@ -359,6 +359,10 @@ int orbs_track_batch_device(orbs_t* h, const uint8_t* d_gray, const float* d_dep
                             int nframes, int rows, int cols);
 int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d_desc, const int32_t** d_nkp,
                         const int32_t** d_cur2last, const int32_t** d_nmatch, int* cap);
+/* Frame glue of frame `frame` of the last batch: mvuRight / mvDepth (Frame::ComputeStereoFromRGBD, src/Frame.cc:850-871), the
+ * world point Frame::UnprojectStereo gives per keypoint under that frame's pose (:879-899) and whether the keypoint has
+ * depth; host arrays of at least the handle's keypoint capacity (NULL = skip). */
+int orbs_read_frame_glue(orbs_t* h, int frame, float* uright, float* depth, float* xw, uint8_t* valid, int cap);
 int orbs_sync(orbs_t* h);
 void* orbs_stream(orbs_t* h);
 long long orbs_launch_count(const orbs_t* h);

@@ -244,6 +244,21 @@ int orbs_device_results(orbs_t* h, const OrbxKeyPoint** d_kps, const uint8_t** d
   return B200ORB_OK;
 }
 
+// Frame-glue outputs of frame `frame` of the last batch (Frame::ComputeStereoFromRGBD + UnprojectStereo per keypoint):
+// mvuRight, mvDepth, the world point of the keypoint under the frame's pose, and whether it has depth.
+int orbs_read_frame_glue(orbs_t* h, int frame, float* uright, float* depth, float* xw, uint8_t* valid, int cap) {
+  if (!h || !h->have || frame < 0 || cap < h->cap) { set_error("bad argument"); return B200ORB_EINVAL; }
+  DeviceGuard g(h->device);
+  const size_t o = (size_t)frame * h->cap, n = (size_t)h->cap;
+  cudaStream_t st = h->ex->stream;
+  if (uright) B200_CUDA(cudaMemcpyAsync(uright, h->d_ur + o, 4 * n, cudaMemcpyDeviceToHost, st));
+  if (depth) B200_CUDA(cudaMemcpyAsync(depth, h->d_dep + o, 4 * n, cudaMemcpyDeviceToHost, st));
+  if (xw) B200_CUDA(cudaMemcpyAsync(xw, h->d_xw + o * 3, 12 * n, cudaMemcpyDeviceToHost, st));
+  if (valid) B200_CUDA(cudaMemcpyAsync(valid, h->d_valid + o, n, cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  return B200ORB_OK;
+}
+
 // orbx::after_select hook of the sparse-depth mode: the keypoints of frames [f0, f0 + F) are selected -> fetch the depth
 // under them on the side stream (the stream of the extractor goes on with blur and descriptors meanwhile)
 static int orbs_after_select(void* ctx, int f0, int F) {

@@ -115,6 +115,13 @@ class StreamTracker:
         _lib.check(self._L.orbs_device_results(self._h, *[C.byref(p) for p in ps], C.byref(cap)))
         return [p.value for p in ps], cap.value
 
+    def frame_glue(self, frame: int, n: int):
+        """(uright, depth, xw, valid) of the first n keypoints of `frame` of the last batch."""
+        cap = self.cap
+        ur, dp, xw, va = np.zeros(cap, np.float32), np.zeros(cap, np.float32), np.zeros((cap, 3), np.float32), np.zeros(cap, np.uint8)
+        _lib.check(self._L.orbs_read_frame_glue(self._h, int(frame), ptr(ur), ptr(dp), ptr(xw), ptr(va), cap))
+        return ur[:n], dp[:n], xw[:n], va[:n]
+
     STAGES = ("resize", "fast", "quadtree", "blur", "orient_desc", "glue", "match")
 
     def profile_enable(self, on: bool = True):
