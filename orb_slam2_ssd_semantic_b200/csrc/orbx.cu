@@ -237,8 +237,10 @@ int orbx::ensure_geometry(int r, int c, int F) {
     fast_rows_max = rhm;
     fast_smem = (size_t)FAST_WARPS * (2 * rhm * fast_tp + 2 * FAST_QLEN + 2 * fast_clist_cap);
     if (fast_smem > 48 * 1024) {
-      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
-      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+      B200_CUDA(cudaFuncSetAttribute(k_fast_cells<FAST_TP_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
     }
   }
   slots_per_frame = align_up(slots, 4);
@@ -370,12 +372,15 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
     if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) fast_aligned = 0;
   {
     const dim3 grd((ncells + FAST_WARPS - 1) / FAST_WARPS, F);
-    if (fast_tp == FAST_TP_SMALL)
-      k_fast_cells<FAST_TP_SMALL><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
-                                                                           prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max, fast_clist_cap);
-    else
-      k_fast_cells<FAST_TP_BIG><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,
-                                                                         prm.min_th_fast, d_cand, d_cellcnt, fast_aligned, fast_rows_max, fast_clist_cap);
+    // B200ORB_FAST_SWEEP=1 selects the one-pixel-per-lane sweep (development A/B switch; default: the word sweep)
+    static const bool sweep4 = [] { const char* e = getenv("B200ORB_FAST_SWEEP"); return !(e && e[0] == '1'); }();
+#define B200_FAST_LAUNCH(TPV, S4)                                                                                          \
+  k_fast_cells<TPV, S4><<<grd, FAST_THREADS, fast_smem, stream>>>(rawv, d_cells, ncells, slots_per_frame, prm.ini_th_fast,   \
+                                                                  prm.min_th_fast, d_cand, d_cellcnt, fast_aligned,        \
+                                                                  fast_rows_max, fast_clist_cap)
+    if (fast_tp == FAST_TP_SMALL) { if (sweep4) B200_FAST_LAUNCH(FAST_TP_SMALL, true); else B200_FAST_LAUNCH(FAST_TP_SMALL, false); }
+    else { if (sweep4) B200_FAST_LAUNCH(FAST_TP_BIG, true); else B200_FAST_LAUNCH(FAST_TP_BIG, false); }
+#undef B200_FAST_LAUNCH
   }
   ++launches;
   B200_CHECK(prof_mark(ST_FAST + 1));

@@ -146,7 +146,7 @@ constexpr int FAST_THREADS = FAST_WARPS * 32;
 constexpr int FAST_MAX_ROI = 72;   // ROI side bound enforced at create (cell <= 60 px + 6, padded)
 constexpr int FAST_TP_SMALL = 48;  // compile-time tile pitches (>= 3 + ROI width, multiple of 4): ring offsets are
 constexpr int FAST_TP_BIG = 80;
-constexpr int FAST_QLEN = 64;      // per-warp ring of pixels that passed the compass test (<= 31 pending + 32 new)    // immediates; SMALL serves ROIs up to 45 px (640x480: 43), BIG the general case
+constexpr int FAST_QLEN = 256;     // per-warp ring of pixels that passed the compass test (<= 31 pending + 128 new)    // immediates; SMALL serves ROIs up to 45 px (640x480: 43), BIG the general case
 
 // m(p) of one pixel.  Packing: one IMAD per ring pixel gives lo16 = 256 + (c - r), hi16 = 256 + (r - c) (biased,
 // both in [1, 511], so no borrow crosses the halves); min3/max3 on s16x2 then evaluate the bright and the dark
@@ -191,7 +191,7 @@ __device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
 //   NMS     32 corners at a time: strict 3x3 maximum, order-preserving compaction into the cell's output segment.
 // `aligned` (host-checked): level rows are 4-byte aligned, so the ROI is fetched as aligned 32-bit words and kept
 // at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).
-template <int TP>
+template <int TP, bool SWEEP4>
 __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
                                                                 int ncells, int slots_per_frame, int ini_th,
                                                                 int min_th, unsigned* __restrict__ cand,
@@ -226,9 +226,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, con
       for (int y = 0; y < rh; ++y)
         for (int x = lane; x < rw; x += 32) tile[y * P + x] = __ldg(img + (size_t)y * pitch + x);
     }
-    // only the one-pixel frame around the detection range is read without being written: clear it
-    for (int i = lane; i < rw; i += 32) { tile[2 * P + TP + sh + i] = 0; tile[(rh - 3) * P + TP + sh + i] = 0; }
-    for (int i = lane; i < rh; i += 32) { tile[i * P + TP + sh + 2] = 0; tile[i * P + TP + sh + rw - 3] = 0; }
+    if (SWEEP4 && aligned) {
+      // the word sweep only writes the scores of corners: clear every score row once (rows 2 .. rh-3 are read by the NMS)
+      constexpr int WPR = TP / 4;
+      for (int i = lane; i < (rh - 4) * WPR; i += 32) {
+        const int y = 2 + i / WPR, k = i - (y - 2) * WPR;
+        reinterpret_cast<unsigned*>(tile + y * P + TP)[k] = 0u;
+      }
+    } else {
+      // only the one-pixel frame around the detection range is read without being written: clear it
+      for (int i = lane; i < rw; i += 32) { tile[2 * P + TP + sh + i] = 0; tile[(rh - 3) * P + TP + sh + i] = 0; }
+      for (int i = lane; i < rh; i += 32) { tile[i * P + TP + sh + 2] = 0; tile[i * P + TP + sh + rw - 3] = 0; }
+    }
   }
   __syncwarp();
   unsigned* out = cand + (size_t)f * slots_per_frame + cd.slot_off;
@@ -254,7 +263,66 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, con
       if (cr) clist[cn + __popc(cb & lt_mask)] = (unsigned short)o;
       cn += __popc(cb);
     };
-    {
+    if (SWEEP4 && aligned) {
+      // Word sweep: a thread owns the 4 pixels of one aligned tile word (columns 4g .. 4g+3) of one row; several rows per
+      // warp step.  The compass test runs on pixel PAIRS in s16x2 lanes, bright and dark polarity in separate registers:
+      //   bright: 256 + r - c,  dark: 256 + c - r   (one IADD3 each per ring pixel and pixel pair, operands spread from the
+      //   byte lanes by one PRMT), q = min(max(v0, v8), max(v4, v12)) per polarity, hit <=> q > 256 + t in either.
+      // Queue positions are the pixels' ranks in ROW-MAJOR order (lanes are ordered (row, word); inside a word by column),
+      // so the corner list the dense phase builds stays row-major.
+      const unsigned kq = (unsigned)(0x7fff - 256 - t) * 0x10001u;
+      const int gA = (sh + 3) >> 2, gB = (sh + rw - 4) >> 2, NW = gB - gA + 1;
+      const int RPI = 32 / NW;                       // rows per warp step (NW <= 19 < 32)
+      const int rs = lane / NW, g = gA + (lane - rs * NW);
+      const int cmin = sh + 3, cmax = sh + rw - 3;   // detection columns [cmin, cmax) in tile coordinates
+      const unsigned* trow = reinterpret_cast<const unsigned*>(tile);
+      for (int y0 = 3; y0 < rh - 3; y0 += RPI) {
+        const int y = y0 + rs;
+        unsigned hits = 0;                           // bit k: pixel 4g+k of row y passed
+        if (rs < RPI && y < rh - 3) {
+          const unsigned* wr = trow + (y * P) / 4;
+          const unsigned wc = wr[g], wl = wr[max(g - 1, 0)], wn = wr[g + 1];
+          const unsigned w0 = wr[g + (3 * P) / 4], w8 = wr[g - (3 * P) / 4];
+          const unsigned w12 = __funnelshift_r(wl, wc, 8);     // bytes x-3 of the four pixels
+          const unsigned w4 = __funnelshift_r(wc, wn, 24);     // bytes x+3
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {                     // pixel pairs (0,2) and (1,3)
+            const unsigned sel = h2 ? 0x4341u : 0x4240u;
+            const unsigned C = __byte_perm(wc, 0u, sel), R0 = __byte_perm(w0, 0u, sel), R8 = __byte_perm(w8, 0u, sel);
+            const unsigned R4 = __byte_perm(w4, 0u, sel), R12 = __byte_perm(w12, 0u, sel);
+            const unsigned cb = 0x01000100u - C, cd = 0x01000100u + C;   // halves stay in [1, 511]: no borrow / carry across
+            const unsigned qb = __vmins2(__vmaxs2(R0 + cb, R8 + cb), __vmaxs2(R4 + cb, R12 + cb));
+            const unsigned qd = __vmins2(__vmaxs2(cd - R0, cd - R8), __vmaxs2(cd - R4, cd - R12));
+            const unsigned hb = ((qb + kq) | (qd + kq)) & 0x80008000u;
+            if (hb & 0x8000u) hits |= 1u << h2;
+            if (hb & 0x80000000u) hits |= 4u << h2;
+          }
+          const int c0 = 4 * g;                                // drop the pixels outside the detection columns
+          unsigned cm = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) cm |= ((c0 + k >= cmin) && (c0 + k < cmax)) ? (1u << k) : 0u;
+          hits &= cm;
+        }
+        const unsigned b0 = __ballot_sync(0xffffffffu, hits & 1u), b1 = __ballot_sync(0xffffffffu, hits & 2u);
+        const unsigned b2 = __ballot_sync(0xffffffffu, hits & 4u), b3 = __ballot_sync(0xffffffffu, hits & 8u);
+        if (hits) {
+          int pos = qh + qn + __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+          const int o = y * P + 4 * g;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (hits & (1u << k)) { queue[pos & (FAST_QLEN - 1)] = (unsigned short)(o + k); ++pos; }
+        }
+        qn += __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+        while (qn >= 32) {
+          __syncwarp();
+          dense(queue[(qh + lane) & (FAST_QLEN - 1)], true);
+          qh += 32;
+          qn -= 32;
+        }
+      }
+      __syncwarp();
+      dense((lane < qn) ? queue[(qh + lane) & (FAST_QLEN - 1)] : 0, lane < qn);
+    } else {
       // The compass test in packed form: a 9-arc always holds one pixel of each opposite compass pair, and all its
       // pixels lie on the same side of the centre, so min(max(v0, v8), max(v4, v12)) > 256 + t in either half is
       // necessary for a corner at t.
