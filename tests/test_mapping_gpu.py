@@ -200,3 +200,41 @@ def test_more_keyframes_than_batch_slots(oracle):
     pb, vb = _leaf_dict(*b.export_leaves()[:2])
     assert len(pa) > 500 and (pa == pb).all() and (va == vb).all()
     assert va.max() > 3.0     # repeated hits ran into the upper clamp: the replay order mattered
+
+
+def test_config4_shape_120_keyframes_with_ground_rays(oracle):
+    """BASELINE.json configs[3] shape at a size the CPU oracle finishes in seconds: 120 keyframes of the room stream (every
+    3rd frame of a 360-frame path: walls, floor, ceiling enter and leave the 0.5 - 3 m gate), 0.05 m voxels, 1 cm
+    pre-filter, both label modes -- A: all non-ground (no rays), B: GT floor as ground (free-space rays) -- inserted in
+    batches of 40 (rounds of 32 mask bits + remainder): leaf set identical, log-odds within 1e-5, points of the last
+    keyframe within 1e-5."""
+    import torch
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    rs = synth.RoomStream(seed=77, n=361)
+    fr = [rs.frame(3 * t, with_label=True) for t in range(120)]
+    depth, rgb = np.stack([f[1] for f in fr]), np.stack([f[2] for f in fr])
+    T, label = np.stack([f[3] for f in fr]).astype(np.float32), np.stack([f[4] for f in fr])
+    d_depth, d_rgb, d_lab = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), torch.from_numpy(label).cuda()
+    for mode in ("A", "B"):
+        pcm = PointCloudMapping(0.05)
+        ref = oracle.RefOccupancy()
+        for b in range(0, 120, 40):
+            idx = list(range(b, b + 40))
+            pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), 480, 640, idx, T[idx], synth.FX, synth.FY, synth.CX,
+                                        synth.CY, d_label=d_lab.data_ptr() if mode == "B" else 0)
+        pcm.sync()
+        ref.insert_keyframes_mt(depth, rgb, label if mode == "B" else None, list(range(120)), T, synth.FX, synth.FY, synth.CX,
+                                synth.CY, 8)
+        kr, lr = ref.export_leaves()
+        kg, lg, _ = pcm.export_leaves()
+        pk = lambda k: k.astype(np.uint64)[:, 0] | (k.astype(np.uint64)[:, 1] << np.uint64(16)) | (k.astype(np.uint64)[:, 2] << np.uint64(32))
+        og, orr = np.argsort(pk(kg)), np.argsort(pk(kr))
+        assert len(kg) == len(kr) > 20000 and (pk(kg)[og] == pk(kr)[orr]).all(), mode
+        assert np.abs(lg[og] - lr[orr]).max() <= 1e-5, mode
+        if mode == "B":
+            assert (lr < 0).sum() > 10000
+        xg, _ = pcm.last_points()
+        xr, _, _ = ref.last_points()
+        assert len(xg) == len(xr)
+        key = lambda a: np.lexsort((a[:, 2], a[:, 1], a[:, 0]))
+        assert np.abs(xg[key(xg)] - xr[key(xr)]).max() <= 1e-5

@@ -162,3 +162,46 @@ def test_full_size_batch_against_cpu_pipeline(oracle):
     assert len(kg) == len(kr) and pcm.num_leaves() == len(kr)
     pk = lambda k: np.sort(k.astype(np.uint64)[:, 0] | (k.astype(np.uint64)[:, 1] << np.uint64(16)) | (k.astype(np.uint64)[:, 2] << np.uint64(32)))
     assert (pk(kg) == pk(kr)).all()
+
+
+def test_full_size_bench_workload_against_reference_sources(oracle):
+    """The bench workload at full size, as bench.py runs it: one 256-frame batch of the ROOM stream (non-planar, panning
+    camera), ORBextractor(2000, ...), SearchByProjection(th = 15) -- per-frame keypoint and match counts of the whole batch
+    against the reference's OWN tracking sources (oracle/_ref: Frame constructor + ORBmatcher of /root/reference), three
+    frames keypoint by keypoint against the oracle, and the occupancy map of the batch's 22 keyframes with the GT floor as
+    ground label (free-space rays) against the sequential occupancy oracle: same leaf set, log-odds within 1e-5."""
+    import os
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping, StreamTracker
+    F, KF, NF = 256, 12, 2000
+    rs = synth.RoomStream(seed=1234, n=F)
+    frames = [rs.frame(t, with_label=True) for t in range(F)]
+    gray, depth = np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+    rgb, T = np.stack([f[2] for f in frames]), np.stack([f[3] for f in frames]).astype(np.float32)
+    label = np.stack([f[4] for f in frames])
+    st = StreamTracker(NF, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, th=15.0, nnratio=0.9, max_frames=F)
+    kps, desc, nkp, c2l, nm = st.track_batch(gray, depth, T)
+    nthreads = min(os.cpu_count() or 1, 64)
+    run = oracle.src_pipeline_run if oracle.refsrc_available() else oracle.pipeline_run
+    _, nkp_ref, nm_ref = run(gray, depth, T, nthreads, NF, fx=synth.FX, fy=synth.FY, cx=synth.CX, cy=synth.CY, bf=synth.BF)
+    assert (nkp == nkp_ref).all() and nkp.min() > 1900
+    assert (nm == nm_ref).all() and nm[1:].min() > 300
+    R = oracle.RefExtractor(NF, 1.2, 8, 20, 7)
+    for t in (0, 131, 255):
+        K, D = R(gray[t])
+        assert kps[t, :nkp[t]].tobytes() == K.tobytes() and (desc[t, :nkp[t]] == D).all()
+    import torch
+    kfs = list(range(0, F, KF))
+    pcm = PointCloudMapping(0.05)
+    d_depth, d_rgb, d_lab = torch.from_numpy(depth).cuda(), torch.from_numpy(rgb).cuda(), torch.from_numpy(label).cuda()
+    pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), 480, 640, kfs, T[kfs], synth.FX, synth.FY, synth.CX, synth.CY,
+                                d_label=d_lab.data_ptr())
+    pcm.sync()
+    ref_map = oracle.RefOccupancy()
+    ref_map.insert_keyframes_mt(depth, rgb, label, kfs, T[kfs], synth.FX, synth.FY, synth.CX, synth.CY, nthreads)
+    kr, lr = ref_map.export_leaves()
+    kg, lg, _ = pcm.export_leaves()
+    pk = lambda k: k.astype(np.uint64)[:, 0] | (k.astype(np.uint64)[:, 1] << np.uint64(16)) | (k.astype(np.uint64)[:, 2] << np.uint64(32))
+    og, orr = np.argsort(pk(kg)), np.argsort(pk(kr))
+    assert len(kg) == len(kr) and (pk(kg)[og] == pk(kr)[orr]).all()
+    assert np.abs(lg[og] - lr[orr]).max() <= 1e-5
+    assert (lr < 0).sum() > 5000 and (lr > 0).sum() > 5000
