@@ -238,3 +238,26 @@ def test_config4_shape_120_keyframes_with_ground_rays(oracle):
         assert len(xg) == len(xr)
         key = lambda a: np.lexsort((a[:, 2], a[:, 1], a[:, 0]))
         assert np.abs(xg[key(xg)] - xr[key(xr)]).max() <= 1e-5
+
+
+def test_sparse_keyframe_under_50_points_is_all_ground(oracle):
+    """perfect/src/MapDrawer.cc:676-680: a cloud of fewer than 50 points skips the plane extraction and becomes ALL ground:
+    free-space rays only, no occupied endpoint -- whatever label is (or is not) supplied."""
+    from orb_slam2_ssd_semantic_b200 import PointCloudMapping
+    rs = synth.RoomStream(seed=5, n=4)
+    gray, depth, rgb, T, lab = rs.frame(1, with_label=True)
+    sparse = np.zeros_like(depth)
+    ys, xs = np.mgrid[60:420:60, 80:560:80]
+    sparse[ys, xs] = np.clip(depth[ys, xs], 0.6, 2.9)          # 36 valid pixels, far apart: 36 points after the 1 cm filter
+    for label in (None, np.zeros_like(lab)):
+        pcm, ref = PointCloudMapping(0.05), oracle.RefOccupancy()
+        pcm.insertKeyFrame(T, sparse, rgb, synth.FX, synth.FY, synth.CX, synth.CY, label)
+        ref.insert_keyframe(T, sparse, rgb, synth.FX, synth.FY, synth.CX, synth.CY, label)
+        kg, lg, _ = pcm.export_leaves()
+        kr, lr = ref.export_leaves()
+        assert len(ref.last_points()[0]) == 36
+        a = {tuple(k): v for k, v in zip(kg.tolist(), lg.tolist())}
+        b = {tuple(k): v for k, v in zip(kr.tolist(), lr.tolist())}
+        assert a.keys() == b.keys() and len(a) > 100
+        assert max(abs(a[k] - b[k]) for k in a) <= 1e-5
+        assert max(b.values()) < 0          # only misses: nothing became occupied
