@@ -9,8 +9,8 @@ SearchByProjection(cur, last, th=15); every 12th frame is a keyframe inserted in
 floor as ground label (mode B: ground points cast free-space rays, perfect/src/MapDrawer.cc:961-969).
 
 A STEP = one pass over SUB x 256 = 4096 frames (16 batches; the same 256 images resident in HBM are walked 16 times --
-629 MB of inputs per pass, far beyond the 126 MB L2 -- with the world shifted by one room per batch so that every batch's
-keyframes fall on fresh map cells).  With the driver's --steps 20 the timed region is > 1 s.
+629 MB of inputs per pass, far beyond the 126 MB L2 -- with the world turned by 22.5 degrees per batch so that every batch's
+keyframes fall on a differently oriented copy of the room).  With the driver's --steps 20 the timed region is > 1 s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--nfeatures 2000] [--no-cpu]
 
@@ -51,8 +51,7 @@ KF_EVERY = 12   # tool/KeyFrameTrajectory_f3_walk_src.txt holds 69 keyframes for
 BATCH = 256     # frames per batched launch set (configs[2])
 SUB = 16        # batches per step
 REF_PASSES = 2  # passes over the batch per step of the CPU arm (bounded sample)
-ROOMS = 64      # distinct world offsets the batches cycle through (the map saturates at 64 rooms)
-ROOM_PITCH = 8.0
+ROOMS = 16      # distinct world orientations the batches cycle through (the map saturates after 16 passes)
 S_IN = ROWS * COLS
 LEVEL_PX = [640 * 480, 533 * 400, 444 * 333, 370 * 278, 309 * 231, 257 * 193, 214 * 161, 179 * 134]
 S_PYR = sum(LEVEL_PX)
@@ -105,11 +104,15 @@ def make_batch(lo: int, hi: int, seed: int = 1234):
 
 
 def shifted_poses(T: np.ndarray, room: int) -> np.ndarray:
-    """Poses of the same camera path in room `room` of a corridor of identical rooms ROOM_PITCH apart along world x:
-    Xw' = Xw + d  =>  tcw' = tcw - Rcw d."""
+    """Poses of the same camera path in a world turned by room * 360/ROOMS degrees about the vertical axis through the
+    world origin: Xw' = Ry Xw  =>  Rcw' = Rcw Ry^T, tcw' = tcw.  Every batch's keyframes then fall on a differently
+    oriented copy of the room (the voxel grid is not rotation invariant: new cells), while the translation of Tcw --
+    which the reference uses as the sensor origin of the free-space rays (perfect/src/MapDrawer.cc:619,631-632) -- stays
+    where it is, so ray lengths stay those of the room."""
+    a = 2.0 * np.pi * room / ROOMS
+    Ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
     out = T.copy()
-    d = np.array([ROOM_PITCH * room, 0.0, 0.0], np.float64)
-    out[:, :3, 3] = (T[:, :3, 3].astype(np.float64) - T[:, :3, :3].astype(np.float64) @ d).astype(np.float32)
+    out[:, :3, :3] = (T[:, :3, :3].astype(np.float64) @ Ry.T).astype(np.float32)
     return out
 
 
