@@ -503,6 +503,7 @@ double X(pipeline_run)(const uint8_t* gray, const float* depth, const float* Tcw
     std::vector<std::thread> pool;
     for (int t = 0; t < nthreads; ++t)
       pool.emplace_back([&]() {
+        Map tmap;   // the reference has ONE tracking thread creating map points; here every worker plays that thread
         for (int i = next++; i < n; i = next++) {
           Frame last(*frames[i - 1]);
           Frame cur(*frames[i]);
@@ -510,7 +511,7 @@ double X(pipeline_run)(const uint8_t* gray, const float* depth, const float* Tcw
           for (int k = 0; k < last.N; ++k) {
             if (last.mvDepth[k] <= 0) continue;
             cv::Mat x3D = last.UnprojectStereo(k);
-            MapPoint* mp = new MapPoint(x3D, &g_map, &last, k);
+            MapPoint* mp = new MapPoint(x3D, &tmap, &last, k);
             mp->nObs = 1;
             last.mvpMapPoints[k] = mp;
             mine.push_back(mp);

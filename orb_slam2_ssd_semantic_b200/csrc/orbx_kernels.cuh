@@ -426,6 +426,18 @@ __device__ __forceinline__ int qt_quadrant(short4 b, unsigned kp) {
   return (x < mx) ? ((y < my) ? 0 : 2) : ((y < my) ? 1 : 3);
 }
 
+// Shared-memory counter increment with warp aggregation: the early rounds of the quad-tree funnel tens of thousands of
+// keypoints into a handful of counters (1 initial node, 4, 16, ... quadrant counters), where plain atomicAdd serialises
+// 32-way inside every warp.  Lanes that hit the same counter elect a leader that adds the group's population.
+// All 32 lanes must call; `active` masks the tail.
+__device__ __forceinline__ void qt_count(int* ctr, int idx, bool active) {
+  const unsigned act = __ballot_sync(0xffffffffu, active);
+  if (active) {
+    const unsigned grp = __match_any_sync(act, idx);
+    if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) atomicAdd(&ctr[idx], __popc(grp));
+  }
+}
+
 // in-place exclusive scan of a[0..n) (shared memory); returns the total. All threads must call.
 __device__ int qt_scan_array(int* a, int n, int* ws) {
   const int per = (n + blockDim.x - 1) / blockDim.x;
@@ -514,12 +526,16 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
   int* icnt = S.cc;   // nIni counters
   for (int i = tid; i < nIni; i += nthr) icnt[i] = 0;
   __syncthreads();
-  for (int k = tid; k < K; k += nthr) {
-    const float xr = (float)(kp_x(qkp[k]) - FAST_BORDER);
-    int ii = (int)__fdiv_rn(xr, hX);
-    ii = min(ii, nIni - 1);
-    qnode[k] = ii;
-    atomicAdd(&icnt[ii], 1);
+  const int Kr = (K + 31) & ~31;   // whole warps take part in the aggregated counting
+  for (int k = tid; k < Kr; k += nthr) {
+    int ii = 0;
+    if (k < K) {
+      const float xr = (float)(kp_x(qkp[k]) - FAST_BORDER);
+      ii = (int)__fdiv_rn(xr, hX);
+      ii = min(ii, nIni - 1);
+      qnode[k] = ii;
+    }
+    qt_count(icnt, ii, k < K);
   }
   __syncthreads();
   for (int i = tid; i < nIni; i += nthr) S.npos[i] = (icnt[i] > 0) ? 1 : 0;
@@ -536,10 +552,14 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
   for (int i = tid; i < nIni * 4; i += nthr) S.cc2[i] = 0;
   __syncthreads();
   // compact the node ids and count, per node, the keypoints of each quadrant (the child populations of round 0)
-  for (int k = tid; k < K; k += nthr) {
-    const int p = S.npos[qnode[k]];
-    qnode[k] = p;
-    atomicAdd(&S.cc2[p * 4 + qt_quadrant(S.box[0][p], qkp[k])], 1);
+  for (int k = tid; k < Kr; k += nthr) {
+    int ci = 0;
+    if (k < K) {
+      const int p = S.npos[qnode[k]];
+      qnode[k] = p;
+      ci = p * 4 + qt_quadrant(S.box[0][p], qkp[k]);
+    }
+    qt_count(S.cc2, ci, k < K);
   }
   __syncthreads();
   { int* t = S.cc; S.cc = S.cc2; S.cc2 = t; }   // S.cc aliased icnt until here
@@ -655,12 +675,18 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
     __syncthreads();
     // (6) re-home the keypoints; the same pass counts the quadrant populations inside the NEW nodes, i.e. the child
     //     populations the next round needs (one pass over the keypoints per round instead of two)
-    for (int k = tid; k < K; k += nthr) {
-      const int p = qnode[k];
-      const unsigned kp = qkp[k];
-      const int np = (S.rk[p] >= 0) ? S.cpos[p * 4 + qt_quadrant(box[p], kp)] : S.npos[p];
-      qnode[k] = np;
-      atomicAdd(&S.cc2[np * 4 + qt_quadrant(nbox[np], kp)], 1);
+    const bool crowded = (TC + nUn) < 256;   // few counters: aggregate inside the warp; many: contention is low anyway
+    for (int k = tid; k < Kr; k += nthr) {
+      int ci = 0;
+      if (k < K) {
+        const int p = qnode[k];
+        const unsigned kp = qkp[k];
+        const int np = (S.rk[p] >= 0) ? S.cpos[p * 4 + qt_quadrant(box[p], kp)] : S.npos[p];
+        qnode[k] = np;
+        ci = np * 4 + qt_quadrant(nbox[np], kp);
+      }
+      if (crowded) qt_count(S.cc2, ci, k < K);
+      else if (k < K) atomicAdd(&S.cc2[ci], 1);
     }
     { int* t = S.cc; S.cc = S.cc2; S.cc2 = t; }
     n = TC + nUn;
