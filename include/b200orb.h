@@ -452,9 +452,10 @@ int ocm_merge_nccl(ocm_t* h, void* nccl_comm, void* stream, OcmMergeStats* stats
 int ocm_nccl_unique_id(uint8_t id[128]);
 int ocm_nccl_comm_create(const uint8_t id[128], int rank, int world, int device, void** nccl_comm);
 int ocm_nccl_comm_destroy(void* nccl_comm);
-/* Sizes of the LAST round of keyframes (at most 32) a batch insert ran: P = points that survived gates + leaf filter,
- * summed over the round's keyframes, U = distinct voxels whose log-odds the round updated (bench.py's B_map). */
-int ocm_last_batch_stats(ocm_t* h, int64_t* points, int64_t* voxels_touched);
+/* Counters for bench.py's B_map: points = P of the LAST round of keyframes (at most 32) a batch insert ran (points that
+ * survived gates + leaf filter, summed over the round's keyframes); voxel_updates = CUMULATIVE number of (voxel, keyframe)
+ * log-odds updates since the map was created (U summed over every keyframe so far). */
+int ocm_last_batch_stats(ocm_t* h, int64_t* points, int64_t* voxel_updates);
 int ocm_sync(ocm_t* h);
 void* ocm_stream(ocm_t* h);
 long long ocm_launch_count(const ocm_t* h);

@@ -123,6 +123,7 @@ struct MapView {
   float* base;
   int* elist;
   int* nelist;
+  unsigned long long* nupd;   // cumulative number of (voxel, keyframe) log-odds updates (bench.py: U of B_map)
 };
 
 // Record "keyframe j of the batch observed voxel `key` as occupied / free".  Order-free (atomicOr), so every keyframe
@@ -413,6 +414,7 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* 
 // is kept).  One thread per touched voxel; the batch masks are cleared for the next batch.
 __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cmax, MapView m) {
   const int n = *m.ntouched;
+  int nup = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int s = m.touched[i];
     const unsigned long long w = m.bm[s];
@@ -421,6 +423,7 @@ __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cma
     float v = m.val[s], a = m.a[s], lo = m.lo[s], hi = m.hi[s];
     if (a == 0.f && lo == -INFINITY) m.elist[atomicAdd(m.nelist, 1)] = s;   // first update of this merge epoch
     unsigned all = hit | miss;
+    nup += __popc(all);
     while (all) {
       const int j = __ffs(all) - 1;
       all &= all - 1u;
@@ -433,6 +436,9 @@ __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cma
     m.val[s] = v; m.a[s] = a; m.lo[s] = lo; m.hi[s] = hi;
     if (hit) { m.rgb[s] = (m.bm_rgb[s] & 0xffffffu) | 0x01000000u; m.bm_rgb[s] = 0u; }   // top byte 1: coloured this epoch
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nup += __shfl_xor_sync(0xffffffffu, nup, o);
+  if ((threadIdx.x & 31) == 0 && nup) atomicAdd(m.nupd, (unsigned long long)nup);
 }
 
 __global__ void k_ocm_fill_leaf(LeafRec* p, long long n) {
@@ -615,7 +621,7 @@ struct ocm {
     DeviceGuard g(device);
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves); F(map.bm); F(map.bm_rgb);
-    F(map.touched); F(map.ntouched); F(map.base); F(map.elist); F(map.nelist);
+    F(map.touched); F(map.ntouched); F(map.base); F(map.elist); F(map.nelist); F(map.nupd);
     F(mg_send); F(mg_recv); F(mg_slots); F(mg_counts);
     if (mg_counts_h) cudaFreeHost(mg_counts_h);
     free_scratch();
@@ -830,6 +836,7 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   if ((e = cudaMalloc(&h->map.base, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.elist, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.nelist, 4)) != cudaSuccess) return fail(e);
+  if ((e = cudaMalloc(&h->map.nupd, 8)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_counters, 16 * ocm::MAX_SLOTS)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_err, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->d_export_counter, 8)) != cudaSuccess) return fail(e);
@@ -842,6 +849,7 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   cudaMemsetAsync(h->map.ntouched, 0, 4, h->stream);
   cudaMemsetAsync(h->map.base, 0, 4 * C, h->stream);
   cudaMemsetAsync(h->map.nelist, 0, 4, h->stream);
+  cudaMemsetAsync(h->map.nupd, 0, 8, h->stream);
   cudaMemsetAsync(h->d_err, 0, 4, h->stream);
   if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return fail(e);
   *out = h;
@@ -1210,14 +1218,14 @@ int ocm_last_batch_stats(ocm_t* h, int64_t* points, int64_t* voxels_touched) {
   if (!h) { set_error("null argument"); return B200ORB_EINVAL; }
   DeviceGuard g(h->device);
   std::vector<int> c(4 * ocm::MAX_SLOTS, 0);
-  int nt = 0;
+  unsigned long long nt = 0;
   B200_CUDA(cudaMemcpyAsync(c.data(), h->d_counters, 16 * ocm::MAX_SLOTS, cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA(cudaMemcpyAsync(&nt, h->map.ntouched, 4, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(&nt, h->map.nupd, 8, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   long long p = 0;
   for (int j = 0; j <= h->last_slot && j < ocm::MAX_SLOTS; ++j) p += c[4 * j + 1];
   if (points) *points = p;
-  if (voxels_touched) *voxels_touched = nt;
+  if (voxels_touched) *voxels_touched = (int64_t)nt;
   return B200ORB_OK;
 }
 

@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, con
 //     (:752-759) is an atomicMax over (response << 24 | ~index).
 // ---------------------------------------------------------------------------------------------------
 constexpr int QT_THREADS = 512;
+constexpr int QT_UNTOUCHED = 0x40000000;   // flag in QtSmem::cpos: the node keeps its box this round
 
 struct QtScratchView {
   unsigned* qkp;    // [F][slots_per_frame] gathered candidates (contiguous per level at slot_begin[l])
@@ -440,7 +441,7 @@ __device__ __forceinline__ void qt_count(int* ctr, int idx, bool active) {
 
 // in-place exclusive scan of a[0..n) (shared memory); returns the total. All threads must call.
 __device__ int qt_scan_array(int* a, int n, int* ws) {
-  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int per = (n + QT_THREADS - 1) / QT_THREADS;   // launch contract: blockDim.x == QT_THREADS (a shift, not a division)
   const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
   int s = 0;
   for (int i = beg; i < end; ++i) s += a[i];
@@ -526,16 +527,12 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
   int* icnt = S.cc;   // nIni counters
   for (int i = tid; i < nIni; i += nthr) icnt[i] = 0;
   __syncthreads();
-  const int Kr = (K + 31) & ~31;   // whole warps take part in the aggregated counting
-  for (int k = tid; k < Kr; k += nthr) {
-    int ii = 0;
-    if (k < K) {
-      const float xr = (float)(kp_x(qkp[k]) - FAST_BORDER);
-      ii = (int)__fdiv_rn(xr, hX);
-      ii = min(ii, nIni - 1);
-      qnode[k] = ii;
-    }
-    qt_count(icnt, ii, k < K);
+  for (int k = tid; k < K; k += nthr) {
+    const float xr = (float)(kp_x(qkp[k]) - FAST_BORDER);
+    int ii = (int)__fdiv_rn(xr, hX);
+    ii = min(ii, nIni - 1);
+    qnode[k] = ii;
+    atomicAdd(&icnt[ii], 1);
   }
   __syncthreads();
   for (int i = tid; i < nIni; i += nthr) S.npos[i] = (icnt[i] > 0) ? 1 : 0;
@@ -552,14 +549,10 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
   for (int i = tid; i < nIni * 4; i += nthr) S.cc2[i] = 0;
   __syncthreads();
   // compact the node ids and count, per node, the keypoints of each quadrant (the child populations of round 0)
-  for (int k = tid; k < Kr; k += nthr) {
-    int ci = 0;
-    if (k < K) {
-      const int p = S.npos[qnode[k]];
-      qnode[k] = p;
-      ci = p * 4 + qt_quadrant(S.box[0][p], qkp[k]);
-    }
-    qt_count(S.cc2, ci, k < K);
+  for (int k = tid; k < K; k += nthr) {
+    const int p = S.npos[qnode[k]];
+    qnode[k] = p;
+    atomicAdd(&S.cc2[p * 4 + qt_quadrant(S.box[0][p], qkp[k])], 1);
   }
   __syncthreads();
   { int* t = S.cc; S.cc = S.cc2; S.cc2 = t; }   // S.cc aliased icnt until here
@@ -644,6 +637,7 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
         nbox[p] = box[i];
         ncnt[p] = cnt[i];
         S.rk[i] = -1;
+        S.cpos[i * 4 + 0] = S.cpos[i * 4 + 1] = S.cpos[i * 4 + 2] = S.cpos[i * 4 + 3] = p | QT_UNTOUCHED;
       }
     }
     // (5) children: block of rank r starts at TC - pre[r]; inside the block n4,n3,n2,n1 (non-empty only)
@@ -675,18 +669,27 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
     __syncthreads();
     // (6) re-home the keypoints; the same pass counts the quadrant populations inside the NEW nodes, i.e. the child
     //     populations the next round needs (one pass over the keypoints per round instead of two)
-    const bool crowded = (TC + nUn) < 256;   // few counters: aggregate inside the warp; many: contention is low anyway
-    for (int k = tid; k < Kr; k += nthr) {
-      int ci = 0;
-      if (k < K) {
-        const int p = qnode[k];
-        const unsigned kp = qkp[k];
-        const int np = (S.rk[p] >= 0) ? S.cpos[p * 4 + qt_quadrant(box[p], kp)] : S.npos[p];
-        qnode[k] = np;
-        ci = np * 4 + qt_quadrant(nbox[np], kp);
+    // cpos[p][q] holds the new list index for quadrant q of node p -- for untouched nodes the node's own new index in
+    // all four entries, flagged -- so the loop needs no branch on the node state and one box load: the child's box, and
+    // with it the quadrant the keypoint will fall into NEXT round, follows from the parent's box and q.
+    for (int k = tid; k < K; k += nthr) {
+      const int p = qnode[k];
+      const unsigned kp = qkp[k];
+      const short4 b = box[p];
+      const int x = kp_x(kp) - FAST_BORDER, y = kp_y(kp) - FAST_BORDER;
+      const int mx = b.x + ((b.z - b.x + 1) >> 1), my = b.y + ((b.w - b.y + 1) >> 1);
+      const int qx = (x < mx) ? 0 : 1, qy = (y < my) ? 0 : 1;
+      const int q = qx | (qy << 1);
+      const int v = S.cpos[p * 4 + q];
+      const int np = v & 0x3fffffff;
+      int q2 = q;
+      if (!(v & QT_UNTOUCHED)) {   // the node was split: quadrant inside child q (DivideNode :478-534 of the child)
+        const int cx0 = qx ? mx : b.x, cx1 = qx ? b.z : mx, cy0 = qy ? my : b.y, cy1 = qy ? b.w : my;
+        const int cmx = cx0 + ((cx1 - cx0 + 1) >> 1), cmy = cy0 + ((cy1 - cy0 + 1) >> 1);
+        q2 = ((x < cmx) ? 0 : 1) | ((y < cmy) ? 0 : 2);
       }
-      if (crowded) qt_count(S.cc2, ci, k < K);
-      else if (k < K) atomicAdd(&S.cc2[ci], 1);
+      qnode[k] = np;
+      atomicAdd(&S.cc2[np * 4 + q2], 1);
     }
     { int* t = S.cc; S.cc = S.cc2; S.cc2 = t; }
     n = TC + nUn;
