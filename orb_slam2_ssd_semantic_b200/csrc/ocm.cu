@@ -344,7 +344,23 @@ __device__ __forceinline__ unsigned long long pack_key(int kx, int ky, int kz) {
 
 // K12/K13: per point -> occupied endpoint key, or (ground) the free cells along the ray (computeRayKeys); the
 // observations go straight into the map's batch masks (bit = keyframe).
+// Free-space rays of neighbouring ground points run through the same cells for most of their length (they share the
+// origin), and a miss is idempotent inside one keyframe (atomicOr of the same bit): every CTA keeps a small direct-mapped
+// cache of the free cells it has already reported and skips the repeats -- the global hash probes + atomics were the whole
+// kernel (long-scoreboard bound), most of them redundant.
+constexpr int SCAN_CACHE = 2048;
+__device__ __forceinline__ bool scan_touch_free(const MapView& m, unsigned long long* seen, unsigned long long key, int j) {
+  const unsigned h = ((unsigned)key * 73856093u ^ (unsigned)(key >> 16) * 19349663u ^ (unsigned)(key >> 32) * 83492791u) &
+                     (SCAN_CACHE - 1);
+  if (seen[h] == key) return true;
+  seen[h] = key;   // benign race: at worst a repeat reaches the map
+  return map_touch(m, key, j, false, 0u);
+}
+
 __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* __restrict__ err) {
+  __shared__ unsigned long long s_seen[SCAN_CACHE];
+  for (int i = threadIdx.x; i < SCAN_CACHE; i += blockDim.x) s_seen[i] = EMPTY_KEY;
+  __syncthreads();
   const int j = blockIdx.y;
   const KfJob& J = jobs[j];
   const OcmConst& c = J.c;
@@ -372,7 +388,7 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* 
       !coord_to_key(c, c.origin[2], ko[2]))
     return;
   if (ko[0] == ke[0] && ko[1] == ke[1] && ko[2] == ke[2]) return;
-  if (!map_touch(m, pack_key(ko[0], ko[1], ko[2]), j, false, 0u)) atomicExch(err, 4);
+  if (!scan_touch_free(m, s_seen, pack_key(ko[0], ko[1], ko[2]), j)) atomicExch(err, 4);
   float dir[3] = {e[0] - c.origin[0], e[1] - c.origin[1], e[2] - c.origin[2]};
   // octomath::Vector3::norm() of octomap 1.9.x: norm_sq() = x*x + y*y + z*z in float, widened for the sqrt only
   const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(dir[0], dir[0]), __fmul_rn(dir[1], dir[1])), __fmul_rn(dir[2], dir[2]));
@@ -405,7 +421,7 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* 
     if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
     const double dist = fmin(fmin(tMax[0], tMax[1]), tMax[2]);
     if (dist > (double)length) break;
-    if (!map_touch(m, pack_key(cur[0], cur[1], cur[2]), j, false, 0u)) { atomicExch(err, 4); break; }
+    if (!scan_touch_free(m, s_seen, pack_key(cur[0], cur[1], cur[2]), j)) { atomicExch(err, 4); break; }
   }
 }
 
@@ -774,7 +790,7 @@ int ocm::insert_batch(int n, const float* const* dd, const uint8_t* const* drgb,
       launches += 1;
     }
     B200_CUDA(cudaMemsetAsync(map.ntouched, 0, 4, stream));
-    k_ocm_scan_keys<<<g128, 128, 0, stream>>>(dj, map, d_err);
+    k_ocm_scan_keys<<<g256, 256, 0, stream>>>(dj, map, d_err);
     // the touched-list length lives on the device: grid-stride kernel on a fixed grid (2 CTAs per SM)
     k_ocm_apply<<<296, 256, 0, stream>>>(hit_log, miss_log, cmin, cmax, map);
     launches += 2;
