@@ -312,7 +312,7 @@ def run_b200(args):
     npx = ROWS * COLS
     step_no = [0]
 
-    def step_device(serial=False):
+    def step_device(serial=False, with_map=True):
         k = step_no[0]
         step_no[0] += 1
         for i, p in enumerate(plan):
@@ -320,11 +320,11 @@ def run_b200(args):
             trk_h = st if (serial or (i & 1) == 0) else st_b
             trk_h.track_batch_device(d_gray.data_ptr() + o * npx, d_depth.data_ptr() + o * npx * 4, d_T.data_ptr() + o * 64,
                                      p["n"], ROWS, COLS)
-            if len(p["kf"]):
+            if with_map and len(p["kf"]):
                 room = (k * SUB + p["room"]) % ROOMS
                 pcm.insert_keyframes_device(d_depth.data_ptr(), d_rgb.data_ptr(), ROWS, COLS, p["kf"], p["Tkf"][room],
                                             synth.FX, synth.FY, synth.CX, synth.CY, d_label=d_label.data_ptr())
-        if world > 1:
+        if world > 1 and with_map:
             return pcm.merge()     # ocm_merge_nccl: inside the timed region
         return None
 
@@ -364,7 +364,7 @@ def run_b200(args):
     # timed region the stages of two batches overlap, which would smear a kernel's duration over its neighbour's)
     st.profile_enable(True)
     st.profile_read()
-    step_device(serial=True)
+    step_device(serial=True, with_map=False)
     st.sync(); pcm.sync()
     stage_ms, prof_frames, prof_runs = st.profile_read()
     st.profile_enable(False)
@@ -511,8 +511,9 @@ def run_b200(args):
                          "traffic": (NCU_DRAM_BYTES_PER_FRAME[dom] * prof_frames / max(prof_runs, 1)
                                      if dom in NCU_DRAM_BYTES_PER_FRAME else None),
                          "traffic_source": NCU_SOURCE, "peak_source": peak_src,
-                         "stages_measured": "one serial step on one tracker handle right after the timed region (inside it two "
-                                            "batches are in flight on two streams and their stages overlap)",
+                         "stages_measured": "tracking stages: one serial step on one tracker handle, nothing else on the GPU, right "
+                                            "after the timed region (inside it two batches and the mapper are in flight on three "
+                                            "streams and their kernels overlap); mapping: one step's keyframes alone",
                          "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
                                       "algorithmic_bytes_per_frame": pipeline_bytes(n_kp),
                                       "note": "B_ext + B_match per tracked frame / whole timed region (mapping overlapped)"},
