@@ -420,7 +420,7 @@ def run_b200(args):
     st2 = st_b
     trk = [st, st2]
     for t in trk:
-        t.set_chunk_frames(BATCH)
+        t.set_chunk_frames(int(os.environ.get("BENCH_CHUNK", BATCH)))
     outs2 = [st.alloc_outputs(BATCH, pinned=True), st2.alloc_outputs(BATCH, pinned=True)]
     e2e_k = [0]
 
@@ -431,7 +431,8 @@ def run_b200(args):
             pcm.insert_keyframes_u16(kp[0].numpy(), kp[1].numpy(), factor, p["Tkf"][room], synth.FX, synth.FY, synth.CX,
                                      synth.CY, label=kp[2].numpy())
         o, n = p["off"], p["n"]
-        trk[j & 1].chain_after(trk[(j + 1) & 1])
+        if not os.environ.get("BENCH_NO_CHAIN"):
+            trk[j & 1].chain_after(trk[(j + 1) & 1])
         trk[j & 1].submit_batch_u16(h_gray[o:o + n], h_d16[o:o + n], factor, h_T[o:o + n], tuple(a[:n] for a in outs2[j & 1]))
 
     def run_host(nsteps):
@@ -462,6 +463,21 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = frames_step_total * e2e_steps / float(te.item())
+    # what the host link itself gives: one pinned gray batch copied alone, each direction (context for the e2e number)
+    link = {}
+    dgray = torch.empty_like(p_gray[:BATCH], device=dev)
+    hback = torch.empty_like(p_gray[:BATCH]).pin_memory()
+    for name, dst, src in (("h2d", dgray, p_gray[:BATCH]), ("d2h", hback, dgray)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(8):
+            dst.copy_(src, non_blocking=True)
+        l1.record()
+        torch.cuda.synchronize()
+        link[name] = 8 * src.numel() * src.element_size() / (l0.elapsed_time(l1) * 1e-3) / 1e9
+    del dgray, hback
     kps, desc, nkp, c2l, nm = [a[:nlast] for a in outs2[which]]
     n_kp = float(nkp.mean())
     n_match = float(nm[1:].mean()) if nlast > 1 else 0.0
@@ -503,7 +519,11 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": workload_config(args, world, frames_step_total),
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "batches_in_flight": 2, "steps": e2e_steps},
+                    "batches_in_flight": 2, "steps": e2e_steps,
+                    "h2d_gbs": h2d / world / (float(te.item()) / e2e_steps) / 1e9,
+                    "link_gbs_measured": link,
+                    "note": "h2d_gbs = bytes one rank uploads per step / its e2e step time; link_gbs_measured = a pinned "
+                            "78.6 MB gray batch copied alone over the same link"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",

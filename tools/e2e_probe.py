@@ -1,4 +1,5 @@
-"""Host-buffer (end-to-end) throughput of the batch tracker under a few configurations (development aid)."""
+"""Where the host-buffer (e2e) path spends its time: one 256-frame batch through each entry alone, host clock around a
+call that waits.  Development aid (not a bench value).  usage: e2e_probe.py [frames] [nfeatures]"""
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
@@ -6,61 +7,63 @@ import torch
 from orb_slam2_ssd_semantic_b200 import PointCloudMapping, StreamTracker, synth
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-KF = 12
-ws = synth.WallStream(seed=1234, n=F)
-fr = [ws.frame(t) for t in range(F)]
-gray = torch.from_numpy(np.stack([f[0] for f in fr])).pin_memory()
-depth = np.stack([f[1] for f in fr])
-d16 = torch.from_numpy(np.rint(depth.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)).pin_memory()
-rgb = np.stack([f[2] for f in fr])
-T = torch.from_numpy(np.ascontiguousarray(np.stack([f[3] for f in fr]), np.float32)).pin_memory()
-kfs = list(range(0, F, KF))
-kf_d16 = torch.from_numpy(np.ascontiguousarray(d16.numpy()[kfs])).pin_memory()
-kf_rgb = torch.from_numpy(np.ascontiguousarray(rgb[kfs])).pin_memory()
+nfeat = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
+rs = synth.RoomStream(seed=1234, n=F)
+fr = [rs.frame(t, with_label=True) for t in range(F)]
+pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+gray_h, depth_f = np.stack([f[0] for f in fr]), np.stack([f[1] for f in fr])
+d16_h = np.rint(depth_f.astype(np.float64) * synth.DEPTH_FACTOR).astype(np.uint16)
+rgb_h, lab_h = np.stack([f[2] for f in fr]), np.stack([f[4] for f in fr])
+Th = np.stack([f[3] for f in fr]).astype(np.float32)
+p_gray, p_d16, p_T = pin(gray_h), pin(d16_h), pin(Th)
+kfs = list(range(0, F, 12))
+p_kd, p_kc, p_kl = pin(d16_h[kfs]), pin(rgb_h[kfs]), pin(lab_h[kfs])
+gray, depth = p_gray.cuda(), torch.from_numpy(depth_f).cuda()
+rgb, lab, T = torch.from_numpy(rgb_h).cuda(), torch.from_numpy(lab_h).cuda(), p_T.cuda()
 factor = np.float32(1.0 / synth.DEPTH_FACTOR)
-mk = lambda: StreamTracker(1000, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, max_frames=F)
-trk = [mk(), mk(), mk()]
-outs = [t.alloc_outputs(F, pinned=True) for t in trk]
+st = StreamTracker(nfeat, 1.2, 8, 20, 7, synth.FX, synth.FY, synth.CX, synth.CY, synth.BF, max_frames=F)
+st.set_chunk_frames(F)
+out = st.alloc_outputs(F, pinned=True)
 pcm = PointCloudMapping(0.05)
-Tk = T.numpy()[kfs]
 
 
-def run(n, inflight, mapper, chunk, full_depth, chain=False):
-    for t in trk:
-        t.set_chunk_frames(chunk)
-        t.set_full_depth_upload(full_depth)
-
-    def submit(k):
-        if mapper:
-            pcm.insert_keyframes_u16(kf_d16.numpy(), kf_rgb.numpy(), factor, Tk, synth.FX, synth.FY, synth.CX, synth.CY)
-        if chain and inflight > 1:
-            trk[k % inflight].chain_after(trk[(k - 1) % inflight])
-        trk[k % inflight].submit_batch_u16(gray.numpy(), d16.numpy(), factor, T.numpy(), outs[k % inflight])
-
-    def go(m):
-        for k in range(m):
-            if k >= inflight:
-                trk[k % inflight].sync()
-            submit(k)
-        for t in trk:
-            t.sync()
-        pcm.sync()
-
-    go(3)
-    torch.cuda.synchronize()
+def timeit(name, fn, n=6):
+    fn(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    go(n)
-    dt = time.perf_counter() - t0
-    return F * n / dt, dt / n * 1e3
+    for _ in range(n):
+        fn()
+    torch.cuda.synchronize()
+    print("%-44s %7.3f ms" % (name, (time.perf_counter() - t0) / n * 1e3), flush=True)
 
 
-cfgs = [(2, True, 128, False, False), (2, True, 128, False, True), (2, True, 256, False, True), (3, True, 256, False, True), (2, False, 256, False, True)] if len(sys.argv) > 2 else \
-    [(i, m, c, f, False) for i in (1, 2) for m in (False, True) for c in (64, 128, 256) for f in (False, True)]
-for inflight, mapper, chunk, full, chain in cfgs:
-    trk[0].profile_enable(True)
-    trk[0].profile_read()
-    fps, ms = run(12, inflight, mapper, chunk, full, chain)
-    print("inflight %d mapper %d chunk %3d full_depth %d chain %d : %8.0f frames/s  %.2f ms/batch" % (inflight, mapper, chunk, full, chain, fps, ms))
-    st_ms, frames, runs = trk[0].profile_read()
-    trk[0].profile_enable(False)
-    print("   handle 0 stage ms per batch:", {k: round(v / max(runs, 1) * (F / max(frames / max(runs, 1), 1)), 3) for k, v in st_ms.items()}, "sum %.3f" % (sum(st_ms.values()) / max(frames, 1) * F))
+def dev():
+    st.track_batch_device(gray.data_ptr(), depth.data_ptr(), T.data_ptr(), F, 480, 640); st.sync()
+def host():
+    st.track_batch_u16(p_gray.numpy(), p_d16.numpy(), factor, p_T.numpy(), out)
+def kdev():
+    pcm.insert_keyframes_device(depth.data_ptr(), rgb.data_ptr(), 480, 640, kfs, Th[kfs], synth.FX, synth.FY, synth.CX, synth.CY,
+                                d_label=lab.data_ptr()); pcm.sync()
+def khost():
+    pcm.insert_keyframes_u16(p_kd.numpy(), p_kc.numpy(), factor, Th[kfs], synth.FX, synth.FY, synth.CX, synth.CY, label=p_kl.numpy()); pcm.sync()
+def h2d():
+    gray.copy_(p_gray, non_blocking=True); torch.cuda.synchronize()
+dback = [torch.empty(a.shape, dtype=torch.uint8).pin_memory() if False else None for a in ()]
+
+timeit("tracker, inputs resident", dev)
+timeit("tracker, host buffers (zero-copy depth)", host)
+st.set_full_depth_upload(True)
+timeit("tracker, host buffers (full depth upload)", host)
+st.set_full_depth_upload(False)
+timeit("gray H2D alone (%.1f MB)" % (gray_h.nbytes / 1e6), h2d)
+timeit("mapper, inputs resident (%d kf)" % len(kfs), kdev)
+timeit("mapper, host buffers", khost)
+st.profile_enable(True)
+for _ in range(3):
+    host()
+ms, frames, runs = st.profile_read()
+print({k: round(v / runs, 3) for k, v in ms.items()}, "ms per batch, host path")
+for _ in range(3):
+    dev()
+ms, frames, runs = st.profile_read()
+print({k: round(v / runs, 3) for k, v in ms.items()}, "ms per batch, device path")
+print("outputs D2H bytes:", sum(a.nbytes for a in out))
