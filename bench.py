@@ -4,17 +4,17 @@
 
 Workload (BASELINE.json configs[2] shape, scene per SURVEY §8(d)): a synthetic RGB-D stream of a 6 x 3 x 6 m textured
 room (RoomStream: camera on a 0.5 m Lissajous, panning <= 1.5 deg/frame, exact depth, GT floor mask), processed in the
-batched many-frame mode: 256-frame batches, ORBextractor(2000,1.2,8,20,7), per frame ComputeStereoFromRGBD + grid +
+batched many-frame mode: 297-frame batches, ORBextractor(2000,1.2,8,20,7), per frame ComputeStereoFromRGBD + grid +
 SearchByProjection(cur, last, th=15); every 12th frame is a keyframe inserted into the 0.05 m occupancy map with the
 floor as ground label (mode B: ground points cast free-space rays, perfect/src/MapDrawer.cc:961-969).
 
-A STEP = one pass over SUB x 256 = 4096 frames (16 batches; the same 256 images resident in HBM are walked 16 times --
-629 MB of inputs per pass, far beyond the 126 MB L2 -- with the world turned by 22.5 degrees per batch so that every batch's
+A STEP = one pass over SUB x 297 = 4752 frames (16 batches; the same 297 images resident in HBM are walked 16 times --
+820 MB of inputs per pass, far beyond the 126 MB L2 -- with the world turned by 22.5 degrees per batch so that every batch's
 keyframes fall on a differently oriented copy of the room).  With the driver's --steps 20 the timed region is > 1 s.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--nfeatures 2000] [--no-cpu]
 
-N > 1 (torchrun, one rank per GPU): STRONG scaling -- the 4096 frames of a step are sharded in contiguous ranges
+N > 1 (torchrun, one rank per GPU): STRONG scaling -- the 4752 frames of a step are sharded in contiguous ranges
 (+1 halo frame each, re-extracted locally), every rank maps its own keyframes, and ocm_merge_nccl (the only collective
 of the path: an exchange of per-voxel clamp-add summaries over NVLink) runs INSIDE the timed region at the end of every
 step; `merge` in the line says what it cost.
@@ -48,7 +48,10 @@ ROWS, COLS = 480, 640
 SCALE, NLEVELS, INI_TH, MIN_TH = 1.2, 8, 20, 7                  # perfect/Examples/RGB-D/TUM3.yaml:45-54
 TH, NNRATIO = 15.0, 0.9                                        # src/Tracking.cc:1327,1346
 KF_EVERY = 12   # tool/KeyFrameTrajectory_f3_walk_src.txt holds 69 keyframes for 827 frames -> 1 in 12
-BATCH = 256     # frames per batched launch set (configs[2])
+# frames per batched launch set (configs[2]).  297 = 2 * 148 + 1: the matcher runs one 190 KB CTA per (frame, previous
+# frame) pair, one per SM, so the 296 pairs of a batch fill the 148 SMs exactly twice (256 frames = 255 pairs left the
+# second wave 28 % empty).  Every other kernel has thousands of CTAs per launch and does not care.
+BATCH = int(os.environ.get("BENCH_BATCH", 297))
 SUB = 16        # batches per step
 REF_PASSES = 2  # passes over the batch per step of the CPU arm (bounded sample)
 ROOMS = 16      # distinct world orientations the batches cycle through (the map saturates after 16 passes)
@@ -90,7 +93,7 @@ def measured_peak():
 
 
 def make_batch(lo: int, hi: int, seed: int = 1234):
-    """Frames [lo, hi) of the 256-frame room stream: gray, depth f32, rgb, floor label, Tcw."""
+    """Frames [lo, hi) of the BATCH-frame room stream: gray, depth f32, rgb, floor label, Tcw."""
     rs = synth.RoomStream(seed=seed, n=BATCH)
     n = hi - lo
     gray = np.empty((n, ROWS, COLS), np.uint8)
@@ -173,7 +176,7 @@ def workload_config(args, world, frames_step):
 # CPU arm
 # --------------------------------------------------------------------------------------------------------------
 def cpu_step(gray, depth, rgb, label, T, nthreads, nfeat, passes):
-    """`passes` walks over the 256-frame batch on the host cores: tracking through the reference's own sources
+    """`passes` walks over the BATCH-frame batch on the host cores: tracking through the reference's own sources
     (frame-parallel on nthreads) while a mapping thread inserts the keyframes (GeneratePointCloud of the keyframes on
     all threads, InsertScan sequential) -- the reference maps on its own std::thread (src/pointcloudmapping.cc:43).
     -> (wall s, tracking s, mapping s, kind)"""

@@ -33,11 +33,24 @@ __device__ __forceinline__ unsigned long long hash64(unsigned long long k) {   /
   k ^= k >> 31;
   return k;
 }
+// Home slot of a key in a power-of-two table.  Tables below 2^32 slots (every one in practice) take a 32-bit mix of the
+// two key halves (murmur3 block + finaliser): about half the instructions of the 64-bit multiplies, and the probe is on
+// the inner loop of the free-space rays (k_ocm_scan_keys: the 64-bit hash was 19 % of its instructions).
+__device__ __forceinline__ long long hash_slot(unsigned long long k, long long mask) {
+  if ((unsigned long long)mask >> 32) return (long long)(hash64(k) & (unsigned long long)mask);
+  unsigned h = (unsigned)k * 0xcc9e2d51u;
+  h = __funnelshift_l(h, h, 15) * 0x1b873593u;
+  h ^= (unsigned)(k >> 32) * 0x85ebca6bu;
+  h ^= h >> 16; h *= 0x85ebca6bu;
+  h ^= h >> 13; h *= 0xc2b2ae35u;
+  h ^= h >> 16;
+  return (long long)(h & (unsigned)mask);
+}
 
 // find-or-insert; returns slot or -1 when the table is full; *fresh = this call created the entry
 __device__ __forceinline__ long long table_insert(unsigned long long* keys, long long cap_mask, unsigned long long key,
                                                   bool* fresh) {
-  long long s = (long long)(hash64(key) & (unsigned long long)cap_mask);
+  long long s = hash_slot(key, cap_mask);
   *fresh = false;
   for (long long probe = 0; probe <= cap_mask; ++probe) {
     const unsigned long long cur = keys[s];
@@ -53,7 +66,7 @@ __device__ __forceinline__ long long table_insert(unsigned long long* keys, long
 }
 
 __device__ __forceinline__ long long table_find(const unsigned long long* keys, long long cap_mask, unsigned long long key) {
-  long long s = (long long)(hash64(key) & (unsigned long long)cap_mask);
+  long long s = hash_slot(key, cap_mask);
   for (long long probe = 0; probe <= cap_mask; ++probe) {
     const unsigned long long cur = keys[s];
     if (cur == key) return s;
@@ -90,7 +103,7 @@ struct LeafTable {
 
 // find-or-insert on the record table; returns slot or -1 when the table is full
 __device__ __forceinline__ long long leaf_insert(const LeafTable& lt, unsigned long long key, bool* fresh) {
-  long long s = (long long)(hash64(key) & (unsigned long long)lt.mask);
+  long long s = hash_slot(key, lt.mask);
   *fresh = false;
   for (long long probe = 0; probe <= lt.mask; ++probe) {
     const unsigned long long cur = lt.rec[s].key;
@@ -113,11 +126,9 @@ struct MapView {
   int* nleaves;
   long long mask;
   // batch accumulation: which keyframes of the running batch hit (high word) / missed (low word) the voxel, the colour
-  // of its latest hit (keyframe << 24 | rgb), and the list of voxels touched by the batch
+  // of its latest hit (keyframe << 24 | rgb); k_ocm_apply finds the touched voxels by sweeping the masks
   unsigned long long* bm;
   unsigned* bm_rgb;
-  int* touched;
-  int* ntouched;
   // merge epochs (ocm_merge_nccl): value of the voxel at the last merge, and the list of voxels whose summary left the
   // identity since then (what this rank has to send)
   float* base;
@@ -129,7 +140,7 @@ struct MapView {
 // Record "keyframe j of the batch observed voxel `key` as occupied / free".  Order-free (atomicOr), so every keyframe
 // of a batch can be scanned in one launch; k_ocm_apply replays the bits of each voxel in keyframe order.
 __device__ __forceinline__ bool map_touch(const MapView& m, unsigned long long key, int j, bool occupied, unsigned rgb) {
-  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  long long s = hash_slot(key, m.mask);
   bool found = false;
   for (long long probe = 0; probe <= m.mask; ++probe) {
     const unsigned long long cur = m.keys[s];
@@ -142,9 +153,12 @@ __device__ __forceinline__ bool map_touch(const MapView& m, unsigned long long k
     s = (s + 1) & m.mask;
   }
   if (!found) return false;
+  // Fire and forget: no atomic here returns a value.  (The free-space rays used to wait on the atomicOr's old value to
+  // build a list of touched voxels: 35 % of k_ocm_scan_keys' stall samples.  Dirty-block flags instead of the list were
+  // worse: the hash scatters a batch over every block, and millions of flag stores / flag reads land on 64 cache lines.
+  // k_ocm_apply simply sweeps the 8-byte masks of the whole table: 67 MB per batch at the default capacity.)
   const unsigned long long bit = occupied ? (1ull << (32 + j)) : (1ull << j);
-  const unsigned long long old = atomicOr(&m.bm[s], bit);
-  if (old == 0ull) m.touched[atomicAdd(m.ntouched, 1)] = (int)s;
+  atomicOr(&m.bm[s], bit);
   if (occupied) atomicMax(&m.bm_rgb[s], ((unsigned)j << 24) | (rgb & 0xffffffu));
   return true;
 }
@@ -357,7 +371,7 @@ __device__ __forceinline__ bool scan_touch_free(const MapView& m, unsigned long 
   return map_touch(m, key, j, false, 0u);
 }
 
-__global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* __restrict__ err) {
+__global__ void __launch_bounds__(256) k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* __restrict__ err) {
   __shared__ unsigned long long s_seen[SCAN_CACHE];
   for (int i = threadIdx.x; i < SCAN_CACHE; i += blockDim.x) s_seen[i] = EMPTY_KEY;
   __syncthreads();
@@ -410,47 +424,70 @@ __global__ void k_ocm_scan_keys(const KfJob* __restrict__ jobs, MapView m, int* 
       tDelta[i] = 1.7976931348623157e308;
     }
   }
+  // computeRayKeys' loop (octomap OcTreeBaseImpl.hxx:  step along the axis of the smallest tMax; stop at the end key;
+  // stop when min(tMax) after the step exceeds the ray length; else the cell is free).  min(tMax) after a step IS the
+  // tMax of the axis the next step takes, so the distance test of cell k rides on the axis selection of step k+1 and
+  // the cell is reported one iteration late (`pending`): no separate three-way double minimum per cell.
+  bool pending = false;
+  unsigned long long pending_key = 0ull;
+  const double dlen = (double)length;
   for (int guard = 0; guard < 3 * 65536; ++guard) {
-    int dim;
-    if (tMax[0] < tMax[1]) dim = (tMax[0] < tMax[2]) ? 0 : 2;
-    else dim = (tMax[1] < tMax[2]) ? 1 : 2;
-    // (no dynamic register indexing: unrolled select)
-    if (dim == 0) { cur[0] = (cur[0] + step[0]) & 0xffff; tMax[0] += tDelta[0]; }
-    else if (dim == 1) { cur[1] = (cur[1] + step[1]) & 0xffff; tMax[1] += tDelta[1]; }
-    else { cur[2] = (cur[2] + step[2]) & 0xffff; tMax[2] += tDelta[2]; }
+    const bool a01 = tMax[0] < tMax[1];
+    const double t01 = a01 ? tMax[0] : tMax[1];
+    const bool a2 = t01 < tMax[2];            // (tMax[0] < tMax[2]) or (tMax[1] < tMax[2]), whichever axis leads
+    const double tmin = a2 ? t01 : tMax[2];
+    if (pending) {
+      if (tmin > dlen) break;
+      if (!scan_touch_free(m, s_seen, pending_key, j)) { atomicExch(err, 4); break; }
+    }
+    const bool d0 = a2 && a01, d1 = a2 && !a01, d2 = !a2;
+    // (no dynamic register indexing, no branches: predicated updates)
+    cur[0] = d0 ? ((cur[0] + step[0]) & 0xffff) : cur[0];
+    cur[1] = d1 ? ((cur[1] + step[1]) & 0xffff) : cur[1];
+    cur[2] = d2 ? ((cur[2] + step[2]) & 0xffff) : cur[2];
+    tMax[0] = d0 ? tMax[0] + tDelta[0] : tMax[0];
+    tMax[1] = d1 ? tMax[1] + tDelta[1] : tMax[1];
+    tMax[2] = d2 ? tMax[2] + tDelta[2] : tMax[2];
     if (cur[0] == ke[0] && cur[1] == ke[1] && cur[2] == ke[2]) break;
-    const double dist = fmin(fmin(tMax[0], tMax[1]), tMax[2]);
-    if (dist > (double)length) break;
-    if (!scan_touch_free(m, s_seen, pack_key(cur[0], cur[1], cur[2]), j)) { atomicExch(err, 4); break; }
+    pending = true;
+    pending_key = pack_key(cur[0], cur[1], cur[2]);
   }
 }
 
 // K14: replay, voxel by voxel, the observations of the batch in keyframe order (MapDrawer.cc:1007-1022 per keyframe:
 // free \ occupied get a miss, occupied get a hit; updateNodeLogOdds clamps after every add, so the order matters and
-// is kept).  One thread per touched voxel; the batch masks are cleared for the next batch.
+// is kept).  Grid-stride sweep over the batch masks of the whole table (16-byte loads); the masks of the voxels found
+// are cleared for the next batch.
+__device__ __forceinline__ int apply_slot(const MapView& m, long long s, unsigned long long w, float hit_log, float miss_log,
+                                          float cmin, float cmax) {
+  m.bm[s] = 0ull;
+  const unsigned hit = (unsigned)(w >> 32), miss = (unsigned)w & ~hit;
+  float v = m.val[s], a = m.a[s], lo = m.lo[s], hi = m.hi[s];
+  if (a == 0.f && lo == -INFINITY) m.elist[atomicAdd(m.nelist, 1)] = (int)s;   // first update of this merge epoch
+  unsigned all = hit | miss;
+  const int nup = __popc(all);
+  while (all) {
+    const int j = __ffs(all) - 1;
+    all &= all - 1u;
+    const float d = ((hit >> j) & 1u) ? hit_log : miss_log;
+    v = fminf(fmaxf(v + d, cmin), cmax);
+    a = a + d;
+    lo = fminf(fmaxf(lo + d, cmin), cmax);
+    hi = fminf(fmaxf(hi + d, cmin), cmax);
+  }
+  m.val[s] = v; m.a[s] = a; m.lo[s] = lo; m.hi[s] = hi;
+  if (hit) { m.rgb[s] = (m.bm_rgb[s] & 0xffffffu) | 0x01000000u; m.bm_rgb[s] = 0u; }   // top byte 1: coloured this epoch
+  return nup;
+}
+
 __global__ void k_ocm_apply(float hit_log, float miss_log, float cmin, float cmax, MapView m) {
-  const int n = *m.ntouched;
+  const long long C = m.mask + 1;   // power of two >= 2
+  const ulonglong2* __restrict__ bm2 = reinterpret_cast<const ulonglong2*>(m.bm);
   int nup = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int s = m.touched[i];
-    const unsigned long long w = m.bm[s];
-    m.bm[s] = 0ull;
-    const unsigned hit = (unsigned)(w >> 32), miss = (unsigned)w & ~hit;
-    float v = m.val[s], a = m.a[s], lo = m.lo[s], hi = m.hi[s];
-    if (a == 0.f && lo == -INFINITY) m.elist[atomicAdd(m.nelist, 1)] = s;   // first update of this merge epoch
-    unsigned all = hit | miss;
-    nup += __popc(all);
-    while (all) {
-      const int j = __ffs(all) - 1;
-      all &= all - 1u;
-      const float d = ((hit >> j) & 1u) ? hit_log : miss_log;
-      v = fminf(fmaxf(v + d, cmin), cmax);
-      a = a + d;
-      lo = fminf(fmaxf(lo + d, cmin), cmax);
-      hi = fminf(fmaxf(hi + d, cmin), cmax);
-    }
-    m.val[s] = v; m.a[s] = a; m.lo[s] = lo; m.hi[s] = hi;
-    if (hit) { m.rgb[s] = (m.bm_rgb[s] & 0xffffffu) | 0x01000000u; m.bm_rgb[s] = 0u; }   // top byte 1: coloured this epoch
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < C / 2; i += (long long)gridDim.x * blockDim.x) {
+    const ulonglong2 w = bm2[i];
+    if (w.x) nup += apply_slot(m, 2 * i, w.x, hit_log, miss_log, cmin, cmax);
+    if (w.y) nup += apply_slot(m, 2 * i + 1, w.y, hit_log, miss_log, cmin, cmax);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nup += __shfl_xor_sync(0xffffffffu, nup, o);
@@ -502,7 +539,7 @@ __global__ void k_ocm_apply_summaries(OcmConst c, MapView m, const unsigned long
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = keys[i];
-  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  long long s = hash_slot(key, m.mask);
   bool found = false;
   for (long long probe = 0; probe <= m.mask; ++probe) {
     const unsigned long long cur = m.keys[s];
@@ -561,7 +598,7 @@ __global__ void k_merge_apply(MapView m, long long n, MergeShard g, int* __restr
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = g.keys[i];
-  long long s = (long long)(hash64(key) & (unsigned long long)m.mask);
+  long long s = hash_slot(key, m.mask);
   bool found = false;
   for (long long probe = 0; probe <= m.mask; ++probe) {
     const unsigned long long cur = m.keys[s];
@@ -637,7 +674,7 @@ struct ocm {
     DeviceGuard g(device);
     auto F = [](void* p) { if (p) cudaFree(p); };
     F(map.keys); F(map.val); F(map.a); F(map.lo); F(map.hi); F(map.rgb); F(map.nleaves); F(map.bm); F(map.bm_rgb);
-    F(map.touched); F(map.ntouched); F(map.base); F(map.elist); F(map.nelist); F(map.nupd);
+    F(map.base); F(map.elist); F(map.nelist); F(map.nupd);
     F(mg_send); F(mg_recv); F(mg_slots); F(mg_counts);
     if (mg_counts_h) cudaFreeHost(mg_counts_h);
     free_scratch();
@@ -789,10 +826,9 @@ int ocm::insert_batch(int n, const float* const* dd, const uint8_t* const* drgb,
       k_ocm_points_nofilter<<<g256, 256, 0, stream>>>(dj);
       launches += 1;
     }
-    B200_CUDA(cudaMemsetAsync(map.ntouched, 0, 4, stream));
     k_ocm_scan_keys<<<g256, 256, 0, stream>>>(dj, map, d_err);
-    // the touched-list length lives on the device: grid-stride kernel on a fixed grid (2 CTAs per SM)
-    k_ocm_apply<<<296, 256, 0, stream>>>(hit_log, miss_log, cmin, cmax, map);
+    // grid-stride sweep on a fixed grid (8 CTAs per SM)
+    k_ocm_apply<<<1184, 256, 0, stream>>>(hit_log, miss_log, cmin, cmax, map);
     launches += 2;
     last_slot = B - 1;
     B200_CUDA(cudaGetLastError());
@@ -825,7 +861,7 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   auto logodds = [](double pr) { return (float)log(pr / (1 - pr)); };   // octomap::logodds (float)
   h->hit_log = logodds(p->prob_hit); h->miss_log = logodds(p->prob_miss);
   h->cmin = logodds(p->clamp_min); h->cmax = logodds(p->clamp_max);
-  h->map_cap = pow2_at_least(p->map_capacity > 0 ? p->map_capacity : (1ll << 23));
+  h->map_cap = pow2_at_least(p->map_capacity > 0 ? std::max<long long>(p->map_capacity, 2) : (1ll << 23));
   auto fail = [&](cudaError_t e) { set_error("ocm_create: %s", cudaGetErrorString(e)); delete h; return B200ORB_ECUDA; };
   cudaError_t e;
   {
@@ -847,8 +883,6 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   if ((e = cudaMalloc(&h->map.nleaves, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.bm, 8 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.bm_rgb, 4 * C)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&h->map.touched, 4 * C)) != cudaSuccess) return fail(e);
-  if ((e = cudaMalloc(&h->map.ntouched, 4)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.base, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.elist, 4 * C)) != cudaSuccess) return fail(e);
   if ((e = cudaMalloc(&h->map.nelist, 4)) != cudaSuccess) return fail(e);
@@ -862,7 +896,6 @@ int ocm_create(const OcmParams* p, int device, ocm_t** out) {
   cudaMemsetAsync(h->map.nleaves, 0, 4, h->stream);
   cudaMemsetAsync(h->map.bm, 0, 8 * C, h->stream);
   cudaMemsetAsync(h->map.bm_rgb, 0, 4 * C, h->stream);
-  cudaMemsetAsync(h->map.ntouched, 0, 4, h->stream);
   cudaMemsetAsync(h->map.base, 0, 4 * C, h->stream);
   cudaMemsetAsync(h->map.nelist, 0, 4, h->stream);
   cudaMemsetAsync(h->map.nupd, 0, 8, h->stream);
