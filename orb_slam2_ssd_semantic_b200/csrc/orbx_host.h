@@ -27,6 +27,7 @@ struct orbx {
   int nfeat[b200::MAX_LEVELS];
   b200::OrientTab otab{};
   signed char* d_pattern = nullptr;
+  float4* d_patf = nullptr;   // the 256 tests as float4 (x0, y0, x1, y1), for k_orient_desc2
   // geometry-dependent state
   int rows = 0, cols = 0, maxF = 0, lastF = 0;
   int lw[b200::MAX_LEVELS], lh[b200::MAX_LEVELS], lpitch[b200::MAX_LEVELS];

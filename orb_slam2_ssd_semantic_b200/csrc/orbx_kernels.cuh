@@ -189,8 +189,10 @@ __device__ __forceinline__ int fast_m_exact(const uint8_t* c) {
 //   dense   whenever 32 pixels are queued, a full warp evaluates their exact m(p); corners (m > t) go to the corner
 //           list -- the queue is FIFO over a row-major sweep, so the list is row-major as well;
 //   NMS     32 corners at a time: strict 3x3 maximum, order-preserving compaction into the cell's output segment.
-// `aligned` (host-checked): level rows are 4-byte aligned, so the ROI is fetched as aligned 32-bit words and kept
-// at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).
+// `aligned` bit 0 (host-checked): level rows are 4-byte aligned, so the ROI is fetched as aligned 32-bit words and kept
+// at the same byte phase (pixel x of the ROI sits at column (x0 & 3) + x).  Bit 1 selects the second tile staging:
+// up to four ROI rows per warp step and 128-bit stores for the score-map clear (the first one spent 8 % of the
+// kernel's instructions there, profiles/r02_ncu_v4_summary.txt).
 template <int TP, bool SWEEP4>
 __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, const CellDesc* __restrict__ cells,
                                                                 int ncells, int slots_per_frame, int ini_th,
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, con
   extern __shared__ __align__(16) uint8_t fsm[];
   constexpr int P = 2 * TP;   // row pitch of the interleaved tile
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int cell = blockIdx.x * FAST_WARPS + w, f = blockIdx.y;
+  const int cell = blockIdx.x * (blockDim.x >> 5) + w, f = blockIdx.y;   // blockDim.x / 32 cells per CTA (host: <= FAST_WARPS)
   if (cell >= ncells) return;
   uint8_t* tile = fsm + (size_t)w * (rows_max * P + 2 * FAST_QLEN + 2 * clist_cap);
   unsigned short* queue = reinterpret_cast<unsigned short*>(tile + (size_t)rows_max * P);
@@ -208,12 +210,24 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, con
   const CellDesc cd = cells[cell];
   const int l = cd.level, rw = cd.rw, rh = cd.rh;
   const int pitch = pyr.pitch[l];
+  const bool stage2 = (aligned & 2) != 0;     // host switch: second formulation of the tile staging (below)
+  aligned &= 1;
   const int sh = aligned ? (cd.x0 & 3) : 0;   // byte phase of the ROI inside its first word
   {
     const uint8_t* img = pyr.p[l] + (size_t)f * pyr.fstride[l] + (size_t)cd.y0 * pitch + (cd.x0 - sh);
     if (aligned) {
-      const int nw = (sh + rw + 3) >> 2;   // words per ROI row
-      if (nw <= 16) {                      // two rows per step: lanes 0-15 / 16-31
+      const int nw = (sh + rw + 3) >> 2;   // words per ROI row (<= (3 + FAST_MAX_ROI + 3) / 4 = 19)
+      if (stage2) {
+        // up to four rows per warp step: lane = r * nw + k (640x480: nw = 10 -> 3 rows, 30 lanes); no integer division
+        const int rpl = (nw <= 8) ? 4 : (nw <= 10) ? 3 : (nw <= 16) ? 2 : 1;
+        const int r0 = (lane >= nw) + (lane >= 2 * nw) + (lane >= 3 * nw), k = lane - r0 * nw;
+        if (r0 < rpl && k < nw) {
+          const unsigned* src = reinterpret_cast<const unsigned*>(img + (size_t)r0 * pitch) + k;
+          unsigned* dst = reinterpret_cast<unsigned*>(tile + r0 * P) + k;
+          const size_t sstep = (size_t)rpl * (pitch >> 2);   // level pitches are multiples of 4 on this path
+          for (int y = r0; y < rh; y += rpl, src += sstep, dst += rpl * (P / 4)) *dst = __ldg(src);
+        }
+      } else if (nw <= 16) {               // two rows per step: lanes 0-15 / 16-31
         const int k = lane & 15, half = lane >> 4;
         for (int y = half; y < rh; y += 2)
           if (k < nw) reinterpret_cast<unsigned*>(tile + y * P)[k] = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)y * pitch) + k);
@@ -228,10 +242,18 @@ __global__ void __launch_bounds__(FAST_THREADS, 4) k_fast_cells(PyrView pyr, con
     }
     if (SWEEP4 && aligned) {
       // the word sweep only writes the scores of corners: clear every score row once (rows 2 .. rh-3 are read by the NMS)
-      constexpr int WPR = TP / 4;
-      for (int i = lane; i < (rh - 4) * WPR; i += 32) {
-        const int y = 2 + i / WPR, k = i - (y - 2) * WPR;
-        reinterpret_cast<unsigned*>(tile + y * P + TP)[k] = 0u;
+      if (stage2) {   // tile, P and TP are multiples of 16 bytes: 128-bit stores
+        constexpr int QPR = TP / 16;
+        for (int i = lane; i < (rh - 4) * QPR; i += 32) {
+          const int y = 2 + i / QPR, k = i - (y - 2) * QPR;
+          reinterpret_cast<uint4*>(tile + y * P + TP)[k] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      } else {
+        constexpr int WPR = TP / 4;
+        for (int i = lane; i < (rh - 4) * WPR; i += 32) {
+          const int y = 2 + i / WPR, k = i - (y - 2) * WPR;
+          reinterpret_cast<unsigned*>(tile + y * P + TP)[k] = 0u;
+        }
       }
     } else {
       // only the one-pixel frame around the detection range is read without being written: clear it
@@ -866,6 +888,110 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(LevelTab lt, Orie
     kp.octave = l;
     kp.class_id = -1;
     kps[(size_t)f * cap + j] = kp;
+  }
+}
+
+// K5, second formulation (selected by experimental_kernels() in orbx.cu, B200ORB_EXPERIMENTAL=0|1): the same arithmetic with fewer
+// instructions -- round-2 ncu capture (profiles/r02_ncu_v4_summary.txt): the first formulation is issue-bound (79 %
+// issue-active, 898 warp-instructions per keypoint) with the XU pipe (I2F / F2I conversions) at 52 %.
+//   * a warp handles KPW keypoints, so the per-CTA set-up (pattern into shared memory, level offsets) is paid once per
+//     8 * KPW keypoints instead of once per 8;
+//   * the pattern sits in shared memory as float4 (x0, y0, x1, y1) per test: one LDS.128 instead of LDS.32 + 4 I2F.S8;
+//   * the level of keypoint j comes from one ballot over the per-level inclusive counts (lane q holds level q) instead
+//     of an 8-iteration scan per warp;
+//   * IC_Angle walks two row pointers (+pitch / -pitch) instead of rebuilding a 64-bit address from u + v * pitch per
+//     load, tests the circular mask as v <= vmax(|u|) (umax is non-increasing in v -- checked at create -- so
+//     {v : |u| <= umax[v]} is the prefix 1..vmax), and accumulates sum(vp + vm) with one 3-input add per row, the
+//     multiplication by u once at the end (exact: integers).
+// Results are identical bit for bit (integer moments; the float sequence of the steered BRIEF is unchanged).
+constexpr int OD_KPW = 4;   // keypoints per warp
+
+__global__ void __launch_bounds__(OD_WARPS * 32, 8) k_orient_desc2(LevelTab lt, OrientTab ot, PyrView raw, PyrView blr,
+                                                                const float4* __restrict__ patf /* 256 tests */,
+                                                                const unsigned* __restrict__ sel,
+                                                                const int* __restrict__ selcnt, int sel_per_frame,
+                                                                OrbxKeyPoint* __restrict__ kps,
+                                                                uint8_t* __restrict__ desc, int* __restrict__ nout,
+                                                                int cap) {
+  __shared__ float4 spat[256];   // test pr: points 2 pr and 2 pr + 1 of the pattern, as floats
+  for (int i = threadIdx.x; i < 256; i += OD_WARPS * 32) spat[i] = __ldg(patf + i);
+  const int f = blockIdx.y, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // inclusive keypoint counts per level: lane q holds levels 0..q (lanes >= nlevels hold the total)
+  const int cq = (lane < lt.nlevels) ? selcnt[(size_t)f * lt.nlevels + lane] : 0;
+  const int incl = warp_incl_scan(cq, lane);
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (blockIdx.x == 0 && threadIdx.x == 0) nout[f] = min(total, cap);
+  const int u = lane - HALF_PATCH_SIZE, au = abs(u);
+  int vmaxu = 0;   // rows v = 1 .. vmaxu of column u lie inside the circular patch
+#pragma unroll
+  for (int v = 1; v <= HALF_PATCH_SIZE; ++v) vmaxu += (au <= ot.umax[v]) ? 1 : 0;
+  __syncthreads();
+  const int jmax = min(total, cap);
+#pragma unroll 1
+  for (int i = 0; i < OD_KPW; ++i) {
+    const int j = (blockIdx.x * OD_KPW + i) * OD_WARPS + w;
+    if (j >= jmax) break;   // warp-uniform
+    // level of keypoint j: the first level whose inclusive count exceeds j
+    const int l = __popc(__ballot_sync(0xffffffffu, lane < lt.nlevels && incl <= j));
+    const int before = __shfl_sync(0xffffffffu, incl, max(l - 1, 0));
+    const int idx = j - ((l > 0) ? before : 0);
+    const unsigned pk = sel[(size_t)f * sel_per_frame + lt.sel_off[l] + idx];
+    const int x = kp_x(pk), y = kp_y(pk);
+    // ---- IC_Angle: lane <-> column u = lane-15 (31 columns), rows +-v through two walking pointers ----
+    const ptrdiff_t rp = raw.pitch[l];
+    int s = 0, m01 = 0;
+    if (lane < 31) {
+      const uint8_t* pp = raw.p[l] + (size_t)f * raw.fstride[l] + (size_t)y * rp + (x + u);
+      const uint8_t* pm = pp;
+      s = *pp;
+#pragma unroll
+      for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+        pp += rp; pm -= rp;
+        if (v <= vmaxu) {
+          const int vp = *pp, vm = *pm;
+          s += vp + vm;
+          m01 += v * (vp - vm);
+        }
+      }
+    }
+    int m10 = u * s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // ---- steered BRIEF ----
+    const float factorPI = (float)(3.14159265358979323846 / 180.f);
+    const float ang = __fmul_rn(angle, factorPI);
+    const float a = b200_cosf(ang), b = b200_sinf(ang);   // glibc's cosf / sinf (not correctly rounded): same algorithm
+    const int bp = blr.pitch[l];
+    const uint8_t* bc = blr.p[l] + (size_t)f * blr.fstride[l] + (size_t)y * bp + x;
+    unsigned word = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 t = spat[k * 32 + lane];   // test k*32+lane -> bit (k*32+lane) of the descriptor
+      const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(t.x, b), __fmul_rn(t.y, a)));
+      const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(t.x, a), __fmul_rn(t.y, b)));
+      const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(t.z, b), __fmul_rn(t.w, a)));
+      const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(t.z, a), __fmul_rn(t.w, b)));
+      const int t0 = bc[r0 * bp + c0], t1 = bc[r1 * bp + c1];
+      const unsigned bits = __ballot_sync(0xffffffffu, t0 < t1);
+      if (lane == k) word = bits;
+    }
+    if (lane < 8) reinterpret_cast<unsigned*>(desc + ((size_t)f * cap + j) * 32)[lane] = word;
+    if (lane == 0) {
+      OrbxKeyPoint kp;
+      const float sc = lt.sf[l];
+      kp.x = (l != 0) ? __fmul_rn((float)x, sc) : (float)x;
+      kp.y = (l != 0) ? __fmul_rn((float)y, sc) : (float)y;
+      kp.size = lt.kp_size[l];
+      kp.angle = angle;
+      kp.response = (float)kp_r(pk);
+      kp.octave = l;
+      kp.class_id = -1;
+      kps[(size_t)f * cap + j] = kp;
+    }
   }
 }
 
