@@ -300,6 +300,39 @@ int orbv_transform(orbv_t* h, const uint8_t* desc, int n, int levelsup, uint32_t
                    uint32_t* node_id);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dynamic-mask stages of the `perfect` variant (the image-arithmetic parts):
+ *   FlowSLAM::Flow::ComputeMask (perfect/include/Flow.h:24-27, perfect/src/Flow.cc:17-52) after the call of
+ *   cv::calcOpticalFlowFarneback -- which stays on the host side: OpenCV's own float code -- i.e. pyrUp of the half-
+ *   resolution flow field (:30), mask = 1 except 0 where x*x + y*y >= max(BInaryThreshold, 40) (:24,31-41), then
+ *   erode, erode, dilate with getStructuringElement(MORPH_ELLIPSE, 21x21) (:42-47);
+ *   and the keypoint loop of the masked RGB-D Frame constructor (perfect/src/Frame.cc:356-377): if cv::sum(mask) >
+ *   rows*cols*0.65, keypoints whose pixel mask.at<uchar>(pt.y, pt.x) is not 1 are dropped together with their
+ *   descriptor rows, order kept; otherwise nothing is dropped.
+ * flow: rows x cols x 2 float (CV_32FC2, continuous) at half resolution; mask: mask_rows x mask_cols bytes (0 / 1),
+ * continuous, the size of the gray image (2 rows <= mask_rows <= 2 rows + 1, likewise the columns: pyrDown halves with
+ * truncation); pixels beyond the 2 rows x 2 cols the up-sampled flow covers keep their initial 1 (:25).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct dynm dynm_t;
+int dynm_create(int device, dynm_t** out);
+void dynm_destroy(dynm_t* h);
+long long dynm_launch_count(const dynm_t* h);
+void* dynm_stream(dynm_t* h);
+int dynm_sync(dynm_t* h);
+int dynm_element(const dynm_t* h, uint8_t* element /* 21 x 21: the structuring element in use */);
+int dynm_mask_from_flow(dynm_t* h, const float* flow, int rows, int cols, float binary_threshold, uint8_t* mask, int mask_rows,
+                        int mask_cols);
+/* nframes flow fields / masks back to back in HBM, asynchronous on the handle's stream */
+int dynm_mask_from_flow_batch_device(dynm_t* h, const float* d_flow, int nframes, int rows, int cols, float binary_threshold,
+                                     uint8_t* d_mask, int mask_rows, int mask_cols);
+/* host buffers, filtered in place; *n_out keypoints remain */
+int dynm_filter_keypoints(dynm_t* h, const uint8_t* mask, int rows, int cols, size_t stride, OrbxKeyPoint* kps, uint8_t* desc,
+                          int n, int* n_out);
+/* the layout of orbx_device_results / orbs_device_results: kps [nframes][cap], desc [nframes][cap][32], counts [nframes],
+ * masks [nframes][rows][cols]; filtered in place, asynchronous on the handle's stream */
+int dynm_filter_keypoints_batch_device(dynm_t* h, const uint8_t* d_mask, int nframes, int rows, int cols, OrbxKeyPoint* d_kps,
+                                       uint8_t* d_desc, int32_t* d_counts, int cap);
+
+/* ------------------------------------------------------------------------------------------------
  * Stream pipeline (batched many-frame mode of north_star): per frame t of a batch, what
  * Tracking::GrabImageRGBD -> Frame::Frame(RGB-D) -> TrackWithMotionModel's SearchByProjection do
  * (src/Tracking.cc:331-375,1324-1352; src/Frame.cc:176-240): extract, ComputeStereoFromRGBD

@@ -37,6 +37,8 @@ EXPORTS = [
     "ocm_export_summaries_device", "ocm_apply_summaries_device", "ocm_sync", "ocm_stream", "ocm_launch_count",
     "ocm_insert_keyframes_labeled_device", "ocm_insert_keyframes_u16_labeled", "ocm_merge_nccl", "ocm_nccl_unique_id",
     "ocm_nccl_comm_create", "ocm_nccl_comm_destroy", "ocm_last_batch_stats",
+    "dynm_create", "dynm_destroy", "dynm_launch_count", "dynm_stream", "dynm_sync", "dynm_element", "dynm_mask_from_flow",
+    "dynm_mask_from_flow_batch_device", "dynm_filter_keypoints", "dynm_filter_keypoints_batch_device",
 ]
 
 
@@ -102,6 +104,19 @@ def lib() -> C.CDLL:
     L.orbv_launch_count.argtypes = [vp]
     L.orbv_launch_count.restype = C.c_longlong
     L.orbv_transform.argtypes = [vp, vp, i, i, vp, vp, vp]
+    L.dynm_create.argtypes = [i, C.POINTER(vp)]
+    L.dynm_destroy.argtypes = [vp]
+    L.dynm_destroy.restype = None
+    L.dynm_launch_count.argtypes = [vp]
+    L.dynm_launch_count.restype = C.c_longlong
+    L.dynm_stream.argtypes = [vp]
+    L.dynm_stream.restype = vp
+    L.dynm_sync.argtypes = [vp]
+    L.dynm_element.argtypes = [vp, vp]
+    L.dynm_mask_from_flow.argtypes = [vp, vp, i, i, C.c_float, vp, i, i]
+    L.dynm_mask_from_flow_batch_device.argtypes = [vp, vp, i, i, i, C.c_float, vp, i, i]
+    L.dynm_filter_keypoints.argtypes = [vp, vp, i, i, sz, vp, vp, i, C.POINTER(i)]
+    L.dynm_filter_keypoints_batch_device.argtypes = [vp, vp, i, i, i, vp, vp, vp, i]
     L.orbs_create.argtypes = [C.POINTER(OrbsParams), i, C.POINTER(vp)]
     L.orbs_destroy.argtypes = [vp]
     L.orbs_destroy.restype = None

@@ -5,3 +5,4 @@
 #include "ocm.cu"
 #include "gcm.cu"
 #include "orbv.cu"
+#include "dynm.cu"

@@ -231,3 +231,22 @@ class RoomStream:
         if with_label:
             return gray, depth, rgb, self.pose(t), (face == 4).astype(np.uint8)
         return gray, depth, rgb, self.pose(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# Dense flow fields for the dynamic-mask stage (perfect/src/Flow.cc): what calcOpticalFlowFarneback hands to pyrUp
+# ------------------------------------------------------------------------------------------------
+def flow_field(seed, rows, cols, blobs=6):
+    """Smooth background flow (camera motion, |flow| ~ 2-5 px) + a few fast-moving blobs (|flow| up to ~15 px) + noise."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    yy, xx = np.mgrid[0:rows, 0:cols].astype(np.float32)
+    f = np.zeros((rows, cols, 2), np.float32)
+    f[..., 0] = 2.5 + 1.5 * np.sin(xx / 37.0) + rng.normal(0, 0.3, (rows, cols))
+    f[..., 1] = -1.0 + 2.0 * np.cos(yy / 29.0) + rng.normal(0, 0.3, (rows, cols))
+    for _ in range(blobs):
+        cy, cx = rng.integers(0, rows), rng.integers(0, cols)
+        ry, rx = rng.integers(4, max(rows // 4, 5)), rng.integers(4, max(cols // 4, 5))
+        v = rng.normal(0, 9.0, 2).astype(np.float32)
+        m = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
+        f[m] += v
+    return f.astype(np.float32)

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     txt = open(os.path.join(ROOT, "include", "b200orb.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:orbx|orbm|orbs|orbv|ocm|gcm|b200orb)_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b((?:orbx|orbm|orbs|orbv|ocm|gcm|dynm|b200orb)_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -43,7 +43,8 @@ def test_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     import orb_slam2_ssd_semantic_b200 as pkg
-    for ctor in (pkg.ORBextractor, pkg.ORBmatcher, pkg.StreamTracker, pkg.PointCloudMapping, pkg.GlobalCloudMapping):
+    from orb_slam2_ssd_semantic_b200.dynmask import DynamicMask
+    for ctor in (pkg.ORBextractor, pkg.ORBmatcher, pkg.StreamTracker, pkg.PointCloudMapping, pkg.GlobalCloudMapping, DynamicMask):
         with pytest.raises(pkg.B200OrbError) as e:
             ctor()
         assert e.value.code == -4 and "no CPU fallback" in str(e.value)
@@ -87,3 +88,13 @@ def test_shims_compile_against_the_reference_sources():
     for name in ("projection_last", "projection_points", "projection_kf", "projection_sim3", "bow", "bow_kf", "initialization",
                  "triangulation", "search_by_sim3", "fuse", "fuse_sim3", "frame_rgbd", "pipeline_run", "orb_extract"):
         assert hasattr(L, "shimsrc_" + name), name
+
+
+def test_flow_shim_syntax():
+    """shim/Flow.h (drop-in for perfect/include/Flow.h) compiles against the stand-in cv:: types; the three OpenCV calls it
+    leaves on the host are declared by oracle/standin/flow_decls.hpp."""
+    import subprocess
+    shim = os.path.join(ROOT, "orb_slam2_ssd_semantic_b200", "csrc", "shim")
+    subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-x", "c++", "-include",
+                           os.path.join(ROOT, "oracle", "standin", "flow_decls.hpp"), os.path.join(shim, "Flow.h"),
+                           "-I" + os.path.join(ROOT, "oracle", "standin"), "-I" + os.path.join(ROOT, "include")])
