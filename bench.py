@@ -158,6 +158,14 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def _experimental_mask():
+    try:
+        from orb_slam2_ssd_semantic_b200 import _lib
+        return int(_lib.lib().b200orb_experimental())
+    except Exception:
+        return None
+
+
 def workload_config(args, world, frames_step):
     return {"workload": "synthetic 640x480 RGB-D room stream (SURVEY 8(d)), batched many-frame mode: %d-frame batches, "
                         "ORBextractor(%d,1.2,8,20,7) + stereo-from-depth + SearchByProjection(cur,last,th=15) per frame, "
@@ -169,7 +177,8 @@ def workload_config(args, world, frames_step):
             "parallelism": ("single GPU" if world == 1 else
                             "strong scaling: contiguous frame shards x%d (+1 halo frame), ocm_merge_nccl per step" % world),
             "l2": "inputs of one pass over the resident batch (%.0f MB gray+depth+rgb+label) exceed the 126 MB L2; no "
-                  "explicit flush" % (BATCH * S_IN * 9 / 1e6)}
+                  "explicit flush" % (BATCH * S_IN * 9 / 1e6),
+            "kernels": {"experimental_mask": _experimental_mask(), "fast_warps_per_cta": os.environ.get("B200ORB_FAST_WPC", "8")}}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -257,13 +266,18 @@ def run_reference(args):
 
 # DRAM traffic of the single-launch stages, bytes per frame, from the ncu capture named in traffic_source
 NCU_DRAM_BYTES_PER_FRAME = {}
+NCU_WARP_INST_PER_FRAME = {}   # smsp__inst_executed.sum per frame of the same capture (kernels with experimental mask 0)
 NCU_SOURCE = None
 try:
     with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as _f:
         _j = json.load(_f)
         NCU_DRAM_BYTES_PER_FRAME, NCU_SOURCE = _j["bytes_per_frame"], _j["source"]
+        NCU_WARP_INST_PER_FRAME = _j.get("warp_inst_per_frame", {})
 except Exception:
     pass
+# stages whose kernel changes with a bit of b200orb_experimental(): the captured instruction count no longer applies
+# (bit 1, the second FAST tile staging, changes k_fast_cells' count by ~2 %: kept, see profiles/r02_notes.md)
+EXPERIMENTAL_STAGE_BITS = {"orient_desc": 1}
 
 
 def run_b200(args):
@@ -504,9 +518,21 @@ def run_b200(args):
         peak, peak_src = measured_peak()
         stages = {}
         prof_frames = max(prof_frames, 1)
+        exp_mask = int(_lib.lib().b200orb_experimental())
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        sm_hz = (clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965) * 1e6
+        issue_peak = n_sm * 4 * sm_hz                # warp instructions / s: 4 schedulers per SM, one issue per clock each
+        inst_tot = t_tot = 0.0
         for k, v in stage_ms.items():
             gbs = ab[k] * prof_frames / (v * 1e-3) / 1e9 if v > 0 else 0.0
             stages[k] = {"ms_per_step": v / stage_steps, "algorithmic_bytes_per_frame": ab[k], "gbs": gbs, "frac": gbs / peak}
+            # the bound these kernels actually run against: the SM's instruction-issue rate (ncu: issue-active 40-80 %)
+            if k in NCU_WARP_INST_PER_FRAME and not (exp_mask & EXPERIMENTAL_STAGE_BITS.get(k, 0)) and v > 0:
+                wi = NCU_WARP_INST_PER_FRAME[k]
+                stages[k]["warp_inst_per_frame"] = wi
+                stages[k]["issue_frac"] = wi * prof_frames / (v * 1e-3) / issue_peak
+                inst_tot += wi * prof_frames
+                t_tot += v * 1e-3
         if nkf_alone:
             bmap = map_bytes(pts_sum / max(last_round, 1), upd_per_kf)
             gbs = bmap * nkf_alone / (map_alone_ms * 1e-3) / 1e9
@@ -537,6 +563,11 @@ def run_b200(args):
                          "stages_measured": "tracking stages: one serial step on one tracker handle, nothing else on the GPU, right "
                                             "after the timed region (inside it two batches and the mapper are in flight on three "
                                             "streams and their kernels overlap); mapping: one step's keyframes alone",
+                         "issue": {"bound": "instruction issue (integer / bitwise path: no kernel is HBM-bound)",
+                                   "peak_warp_inst_per_s": issue_peak, "sms": n_sm,
+                                   "achieved_frac_counted_stages": (inst_tot / t_tot / issue_peak) if t_tot > 0 else None,
+                                   "source": "warp_inst_per_frame: smsp__inst_executed.sum of " + str(NCU_SOURCE) +
+                                             "; stages whose kernel was switched by b200orb_experimental() are left out"},
                          "pipeline": {"achieved": pipe_gbs, "frac": pipe_gbs / peak,
                                       "algorithmic_bytes_per_frame": pipeline_bytes(n_kp),
                                       "note": "B_ext + B_match per tracked frame / whole timed region (mapping overlapped)"},

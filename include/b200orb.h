@@ -30,6 +30,9 @@ extern "C" {
 const char* b200orb_last_error(void);   /* thread-local message of the last failing call */
 int b200orb_device_count(void);         /* number of CUDA devices visible (0 if none / no driver) */
 const char* b200orb_version(void);
+/* Bit mask of the kernel formulations in force that were added after the previous hardware validation (0 = none;
+ * environment B200ORB_EXPERIMENTAL overrides the built-in default): bit 0 k_orient_desc2, bit 1 second FAST tile staging. */
+int b200orb_experimental(void);
 
 /* ------------------------------------------------------------------------------------------------
  * ORB extractor  --  ORB_SLAM2::ORBextractor (include/ORBextractor.h:41-118, src/ORBextractor.cc)

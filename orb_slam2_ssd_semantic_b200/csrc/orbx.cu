@@ -40,14 +40,16 @@ static const signed char kPatternHost[1024] = {
 };
 
 // Kernel formulations added after the last hardware-validated state sit behind this switch until the GPU parity suite
-// has seen them: B200ORB_EXPERIMENTAL=1 / 0 overrides the built-in default.
-constexpr bool kExperimentalDefault = false;
-static inline bool experimental_kernels() {
-  static const bool on = [] {
+// has seen them.  B200ORB_EXPERIMENTAL=<mask> overrides the built-in default: bit 0 = k_orient_desc2, bit 1 = second
+// tile staging of k_fast_cells.  b200orb_experimental() reports the mask in force (bench.py prints it).
+constexpr int kExperimentalDefault = 0;
+constexpr int EXP_ORIENT2 = 1, EXP_FAST_STAGE2 = 2;
+static inline int experimental_mask() {
+  static const int mask = [] {
     const char* e = getenv("B200ORB_EXPERIMENTAL");
-    return e ? (e[0] == '1') : kExperimentalDefault;
+    return e ? atoi(e) : kExperimentalDefault;
   }();
-  return on;
+  return mask;
 }
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
@@ -388,7 +390,7 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
   int fast_aligned = 1;   // every level's rows 4-byte aligned? (internal planes always are; level 0 may alias a caller buffer)
   for (int l = 0; l < nl; ++l)
     if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) fast_aligned = 0;
-  if (fast_aligned && experimental_kernels()) fast_aligned |= 2;   // second tile staging of k_fast_cells
+  if (fast_aligned && (experimental_mask() & EXP_FAST_STAGE2)) fast_aligned |= 2;   // second tile staging of k_fast_cells
   {
     // cells (= warps) per CTA: 8 by default; B200ORB_FAST_WPC=1|2|4 launches smaller CTAs (same kernel: a warp never
     // synchronises with its neighbours), which shortens the tail a CTA spends waiting for its slowest cell
@@ -444,7 +446,7 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
   B200_CHECK(prof_mark(ST_BLUR + 1));
   // K5 orientation + descriptors
   {
-    if (!experimental_kernels())
+    if (!(experimental_mask() & EXP_ORIENT2))
       k_orient_desc<<<dim3((cap + OD_WARPS - 1) / OD_WARPS, F), OD_WARPS * 32, 0, stream>>>(
           ltab, otab, rawv, blurv, d_pattern, d_sel, d_selcnt, sel_per_frame, d_kps, d_desc, d_n, cap);
     else
@@ -499,6 +501,9 @@ int orbx::ensure_tmp(size_t bytes) {
 // C-ABI
 // =====================================================================================================
 extern "C" {
+
+int b200orb_experimental(void) { return experimental_mask(); }
+
 
 const char* b200orb_last_error(void) { return g_err; }
 const char* b200orb_version(void) { return "b200orb 0.1 (sm_100a)"; }

@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(OD_WARPS * 32) k_orient_desc(LevelTab lt, Orie
   }
 }
 
-// K5, second formulation (selected by experimental_kernels() in orbx.cu, B200ORB_EXPERIMENTAL=0|1): the same arithmetic with fewer
+// K5, second formulation (bit 0 of experimental_mask() in orbx.cu, B200ORB_EXPERIMENTAL): the same arithmetic with fewer
 // instructions -- round-2 ncu capture (profiles/r02_ncu_v4_summary.txt): the first formulation is issue-bound (79 %
 // issue-active, 898 warp-instructions per keypoint) with the XU pipe (I2F / F2I conversions) at 52 %.
 //   * a warp handles KPW keypoints, so the per-CTA set-up (pattern into shared memory, level offsets) is paid once per
