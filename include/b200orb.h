@@ -33,6 +33,11 @@ const char* b200orb_version(void);
 /* Bit mask of the kernel formulations in force that were added after the previous hardware validation (0 = none;
  * environment B200ORB_EXPERIMENTAL overrides the built-in default): bit 0 k_orient_desc2, bit 1 second FAST tile staging. */
 int b200orb_experimental(void);
+/* Launch-shape tuning of the extractor (process-wide; results never depend on it): FAST cells per CTA (1, 2, 4, 8) and the
+ * quad-tree's register budget (2, 3 or 4 CTAs per SM); exp_mask as above.  Negative arguments keep the current value.
+ * Environment at load: B200ORB_EXPERIMENTAL, B200ORB_FAST_WPC, B200ORB_QT_MINB. */
+int b200orb_get_tuning(int* exp_mask, int* fast_wpc, int* qt_minblocks);
+int b200orb_set_tuning(int exp_mask, int fast_wpc, int qt_minblocks);
 
 /* ------------------------------------------------------------------------------------------------
  * ORB extractor  --  ORB_SLAM2::ORBextractor (include/ORBextractor.h:41-118, src/ORBextractor.cc)

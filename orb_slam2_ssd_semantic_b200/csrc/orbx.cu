@@ -39,18 +39,27 @@ static const signed char kPatternHost[1024] = {
 #include "../../include/orb_pattern_31.inc"
 };
 
-// Kernel formulations added after the last hardware-validated state sit behind this switch until the GPU parity suite
-// has seen them.  B200ORB_EXPERIMENTAL=<mask> overrides the built-in default: bit 0 = k_orient_desc2, bit 1 = second
-// tile staging of k_fast_cells.  b200orb_experimental() reports the mask in force (bench.py prints it).
-constexpr int kExperimentalDefault = 0;
+// Kernel selection.  Formulations added after the last hardware-validated state sit behind `exp_mask` until the GPU
+// parity suite has seen them (bit 0 = k_orient_desc2, bit 1 = second tile staging of k_fast_cells); `fast_wpc` (FAST cells
+// = warps per CTA: 1, 2, 4, 8) and `qt_minb` (quad-tree register budget for 2, 3 or 4 CTAs per SM) only change launch
+// shapes.  Defaults below; the environment (B200ORB_EXPERIMENTAL, B200ORB_FAST_WPC, B200ORB_QT_MINB) overrides them at
+// load, b200orb_set_tuning() at run time (tools/tune_extractor.py); b200orb_experimental() / b200orb_get_tuning() report.
+constexpr int kExperimentalDefault = 0, kFastWpcDefault = 8, kQtMinbDefault = 2;
 constexpr int EXP_ORIENT2 = 1, EXP_FAST_STAGE2 = 2;
-static inline int experimental_mask() {
-  static const int mask = [] {
-    const char* e = getenv("B200ORB_EXPERIMENTAL");
-    return e ? atoi(e) : kExperimentalDefault;
+struct Tuning { int exp_mask, fast_wpc, qt_minb; };
+static inline bool valid_wpc(int v) { return v == 1 || v == 2 || v == 4 || v == 8; }
+static inline bool valid_minb(int v) { return v >= 2 && v <= 4; }
+static Tuning& tuning() {
+  static Tuning t = [] {
+    Tuning d{kExperimentalDefault, kFastWpcDefault, kQtMinbDefault};
+    if (const char* e = getenv("B200ORB_EXPERIMENTAL")) d.exp_mask = atoi(e);
+    if (const char* e = getenv("B200ORB_FAST_WPC")) { const int v = atoi(e); if (valid_wpc(v)) d.fast_wpc = v; }
+    if (const char* e = getenv("B200ORB_QT_MINB")) { const int v = atoi(e); if (valid_minb(v)) d.qt_minb = v; }
+    return d;
   }();
-  return mask;
+  return t;
 }
+static inline int experimental_mask() { return tuning().exp_mask; }
 
 static inline int cv_round_f(float v) { return (int)lrintf(v); }
 static inline int cv_round_d(double v) { return (int)lrint(v); }
@@ -291,6 +300,8 @@ int orbx::ensure_geometry(int r, int c, int F) {
       mx = std::max(mx, qt_group_smem[g]);
     }
     B200_CUDA(cudaFuncSetAttribute(k_quadtree, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+    B200_CUDA(cudaFuncSetAttribute(k_quadtree_o3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+    B200_CUDA(cudaFuncSetAttribute(k_quadtree_o4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
   }
 
   rows = r; cols = c; maxF = keepF;
@@ -392,13 +403,9 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
     if ((((uintptr_t)rawv.p[l]) & 3) || (rawv.pitch[l] & 3) || (rawv.fstride[l] & 3)) fast_aligned = 0;
   if (fast_aligned && (experimental_mask() & EXP_FAST_STAGE2)) fast_aligned |= 2;   // second tile staging of k_fast_cells
   {
-    // cells (= warps) per CTA: 8 by default; B200ORB_FAST_WPC=1|2|4 launches smaller CTAs (same kernel: a warp never
-    // synchronises with its neighbours), which shortens the tail a CTA spends waiting for its slowest cell
-    static const int wpc = [] {
-      const char* e = getenv("B200ORB_FAST_WPC");
-      const int v = e ? atoi(e) : FAST_WARPS;
-      return (v == 1 || v == 2 || v == 4) ? v : FAST_WARPS;
-    }();
+    // cells (= warps) per CTA: smaller CTAs (same kernel: a warp never synchronises with its neighbours) shorten the
+    // tail a CTA spends waiting for its slowest cell
+    const int wpc = tuning().fast_wpc;
     const dim3 grd((ncells + wpc - 1) / wpc, F);
     const size_t fast_smem_l = fast_smem / FAST_WARPS * wpc;
     // B200ORB_FAST_SWEEP=1 selects the one-pixel-per-lane sweep (development A/B switch; default: the word sweep)
@@ -418,9 +425,10 @@ int orbx::run(const uint8_t* d_l0, int pitch0, size_t fstride0, int F, int f0) {
   for (int g = 0; g < 3; ++g) {
     const int lb = qt_group_lb[g], le = qt_group_le[g];
     if (le <= lb) continue;
-    k_quadtree<<<dim3(le - lb, F), QT_THREADS, qt_group_smem[g], stream>>>(ltab, d_cells, d_cand, d_cellcnt, ncells,
-                                                                           slots_per_frame, qs, qt_cap, d_sel, d_selcnt,
-                                                                           d_candcnt, sel_per_frame, lb, qt_group_kcap[g]);
+    auto* qt_kernel = tuning().qt_minb == 4 ? k_quadtree_o4 : tuning().qt_minb == 3 ? k_quadtree_o3 : k_quadtree;
+    qt_kernel<<<dim3(le - lb, F), QT_THREADS, qt_group_smem[g], stream>>>(ltab, d_cells, d_cand, d_cellcnt, ncells,
+                                                                          slots_per_frame, qs, qt_cap, d_sel, d_selcnt,
+                                                                          d_candcnt, sel_per_frame, lb, qt_group_kcap[g]);
     ++launches;
   }
   B200_CHECK(prof_mark(ST_QUADTREE + 1));
@@ -503,6 +511,24 @@ int orbx::ensure_tmp(size_t bytes) {
 extern "C" {
 
 int b200orb_experimental(void) { return experimental_mask(); }
+int b200orb_get_tuning(int* exp_mask, int* fast_wpc, int* qt_minblocks) {
+  const Tuning& t = tuning();
+  if (exp_mask) *exp_mask = t.exp_mask;
+  if (fast_wpc) *fast_wpc = t.fast_wpc;
+  if (qt_minblocks) *qt_minblocks = t.qt_minb;
+  return B200ORB_OK;
+}
+int b200orb_set_tuning(int exp_mask, int fast_wpc, int qt_minblocks) {   // negative = keep
+  if ((fast_wpc >= 0 && !valid_wpc(fast_wpc)) || (qt_minblocks >= 0 && !valid_minb(qt_minblocks))) {
+    set_error("bad tuning value");
+    return B200ORB_EINVAL;
+  }
+  Tuning& t = tuning();
+  if (exp_mask >= 0) t.exp_mask = exp_mask;
+  if (fast_wpc >= 0) t.fast_wpc = fast_wpc;
+  if (qt_minblocks >= 0) t.qt_minb = qt_minblocks;
+  return B200ORB_OK;
+}
 
 
 const char* b200orb_last_error(void) { return g_err; }

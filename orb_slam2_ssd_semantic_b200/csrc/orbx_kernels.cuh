@@ -478,13 +478,16 @@ __device__ int qt_scan_array(int* a, int n, int* ws) {
   return total;
 }
 
-__global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const CellDesc* __restrict__ cells,
-                                                         const unsigned* __restrict__ cand,
-                                                         const int* __restrict__ cellcnt, int ncells,
-                                                         int slots_per_frame, QtScratchView sc, int qt_cap,
-                                                         unsigned* __restrict__ sel, int* __restrict__ selcnt,
-                                                         int* __restrict__ candcnt, int sel_per_frame,
-                                                         int level_begin, int kp_smem_cap) {
+// The body is shared by three entry points that differ only in their register budget (k_quadtree: the compiler's choice,
+// 53 registers -> 2 CTAs per SM; k_quadtree_o3 / _o4: capped for 3 / 4 CTAs per SM): the kernel is latency-bound
+// (42 % issue-active, barrier + L2 stalls, profiles/r02_ncu_v4_summary.txt), so resident CTAs are what hides it.
+__device__ __forceinline__ void quadtree_body(const LevelTab& lt, const CellDesc* __restrict__ cells,
+                                              const unsigned* __restrict__ cand,
+                                              const int* __restrict__ cellcnt, int ncells,
+                                              int slots_per_frame, QtScratchView sc, int qt_cap,
+                                              unsigned* __restrict__ sel, int* __restrict__ selcnt,
+                                              int* __restrict__ candcnt, int sel_per_frame,
+                                              int level_begin, int kp_smem_cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int ws[33];
   __shared__ int s_coff[QT_THREADS];
@@ -734,6 +737,18 @@ __global__ void __launch_bounds__(QT_THREADS) k_quadtree(LevelTab lt, const Cell
   for (int i = tid; i < n; i += nthr) out[i] = qkp[0xffffffu - (best[i] & 0xffffffu)];
   if (tid == 0) selcnt[(size_t)f * nlev + l] = n;
 }
+
+#define B200_QT_ARGS LevelTab lt, const CellDesc* __restrict__ cells, const unsigned* __restrict__ cand,             \
+                     const int* __restrict__ cellcnt, int ncells, int slots_per_frame, QtScratchView sc, int qt_cap,   \
+                     unsigned* __restrict__ sel, int* __restrict__ selcnt, int* __restrict__ candcnt, int sel_per_frame, \
+                     int level_begin, int kp_smem_cap
+#define B200_QT_PASS lt, cells, cand, cellcnt, ncells, slots_per_frame, sc, qt_cap, sel, selcnt, candcnt, sel_per_frame, \
+                     level_begin, kp_smem_cap
+__global__ void __launch_bounds__(QT_THREADS) k_quadtree(B200_QT_ARGS) { quadtree_body(B200_QT_PASS); }
+__global__ void __launch_bounds__(QT_THREADS, 3) k_quadtree_o3(B200_QT_ARGS) { quadtree_body(B200_QT_PASS); }
+__global__ void __launch_bounds__(QT_THREADS, 4) k_quadtree_o4(B200_QT_ARGS) { quadtree_body(B200_QT_PASS); }
+#undef B200_QT_ARGS
+#undef B200_QT_PASS
 
 // ---------------------------------------------------------------------------------------------------
 // K4  GaussianBlur 7x7 sigma 2, BORDER_REFLECT_101 (call site :1094-1095).
