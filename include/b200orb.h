@@ -30,8 +30,8 @@ extern "C" {
 const char* b200orb_last_error(void);   /* thread-local message of the last failing call */
 int b200orb_device_count(void);         /* number of CUDA devices visible (0 if none / no driver) */
 const char* b200orb_version(void);
-/* Bit mask of the kernel formulations in force that were added after the previous hardware validation (0 = none;
- * environment B200ORB_EXPERIMENTAL overrides the built-in default): bit 0 k_orient_desc2, bit 1 second FAST tile staging. */
+/* Bit mask of the round-2 kernel formulations in force (default 3; environment B200ORB_EXPERIMENTAL overrides it, 0 = the
+ * first formulations, kept for A/B): bit 0 k_orient_desc2, bit 1 second FAST tile staging.  Results never depend on it. */
 int b200orb_experimental(void);
 /* Launch-shape tuning of the extractor (process-wide; results never depend on it): FAST cells per CTA (1, 2, 4, 8) and the
  * quad-tree's register budget (2, 3 or 4 CTAs per SM); exp_mask as above.  Negative arguments keep the current value.
