@@ -44,10 +44,11 @@ static const signed char kPatternHost[1024] = {
 // = warps per CTA: 1, 2, 4, 8) and `qt_minb` (quad-tree register budget for 2, 3 or 4 CTAs per SM) only change launch
 // shapes.  Defaults below; the environment (B200ORB_EXPERIMENTAL, B200ORB_FAST_WPC, B200ORB_QT_MINB) overrides them at
 // load, b200orb_set_tuning() at run time (tools/tune_extractor.py); b200orb_experimental() / b200orb_get_tuning() report.
-// Defaults = the configuration the B200 runs of round 2 ended on (profiles/r02_notes.md): both formulations passed the
-// whole GPU parity suite (B200ORB_EXPERIMENTAL=3: 77 passed) and tools/tune_extractor.py found every setting byte-identical
-// to (0, 8, 2) and (3, 4, 4) the fastest; B200ORB_EXPERIMENTAL=0 B200ORB_FAST_WPC=8 B200ORB_QT_MINB=2 restores round 1's.
-constexpr int kExperimentalDefault = 3, kFastWpcDefault = 4, kQtMinbDefault = 4;
+// Defaults = what the B200 runs of round 2 ended on (profiles/r02_notes.md): both formulations passed the whole GPU parity
+// suite (B200ORB_EXPERIMENTAL=3: 77 passed), tools/tune_extractor.py found every setting byte-identical to (0, 8, 2), the
+// quad-tree 7 - 19 % faster with 4 CTAs per SM and the FAST CTA size irrelevant (within 1 %: the suite's 8 stays).
+// B200ORB_EXPERIMENTAL=0 B200ORB_QT_MINB=2 restores round 1's kernels.
+constexpr int kExperimentalDefault = 3, kFastWpcDefault = 8, kQtMinbDefault = 4;
 constexpr int EXP_ORIENT2 = 1, EXP_FAST_STAGE2 = 2;
 struct Tuning { int exp_mask, fast_wpc, qt_minb; };
 static inline bool valid_wpc(int v) { return v == 1 || v == 2 || v == 4 || v == 8; }
