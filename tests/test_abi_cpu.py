@@ -98,3 +98,23 @@ def test_flow_shim_syntax():
     subprocess.check_call(["g++", "-std=c++14", "-fsyntax-only", "-Wall", "-x", "c++", "-include",
                            os.path.join(ROOT, "oracle", "standin", "flow_decls.hpp"), os.path.join(shim, "Flow.h"),
                            "-I" + os.path.join(ROOT, "oracle", "standin"), "-I" + os.path.join(ROOT, "include")])
+
+
+def test_tuning_get_set_round_trip():
+    """b200orb_get_tuning / b200orb_set_tuning are plain process state (no GPU): defaults, validation, keep-on-negative."""
+    import orb_slam2_ssd_semantic_b200 as pkg
+    L = pkg.lib()
+    m, w, q = C.c_int(), C.c_int(), C.c_int()
+    assert L.b200orb_get_tuning(C.byref(m), C.byref(w), C.byref(q)) == 0
+    saved = (m.value, w.value, q.value)
+    assert w.value in (1, 2, 4, 8) and q.value in (2, 3, 4) and L.b200orb_experimental() == m.value
+    try:
+        assert L.b200orb_set_tuning(1, 2, 3) == 0
+        L.b200orb_get_tuning(C.byref(m), C.byref(w), C.byref(q))
+        assert (m.value, w.value, q.value) == (1, 2, 3)
+        assert L.b200orb_set_tuning(-1, 3, -1) != 0 and L.b200orb_set_tuning(-1, -1, 7) != 0     # rejected, nothing changes
+        assert L.b200orb_set_tuning(-1, -1, -1) == 0
+        L.b200orb_get_tuning(C.byref(m), C.byref(w), C.byref(q))
+        assert (m.value, w.value, q.value) == (1, 2, 3)
+    finally:
+        assert L.b200orb_set_tuning(*saved) == 0
