@@ -1,4 +1,5 @@
 #!/bin/bash
+# (kept for the record: the last full GPU call of round 2, run as `gpurun -- bash tools/gpu_final_check.sh`)
 # last GPU call of the round: parity of the formulations behind B200ORB_EXPERIMENTAL (+ the new dynm_* kernels), launch-shape
 # A/B in one process, then the bench line with the configuration that survived.
 mkdir -p gpurun_out
