@@ -1,7 +1,8 @@
 """CPU restatement (numpy) of the dynamic-mask stages -- TEST INFRASTRUCTURE ONLY (tests/, smoke): never imported by the
 product.  Pinned against the third-party code the reference calls: cv2 4.13's pyrUp / erode / dilate /
 getStructuringElement (tools/make_dynmask_golden.py wrote tests/golden/dynmask_*.npz from cv2's outputs;
-tests/test_oracle_cpu.py checks this file against them and, where cv2 is importable, against cv2 live).
+tests/test_dynmask_cpu.py checks this file against them and, where cv2 is importable, against cv2 live); filter_keypoints is
+pinned to the reference's own masked Frame constructor (perfect/src/Frame.cc compiled unmodified: oracle/_ref/librefperfect.so).
 
   perfect/src/Flow.cc:30      pyrUp(flow, flow2, Size(2 cols, 2 rows))        -> pyr_up
   perfect/src/Flow.cc:24,31-41 threshold loop                                  -> flow_mask

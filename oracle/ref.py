@@ -925,3 +925,43 @@ def src_bow_transform(k, L, parent, node_desc, weight, desc, prefix="refsrc"):
     bow = {int(words[i]): float(values[i]) for i in range(nw.value)}
     fv = {int(node_ids[j]): [int(v) for v in idx[node_off[j]:node_off[j + 1]]] for j in range(nn.value)}
     return bow, fv
+
+
+# ------------------------------------------------------------------------------------------------
+# oracle/_ref/librefperfect.so: the `perfect` tree's OWN sources (perfect/src/Frame.cc with its masked RGB-D constructor,
+# KeyFrame.cc, MapPoint.cc, Map.cc, ORBextractor.cc, ORBmatcher.cc) compiled unmodified (oracle/Makefile, target `perfect`).
+_PERFSO = os.path.join(_HERE, "_ref", "librefperfect.so")
+_perflib = None
+
+
+def refperfect_available() -> bool:
+    return os.path.exists(_PERFSO) or os.path.exists("/root/reference/perfect/src/Frame.cc")
+
+
+def perfect_frames(gray: np.ndarray, depth: np.ndarray, mask: np.ndarray, nfeatures=1000, scale=1.2, nlevels=8, ini_th=20,
+                   min_th=7, fx=535.4, fy=539.2, cx=320.1, cy=247.6, bf=40.0):
+    """The perfect tree's two RGB-D Frame constructors on one image pair: plain (perfect/src/Frame.cc:255) and masked
+    (:328).  -> ((kps, desc) the plain frame keeps, (kps, desc) the masked frame keeps); kps = cv::KeyPoint records (mvKeys)."""
+    global _perflib
+    from orb_slam2_ssd_semantic_b200.extractor import KP_DTYPE
+    if _perflib is None:
+        if not os.path.exists(_PERFSO):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "perfect"])
+        _perflib = C.CDLL(_PERFSO)
+        _perflib.refperfect_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                               C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    gray = np.ascontiguousarray(gray, np.uint8)
+    depth = np.ascontiguousarray(depth, np.float32)
+    mask = np.ascontiguousarray(mask, np.uint8)
+    assert gray.shape == depth.shape == mask.shape
+    cap = nfeatures + 3 * nlevels + 64
+    ka, kb = np.zeros(cap, KP_DTYPE), np.zeros(cap, KP_DTYPE)
+    da, db = np.zeros((cap, 32), np.uint8), np.zeros((cap, 32), np.uint8)
+    na, nb = C.c_int(0), C.c_int(0)
+    rc = _perflib.refperfect_frames(_p(gray), _p(depth), _p(mask), gray.shape[0], gray.shape[1], int(nfeatures), float(scale),
+                                    int(nlevels), int(ini_th), int(min_th), float(fx), float(fy), float(cx), float(cy), float(bf),
+                                    _p(ka), _p(da), C.byref(na), _p(kb), _p(db), C.byref(nb), cap)
+    if rc != 0:
+        raise RuntimeError("refperfect_frames: %d" % rc)
+    return (ka[:na.value].copy(), da[:na.value].copy()), (kb[:nb.value].copy(), db[:nb.value].copy())

@@ -14,6 +14,10 @@ class Converter {
     for (int j = 0; j < Descriptors.rows; j++) vDesc.push_back(Descriptors.row(j));
     return vDesc;
   }
+  // the perfect tree's map save / load (perfect/src/Map.cc:163,354) names two quaternion helpers; declared only -- Eigen is
+  // absent and the path never calls them (oracle/refperfect_harness.cpp defines aborting bodies for the link)
+  static std::vector<float> toQuaternion(const cv::Mat& M);
+  void RmatOfQuat(cv::Mat& M, const cv::Mat& q);
 };
 }  // namespace ORB_SLAM2
 #endif

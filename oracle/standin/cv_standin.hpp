@@ -406,6 +406,13 @@ inline double norm(const Mat& a, int normType = NORM_L2) {
   return normType == NORM_L2 ? std::sqrt(s) : s;
 }
 inline double norm(const Mat& a, const Mat& b, int normType = NORM_L2) { return norm(a - b, normType); }
+inline Scalar sum(const Mat& a) {   // cv::sum: per-channel sums (integer inputs: exact in double whatever OpenCV's blocking)
+  Scalar s;
+  const int cn = a.channels();
+  for (int i = 0; i < a.rows; ++i)
+    for (int j = 0; j < a.cols * cn; ++j) s.val[j % cn] += a.get_d(i, j);
+  return s;
+}
 inline double norm(const GemmExpr& g) { return norm(Mat(g)); }
 
 inline Mat Mat::inv() const {   // only used by out-of-path code; Gauss-Jordan in double

@@ -77,3 +77,31 @@ def test_filter_keypoints_rule():
     mask2[:31] = 1                                       # 31/48 = 64.6 %
     k3, d3 = O.filter_keypoints(mask2, kps, desc)
     assert len(k3) == 200 and (d3 == desc).all()
+
+
+def test_filter_oracle_equals_the_reference_masked_constructor():
+    """oracle == the `perfect` tree's OWN code: perfect/src/Frame.cc compiled unmodified (oracle/_ref/librefperfect.so).
+    filter_keypoints(mask, what the plain RGB-D constructor keeps) must be what the masked constructor keeps (:328-427),
+    bit for bit -- with a real dynamic mask (filter on), with a mask at 64.6 % (filter off, :358) and with stray values."""
+    from oracle import ref
+    if not ref.refperfect_available():
+        pytest.skip("neither oracle/_ref/librefperfect.so nor the reference is on this box")
+    from orb_slam2_ssd_semantic_b200 import synth
+    ws = synth.WallStream(seed=1234, n=2)
+    gray, depth, _, _ = ws.frame(1)
+    real = O.mask_from_flow(synth.flow_field(11, 240, 320), 40.0)
+    assert 0.65 < real.mean() < 0.9
+    off = np.zeros((480, 640), np.uint8)
+    off[:310] = 1                                          # 64.6 % ones: not above 65 %, nothing may be dropped
+    stray = np.ones((480, 640), np.uint8)
+    stray[:, 200:330] = 2                                  # "val == 1" only: a 2 is outside
+    stray[100:140] = 0
+    for name, mask in (("real", real), ("off", off), ("stray", stray)):
+        (kp, dp), (km, dmk) = ref.perfect_frames(gray, depth, mask)
+        assert len(kp) > 900
+        ko, do = O.filter_keypoints(mask, kp, dp)
+        assert len(ko) == len(km) and ko.tobytes() == km.tobytes() and (do == dmk).all(), name
+        if name == "off":
+            assert len(km) == len(kp)
+        else:
+            assert 0 < len(km) < len(kp)
