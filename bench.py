@@ -119,6 +119,18 @@ def shifted_poses(T: np.ndarray, room: int) -> np.ndarray:
     return out
 
 
+def rank_pieces(world: int, rank: int):
+    """Strong scaling: the contiguous range of the SUB * BATCH frames of a step that `rank` owns, cut at batch boundaries
+    -> [(batch, lo, hi)] with lo / hi relative to the batch (tests/test_distributed_cpu.py checks the partition)."""
+    g_lo, g_hi = shard_range(SUB * BATCH, world, rank)
+    pieces = []
+    for b in range(SUB):
+        lo, hi = max(g_lo, b * BATCH), min(g_hi, (b + 1) * BATCH)
+        if lo < hi:
+            pieces.append((b, lo - b * BATCH, hi - b * BATCH))
+    return pieces
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
@@ -298,12 +310,7 @@ def run_b200(args):
     nfeat = args.nfeatures
     # ---- shard of this rank: contiguous range of the SUB*BATCH frames of a step, as (batch, lo, hi) pieces; the frame
     # before `lo` is the halo (re-extracted locally for the match of frame lo), batch-initial frames have none
-    g_lo, g_hi = shard_range(SUB * BATCH, world, rank)
-    pieces = []
-    for b in range(SUB):
-        lo, hi = max(g_lo, b * BATCH), min(g_hi, (b + 1) * BATCH)
-        if lo < hi:
-            pieces.append((b, lo - b * BATCH, hi - b * BATCH))
+    pieces = rank_pieces(world, rank)
     f_lo = min(max(p[1] - 1, 0) for p in pieces)
     f_hi = max(p[2] for p in pieces)
     gray, depth, rgb, label, T = make_batch(f_lo, f_hi)          # only the frames this rank touches

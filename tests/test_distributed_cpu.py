@@ -105,3 +105,32 @@ def test_gloo_world2_allgather_and_sharding():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bench_strong_scaling_partition():
+    """bench.py's frame shards at 1 / 2 / 3 / 4 / 8 ranks: every frame of a step is owned by exactly one rank, pieces stay
+    inside their batch, a tracked piece (owned frames + the halo frame) never exceeds a batch, keyframes are partitioned."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    total = bench.SUB * bench.BATCH
+    for world in (1, 2, 3, 4, 8):
+        owner = np.full(total, -1)
+        nkf = 0
+        for rank in range(world):
+            pieces = bench.rank_pieces(world, rank)
+            assert pieces, (world, rank)
+            for (b, lo, hi) in pieces:
+                assert 0 <= lo < hi <= bench.BATCH
+                assert hi - max(lo - 1, 0) <= bench.BATCH
+                assert (owner[b * bench.BATCH + lo:b * bench.BATCH + hi] == -1).all()
+                owner[b * bench.BATCH + lo:b * bench.BATCH + hi] = rank
+                nkf += sum(1 for t in range(lo, hi) if t % bench.KF_EVERY == 0)
+            # contiguous global range
+            g = [b * bench.BATCH + lo for (b, lo, hi) in pieces] + [pieces[-1][0] * bench.BATCH + pieces[-1][2]]
+            assert all(x <= y for x, y in zip(g, g[1:]))
+        assert (owner >= 0).all() and (np.diff(owner) >= 0).all()
+        assert nkf == bench.SUB * len(range(0, bench.BATCH, bench.KF_EVERY))
