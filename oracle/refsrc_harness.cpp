@@ -10,6 +10,8 @@
 // Nothing here restates reference logic.  `#define private public` only opens the classes so that a Frame can be
 // filled from arrays instead of from an image (the class layout is unchanged; the reference's .cc files are compiled
 // without it).  OpenCV / DBoW2 are stand-ins (oracle/standin/), third-party arithmetic stated there.
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -73,15 +75,37 @@ const size_t kNodeBytes = sizeof(std::_List_node<ExtractorNode>);
 #endif
 const size_t kArenaBytes = 16u << 20;          // one per thread that extracts (a frame needs ~2 MB of list nodes)
 const int kMaxArenas = 512;
-char* g_arenas[kMaxArenas];
-std::atomic<int> g_narenas(0);
+// All arenas are slices of ONE reserved address range (mmap, MAP_NORESERVE: pages exist once touched), so operator delete
+// recognises an arena pointer with two compares however many threads extract -- the frame-parallel CPU baseline runs
+// nthreads extractors at once -- and a thread hands its slice back when it ends (the pipeline starts fresh threads per call).
+char* g_region = nullptr;
+std::once_flag g_region_once;
+std::mutex g_free_mu;
+std::vector<int> g_free;
+int g_next = 0;
+struct ArenaSlot {
+  int id = -1;
+  ~ArenaSlot() {
+    if (id >= 0) { std::lock_guard<std::mutex> lk(g_free_mu); g_free.push_back(id); }
+  }
+};
+thread_local ArenaSlot t_slot;
 thread_local char* t_arena = nullptr;
 thread_local size_t t_arena_used = 0;
 thread_local bool t_arena_on = false;
 inline void arena_reset() {
   if (!t_arena) {
-    const int id = g_narenas.fetch_add(1);
-    if (id < kMaxArenas) { t_arena = (char*)malloc(kArenaBytes); g_arenas[id] = t_arena; }
+    std::call_once(g_region_once, [] {
+      void* r = mmap(nullptr, (size_t)kMaxArenas * kArenaBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+      g_region = (r == MAP_FAILED) ? nullptr : (char*)r;
+    });
+    if (g_region) {
+      std::lock_guard<std::mutex> lk(g_free_mu);
+      int id = -1;
+      if (!g_free.empty()) { id = g_free.back(); g_free.pop_back(); }
+      else if (g_next < kMaxArenas) id = g_next++;
+      if (id >= 0) { t_slot.id = id; t_arena = g_region + (size_t)id * kArenaBytes; }
+    }
   }
   t_arena_used = 0;
   t_arena_on = t_arena != nullptr;
@@ -98,11 +122,8 @@ void* operator new(size_t n) {
   return p;
 }
 void operator delete(void* p) noexcept {
-  const int na = std::min(g_narenas.load(std::memory_order_relaxed), kMaxArenas);
-  for (int i = 0; i < na; ++i) {
-    const char* b = g_arenas[i];
-    if (b && (char*)p >= b && (char*)p < b + kArenaBytes) return;
-  }
+  const char* r = g_region;
+  if (r && (const char*)p >= r && (const char*)p < r + (size_t)kMaxArenas * kArenaBytes) return;
   free(p);
 }
 void operator delete(void* p, size_t) noexcept { operator delete(p); }
