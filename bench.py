@@ -483,7 +483,7 @@ def run_b200(args):
     run_host(1)
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(2, min(args.steps, 10))
+    e2e_steps = max(2, min(args.steps, 16))   # 16 steps x ~82 ms: the e2e timed region exceeds 1 s at the default --steps 20
     which, nlast = run_host(e2e_steps)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
