@@ -105,3 +105,20 @@ def test_filter_oracle_equals_the_reference_masked_constructor():
             assert len(km) == len(kp)
         else:
             assert 0 < len(km) < len(kp)
+
+
+@pytest.mark.parametrize("rows,cols,gray_shape,thr,seed", [(2, 2, (4, 4), 40.0, 1), (2, 9, (5, 19), 40.0, 2), (31, 17, (63, 34), 55.5, 3),
+                                                           (64, 48, (128, 97), 200.0, 4), (100, 3, (201, 7), 0.0, 5)])
+def test_mask_oracle_equals_cv2_live_shapes(rows, cols, gray_shape, thr, seed):
+    """Random shapes incl. 2-pixel-wide fields and odd-sized gray images, against cv2 run here (skipped without cv2)."""
+    cv2 = pytest.importorskip("cv2")
+    from orb_slam2_ssd_semantic_b200.synth import flow_field
+    flow = flow_field(100 + seed, rows, cols, blobs=3)
+    up = cv2.pyrUp(flow, dstsize=(2 * cols, 2 * rows))
+    assert (O.pyr_up(flow) == up).all()
+    m0 = np.ones(gray_shape, np.uint8)
+    t2 = up[..., 0] * up[..., 0] + up[..., 1] * up[..., 1]
+    m0[:2 * rows, :2 * cols] = (t2 < max(np.float32(thr), np.float32(40.0))).astype(np.uint8)
+    k = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (21, 21), (10, 10))
+    ref = cv2.dilate(cv2.erode(cv2.erode(m0, k), k), k)
+    assert (O.mask_from_flow(flow, thr, gray_shape) == ref).all()
