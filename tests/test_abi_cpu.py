@@ -108,6 +108,8 @@ def test_tuning_get_set_round_trip():
     assert L.b200orb_get_tuning(C.byref(m), C.byref(w), C.byref(q)) == 0
     saved = (m.value, w.value, q.value)
     assert w.value in (1, 2, 4, 8) and q.value in (2, 3, 4) and L.b200orb_experimental() == m.value
+    if not any(k in os.environ for k in ("B200ORB_EXPERIMENTAL", "B200ORB_FAST_WPC", "B200ORB_QT_MINB")):
+        assert saved == (3, 8, 4)          # the configuration the last B200 runs validated (profiles/r02_notes.md)
     try:
         assert L.b200orb_set_tuning(1, 2, 3) == 0
         L.b200orb_get_tuning(C.byref(m), C.byref(w), C.byref(q))
